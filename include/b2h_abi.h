@@ -1,0 +1,332 @@
+/*
+ * b2h_abi.h -- C ABI of libb2h.so: the B200 (sm_100a) implementation of the Body2Hands-style
+ * temporal pose regressor / discriminator GAN hot path.
+ *
+ * The reference (alvaro-budria/Multimodal-Hand-Pose-Enhancement-for-Sign-Language) has NO
+ * FFI / plugin layer: its hot path is `torch.nn` modules (modelZoo.py) driven by train_gan.py
+ * and inference.py.  This header is therefore the boundary a maintainer would bind with
+ * `ctypes`; every entry point cites the reference lines it replaces.
+ * File:line citations are relative to the reference repository root.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch types.  All pointers are DEVICE pointers
+ *     unless the name says `host`.  Nothing allocates, nothing synchronises the host, every
+ *     launch goes to the given stream -> every call is CUDA-graph capturable.
+ *   - Return value: 0 = OK, negative = b2h_status; `b2h_last_error()` gives the message.
+ *   - Activations inside the path are channels-last "BLC": [B][L][ld] with the channel dimension
+ *     padded to a multiple of 64 (zero filled), in the *activation dtype* of the precision mode
+ *     (B2H_F32 -> float, B2H_BF16 -> __nv_bfloat16).  Boundary tensors keep the reference layout
+ *     "NCL" = (B, C, T) fp32 contiguous (modelZoo.py forward signatures).
+ *   - A *program* is a recorded list of ops (built once per shape by the host-side mirror of
+ *     modelZoo) that `b2h_program_run` replays on a stream with one call.
+ */
+#ifndef B2H_ABI_H_
+#define B2H_ABI_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2H_ABI_VERSION 1
+
+typedef void* b2h_stream_t; /* cudaStream_t */
+
+enum b2h_status {
+  B2H_OK = 0,
+  B2H_ERR_SHAPE = -1,
+  B2H_ERR_ALIGN = -2,
+  B2H_ERR_ARCH = -3,
+  B2H_ERR_CUDA = -4,
+  B2H_ERR_ARG = -5
+};
+
+enum b2h_dtype { B2H_F32 = 0, B2H_BF16 = 1 };
+enum b2h_act { B2H_ACT_NONE = 0, B2H_ACT_LEAKY = 1 /* slope 0.2 */, B2H_ACT_RELU = 2 };
+enum b2h_rowmap {
+  B2H_ROW_IDENT = 0, /* src row (b, l)                                             */
+  B2H_ROW_UP2 = 1,   /* fwd: src row (b, l/2)  [repeat_interleave(2)[:L], modelZoo.py:295-296]
+                        bwd: dy(b, j) = g(b, 2j) + g(b, 2j+1)                      */
+  B2H_ROW_POOL2 = 2, /* fwd: max over src rows (b, 2l), (b, 2l+1) [MaxPool1d(2,2), modelZoo.py:197]
+                        bwd: dy(b, t) = g(b, t/2) if t is the (first) argmax       */
+  B2H_ROW_BCAST = 3  /* fwd: src row (b) for every l (eval-mode text rows are identical) */
+};
+enum b2h_prep_src {
+  B2H_SRC_NCL = 0,    /* fp32 (B, C, L): modelZoo input_ / loss gradients                     */
+  B2H_SRC_ROWS = 1,   /* fp32 (B*L, C) row major: image feats (B, T, 2000)                    */
+  B2H_SRC_BCAST = 2,  /* fp32 (B, C) repeated L times: text feats, process_text modelZoo.py:284-287 */
+  B2H_SRC_MOTION = 3  /* fp32 NCL (B, C, L+1): out[b,l,c] = x[b,c,0] - x[b,c,l]  (calc_motion, train_gan.py:209-211) */
+};
+enum b2h_dropout_mode { B2H_DROP_NONE = 0, B2H_DROP_MASK = 1, B2H_DROP_PHILOX = 2 };
+
+/* nn.Dropout(0.5) (modelZoo.py:193 and every block): y = x * keep * 2.
+ * MASK: explicit keep-mask (parity tests).  PHILOX: Philox4x32-10 keyed by (seed, step, site, element). */
+typedef struct {
+  int32_t mode;
+  int32_t site;
+  const uint8_t* mask;   /* MASK: [rows][C] keep flags, C = drop_C of the op */
+  const uint64_t* state; /* PHILOX: device {seed, step} */
+} b2h_dropout_t;
+
+/* ------------------------------------------------------------------------------------------- */
+/* tap-GEMM: every contraction of the path (Conv1d, its dgrad, ConvTranspose1d as a 2-phase     */
+/* sub-pixel conv, its dgrad as a strided conv, Linear) is                                       */
+/*   out[b, lo, n] = epi( sum_t sum_c A[b, lo*stride + tap_off[t], c] * W[n, t, c] )            */
+/* with zero rows outside [0, La).  Replaces nn.Conv1d / nn.ConvTranspose1d / nn.Linear call    */
+/* sites modelZoo.py:19-118,182-281,768-813 and their autograd backward.                         */
+/* ------------------------------------------------------------------------------------------- */
+#define B2H_MAX_TAPS 8
+typedef struct {
+  const void* A;     /* [B][La][lda], act dtype                                                */
+  const void* W;     /* packed [Npad][ntaps][Kc], act dtype (b2h_pack_weight)                  */
+  const float* bias; /* [Npad/nphase] packed fp32 (indexed by the channel within a phase) or NULL */
+  void* out;         /* [B][Lo_actual][ldo] (+ out_coff); act dtype, or fp32 if out_f32        */
+  int32_t B, La, Lo, lda, ldo, out_coff;
+  int32_t Kc;     /* channels per tap, multiple of 64 (zero padded)                            */
+  int32_t Npad;   /* multiple of 64                                                            */
+  int32_t Nvalid; /* columns >= Nvalid (per phase) are not written                            */
+  int32_t ntaps, stride;
+  int32_t tap_off[B2H_MAX_TAPS];
+  int32_t nphase;    /* 1, or 2: columns [p*Npad/2, (p+1)*Npad/2) are output row lo*2+p (sub-pixel) */
+  int32_t Lo_actual; /* rows per sample of the real output tensor (= Lo*nphase unless ragged)  */
+  int32_t act;       /* b2h_act, applied after bias                                            */
+  const float* post_scale; /* eval-mode BatchNorm folded to y = v*scale + shift after act, or NULL */
+  const float* post_shift;
+  int32_t out_f32;
+  b2h_dropout_t drop; /* dgrad: multiply by keep*2 of the dropout site that produced A_prev    */
+  int32_t drop_C;     /* valid channel count of that site (mask row length)                    */
+} b2h_gemm_t;
+
+/* wgrad: dW[m][n][t] = sum_{b,r} P[b, r, m] * Q[b, r*stride + tap_off[t], n]   (PyTorch weight layout)
+ * conv: P = dpre, Q = a (dW[n][c][k]);  convT: P = a, Q = dpre (dW[c][n][k]); Linear: ntaps = 1. */
+typedef struct {
+  const void* P; /* [B][Lp][ldp] act dtype */
+  const void* Q; /* [B][Lq][ldq] act dtype */
+  float* dW;     /* [Mvalid][Nvalid][ntaps] fp32 */
+  float* partial; /* workspace: >= b2h_wgrad_workspace_bytes() */
+  int32_t B, Lp, Lq, ldp, ldq;
+  int32_t Mpad, Npad, Mvalid, Nvalid; /* pads are multiples of 64 */
+  int32_t ntaps, stride;
+  int32_t tap_off[B2H_MAX_TAPS];
+  int32_t splits; /* 0 = let the library choose */
+} b2h_wgrad_t;
+
+/* ------------------------------------------------------------------------------------------- */
+/* BatchNorm1d pieces (modelZoo.py:196 etc.; block order conv -> LeakyReLU -> BN)    */
+/* ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* z;  /* post-activation, pre-BN tensor [rows][ld], act dtype */
+  int32_t ld, coff, rowmap, L_src;
+  const float* mean;    /* [groups][C] batch mean          (train)  */
+  const float* invstd;  /* [groups][C] 1/sqrt(var_b + eps) (train)  */
+  const float* running_mean; /* eval: y = (z - rm)/sqrt(rv + eps)*gamma + beta */
+  const float* running_var;
+  const float* gamma;
+  const float* beta;
+  float eps;
+  int32_t use_running;
+} b2h_bn_src_t;
+
+/* batch statistics of z over (rows of one group): mean, biased var -> invstd; running update
+ * running = (1-m)*running + m*batch (unbiased var), num_batches_tracked += 1. */
+typedef struct {
+  const void* z;
+  int32_t ld, C, rows_per_group, groups;
+  float* mean;   /* [groups][C] */
+  float* invstd; /* [groups][C] */
+  float* running_mean; /* may be NULL (no update); updated from group `running_group` */
+  float* running_var;
+  int64_t* num_batches_tracked;
+  float momentum, eps;
+  float* partial;        /* workspace [nchunks][groups][C][2] */
+  uint32_t* ticket;      /* workspace, zero-initialised, self-resetting */
+  int32_t update_all_groups; /* 1: apply the running update once per group in order (two D forwards) */
+} b2h_bn_stats_t;
+
+/* out[b,l,coff+c] = dropout( BN0(src0) [+ BN1(src1)] ), zero fill up to Cfill */
+typedef struct {
+  b2h_bn_src_t src[2];
+  int32_t nsrc;
+  void* out;
+  int32_t out_ld, out_coff;
+  int32_t B, L, C, Cfill, groups;
+  b2h_dropout_t drop;
+  int32_t drop_C, drop_coff;
+} b2h_bn_apply_t;
+
+typedef struct {
+  const void* g; /* gradient w.r.t. the consumer's pre-dropout input (mask already applied) */
+  int32_t ld, coff, rowmap, L_src, f32;
+} b2h_grad_src_t;
+
+/* BN + activation backward. dy = sum of grad sources;
+ *   dz = gamma*invstd*(dy - mean(dy) - zhat*mean(dy*zhat));  dpre = dz * act'(z)
+ * also dgamma = sum(dy*zhat), dbeta = sum(dy), dbias = sum(dpre). */
+typedef struct {
+  b2h_grad_src_t gsrc[2];
+  int32_t ngsrc;
+  b2h_bn_src_t bn; /* z, mean, invstd, gamma of THIS layer (rowmap IDENT) */
+  /* for POOL2 grad sources the pooled tensor was max over BN(z) pairs of this layer */
+  void* dpre;      /* [rows][ld_dpre] act dtype, zero filled up to Cfill */
+  int32_t ld_dpre, Cfill;
+  int32_t B, L, C, groups, act;
+  float* dgamma; /* [C] (summed over groups) */
+  float* dbeta;
+  float* dbias;
+  float* sums;    /* workspace [groups][C][2]  (sum dy, sum dy*zhat) */
+  float* partial; /* workspace [nchunks][groups][C][2] (shared by both passes) */
+  uint32_t* ticket;
+} b2h_bn_bwd_t;
+
+/* ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* src;
+  void* out; /* [B][L][ld] act dtype */
+  int32_t kind; /* b2h_prep_src */
+  int32_t B, L, C, ld, Cfill;
+  int32_t src_ld; /* ROWS/BCAST: row pitch of src in floats */
+  b2h_dropout_t drop;
+  int32_t out_f32;
+} b2h_prep_t;
+
+typedef struct {
+  const void* src; /* [B][L][ld] */
+  float* dst;      /* (B, C, L) fp32 */
+  int32_t B, L, C, ld, src_f32;
+} b2h_to_ncl_t;
+
+/* L1Loss(out, gt) forward + backward in one pass (utils/constants.py:55, train_gan.py:292):
+ *   loss[0] = mean|out - gt| ; dout = sign(out - gt) * gscale / numel written BLC act dtype. */
+typedef struct {
+  const float* out; /* NCL fp32 */
+  const float* gt;  /* NCL fp32 */
+  void* dout;       /* [B][L][ld] act dtype (may be NULL: forward only) */
+  float* loss;      /* loss[0] */
+  float* partial;
+  uint32_t* ticket;
+  int32_t B, C, L, ld, Cfill;
+  float gscale;
+} b2h_l1_t;
+
+/* nn.MSELoss(score, target) (train_gan.py:93,247,292) on (groups, n) scores, one target per group;
+ * loss[0] = sum_g mean((s_g - t_g)^2); dscore = 2*(s - t)/n (NULL: forward only);
+ * optionally total[0] = loss[0] + add[0]. */
+typedef struct {
+  const float* score;
+  float* dscore;
+  float* loss;
+  const float* add;
+  float* total;
+  int32_t groups, n;
+  float target[2];
+} b2h_mse_t;
+
+typedef struct {
+  const void* src; /* [rows][ld] act dtype */
+  float* out;      /* [C] */
+  float* partial;
+  uint32_t* ticket;
+  int32_t rows, ld, C, f32;
+} b2h_colsum_t;
+
+/* torch.optim.Adam(lr, betas=(0.9,0.999), eps=1e-8, weight_decay=0) (train_gan.py:69,88) over a
+ * flat buffer; step count lives on the device (graph replay); gscale folds the 1/world of DDP. */
+typedef struct {
+  float* p;
+  const float* g;
+  float* m;
+  float* v;
+  int64_t n;
+  double lr, beta1, beta2, eps; /* Python-float hyper-parameters, as torch.optim.Adam holds them */
+  float gscale;
+  int64_t* step; /* device; incremented by this op BEFORE use (t = ++step) */
+} b2h_adam_t;
+
+/* weight repack: out[(ph*Opad + o)][t][i] = W[o*o_stride + i*i_stride + tapmap[ph][t]*k_stride]
+ * (0 when tapmap < 0 or o >= O or i >= I); optional bias repack out_bias[o] = bias[o], o < Opad. */
+typedef struct {
+  const float* W;
+  void* out; /* act dtype */
+  int32_t O, I, Opad, Ipad, ntaps, nphase;
+  int32_t o_stride, i_stride, k_stride;
+  int32_t tapmap[2][B2H_MAX_TAPS];
+  const float* bias;
+  float* out_bias;
+} b2h_pack_t;
+
+/* eval-mode BN folded to scale/shift: scale = gamma/sqrt(rv+eps), shift = beta - rm*scale, padded */
+typedef struct {
+  const float *gamma, *beta, *running_mean, *running_var;
+  float* scale;
+  float* shift;
+  int32_t C, Cpad;
+  float eps;
+} b2h_bn_fold_t;
+
+/* 6D rotation -> 3x3 matrix, row-major 9 floats per joint (utils/conversion_utils.py:86-107) */
+typedef struct {
+  const float* r6d; /* [n][6] */
+  float* mat;       /* [n][9] */
+  int64_t n;
+} b2h_rot6d_t;
+
+typedef struct {
+  void* ptr;
+  int64_t bytes;
+  int32_t value; /* byte value */
+} b2h_fill_t;
+
+/* ------------------------------------------------------------------------------------------- */
+/* library                                                                                      */
+/* ------------------------------------------------------------------------------------------- */
+int b2h_abi_version(void);
+const char* b2h_last_error(void);
+/* 0 if a CUDA device of compute capability 10.x is current, else B2H_ERR_ARCH / B2H_ERR_CUDA */
+int b2h_check_device(void);
+int b2h_sm_count(void);
+
+/* one-shot launches (unit tests, eager use). `dtype` is the activation dtype (b2h_dtype). */
+int b2h_gemm(const b2h_gemm_t* d, int dtype, b2h_stream_t s);
+int b2h_wgrad(const b2h_wgrad_t* d, int dtype, b2h_stream_t s);
+int64_t b2h_wgrad_workspace_bytes(const b2h_wgrad_t* d, int dtype);
+int b2h_bn_stats(const b2h_bn_stats_t* d, int dtype, b2h_stream_t s);
+int64_t b2h_bn_partial_floats(int rows, int C, int groups); /* size of `partial` for stats / bwd */
+int b2h_bn_apply(const b2h_bn_apply_t* d, int dtype, b2h_stream_t s);
+int b2h_bn_bwd(const b2h_bn_bwd_t* d, int dtype, b2h_stream_t s);
+int b2h_prep(const b2h_prep_t* d, int dtype, b2h_stream_t s);
+int b2h_to_ncl(const b2h_to_ncl_t* d, int dtype, b2h_stream_t s);
+int b2h_l1(const b2h_l1_t* d, int dtype, b2h_stream_t s);
+int64_t b2h_l1_partial_floats(const b2h_l1_t* d);
+int b2h_mse(const b2h_mse_t* d, b2h_stream_t s);
+int b2h_colsum(const b2h_colsum_t* d, int dtype, b2h_stream_t s);
+int b2h_adam(const b2h_adam_t* d, b2h_stream_t s);
+int b2h_pack(const b2h_pack_t* d, int dtype, b2h_stream_t s);
+int b2h_bn_fold(const b2h_bn_fold_t* d, b2h_stream_t s);
+int b2h_rot6d_to_mat(const b2h_rot6d_t* d, b2h_stream_t s);
+int b2h_fill(const b2h_fill_t* d, b2h_stream_t s);
+
+/* recorded programs: the whole-graph entry points (generator forward / step, discriminator step)
+ * are programs built by the host-side mirror of modelZoo and replayed with ONE call. */
+typedef struct b2h_program b2h_program;
+enum b2h_op_kind {
+  B2H_OP_GEMM = 1, B2H_OP_WGRAD, B2H_OP_BN_STATS, B2H_OP_BN_APPLY, B2H_OP_BN_BWD, B2H_OP_PREP,
+  B2H_OP_TO_NCL, B2H_OP_L1, B2H_OP_MSE, B2H_OP_COLSUM, B2H_OP_ADAM, B2H_OP_PACK, B2H_OP_BN_FOLD,
+  B2H_OP_ROT6D, B2H_OP_FILL
+};
+b2h_program* b2h_program_create(int dtype);
+void b2h_program_destroy(b2h_program* p);
+/* appends a copy of the descriptor (`desc` points at the struct matching `kind`); returns the op
+ * index or a negative b2h_status */
+int b2h_program_add(b2h_program* p, int kind, const void* desc);
+int b2h_program_size(const b2h_program* p);
+/* replay ops [first, first+count) on the stream; count < 0 = to the end */
+int b2h_program_run(b2h_program* p, int first, int count, b2h_stream_t s);
+/* number of kernel launches the last run issued (bench.py's gpu_launches) */
+int64_t b2h_program_launches(const b2h_program* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2H_ABI_H_ */

@@ -1,0 +1,194 @@
+// Shared device/host helpers for libb2h (sm_100a).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/b2h_abi.h"
+
+namespace b2h {
+
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+int sm_count();
+extern thread_local int64_t g_launch_count;
+
+#define B2H_CHECK_ARG(cond, code, ...)   \
+  do {                                   \
+    if (!(cond)) {                       \
+      ::b2h::set_error(__VA_ARGS__);     \
+      return (code);                     \
+    }                                    \
+  } while (0)
+
+#define B2H_LAUNCH_CHECK(what)                                   \
+  do {                                                           \
+    ::b2h::g_launch_count++;                                     \
+    cudaError_t e__ = cudaGetLastError();                        \
+    if (e__ != cudaSuccess) return ::b2h::cuda_fail(e__, what);  \
+  } while (0)
+
+constexpr float kLeakySlope = 0.2f;  // nn.LeakyReLU(0.2, True), modelZoo.py:195
+
+// ---------------------------------------------------------------------------------------------
+// 4-wide vector access in the activation dtype
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ float4 load4(const T* p);
+template <>
+__device__ __forceinline__ float4 load4<float>(const float* p) {
+  return *reinterpret_cast<const float4*>(p);
+}
+template <>
+__device__ __forceinline__ float4 load4<__nv_bfloat16>(const __nv_bfloat16* p) {
+  uint2 u = *reinterpret_cast<const uint2*>(p);
+  __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&u.x);
+  __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&u.y);
+  float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+  return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+template <typename T>
+__device__ __forceinline__ void store4(T* p, float4 v);
+template <>
+__device__ __forceinline__ void store4<float>(float* p, float4 v) {
+  *reinterpret_cast<float4*>(p) = v;
+}
+template <>
+__device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, float4 v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y);
+  __nv_bfloat162 b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&a);
+  u.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+template <typename T>
+__device__ __forceinline__ float to_f(T v);
+template <>
+__device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T>
+__device__ __forceinline__ T from_f(float v);
+template <>
+__device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float& f4(float4& v, int i) { return (&v.x)[i]; }
+__device__ __forceinline__ float f4c(const float4& v, int i) { return (&v.x)[i]; }
+
+// ---------------------------------------------------------------------------------------------
+// Dropout: explicit keep-mask or Philox4x32-10 keyed by (seed, step, site, element index)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr;
+}
+
+struct DropCtx {
+  int mode;
+  uint32_t site;
+  const uint8_t* mask;
+  uint2 key;      // seed
+  uint32_t step;  // low 32 bits of the step counter
+  __device__ __forceinline__ void init(const b2h_dropout_t& d) {
+    mode = d.mode;
+    site = (uint32_t)d.site;
+    mask = d.mask;
+    key = make_uint2(0u, 0u);
+    step = 0u;
+    if (mode == B2H_DROP_PHILOX) {
+      uint64_t seed = d.state[0], st = d.state[1];
+      key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+      step = (uint32_t)st;
+    }
+  }
+  // dropout multiplier (0 or 2) of element `idx` of the site's tensor
+  __device__ __forceinline__ float scale1(uint64_t idx) const {
+    if (mode == B2H_DROP_NONE) return 1.f;
+    if (mode == B2H_DROP_MASK) return mask[idx] ? 2.f : 0.f;
+    uint64_t c = idx >> 2;
+    uint4 r = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), site, step), key);
+    uint32_t w = (idx & 3) == 0 ? r.x : (idx & 3) == 1 ? r.y : (idx & 3) == 2 ? r.z : r.w;
+    return (w & 0x80000000u) ? 2.f : 0.f;
+  }
+  // multipliers of elements idx .. idx+3
+  __device__ __forceinline__ float4 scale4(uint64_t idx) const {
+    if (mode == B2H_DROP_NONE) return make_float4(1.f, 1.f, 1.f, 1.f);
+    if (mode == B2H_DROP_PHILOX && (idx & 3) == 0) {
+      uint64_t c = idx >> 2;
+      uint4 r = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), site, step), key);
+      return make_float4((r.x >> 31) ? 2.f : 0.f, (r.y >> 31) ? 2.f : 0.f, (r.z >> 31) ? 2.f : 0.f,
+                         (r.w >> 31) ? 2.f : 0.f);
+    }
+    return make_float4(scale1(idx), scale1(idx + 1), scale1(idx + 2), scale1(idx + 3));
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// "last block done" ticket: the last CTA of a grid performs the ordered final reduction
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool last_block_done(uint32_t* ticket, uint32_t nblocks) {
+  __shared__ int s_is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0 && threadIdx.y == 0) {
+    uint32_t t = atomicAdd(ticket, 1u);
+    s_is_last = (t == nblocks - 1u);
+    if (s_is_last) *ticket = 0u;  // self reset for the next launch / graph replay
+  }
+  __syncthreads();
+  if (s_is_last) __threadfence();
+  return s_is_last != 0;
+}
+
+__device__ __forceinline__ float act_fwd(float v, int act) {
+  if (act == B2H_ACT_LEAKY) return v > 0.f ? v : v * kLeakySlope;
+  if (act == B2H_ACT_RELU) return v > 0.f ? v : 0.f;
+  return v;
+}
+// derivative expressed on the OUTPUT of the in-place activation (sign(out) == sign(pre))
+__device__ __forceinline__ float act_bwd(float out, int act) {
+  if (act == B2H_ACT_LEAKY) return out > 0.f ? 1.f : kLeakySlope;
+  if (act == B2H_ACT_RELU) return out > 0.f ? 1.f : 0.f;
+  return 1.f;
+}
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// launchers implemented in the .cu files
+int launch_gemm_f32(const b2h_gemm_t& d, cudaStream_t s);
+int launch_wgrad_f32(const b2h_wgrad_t& d, cudaStream_t s);
+int launch_gemm_bf16(const b2h_gemm_t& d, void* cache, cudaStream_t s);
+int launch_wgrad_bf16(const b2h_wgrad_t& d, void* cache, cudaStream_t s);
+int wgrad_choose_splits(const b2h_wgrad_t& d, int dtype);
+int launch_wgrad_reduce(const b2h_wgrad_t& d, int splits, cudaStream_t s);
+
+int launch_bn_stats(const b2h_bn_stats_t& d, int dtype, cudaStream_t s);
+int launch_bn_apply(const b2h_bn_apply_t& d, int dtype, cudaStream_t s);
+int launch_bn_bwd(const b2h_bn_bwd_t& d, int dtype, cudaStream_t s);
+int launch_prep(const b2h_prep_t& d, int dtype, cudaStream_t s);
+int launch_to_ncl(const b2h_to_ncl_t& d, int dtype, cudaStream_t s);
+int launch_l1(const b2h_l1_t& d, int dtype, cudaStream_t s);
+int launch_mse(const b2h_mse_t& d, cudaStream_t s);
+int launch_colsum(const b2h_colsum_t& d, int dtype, cudaStream_t s);
+int launch_adam(const b2h_adam_t& d, cudaStream_t s);
+int launch_pack(const b2h_pack_t& d, int dtype, cudaStream_t s);
+int launch_bn_fold(const b2h_bn_fold_t& d, cudaStream_t s);
+int launch_rot6d(const b2h_rot6d_t& d, cudaStream_t s);
+int launch_fill(const b2h_fill_t& d, cudaStream_t s);
+
+constexpr int kBnChunkRows = 64;  // rows per CTA of the BN / colsum reductions
+inline int bn_nchunks(int rows_per_group) { return ceil_div(rows_per_group, kBnChunkRows); }
+
+}  // namespace b2h

@@ -1,0 +1,523 @@
+// bf16 precision mode of the tap-GEMM family on the Blackwell tensor cores (sm_100a):
+//   * operands staged by TMA (cp.async.bulk.tensor) into 128B-swizzled shared memory; the temporal
+//     taps of the convolution are row-shifted 3-D boxes (C, L, B) whose out-of-bounds rows are
+//     zero filled by the TMA unit == the conv zero padding, per sample, with no im2col;
+//   * tcgen05.mma (kind::f16, BF16 x BF16 -> FP32) issued by one thread, accumulators in TMEM;
+//   * warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer / TMEM owner, warps 2-5 =
+//     epilogue (tcgen05.ld -> bias / activation / eval-BN / dropout -> global);
+//   * wgrad contracts over the row dimension, i.e. both operands are MN-major in shared memory:
+//     the same TMA boxes, described to the MMA with MN-major descriptors (no transposes).
+#include "gemm_epilogue.cuh"
+#include "ptx_sm100.cuh"
+#include "tc_plans.h"
+
+namespace b2h {
+
+using namespace ptx;
+
+// ---------------------------------------------------------------------------------------------
+// device: fprop-like kernel
+// ---------------------------------------------------------------------------------------------
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;                       // bf16 elements = 128 bytes = one swizzle row
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;   // 16 KB
+
+template <int BN>
+struct FpropCfg {
+  static constexpr int B_BYTES = BN * TC_BK * 2;
+  static constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+               const __grid_constant__ CUtensorMap tmB, TcGemmParams p, EpiParams e) {
+  using Cfg = FpropCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mt = blockIdx.x, nt = blockIdx.y;
+  const int bt = mt / p.n_lchunks, lc = mt - bt * p.n_lchunks;
+  const int b0 = bt * p.tb, l0 = lc * p.tl;
+  const int n0 = nt * BN;
+  const int kpt = p.Kc / TC_BK;
+  const int nkb = p.ntaps * kpt;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA0);
+    prefetch_tmap(&tmA1);
+    prefetch_tmap(&tmB);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int stage = kb % STAGES;
+        const uint32_t phase = (kb / STAGES) & 1;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+        const int t = kb / kpt, kc = kb - t * kpt;
+        uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
+        uint8_t* sB = sA + TC_A_BYTES;
+        tma_load_3d(sA, p.tap_map[t] ? &tmA1 : &tmA0, &full_bar[stage], kc * TC_BK, l0 + p.tap_coord[t], b0);
+        tma_load_2d(sB, &tmB, &full_bar[stage], p.tap_w[t] * p.Kc + kc * TC_BK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = idesc_bf16(TC_BM, BN, 0, 0);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int stage = kb % STAGES;
+        const uint32_t phase = (kb / STAGES) & 1;
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sA = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+        const uint32_t sB = sA + TC_A_BYTES;
+        const uint64_t adesc = smem_desc_sw128(sA, 16, 1024);
+        const uint64_t bdesc = smem_desc_sw128(sB, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < TC_BK / 16; ++k) {
+          // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in the >>4 address field
+          umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+        }
+        umma_commit(&empty_bar[stage]);
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else {
+    // epilogue warps 2..5 -> TMEM sub-partitions (warp % 4)
+    const int sub = warp & 3;
+    const int r = sub * 32 + lane;  // tile row == TMEM lane
+    const int bi = r / p.tl, li = r - bi * p.tl;
+    const int b = b0 + bi, lo = l0 + li;
+    const bool row_ok = (b < p.B) && (lo < p.Lo);
+    DropCtx drop;
+    drop.init(e.drop);
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)c, v);
+      tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8)
+          epilogue_store<__nv_bfloat16, 8>(e, drop, b, lo, n0 + c + j, reinterpret_cast<const float*>(v) + j);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BN);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// device: wgrad kernel.  D[m][n] = sum_rows P[row][m] * Q[shift_t(row)][n]; both operands MN-major.
+// ---------------------------------------------------------------------------------------------
+constexpr int WG_BM = 128;
+constexpr int WG_BK = 64;  // rows per k-block
+constexpr int WG_SLAB = WG_BK * 128;  // one (64 rows x 64 channels) box = 8 KB
+
+template <int WN>
+struct WgradCfg {
+  static constexpr int A_BYTES = (WG_BM / 64) * WG_SLAB;  // 16 KB
+  static constexpr int B_BYTES = (WN / 64) * WG_SLAB;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (WN == 256) ? 4 : (WN == 128 ? 6 : 8);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+template <int WN>
+__global__ void __launch_bounds__(192, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmQ0,
+                const __grid_constant__ CUtensorMap tmQ1, TcWgradParams p, float* __restrict__ partial) {
+  using Cfg = WgradCfg<WN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = p.Npad / WN;
+  const int m0 = (blockIdx.x / n_tiles) * WG_BM, n0 = (blockIdx.x % n_tiles) * WN;
+  const int t = blockIdx.y, split = blockIdx.z;
+  const int kb_begin = split * p.kb_per_split;
+  const int kb_end = min(kb_begin + p.kb_per_split, p.total_kb);
+  const int nkb = kb_end - kb_begin;  // >= 1 by construction
+  // Mpad may be 64 (discriminator layers): only the slabs that exist are loaded; the accumulator rows
+  // of the missing slab hold garbage that is never stored (rows of D are independent)
+  const int a_slabs = min(WG_BM / 64, (p.Mpad - m0) / 64);
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmP);
+    prefetch_tmap(&tmQ0);
+    prefetch_tmap(&tmQ1);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, WN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const CUtensorMap* tq = p.tap_map[t] ? &tmQ1 : &tmQ0;
+      for (int i = 0; i < nkb; ++i) {
+        const int stage = i % STAGES;
+        const uint32_t phase = (i / STAGES) & 1;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full_bar[stage], a_slabs * WG_SLAB + Cfg::B_BYTES);
+        const int kb = kb_begin + i;
+        const int bt = kb / p.n_lchunks, lc = kb - bt * p.n_lchunks;
+        const int b0 = bt * p.tb, r0 = lc * p.tl;
+        uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
+        uint8_t* sB = sA + Cfg::A_BYTES;
+#pragma unroll
+        for (int j = 0; j < WG_BM / 64; ++j)
+          if (j < a_slabs) tma_load_3d(sA + j * WG_SLAB, &tmP, &full_bar[stage], m0 + j * 64, r0, b0);
+#pragma unroll
+        for (int j = 0; j < WN / 64; ++j)
+          tma_load_3d(sB + j * WG_SLAB, tq, &full_bar[stage], n0 + j * 64, r0 + p.tap_coord[t], b0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = idesc_bf16(WG_BM, WN, 1, 1);
+      for (int i = 0; i < nkb; ++i) {
+        const int stage = i % STAGES;
+        const uint32_t phase = (i / STAGES) & 1;
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sA = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+        const uint32_t sB = sA + Cfg::A_BYTES;
+        // MN-major, 128B swizzle: LBO = stride between 64-channel slabs, SBO = stride between 8-row groups
+        const uint64_t adesc = smem_desc_sw128(sA, WG_SLAB, 1024);
+        const uint64_t bdesc = smem_desc_sw128(sB, WG_SLAB, 1024);
+#pragma unroll
+        for (int k = 0; k < WG_BK / 16; ++k) {
+          // advance 16 rows (K) = 2 swizzle atoms of 1024 bytes: +128 in the >>4 address field
+          umma_bf16(tmem_base, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), idesc, (i | k) != 0);
+        }
+        umma_commit(&empty_bar[stage]);
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else {
+    const int sub = warp & 3;
+    const int m = m0 + sub * 32 + lane;
+    float* dst = partial + (((int64_t)split * p.ntaps + t) * p.Mpad + m) * p.Npad + n0;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < WN; c += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)c, v);
+      tmem_ld_wait();
+      const float* f = reinterpret_cast<const float*>(v);
+      if (m < p.Mpad) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(dst + c + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, WN);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host: tensor maps and launch plans
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// bf16 tensor map over a (C, L, B) view: element (c, l, b) at base + (b*sample_pitch + l*row_pitch + c)*2 bytes
+static int make_map_3d(CUtensorMap* m, const void* base, int64_t C, int64_t L, int64_t B, int64_t row_pitch,
+                       int64_t sample_pitch, int box_c, int box_l, int box_b) {
+  EncodeTiledFn fn = get_encode_fn();
+  B2H_CHECK_ARG(fn != nullptr, B2H_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)L, (cuuint64_t)B};
+  cuuint64_t strides[2] = {(cuuint64_t)row_pitch * 2, (cuuint64_t)sample_pitch * 2};
+  cuuint32_t box[3] = {(cuuint32_t)box_c, (cuuint32_t)box_l, (cuuint32_t)box_b};
+  cuuint32_t estr[3] = {1, 1, 1};
+  B2H_CHECK_ARG(((uintptr_t)base % 16) == 0 && strides[0] % 16 == 0 && strides[1] % 16 == 0, B2H_ERR_ALIGN,
+                "tensor map: base/strides must be 16-byte aligned");
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B2H_CHECK_ARG(r == CUDA_SUCCESS, B2H_ERR_CUDA, "cuTensorMapEncodeTiled(3d) failed: %d (C=%lld L=%lld B=%lld)", (int)r,
+                (long long)C, (long long)L, (long long)B);
+  return B2H_OK;
+}
+
+static int make_map_2d(CUtensorMap* m, const void* base, int64_t K, int64_t N, int64_t row_pitch, int box_k, int box_n) {
+  EncodeTiledFn fn = get_encode_fn();
+  B2H_CHECK_ARG(fn != nullptr, B2H_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
+  cuuint64_t strides[1] = {(cuuint64_t)row_pitch * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_k, (cuuint32_t)box_n};
+  cuuint32_t estr[2] = {1, 1};
+  B2H_CHECK_ARG(((uintptr_t)base % 16) == 0 && strides[0] % 16 == 0, B2H_ERR_ALIGN, "tensor map: alignment");
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B2H_CHECK_ARG(r == CUDA_SUCCESS, B2H_ERR_CUDA, "cuTensorMapEncodeTiled(2d) failed: %d", (int)r);
+  return B2H_OK;
+}
+
+// rows-per-sample chunk (power of two <= cap) that wastes the fewest padded rows; ties -> larger
+static int choose_tl(int L, int cap) {
+  int best = 1;
+  int64_t best_pad = (int64_t)L;
+  for (int tl = 1; tl <= cap; tl <<= 1) {
+    int64_t pad = (int64_t)ceil_div(L, tl) * tl;
+    if (pad <= best_pad) {
+      best_pad = pad;
+      best = tl;
+    }
+  }
+  return best;
+}
+
+// (map index, coordinate offset) of the strided row  lo*stride + off  in the even/odd row views
+static void tap_view(int stride, int off, int* map, int* coord) {
+  if (stride == 1) {
+    *map = 0;
+    *coord = off;
+  } else {
+    int par = ((off % 2) + 2) % 2;
+    *map = par;
+    *coord = (off - par) / 2;
+  }
+}
+
+// strided views of a [B][L][ld] tensor: view 0 = rows 0,2,4.. (or all rows if stride 1), view 1 = rows 1,3,5..
+static int make_row_views(CUtensorMap* m0, CUtensorMap* m1, bool* has1, const void* base, int C, int L, int B, int ld,
+                          int stride, int box_l, int box_b) {
+  const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(base);
+  int rc;
+  if (stride == 1) {
+    rc = make_map_3d(m0, p, C, L, B, ld, (int64_t)L * ld, 64, box_l, box_b);
+    if (rc) return rc;
+    *m1 = *m0;
+    *has1 = false;
+    return B2H_OK;
+  }
+  int Le = (L + 1) / 2, Lod = L / 2;
+  rc = make_map_3d(m0, p, C, Le, B, 2 * (int64_t)ld, (int64_t)L * ld, 64, box_l, box_b);
+  if (rc) return rc;
+  if (Lod > 0) {
+    rc = make_map_3d(m1, p + ld, C, Lod, B, 2 * (int64_t)ld, (int64_t)L * ld, 64, box_l, box_b);
+    if (rc) return rc;
+    *has1 = true;
+  } else {
+    *m1 = *m0;
+    *has1 = false;
+  }
+  return B2H_OK;
+}
+
+int plan_gemm_bf16(const b2h_gemm_t& d, TcGemmPlan* plan) {
+  TcGemmParams& p = plan->p;
+  p.B = d.B;
+  p.Lo = d.Lo;
+  p.Kc = d.Kc;
+  p.stride = d.stride;
+  p.tl = choose_tl(d.Lo, TC_BM);
+  p.tb = TC_BM / p.tl;
+  p.n_lchunks = ceil_div(d.Lo, p.tl);
+  const int m_tiles = ceil_div(d.B, p.tb) * p.n_lchunks;
+  bool has1 = false;
+  int rc = make_row_views(&plan->tmA0, &plan->tmA1, &has1, d.A, d.Kc, d.La, d.B, d.lda, d.stride, p.tl, p.tb);
+  if (rc) return rc;
+  // taps that only ever read the (empty) odd view contribute nothing: drop them
+  p.ntaps = 0;
+  for (int t = 0; t < d.ntaps; ++t) {
+    int map, coord;
+    tap_view(d.stride, d.tap_off[t], &map, &coord);
+    if (map == 1 && !has1) continue;
+    p.tap_map[p.ntaps] = map;
+    p.tap_coord[p.ntaps] = coord;
+    p.tap_w[p.ntaps] = t;
+    p.ntaps++;
+  }
+  B2H_CHECK_ARG(p.ntaps >= 1, B2H_ERR_SHAPE, "gemm_bf16: no tap reads inside the input (La=%d)", d.La);
+  // tile width: the largest BN (dividing one phase) that minimises the estimated wave time
+  const int half = d.Npad / d.nphase;
+  const int nkb = p.ntaps * (d.Kc / TC_BK);
+  int best_bn = 64;
+  double best_t = 1e30;
+  const int sms = sm_count();
+  for (int bn = 64; bn <= 256; bn <<= 1) {
+    if (half % bn) continue;
+    int64_t tiles = (int64_t)m_tiles * (d.Npad / bn);
+    double waves = (double)((tiles + sms - 1) / sms);
+    double t = waves * (3000.0 + (double)nkb * 2.0 * bn + 12.0 * bn);
+    if (t < best_t * 0.999) {
+      best_t = t;
+      best_bn = bn;
+    }
+  }
+  plan->BN = best_bn;
+  plan->grid_x = m_tiles;
+  plan->grid_y = d.Npad / best_bn;
+  rc = make_map_2d(&plan->tmB, d.W, (int64_t)d.ntaps * d.Kc, d.Npad, (int64_t)d.ntaps * d.Kc, 64, best_bn);
+  return rc;
+}
+
+template <int BN>
+static int launch_fprop(const TcGemmPlan& plan, const EpiParams& e, cudaStream_t s) {
+  using Cfg = FpropCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t er = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (er != cudaSuccess) return cuda_fail(er, "gemm_tc smem attribute");
+    attr_set = true;
+  }
+  dim3 grid(plan.grid_x, plan.grid_y);
+  gemm_tc_kernel<BN><<<grid, 192, Cfg::SMEM_BYTES, s>>>(plan.tmA0, plan.tmA1, plan.tmB, plan.p, e);
+  B2H_LAUNCH_CHECK("gemm_tc");
+  return B2H_OK;
+}
+
+int run_gemm_bf16(const TcGemmPlan& plan, const b2h_gemm_t& d, cudaStream_t s) {
+  EpiParams e = make_epi(d);
+  switch (plan.BN) {
+    case 256: return launch_fprop<256>(plan, e, s);
+    case 128: return launch_fprop<128>(plan, e, s);
+    default: return launch_fprop<64>(plan, e, s);
+  }
+}
+
+int plan_wgrad_bf16(const b2h_wgrad_t& d, TcWgradPlan* plan) {
+  TcWgradParams& p = plan->p;
+  p.Mpad = d.Mpad;
+  p.Npad = d.Npad;
+  p.ntaps = d.ntaps;
+  p.tl = choose_tl(d.Lp, WG_BK);
+  p.tb = WG_BK / p.tl;
+  p.n_lchunks = ceil_div(d.Lp, p.tl);
+  p.total_kb = ceil_div(d.B, p.tb) * p.n_lchunks;
+  int rc = make_map_3d(&plan->tmP, d.P, d.Mpad, d.Lp, d.B, d.ldp, (int64_t)d.Lp * d.ldp, 64, p.tl, p.tb);
+  if (rc) return rc;
+  bool has1 = false;
+  rc = make_row_views(&plan->tmQ0, &plan->tmQ1, &has1, d.Q, d.Npad, d.Lq, d.B, d.ldq, d.stride, p.tl, p.tb);
+  if (rc) return rc;
+  for (int t = 0; t < d.ntaps; ++t) {
+    tap_view(d.stride, d.tap_off[t], &p.tap_map[t], &p.tap_coord[t]);
+    B2H_CHECK_ARG(!(p.tap_map[t] == 1 && !has1), B2H_ERR_SHAPE, "wgrad_bf16: tap reads only rows outside Q");
+  }
+  int wn = 64;
+  if (d.Npad % 256 == 0)
+    wn = 256;
+  else if (d.Npad % 128 == 0)
+    wn = 128;
+  // prefer more tiles over wider tiles when the grid would not fill the machine
+  const int sms = sm_count();
+  while (wn > 64 && (int64_t)ceil_div(d.Mpad, WG_BM) * (d.Npad / wn) * d.ntaps * std::max(1, p.total_kb / 8) < sms) wn >>= 1;
+  plan->WN = wn;
+  int64_t tiles = (int64_t)ceil_div(d.Mpad, WG_BM) * (d.Npad / wn) * d.ntaps;
+  int splits = d.splits > 0 ? d.splits : (int)std::max<int64_t>(1, (sms + tiles - 1) / tiles);
+  if (splits > p.total_kb) splits = p.total_kb;
+  if (splits > 64) splits = 64;
+  p.kb_per_split = ceil_div(p.total_kb, splits);
+  plan->splits = ceil_div(p.total_kb, p.kb_per_split);
+  plan->grid_x = ceil_div(d.Mpad, WG_BM) * (d.Npad / wn);
+  return B2H_OK;
+}
+
+template <int WN>
+static int launch_wg(const TcWgradPlan& plan, float* partial, cudaStream_t s) {
+  using Cfg = WgradCfg<WN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t er = cudaFuncSetAttribute(wgrad_tc_kernel<WN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (er != cudaSuccess) return cuda_fail(er, "wgrad_tc smem attribute");
+    attr_set = true;
+  }
+  dim3 grid(plan.grid_x, plan.p.ntaps, plan.splits);
+  wgrad_tc_kernel<WN><<<grid, 192, Cfg::SMEM_BYTES, s>>>(plan.tmP, plan.tmQ0, plan.tmQ1, plan.p, partial);
+  B2H_LAUNCH_CHECK("wgrad_tc");
+  return B2H_OK;
+}
+
+int run_wgrad_bf16(const TcWgradPlan& plan, const b2h_wgrad_t& d, cudaStream_t s) {
+  int rc;
+  switch (plan.WN) {
+    case 256: rc = launch_wg<256>(plan, d.partial, s); break;
+    case 128: rc = launch_wg<128>(plan, d.partial, s); break;
+    default: rc = launch_wg<64>(plan, d.partial, s); break;
+  }
+  if (rc) return rc;
+  return launch_wgrad_reduce(d, plan.splits, s);
+}
+
+int64_t wgrad_bf16_workspace_bytes(const b2h_wgrad_t& d) {
+  // upper bound independent of the plan: splits <= 64 but never more than total k-blocks
+  int tl = choose_tl(d.Lp, WG_BK);
+  int total_kb = ceil_div(d.B, WG_BK / tl) * ceil_div(d.Lp, tl);
+  int sms = sm_count();
+  int64_t tiles_min = (int64_t)ceil_div(d.Mpad, WG_BM) * std::max(1, d.Npad / 256) * d.ntaps;
+  int64_t splits = d.splits > 0 ? d.splits : std::max<int64_t>(1, (sms + tiles_min - 1) / tiles_min);
+  splits = std::min<int64_t>(std::min<int64_t>(splits, total_kb), 64);
+  return (splits + 1) * (int64_t)d.ntaps * d.Mpad * d.Npad * (int64_t)sizeof(float);
+}
+
+}  // namespace b2h

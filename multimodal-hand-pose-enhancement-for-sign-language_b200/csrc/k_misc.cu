@@ -1,0 +1,393 @@
+// Boundary layout changes (NCL fp32 <-> BLC act dtype), calc_motion, losses, fused Adam, weight
+// repacking and 6D->rotation-matrix.  All HBM/L2-bound: coalesced on both sides via 32x32 smem
+// tile transposes, float4 access where the layout allows, warp-shuffle + ordered final reductions.
+#include "b2h_common.cuh"
+
+namespace b2h {
+
+// ---------------------------------------------------------------------------------------------
+// prep: fp32 source (NCL / rows / broadcast rows / calc_motion of NCL) -> dropout -> BLC act dtype
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) prep_ncl_kernel(b2h_prep_t d) {
+  // tile: 32 channels x 32 time steps of sample blockIdx.z
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, l0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  const bool motion = d.kind == B2H_SRC_MOTION;
+  const int Ls = motion ? d.L + 1 : d.L;  // source time length
+  const float* src = d.src + (int64_t)b * d.C * Ls;
+  for (int j = ty; j < 32; j += 8) {
+    int c = c0 + j, l = l0 + tx;
+    float v = 0.f;
+    if (c < d.C && l < d.L) {
+      v = src[(int64_t)c * Ls + l];
+      if (motion) v = src[(int64_t)c * Ls] - v;  // x[:, :, :1] - x[:, :, :-1]  (train_gan.py:210)
+    }
+    tile[j][tx] = v;
+  }
+  __syncthreads();
+  DropCtx drop;
+  drop.init(d.drop);
+  for (int j = ty; j < 32; j += 8) {
+    int l = l0 + j, c = c0 + tx;
+    if (l < d.L && c < d.Cfill) {
+      float v = 0.f;
+      if (c < d.C) {
+        int64_t row = (int64_t)b * d.L + l;
+        v = tile[tx][j] * drop.scale1((uint64_t)row * d.C + c);
+      }
+      int64_t o = ((int64_t)b * d.L + l) * d.ld + c;
+      if (d.out_f32)
+        reinterpret_cast<float*>(d.out)[o] = v;
+      else
+        reinterpret_cast<T*>(d.out)[o] = from_f<T>(v);
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) prep_rows_kernel(b2h_prep_t d) {
+  // one thread per 4 channels; rows = B*L
+  const int64_t rows = (int64_t)d.B * d.L;
+  const int nq = d.Cfill / 4;
+  DropCtx drop;
+  drop.init(d.drop);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows * nq;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t row = i / nq;
+    int c0 = (int)(i - row * nq) * 4;
+    int64_t srow = d.kind == B2H_SRC_BCAST ? row / d.L : row;
+    const float* sp = d.src + srow * d.src_ld + c0;
+    float4 v = make_float4(0, 0, 0, 0);
+    if (c0 + 3 < d.C && (d.src_ld % 4 == 0)) {
+      v = *reinterpret_cast<const float4*>(sp);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (c0 + k < d.C) f4(v, k) = sp[k];
+    }
+    if (drop.mode != B2H_DROP_NONE && c0 < d.C) {
+      uint64_t idx = (uint64_t)row * d.C + c0;
+      if (c0 + 3 < d.C) {
+        float4 m = drop.scale4(idx);
+        v.x *= m.x, v.y *= m.y, v.z *= m.z, v.w *= m.w;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (c0 + k < d.C) f4(v, k) *= drop.scale1(idx + k);
+      }
+    }
+    if (d.out_f32)
+      store4<float>(reinterpret_cast<float*>(d.out) + row * d.ld + c0, v);
+    else
+      store4<T>(reinterpret_cast<T*>(d.out) + row * d.ld + c0, v);
+  }
+}
+
+int launch_prep(const b2h_prep_t& d, int dtype, cudaStream_t s) {
+  B2H_CHECK_ARG(d.B > 0 && d.L > 0 && d.C > 0 && d.Cfill >= d.C && d.ld >= d.Cfill, B2H_ERR_SHAPE,
+                "prep: bad shape B=%d L=%d C=%d Cfill=%d ld=%d", d.B, d.L, d.C, d.Cfill, d.ld);
+  if (d.kind == B2H_SRC_NCL || d.kind == B2H_SRC_MOTION) {
+    B2H_CHECK_ARG(d.B <= 65535, B2H_ERR_SHAPE, "prep: B too large for grid.z");
+    dim3 grid(ceil_div(d.L, 32), ceil_div(d.Cfill, 32), d.B), block(32, 8);
+    if (dtype == B2H_BF16)
+      prep_ncl_kernel<__nv_bfloat16><<<grid, block, 0, s>>>(d);
+    else
+      prep_ncl_kernel<float><<<grid, block, 0, s>>>(d);
+  } else {
+    B2H_CHECK_ARG(d.Cfill % 4 == 0 && d.ld % 4 == 0, B2H_ERR_ALIGN, "prep: Cfill/ld must be multiples of 4");
+    int64_t work = (int64_t)d.B * d.L * (d.Cfill / 4);
+    int blocks = (int)std::min<int64_t>(ceil_div64(work, 256), (int64_t)sm_count() * 16);
+    if (dtype == B2H_BF16)
+      prep_rows_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>(d);
+    else
+      prep_rows_kernel<float><<<blocks, 256, 0, s>>>(d);
+  }
+  B2H_LAUNCH_CHECK("prep");
+  return B2H_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// to_ncl: BLC -> (B, C, L) fp32
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) to_ncl_kernel(b2h_to_ncl_t d) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, l0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const T* src = reinterpret_cast<const T*>(d.src) + (int64_t)b * d.L * d.ld;
+  for (int j = ty; j < 32; j += 8) {
+    int l = l0 + j, c = c0 + tx;
+    tile[j][tx] = (l < d.L && c < d.C) ? to_f<T>(src[(int64_t)l * d.ld + c]) : 0.f;
+  }
+  __syncthreads();
+  float* dst = d.dst + (int64_t)b * d.C * d.L;
+  for (int j = ty; j < 32; j += 8) {
+    int c = c0 + j, l = l0 + tx;
+    if (c < d.C && l < d.L) dst[(int64_t)c * d.L + l] = tile[tx][j];
+  }
+}
+
+int launch_to_ncl(const b2h_to_ncl_t& d, int dtype, cudaStream_t s) {
+  B2H_CHECK_ARG(d.B > 0 && d.B <= 65535 && d.L > 0 && d.C > 0 && d.ld >= d.C, B2H_ERR_SHAPE, "to_ncl: bad shape");
+  dim3 grid(ceil_div(d.L, 32), ceil_div(d.C, 32), d.B), block(32, 8);
+  if (dtype == B2H_BF16 && !d.src_f32)
+    to_ncl_kernel<__nv_bfloat16><<<grid, block, 0, s>>>(d);
+  else
+    to_ncl_kernel<float><<<grid, block, 0, s>>>(d);
+  B2H_LAUNCH_CHECK("to_ncl");
+  return B2H_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// L1 loss forward + backward (nn.L1Loss, utils/constants.py:55): one pass over out and gt
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) l1_kernel(b2h_l1_t d) {
+  __shared__ float tile[32][33];
+  __shared__ float s_part[8];
+  const int b = blockIdx.z, l0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int64_t numel = (int64_t)d.B * d.C * d.L;
+  const float gval = d.gscale / (float)numel;
+  float acc = 0.f;
+  for (int j = ty; j < 32; j += 8) {
+    int c = c0 + j, l = l0 + tx;
+    float sg = 0.f;
+    if (c < d.C && l < d.L) {
+      int64_t i = ((int64_t)b * d.C + c) * d.L + l;
+      float diff = d.out[i] - d.gt[i];
+      acc += fabsf(diff);
+      sg = diff > 0.f ? gval : (diff < 0.f ? -gval : 0.f);  // sign(diff)/numel, sign(0) = 0
+    }
+    tile[j][tx] = sg;
+  }
+  acc = warp_sum(acc);
+  if (tx == 0) s_part[ty] = acc;
+  __syncthreads();
+  if (d.dout) {
+    T* dout = reinterpret_cast<T*>(d.dout);
+    for (int j = ty; j < 32; j += 8) {
+      int l = l0 + j, c = c0 + tx;
+      if (l < d.L && c < d.Cfill) dout[((int64_t)b * d.L + l) * d.ld + c] = from_f<T>(c < d.C ? tile[tx][j] : 0.f);
+    }
+  }
+  const uint32_t nblocks = gridDim.x * gridDim.y * gridDim.z;
+  const uint32_t bid = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  if (tx == 0 && ty == 0) {
+    float t = 0.f;
+    for (int k = 0; k < 8; ++k) t += s_part[k];
+    d.partial[bid] = t;
+  }
+  if (!last_block_done(d.ticket, nblocks)) return;
+  // ordered final sum in double by one warp
+  if (ty == 0) {
+    double t = 0.0;
+    for (uint32_t k = tx; k < nblocks; k += 32) t += (double)__ldcg(d.partial + k);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (tx == 0) d.loss[0] = (float)(t / (double)numel);
+  }
+}
+
+int launch_l1(const b2h_l1_t& d, int dtype, cudaStream_t s) {
+  B2H_CHECK_ARG(d.B > 0 && d.B <= 65535 && d.C > 0 && d.L > 0, B2H_ERR_SHAPE, "l1: bad shape");
+  B2H_CHECK_ARG(!d.dout || (d.ld >= d.Cfill && d.Cfill >= d.C), B2H_ERR_SHAPE, "l1: bad dout shape");
+  int cext = d.dout ? d.Cfill : d.C;
+  dim3 grid(ceil_div(d.L, 32), ceil_div(cext, 32), d.B), block(32, 8);
+  if (dtype == B2H_BF16)
+    l1_kernel<__nv_bfloat16><<<grid, block, 0, s>>>(d);
+  else
+    l1_kernel<float><<<grid, block, 0, s>>>(d);
+  B2H_LAUNCH_CHECK("l1");
+  return B2H_OK;
+}
+int64_t l1_partial_floats(const b2h_l1_t& d) {
+  int cext = d.dout ? d.Cfill : d.C;
+  return (int64_t)ceil_div(d.L, 32) * ceil_div(cext, 32) * d.B;
+}
+
+// ---------------------------------------------------------------------------------------------
+// MSE on discriminator scores (nn.MSELoss, train_gan.py:93): tiny, one CTA
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) mse_kernel(b2h_mse_t d) {
+  __shared__ double s_red[256];
+  double total = 0.0;
+  for (int g = 0; g < d.groups; ++g) {
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < d.n; i += 256) {
+      float diff = d.score[(int64_t)g * d.n + i] - d.target[g];
+      acc += (double)diff * (double)diff;
+      if (d.dscore) d.dscore[(int64_t)g * d.n + i] = 2.0f * diff / (float)d.n;
+    }
+    s_red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if (threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o];
+      __syncthreads();
+    }
+    total += s_red[0] / (double)d.n;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    d.loss[0] = (float)total;
+    if (d.total) d.total[0] = (float)total + (d.add ? d.add[0] : 0.f);
+  }
+}
+
+int launch_mse(const b2h_mse_t& d, cudaStream_t s) {
+  B2H_CHECK_ARG(d.groups >= 1 && d.groups <= 2 && d.n > 0, B2H_ERR_SHAPE, "mse: bad shape");
+  mse_kernel<<<1, 256, 0, s>>>(d);
+  B2H_LAUNCH_CHECK("mse");
+  return B2H_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused Adam over a flat parameter buffer (torch.optim.Adam semantics, train_gan.py:69,88)
+//   m = m + (g - m)(1 - b1);  v = v*b2 + (1 - b2) g^2
+//   p -= (lr / (1 - b1^t)) * m / (sqrt(v)/sqrt(1 - b2^t) + eps)
+// 28 B/param: reads p,g,m,v, writes p,m,v.
+// ---------------------------------------------------------------------------------------------
+__global__ void adam_step_kernel(int64_t* step) { *step += 1; }
+
+__global__ void __launch_bounds__(256) adam_kernel(b2h_adam_t d) {
+  // scalar prologue mirrors torch/optim/adam.py (_single_tensor_adam): Python-double arithmetic
+  const int64_t t = *d.step;
+  const double bc1 = 1.0 - pow(d.beta1, (double)t);
+  const double bc2 = 1.0 - pow(d.beta2, (double)t);
+  const float neg_step = (float)(-(d.lr / bc1));
+  const float bc2_sqrt = (float)sqrt(bc2);
+  const float w1 = (float)(1.0 - d.beta1), w2 = (float)(1.0 - d.beta2);
+  const float b2 = (float)d.beta2, eps = (float)d.eps, gs = d.gscale;
+  const int64_t n4 = d.n / 4;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 p = reinterpret_cast<float4*>(d.p)[i];
+    float4 g = reinterpret_cast<const float4*>(d.g)[i];
+    float4 m = reinterpret_cast<float4*>(d.m)[i];
+    float4 v = reinterpret_cast<float4*>(d.v)[i];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float gk = f4(g, k) * gs;
+      float mk = f4(m, k) + w1 * (gk - f4(m, k));         // exp_avg.lerp_(grad, 1 - beta1)
+      float vk = f4(v, k) * b2 + (w2 * gk) * gk;          // mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+      float denom = sqrtf(vk) / bc2_sqrt + eps;           // (sqrt(v) / sqrt(bc2)).add_(eps)
+      f4(p, k) += (neg_step * mk) / denom;                // addcdiv_(exp_avg, denom, value=-step_size)
+      f4(m, k) = mk;
+      f4(v, k) = vk;
+    }
+    reinterpret_cast<float4*>(d.p)[i] = p;
+    reinterpret_cast<float4*>(d.m)[i] = m;
+    reinterpret_cast<float4*>(d.v)[i] = v;
+  }
+  for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < d.n; i += stride) {
+    float gk = d.g[i] * gs;
+    float mk = d.m[i] + w1 * (gk - d.m[i]);
+    float vk = d.v[i] * b2 + (w2 * gk) * gk;
+    float denom = sqrtf(vk) / bc2_sqrt + eps;
+    d.p[i] += (neg_step * mk) / denom;
+    d.m[i] = mk;
+    d.v[i] = vk;
+  }
+}
+
+int launch_adam(const b2h_adam_t& d, cudaStream_t s) {
+  B2H_CHECK_ARG(d.n > 0 && d.step, B2H_ERR_ARG, "adam: bad args");
+  B2H_CHECK_ARG(((uintptr_t)d.p % 16 == 0) && ((uintptr_t)d.g % 16 == 0) && ((uintptr_t)d.m % 16 == 0) &&
+                    ((uintptr_t)d.v % 16 == 0),
+                B2H_ERR_ALIGN, "adam: buffers must be 16-byte aligned");
+  adam_step_kernel<<<1, 1, 0, s>>>(d.step);
+  B2H_LAUNCH_CHECK("adam_step");
+  int blocks = (int)std::min<int64_t>(ceil_div64(d.n / 4 + 1, 256), (int64_t)sm_count() * 8);
+  adam_kernel<<<blocks, 256, 0, s>>>(d);
+  B2H_LAUNCH_CHECK("adam");
+  return B2H_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight repack (PyTorch layout fp32 -> GEMM operand layout [Opad*nphase][ntaps][Ipad], act dtype)
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) pack_kernel(b2h_pack_t d) {
+  const int64_t total = (int64_t)d.nphase * d.Opad * d.ntaps * d.Ipad;
+  T* out = reinterpret_cast<T*>(d.out);
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    int i = (int)(idx % d.Ipad);
+    int64_t r = idx / d.Ipad;
+    int t = (int)(r % d.ntaps);
+    r /= d.ntaps;
+    int o = (int)(r % d.Opad);
+    int ph = (int)(r / d.Opad);
+    int k = d.tapmap[ph][t];
+    float v = 0.f;
+    if (k >= 0 && o < d.O && i < d.I) v = d.W[(int64_t)o * d.o_stride + (int64_t)i * d.i_stride + (int64_t)k * d.k_stride];
+    out[idx] = from_f<T>(v);
+  }
+  if (d.out_bias) {
+    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < (int64_t)d.Opad;
+         o += (int64_t)gridDim.x * blockDim.x)
+      d.out_bias[o] = (d.bias && o < d.O) ? d.bias[o] : 0.f;
+  }
+}
+
+int launch_pack(const b2h_pack_t& d, int dtype, cudaStream_t s) {
+  B2H_CHECK_ARG(d.O > 0 && d.I > 0 && d.Opad >= d.O && d.Ipad >= d.I && d.ntaps >= 1 && d.ntaps <= B2H_MAX_TAPS &&
+                    d.nphase >= 1 && d.nphase <= 2,
+                B2H_ERR_SHAPE, "pack: bad shape");
+  int64_t total = (int64_t)d.nphase * d.Opad * d.ntaps * d.Ipad;
+  int blocks = (int)std::min<int64_t>(ceil_div64(total, 256), (int64_t)sm_count() * 8);
+  if (dtype == B2H_BF16)
+    pack_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>(d);
+  else
+    pack_kernel<float><<<blocks, 256, 0, s>>>(d);
+  B2H_LAUNCH_CHECK("pack");
+  return B2H_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// rot6d -> rotation matrix (utils/conversion_utils.py:86-107), one joint per thread
+//   x = a/(|a|+1e-6); z = x X b; z /= (|z|+1e-6); y = z X x; M = [x y z] as columns, row-major
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) rot6d_kernel(b2h_rot6d_t d) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < d.n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float2* p = reinterpret_cast<const float2*>(d.r6d + i * 6);
+    float2 p0 = p[0], p1 = p[1], p2 = p[2];
+    float ax = p0.x, ay = p0.y, az = p1.x, bx = p1.y, by = p2.x, bz = p2.y;
+    float na = sqrtf(ax * ax + ay * ay + az * az) + 1e-6f;
+    float xx = ax / na, xy = ay / na, xz = az / na;
+    float zx = xy * bz - xz * by, zy = xz * bx - xx * bz, zz = xx * by - xy * bx;
+    float nz = sqrtf(zx * zx + zy * zy + zz * zz) + 1e-6f;
+    zx /= nz, zy /= nz, zz /= nz;
+    float yx = zy * xz - zz * xy, yy = zz * xx - zx * xz, yz = zx * xy - zy * xx;
+    float* o = d.mat + i * 9;
+    o[0] = xx, o[1] = yx, o[2] = zx;
+    o[3] = xy, o[4] = yy, o[5] = zy;
+    o[6] = xz, o[7] = yz, o[8] = zz;
+  }
+}
+
+int launch_rot6d(const b2h_rot6d_t& d, cudaStream_t s) {
+  B2H_CHECK_ARG(d.n > 0, B2H_ERR_SHAPE, "rot6d: n must be positive");
+  B2H_CHECK_ARG((uintptr_t)d.r6d % 8 == 0, B2H_ERR_ALIGN, "rot6d: input must be 8-byte aligned");
+  int blocks = (int)std::min<int64_t>(ceil_div64(d.n, 256), (int64_t)sm_count() * 8);
+  rot6d_kernel<<<blocks, 256, 0, s>>>(d);
+  B2H_LAUNCH_CHECK("rot6d");
+  return B2H_OK;
+}
+
+int launch_fill(const b2h_fill_t& d, cudaStream_t s) {
+  B2H_CHECK_ARG(d.ptr && d.bytes >= 0, B2H_ERR_ARG, "fill: bad args");
+  cudaError_t e = cudaMemsetAsync(d.ptr, d.value, (size_t)d.bytes, s);
+  if (e != cudaSuccess) return cuda_fail(e, "fill");
+  return B2H_OK;
+}
+
+}  // namespace b2h

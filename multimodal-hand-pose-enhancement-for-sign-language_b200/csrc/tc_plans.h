@@ -1,0 +1,49 @@
+// Host-side launch plans of the tcgen05 kernels: encoded TMA tensor maps + tiling parameters.
+// Built once per op (b2h_program_add) and replayed; one-shot calls build them per call.
+#pragma once
+#include <cuda.h>
+#include <stdint.h>
+
+#include "../../include/b2h_abi.h"
+
+namespace b2h {
+
+struct TcGemmParams {
+  int B, Lo, Kc, stride;
+  int tl, tb, n_lchunks;  // M tile = tb samples x tl rows (tl * tb = 128)
+  int ntaps;
+  int tap_map[B2H_MAX_TAPS];    // 0: base / even-row view, 1: odd-row view
+  int tap_coord[B2H_MAX_TAPS];  // row coordinate offset inside that view
+  int tap_w[B2H_MAX_TAPS];      // tap index inside the packed weight (K offset = tap_w * Kc)
+};
+
+struct alignas(64) TcGemmPlan {
+  CUtensorMap tmA0, tmA1, tmB;
+  TcGemmParams p;
+  int BN, grid_x, grid_y;
+};
+
+struct TcWgradParams {
+  int Mpad, Npad, ntaps;
+  int tl, tb, n_lchunks;  // k-block = tb samples x tl rows (tl * tb = 64)
+  int total_kb, kb_per_split;
+  int tap_map[B2H_MAX_TAPS];
+  int tap_coord[B2H_MAX_TAPS];
+};
+
+struct alignas(64) TcWgradPlan {
+  CUtensorMap tmP, tmQ0, tmQ1;
+  TcWgradParams p;
+  int WN, grid_x, splits;
+};
+
+int plan_gemm_bf16(const b2h_gemm_t& d, TcGemmPlan* plan);
+int run_gemm_bf16(const TcGemmPlan& plan, const b2h_gemm_t& d, cudaStream_t s);
+int plan_wgrad_bf16(const b2h_wgrad_t& d, TcWgradPlan* plan);
+int run_wgrad_bf16(const TcWgradPlan& plan, const b2h_wgrad_t& d, cudaStream_t s);
+int64_t wgrad_bf16_workspace_bytes(const b2h_wgrad_t& d);
+int64_t wgrad_workspace_bytes(const b2h_wgrad_t& d, int dtype);
+int64_t bn_partial_floats(int rows, int C, int groups);
+int64_t l1_partial_floats(const b2h_l1_t& d);
+
+}  // namespace b2h

@@ -1,0 +1,116 @@
+"""Pin the oracle restatement (oracle/ref_models.py) against the REAL reference modules.
+
+Runs only where /root/reference is mounted (the authoring container).  The same pins travel
+to the GPU box as tests/golden/*.npz (see tools/make_golden.py, tests/test_golden.py).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_models as R
+
+pytestmark = pytest.mark.reference
+
+CASES = [  # (variant, require_feats, in_dim, out_dim, T)
+    ("v1", False, 36, 252, 64), ("v1", True, 36, 252, 64), ("b2h", False, 36, 252, 32),
+    ("b2h", True, 36, 252, 32), ("v2", False, 264, 24, 64), ("v2", True, 36, 252, 62),
+    ("v4", False, 36, 252, 64), ("v4", True, 36, 252, 64), ("v4_deeper", False, 36, 252, 64),
+    ("v4_deeper", True, 36, 252, 64), ("v1", False, 36, 252, 192), ("v1", False, 36, 252, 66),
+]
+
+
+def _build_ref(mz, variant, rf, cin, cout):
+    m = getattr(mz, R.REF_CLASS[variant])()
+    if variant == "b2h":
+        m.build_net(cin, cout, require_image=rf)
+    else:
+        m.build_net(cin, cout, require_text=rf)
+    return m
+
+
+def _feats(variant, rf, B, T, g):
+    if not rf:
+        return None
+    if variant == "b2h":
+        return torch.randn(B, T, 2000, generator=g)
+    return torch.randn(B, 512, generator=g)
+
+
+@pytest.mark.parametrize("variant,rf,cin,cout,T", CASES)
+def test_generator_matches_reference(reference_modelzoo, variant, rf, cin, cout, T):
+    torch.manual_seed(23456)
+    ref = _build_ref(reference_modelzoo, variant, rf, cin, cout)
+    ora = R.build_generator(variant, cin, cout, rf)
+    sd = ref.state_dict()
+    osd = ora.state_dict()
+    assert list(sd.keys()) == list(osd.keys())
+    for k in sd:
+        assert sd[k].shape == osd[k].shape, k
+    ora.load_state_dict(sd)
+    g = torch.Generator().manual_seed(1)
+    B = 3
+    x = torch.randn(B, cin, T, generator=g)
+    f = _feats(variant, rf, B, T, g)
+    # eval forward: bit-identical
+    ref.eval(), ora.eval()
+    with torch.no_grad():
+        a, b = ref(x, feats_=f), ora(x, feats_=f)
+    assert a.shape == (B, cout, T)
+    assert torch.equal(a, b)
+    # train forward/backward with the same torch RNG stream: bit-identical outputs, grads, BN buffers
+    ref.train(), ora.train()
+    torch.manual_seed(7)
+    a = ref(x, feats_=f)
+    a.abs().mean().backward()
+    torch.manual_seed(7)
+    b = ora(x, feats_=f)
+    b.abs().mean().backward()
+    assert torch.equal(a, b)
+    for (k, p), (_, q) in zip(ref.named_parameters(), ora.named_parameters()):
+        if p.grad is None:
+            assert q.grad is None, k
+        else:
+            assert torch.equal(p.grad, q.grad), k
+    for k, v in ref.state_dict().items():
+        assert torch.equal(v, ora.state_dict()[k]), k
+
+
+def test_discriminator_matches_reference(reference_modelzoo):
+    torch.manual_seed(23456)
+    ref = reference_modelzoo.regressor_fcn_bn_discriminator()
+    ref.build_net(252)
+    ora = R.build_discriminator(252)
+    assert list(ref.state_dict().keys()) == list(ora.state_dict().keys())
+    ora.load_state_dict(ref.state_dict())
+    x = torch.randn(4, 252, 63)
+    for T in (63, 191):
+        x = torch.randn(4, 252, T)
+        ref.eval(), ora.eval()
+        with torch.no_grad():
+            assert torch.equal(ref(x), ora(x))
+    ref.train(), ora.train()
+    torch.manual_seed(3)
+    a = ref(x)
+    torch.manual_seed(3)
+    b = ora(x)
+    assert torch.equal(a, b)
+    assert a.shape == (4, 1, 2)
+
+
+def test_mask_replay_equals_torch_dropout_scaling():
+    d = R.ReplayDropout(0.5)
+    d.site = "s"
+    d.train()
+    x = torch.randn(2, 3, 5)
+    keep = (torch.rand(2, 3, 5) < 0.5).to(torch.uint8)
+    d.store = {"s": keep}
+    assert torch.equal(d(x), x * keep.float() * 2.0)
+
+
+def test_mac_counts_match_survey():
+    # hook-measured on the reference
+    assert R.macs_per_clip(R.build_generator("v1", 36, 252), 64) == 81_369_600 or \
+        abs(R.macs_per_clip(R.build_generator("v1", 36, 252), 64) - 81.370e6) < 1e3
+    assert abs(R.macs_per_clip(R.build_generator("v1", 36, 252, True), 64, "text") - 214.310e6) < 1e3
+    assert abs(R.macs_per_clip(R.build_generator("b2h", 36, 252, True), 64, "image") - 238.689e6) < 1e3
+    assert abs(R.macs_per_clip(R.build_discriminator(252), 63) - 3.018e6) < 1e3
