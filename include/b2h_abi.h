@@ -119,8 +119,10 @@ typedef struct {
 typedef struct {
   const void* z;  /* post-activation, pre-BN tensor [rows][ld], act dtype */
   int32_t ld, coff, rowmap, L_src;
-  const float* mean;    /* [groups][C] batch mean          (train)  */
-  const float* invstd;  /* [groups][C] 1/sqrt(var_b + eps) (train)  */
+  int32_t C_total;      /* channel count of the source layer: the per-channel arrays below are
+                           indexed by (coff + c), the batch statistics by g*C_total + coff + c */
+  const float* mean;    /* [groups][C_total] batch mean          (train)  */
+  const float* invstd;  /* [groups][C_total] 1/sqrt(var_b + eps) (train)  */
   const float* running_mean; /* eval: y = (z - rm)/sqrt(rv + eps)*gamma + beta */
   const float* running_var;
   const float* gamma;
@@ -214,12 +216,12 @@ typedef struct {
  * loss[0] = sum_g mean((s_g - t_g)^2); dscore = 2*(s - t)/n (NULL: forward only);
  * optionally total[0] = loss[0] + add[0]. */
 typedef struct {
-  const float* score;
-  float* dscore;
+  const float* score; /* element (g, i) at score[(g*n + i)*ld] */
+  float* dscore;      /* same addressing */
   float* loss;
   const float* add;
   float* total;
-  int32_t groups, n;
+  int32_t groups, n, ld;
   float target[2];
 } b2h_mse_t;
 
@@ -286,6 +288,8 @@ const char* b2h_last_error(void);
 /* 0 if a CUDA device of compute capability 10.x is current, else B2H_ERR_ARCH / B2H_ERR_CUDA */
 int b2h_check_device(void);
 int b2h_sm_count(void);
+/* sizeof() of the descriptor struct of an op kind (b2h_op_kind), for binding self-checks */
+int b2h_desc_size(int kind);
 
 /* one-shot launches (unit tests, eager use). `dtype` is the activation dtype (b2h_dtype). */
 int b2h_gemm(const b2h_gemm_t* d, int dtype, b2h_stream_t s);

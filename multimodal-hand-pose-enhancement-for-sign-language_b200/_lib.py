@@ -1,0 +1,211 @@
+"""ctypes binding of libb2h.so (include/b2h_abi.h).  No fallbacks: if the library is missing or the
+device is not a B200-class (sm_100) GPU, calls fail loudly."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libb2h.so")
+
+MAX_TAPS = 8
+F32, BF16 = 0, 1
+ACT_NONE, ACT_LEAKY, ACT_RELU = 0, 1, 2
+ROW_IDENT, ROW_UP2, ROW_POOL2, ROW_BCAST = 0, 1, 2, 3
+SRC_NCL, SRC_ROWS, SRC_BCAST, SRC_MOTION = 0, 1, 2, 3
+DROP_NONE, DROP_MASK, DROP_PHILOX = 0, 1, 2
+(OP_GEMM, OP_WGRAD, OP_BN_STATS, OP_BN_APPLY, OP_BN_BWD, OP_PREP, OP_TO_NCL, OP_L1, OP_MSE, OP_COLSUM,
+ OP_ADAM, OP_PACK, OP_BN_FOLD, OP_ROT6D, OP_FILL) = range(1, 16)
+
+i32, i64, f32, f64, vp = C.c_int32, C.c_int64, C.c_float, C.c_double, C.c_void_p
+
+
+class Dropout(C.Structure):
+    _fields_ = [("mode", i32), ("site", i32), ("mask", vp), ("state", vp)]
+
+
+class Gemm(C.Structure):
+    _fields_ = [("A", vp), ("W", vp), ("bias", vp), ("out", vp),
+                ("B", i32), ("La", i32), ("Lo", i32), ("lda", i32), ("ldo", i32), ("out_coff", i32),
+                ("Kc", i32), ("Npad", i32), ("Nvalid", i32), ("ntaps", i32), ("stride", i32),
+                ("tap_off", i32 * MAX_TAPS), ("nphase", i32), ("Lo_actual", i32), ("act", i32),
+                ("post_scale", vp), ("post_shift", vp), ("out_f32", i32), ("drop", Dropout), ("drop_C", i32)]
+
+
+class Wgrad(C.Structure):
+    _fields_ = [("P", vp), ("Q", vp), ("dW", vp), ("partial", vp),
+                ("B", i32), ("Lp", i32), ("Lq", i32), ("ldp", i32), ("ldq", i32),
+                ("Mpad", i32), ("Npad", i32), ("Mvalid", i32), ("Nvalid", i32),
+                ("ntaps", i32), ("stride", i32), ("tap_off", i32 * MAX_TAPS), ("splits", i32)]
+
+
+class BnSrc(C.Structure):
+    _fields_ = [("z", vp), ("ld", i32), ("coff", i32), ("rowmap", i32), ("L_src", i32), ("C_total", i32),
+                ("mean", vp), ("invstd", vp), ("running_mean", vp), ("running_var", vp),
+                ("gamma", vp), ("beta", vp), ("eps", f32), ("use_running", i32)]
+
+
+class BnStats(C.Structure):
+    _fields_ = [("z", vp), ("ld", i32), ("C", i32), ("rows_per_group", i32), ("groups", i32),
+                ("mean", vp), ("invstd", vp), ("running_mean", vp), ("running_var", vp),
+                ("num_batches_tracked", vp), ("momentum", f32), ("eps", f32),
+                ("partial", vp), ("ticket", vp), ("update_all_groups", i32)]
+
+
+class BnApply(C.Structure):
+    _fields_ = [("src", BnSrc * 2), ("nsrc", i32), ("out", vp), ("out_ld", i32), ("out_coff", i32),
+                ("B", i32), ("L", i32), ("C", i32), ("Cfill", i32), ("groups", i32),
+                ("drop", Dropout), ("drop_C", i32), ("drop_coff", i32)]
+
+
+class GradSrc(C.Structure):
+    _fields_ = [("g", vp), ("ld", i32), ("coff", i32), ("rowmap", i32), ("L_src", i32), ("f32", i32)]
+
+
+class BnBwd(C.Structure):
+    _fields_ = [("gsrc", GradSrc * 2), ("ngsrc", i32), ("bn", BnSrc), ("dpre", vp),
+                ("ld_dpre", i32), ("Cfill", i32), ("B", i32), ("L", i32), ("C", i32), ("groups", i32),
+                ("act", i32), ("dgamma", vp), ("dbeta", vp), ("dbias", vp), ("sums", vp), ("partial", vp),
+                ("ticket", vp)]
+
+
+class Prep(C.Structure):
+    _fields_ = [("src", vp), ("out", vp), ("kind", i32), ("B", i32), ("L", i32), ("C", i32), ("ld", i32),
+                ("Cfill", i32), ("src_ld", i32), ("drop", Dropout), ("out_f32", i32)]
+
+
+class ToNcl(C.Structure):
+    _fields_ = [("src", vp), ("dst", vp), ("B", i32), ("L", i32), ("C", i32), ("ld", i32), ("src_f32", i32)]
+
+
+class L1(C.Structure):
+    _fields_ = [("out", vp), ("gt", vp), ("dout", vp), ("loss", vp), ("partial", vp), ("ticket", vp),
+                ("B", i32), ("C", i32), ("L", i32), ("ld", i32), ("Cfill", i32), ("gscale", f32)]
+
+
+class Mse(C.Structure):
+    _fields_ = [("score", vp), ("dscore", vp), ("loss", vp), ("add", vp), ("total", vp),
+                ("groups", i32), ("n", i32), ("ld", i32), ("target", f32 * 2)]
+
+
+class Colsum(C.Structure):
+    _fields_ = [("src", vp), ("out", vp), ("partial", vp), ("ticket", vp),
+                ("rows", i32), ("ld", i32), ("C", i32), ("f32", i32)]
+
+
+class Adam(C.Structure):
+    _fields_ = [("p", vp), ("g", vp), ("m", vp), ("v", vp), ("n", i64),
+                ("lr", f64), ("beta1", f64), ("beta2", f64), ("eps", f64), ("gscale", f32), ("step", vp)]
+
+
+class Pack(C.Structure):
+    _fields_ = [("W", vp), ("out", vp), ("O", i32), ("I", i32), ("Opad", i32), ("Ipad", i32),
+                ("ntaps", i32), ("nphase", i32), ("o_stride", i32), ("i_stride", i32), ("k_stride", i32),
+                ("tapmap", (i32 * MAX_TAPS) * 2), ("bias", vp), ("out_bias", vp)]
+
+
+class BnFold(C.Structure):
+    _fields_ = [("gamma", vp), ("beta", vp), ("running_mean", vp), ("running_var", vp),
+                ("scale", vp), ("shift", vp), ("C", i32), ("Cpad", i32), ("eps", f32)]
+
+
+class Rot6d(C.Structure):
+    _fields_ = [("r6d", vp), ("mat", vp), ("n", i64)]
+
+
+class Fill(C.Structure):
+    _fields_ = [("ptr", vp), ("bytes", i64), ("value", i32)]
+
+
+OP_STRUCT = {OP_GEMM: Gemm, OP_WGRAD: Wgrad, OP_BN_STATS: BnStats, OP_BN_APPLY: BnApply, OP_BN_BWD: BnBwd,
+             OP_PREP: Prep, OP_TO_NCL: ToNcl, OP_L1: L1, OP_MSE: Mse, OP_COLSUM: Colsum, OP_ADAM: Adam,
+             OP_PACK: Pack, OP_BN_FOLD: BnFold, OP_ROT6D: Rot6d, OP_FILL: Fill}
+KIND_OF = {v: k for k, v in OP_STRUCT.items()}
+
+# every symbol include/b2h_abi.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "b2h_abi_version": (C.c_int, []),
+    "b2h_last_error": (C.c_char_p, []),
+    "b2h_check_device": (C.c_int, []),
+    "b2h_sm_count": (C.c_int, []),
+    "b2h_desc_size": (C.c_int, [C.c_int]),
+    "b2h_gemm": (C.c_int, [C.POINTER(Gemm), C.c_int, vp]),
+    "b2h_wgrad": (C.c_int, [C.POINTER(Wgrad), C.c_int, vp]),
+    "b2h_wgrad_workspace_bytes": (i64, [C.POINTER(Wgrad), C.c_int]),
+    "b2h_bn_stats": (C.c_int, [C.POINTER(BnStats), C.c_int, vp]),
+    "b2h_bn_partial_floats": (i64, [C.c_int, C.c_int, C.c_int]),
+    "b2h_bn_apply": (C.c_int, [C.POINTER(BnApply), C.c_int, vp]),
+    "b2h_bn_bwd": (C.c_int, [C.POINTER(BnBwd), C.c_int, vp]),
+    "b2h_prep": (C.c_int, [C.POINTER(Prep), C.c_int, vp]),
+    "b2h_to_ncl": (C.c_int, [C.POINTER(ToNcl), C.c_int, vp]),
+    "b2h_l1": (C.c_int, [C.POINTER(L1), C.c_int, vp]),
+    "b2h_l1_partial_floats": (i64, [C.POINTER(L1)]),
+    "b2h_mse": (C.c_int, [C.POINTER(Mse), vp]),
+    "b2h_colsum": (C.c_int, [C.POINTER(Colsum), C.c_int, vp]),
+    "b2h_adam": (C.c_int, [C.POINTER(Adam), vp]),
+    "b2h_pack": (C.c_int, [C.POINTER(Pack), C.c_int, vp]),
+    "b2h_bn_fold": (C.c_int, [C.POINTER(BnFold), vp]),
+    "b2h_rot6d_to_mat": (C.c_int, [C.POINTER(Rot6d), vp]),
+    "b2h_fill": (C.c_int, [C.POINTER(Fill), vp]),
+    "b2h_program_create": (vp, [C.c_int]),
+    "b2h_program_destroy": (None, [vp]),
+    "b2h_program_add": (C.c_int, [vp, C.c_int, vp]),
+    "b2h_program_size": (C.c_int, [vp]),
+    "b2h_program_run": (C.c_int, [vp, C.c_int, C.c_int, vp]),
+    "b2h_program_launches": (i64, [vp]),
+}
+
+ONESHOT = {OP_GEMM: ("b2h_gemm", True), OP_WGRAD: ("b2h_wgrad", True), OP_BN_STATS: ("b2h_bn_stats", True),
+           OP_BN_APPLY: ("b2h_bn_apply", True), OP_BN_BWD: ("b2h_bn_bwd", True), OP_PREP: ("b2h_prep", True),
+           OP_TO_NCL: ("b2h_to_ncl", True), OP_L1: ("b2h_l1", True), OP_MSE: ("b2h_mse", False),
+           OP_COLSUM: ("b2h_colsum", True), OP_ADAM: ("b2h_adam", False), OP_PACK: ("b2h_pack", True),
+           OP_BN_FOLD: ("b2h_bn_fold", False), OP_ROT6D: ("b2h_rot6d_to_mat", False), OP_FILL: ("b2h_fill", False)}
+
+
+class B2HError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load(build_if_missing: bool = False):
+    """Load libb2h.so.  Raises (never falls back) if the library cannot be loaded."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        if build_if_missing:
+            from . import build as _build
+            _build.build()
+        else:
+            raise B2HError(f"{LIB_PATH} is missing: run `python __graft_entry__.py build` "
+                           "(the B200 path has no CPU or PyTorch fallback)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    if lib.b2h_abi_version() != 1:
+        raise B2HError("libb2h.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = ""):
+    if rc < 0:
+        msg = load().b2h_last_error().decode(errors="replace")
+        raise B2HError(f"{what} failed ({rc}): {msg}")
+    return rc
+
+
+def require_device():
+    check(load().b2h_check_device(), "b2h_check_device")
+
+
+def run_oneshot(desc, dtype: int, stream: int):
+    lib = load()
+    name, has_dtype = ONESHOT[KIND_OF[type(desc)]]
+    fn = getattr(lib, name)
+    rc = fn(C.byref(desc), dtype, stream) if has_dtype else fn(C.byref(desc), stream)
+    check(rc, name)

@@ -152,6 +152,7 @@ int b2h_abi_version(void) { return B2H_ABI_VERSION; }
 const char* b2h_last_error(void) { return g_err; }
 int b2h_check_device(void) { return check_device(); }
 int b2h_sm_count(void) { return sm_count(); }
+int b2h_desc_size(int kind) { return (int)desc_size(kind); }
 
 #define B2H_ONESHOT(kind_, field_, desc_)                      \
   int rc = check_dtype(dtype);                                 \

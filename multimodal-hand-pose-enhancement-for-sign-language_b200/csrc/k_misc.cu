@@ -223,9 +223,9 @@ __global__ void __launch_bounds__(256) mse_kernel(b2h_mse_t d) {
   for (int g = 0; g < d.groups; ++g) {
     double acc = 0.0;
     for (int i = threadIdx.x; i < d.n; i += 256) {
-      float diff = d.score[(int64_t)g * d.n + i] - d.target[g];
+      float diff = d.score[((int64_t)g * d.n + i) * d.ld] - d.target[g];
       acc += (double)diff * (double)diff;
-      if (d.dscore) d.dscore[(int64_t)g * d.n + i] = 2.0f * diff / (float)d.n;
+      if (d.dscore) d.dscore[((int64_t)g * d.n + i) * d.ld] = 2.0f * diff / (float)d.n;
     }
     s_red[threadIdx.x] = acc;
     __syncthreads();
@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(256) mse_kernel(b2h_mse_t d) {
 }
 
 int launch_mse(const b2h_mse_t& d, cudaStream_t s) {
-  B2H_CHECK_ARG(d.groups >= 1 && d.groups <= 2 && d.n > 0, B2H_ERR_SHAPE, "mse: bad shape");
+  B2H_CHECK_ARG(d.groups >= 1 && d.groups <= 2 && d.n > 0 && d.ld >= 1, B2H_ERR_SHAPE, "mse: bad shape");
   mse_kernel<<<1, 256, 0, s>>>(d);
   B2H_LAUNCH_CHECK("mse");
   return B2H_OK;

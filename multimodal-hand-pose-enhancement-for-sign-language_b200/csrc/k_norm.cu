@@ -33,15 +33,16 @@ __device__ __forceinline__ Affine4 bn_affine(const b2h_bn_src_t& src, int g, int
     int c = c0 + i;
     float s = 0.f, t = 0.f;
     if (c < C) {
-      float gamma = src.gamma ? src.gamma[c] : 1.f;
-      float beta = src.beta ? src.beta[c] : 0.f;
+      const int cs = src.coff + c;  // channel index inside the source layer
+      float gamma = src.gamma ? src.gamma[cs] : 1.f;
+      float beta = src.beta ? src.beta[cs] : 0.f;
       float mean, invstd;
       if (src.use_running) {
-        mean = src.running_mean[c];
-        invstd = 1.0f / sqrtf(src.running_var[c] + src.eps);
+        mean = src.running_mean[cs];
+        invstd = 1.0f / sqrtf(src.running_var[cs] + src.eps);
       } else {
-        mean = src.mean[g * C + c];
-        invstd = src.invstd[g * C + c];
+        mean = src.mean[g * src.C_total + cs];
+        invstd = src.invstd[g * src.C_total + cs];
       }
       s = invstd * gamma;
       t = beta - mean * s;
@@ -244,8 +245,10 @@ int launch_bn_apply(const b2h_bn_apply_t& d, int dtype, cudaStream_t s) {
   B2H_CHECK_ARG(d.Cfill % 4 == 0 && d.out_ld % 4 == 0 && d.out_coff % 4 == 0, B2H_ERR_ALIGN,
                 "bn_apply: alignment Cfill=%d ld=%d coff=%d", d.Cfill, d.out_ld, d.out_coff);
   B2H_CHECK_ARG((d.B * d.L) % d.groups == 0, B2H_ERR_SHAPE, "bn_apply: rows not divisible by groups");
-  for (int i = 0; i < d.nsrc; ++i)
+  for (int i = 0; i < d.nsrc; ++i) {
     B2H_CHECK_ARG(d.src[i].ld % 4 == 0 && d.src[i].coff % 4 == 0, B2H_ERR_ALIGN, "bn_apply: src alignment");
+    B2H_CHECK_ARG(d.src[i].coff + d.C <= d.src[i].C_total, B2H_ERR_SHAPE, "bn_apply: source channel range");
+  }
   BlockShape bs = block_shape(d.Cfill);
   dim3 grid(ceil_div(d.B * d.L, kBnChunkRows)), block(bs.txp, bs.ty);
   if (dtype == B2H_BF16)
@@ -413,6 +416,7 @@ int launch_bn_bwd(const b2h_bn_bwd_t& d, int dtype, cudaStream_t s) {
                 "bn_bwd: alignment");
   B2H_CHECK_ARG((d.B * d.L) % d.groups == 0, B2H_ERR_SHAPE, "bn_bwd: rows not divisible by groups");
   B2H_CHECK_ARG(!d.bn.use_running, B2H_ERR_ARG, "bn_bwd: backward is only defined for batch statistics");
+  B2H_CHECK_ARG(d.bn.coff == 0 && d.bn.C_total == d.C, B2H_ERR_SHAPE, "bn_bwd: bn source must cover the whole layer");
   BlockShape bs = block_shape(d.Cfill);
   int rpg = d.B * d.L / d.groups;
   int nchunks = bn_nchunks(rpg);

@@ -1,0 +1,708 @@
+"""Network specs (the five generator variants + the discriminator of modelZoo.py) as small DAGs of
+Dropout->Conv/Linear->Act->BN blocks, the flat parameter store with the reference's state_dict
+names, and `NetPlan`, which lowers a spec at a fixed (B, T) to recorded programs of libb2h ops:
+  pack      master fp32 weights -> GEMM operand layouts (activation dtype)
+  fwd       prep / bn_apply(+residual, up/pool, dropout) -> tap-GEMM(bias, act) -> bn_stats
+  bwd       bn_bwd -> wgrad -> dgrad(+dropout mask) per block, in reverse order
+
+Reference citations: modelZoo.py:6-166 (b2h), :169-328 (v1), :331-440 (v2), :443-554 (v4),
+:557-710 (v4_deeper), :763-817 (discriminator).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple, Union
+
+import torch
+
+from . import _lib as L
+from .program import Program, no_drop
+
+BN_EPS = 1e-5
+
+
+def ceil64(c: int) -> int:
+    return (c + 63) // 64 * 64
+
+
+# ------------------------------------------------------------------------------------------------
+# spec
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class Feed:
+    src: Union["Layer", str]  # a Layer, or 'x' / 'feats' / 'motion'
+    rowmap: int = L.ROW_IDENT
+    dst_coff: int = 0
+
+
+@dataclass
+class Layer:
+    name: str
+    seq: str           # nn.Sequential attribute holding the block
+    w_idx: int         # index of the Conv1d / ConvTranspose1d / Linear inside it
+    kind: str          # 'conv' | 'convT' | 'linear'
+    cin: int
+    cout: int
+    k: int = 1
+    stride: int = 1
+    pad: int = 0
+    act: int = L.ACT_LEAKY
+    bn: bool = True
+    momentum: float = 0.1
+    feeds: List[Feed] = field(default_factory=list)
+    rows_like: Optional["Layer"] = None   # 'feats' linear layers: rows per sample follow this layer's output
+    # filled by NetPlan
+    La: int = 0
+    Lo: int = 0
+
+    @property
+    def drop_site(self):
+        return f"{self.seq}.{self.w_idx - 1}"
+
+    @property
+    def wkey(self):
+        return f"{self.seq}.{self.w_idx}"
+
+    @property
+    def bnkey(self):
+        return f"{self.seq}.{self.w_idx + 2}"
+
+
+@dataclass
+class NetSpec:
+    name: str
+    layers: List[Layer]            # topological order, live layers only
+    module_order: List[str]        # registration order of the Sequentials (parameter order)
+    in_dim: int
+    out_dim: int
+    feats: Optional[str] = None    # None | 'text' | 'image'
+    dead: List[Layer] = field(default_factory=list)  # parameters that exist but never reach the output
+    input_kind: str = "x"          # 'x' (generator) | 'motion' (discriminator)
+
+    def all_layers(self):
+        return self.layers + self.dead
+
+
+def _blk(name, seq, w_idx, cin, cout, k, stride=1, pad=None, **kw):
+    return Layer(name, seq, w_idx, "conv", cin, cout, k, stride, k // 2 if pad is None else pad, **kw)
+
+
+def generator_spec(variant: str, in_dim: int, out_dim: int, require_feats: bool = False,
+                   default_size: int = 256, train: bool = True) -> NetSpec:
+    """DAG of one generator variant.  `train` only matters for text branches whose rows are identical
+    over time in eval mode (no dropout): they are then computed once per clip and broadcast."""
+    D = default_size
+    rf = bool(require_feats)
+    E = D + (D if rf else 0)
+    layers: List[Layer] = []
+    dead: List[Layer] = []
+    feats_kind = None
+    if variant in ("v1", "b2h"):
+        enc_out = D
+    else:
+        enc_out = E
+    enc = _blk("encoder", "encoder", 1, in_dim, enc_out, 3, feeds=[Feed("x")])
+    layers.append(enc)
+    side = None
+    order: List[str] = []
+    if rf and variant == "v1":
+        feats_kind = "text"
+        side = Layer("text", "text_embeds_postprocess", 1, "linear", 512, D, momentum=0.01, feeds=[Feed("feats")])
+        layers.append(side)
+        order += ["text_embeds_postprocess"]
+    elif rf and variant == "b2h":
+        feats_kind = "image"
+        side = Layer("image", "image_resnet_postprocess", 1, "linear", 2000, D, momentum=0.01, feeds=[Feed("feats")])
+        layers.append(side)
+        order += ["image_resnet_postprocess"]
+    elif rf:
+        feats_kind = "text"
+        order += ["text_embeds_postprocess"]
+    order += ["encoder", "conv5", "conv6", "conv7"]
+    f5 = [Feed(enc, L.ROW_POOL2, 0)]
+    if side is not None:
+        text_eval_bcast = (feats_kind == "text" and not train)
+        f5.append(Feed(side, L.ROW_BCAST if text_eval_bcast else L.ROW_POOL2, D))
+    conv5 = _blk("conv5", "conv5", 1, E, E, 3, feeds=f5)
+    conv6 = _blk("conv6", "conv6", 1, E, E, 3, feeds=[Feed(conv5)])
+    narrow = E // 2 if (rf and variant in ("v4", "v4_deeper")) else E
+    c7out = narrow if variant == "v4" else E
+    conv7 = _blk("conv7", "conv7", 1, E, c7out, 5, stride=2, pad=2, feeds=[Feed(conv6)])
+    layers += [conv5, conv6, conv7]
+    up_feeds = [Feed(conv7, L.ROW_UP2, 0)]
+    if rf and variant == "v4":
+        text = Layer("text", "text_embeds_postprocess", 1, "linear", 512, E // 2, momentum=0.01,
+                     feeds=[Feed("feats")], rows_like=conv7)
+        layers.append(text)
+        up_feeds.append(Feed(text, L.ROW_UP2 if train else L.ROW_BCAST, c7out))
+    if rf and variant == "v2":
+        # modelZoo.py:429-433: the text row is appended as an extra TIME step and cropped away by
+        # upsample(); it never reaches the output -> parameters exist, gradients are 0
+        dead.append(Layer("text", "text_embeds_postprocess", 1, "linear", 512, E, momentum=0.01))
+    if variant == "v4_deeper":
+        sa, sb = "skip3", "skip4"
+        order += ["conv8", "conv9", "conv10", "skip1", "skip2", "skip3", "skip4"]
+        # modelZoo.py:689-704: conv8..conv10, skip1, skip2 and the text branch never reach the output (S7)
+        dead += [_blk("conv8", "conv8", 1, E, E, 3), _blk("conv9", "conv9", 1, E, narrow, 3),
+                 _blk("conv10", "conv10", 1, narrow, narrow, 3), _blk("skip1", "skip1", 1, E, E, 3),
+                 _blk("skip2", "skip2", 1, E, E, 3)]
+        if rf:
+            dead.append(Layer("text", "text_embeds_postprocess", 1, "linear", 512, E // 2, momentum=0.01))
+    else:
+        sa, sb = "skip4", "skip5"
+        order += ["skip4", "skip5"]
+    order += ["decoder"]
+    skipa = _blk(sa, sa, 1, E, E, 3, feeds=up_feeds + [Feed(conv6)])
+    skipb = _blk(sb, sb, 1, E, E, 3, feeds=[Feed(skipa), Feed(conv5)])
+    dec1 = _blk("decoder.1", "decoder", 1, E, E, 3, feeds=[Feed(skipb)])
+    dec5 = Layer("decoder.5", "decoder", 5, "convT", E, out_dim, 7, 2, 3, act=L.ACT_RELU, feeds=[Feed(dec1)])
+    dec9 = _blk("decoder.9", "decoder", 9, out_dim, out_dim, 7, act=L.ACT_NONE, bn=False, feeds=[Feed(dec5)])
+    layers += [skipa, skipb, dec1, dec5, dec9]
+    return NetSpec(f"{variant}{'+' + feats_kind if feats_kind else ''}", layers, order, in_dim, out_dim, feats_kind,
+                   dead)
+
+
+def discriminator_spec(in_dim: int) -> NetSpec:
+    chans = [in_dim, 64, 64, 32, 32, 16, 16, 8]
+    layers = []
+    prev: Union[Layer, str] = "motion"
+    for i in range(7):
+        lay = _blk(f"convs.{4 * i + 1}", "convs", 4 * i + 1, chans[i], chans[i + 1], 5, stride=2, pad=2,
+                   feeds=[Feed(prev)])
+        layers.append(lay)
+        prev = lay
+    layers.append(_blk("convs.29", "convs", 29, 8, 1, 3, act=L.ACT_NONE, bn=False, feeds=[Feed(prev)]))
+    return NetSpec("discriminator", layers, ["convs"], in_dim, 1, None, [], input_kind="motion")
+
+
+# ------------------------------------------------------------------------------------------------
+# parameters: flat fp32 buffers exposed under the reference's state_dict names
+# ------------------------------------------------------------------------------------------------
+def _wshape(l: Layer):
+    if l.kind == "conv":
+        return (l.cout, l.cin, l.k)
+    if l.kind == "convT":
+        return (l.cin, l.cout, l.k)
+    return (l.cout, l.cin)
+
+
+class ParamStore:
+    """Flat parameter / gradient / Adam-state buffers + BN buffers, with named views.
+
+    Parameter order == the reference's `named_parameters()` order (module registration order, then
+    weight/bias of each child in index order) so optimizer state indices line up."""
+
+    def __init__(self, spec: NetSpec, device, seed: Optional[int] = None):
+        self.spec = spec
+        self.device = torch.device(device)
+        by_seq: Dict[str, List[Layer]] = {}
+        for l in spec.all_layers():
+            by_seq.setdefault(l.seq, []).append(l)
+        self.param_shapes: List[Tuple[str, Tuple[int, ...]]] = []
+        self.buffer_shapes: List[Tuple[str, Tuple[int, ...]]] = []
+        for seq in spec.module_order:
+            for l in sorted(by_seq[seq], key=lambda x: x.w_idx):
+                self.param_shapes += [(l.wkey + ".weight", _wshape(l)), (l.wkey + ".bias", (l.cout,))]
+                if l.bn:
+                    self.param_shapes += [(l.bnkey + ".weight", (l.cout,)), (l.bnkey + ".bias", (l.cout,))]
+                    self.buffer_shapes += [(l.bnkey + ".running_mean", (l.cout,)), (l.bnkey + ".running_var", (l.cout,))]
+        self.offsets: Dict[str, int] = {}
+        off = 0
+        for k, shp in self.param_shapes:
+            self.offsets[k] = off
+            off += (math.prod(shp) + 3) // 4 * 4
+        self.n = off
+        boff = 0
+        self.boffsets: Dict[str, int] = {}
+        for k, shp in self.buffer_shapes:
+            self.boffsets[k] = boff
+            boff += (math.prod(shp) + 3) // 4 * 4
+        self.flat = torch.zeros(self.n, dtype=torch.float32, device=self.device)
+        self.grad = torch.zeros(self.n, dtype=torch.float32, device=self.device)
+        self.bufs = torch.zeros(max(boff, 4), dtype=torch.float32, device=self.device)
+        bn_layers = [l for l in spec.all_layers() if l.bn]
+        self.nbt_index = {l.bnkey + ".num_batches_tracked": i for i, l in enumerate(bn_layers)}
+        self.nbt = torch.zeros(max(len(bn_layers), 1), dtype=torch.int64, device=self.device)
+        self.version = 0  # bumped by whoever changes `flat` (re-pack trigger)
+        self.reset_parameters(seed)
+
+    # views -----------------------------------------------------------------------------------
+    def _view(self, flat, k, shapes, offsets):
+        shp = dict(shapes)[k]
+        o = offsets[k]
+        return flat[o:o + math.prod(shp)].view(shp)
+
+    def p(self, k):
+        return self._view(self.flat, k, self.param_shapes, self.offsets)
+
+    def g(self, k):
+        return self._view(self.grad, k, self.param_shapes, self.offsets)
+
+    def b(self, k):
+        return self._view(self.bufs, k, self.buffer_shapes, self.boffsets)
+
+    def nbt_view(self, k):
+        i = self.nbt_index[k]
+        return self.nbt[i:i + 1]
+
+    def reset_parameters(self, seed: Optional[int] = None):
+        """PyTorch default init (kaiming_uniform(a=sqrt(5)) weights, U(+-1/sqrt(fan_in)) biases, BN 1/0)."""
+        gen = torch.Generator(device="cpu")
+        if seed is not None:
+            gen.manual_seed(seed)
+        else:
+            gen.seed()
+        with torch.no_grad():
+            for k, shp in self.param_shapes:
+                v = self.p(k)
+                if k.endswith(".weight") and len(shp) >= 2:
+                    fan_in = shp[1] * (shp[2] if len(shp) == 3 else 1)
+                    bound = 1.0 / math.sqrt(fan_in)
+                    v.copy_((torch.rand(shp, generator=gen) * 2 - 1) * bound)
+                    bk = k[:-len("weight")] + "bias"
+                    self.p(bk).copy_((torch.rand(dict(self.param_shapes)[bk], generator=gen) * 2 - 1) * bound)
+                elif k.endswith(".weight"):
+                    v.fill_(1.0)   # BN gamma
+                elif len(shp) == 1 and (k[:-len("bias")] + "weight") in self.offsets and \
+                        len(dict(self.param_shapes)[k[:-len("bias")] + "weight"]) == 1:
+                    v.zero_()      # BN beta
+            for k, _ in self.buffer_shapes:
+                self.b(k).fill_(1.0 if k.endswith("running_var") else 0.0)
+            self.nbt.zero_()
+        self.version += 1
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        """Reference-ordered state_dict (clones)."""
+        out = {}
+        bn_keys = {k for k, _ in self.buffer_shapes}
+        for k, _ in self.param_shapes:
+            out[k] = self.p(k).detach().clone()
+            if k.endswith(".bias"):
+                base = k[:-len(".bias")]
+                if base + ".running_mean" in bn_keys:
+                    out[base + ".running_mean"] = self.b(base + ".running_mean").clone()
+                    out[base + ".running_var"] = self.b(base + ".running_var").clone()
+                    out[base + ".num_batches_tracked"] = self.nbt_view(base + ".num_batches_tracked")[0].clone()
+        return out
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor], strict: bool = True):
+        missing = []
+        with torch.no_grad():
+            for k, _ in self.param_shapes:
+                if k in sd:
+                    self.p(k).copy_(sd[k])
+                else:
+                    missing.append(k)
+            for k, _ in self.buffer_shapes:
+                if k in sd:
+                    self.b(k).copy_(sd[k])
+                else:
+                    missing.append(k)
+            for k in self.nbt_index:
+                if k in sd:
+                    self.nbt_view(k).fill_(int(sd[k]))
+        if strict and missing:
+            raise KeyError(f"missing keys: {missing}")
+        self.version += 1
+        return missing
+
+
+# ------------------------------------------------------------------------------------------------
+# plan
+# ------------------------------------------------------------------------------------------------
+def _conv_out_len(La, k, stride, pad):
+    return (La + 2 * pad - k) // stride + 1
+
+
+@dataclass
+class LayerBufs:
+    a: torch.Tensor = None        # (B, La, Kc)    conv input after dropout
+    z: torch.Tensor = None        # (B, Lo_act, Cp) post-activation, pre-BN
+    mean: torch.Tensor = None
+    invstd: torch.Tensor = None
+    dpre: torch.Tensor = None     # (B, Lo_act, Cp)
+    g: torch.Tensor = None        # (B, La, Kc) gradient w.r.t. the pre-dropout input (mask applied)
+    wf: torch.Tensor = None       # packed forward weights
+    wb: torch.Tensor = None       # packed dgrad weights
+    bias: torch.Tensor = None     # packed bias
+    Kc: int = 0
+    Cp: int = 0
+    Lz: int = 0                   # rows per sample of z (2*La for convT)
+    ain_C: int = 0                # valid channels of `a`
+
+
+class NetPlan:
+    """One network at a fixed batch / length / precision / mode, lowered to a recorded program."""
+
+    def __init__(self, spec: NetSpec, store: ParamStore, B: int, T: int, dtype: int, device,
+                 train: bool, groups: int = 1, drop_mode: str = "philox", need_input_grad: bool = False,
+                 drop_state: Optional[torch.Tensor] = None, site_base: int = 0):
+        assert drop_mode in ("none", "mask", "philox")
+        self.spec, self.store, self.B, self.T, self.dtype = spec, store, B, T, dtype
+        self.device = torch.device(device)
+        self.train, self.groups = train, groups
+        self.drop_mode = drop_mode if train else "none"
+        self.act_dtype = torch.bfloat16 if dtype == L.BF16 else torch.float32
+        self.prog = Program(dtype, self.device)
+        self.bufs: Dict[str, LayerBufs] = {}
+        self.masks: Dict[str, torch.Tensor] = {}
+        self.site_ids: Dict[str, int] = {}
+        self.drop_state = drop_state
+        if self.drop_mode == "philox" and drop_state is None:
+            self.drop_state = torch.zeros(2, dtype=torch.int64, device=self.device)
+        self._tickets: List[torch.Tensor] = []
+        self._partial_need = 4
+        self._wg_need = 16
+        self._pending_partial: List[Tuple[int, str]] = []
+        self._site_base = site_base
+        self._build()
+
+    # ---- helpers -----------------------------------------------------------------------------
+    def _zeros(self, *shape, dtype=None):
+        return torch.zeros(*shape, dtype=dtype or self.act_dtype, device=self.device)
+
+    def _ticket(self):
+        if not self._tickets or self._tickets[-1][1] >= 256:
+            self._tickets.append([torch.zeros(256, dtype=torch.int32, device=self.device), 0])
+        t, n = self._tickets[-1]
+        self._tickets[-1][1] = n + 1
+        return t[n:n + 1]
+
+    def _drop(self, site: str, shape: Tuple[int, int, int]):
+        """Dropout descriptor of a site whose tensor is (B, L, C) in BLC order."""
+        if self.drop_mode == "none":
+            return no_drop()
+        sid = self.site_ids.setdefault(site, self._site_base + len(self.site_ids) + 1)
+        if self.drop_mode == "mask":
+            if site not in self.masks:
+                self.masks[site] = torch.ones(shape, dtype=torch.uint8, device=self.device)
+            assert tuple(self.masks[site].shape) == tuple(shape), (site, self.masks[site].shape, shape)
+            return {"mode": L.DROP_MASK, "site": sid, "mask": self.masks[site], "state": None}
+        return {"mode": L.DROP_PHILOX, "site": sid, "mask": None, "state": self.drop_state}
+
+    def set_masks(self, masks_ncl: Dict[str, torch.Tensor], group: Optional[int] = None):
+        """Install keep-masks given in the reference's layout: (B, C, L) per conv site, (rows, C) per
+        Linear site.  `group` selects the batch slice of a grouped (fake / real) discriminator batch."""
+        assert self.drop_mode == "mask"
+        for site, dst in self.masks.items():
+            m = masks_ncl[site]
+            if m.dim() == 3:
+                m = m.permute(0, 2, 1)
+            if group is not None:
+                Bg = self.B // self.groups
+                dst = dst[group * Bg:(group + 1) * Bg]
+            dst.copy_(m.reshape(dst.shape).to(dst.device, torch.uint8))
+
+    def _bn_src(self, l: Layer, rowmap=L.ROW_IDENT, coff=0):
+        lb = self.bufs[l.name]
+        st = self.store
+        d = {"z": lb.z, "ld": lb.Cp, "coff": coff, "rowmap": rowmap, "L_src": lb.Lz if rowmap != L.ROW_BCAST else 1,
+             "C_total": l.cout,
+             "gamma": st.p(l.bnkey + ".weight"), "beta": st.p(l.bnkey + ".bias"), "eps": BN_EPS}
+        if self.train:
+            d.update(mean=lb.mean, invstd=lb.invstd, running_mean=None, running_var=None, use_running=0)
+        else:
+            d.update(mean=None, invstd=None, running_mean=st.b(l.bnkey + ".running_mean"),
+                     running_var=st.b(l.bnkey + ".running_var"), use_running=1)
+        return d
+
+    # ---- build -------------------------------------------------------------------------------
+    def _build(self):
+        spec, B, T = self.spec, self.B, self.T
+        P = self.prog
+        self.consumers: Dict[str, List[Tuple[Layer, Feed]]] = {l.name: [] for l in spec.layers}
+        # shapes
+        for l in spec.layers:
+            f0 = l.feeds[0]
+            if f0.src == "x":
+                l.La = T
+            elif f0.src == "motion":
+                l.La = T - 1
+            elif f0.src == "feats":
+                if not (self.train or spec.feats == "image"):
+                    l.La = 1          # eval-mode text rows are identical over time: one row per clip
+                else:
+                    l.La = self.bufs[l.rows_like.name].Lz if l.rows_like is not None else T
+            else:
+                srcl = f0.src
+                Lz = self.bufs[srcl.name].Lz
+                l.La = {L.ROW_IDENT: Lz, L.ROW_UP2: None, L.ROW_POOL2: Lz // 2, L.ROW_BCAST: None}[f0.rowmap]
+                if l.La is None:  # up-sampled / broadcast feeds take the length of the identity feed
+                    ident = [f for f in l.feeds if f.rowmap == L.ROW_IDENT]
+                    l.La = self.bufs[ident[0].src.name].Lz
+            for f in l.feeds:
+                if isinstance(f.src, Layer):
+                    self.consumers[f.src.name].append((l, f))
+            if l.kind == "convT":
+                l.Lo = l.La
+                Lz = 2 * l.La
+            else:
+                l.Lo = _conv_out_len(l.La, l.k, l.stride, l.pad)
+                Lz = l.Lo
+            assert l.Lo >= 1, f"{l.name}: sequence too short (T={T})"
+            lb = LayerBufs(Kc=ceil64(l.cin), Cp=ceil64(l.cout), Lz=Lz, ain_C=l.cin)
+            lb.a = self._zeros(B, l.La, lb.Kc)
+            if l.bn:
+                lb.z = self._zeros(B, Lz, lb.Cp)
+                lb.mean = self._zeros(self.groups, l.cout, dtype=torch.float32)
+                lb.invstd = self._zeros(self.groups, l.cout, dtype=torch.float32)
+            self.bufs[l.name] = lb
+        self.out_layer = spec.layers[-1]
+        ol = self.out_layer
+        # static inputs / outputs (reference layouts)
+        if spec.input_kind == "x":
+            self.x = self._zeros(B, spec.in_dim, T, dtype=torch.float32)
+        else:
+            # discriminator: `groups` NCL tensors of (B/groups, C, T) whose calc_motion it scores
+            self.motion_src = [self._zeros(B // self.groups, spec.in_dim, T, dtype=torch.float32)
+                               for _ in range(self.groups)]
+        if spec.feats == "text":
+            self.feats = self._zeros(B, 512, dtype=torch.float32)
+        elif spec.feats == "image":
+            self.feats = self._zeros(B, T, 2000, dtype=torch.float32)
+        else:
+            self.feats = None
+        olb = self.bufs[ol.name]
+        self.out_blc = self._zeros(B, olb.Lz, max(olb.Cp, 4), dtype=torch.float32)
+        self.out = self._zeros(B, ol.cout, olb.Lz, dtype=torch.float32)   # (B, C_out, T) NCL
+
+        with P.segment("pack"):
+            for l in spec.layers:
+                self._emit_pack(l)
+        with P.segment("fwd"):
+            for l in spec.layers:
+                self._emit_input(l)
+                self._emit_fwd_gemm(l)
+                if l.bn and self.train:
+                    self._emit_bn_stats(l)
+            if spec.input_kind == "x":
+                P.add(L.OP_TO_NCL, "out", src=self.out_blc, dst=self.out, B=B, L=olb.Lz, C=ol.cout,
+                      ld=self.out_blc.shape[-1], src_f32=1)
+        if self.train:
+            # gradient of the loss w.r.t. the output layer's pre-activation, BLC act dtype
+            olb.dpre = self._zeros(B, olb.Lz, olb.Cp)
+            with P.segment("bwd"):
+                for l in reversed(spec.layers):
+                    self._emit_bwd(l)
+        # shared workspaces, patched into the records
+        self.partial = self._zeros(self._partial_need, dtype=torch.float32)
+        self.wg_partial = self._zeros(self._wg_need // 4 + 4, dtype=torch.float32)
+        for i, fld in self._pending_partial:
+            self.prog.recs[i].f[fld] = self.wg_partial if self.prog.recs[i].kind == L.OP_WGRAD else self.partial
+
+    def _need_partial(self, idx: int, floats: int, fld: str = "partial"):
+        self._partial_need = max(self._partial_need, int(floats))
+        self._pending_partial.append((idx, fld))
+
+    # ---- pack --------------------------------------------------------------------------------
+    def _emit_pack(self, l: Layer):
+        P, st, lb = self.prog, self.store, self.bufs[l.name]
+        W = st.p(l.wkey + ".weight")
+        bias = st.p(l.wkey + ".bias")
+        k = l.k
+        lb.bias = self._zeros(lb.Cp, dtype=torch.float32)
+        if l.kind in ("conv", "linear"):
+            lb.fwd_taps = [t - l.pad for t in range(k)]
+            lb.wf = self._zeros(lb.Cp, k, lb.Kc)
+            P.add(L.OP_PACK, f"pack.{l.name}.fwd", W=W, out=lb.wf, O=l.cout, I=l.cin, Opad=lb.Cp, Ipad=lb.Kc,
+                  ntaps=k, nphase=1, o_stride=l.cin * k, i_stride=k, k_stride=1,
+                  tapmap=[list(range(k)) + [-1] * (L.MAX_TAPS - k), [-1] * L.MAX_TAPS], bias=bias, out_bias=lb.bias)
+        else:  # convT k7 s2 p3 op1 as a 2-phase sub-pixel conv over taps {-1, 0, 1, 2}
+            assert (l.k, l.stride, l.pad) == (7, 2, 3)
+            lb.fwd_taps = [-1, 0, 1, 2]
+            lb.wf = self._zeros(2 * lb.Cp, 4, lb.Kc)
+            tm = [[3 - 2 * o for o in lb.fwd_taps], [4 - 2 * o for o in lb.fwd_taps]]
+            tm = [[kk if 0 <= kk < k else -1 for kk in row] + [-1] * 4 for row in tm]
+            P.add(L.OP_PACK, f"pack.{l.name}.fwd", W=W, out=lb.wf, O=l.cout, I=l.cin, Opad=lb.Cp, Ipad=lb.Kc,
+                  ntaps=4, nphase=2, o_stride=k, i_stride=l.cout * k, k_stride=1, tapmap=tm, bias=bias,
+                  out_bias=lb.bias)
+        if not (self.train and self._needs_dgrad(l)):
+            return
+        if l.kind == "convT":
+            # dA[b,i,c] = sum_k sum_n dpre[b, 2i + k - 3, n] W[c,n,k]: a stride-2 conv over dpre
+            lb.bwd_taps = [kk - l.pad for kk in range(k)]
+            lb.bwd_stride, lb.bwd_nphase = 2, 1
+            lb.wb = self._zeros(lb.Kc, k, lb.Cp)
+            P.add(L.OP_PACK, f"pack.{l.name}.bwd", W=W, out=lb.wb, O=l.cin, I=l.cout, Opad=lb.Kc, Ipad=lb.Cp,
+                  ntaps=k, nphase=1, o_stride=l.cout * k, i_stride=k, k_stride=1,
+                  tapmap=[list(range(k)) + [-1] * (L.MAX_TAPS - k), [-1] * L.MAX_TAPS], bias=None, out_bias=None)
+        elif l.stride == 1:
+            # dA[b,i,c] = sum_k sum_n dpre[b, i + p - k, n] W[n,c,k]
+            offs = [t - (k - 1 - l.pad) for t in range(k)]
+            lb.bwd_taps, lb.bwd_stride, lb.bwd_nphase = offs, 1, 1
+            lb.wb = self._zeros(lb.Kc, k, lb.Cp)
+            P.add(L.OP_PACK, f"pack.{l.name}.bwd", W=W, out=lb.wb, O=l.cin, I=l.cout, Opad=lb.Kc, Ipad=lb.Cp,
+                  ntaps=k, nphase=1, o_stride=k, i_stride=l.cin * k, k_stride=1,
+                  tapmap=[[l.pad - o for o in offs] + [-1] * (L.MAX_TAPS - k), [-1] * L.MAX_TAPS], bias=None,
+                  out_bias=None)
+        else:
+            # stride 2: input row i = 2m + ph gets dpre[b, m + off, n] W[n,c,k] with k = ph + p - 2 off
+            assert l.stride == 2
+            cand = sorted({(ph + l.pad - kk) // 2 for ph in (0, 1) for kk in range(k) if (ph + l.pad - kk) % 2 == 0})
+            lb.bwd_taps, lb.bwd_stride, lb.bwd_nphase = cand, 1, 2
+            tm = [[(ph + l.pad - 2 * o) for o in cand] for ph in (0, 1)]
+            tm = [[kk if 0 <= kk < k else -1 for kk in row] + [-1] * (L.MAX_TAPS - len(cand)) for row in tm]
+            lb.wb = self._zeros(2 * lb.Kc, len(cand), lb.Cp)
+            P.add(L.OP_PACK, f"pack.{l.name}.bwd", W=W, out=lb.wb, O=l.cin, I=l.cout, Opad=lb.Kc, Ipad=lb.Cp,
+                  ntaps=len(cand), nphase=2, o_stride=k, i_stride=l.cin * k, k_stride=1, tapmap=tm, bias=None,
+                  out_bias=None)
+
+    def _needs_dgrad(self, l: Layer) -> bool:
+        return any(isinstance(f.src, Layer) for f in l.feeds)
+
+    # ---- forward -----------------------------------------------------------------------------
+    def _emit_input(self, l: Layer):
+        P, B, lb = self.prog, self.B, self.bufs[l.name]
+        f0 = l.feeds[0]
+        site_shape = (B, l.La, l.cin)
+        if f0.src == "x":
+            P.add(L.OP_PREP, f"prep.{l.name}", src=self.x, out=lb.a, kind=L.SRC_NCL, B=B, L=l.La, C=l.cin, ld=lb.Kc,
+                  Cfill=lb.Kc, src_ld=0, drop=self._drop(l.drop_site, site_shape), out_f32=0)
+            return
+        if f0.src == "motion":
+            Bg = B // self.groups
+            drop = self._drop(l.drop_site, site_shape)
+            for g in range(self.groups):
+                d = dict(drop)
+                a_g = lb.a[g * Bg:(g + 1) * Bg]
+                if d["mode"] == L.DROP_MASK:
+                    d["mask"] = self.masks[l.drop_site][g * Bg:(g + 1) * Bg]
+                elif d["mode"] == L.DROP_PHILOX:
+                    d["site"] = d["site"] + 1000 * g   # independent streams for the fake / real halves
+                P.add(L.OP_PREP, f"motion.{l.name}.{g}", src=self.motion_src[g], out=a_g, kind=L.SRC_MOTION, B=Bg,
+                      L=l.La, C=l.cin, ld=lb.Kc, Cfill=lb.Kc, src_ld=0, drop=d, out_f32=0)
+            return
+        if f0.src == "feats":
+            if self.spec.feats == "image":
+                P.add(L.OP_PREP, f"prep.{l.name}", src=self.feats, out=lb.a, kind=L.SRC_ROWS, B=B, L=l.La, C=l.cin,
+                      ld=lb.Kc, Cfill=lb.Kc, src_ld=l.cin, drop=self._drop(l.drop_site, site_shape), out_f32=0)
+            else:
+                P.add(L.OP_PREP, f"prep.{l.name}", src=self.feats, out=lb.a, kind=L.SRC_BCAST, B=B, L=l.La, C=l.cin,
+                      ld=lb.Kc, Cfill=lb.Kc, src_ld=l.cin, drop=self._drop(l.drop_site, site_shape), out_f32=0)
+            return
+        # BN outputs of producer layers (+ residual / up-sampling / pooling), then this block's dropout
+        cuts = sorted({f.dst_coff for f in l.feeds} | {f.dst_coff + f.src.cout for f in l.feeds})
+        assert cuts[0] == 0 and cuts[-1] == l.cin, (l.name, cuts, l.cin)
+        drop = self._drop(l.drop_site, site_shape)
+        for s, e in zip(cuts[:-1], cuts[1:]):
+            srcs = [f for f in l.feeds if f.dst_coff <= s and e <= f.dst_coff + f.src.cout]
+            assert 1 <= len(srcs) <= 2, (l.name, s, e)
+            srcs.sort(key=lambda f: f.rowmap == L.ROW_IDENT)   # non-identity source first (reference add order)
+            src_d = [self._bn_src(f.src, f.rowmap, s - f.dst_coff) for f in srcs]
+            while len(src_d) < 2:
+                src_d.append({})
+            last = e == l.cin
+            P.add(L.OP_BN_APPLY, f"apply.{l.name}[{s}:{e}]", src=src_d, nsrc=len(srcs), out=lb.a, out_ld=lb.Kc,
+                  out_coff=s, B=B, L=l.La, C=e - s, Cfill=(lb.Kc - s) if last else (e - s), groups=self.groups,
+                  drop=drop, drop_C=l.cin, drop_coff=s)
+
+    def _emit_fwd_gemm(self, l: Layer):
+        P, B, lb = self.prog, self.B, self.bufs[l.name]
+        is_out = l is self.out_layer
+        out = self.out_blc if is_out else lb.z
+        ldo = out.shape[-1]
+        taps = lb.fwd_taps
+        common = dict(A=lb.a, W=lb.wf, bias=lb.bias, out=out, B=B, La=l.La, lda=lb.Kc, ldo=ldo, out_coff=0, Kc=lb.Kc,
+                      Nvalid=l.cout, ntaps=len(taps), tap_off=taps + [0] * (L.MAX_TAPS - len(taps)), act=l.act,
+                      post_scale=None, post_shift=None, out_f32=1 if is_out else 0, drop=no_drop(), drop_C=0)
+        if l.kind == "convT":
+            P.add(L.OP_GEMM, f"gemm.{l.name}", Lo=l.La, Npad=2 * lb.Cp, stride=1, nphase=2, Lo_actual=2 * l.La, **common)
+        else:
+            P.add(L.OP_GEMM, f"gemm.{l.name}", Lo=l.Lo, Npad=lb.Cp, stride=l.stride, nphase=1, Lo_actual=l.Lo, **common)
+
+    def _emit_bn_stats(self, l: Layer):
+        P, st, lb = self.prog, self.store, self.bufs[l.name]
+        rows = self.B * lb.Lz
+        i = P.add(L.OP_BN_STATS, f"stats.{l.name}", z=lb.z, ld=lb.Cp, C=l.cout, rows_per_group=rows // self.groups,
+                  groups=self.groups, mean=lb.mean, invstd=lb.invstd, running_mean=st.b(l.bnkey + ".running_mean"),
+                  running_var=st.b(l.bnkey + ".running_var"),
+                  num_batches_tracked=st.nbt_view(l.bnkey + ".num_batches_tracked"), momentum=l.momentum, eps=BN_EPS,
+                  partial=None, ticket=self._ticket(), update_all_groups=1 if self.groups > 1 else 0)
+        self._need_partial(i, _bn_partial_floats(rows, l.cout, self.groups))
+
+    # ---- backward ----------------------------------------------------------------------------
+    def _emit_bwd(self, l: Layer):
+        P, st, B, lb = self.prog, self.store, self.B, self.bufs[l.name]
+        rows = B * lb.Lz
+        if l is self.out_layer:
+            # dpre is provided by the loss (or by an external output gradient); bias grad = column sums
+            i = P.add(L.OP_COLSUM, f"dbias.{l.name}", src=lb.dpre, out=st.g(l.wkey + ".bias"), partial=None,
+                      ticket=self._ticket(), rows=rows, ld=lb.Cp, C=l.cout, f32=0)
+            self._need_partial(i, _ceil_div(rows, 64) * l.cout)
+        else:
+            lb.dpre = self._zeros(B, lb.Lz, lb.Cp)
+            gs = []
+            for (c, f) in self.consumers[l.name]:
+                cb = self.bufs[c.name]
+                gs.append({"g": cb.g, "ld": cb.Kc, "coff": f.dst_coff, "rowmap": f.rowmap, "L_src": c.La, "f32": 0})
+            assert 1 <= len(gs) <= 2, (l.name, len(gs))
+            while len(gs) < 2:
+                gs.append({})
+            lb.sums = self._zeros(self.groups, l.cout, 2, dtype=torch.float32)
+            i = P.add(L.OP_BN_BWD, f"bn_bwd.{l.name}", gsrc=gs, ngsrc=len(self.consumers[l.name]),
+                      bn=self._bn_src(l), dpre=lb.dpre, ld_dpre=lb.Cp, Cfill=lb.Cp, B=B, L=lb.Lz, C=l.cout,
+                      groups=self.groups, act=l.act, dgamma=st.g(l.bnkey + ".weight"), dbeta=st.g(l.bnkey + ".bias"),
+                      dbias=st.g(l.wkey + ".bias"), sums=lb.sums, partial=None, ticket=self._ticket())
+            self._need_partial(i, _bn_partial_floats(rows, l.cout, self.groups))
+        # weight gradient
+        k = l.k
+        if l.kind == "convT":
+            wg = dict(P=lb.a, Q=lb.dpre, Lp=l.La, Lq=lb.Lz, ldp=lb.Kc, ldq=lb.Cp, Mpad=lb.Kc, Npad=lb.Cp, Mvalid=l.cin,
+                      Nvalid=l.cout, ntaps=k, stride=2, tap_off=[kk - l.pad for kk in range(k)] + [0] * (L.MAX_TAPS - k))
+        else:
+            wg = dict(P=lb.dpre, Q=lb.a, Lp=lb.Lz, Lq=l.La, ldp=lb.Cp, ldq=lb.Kc, Mpad=lb.Cp, Npad=lb.Kc, Mvalid=l.cout,
+                      Nvalid=l.cin, ntaps=k, stride=l.stride,
+                      tap_off=[t - l.pad for t in range(k)] + [0] * (L.MAX_TAPS - k))
+        i = P.add(L.OP_WGRAD, f"wgrad.{l.name}", dW=st.g(l.wkey + ".weight"), partial=None, B=B, splits=0, **wg)
+        self._wg_need = max(self._wg_need, _wgrad_ws_bytes(self.prog.recs[i], self.dtype))
+        self._pending_partial.append((i, "partial"))
+        # input gradient (with the dropout mask of this block's site)
+        if not self._needs_dgrad(l):
+            return
+        lb.g = self._zeros(B, l.La, lb.Kc)
+        taps = lb.bwd_taps
+        drop = self._drop(l.drop_site, (B, l.La, l.cin))
+        common = dict(A=lb.dpre, W=lb.wb, bias=None, out=lb.g, B=B, La=lb.Lz, lda=lb.Cp, ldo=lb.Kc, out_coff=0,
+                      Kc=lb.Cp, Nvalid=l.cin, ntaps=len(taps), tap_off=taps + [0] * (L.MAX_TAPS - len(taps)),
+                      act=L.ACT_NONE, post_scale=None, post_shift=None, out_f32=0, drop=drop, drop_C=l.cin)
+        if lb.bwd_nphase == 2:
+            P.add(L.OP_GEMM, f"dgrad.{l.name}", Lo=_ceil_div(l.La, 2), Npad=2 * lb.Kc, stride=1, nphase=2,
+                  Lo_actual=l.La, **common)
+        else:
+            P.add(L.OP_GEMM, f"dgrad.{l.name}", Lo=l.La, Npad=lb.Kc, stride=lb.bwd_stride, nphase=1, Lo_actual=l.La,
+                  **common)
+
+    # ---- execution ---------------------------------------------------------------------------
+    def pack(self):
+        self.prog.run("pack")
+        self._packed_version = self.store.version
+
+    def ensure_packed(self):
+        if getattr(self, "_packed_version", None) != self.store.version:
+            self.pack()
+
+    def forward(self):
+        self.ensure_packed()
+        self.prog.run("fwd")
+
+    def backward(self):
+        self.prog.run("bwd")
+
+
+def _ceil_div(a, b):
+    return (a + b - 1) // b
+
+
+def _bn_partial_floats(rows, C, groups):
+    rpg = rows // groups
+    return _ceil_div(rpg, 64) * groups * C * 2
+
+
+def _wgrad_ws_bytes(rec, dtype) -> int:
+    """Upper bound of the wgrad split-K workspace (mirrors b2h_wgrad_workspace_bytes: <= 65 planes)."""
+    f = rec.f
+    planes = f["ntaps"] * f["Mpad"] * f["Npad"] * 4
+    rows = f["B"] * f["Lp"]
+    max_splits = min(64, max(1, rows // 64))
+    return (max_splits + 1) * planes

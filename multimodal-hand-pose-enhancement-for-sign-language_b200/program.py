@@ -1,0 +1,141 @@
+"""Op records and recorded programs.
+
+A `Program` is an ordered list of op records (kind + fields holding torch tensors / scalars) with
+named segments.  `finalize()` lowers every record to its C descriptor (include/b2h_abi.h) inside a
+native `b2h_program`; `run(segment)` replays a segment on the current CUDA stream with ONE C call,
+which makes the whole generator / discriminator step a single capturable launch sequence.
+
+The records are plain data so that tests can interpret the very same program with the CPU op
+restatements in oracle/ops_emul.py (graph-logic check without a GPU).  The product path never does
+that: `run()` always goes through libb2h.so and raises if it is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from contextlib import contextmanager
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import _lib as L
+
+
+class OpRec:
+    __slots__ = ("kind", "f", "tag")
+
+    def __init__(self, kind: int, tag: str, fields: dict):
+        self.kind, self.tag, self.f = kind, tag, fields
+
+    def __repr__(self):
+        return f"OpRec({L.OP_STRUCT[self.kind].__name__}, {self.tag})"
+
+
+def _ptr(v):
+    if v is None:
+        return None
+    if isinstance(v, torch.Tensor):
+        return v.data_ptr()
+    return int(v)
+
+
+def _fill_struct(st, fields: dict):
+    """Recursively copy a dict of python values / tensors into a ctypes Structure."""
+    for name, ctype in st._fields_:
+        if name not in fields:
+            continue
+        v = fields[name]
+        if isinstance(ctype, type) and issubclass(ctype, C.Structure):
+            _fill_struct(getattr(st, name), v or {})
+        elif isinstance(ctype, type) and issubclass(ctype, C.Array):
+            arr = getattr(st, name)
+            elem = ctype._type_
+            if isinstance(elem, type) and issubclass(elem, C.Structure):
+                for i, item in enumerate(v):
+                    _fill_struct(arr[i], item)
+            elif isinstance(elem, type) and issubclass(elem, C.Array):
+                for i, row in enumerate(v):
+                    for j, x in enumerate(row):
+                        arr[i][j] = x
+            else:
+                for i, x in enumerate(v):
+                    arr[i] = x
+        elif ctype is L.vp:
+            setattr(st, name, _ptr(v))
+        else:
+            setattr(st, name, v)
+    return st
+
+
+def lower(rec: OpRec):
+    st = L.OP_STRUCT[rec.kind]()
+    unknown = set(rec.f) - {n for n, _ in st._fields_}
+    if unknown:
+        raise KeyError(f"{rec}: unknown fields {sorted(unknown)}")
+    return _fill_struct(st, rec.f)
+
+
+def no_drop():
+    return {"mode": L.DROP_NONE, "site": 0, "mask": None, "state": None}
+
+
+class Program:
+    def __init__(self, dtype: int, device: torch.device):
+        self.dtype = dtype
+        self.device = torch.device(device)
+        self.recs: List[OpRec] = []
+        self.segments: Dict[str, Tuple[int, int]] = {}
+        self._handle = None
+        self._keep = []  # tensors referenced only by pointer
+
+    @property
+    def act_dtype(self):
+        return torch.bfloat16 if self.dtype == L.BF16 else torch.float32
+
+    def add(self, op_kind: int, tag: str = "", /, **fields) -> int:
+        assert self._handle is None, "program already finalized"
+        self.recs.append(OpRec(op_kind, tag, fields))
+        return len(self.recs) - 1
+
+    @contextmanager
+    def segment(self, name: str):
+        start = len(self.recs)
+        yield
+        assert name not in self.segments, name
+        self.segments[name] = (start, len(self.recs))
+
+    # ---- native execution -------------------------------------------------------------------
+    def finalize(self):
+        if self.device.type != "cuda":
+            raise L.B2HError("programs execute on a CUDA device only (no CPU fallback)")
+        lib = L.load()
+        L.require_device()
+        h = lib.b2h_program_create(self.dtype)
+        if not h:
+            raise L.B2HError("b2h_program_create failed: " + lib.b2h_last_error().decode())
+        self._handle = C.c_void_p(h)
+        for rec in self.recs:
+            st = lower(rec)
+            rc = lib.b2h_program_add(self._handle, rec.kind, C.byref(st))
+            L.check(rc, f"b2h_program_add[{rec}]")
+        return self
+
+    def run(self, segment: Optional[str] = None, stream: Optional[int] = None):
+        if self._handle is None:
+            self.finalize()
+        first, end = self.segments[segment] if segment is not None else (0, len(self.recs))
+        if end == first:
+            return
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+        rc = L.load().b2h_program_run(self._handle, first, end - first, C.c_void_p(stream))
+        L.check(rc, f"b2h_program_run[{segment}]")
+
+    def launches(self) -> int:
+        return int(L.load().b2h_program_launches(self._handle)) if self._handle else 0
+
+    def __del__(self):
+        try:
+            if self._handle is not None and L._lib is not None:
+                L._lib.b2h_program_destroy(self._handle)
+        except Exception:
+            pass

@@ -1,0 +1,396 @@
+"""ORACLE (test infrastructure only) -- CPU restatement of every libb2h op contract.
+
+Each function interprets one op record (see b2h_b200/program.py) with plain torch on CPU, following the
+contract written in include/b2h_abi.h.  Two uses, both in tests only:
+  * GPU tests check each CUDA kernel against its restatement on random inputs;
+  * CPU tests interpret whole recorded programs (graph wiring, backward formulas) and compare the
+    result with oracle/ref_models.py, so the host logic is validated without a GPU.
+The product never imports this module.
+
+Arithmetic is fp32 with the results rounded to the activation dtype on store, like the kernels.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict
+
+import torch
+
+# mirrored constants of include/b2h_abi.h
+ACT_NONE, ACT_LEAKY, ACT_RELU = 0, 1, 2
+ROW_IDENT, ROW_UP2, ROW_POOL2, ROW_BCAST = 0, 1, 2, 3
+SRC_NCL, SRC_ROWS, SRC_BCAST, SRC_MOTION = 0, 1, 2, 3
+DROP_NONE, DROP_MASK, DROP_PHILOX = 0, 1, 2
+(OP_GEMM, OP_WGRAD, OP_BN_STATS, OP_BN_APPLY, OP_BN_BWD, OP_PREP, OP_TO_NCL, OP_L1, OP_MSE, OP_COLSUM,
+ OP_ADAM, OP_PACK, OP_BN_FOLD, OP_ROT6D, OP_FILL) = range(1, 16)
+
+
+def _act(x, act):
+    if act == ACT_LEAKY:
+        return torch.where(x > 0, x, x * 0.2)
+    if act == ACT_RELU:
+        return torch.clamp_min(x, 0)
+    return x
+
+
+def _dact(out, act):
+    if act == ACT_LEAKY:
+        return torch.where(out > 0, torch.ones_like(out), torch.full_like(out, 0.2))
+    if act == ACT_RELU:
+        return (out > 0).to(out.dtype)
+    return torch.ones_like(out)
+
+
+def _drop_scale(drop, rows, C, row0=0):
+    """(rows, C) multiplier of a dropout site restricted to rows [row0, row0+rows)."""
+    if not drop or drop.get("mode", 0) == DROP_NONE:
+        return None
+    if drop["mode"] == DROP_MASK:
+        m = drop["mask"].reshape(-1, C)[row0:row0 + rows]
+        return m.to(torch.float32) * 2.0
+    raise NotImplementedError("Philox dropout is not emulated on CPU (statistical test on GPU)")
+
+
+def _rows2d(t):
+    return t.reshape(-1, t.shape[-1])
+
+
+# ---------------------------------------------------------------------------------------------
+def gemm(f: Dict):
+    A = f["A"].to(torch.float32)                      # (B, La, lda)
+    B, La, Kc = f["B"], f["La"], f["Kc"]
+    Lo, nt, stride = f["Lo"], f["ntaps"], f["stride"]
+    W = f["W"].to(torch.float32).reshape(f["Npad"], nt, Kc)
+    A = A.reshape(B, La, -1)[:, :, :Kc]
+    acc = torch.zeros(B, Lo, f["Npad"])
+    lo = torch.arange(Lo)
+    for t in range(nt):
+        li = lo * stride + f["tap_off"][t]
+        ok = (li >= 0) & (li < La)
+        if not ok.any():
+            continue
+        rows = torch.zeros(B, Lo, Kc)
+        rows[:, ok] = A[:, li[ok]]
+        acc += rows @ W[:, t, :].T
+    nph = f["nphase"]
+    half = f["Npad"] // nph
+    Nv, Lact = f["Nvalid"], f["Lo_actual"]
+    out = f["out"]
+    ldo = out.shape[-1]
+    out2 = out.reshape(B, Lact, ldo)
+    assert ldo == f["ldo"]
+    for ph in range(nph):
+        v = acc[:, :, ph * half: ph * half + Nv]
+        if f.get("bias") is not None:
+            v = v + f["bias"][:Nv]
+        v = _act(v, f["act"])
+        if f.get("post_scale") is not None:
+            v = v * f["post_scale"][:Nv] + f["post_shift"][:Nv]
+        rows_act = lo * nph + ph
+        ok = rows_act < Lact
+        v = v[:, ok]
+        ra = rows_act[ok]
+        drop = f.get("drop")
+        if drop and drop.get("mode", 0) != DROP_NONE:
+            C = f["drop_C"]
+            m = _drop_scale(drop, B * Lact, C).reshape(B, Lact, C)[:, ra, :]
+            nn = min(Nv, C)
+            v = v.clone()
+            v[:, :, :nn] = v[:, :, :nn] * m[:, :, :nn]
+        out2[:, ra, f["out_coff"]: f["out_coff"] + Nv] = v.to(out.dtype)
+
+
+def wgrad(f: Dict):
+    B, Lp, Lq = f["B"], f["Lp"], f["Lq"]
+    P = f["P"].to(torch.float32).reshape(B, Lp, -1)[:, :, :f["Mvalid"]]
+    Q = f["Q"].to(torch.float32).reshape(B, Lq, -1)[:, :, :f["Nvalid"]]
+    dW = f["dW"].reshape(f["Mvalid"], f["Nvalid"], f["ntaps"])
+    r = torch.arange(Lp)
+    for t in range(f["ntaps"]):
+        rq = r * f["stride"] + f["tap_off"][t]
+        ok = (rq >= 0) & (rq < Lq)
+        if not ok.any():
+            dW[:, :, t] = 0
+            continue
+        Pm = P[:, ok].reshape(-1, f["Mvalid"])
+        Qm = Q[:, rq[ok]].reshape(-1, f["Nvalid"])
+        dW[:, :, t] = Pm.T @ Qm
+
+
+def bn_stats(f: Dict):
+    C, G, rpg = f["C"], f["groups"], f["rows_per_group"]
+    z = _rows2d(f["z"]).to(torch.float32)[:, :C].reshape(G, rpg, C)
+    for g in range(G):
+        mean = z[g].mean(0)
+        var_b = z[g].var(0, unbiased=False)
+        f["mean"][g] = mean
+        f["invstd"][g] = 1.0 / torch.sqrt(var_b + f["eps"])
+        if f.get("running_mean") is not None and (g == 0 or f["update_all_groups"]):
+            var_u = z[g].var(0, unbiased=True) if rpg > 1 else var_b
+            m = f["momentum"]
+            f["running_mean"].mul_(1 - m).add_(m * mean)
+            f["running_var"].mul_(1 - m).add_(m * var_u)
+    if f.get("running_mean") is not None and f.get("num_batches_tracked") is not None:
+        f["num_batches_tracked"] += G if f["update_all_groups"] else 1
+
+
+def _affine(src, C, g):
+    gamma = src["gamma"][:C] if src.get("gamma") is not None else torch.ones(C)
+    beta = src["beta"][:C] if src.get("beta") is not None else torch.zeros(C)
+    if src["use_running"]:
+        mean, invstd = src["running_mean"][:C], 1.0 / torch.sqrt(src["running_var"][:C] + src["eps"])
+    else:
+        mean, invstd = src["mean"][g, :C], src["invstd"][g, :C]
+    s = invstd * gamma
+    return s, beta - mean * s
+
+
+def _bn_src_eval(src, B, L, C, groups, Cs=None):
+    """(B, L, C) tensor of BN(src) under the source's row map."""
+    z = src["z"].to(torch.float32)
+    Ls = src["L_src"]
+    z = z.reshape(B, Ls, -1)[:, :, src["coff"]: src["coff"] + C]
+    Bg = B // groups
+    y = torch.empty_like(z)
+    # the affine of the SOURCE layer is indexed by the source's own channel index: callers pass slices
+    for g in range(groups):
+        s, t = _affine(_slice_affine(src, C), C, g)
+        y[g * Bg:(g + 1) * Bg] = z[g * Bg:(g + 1) * Bg] * s + t
+    rm = src["rowmap"]
+    if rm == ROW_IDENT:
+        assert Ls == L
+        return y
+    if rm == ROW_UP2:
+        return y.repeat_interleave(2, dim=1)[:, :L]
+    if rm == ROW_POOL2:
+        assert L == Ls // 2
+        y0, y1 = y[:, 0:2 * L:2], y[:, 1:2 * L:2]
+        return torch.where(y1 > y0, y1, y0)
+    if rm == ROW_BCAST:
+        return y[:, :1].expand(B, L, C)
+    raise ValueError(rm)
+
+
+def _slice_affine(src, C):
+    """The per-channel BN arrays of a source are stored for ALL its channels; a consumer segment that
+    starts at channel `coff` of the source must read them at the same offset."""
+    o = src["coff"]
+    d = dict(src)
+    for k in ("gamma", "beta", "running_mean", "running_var"):
+        if d.get(k) is not None:
+            d[k] = d[k][o:o + C]
+    for k in ("mean", "invstd"):
+        if d.get(k) is not None:
+            d[k] = d[k][:, o:o + C]
+    return d
+
+
+def bn_apply(f: Dict):
+    B, L, C, G = f["B"], f["L"], f["C"], f["groups"]
+    y = torch.zeros(B, L, C)
+    for i in range(f["nsrc"]):
+        y = y + _bn_src_eval(f["src"][i], B, L, C, G)
+    drop = f.get("drop")
+    if drop and drop.get("mode", 0) != DROP_NONE:
+        m = _drop_scale(drop, B * L, f["drop_C"]).reshape(B, L, f["drop_C"])
+        y = y * m[:, :, f["drop_coff"]: f["drop_coff"] + C]
+    out = f["out"].reshape(B, L, -1)
+    o = f["out_coff"]
+    out[:, :, o:o + C] = y.to(out.dtype)
+    out[:, :, o + C:o + f["Cfill"]] = 0
+
+
+def _grad_src(gs, B, L, C, bnf, aff):
+    """dy contribution (B, L, C) of one gradient source."""
+    g = gs["g"].to(torch.float32).reshape(B, gs["L_src"], -1)[:, :, gs["coff"]: gs["coff"] + C]
+    rm = gs["rowmap"]
+    if rm == ROW_IDENT:
+        return g
+    if rm == ROW_UP2:
+        Ls = gs["L_src"]
+        out = torch.zeros(B, L, C)
+        n0 = (Ls + 1) // 2
+        out[:, :n0] += g[:, 0::2]
+        out[:, :Ls // 2] += g[:, 1::2]
+        return out
+    if rm == ROW_POOL2:
+        z, s, t = aff
+        y = z * s + t
+        Lp = gs["L_src"]
+        y0, y1 = y[:, 0:2 * Lp:2], y[:, 1:2 * Lp:2]
+        sel1 = y1 > y0
+        out = torch.zeros(B, L, C)
+        out[:, 0:2 * Lp:2] = torch.where(sel1, torch.zeros_like(g), g)
+        out[:, 1:2 * Lp:2] = torch.where(sel1, g, torch.zeros_like(g))
+        return out
+    raise ValueError(rm)
+
+
+def bn_bwd(f: Dict):
+    B, L, C, G = f["B"], f["L"], f["C"], f["groups"]
+    bn = f["bn"]
+    z = bn["z"].to(torch.float32).reshape(B, L, -1)[:, :, bn["coff"]: bn["coff"] + C]
+    Bg = B // G
+    dpre = f["dpre"].reshape(B, L, -1)
+    dgamma, dbeta, dbias = torch.zeros(C), torch.zeros(C), torch.zeros(C)
+    for g in range(G):
+        sl = slice(g * Bg, (g + 1) * Bg)
+        mean, invstd = bn["mean"][g, :C], bn["invstd"][g, :C]
+        gamma = bn["gamma"][:C] if bn.get("gamma") is not None else torch.ones(C)
+        beta = bn["beta"][:C] if bn.get("beta") is not None else torch.zeros(C)
+        s = invstd * gamma
+        t = beta - mean * s
+        zg = z[sl]
+        dy = torch.zeros(Bg, L, C)
+        for i in range(f["ngsrc"]):
+            gs = dict(f["gsrc"][i])
+            gfull = gs["g"].reshape(B, gs["L_src"], -1)
+            gs["g"] = gfull[sl]
+            dy = dy + _grad_src(gs, Bg, L, C, bn, (zg, s, t))
+        zh = (zg - mean) * invstd
+        n = Bg * L
+        sdy = dy.sum((0, 1))
+        sdyz = (dy * zh).sum((0, 1))
+        dz = s * (dy - sdy / n - zh * (sdyz / n))
+        dp = dz * _dact(zg, f["act"])
+        dpre[sl, :, :C] = dp.to(dpre.dtype)
+        dpre[sl, :, C:f["Cfill"]] = 0
+        dgamma += sdyz
+        dbeta += sdy
+        dbias += dp.sum((0, 1))
+    if f.get("dgamma") is not None:
+        f["dgamma"].copy_(dgamma)
+    if f.get("dbeta") is not None:
+        f["dbeta"].copy_(dbeta)
+    if f.get("dbias") is not None:
+        f["dbias"].copy_(dbias)
+
+
+def prep(f: Dict):
+    B, L, C = f["B"], f["L"], f["C"]
+    src = f["src"]
+    k = f["kind"]
+    if k == SRC_NCL:
+        v = src.reshape(B, C, L).permute(0, 2, 1)
+    elif k == SRC_MOTION:
+        x = src.reshape(B, C, L + 1)
+        v = (x[:, :, :1] - x[:, :, :-1]).permute(0, 2, 1)
+    elif k == SRC_ROWS:
+        v = src.reshape(B * L, -1)[:, :C].reshape(B, L, C)
+    else:
+        v = src.reshape(B, -1)[:, :C].unsqueeze(1).expand(B, L, C)
+    v = v.to(torch.float32)
+    m = _drop_scale(f.get("drop"), B * L, C)
+    if m is not None:
+        v = v * m.reshape(B, L, C)
+    out = f["out"].reshape(B, L, -1)
+    out[:, :, :C] = v.to(out.dtype)
+    out[:, :, C:f["Cfill"]] = 0
+
+
+def to_ncl(f: Dict):
+    B, L, C = f["B"], f["L"], f["C"]
+    f["dst"].reshape(B, C, L).copy_(f["src"].reshape(B, L, -1)[:, :, :C].permute(0, 2, 1).to(torch.float32))
+
+
+def l1(f: Dict):
+    B, C, L = f["B"], f["C"], f["L"]
+    o, g = f["out"].reshape(B, C, L), f["gt"].reshape(B, C, L)
+    d = o - g
+    f["loss"][0] = d.abs().double().mean().float()
+    if f.get("dout") is not None:
+        gv = f["gscale"] / d.numel()
+        dout = f["dout"].reshape(B, L, -1)
+        dout[:, :, :C] = (torch.sign(d) * gv).permute(0, 2, 1).to(dout.dtype)
+        dout[:, :, C:f["Cfill"]] = 0
+
+
+def mse(f: Dict):
+    G, n, ld = f["groups"], f["n"], f["ld"]
+    s = f["score"].reshape(-1)[: G * n * ld: ld].reshape(G, n)
+    total = 0.0
+    for g in range(G):
+        diff = s[g] - f["target"][g]
+        total += float((diff.double() ** 2).mean())
+        if f.get("dscore") is not None:
+            f["dscore"].reshape(-1)[g * n * ld:(g + 1) * n * ld: ld] = 2.0 * diff / n
+    f["loss"][0] = total
+    if f.get("total") is not None:
+        f["total"][0] = total + (float(f["add"][0]) if f.get("add") is not None else 0.0)
+
+
+def colsum(f: Dict):
+    src = _rows2d(f["src"]).to(torch.float32)[: f["rows"], : f["C"]]
+    f["out"].copy_(src.double().sum(0).float())
+
+
+def adam(f: Dict):
+    f["step"] += 1
+    t = int(f["step"][0])
+    b1, b2, lr, eps = f["beta1"], f["beta2"], f["lr"], f["eps"]
+    g = f["g"] * f["gscale"]
+    f["m"].lerp_(g, 1 - b1)
+    f["v"].mul_(b2).addcmul_(g, g, value=1 - b2)
+    bc1, bc2 = 1 - b1 ** t, 1 - b2 ** t
+    denom = (f["v"].sqrt() / math.sqrt(bc2)).add_(eps)
+    f["p"].addcdiv_(f["m"], denom, value=-(lr / bc1))
+
+
+def pack(f: Dict):
+    W = f["W"].reshape(-1)
+    nph, Op, nt, Ip = f["nphase"], f["Opad"], f["ntaps"], f["Ipad"]
+    out = torch.zeros(nph, Op, nt, Ip)
+    o = torch.arange(f["O"]).view(-1, 1)
+    i = torch.arange(f["I"]).view(1, -1)
+    for ph in range(nph):
+        for t in range(nt):
+            k = f["tapmap"][ph][t]
+            if k < 0:
+                continue
+            idx = o * f["o_stride"] + i * f["i_stride"] + k * f["k_stride"]
+            out[ph, : f["O"], t, : f["I"]] = W[idx]
+    f["out"].reshape(nph, Op, nt, Ip).copy_(out.to(f["out"].dtype))
+    if f.get("out_bias") is not None:
+        f["out_bias"].zero_()
+        if f.get("bias") is not None:
+            f["out_bias"][: f["O"]] = f["bias"]
+
+
+def bn_fold(f: Dict):
+    C = f["C"]
+    invstd = 1.0 / torch.sqrt(f["running_var"][:C] + f["eps"])
+    s = invstd * (f["gamma"][:C] if f.get("gamma") is not None else 1.0)
+    f["scale"].zero_()
+    f["shift"].zero_()
+    f["scale"][:C] = s
+    f["shift"][:C] = (f["beta"][:C] if f.get("beta") is not None else 0.0) - f["running_mean"][:C] * s
+
+
+def rot6d(f: Dict):
+    f["mat"].reshape(-1, 9).copy_(rot6d_to_mat(f["r6d"].reshape(-1, 6)))
+
+
+def rot6d_to_mat(r6d: torch.Tensor) -> torch.Tensor:
+    """Row-wise restatement of np_rot6d_to_mat (utils/conversion_utils.py:86-107; SURVEY S10: the
+    reference function is only correct one row at a time, which is how it is called at :36-37)."""
+    x_raw, y_raw = r6d[:, 0:3], r6d[:, 3:6]
+    x = x_raw / (x_raw.norm(dim=1, keepdim=True) + 1e-6)
+    z = torch.linalg.cross(x, y_raw)
+    z = z / (z.norm(dim=1, keepdim=True) + 1e-6)
+    y = torch.linalg.cross(z, x)
+    return torch.stack([x, y, z], dim=-1).reshape(-1, 9)
+
+
+def fill(f: Dict):
+    raise NotImplementedError
+
+
+DISPATCH = {OP_GEMM: gemm, OP_WGRAD: wgrad, OP_BN_STATS: bn_stats, OP_BN_APPLY: bn_apply, OP_BN_BWD: bn_bwd,
+            OP_PREP: prep, OP_TO_NCL: to_ncl, OP_L1: l1, OP_MSE: mse, OP_COLSUM: colsum, OP_ADAM: adam,
+            OP_PACK: pack, OP_BN_FOLD: bn_fold, OP_ROT6D: rot6d, OP_FILL: fill}
+
+
+def run_records(recs, first=0, end=None):
+    """Interpret op records [first, end) on CPU."""
+    for rec in recs[first: end if end is not None else len(recs)]:
+        DISPATCH[rec.kind](rec.f)
