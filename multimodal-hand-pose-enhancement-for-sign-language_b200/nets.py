@@ -336,8 +336,9 @@ class NetPlan:
     """One network at a fixed batch / length / precision / mode, lowered to a recorded program."""
 
     def __init__(self, spec: NetSpec, store: ParamStore, B: int, T: int, dtype: int, device,
-                 train: bool, groups: int = 1, drop_mode: str = "philox", need_input_grad: bool = False,
-                 drop_state: Optional[torch.Tensor] = None, site_base: int = 0):
+                 train: bool, groups: int = 1, drop_mode: str = "philox",
+                 drop_state: Optional[torch.Tensor] = None, site_base: int = 0,
+                 motion_src: Optional[Sequence[torch.Tensor]] = None):
         assert drop_mode in ("none", "mask", "philox")
         self.spec, self.store, self.B, self.T, self.dtype = spec, store, B, T, dtype
         self.device = torch.device(device)
@@ -356,6 +357,8 @@ class NetPlan:
         self._wg_need = 16
         self._pending_partial: List[Tuple[int, str]] = []
         self._site_base = site_base
+        self._motion_src_arg = list(motion_src) if motion_src is not None else None
+        self.bwd_marks: List[Tuple[str, int]] = []   # (layer name, first op index) inside the bwd segment
         self._build()
 
     # ---- helpers -----------------------------------------------------------------------------
@@ -455,8 +458,14 @@ class NetPlan:
             self.x = self._zeros(B, spec.in_dim, T, dtype=torch.float32)
         else:
             # discriminator: `groups` NCL tensors of (B/groups, C, T) whose calc_motion it scores
-            self.motion_src = [self._zeros(B // self.groups, spec.in_dim, T, dtype=torch.float32)
-                               for _ in range(self.groups)]
+            if self._motion_src_arg is not None:
+                self.motion_src = self._motion_src_arg
+                assert len(self.motion_src) == self.groups
+                for t in self.motion_src:
+                    assert tuple(t.shape) == (B // self.groups, spec.in_dim, T) and t.dtype == torch.float32
+            else:
+                self.motion_src = [self._zeros(B // self.groups, spec.in_dim, T, dtype=torch.float32)
+                                   for _ in range(self.groups)]
         if spec.feats == "text":
             self.feats = self._zeros(B, 512, dtype=torch.float32)
         elif spec.feats == "image":
@@ -484,6 +493,7 @@ class NetPlan:
             olb.dpre = self._zeros(B, olb.Lz, olb.Cp)
             with P.segment("bwd"):
                 for l in reversed(spec.layers):
+                    self.bwd_marks.append((l.name, len(P.recs)))
                     self._emit_bwd(l)
         # shared workspaces, patched into the records
         self.partial = self._zeros(self._partial_need, dtype=torch.float32)

@@ -85,7 +85,7 @@ class Program:
         self.recs: List[OpRec] = []
         self.segments: Dict[str, Tuple[int, int]] = {}
         self._handle = None
-        self._keep = []  # tensors referenced only by pointer
+        self.segment_launches: Dict[str, int] = {}  # kernel launches of the last run of each segment
 
     @property
     def act_dtype(self):
@@ -129,6 +129,15 @@ class Program:
             stream = torch.cuda.current_stream(self.device).cuda_stream
         rc = L.load().b2h_program_run(self._handle, first, end - first, C.c_void_p(stream))
         L.check(rc, f"b2h_program_run[{segment}]")
+        self.segment_launches[segment or "*"] = self.launches()
+
+    def run_range(self, first: int, end: int, stream: Optional[int] = None):
+        if self._handle is None:
+            self.finalize()
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+        rc = L.load().b2h_program_run(self._handle, first, end - first, C.c_void_p(stream))
+        L.check(rc, f"b2h_program_run[{first}:{end}]")
 
     def launches(self) -> int:
         return int(L.load().b2h_program_launches(self._handle)) if self._handle else 0

@@ -1,0 +1,289 @@
+"""GAN training step (train_gan.py:215-299) and batched inference (inference.py:96-121) as recorded
+programs of libb2h ops, replayed on one stream and captured in CUDA graphs.
+
+  generator step   G fwd (train) -> calc_motion -> D fwd (eval, no grad) -> L1(out, gt) + MSE(score, 1)
+                   -> G bwd -> [bucketed NCCL all-reduce of the flat gradient, overlapped] -> fused Adam
+  discriminator    G fwd (eval, no grad) -> calc_motion(fake), calc_motion(gt) -> ONE grouped D fwd
+  step             (train; separate BN statistics / dropout per group, train_gan.py:240-241) -> MSE+MSE
+                   -> D bwd -> all-reduce -> fused Adam
+
+Reference quirks kept: calc_motion is frame0 - frames[0..T-2]; the adversarial term of
+the generator loss adds a value but no gradient; there is no velocity term.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional
+
+import torch
+
+from . import _lib as L
+from . import nets
+from .program import Program
+
+
+def dtype_of(precision: str) -> int:
+    if precision not in ("fp32", "bf16"):
+        raise ValueError("precision must be 'fp32' or 'bf16'")
+    return L.BF16 if precision == "bf16" else L.F32
+
+
+class FlatAdam:
+    """torch.optim.Adam(lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0) over a ParamStore's flat buffers.
+    `state_dict()` / `load_state_dict()` speak torch.optim.Adam's format (train_gan.py:356-370)."""
+
+    def __init__(self, store: nets.ParamStore, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8):
+        self.store, self.lr, self.betas, self.eps = store, float(lr), (float(betas[0]), float(betas[1])), float(eps)
+        dev = store.device
+        self.m = torch.zeros_like(store.flat)
+        self.v = torch.zeros_like(store.flat)
+        self.step = torch.zeros(1, dtype=torch.int64, device=dev)
+
+    def record(self, prog: Program, gscale: float = 1.0):
+        return prog.add(L.OP_ADAM, "adam", p=self.store.flat, g=self.store.grad, m=self.m, v=self.v, n=self.store.n,
+                        lr=self.lr, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, gscale=float(gscale),
+                        step=self.step)
+
+    def state_dict(self):
+        st = self.store
+        state = {}
+        step = float(self.step.item())
+        for i, (k, shp) in enumerate(st.param_shapes):
+            o, n = st.offsets[k], math.prod(shp)
+            state[i] = {"step": torch.tensor(step), "exp_avg": self.m[o:o + n].view(shp).clone(),
+                        "exp_avg_sq": self.v[o:o + n].view(shp).clone()}
+        group = {"lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": 0, "amsgrad": False,
+                 "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
+                 "params": list(range(len(st.param_shapes)))}
+        return {"state": state if step > 0 else {}, "param_groups": [group]}
+
+    def load_state_dict(self, sd):
+        st = self.store
+        steps = []
+        for i, (k, shp) in enumerate(st.param_shapes):
+            s = sd["state"].get(i)
+            if s is None:
+                continue   # parameter never had a gradient in the reference (dead branch): state stays zero
+            o, n = st.offsets[k], math.prod(shp)
+            self.m[o:o + n].copy_(s["exp_avg"].reshape(-1))
+            self.v[o:o + n].copy_(s["exp_avg_sq"].reshape(-1))
+            steps.append(int(float(s["step"])))
+        if steps:
+            self.step.fill_(max(steps))
+        g = sd["param_groups"][0]
+        self.lr, self.betas, self.eps = float(g["lr"]), tuple(g["betas"]), float(g["eps"])
+
+
+class GanTrainer:
+    """One process = one GPU.  Static device buffers `x`, `y`, `feats` hold the current batch."""
+
+    def __init__(self, variant: str = "v1", in_dim: int = 36, out_dim: int = 252, require_feats: bool = False,
+                 batch_size: int = 256, T: int = 64, precision: str = "bf16", device="cuda", lr: float = 1e-4,
+                 seed: int = 23456, drop_mode: str = "philox", label_smooth: bool = False,
+                 world_size: int = 1, process_group=None, n_buckets: int = 2):
+        self.device = torch.device(device)
+        self.B, self.T, self.precision = batch_size, T, precision
+        self.dtype = dtype_of(precision)
+        self.variant, self.require_feats = variant, require_feats
+        self.world_size, self.pg, self.n_buckets = world_size, process_group, max(1, n_buckets)
+        B = batch_size
+        dev = self.device
+        self.g_spec = nets.generator_spec(variant, in_dim, out_dim, require_feats, train=True)
+        self.g_spec_eval = nets.generator_spec(variant, in_dim, out_dim, require_feats, train=False)
+        self.d_spec = nets.discriminator_spec(out_dim)
+        self.g_store = nets.ParamStore(self.g_spec, dev, seed=seed)
+        self.d_store = nets.ParamStore(self.d_spec, dev, seed=seed + 1)
+        self.g_opt = FlatAdam(self.g_store, lr)
+        self.d_opt = FlatAdam(self.d_store, lr)
+        self.drop_state = torch.zeros(2, dtype=torch.int64, device=dev)
+        self.drop_state[0] = seed
+        kw = dict(drop_mode=drop_mode, drop_state=self.drop_state)
+        # generator: train plan (G step) and eval plan (D step / inference)
+        self.G_train = nets.NetPlan(self.g_spec, self.g_store, B, T, self.dtype, dev, train=True, site_base=0, **kw)
+        self.G_eval = nets.NetPlan(self.g_spec_eval, self.g_store, B, T, self.dtype, dev, train=False)
+        self.y = torch.zeros(B, out_dim, T, dtype=torch.float32, device=dev)
+        # the eval plan shares the input buffers of the train plan
+        self.x = self.G_train.x
+        self.feats = self.G_train.feats
+        self._alias_inputs(self.G_eval, self.G_train)
+        # discriminator: eval plan scoring calc_motion(G_train.out); grouped train plan on (fake, real)
+        self.D_eval = nets.NetPlan(self.d_spec, self.d_store, B, T, self.dtype, dev, train=False,
+                                   motion_src=[self.G_train.out])
+        self.D_train = nets.NetPlan(self.d_spec, self.d_store, 2 * B, T, self.dtype, dev, train=True, groups=2,
+                                    motion_src=[self.G_eval.out, self.y], site_base=100, **kw)
+        self.losses = torch.zeros(8, dtype=torch.float32, device=dev)  # [l1, adv, g_total, d_loss]
+        self._build_loss_programs(label_smooth)
+        self._graphs: Dict[str, torch.cuda.CUDAGraph] = {}
+        self._comm_stream = None
+
+    @staticmethod
+    def _alias_inputs(dst: nets.NetPlan, src: nets.NetPlan):
+        """Make `dst` read the same static input tensors as `src` (records hold tensor references)."""
+        for rec in dst.prog.recs:
+            if rec.kind == L.OP_PREP:
+                if rec.f["src"] is dst.x:
+                    rec.f["src"] = src.x
+                elif dst.feats is not None and rec.f["src"] is dst.feats:
+                    rec.f["src"] = src.feats
+        dst.x, dst.feats = src.x, src.feats
+
+    def _build_loss_programs(self, label_smooth: bool):
+        B, T, dev = self.B, self.T, self.device
+        Gt, De, Dt = self.G_train, self.D_eval, self.D_train
+        out_dim = self.g_spec.out_dim
+        olb = Gt.bufs[Gt.out_layer.name]
+        self.ticket = torch.zeros(8, dtype=torch.int32, device=dev)
+        # ---- generator loss: L1(out, y) (+ gradient into the G backward) and MSE(D(motion(out)), 1)
+        P = self.g_loss_prog = Program(self.dtype, dev)
+        nblk = ((T + 31) // 32) * ((olb.Cp + 31) // 32) * B
+        self.l1_partial = torch.zeros(nblk, dtype=torch.float32, device=dev)
+        Ld = De.bufs[De.out_layer.name].Lz
+        with P.segment("loss"):
+            P.add(L.OP_L1, "l1", out=Gt.out, gt=self.y, dout=olb.dpre, loss=self.losses[0:1], partial=self.l1_partial,
+                  ticket=self.ticket[0:1], B=B, C=out_dim, L=T, ld=olb.Cp, Cfill=olb.Cp, gscale=1.0)
+            P.add(L.OP_MSE, "adv", score=De.out_blc, dscore=None, loss=self.losses[1:2], add=self.losses[0:1],
+                  total=self.losses[2:3], groups=1, n=B * Ld, ld=De.out_blc.shape[-1], target=[1.0, 0.0])
+        with P.segment("opt"):
+            self.g_opt.record(P, gscale=1.0 / self.world_size)
+        # ---- discriminator loss: MSE(fake, t_fake) + MSE(real, t_real) and its gradient
+        P = self.d_loss_prog = Program(self.dtype, dev)
+        tf, tr = (0.1, 0.9) if label_smooth else (0.0, 1.0)   # train_gan.py:244-245
+        dlb = Dt.bufs[Dt.out_layer.name]
+        self.dscore = torch.zeros_like(Dt.out_blc)
+        with P.segment("loss"):
+            P.add(L.OP_MSE, "d_mse", score=Dt.out_blc, dscore=self.dscore, loss=self.losses[3:4], add=None, total=None,
+                  groups=2, n=B * Ld, ld=Dt.out_blc.shape[-1], target=[tf, tr])
+            P.add(L.OP_PREP, "dscore", src=self.dscore, out=dlb.dpre, kind=L.SRC_ROWS, B=2 * B, L=Ld, C=1, ld=dlb.Cp,
+                  Cfill=dlb.Cp, src_ld=self.dscore.shape[-1], drop=None, out_f32=0)
+        with P.segment("opt"):
+            self.d_opt.record(P, gscale=1.0 / self.world_size)
+
+    # ---- gradient all-reduce (data parallel) ---------------------------------------------------
+    def _allreduce(self, store: nets.ParamStore):
+        if self.world_size > 1:
+            import torch.distributed as dist
+            dist.all_reduce(store.grad, op=dist.ReduceOp.SUM, group=self.pg)
+
+    def _bwd_bucketed(self, plan: nets.NetPlan):
+        """Backward in `n_buckets` pieces; each piece's flat-gradient range is all-reduced on a side
+        stream while the next piece computes (parameters are laid out in forward order, the backward
+        runs in reverse, so finished gradients form a suffix of the flat buffer)."""
+        if self.world_size == 1:
+            plan.prog.run("bwd")
+            return
+        import torch.distributed as dist
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(self.device)
+        st = plan.store
+        first, end = plan.prog.segments["bwd"]
+        marks = plan.bwd_marks
+        nb = min(self.n_buckets, len(marks))
+        per = math.ceil(len(marks) / nb)
+        cur = torch.cuda.current_stream(self.device)
+        hi = st.n
+        pending = []
+        for bi in range(nb):
+            names = marks[bi * per:(bi + 1) * per]
+            if not names:
+                break
+            s = names[0][1]
+            e = marks[(bi + 1) * per][1] if (bi + 1) * per < len(marks) else end
+            plan.prog.run_range(s, e, cur.cuda_stream)
+            last = bi == nb - 1 or (bi + 1) * per >= len(marks)
+            layer_names = {n for n, _ in names}
+            lo = 0 if last else min(st.offsets[l.wkey + ".weight"] for l in plan.spec.layers if l.name in layer_names)
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            self._comm_stream.wait_event(ev)
+            with torch.cuda.stream(self._comm_stream):
+                dist.all_reduce(st.grad[lo:hi], op=dist.ReduceOp.SUM, group=self.pg)
+            hi = lo
+            done = torch.cuda.Event()
+            done.record(self._comm_stream)
+            pending.append(done)
+        for ev in pending:
+            cur.wait_event(ev)
+
+    # ---- steps ---------------------------------------------------------------------------------
+    def _g_step_body(self):
+        self.G_train.pack()
+        self.D_eval.ensure_packed()
+        self.G_train.prog.run("fwd")
+        self.D_eval.prog.run("fwd")
+        self.g_loss_prog.run("loss")
+        self._bwd_bucketed(self.G_train)
+        self.g_loss_prog.run("opt")
+        self.g_store.version += 1
+
+    def _d_step_body(self):
+        self.G_eval.ensure_packed()
+        self.D_train.pack()
+        self.G_eval.prog.run("fwd")
+        self.D_train.prog.run("fwd")
+        self.d_loss_prog.run("loss")
+        self._bwd_bucketed(self.D_train)
+        self.d_loss_prog.run("opt")
+        self.d_store.version += 1
+
+    def _bump_step(self):
+        self.drop_state[1] += 1
+
+    def generator_step(self, graph: bool = False):
+        """One train_generator iteration on the batch currently in x / y / feats (train_gan.py:266-299)."""
+        self._run("g", self._g_step_body, graph)
+
+    def discriminator_step(self, graph: bool = False):
+        """One train_discriminator iteration (train_gan.py:221-251)."""
+        self._run("d", self._d_step_body, graph)
+
+    def _run(self, key, body, graph):
+        if not graph:
+            body()
+            self._bump_step()
+            return
+        # the frozen network of the step is re-packed outside the graph, only when its weights changed
+        (self.D_eval if key == "g" else self.G_eval).ensure_packed()
+        g = self._graphs.get(key)
+        if g is None:
+            body()   # warm up eagerly (finalises programs, sets kernel attributes)
+            self._bump_step()
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                if key == "g":
+                    self.G_train.prog.run("pack")
+                    self.G_train.prog.run("fwd")
+                    self.D_eval.prog.run("fwd")
+                    self.g_loss_prog.run("loss")
+                    self._bwd_bucketed(self.G_train)
+                    self.g_loss_prog.run("opt")
+                else:
+                    self.D_train.prog.run("pack")
+                    self.G_eval.prog.run("fwd")
+                    self.D_train.prog.run("fwd")
+                    self.d_loss_prog.run("loss")
+                    self._bwd_bucketed(self.D_train)
+                    self.d_loss_prog.run("opt")
+                self.drop_state[1] += 1
+            self._graphs[key] = g
+            return
+        g.replay()
+        if key == "g":
+            self.g_store.version += 1
+        else:
+            self.d_store.version += 1
+
+    # ---- inference -----------------------------------------------------------------------------
+    def infer(self):
+        """Eval forward of the generator on the batch in x / feats; result in G_eval.out (inference.py:115)."""
+        self.G_eval.forward()
+        return self.G_eval.out
+
+    def launches_per_gan_step(self) -> int:
+        """Kernel launches of one generator step + one discriminator step (measured from the programs)."""
+        n = 0
+        for p, segs in ((self.G_train.prog, ("pack", "fwd", "bwd")), (self.D_eval.prog, ("fwd",)),
+                        (self.g_loss_prog, ("loss", "opt")), (self.G_eval.prog, ("fwd",)),
+                        (self.D_train.prog, ("pack", "fwd", "bwd")), (self.d_loss_prog, ("loss", "opt"))):
+            n += sum(p.segment_launches.get(s, 0) for s in segs)
+        return n

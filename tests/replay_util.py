@@ -1,0 +1,76 @@
+"""Differential replay: run a recorded program op by op on the GPU (through libb2h.so) and on a CPU
+twin (oracle/ops_emul.py), compare every output of every op, and "teacher-force" the GPU buffers with
+the CPU results so each kernel is judged on identical inputs.  Pinpoints the first kernel that
+disagrees with its contract."""
+import torch
+
+from b2h_b200 import _lib as L
+from oracle import ops_emul as E
+
+OUT_FIELDS = {
+    L.OP_GEMM: ["out"], L.OP_WGRAD: ["dW"],
+    L.OP_BN_STATS: ["mean", "invstd", "running_mean", "running_var", "num_batches_tracked"],
+    L.OP_BN_APPLY: ["out"], L.OP_BN_BWD: ["dpre", "dgamma", "dbeta", "dbias"], L.OP_PREP: ["out"],
+    L.OP_TO_NCL: ["dst"], L.OP_L1: ["loss", "dout"], L.OP_MSE: ["loss", "dscore", "total"], L.OP_COLSUM: ["out"],
+    L.OP_ADAM: ["p", "m", "v", "step"], L.OP_PACK: ["out", "out_bias"], L.OP_BN_FOLD: ["scale", "shift"],
+    L.OP_ROT6D: ["mat"],
+}
+
+
+def rel_err(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+def sync_inputs(prog_gpu, prog_cpu):
+    """Copy every tensor the CPU program references onto its GPU counterpart (weights, masks, inputs)."""
+    seen = set()
+
+    def walk(fg, fc):
+        for k, vc in fc.items():
+            vg = fg.get(k)
+            if isinstance(vc, torch.Tensor):
+                if vc.data_ptr() not in seen:
+                    seen.add(vc.data_ptr())
+                    vg.copy_(vc)
+            elif isinstance(vc, dict):
+                walk(vg, vc)
+            elif isinstance(vc, list):
+                for a, b in zip(vg, vc):
+                    if isinstance(b, dict):
+                        walk(a, b)
+
+    for rg, rc in zip(prog_gpu.recs, prog_cpu.recs):
+        walk(rg.f, rc.f)
+
+
+def replay_pair(prog_gpu, prog_cpu, segments, teacher_force=True):
+    """Returns a list of (op index, tag, field, rel_err)."""
+    report = []
+    assert len(prog_gpu.recs) == len(prog_cpu.recs)
+    for seg in segments:
+        first, end = prog_gpu.segments[seg]
+        assert (first, end) == prog_cpu.segments[seg]
+        for i in range(first, end):
+            rg, rc = prog_gpu.recs[i], prog_cpu.recs[i]
+            assert rg.kind == rc.kind and rg.tag == rc.tag
+            prog_gpu.run_range(i, i + 1)
+            torch.cuda.synchronize()
+            E.DISPATCH[rc.kind](rc.f)
+            for fld in OUT_FIELDS[rc.kind]:
+                vc, vg = rc.f.get(fld), rg.f.get(fld)
+                if vc is None:
+                    continue
+                got = vg.detach().to("cpu")
+                if not torch.isfinite(got.float()).all():
+                    report.append((i, rc.tag, fld, float("inf")))
+                else:
+                    report.append((i, rc.tag, fld, rel_err(got.float(), vc.float())))
+                if teacher_force:
+                    vg.copy_(vc)
+    return report
+
+
+def format_report(report, top=12):
+    worst = sorted(report, key=lambda r: -r[3])[:top]
+    return "\n".join(f"  op {i:4d} {tag:32s} {fld:12s} rel_err={e:.3e}" for i, tag, fld, e in worst)
