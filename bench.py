@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: the Body2Hands-style GAN training step (train_gan.py:215-299).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on host cores
+
+A "step" = one generator step + one discriminator step on one synthetic How2Sign-shaped batch
+(BASELINE.json configs[1]: v1 body-only regressor + discriminator, batch 256 x 64 frames per GPU).
+metric = training frames/s = B*T*N / step time.  One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--variant", default="v1")
+    ap.add_argument("--feats", action="store_true", help="text (v1/v2/v4) or image (b2h) conditioning")
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--frames", type=int, default=64)
+    ap.add_argument("--mode", default="train", choices=["train", "infer"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kernel-breakdown", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    cond = ""
+    if a.feats:
+        cond = "+image" if a.variant == "b2h" else "+text"
+    what = "GAN training step (1 generator step + 1 discriminator step)" if a.mode == "train" else "eval forward"
+    return f"{a.variant}{cond} arm2wh 36->252, {what}, batch {a.batch} x {a.frames} frames per GPU"
+
+
+def synth_batch(B, T, cin, cout, feats_kind, seed=23456):
+    """How2Sign-shaped synthetic batch: standardised 6-D rotations with a temporal random walk."""
+    rng = np.random.RandomState(seed)
+    base = rng.randn(B, cin + cout, 1).astype(np.float32)
+    walk = np.cumsum(rng.randn(B, cin + cout, T).astype(np.float32) * 0.05, axis=2)
+    data = base + walk
+    data = (data - data.mean(axis=(0, 2), keepdims=True)) / (data.std(axis=(0, 2), keepdims=True) + 1e-6)
+    x = torch.from_numpy(np.ascontiguousarray(data[:, :cin]))
+    y = torch.from_numpy(np.ascontiguousarray(data[:, cin:]))
+    f = None
+    if feats_kind == "text":
+        f = rng.randn(B, 512).astype(np.float32)
+        f /= np.linalg.norm(f, axis=1, keepdims=True)
+        f = torch.from_numpy(f)
+    elif feats_kind == "image":
+        f = torch.from_numpy((rng.randn(B, T, 2000) * 2).astype(np.float32))
+    return x, y, f
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle restatement of train_gan's step bodies on host cores
+# ------------------------------------------------------------------------------------------------
+def run_cpu_reference(a, steps, warmup):
+    from oracle import ref_models as R
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(23456)
+    cin, cout = 36, 252
+    feats_kind = None if not a.feats else ("image" if a.variant == "b2h" else "text")
+    G = R.build_generator(a.variant, cin, cout, a.feats)
+    D = R.build_discriminator(cout)
+    x, y, f = synth_batch(a.batch, a.frames, cin, cout, feats_kind)
+    g_opt = torch.optim.Adam(G.parameters(), lr=1e-4)
+    d_opt = torch.optim.Adam(D.parameters(), lr=1e-4)
+
+    def step():
+        if a.mode == "train":
+            R.generator_step(G, D, g_opt, x, y, f)
+            R.discriminator_step(G, D, d_opt, x, y, f)
+        else:
+            G.eval()
+            with torch.no_grad():
+                G(x, feats_=f)
+
+    for _ in range(warmup):
+        step()
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+    med = statistics.median(times)
+    return a.batch * a.frames / med, med, os.cpu_count() or 1
+
+
+def reference_main(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = min(a.steps, 8)
+    warmup = min(a.warmup, 2)
+    fps, med, cores = run_cpu_reference(a, steps, warmup)
+    sample = f"{steps} steps (+{warmup} warm-up) of the full {a.batch}x{a.frames} batch, torch CPU, {cores} threads"
+    line = {
+        "impl": "reference", "metric": "training frames/sec" if a.mode == "train" else "inference frames/sec",
+        "value": fps, "unit": "frames/s", "n_gpus": a.gpus, "steps": steps, "warmup": warmup,
+        "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": {"workload": workload_name(a)},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        for ln in out.strip().splitlines():
+            p = [t.strip() for t in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1]))
+                mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# this repo's arm
+# ------------------------------------------------------------------------------------------------
+def kernel_breakdown(tr, flush, reps=5):
+    """CUDA-event time of every GEMM-class op of the step (L2 flushed before each launch) and its
+    algorithmic FLOP/s; returns (list, dominant entry)."""
+    from b2h_b200 import _lib as L
+    rows = []
+    plans = [("G_train", tr.G_train), ("D_eval", tr.D_eval), ("G_eval", tr.G_eval), ("D_train", tr.D_train)]
+    for pname, plan in plans:
+        for idx, macs in sorted(plan.op_macs.items()):
+            rec = plan.prog.recs[idx]
+            seg_ok = any(s <= idx < e for n, (s, e) in plan.prog.segments.items() if n in ("fwd", "bwd"))
+            if not seg_ok:
+                continue
+            ts = []
+            for _ in range(reps):
+                flush()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                plan.prog.run_range(idx, idx + 1)
+                e1.record()
+                e1.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            ms = statistics.median(ts)
+            rows.append({"op": f"{pname}.{rec.tag}", "ms": ms, "gflop": 2 * macs / 1e9,
+                         "tflops": 2 * macs / (ms * 1e-3) / 1e12 if ms > 0 else 0.0})
+    return rows
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        return reference_main(a)
+    import torch.distributed as dist
+    import b2h_b200  # noqa: F401
+    from b2h_b200.trainer import GanTrainer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == a.gpus or world == 1, f"--gpus {a.gpus} but WORLD_SIZE={world}"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    pg = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        pg = dist.group.WORLD
+    cin, cout = 36, 252
+    feats_kind = None if not a.feats else ("image" if a.variant == "b2h" else "text")
+    B, T = a.batch, a.frames
+    tr = GanTrainer(a.variant, cin, cout, a.feats, B, T, precision=a.precision, device=dev, lr=1e-4, seed=23456 + rank,
+                    drop_mode="philox", world_size=world, process_group=pg)
+    if world > 1:   # identical initial weights on every rank (DDP convention)
+        for st in (tr.g_store, tr.d_store):
+            dist.broadcast(st.flat, 0)
+            dist.broadcast(st.bufs, 0)
+    x, y, f = synth_batch(B, T, cin, cout, feats_kind, seed=23456 + rank)
+    hx, hy = x.pin_memory(), y.pin_memory()
+    hf = f.pin_memory() if f is not None else None
+    tr.x.copy_(hx)
+    tr.y.copy_(hy)
+    if hf is not None:
+        tr.feats.copy_(hf)
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def flush():
+        flush_buf.fill_(1)
+
+    use_graph = True
+
+    def step():
+        if a.mode == "train":
+            tr.generator_step(graph=use_graph)
+            tr.discriminator_step(graph=use_graph)
+        else:
+            tr.infer()
+
+    for _ in range(max(a.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    torch.cuda.synchronize()
+    ev = []
+    t_wall0 = time.perf_counter()
+    for _ in range(a.steps):
+        flush()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step()
+        e1.record()
+        ev.append((e0, e1))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t_wall = time.perf_counter() - t_wall0
+    dev_ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
+    # ---- end to end: pinned host buffers -> H2D -> step -> D2H of the losses, every step
+    h_loss = torch.empty(8, dtype=torch.float32).pin_memory()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        tr.x.copy_(hx, non_blocking=True)
+        tr.y.copy_(hy, non_blocking=True)
+        if hf is not None:
+            tr.feats.copy_(hf, non_blocking=True)
+        step()
+        if a.mode == "train":
+            h_loss.copy_(tr.losses, non_blocking=True)
+        else:
+            h_out = tr.G_eval.out.to("cpu", non_blocking=False)
+        torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()
+    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    frames = B * T * world * a.steps
+    value = frames / (dev_ms * 1e-3)
+    e2e_value = frames / (e2e_ms * 1e-3)
+    h2d = hx.numel() * 4 + hy.numel() * 4 + (hf.numel() * 4 if hf is not None else 0)
+    d2h = 32 if a.mode == "train" else tr.G_eval.out.numel() * 4
+    launches = tr.launches_per_gan_step() if a.mode == "train" else tr.G_eval.prog.segment_launches.get("fwd", 0)
+    line = {
+        "metric": "training frames/sec" if a.mode == "train" else "inference frames/sec",
+        "value": value, "unit": "frames/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+        "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": a.precision if a.precision == "bf16" else "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "global_batch": B * world, "frames": T,
+                   "parallelism": f"dp{world}" if world > 1 else "single",
+                   "timing": "CUDA events per step on the launch stream, 256 MiB L2 flush before every timed step, "
+                             "CUDA-graph replay, dropout = Philox"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches) * a.steps,
+        "wall_s": t_wall,
+    }
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        if not a.no_kernel_breakdown and a.mode == "train":
+            rows = kernel_breakdown(tr, flush)
+            rows.sort(key=lambda r: -r["ms"])
+            dom = rows[0]
+            peak = peaks.get("bf16_tflops", 1590.0)
+            which = "measured burst (MEASURED_PEAKS.json bf16_tflops)" if "bf16_tflops" in peaks else "fallback 1.59 PF"
+            traffic = None
+            try:
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(dom["op"])
+            except Exception:
+                pass
+            line["roofline"] = {"bound": "tensor", "kernel": dom["op"], "achieved": dom["tflops"], "peak": peak,
+                                "unit": "TFLOP/s", "frac": dom["tflops"] / peak, "traffic": traffic,
+                                "peak_source": which, "launch_ms": dom["ms"], "algorithmic_gflop": dom["gflop"]}
+            line["kernel_breakdown"] = [{k: (round(v, 5) if isinstance(v, float) else v) for k, v in r.items()}
+                                        for r in rows[:12]]
+            line["gemm_ms_sum"] = sum(r["ms"] for r in rows)
+        if not a.no_cpu_baseline:
+            fps, med, cores = run_cpu_reference(a, steps=5, warmup=2)
+            line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                                    "sample": f"5 steps (+2 warm-up) of the full {B}x{T} batch through the oracle "
+                                              f"restatement of train_gan (torch CPU fp32, {cores} threads)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -176,6 +176,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__
   // Mpad may be 64 (discriminator layers): only the slabs that exist are loaded; the accumulator rows
   // of the missing slab hold garbage that is never stored (rows of D are independent)
   const int a_slabs = min(WG_BM / 64, (p.Mpad - m0) / 64);
+  // a tap whose strided row view of Q is empty (e.g. odd rows of a 1-row input) contributes zeros
+  const bool dead_tap = p.tap_map[t] < 0;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmP);
@@ -197,7 +199,15 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp == 0) {
+  if (dead_tap) {
+    if (warp >= 2) {
+      const int m = m0 + (warp & 3) * 32 + lane;
+      if (m < p.Mpad) {
+        float* dst = partial + (((int64_t)split * p.ntaps + t) * p.Mpad + m) * p.Npad + n0;
+        for (int c = 0; c < WN; c += 4) *reinterpret_cast<float4*>(dst + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  } else if (warp == 0) {
     if (lane == 0) {
       const CUtensorMap* tq = p.tap_map[t] ? &tmQ1 : &tmQ0;
       for (int i = 0; i < nkb; ++i) {
@@ -462,7 +472,7 @@ int plan_wgrad_bf16(const b2h_wgrad_t& d, TcWgradPlan* plan) {
   if (rc) return rc;
   for (int t = 0; t < d.ntaps; ++t) {
     tap_view(d.stride, d.tap_off[t], &p.tap_map[t], &p.tap_coord[t]);
-    B2H_CHECK_ARG(!(p.tap_map[t] == 1 && !has1), B2H_ERR_SHAPE, "wgrad_bf16: tap reads only rows outside Q");
+    if (p.tap_map[t] == 1 && !has1) p.tap_map[t] = -1;  // empty odd-row view: the tap's gradient is zero
   }
   int wn = 64;
   if (d.Npad % 256 == 0)

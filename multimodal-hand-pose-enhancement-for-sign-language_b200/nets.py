@@ -359,6 +359,7 @@ class NetPlan:
         self._site_base = site_base
         self._motion_src_arg = list(motion_src) if motion_src is not None else None
         self.bwd_marks: List[Tuple[str, int]] = []   # (layer name, first op index) inside the bwd segment
+        self.op_macs: Dict[int, int] = {}            # op index -> algorithmic MACs (padding not counted)
         self._build()
 
     # ---- helpers -----------------------------------------------------------------------------
@@ -617,9 +618,17 @@ class NetPlan:
                       Nvalid=l.cout, ntaps=len(taps), tap_off=taps + [0] * (L.MAX_TAPS - len(taps)), act=l.act,
                       post_scale=None, post_shift=None, out_f32=1 if is_out else 0, drop=no_drop(), drop_C=0)
         if l.kind == "convT":
-            P.add(L.OP_GEMM, f"gemm.{l.name}", Lo=l.La, Npad=2 * lb.Cp, stride=1, nphase=2, Lo_actual=2 * l.La, **common)
+            i = P.add(L.OP_GEMM, f"gemm.{l.name}", Lo=l.La, Npad=2 * lb.Cp, stride=1, nphase=2, Lo_actual=2 * l.La,
+                      **common)
         else:
-            P.add(L.OP_GEMM, f"gemm.{l.name}", Lo=l.Lo, Npad=lb.Cp, stride=l.stride, nphase=1, Lo_actual=l.Lo, **common)
+            i = P.add(L.OP_GEMM, f"gemm.{l.name}", Lo=l.Lo, Npad=lb.Cp, stride=l.stride, nphase=1, Lo_actual=l.Lo,
+                      **common)
+        self.op_macs[i] = self._layer_macs(l)
+
+    def _layer_macs(self, l: Layer) -> int:
+        """MACs of the layer's contraction as the reference counts them, whole batch."""
+        rows = self.B * (l.La if l.kind == "convT" else l.Lo)
+        return rows * l.cin * l.cout * l.k
 
     def _emit_bn_stats(self, l: Layer):
         P, st, lb = self.prog, self.store, self.bufs[l.name]
@@ -665,6 +674,7 @@ class NetPlan:
                       Nvalid=l.cin, ntaps=k, stride=l.stride,
                       tap_off=[t - l.pad for t in range(k)] + [0] * (L.MAX_TAPS - k))
         i = P.add(L.OP_WGRAD, f"wgrad.{l.name}", dW=st.g(l.wkey + ".weight"), partial=None, B=B, splits=0, **wg)
+        self.op_macs[i] = self._layer_macs(l)
         self._wg_need = max(self._wg_need, _wgrad_ws_bytes(self.prog.recs[i], self.dtype))
         self._pending_partial.append((i, "partial"))
         # input gradient (with the dropout mask of this block's site)
@@ -677,11 +687,12 @@ class NetPlan:
                       Kc=lb.Cp, Nvalid=l.cin, ntaps=len(taps), tap_off=taps + [0] * (L.MAX_TAPS - len(taps)),
                       act=L.ACT_NONE, post_scale=None, post_shift=None, out_f32=0, drop=drop, drop_C=l.cin)
         if lb.bwd_nphase == 2:
-            P.add(L.OP_GEMM, f"dgrad.{l.name}", Lo=_ceil_div(l.La, 2), Npad=2 * lb.Kc, stride=1, nphase=2,
-                  Lo_actual=l.La, **common)
+            i = P.add(L.OP_GEMM, f"dgrad.{l.name}", Lo=_ceil_div(l.La, 2), Npad=2 * lb.Kc, stride=1, nphase=2,
+                      Lo_actual=l.La, **common)
         else:
-            P.add(L.OP_GEMM, f"dgrad.{l.name}", Lo=l.La, Npad=lb.Kc, stride=lb.bwd_stride, nphase=1, Lo_actual=l.La,
-                  **common)
+            i = P.add(L.OP_GEMM, f"dgrad.{l.name}", Lo=l.La, Npad=lb.Kc, stride=lb.bwd_stride, nphase=1,
+                      Lo_actual=l.La, **common)
+        self.op_macs[i] = self._layer_macs(l)
 
     # ---- execution ---------------------------------------------------------------------------
     def pack(self):

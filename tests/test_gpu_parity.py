@@ -1,0 +1,263 @@
+"""GPU parity proper: the CUDA path (through the C ABI) against the oracle restatement of the reference,
+end to end (no teacher forcing), at the tolerances BASELINE.json's north_star states:
+fp32 mode <= 1e-5 relative, bf16 mode <= 2e-2 relative."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import b2h_b200  # noqa: F401
+from b2h_b200 import _lib as L
+from b2h_b200 import nets
+from b2h_b200.trainer import GanTrainer
+from oracle import ops_emul as E
+from oracle import ref_models as R
+from tests.test_plan_emulated import feats_for, randomize_bn
+from tests.test_trainer_emulated import activation_hooks, check_adam_params, count_kink_flips, grads_close
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-5     # north_star: within 1e-5 relative in fp32 mode
+BF16_TOL = 2e-2     # north_star: within 2e-2 relative in bf16 mode
+
+
+def rel_err(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+def make_trainer(variant, rf, B, T, precision, G, D, lr=1e-3, drop_mode="mask", cin=36, cout=252, **kw):
+    tr = GanTrainer(variant, cin, cout, rf, B, T, precision=precision, device="cuda", lr=lr, drop_mode=drop_mode, **kw)
+    tr.g_store.load_state_dict({k: v.cuda() for k, v in G.state_dict().items()})
+    tr.d_store.load_state_dict({k: v.cuda() for k, v in D.state_dict().items()})
+    return tr
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", FP32_TOL), ("bf16", BF16_TOL)])
+@pytest.mark.parametrize("variant,rf,B,T", [("v1", False, 32, 64), ("v1", True, 8, 64), ("b2h", True, 4, 32),
+                                            ("v2", True, 4, 64), ("v4", True, 4, 64), ("v4_deeper", True, 4, 64),
+                                            ("v1", False, 3, 192), ("v1", False, 5, 62), ("v1", False, 2, 1024)])
+def test_eval_forward_vs_oracle(variant, rf, B, T, precision, tol):
+    """BASELINE config 1 (B=32, T=64 eval forward) and the inference.py sweep shapes."""
+    torch.manual_seed(0)
+    G = R.build_generator(variant, 36, 252, rf)
+    D = R.build_discriminator(252)
+    randomize_bn(G)
+    G.eval()
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(B, 36, T, generator=g)
+    f = feats_for(variant, rf, B, T, g)
+    with torch.no_grad():
+        ref = G(x, feats_=f)
+    tr = make_trainer(variant, rf, B, T, precision, G, D)
+    tr.x.copy_(x)
+    if f is not None:
+        tr.feats.copy_(f)
+    out = tr.infer()
+    assert rel_err(out, ref) <= tol
+
+
+@pytest.mark.parametrize("cin,cout", [(264, 24), (162, 126), (42, 246)])
+def test_incremental_finger_pipelines_fp32(cin, cout):
+    """FEATURE_MAP rows arm_wh2finger1 / 6 / 11 (utils/constants.py:14-25): channel counts that are not
+    multiples of 4 or 64."""
+    torch.manual_seed(0)
+    G = R.build_generator("v2", cin, cout, True)
+    D = R.build_discriminator(cout)
+    randomize_bn(G)
+    G.eval()
+    g = torch.Generator().manual_seed(1)
+    B, T = 6, 64
+    x = torch.randn(B, cin, T, generator=g)
+    f = torch.randn(B, 512, generator=g)
+    with torch.no_grad():
+        ref = G(x, feats_=f)
+    tr = make_trainer("v2", True, B, T, "fp32", G, D, cin=cin, cout=cout)
+    tr.x.copy_(x)
+    tr.feats.copy_(f)
+    assert rel_err(tr.infer(), ref) <= FP32_TOL
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("variant,rf", [("v1", False), ("v1", True), ("b2h", True)])
+def test_gan_step_vs_oracle(variant, rf, precision):
+    """One generator step + one discriminator step with replayed dropout masks (BASELINE config 2 shape
+    family) against train_gan's restatement with torch.optim.Adam."""
+    torch.manual_seed(0)
+    B, T, cin, cout, lr = 32, 64, 36, 252, 1e-3
+    G = R.build_generator(variant, cin, cout, rf)
+    D = R.build_discriminator(cout)
+    randomize_bn(G, 5)
+    randomize_bn(D, 6)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(B, cin, T, generator=g)
+    y = torch.randn(B, cout, T, generator=g)
+    f = feats_for(variant, rf, B, T, g)
+    tr = make_trainer(variant, rf, B, T, precision, G, D, lr=lr)
+    tr.x.copy_(x)
+    tr.y.copy_(y)
+    if f is not None:
+        tr.feats.copy_(f)
+    g_opt = torch.optim.Adam(G.parameters(), lr=lr)
+    d_opt = torch.optim.Adam(D.parameters(), lr=lr)
+    g_acts, _ = activation_hooks(G)
+    fp32 = precision == "fp32"
+    tol = FP32_TOL if fp32 else BF16_TOL
+    # ---- generator step
+    g_masks = R.make_masks(G, x, seed=100, feats=f)
+    tr.G_train.set_masks(g_masks)
+    g_loss, l1, adv, out = R.generator_step(G, D, g_opt, x, y, f, g_masks)
+    tr.generator_step()
+    torch.cuda.synchronize()
+    assert rel_err(tr.G_train.out, out) <= tol
+    losses = tr.losses.cpu()
+    assert abs(float(losses[0]) - float(l1)) <= tol * abs(float(l1))
+    assert abs(float(losses[1]) - float(adv)) <= 20 * tol * abs(float(adv)) + 1e-6
+    assert abs(float(losses[2]) - float(g_loss)) <= 20 * tol * abs(float(g_loss))
+    if fp32:
+        flips = count_kink_flips(tr.G_train, g_acts)
+        flips += int((torch.sign(tr.G_train.out.cpu() - y) != torch.sign(out - y)).sum())
+        gtol = 5e-5 if flips == 0 else 0.2
+        for k, p in G.named_parameters():
+            if p.grad is not None:
+                assert grads_close(tr.g_store.g(k).cpu(), p.grad, gtol), (k, flips)
+            check_adam_params(tr.g_store.p(k).cpu(), p, lr, k, tight=flips == 0)
+    else:
+        for k, p in G.named_parameters():
+            if p.grad is not None and p.grad.numel() > 1024:
+                # the L1 gradient is sign(out - gt)/N: a bf16-level output difference flips the sign of
+                # ~0.3 % of its elements (and a few ReLU / max-pool branches), i.e. ~10 % in L2; the
+                # per-kernel bf16 accuracy is pinned by test_gpu_replay, here only the direction is
+                cos = torch.nn.functional.cosine_similarity(tr.g_store.g(k).cpu().reshape(-1), p.grad.reshape(-1), dim=0)
+                assert float(cos) > 0.95, (k, float(cos))
+    for k, v in G.state_dict().items():
+        if k.endswith(("running_mean", "running_var")) and k in dict(tr.g_store.buffer_shapes) and \
+                k.rsplit(".", 1)[0] in {l.bnkey for l in tr.g_spec.layers}:
+            assert rel_err(tr.g_store.b(k), v) <= 5 * tol, k
+    # ---- discriminator step (restart from the oracle's exact generator state)
+    tr.g_store.load_state_dict({k: v.cuda() for k, v in G.state_dict().items()})
+    with torch.no_grad():
+        G.eval()
+        fake = G(x, feats_=f)
+    mf = R.make_masks(D, R.calc_motion(fake), seed=200)
+    mr = R.make_masks(D, R.calc_motion(y), seed=300)
+    tr.D_train.set_masks(mf, group=0)
+    tr.D_train.set_masks(mr, group=1)
+    d_loss, fs, rs = R.discriminator_step(G, D, d_opt, x, y, f, mf, mr)
+    tr.discriminator_step()
+    torch.cuda.synchronize()
+    assert abs(float(tr.losses[3]) - float(d_loss)) <= 50 * tol * abs(float(d_loss))
+    if fp32:
+        for k, p in D.named_parameters():
+            assert grads_close(tr.d_store.g(k).cpu(), p.grad, 5e-4), k
+        for k, v in D.state_dict().items():
+            if k.endswith(("running_mean", "running_var")):
+                assert rel_err(tr.d_store.b(k), v) <= 1e-4, k
+
+
+def test_graph_replay_equals_eager():
+    """CUDA-graph replay of the step must reproduce the eager launch sequence bit for bit (same masks)."""
+    torch.manual_seed(0)
+    B, T = 16, 64
+    G = R.build_generator("v1", 36, 252)
+    D = R.build_discriminator(252)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(B, 36, T, generator=g)
+    y = torch.randn(B, 252, T, generator=g)
+    res = []
+    for graph in (False, True):
+        tr = make_trainer("v1", False, B, T, "bf16", G, D, drop_mode="none")
+        tr.x.copy_(x)
+        tr.y.copy_(y)
+        for _ in range(3):
+            tr.generator_step(graph=graph)
+            tr.discriminator_step(graph=graph)
+        torch.cuda.synchronize()
+        res.append((tr.g_store.flat.clone(), tr.d_store.flat.clone(), tr.losses.clone()))
+    assert torch.equal(res[0][0], res[1][0])
+    assert torch.equal(res[0][1], res[1][1])
+    assert torch.equal(res[0][2], res[1][2])
+
+
+def test_philox_dropout_statistics_and_fwd_bwd_consistency():
+    """Production dropout: keep rate 0.5, scale 2, different per step, and the backward regenerates the
+    same mask as the forward (zero pattern of the input gradient == zero pattern of the activations)."""
+    torch.manual_seed(0)
+    B, T = 16, 64
+    G = R.build_generator("v1", 36, 252)
+    D = R.build_discriminator(252)
+    tr = make_trainer("v1", False, B, T, "fp32", G, D, drop_mode="philox")
+    g = torch.Generator().manual_seed(1)
+    tr.x.copy_(torch.randn(B, 36, T, generator=g) + 3.0)   # no exact zeros in the input
+    tr.y.copy_(torch.randn(B, 252, T, generator=g))
+    tr.generator_step()
+    torch.cuda.synchronize()
+    a0 = tr.G_train.bufs["encoder"].a[:, :, :36].clone()
+    keep = (a0 != 0).float().mean().item()
+    assert abs(keep - 0.5) < 0.02
+    ratio = (a0[a0 != 0] / (tr.x.permute(0, 2, 1)[a0 != 0])).cpu()
+    assert torch.allclose(ratio, torch.full_like(ratio, 2.0))
+    # conv5's input gradient carries conv5's dropout mask: zero exactly where a5 is zero
+    a5 = tr.G_train.bufs["conv5"].a
+    g5 = tr.G_train.bufs["conv5"].g
+    nz_a, nz_g = (a5 != 0), (g5 != 0)
+    assert float((nz_a != nz_g).float().mean()) < 1e-3
+    tr.generator_step()
+    torch.cuda.synchronize()
+    a1 = tr.G_train.bufs["encoder"].a[:, :, :36]
+    assert float(((a0 != 0) != (a1 != 0)).float().mean()) > 0.4   # a new mask every step
+
+
+def test_adam_matches_torch():
+    """Fused flat Adam against torch.optim.Adam over 12 steps with identical gradients."""
+    n = 100_003
+    g = torch.Generator().manual_seed(0)
+    p0 = torch.randn(n, generator=g)
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([ref], lr=1e-3)
+    p = p0.clone().cuda()
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    grad = torch.zeros_like(p)
+    step = torch.zeros(1, dtype=torch.int64, device="cuda")
+    for it in range(12):
+        gr = torch.randn(n, generator=g) * (10.0 ** ((it % 5) - 4))
+        ref.grad = gr.clone()
+        opt.step()
+        grad.copy_(gr)
+        d = L.Adam(p=p.data_ptr(), g=grad.data_ptr(), m=m.data_ptr(), v=v.data_ptr(), n=n, lr=1e-3, beta1=0.9,
+                   beta2=0.999, eps=1e-8, gscale=1.0, step=step.data_ptr())
+        L.run_oneshot(d, L.F32, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert int(step.item()) == 12
+    assert rel_err(p, ref) <= 2e-6
+    st = opt.state[ref]
+    assert rel_err(m, st["exp_avg"]) <= 2e-6 and rel_err(v, st["exp_avg_sq"]) <= 2e-6
+
+
+def test_rot6d_to_mat():
+    """6D -> rotation matrix against the row-wise restatement of np_rot6d_to_mat, incl. golden vectors."""
+    g = torch.Generator().manual_seed(0)
+    r6d = torch.randn(42 * 64 * 7 + 3, 6, generator=g)
+    ref = E.rot6d_to_mat(r6d)
+    d_in = r6d.cuda()
+    out = torch.empty(r6d.shape[0], 9, device="cuda")
+    L.run_oneshot(L.Rot6d(r6d=d_in.data_ptr(), mat=out.data_ptr(), n=r6d.shape[0]), L.F32,
+                  torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert rel_err(out, ref) <= 1e-5
+    R3 = out.view(-1, 3, 3).cpu()
+    eye = torch.eye(3).expand_as(R3)
+    # orthonormal proper rotations up to the reference's own +1e-6 regularisers (conversion_utils.py:92,94)
+    assert float((R3.transpose(1, 2) @ R3 - eye).abs().max()) < 2e-3
+    assert float((torch.linalg.det(R3) - 1).abs().max()) < 2e-3
+
+
+def test_missing_device_or_bad_args_fail_loudly():
+    lib = L.load()
+    d = L.Rot6d(r6d=None, mat=None, n=0)
+    rc = lib.b2h_rot6d_to_mat(d, None)
+    assert rc == -1 and b"rot6d" in lib.b2h_last_error()
+    with pytest.raises(L.B2HError):
+        nets.NetPlan(nets.discriminator_spec(252), nets.ParamStore(nets.discriminator_spec(252), "cpu"), 4, 16, L.F32,
+                     "cpu", train=False).forward()

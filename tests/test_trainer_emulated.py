@@ -39,7 +39,7 @@ def count_kink_flips(plan, acts, groups_slice=None):
         key = f"{l.seq}.{l.w_idx + 1}"
         if key not in acts or not l.bn:
             continue
-        z = plan.bufs[l.name].z[:, :, :l.cout]
+        z = plan.bufs[l.name].z[:, :, :l.cout].float().cpu()
         ref = acts[key]
         ref = ref.permute(0, 2, 1) if ref.dim() == 3 else ref.reshape(z.shape[0], -1, l.cout)
         if groups_slice is not None:
