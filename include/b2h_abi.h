@@ -258,6 +258,14 @@ typedef struct {
   float* out_bias;
 } b2h_pack_t;
 
+/* many weight repacks in ONE launch: `descs` is a DEVICE array of n descriptors (the per-step repack of a
+ * whole network after the optimizer step) */
+typedef struct {
+  const b2h_pack_t* descs;
+  int32_t n;
+  int64_t max_elems; /* largest nphase*Opad*ntaps*Ipad among the descriptors */
+} b2h_pack_multi_t;
+
 /* eval-mode BN folded to scale/shift: scale = gamma/sqrt(rv+eps), shift = beta - rm*scale, padded */
 typedef struct {
   const float *gamma, *beta, *running_mean, *running_var;
@@ -307,6 +315,7 @@ int b2h_mse(const b2h_mse_t* d, b2h_stream_t s);
 int b2h_colsum(const b2h_colsum_t* d, int dtype, b2h_stream_t s);
 int b2h_adam(const b2h_adam_t* d, b2h_stream_t s);
 int b2h_pack(const b2h_pack_t* d, int dtype, b2h_stream_t s);
+int b2h_pack_multi(const b2h_pack_multi_t* d, int dtype, b2h_stream_t s);
 int b2h_bn_fold(const b2h_bn_fold_t* d, b2h_stream_t s);
 int b2h_rot6d_to_mat(const b2h_rot6d_t* d, b2h_stream_t s);
 int b2h_fill(const b2h_fill_t* d, b2h_stream_t s);
@@ -317,7 +326,7 @@ typedef struct b2h_program b2h_program;
 enum b2h_op_kind {
   B2H_OP_GEMM = 1, B2H_OP_WGRAD, B2H_OP_BN_STATS, B2H_OP_BN_APPLY, B2H_OP_BN_BWD, B2H_OP_PREP,
   B2H_OP_TO_NCL, B2H_OP_L1, B2H_OP_MSE, B2H_OP_COLSUM, B2H_OP_ADAM, B2H_OP_PACK, B2H_OP_BN_FOLD,
-  B2H_OP_ROT6D, B2H_OP_FILL
+  B2H_OP_ROT6D, B2H_OP_FILL, B2H_OP_PACK_MULTI
 };
 b2h_program* b2h_program_create(int dtype);
 void b2h_program_destroy(b2h_program* p);

@@ -15,7 +15,7 @@ ROW_IDENT, ROW_UP2, ROW_POOL2, ROW_BCAST = 0, 1, 2, 3
 SRC_NCL, SRC_ROWS, SRC_BCAST, SRC_MOTION = 0, 1, 2, 3
 DROP_NONE, DROP_MASK, DROP_PHILOX = 0, 1, 2
 (OP_GEMM, OP_WGRAD, OP_BN_STATS, OP_BN_APPLY, OP_BN_BWD, OP_PREP, OP_TO_NCL, OP_L1, OP_MSE, OP_COLSUM,
- OP_ADAM, OP_PACK, OP_BN_FOLD, OP_ROT6D, OP_FILL) = range(1, 16)
+ OP_ADAM, OP_PACK, OP_BN_FOLD, OP_ROT6D, OP_FILL, OP_PACK_MULTI) = range(1, 17)
 
 i32, i64, f32, f64, vp = C.c_int32, C.c_int64, C.c_float, C.c_double, C.c_void_p
 
@@ -104,6 +104,10 @@ class Pack(C.Structure):
                 ("tapmap", (i32 * MAX_TAPS) * 2), ("bias", vp), ("out_bias", vp)]
 
 
+class PackMulti(C.Structure):
+    _fields_ = [("descs", vp), ("n", i32), ("max_elems", i64)]
+
+
 class BnFold(C.Structure):
     _fields_ = [("gamma", vp), ("beta", vp), ("running_mean", vp), ("running_var", vp),
                 ("scale", vp), ("shift", vp), ("C", i32), ("Cpad", i32), ("eps", f32)]
@@ -119,7 +123,7 @@ class Fill(C.Structure):
 
 OP_STRUCT = {OP_GEMM: Gemm, OP_WGRAD: Wgrad, OP_BN_STATS: BnStats, OP_BN_APPLY: BnApply, OP_BN_BWD: BnBwd,
              OP_PREP: Prep, OP_TO_NCL: ToNcl, OP_L1: L1, OP_MSE: Mse, OP_COLSUM: Colsum, OP_ADAM: Adam,
-             OP_PACK: Pack, OP_BN_FOLD: BnFold, OP_ROT6D: Rot6d, OP_FILL: Fill}
+             OP_PACK: Pack, OP_BN_FOLD: BnFold, OP_ROT6D: Rot6d, OP_FILL: Fill, OP_PACK_MULTI: PackMulti}
 KIND_OF = {v: k for k, v in OP_STRUCT.items()}
 
 # every symbol include/b2h_abi.h declares: name -> (restype, argtypes)
@@ -144,6 +148,7 @@ SYMBOLS = {
     "b2h_colsum": (C.c_int, [C.POINTER(Colsum), C.c_int, vp]),
     "b2h_adam": (C.c_int, [C.POINTER(Adam), vp]),
     "b2h_pack": (C.c_int, [C.POINTER(Pack), C.c_int, vp]),
+    "b2h_pack_multi": (C.c_int, [C.POINTER(PackMulti), C.c_int, vp]),
     "b2h_bn_fold": (C.c_int, [C.POINTER(BnFold), vp]),
     "b2h_rot6d_to_mat": (C.c_int, [C.POINTER(Rot6d), vp]),
     "b2h_fill": (C.c_int, [C.POINTER(Fill), vp]),
@@ -159,7 +164,8 @@ ONESHOT = {OP_GEMM: ("b2h_gemm", True), OP_WGRAD: ("b2h_wgrad", True), OP_BN_STA
            OP_BN_APPLY: ("b2h_bn_apply", True), OP_BN_BWD: ("b2h_bn_bwd", True), OP_PREP: ("b2h_prep", True),
            OP_TO_NCL: ("b2h_to_ncl", True), OP_L1: ("b2h_l1", True), OP_MSE: ("b2h_mse", False),
            OP_COLSUM: ("b2h_colsum", True), OP_ADAM: ("b2h_adam", False), OP_PACK: ("b2h_pack", True),
-           OP_BN_FOLD: ("b2h_bn_fold", False), OP_ROT6D: ("b2h_rot6d_to_mat", False), OP_FILL: ("b2h_fill", False)}
+           OP_BN_FOLD: ("b2h_bn_fold", False), OP_ROT6D: ("b2h_rot6d_to_mat", False), OP_FILL: ("b2h_fill", False),
+           OP_PACK_MULTI: ("b2h_pack_multi", True)}
 
 
 class B2HError(RuntimeError):

@@ -69,6 +69,7 @@ union OpDesc {
   b2h_bn_fold_t bn_fold;
   b2h_rot6d_t rot6d;
   b2h_fill_t fill;
+  b2h_pack_multi_t pack_multi;
   OpDesc() { memset(this, 0, sizeof(*this)); }
 };
 
@@ -89,6 +90,7 @@ static size_t desc_size(int kind) {
     case B2H_OP_BN_FOLD: return sizeof(b2h_bn_fold_t);
     case B2H_OP_ROT6D: return sizeof(b2h_rot6d_t);
     case B2H_OP_FILL: return sizeof(b2h_fill_t);
+    case B2H_OP_PACK_MULTI: return sizeof(b2h_pack_multi_t);
     default: return 0;
   }
 }
@@ -119,6 +121,7 @@ static int run_op(const Op& op, int dtype, cudaStream_t s) {
     case B2H_OP_BN_FOLD: return launch_bn_fold(op.d.bn_fold, s);
     case B2H_OP_ROT6D: return launch_rot6d(op.d.rot6d, s);
     case B2H_OP_FILL: return launch_fill(op.d.fill, s);
+    case B2H_OP_PACK_MULTI: return launch_pack_multi(op.d.pack_multi, dtype, s);
     default: set_error("unknown op kind %d", op.kind); return B2H_ERR_ARG;
   }
 }
@@ -177,6 +180,9 @@ int b2h_to_ncl(const b2h_to_ncl_t* d, int dtype, b2h_stream_t s) { B2H_ONESHOT(B
 int b2h_l1(const b2h_l1_t* d, int dtype, b2h_stream_t s) { B2H_ONESHOT(B2H_OP_L1, l1, d) }
 int b2h_colsum(const b2h_colsum_t* d, int dtype, b2h_stream_t s) { B2H_ONESHOT(B2H_OP_COLSUM, colsum, d) }
 int b2h_pack(const b2h_pack_t* d, int dtype, b2h_stream_t s) { B2H_ONESHOT(B2H_OP_PACK, pack, d) }
+int b2h_pack_multi(const b2h_pack_multi_t* d, int dtype, b2h_stream_t s) {
+  B2H_ONESHOT(B2H_OP_PACK_MULTI, pack_multi, d)
+}
 int b2h_mse(const b2h_mse_t* d, b2h_stream_t s) {
   const int dtype = B2H_F32;
   B2H_ONESHOT(B2H_OP_MSE, mse, d)

@@ -7,6 +7,8 @@
 //     epilogue (tcgen05.ld -> bias / activation / eval-BN / dropout -> global);
 //   * wgrad contracts over the row dimension, i.e. both operands are MN-major in shared memory:
 //     the same TMA boxes, described to the MMA with MN-major descriptors (no transposes).
+#include <stdlib.h>
+
 #include "gemm_epilogue.cuh"
 #include "ptx_sm100.cuh"
 #include "tc_plans.h"
@@ -22,23 +24,57 @@ constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;                       // bf16 elements = 128 bytes = one swizzle row
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;   // 16 KB
 
+// BN = 256: one CTA per SM, 4 stages.  BN <= 128: two co-resident CTAs per SM (<= 113 KB each) so that one
+// CTA's epilogue overlaps the other's MMA main loop on the shared tensor core.
 template <int BN>
 struct FpropCfg {
   static constexpr int B_BYTES = BN * TC_BK * 2;
   static constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int OCC = (BN == 256) ? 1 : 2;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 3 : 4);
+  // epilogue staging (reuses the pipeline buffers): 128 rows x (BN * 4 bytes + 16)
+  static constexpr int EPI_PITCH_MAX = BN * 4 + 16;
+  static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
+  static constexpr int EPI_BYTES = 128 * EPI_PITCH_MAX;
+  static constexpr int MAIN_BYTES = PIPE_BYTES > EPI_BYTES ? PIPE_BYTES : EPI_BYTES;
+  static constexpr int SMEM_BYTES = MAIN_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
+// finish 8 accumulator columns [nn, nn+8) of one output row: bias -> act -> eval-BN -> dropout keep*2
+__device__ __forceinline__ void epi_finish8(const EpiParams& e, const DropCtx& drop, uint64_t drop_row_base, int nn,
+                                            const uint32_t* acc_bits, float* v) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float x = __uint_as_float(acc_bits[j]);
+    if (e.bias) x += __ldg(e.bias + nn + j);
+    x = act_fwd(x, e.act);
+    if (e.post_scale) x = fmaf(x, __ldg(e.post_scale + nn + j), __ldg(e.post_shift + nn + j));
+    v[j] = x;
+  }
+  if (drop.mode != B2H_DROP_NONE) {
+#pragma unroll
+    for (int j = 0; j < 8; j += 4) {
+      if (nn + j + 3 < e.drop_C) {
+        float4 m = drop.scale4(drop_row_base + nn + j);
+        v[j] *= m.x, v[j + 1] *= m.y, v[j + 2] *= m.z, v[j + 3] *= m.w;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (nn + j + k < e.drop_C) v[j + k] *= drop.scale1(drop_row_base + nn + j + k);
+      }
+    }
+  }
+}
+
 template <int BN>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(192, FpropCfg<BN>::OCC)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmB, TcGemmParams p, EpiParams e) {
   using Cfg = FpropCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::MAIN_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
@@ -107,25 +143,77 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       umma_commit(tmem_full_bar);
     }
   } else {
-    // epilogue warps 2..5 -> TMEM sub-partitions (warp % 4)
+    // epilogue warps 2..5 -> TMEM sub-partitions (warp % 4).
+    // stage 1: thread == tile row: tcgen05.ld -> bias/act/BN/dropout -> own row of a padded smem tile
+    // stage 2: the warp copies its 32 rows out with row-contiguous 16-byte accesses (coalesced)
     const int sub = warp & 3;
-    const int r = sub * 32 + lane;  // tile row == TMEM lane
-    const int bi = r / p.tl, li = r - bi * p.tl;
-    const int b = b0 + bi, lo = l0 + li;
-    const bool row_ok = (b < p.B) && (lo < p.Lo);
+    const int ph = n0 / e.half;           // a tile never straddles a sub-pixel phase
+    const int nn0 = n0 - ph * e.half;     // first channel (within the phase) of this tile
+    const int valid_cols = min(BN, e.Nvalid - nn0);
+    const int esz = e.out_f32 ? 4 : 2;
+    const int pitch = BN * esz + 16;
+    uint8_t* stage = smem + (size_t)sub * 32 * pitch;
     DropCtx drop;
     drop.init(e.drop);
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
+    {
+      const int r = sub * 32 + lane;  // tile row == TMEM lane
+      const int bi = r >> p.tl_log2, li = r & (p.tl - 1);
+      const int b = b0 + bi, lo = l0 + li;
+      const int64_t grow = (int64_t)b * e.Lo_actual + (int64_t)lo * e.nphase + ph;
+      const uint64_t drop_row_base = (uint64_t)grow * (uint64_t)e.drop_C;
+      uint8_t* my = stage + (size_t)lane * pitch;
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
 #pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
-      uint32_t v[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)c, v);
-      tmem_ld_wait();
-      if (row_ok) {
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t acc[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)c, acc);
+        tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; j += 8)
-          epilogue_store<__nv_bfloat16, 8>(e, drop, b, lo, n0 + c + j, reinterpret_cast<const float*>(v) + j);
+        for (int j = 0; j < 32; j += 8) {
+          float v[8];
+          epi_finish8(e, drop, drop_row_base, nn0 + c + j, acc + j, v);
+          if (e.out_f32) {
+            float4* dst = reinterpret_cast<float4*>(my + (size_t)(c + j) * 4);
+            dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+            dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+          } else {
+            __nv_bfloat162 q0 = __floats2bfloat162_rn(v[0], v[1]), q1 = __floats2bfloat162_rn(v[2], v[3]);
+            __nv_bfloat162 q2 = __floats2bfloat162_rn(v[4], v[5]), q3 = __floats2bfloat162_rn(v[6], v[7]);
+            uint4 u;
+            u.x = *reinterpret_cast<uint32_t*>(&q0);
+            u.y = *reinterpret_cast<uint32_t*>(&q1);
+            u.z = *reinterpret_cast<uint32_t*>(&q2);
+            u.w = *reinterpret_cast<uint32_t*>(&q3);
+            *reinterpret_cast<uint4*>(my + (size_t)(c + j) * 2) = u;
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (valid_cols > 0) {
+      const int row_bytes = valid_cols * esz;
+      const int full16 = row_bytes >> 4;  // 16-byte chunks that are entirely valid
+#pragma unroll 1
+      for (int rr = 0; rr < 32; ++rr) {
+        const int r = sub * 32 + rr;
+        const int bi = r >> p.tl_log2, li = r & (p.tl - 1);
+        const int b = b0 + bi, lo = l0 + li;
+        const int ris = lo * e.nphase + ph;
+        if (b >= p.B || lo >= p.Lo || ris >= e.Lo_actual) continue;
+        const int64_t grow = (int64_t)b * e.Lo_actual + ris;
+        uint8_t* gdst = reinterpret_cast<uint8_t*>(e.out) + ((size_t)grow * e.ldo + e.out_coff + nn0) * esz;
+        const uint8_t* src = stage + (size_t)rr * pitch;
+        for (int ch = lane; ch < full16; ch += 32)
+          *reinterpret_cast<uint4*>(gdst + ch * 16) = *reinterpret_cast<const uint4*>(src + ch * 16);
+        // ragged tail (Nvalid not a multiple of the vector width): element-wise
+        const int tail0 = full16 * 16;
+        for (int bo = tail0 + lane * esz; bo < row_bytes; bo += 32 * esz) {
+          if (esz == 4)
+            *reinterpret_cast<uint32_t*>(gdst + bo) = *reinterpret_cast<const uint32_t*>(src + bo);
+          else
+            *reinterpret_cast<uint16_t*>(gdst + bo) = *reinterpret_cast<const uint16_t*>(src + bo);
+        }
       }
     }
   }
@@ -149,19 +237,24 @@ struct WgradCfg {
   static constexpr int A_BYTES = (WG_BM / 64) * WG_SLAB;  // 16 KB
   static constexpr int B_BYTES = (WN / 64) * WG_SLAB;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (WN == 256) ? 4 : (WN == 128 ? 6 : 8);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int OCC = (WN == 256) ? 1 : 2;
+  static constexpr int STAGES = (WN == 256) ? 4 : (WN == 128 ? 3 : 4);
+  static constexpr int EPI_PITCH = WN * 4 + 16;
+  static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
+  static constexpr int EPI_BYTES = 128 * EPI_PITCH;
+  static constexpr int MAIN_BYTES = PIPE_BYTES > EPI_BYTES ? PIPE_BYTES : EPI_BYTES;
+  static constexpr int SMEM_BYTES = MAIN_BYTES + 1024 + 256;
 };
 
 template <int WN>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(192, WgradCfg<WN>::OCC)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmQ0,
                 const __grid_constant__ CUtensorMap tmQ1, TcWgradParams p, float* __restrict__ partial) {
   using Cfg = WgradCfg<WN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::MAIN_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
@@ -251,22 +344,33 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__
       umma_commit(tmem_full_bar);
     }
   } else {
+    // stage 1: thread == accumulator row -> padded smem row; stage 2: coalesced row copies to the partial plane
     const int sub = warp & 3;
-    const int m = m0 + sub * 32 + lane;
-    float* dst = partial + (((int64_t)split * p.ntaps + t) * p.Mpad + m) * p.Npad + n0;
+    constexpr int pitch = Cfg::EPI_PITCH;
+    uint8_t* stage = smem + (size_t)sub * 32 * pitch;
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
+    {
+      uint8_t* my = stage + (size_t)lane * pitch;
 #pragma unroll 1
-    for (int c = 0; c < WN; c += 32) {
-      uint32_t v[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)c, v);
-      tmem_ld_wait();
-      const float* f = reinterpret_cast<const float*>(v);
-      if (m < p.Mpad) {
+      for (int c = 0; c < WN; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)c, v);
+        tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(dst + c + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+          *reinterpret_cast<uint4*>(my + (size_t)(c + j) * 4) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
       }
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int rr = 0; rr < 32; ++rr) {
+      const int m = m0 + sub * 32 + rr;
+      if (m >= p.Mpad) break;
+      uint8_t* gdst = reinterpret_cast<uint8_t*>(partial + (((int64_t)split * p.ntaps + t) * p.Mpad + m) * p.Npad + n0);
+      const uint8_t* src = stage + (size_t)rr * pitch;
+      for (int ch = lane; ch < WN / 4; ch += 32)
+        *reinterpret_cast<uint4*>(gdst + ch * 16) = *reinterpret_cast<const uint4*>(src + ch * 16);
     }
   }
   tc_fence_before();
@@ -391,9 +495,13 @@ int plan_gemm_bf16(const b2h_gemm_t& d, TcGemmPlan* plan) {
   p.Kc = d.Kc;
   p.stride = d.stride;
   p.tl = choose_tl(d.Lo, TC_BM);
+  p.tl_log2 = 0;
+  while ((1 << p.tl_log2) < p.tl) ++p.tl_log2;
   p.tb = TC_BM / p.tl;
   p.n_lchunks = ceil_div(d.Lo, p.tl);
   const int m_tiles = ceil_div(d.B, p.tb) * p.n_lchunks;
+  B2H_CHECK_ARG(d.ldo % 8 == 0 && d.out_coff % 8 == 0 && ((uintptr_t)d.out % 16) == 0, B2H_ERR_ALIGN,
+                "gemm_bf16: out/ldo/out_coff must allow 16-byte row stores (ldo=%d coff=%d)", d.ldo, d.out_coff);
   bool has1 = false;
   int rc = make_row_views(&plan->tmA0, &plan->tmA1, &has1, d.A, d.Kc, d.La, d.B, d.lda, d.stride, p.tl, p.tb);
   if (rc) return rc;
@@ -424,6 +532,10 @@ int plan_gemm_bf16(const b2h_gemm_t& d, TcGemmPlan* plan) {
       best_t = t;
       best_bn = bn;
     }
+  }
+  if (const char* f = getenv("B2H_FORCE_BN")) {  // tuning aid
+    int bn = atoi(f);
+    if ((bn == 64 || bn == 128 || bn == 256) && half % bn == 0) best_bn = bn;
   }
   plan->BN = best_bn;
   plan->grid_x = m_tiles;

@@ -29,20 +29,32 @@ __global__ void __launch_bounds__(256) prep_ncl_kernel(b2h_prep_t d) {
   __syncthreads();
   DropCtx drop;
   drop.init(d.drop);
-  for (int j = ty; j < 32; j += 8) {
-    int l = l0 + j, c = c0 + tx;
-    if (l < d.L && c < d.Cfill) {
-      float v = 0.f;
-      if (c < d.C) {
-        int64_t row = (int64_t)b * d.L + l;
-        v = tile[tx][j] * drop.scale1((uint64_t)row * d.C + c);
+  // write phase: each thread stores 4 consecutive channels of one time step (8 B bf16 / 16 B fp32)
+  const int tid = ty * 32 + tx;
+  const int l = l0 + (tid >> 3), c = c0 + (tid & 7) * 4;
+  if (l < d.L && c < d.Cfill) {
+    const int64_t row = (int64_t)b * d.L + l;
+    float4 v = make_float4(0, 0, 0, 0);
+    if (c < d.C) {
+      v = make_float4(tile[(tid & 7) * 4 + 0][tid >> 3], tile[(tid & 7) * 4 + 1][tid >> 3],
+                      tile[(tid & 7) * 4 + 2][tid >> 3], tile[(tid & 7) * 4 + 3][tid >> 3]);
+      if (drop.mode != B2H_DROP_NONE) {
+        const uint64_t idx = (uint64_t)row * d.C + c;
+        if (c + 3 < d.C) {
+          float4 m = drop.scale4(idx);
+          v.x *= m.x, v.y *= m.y, v.z *= m.z, v.w *= m.w;
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (c + k < d.C) f4(v, k) *= drop.scale1(idx + k);
+        }
       }
-      int64_t o = ((int64_t)b * d.L + l) * d.ld + c;
-      if (d.out_f32)
-        reinterpret_cast<float*>(d.out)[o] = v;
-      else
-        reinterpret_cast<T*>(d.out)[o] = from_f<T>(v);
     }
+    const int64_t o = row * d.ld + c;
+    if (d.out_f32)
+      store4<float>(reinterpret_cast<float*>(d.out) + o, v);
+    else
+      store4<T>(reinterpret_cast<T*>(d.out) + o, v);
   }
 }
 
@@ -90,6 +102,7 @@ int launch_prep(const b2h_prep_t& d, int dtype, cudaStream_t s) {
                 "prep: bad shape B=%d L=%d C=%d Cfill=%d ld=%d", d.B, d.L, d.C, d.Cfill, d.ld);
   if (d.kind == B2H_SRC_NCL || d.kind == B2H_SRC_MOTION) {
     B2H_CHECK_ARG(d.B <= 65535, B2H_ERR_SHAPE, "prep: B too large for grid.z");
+    B2H_CHECK_ARG(d.Cfill % 4 == 0 && d.ld % 4 == 0, B2H_ERR_ALIGN, "prep: Cfill/ld must be multiples of 4");
     dim3 grid(ceil_div(d.L, 32), ceil_div(d.Cfill, 32), d.B), block(32, 8);
     if (dtype == B2H_BF16)
       prep_ncl_kernel<__nv_bfloat16><<<grid, block, 0, s>>>(d);
@@ -150,69 +163,75 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) l1_kernel(b2h_l1_t d) {
+__global__ void __launch_bounds__(256) l1_kernel(b2h_l1_t d, int cext) {
   __shared__ float tile[32][33];
-  __shared__ float s_part[8];
-  const int b = blockIdx.z, l0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  __shared__ double s_part[256];
+  const int b = blockIdx.y, l0 = blockIdx.x * 32;
   const int tx = threadIdx.x, ty = threadIdx.y;
+  const int tid = ty * 32 + tx;
   const int64_t numel = (int64_t)d.B * d.C * d.L;
   const float gval = d.gscale / (float)numel;
   float acc = 0.f;
-  for (int j = ty; j < 32; j += 8) {
-    int c = c0 + j, l = l0 + tx;
-    float sg = 0.f;
-    if (c < d.C && l < d.L) {
-      int64_t i = ((int64_t)b * d.C + c) * d.L + l;
-      float diff = d.out[i] - d.gt[i];
-      acc += fabsf(diff);
-      sg = diff > 0.f ? gval : (diff < 0.f ? -gval : 0.f);  // sign(diff)/numel, sign(0) = 0
-    }
-    tile[j][tx] = sg;
-  }
-  acc = warp_sum(acc);
-  if (tx == 0) s_part[ty] = acc;
-  __syncthreads();
-  if (d.dout) {
-    T* dout = reinterpret_cast<T*>(d.dout);
+  for (int c0 = 0; c0 < cext; c0 += 32) {
     for (int j = ty; j < 32; j += 8) {
-      int l = l0 + j, c = c0 + tx;
-      if (l < d.L && c < d.Cfill) dout[((int64_t)b * d.L + l) * d.ld + c] = from_f<T>(c < d.C ? tile[tx][j] : 0.f);
+      int c = c0 + j, l = l0 + tx;
+      float sg = 0.f;
+      if (c < d.C && l < d.L) {
+        int64_t i = ((int64_t)b * d.C + c) * d.L + l;
+        float diff = d.out[i] - d.gt[i];
+        acc += fabsf(diff);
+        sg = diff > 0.f ? gval : (diff < 0.f ? -gval : 0.f);  // sign(diff)/numel, sign(0) = 0
+      }
+      tile[j][tx] = sg;
     }
+    __syncthreads();
+    if (d.dout) {
+      // 4 consecutive channels of one time step per thread
+      const int l = l0 + (tid >> 3), c = c0 + (tid & 7) * 4;
+      if (l < d.L && c < d.Cfill) {
+        float4 v = make_float4(tile[(tid & 7) * 4 + 0][tid >> 3], tile[(tid & 7) * 4 + 1][tid >> 3],
+                               tile[(tid & 7) * 4 + 2][tid >> 3], tile[(tid & 7) * 4 + 3][tid >> 3]);
+        store4<T>(reinterpret_cast<T*>(d.dout) + ((int64_t)b * d.L + l) * d.ld + c, v);
+      }
+    }
+    __syncthreads();
   }
-  const uint32_t nblocks = gridDim.x * gridDim.y * gridDim.z;
-  const uint32_t bid = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-  if (tx == 0 && ty == 0) {
-    float t = 0.f;
-    for (int k = 0; k < 8; ++k) t += s_part[k];
-    d.partial[bid] = t;
+  s_part[tid] = (double)acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (tid < o) s_part[tid] += s_part[tid + o];
+    __syncthreads();
   }
+  const uint32_t nblocks = gridDim.x * gridDim.y;
+  const uint32_t bid = blockIdx.y * gridDim.x + blockIdx.x;
+  if (tid == 0) d.partial[bid] = (float)s_part[0];
   if (!last_block_done(d.ticket, nblocks)) return;
-  // ordered final sum in double by one warp
-  if (ty == 0) {
-    double t = 0.0;
-    for (uint32_t k = tx; k < nblocks; k += 32) t += (double)__ldcg(d.partial + k);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-    if (tx == 0) d.loss[0] = (float)(t / (double)numel);
+  double t = 0.0;
+  for (uint32_t k = tid; k < nblocks; k += 256) t += (double)__ldcg(d.partial + k);
+  __syncthreads();
+  s_part[tid] = t;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (tid < o) s_part[tid] += s_part[tid + o];
+    __syncthreads();
   }
+  if (tid == 0) d.loss[0] = (float)(s_part[0] / (double)numel);
 }
 
 int launch_l1(const b2h_l1_t& d, int dtype, cudaStream_t s) {
   B2H_CHECK_ARG(d.B > 0 && d.B <= 65535 && d.C > 0 && d.L > 0, B2H_ERR_SHAPE, "l1: bad shape");
-  B2H_CHECK_ARG(!d.dout || (d.ld >= d.Cfill && d.Cfill >= d.C), B2H_ERR_SHAPE, "l1: bad dout shape");
+  B2H_CHECK_ARG(!d.dout || (d.ld >= d.Cfill && d.Cfill >= d.C && d.Cfill % 4 == 0 && d.ld % 4 == 0), B2H_ERR_SHAPE,
+                "l1: bad dout shape");
   int cext = d.dout ? d.Cfill : d.C;
-  dim3 grid(ceil_div(d.L, 32), ceil_div(cext, 32), d.B), block(32, 8);
+  dim3 grid(ceil_div(d.L, 32), d.B), block(32, 8);
   if (dtype == B2H_BF16)
-    l1_kernel<__nv_bfloat16><<<grid, block, 0, s>>>(d);
+    l1_kernel<__nv_bfloat16><<<grid, block, 0, s>>>(d, cext);
   else
-    l1_kernel<float><<<grid, block, 0, s>>>(d);
+    l1_kernel<float><<<grid, block, 0, s>>>(d, cext);
   B2H_LAUNCH_CHECK("l1");
   return B2H_OK;
 }
-int64_t l1_partial_floats(const b2h_l1_t& d) {
-  int cext = d.dout ? d.Cfill : d.C;
-  return (int64_t)ceil_div(d.L, 32) * ceil_div(cext, 32) * d.B;
-}
+int64_t l1_partial_floats(const b2h_l1_t& d) { return (int64_t)ceil_div(d.L, 32) * d.B; }
 
 // ---------------------------------------------------------------------------------------------
 // MSE on discriminator scores (nn.MSELoss, train_gan.py:93): tiny, one CTA
@@ -315,11 +334,10 @@ int launch_adam(const b2h_adam_t& d, cudaStream_t s) {
 // weight repack (PyTorch layout fp32 -> GEMM operand layout [Opad*nphase][ntaps][Ipad], act dtype)
 // ---------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(256) pack_kernel(b2h_pack_t d) {
+__device__ __forceinline__ void pack_body(const b2h_pack_t& d, int64_t first, int64_t stride) {
   const int64_t total = (int64_t)d.nphase * d.Opad * d.ntaps * d.Ipad;
   T* out = reinterpret_cast<T*>(d.out);
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
+  for (int64_t idx = first; idx < total; idx += stride) {
     int i = (int)(idx % d.Ipad);
     int64_t r = idx / d.Ipad;
     int t = (int)(r % d.ntaps);
@@ -332,10 +350,35 @@ __global__ void __launch_bounds__(256) pack_kernel(b2h_pack_t d) {
     out[idx] = from_f<T>(v);
   }
   if (d.out_bias) {
-    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < (int64_t)d.Opad;
-         o += (int64_t)gridDim.x * blockDim.x)
-      d.out_bias[o] = (d.bias && o < d.O) ? d.bias[o] : 0.f;
+    for (int64_t o = first; o < (int64_t)d.Opad; o += stride) d.out_bias[o] = (d.bias && o < d.O) ? d.bias[o] : 0.f;
   }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) pack_kernel(b2h_pack_t d) {
+  pack_body<T>(d, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) pack_multi_kernel(b2h_pack_multi_t m) {
+  __shared__ b2h_pack_t d;
+  if (threadIdx.x < sizeof(b2h_pack_t) / 4)
+    reinterpret_cast<uint32_t*>(&d)[threadIdx.x] = reinterpret_cast<const uint32_t*>(m.descs + blockIdx.y)[threadIdx.x];
+  __syncthreads();
+  pack_body<T>(d, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x);
+}
+
+int launch_pack_multi(const b2h_pack_multi_t& m, int dtype, cudaStream_t s) {
+  B2H_CHECK_ARG(m.descs && m.n > 0 && m.n <= 65535 && m.max_elems > 0, B2H_ERR_ARG, "pack_multi: bad args");
+  static_assert(sizeof(b2h_pack_t) % 4 == 0 && sizeof(b2h_pack_t) / 4 <= 256, "descriptor staging");
+  int bx = (int)std::min<int64_t>(ceil_div64(m.max_elems, 256 * 8), 64);
+  dim3 grid(std::max(bx, 1), m.n);
+  if (dtype == B2H_BF16)
+    pack_multi_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(m);
+  else
+    pack_multi_kernel<float><<<grid, 256, 0, s>>>(m);
+  B2H_LAUNCH_CHECK("pack_multi");
+  return B2H_OK;
 }
 
 int launch_pack(const b2h_pack_t& d, int dtype, cudaStream_t s) {

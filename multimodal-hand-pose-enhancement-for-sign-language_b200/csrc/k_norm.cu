@@ -6,20 +6,63 @@
 //   train: y = (z - mean_b) / sqrt(var_b(biased) + eps) * gamma + beta;
 //          running = (1-m)*running + m*batch (running_var from the UNBIASED batch variance);
 //   eval:  y = (z - running_mean) / sqrt(running_var + eps) * gamma + beta.
+#include <algorithm>
+
 #include "b2h_common.cuh"
 
 namespace b2h {
 
-struct BlockShape {
-  int txp, ty;
+// Thread geometry shared by the kernels below: a CTA is (TXp, TY) threads, thread (tx, ty) owns channels
+// 4*tx .. 4*tx+3 and rows ty, ty+TY, ... of the CTA's row chunk.  Reduction kernels use 512 threads and at
+// most kMaxChunks chunks per group so that the ordered final merge by the last CTA stays short.
+constexpr int kRedThreads = 512;
+constexpr int kMaxChunks = 128;
+struct RedShape {
+  int txp, ty, rows_per_chunk, nchunks;
 };
-static BlockShape block_shape(int Cwork) {
-  int tx = ceil_div(Cwork, 4);
-  int txp = 1;
-  while (txp < tx) txp <<= 1;
-  if (txp > 256) txp = 256;
-  return {txp, 256 / txp};
+static int pow2_ceil(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
 }
+static RedShape red_shape(int Cwork, int rows_per_group, int threads) {
+  RedShape r;
+  r.txp = std::min(pow2_ceil(ceil_div(Cwork, 4)), threads / 2);
+  r.ty = threads / r.txp;
+  int R = std::max(r.ty * 4, ceil_div(ceil_div(rows_per_group, kMaxChunks), r.ty) * r.ty);
+  r.rows_per_chunk = R;
+  r.nchunks = ceil_div(rows_per_group, R);
+  return r;
+}
+
+// sum the per-thread accumulators over ty (fixed pairing tree -> deterministic); result valid for ty == 0
+__device__ __forceinline__ void reduce_over_ty(float4* sm, float4& v, int tx, int ty, int TXp, int TY) {
+  __syncthreads();
+  sm[ty * TXp + tx] = v;
+  __syncthreads();
+  for (int off = TY >> 1; off > 0; off >>= 1) {
+    if (ty < off) {
+      float4 a = sm[ty * TXp + tx], b = sm[(ty + off) * TXp + tx];
+      sm[ty * TXp + tx] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+    }
+    __syncthreads();
+  }
+  v = sm[tx];
+}
+
+// ordered sum over chunks of partial[(chunk*groups + g)*C + c][which] by the last CTA:
+// thread (c, lane) takes chunks lane, lane+NL, ...; lanes are then added in order by lane 0.
+struct FinalLanes {
+  int Cp2, NL, c, lane;
+  __device__ __forceinline__ FinalLanes(int C, int tid) {
+    Cp2 = 1;
+    while (Cp2 < C) Cp2 <<= 1;
+    NL = kRedThreads / Cp2;
+    if (NL < 1) NL = 1;
+    c = tid % Cp2;
+    lane = tid / Cp2;
+  }
+};
 
 struct Affine4 {
   float4 s, t;
@@ -87,89 +130,104 @@ __device__ __forceinline__ float4 bn_src_eval(const b2h_bn_src_t& src, const Aff
 }
 
 // ---------------------------------------------------------------------------------------------
-// bn_stats: chunked Welford + ordered Chan merge (deterministic), finalised by the last CTA
+// bn_stats: per-chunk shifted sums (pivot = first row of the chunk) -> (mean, M2) per chunk ->
+// ordered, division-free merge in double by the last CTA (deterministic)
 // ---------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(256) bn_stats_kernel(b2h_bn_stats_t d, int nchunks) {
-  __shared__ float4 s_mean[256];
-  __shared__ float4 s_m2[256];
-  __shared__ int s_n[256];
+__global__ void __launch_bounds__(kRedThreads) bn_stats_kernel(b2h_bn_stats_t d, int nchunks, int R) {
+  __shared__ float4 s_red[kRedThreads];
+  __shared__ double s_dbl[kRedThreads];
+  __shared__ double s_mean[kRedThreads];
   const int tx = threadIdx.x, ty = threadIdx.y, TXp = blockDim.x, TY = blockDim.y;
   const int chunk = blockIdx.x, g = blockIdx.y;
   const int c0 = tx * 4;
   const int rpg = d.rows_per_group;
-  const int r_begin = chunk * kBnChunkRows;
-  const int r_end = min(r_begin + kBnChunkRows, rpg);
-  const T* z = reinterpret_cast<const T*>(d.z);
-  float4 mean = make_float4(0, 0, 0, 0), m2 = make_float4(0, 0, 0, 0);
-  int n = 0;
+  const int r_begin = chunk * R;
+  const int r_end = min(r_begin + R, rpg);
+  const T* z = reinterpret_cast<const T*>(d.z) + (int64_t)g * rpg * d.ld + c0;
+  float4 s1 = make_float4(0, 0, 0, 0), s2 = s1, piv = s1;
   if (c0 < d.C) {
-    for (int r = r_begin + ty; r < r_end; r += TY) {
-      float4 v = load4<T>(z + ((int64_t)g * rpg + r) * d.ld + c0);
-      ++n;
-      float inv = 1.0f / (float)n;
+    piv = load4<T>(z + (int64_t)r_begin * d.ld);
+    for (int r = r_begin + ty; r < r_end; r += 4 * TY) {
+      float4 v[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float delta = f4(v, i) - f4(mean, i);
-        f4(mean, i) += delta * inv;
-        f4(m2, i) += delta * (f4(v, i) - f4(mean, i));
+      for (int u = 0; u < 4; ++u) {
+        int rr = r + u * TY;
+        v[u] = rr < r_end ? load4<T>(z + (int64_t)rr * d.ld) : piv;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float dx = f4(v[u], i) - f4(piv, i);
+          f4(s1, i) += dx;
+          f4(s2, i) = fmaf(dx, dx, f4(s2, i));
+        }
       }
     }
   }
-  const int sidx = ty * TXp + tx;
-  s_mean[sidx] = mean;
-  s_m2[sidx] = m2;
-  s_n[sidx] = n;
-  __syncthreads();
+  reduce_over_ty(s_red, s1, tx, ty, TXp, TY);
+  reduce_over_ty(s_red, s2, tx, ty, TXp, TY);
   if (ty == 0 && c0 < d.C) {
-    float na = (float)n;
-    for (int j = 1; j < TY; ++j) {
-      int nbj = s_n[j * TXp + tx];
-      if (nbj == 0) continue;
-      float nb = (float)nbj;
-      float4 mb = s_mean[j * TXp + tx], qb = s_m2[j * TXp + tx];
-      float nab = na + nb;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float delta = f4(mb, i) - f4(mean, i);
-        f4(mean, i) += delta * (nb / nab);
-        f4(m2, i) += f4(qb, i) + delta * delta * (na * nb / nab);
-      }
-      na = nab;
-    }
+    const float n = (float)(r_end - r_begin);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       int c = c0 + i;
       if (c < d.C) {
+        float m = f4(s1, i) / n;
         float* p = d.partial + (((int64_t)chunk * d.groups + g) * d.C + c) * 2;
-        p[0] = f4(mean, i);
-        p[1] = f4(m2, i);
+        p[0] = f4(piv, i) + m;
+        p[1] = fmaxf(f4(s2, i) - f4(s1, i) * m, 0.f);
       }
     }
   }
   if (!last_block_done(d.ticket, gridDim.x * gridDim.y)) return;
-  // ordered merge over chunks, in double
   const int tid = ty * TXp + tx;
-  for (int c = tid; c < d.C; c += 256) {
-    for (int gg = 0; gg < d.groups; ++gg) {
-      double na = 0.0, ma = 0.0, qa = 0.0;
-      for (int ch = 0; ch < nchunks; ++ch) {
-        int rb = ch * kBnChunkRows;
-        double nb = (double)(min(rb + kBnChunkRows, rpg) - rb);
-        const float* p = d.partial + (((int64_t)ch * d.groups + gg) * d.C + c) * 2;
-        double mb = (double)__ldcg(p), qb = (double)__ldcg(p + 1);
-        double nab = na + nb, delta = mb - ma;
-        ma += delta * (nb / nab);
-        qa += qb + delta * delta * (na * nb / nab);
-        na = nab;
+  const FinalLanes fl(d.C, tid);
+  const bool act = fl.c < d.C && fl.lane < fl.NL;
+  for (int gg = 0; gg < d.groups; ++gg) {
+    // pass A: mean = sum n_c mean_c / N
+    double acc = 0.0;
+    if (act)
+      for (int ch = fl.lane; ch < nchunks; ch += fl.NL) {
+        double nb = (double)(min(ch * R + R, rpg) - ch * R);
+        acc += nb * (double)__ldcg(d.partial + (((int64_t)ch * d.groups + gg) * d.C + fl.c) * 2);
       }
-      double var_b = qa / na;
-      d.mean[gg * d.C + c] = (float)ma;
+    __syncthreads();
+    s_dbl[tid] = acc;
+    __syncthreads();
+    if (act && fl.lane == 0) {
+      double t = 0.0;
+      for (int l = 0; l < fl.NL; ++l) t += s_dbl[l * fl.Cp2 + fl.c];
+      s_mean[fl.c] = t / (double)rpg;
+    }
+    __syncthreads();
+    // pass B: M2 = sum M2_c + n_c (mean_c - mean)^2
+    acc = 0.0;
+    if (act) {
+      const double mean = s_mean[fl.c];
+      for (int ch = fl.lane; ch < nchunks; ch += fl.NL) {
+        double nb = (double)(min(ch * R + R, rpg) - ch * R);
+        const float* p = d.partial + (((int64_t)ch * d.groups + gg) * d.C + fl.c) * 2;
+        double dm = (double)__ldcg(p) - mean;
+        acc += (double)__ldcg(p + 1) + nb * dm * dm;
+      }
+    }
+    __syncthreads();
+    s_dbl[tid] = acc;
+    __syncthreads();
+    if (act && fl.lane == 0) {
+      double m2 = 0.0;
+      for (int l = 0; l < fl.NL; ++l) m2 += s_dbl[l * fl.Cp2 + fl.c];
+      const int c = fl.c;
+      const double mean = s_mean[c];
+      const double var_b = m2 / (double)rpg;
+      d.mean[gg * d.C + c] = (float)mean;
       d.invstd[gg * d.C + c] = (float)(1.0 / sqrt(var_b + (double)d.eps));
       if (d.running_mean && (gg == 0 || d.update_all_groups)) {
-        double var_u = na > 1.0 ? qa / (na - 1.0) : var_b;
+        double var_u = rpg > 1 ? m2 / (double)(rpg - 1) : var_b;
         float mom = d.momentum;
-        d.running_mean[c] = (1.f - mom) * d.running_mean[c] + mom * (float)ma;
+        d.running_mean[c] = (1.f - mom) * d.running_mean[c] + mom * (float)mean;
         d.running_var[c] = (1.f - mom) * d.running_var[c] + mom * (float)var_u;
       }
     }
@@ -179,27 +237,27 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(b2h_bn_stats_t d, int nch
 }
 
 int64_t bn_partial_floats(int rows, int C, int groups) {
-  int rpg = rows / (groups > 0 ? groups : 1);
-  return (int64_t)bn_nchunks(rpg) * groups * C * 2;
+  (void)rows;
+  return (int64_t)kMaxChunks * (groups > 0 ? groups : 1) * C * 2;
 }
 
 int launch_bn_stats(const b2h_bn_stats_t& d, int dtype, cudaStream_t s) {
-  B2H_CHECK_ARG(d.C > 0 && d.C <= 1024 && d.groups >= 1 && d.rows_per_group > 0, B2H_ERR_SHAPE,
+  B2H_CHECK_ARG(d.C > 0 && d.C <= 512 && d.groups >= 1 && d.rows_per_group > 0, B2H_ERR_SHAPE,
                 "bn_stats: bad shape C=%d groups=%d rows=%d", d.C, d.groups, d.rows_per_group);
   B2H_CHECK_ARG(d.ld % 4 == 0 && d.ld >= ((d.C + 3) & ~3), B2H_ERR_ALIGN, "bn_stats: ld=%d C=%d", d.ld, d.C);
-  BlockShape bs = block_shape(d.C);
-  int nchunks = bn_nchunks(d.rows_per_group);
-  dim3 grid(nchunks, d.groups), block(bs.txp, bs.ty);
+  RedShape rs = red_shape(d.C, d.rows_per_group, kRedThreads);
+  dim3 grid(rs.nchunks, d.groups), block(rs.txp, rs.ty);
   if (dtype == B2H_BF16)
-    bn_stats_kernel<__nv_bfloat16><<<grid, block, 0, s>>>(d, nchunks);
+    bn_stats_kernel<__nv_bfloat16><<<grid, block, 0, s>>>(d, rs.nchunks, rs.rows_per_chunk);
   else
-    bn_stats_kernel<float><<<grid, block, 0, s>>>(d, nchunks);
+    bn_stats_kernel<float><<<grid, block, 0, s>>>(d, rs.nchunks, rs.rows_per_chunk);
   B2H_LAUNCH_CHECK("bn_stats");
   return B2H_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
-// bn_apply: out = dropout( BN0(src0) [+ BN1(src1)] ), zero fill of the channel padding
+// bn_apply: out = dropout( BN0(src0) [+ BN1(src1)] ), zero fill of the channel padding.
+// 256 threads, 4 rows per thread with all loads issued before the first store.
 // ---------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) bn_apply_kernel(b2h_bn_apply_t d) {
@@ -208,34 +266,44 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(b2h_bn_apply_t d) {
   if (c0 >= d.Cfill) return;
   const int rows = d.B * d.L;
   const int rpg = rows / d.groups;
-  const int r_begin = blockIdx.x * kBnChunkRows;
-  const int r_end = min(r_begin + kBnChunkRows, rows);
+  const int r0 = blockIdx.x * (TY * 4) + ty;
   DropCtx drop;
   drop.init(d.drop);
   T* out = reinterpret_cast<T*>(d.out);
+  const bool live = c0 < d.C;
+  float4 y[4];
   Affine4 a0, a1;
   int gcur = -1;
-  for (int row = r_begin + ty; row < r_end; row += TY) {
-    const int b = row / d.L, l = row - b * d.L;
-    const int g = row / rpg;
-    float4 y = make_float4(0, 0, 0, 0);
-    if (c0 < d.C) {
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int row = r0 + u * TY;
+    y[u] = make_float4(0, 0, 0, 0);
+    if (row < rows && live) {
+      const int b = row / d.L, l = row - b * d.L;
+      const int g = row / rpg;
       if (g != gcur) {
         a0 = bn_affine(d.src[0], g, d.C, c0);
         if (d.nsrc > 1) a1 = bn_affine(d.src[1], g, d.C, c0);
         gcur = g;
       }
-      y = bn_src_eval<T>(d.src[0], a0, b, l, c0);
-      if (d.nsrc > 1) y = add4(y, bn_src_eval<T>(d.src[1], a1, b, l, c0));
+      y[u] = bn_src_eval<T>(d.src[0], a0, b, l, c0);
+      if (d.nsrc > 1) y[u] = add4(y[u], bn_src_eval<T>(d.src[1], a1, b, l, c0));
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int row = r0 + u * TY;
+    if (row >= rows) continue;
+    if (live) {
       if (drop.mode != B2H_DROP_NONE) {
         float4 m = drop.scale4((uint64_t)row * d.drop_C + d.drop_coff + c0);
-        y.x *= m.x, y.y *= m.y, y.z *= m.z, y.w *= m.w;
+        y[u].x *= m.x, y[u].y *= m.y, y[u].z *= m.z, y[u].w *= m.w;
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i)
-        if (c0 + i >= d.C) f4(y, i) = 0.f;
+        if (c0 + i >= d.C) f4(y[u], i) = 0.f;
     }
-    store4<T>(out + (int64_t)row * d.out_ld + d.out_coff + c0, y);
+    store4<T>(out + (int64_t)row * d.out_ld + d.out_coff + c0, y[u]);
   }
 }
 
@@ -249,8 +317,9 @@ int launch_bn_apply(const b2h_bn_apply_t& d, int dtype, cudaStream_t s) {
     B2H_CHECK_ARG(d.src[i].ld % 4 == 0 && d.src[i].coff % 4 == 0, B2H_ERR_ALIGN, "bn_apply: src alignment");
     B2H_CHECK_ARG(d.src[i].coff + d.C <= d.src[i].C_total, B2H_ERR_SHAPE, "bn_apply: source channel range");
   }
-  BlockShape bs = block_shape(d.Cfill);
-  dim3 grid(ceil_div(d.B * d.L, kBnChunkRows)), block(bs.txp, bs.ty);
+  int txp = std::min(pow2_ceil(ceil_div(d.Cfill, 4)), 256);
+  int ty = 256 / txp;
+  dim3 grid(ceil_div(d.B * d.L, ty * 4)), block(txp, ty);
   if (dtype == B2H_BF16)
     bn_apply_kernel<__nv_bfloat16><<<grid, block, 0, s>>>(d);
   else
@@ -304,23 +373,24 @@ __device__ __forceinline__ float4 bn_bwd_dy(const b2h_bn_bwd_t& d, const Affine4
 }
 
 template <typename T, int PASS>
-__global__ void __launch_bounds__(256) bn_bwd_kernel(b2h_bn_bwd_t d, int nchunks) {
-  __shared__ float4 s_a[256];
-  __shared__ float4 s_b[256];
+__global__ void __launch_bounds__(kRedThreads) bn_bwd_kernel(b2h_bn_bwd_t d, int nchunks, int R) {
+  __shared__ float4 s_red[kRedThreads];
+  __shared__ double s_dbl[2][kRedThreads];
   const int tx = threadIdx.x, ty = threadIdx.y, TXp = blockDim.x, TY = blockDim.y;
   const int chunk = blockIdx.x, g = blockIdx.y;
   const int c0 = tx * 4;
   const int rows = d.B * d.L;
   const int rpg = rows / d.groups;
-  const int r_begin = chunk * kBnChunkRows;
-  const int r_end = min(r_begin + kBnChunkRows, rpg);
+  const int r_begin = chunk * R;
+  const int r_end = min(r_begin + R, rpg);
   const T* z = reinterpret_cast<const T*>(d.bn.z);
   T* dpre = reinterpret_cast<T*>(d.dpre);
   float4 acc_a = make_float4(0, 0, 0, 0), acc_b = make_float4(0, 0, 0, 0);
   if (c0 < d.Cfill) {
     Affine4 aff;
     float4 mean4 = make_float4(0, 0, 0, 0), istd4 = mean4, sg4 = mean4, mdy = mean4, mdyz = mean4;
-    if (c0 < d.C) {
+    const bool live = c0 < d.C;
+    if (live) {
       aff = bn_affine(d.bn, g, d.C, c0);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -337,41 +407,48 @@ __global__ void __launch_bounds__(256) bn_bwd_kernel(b2h_bn_bwd_t d, int nchunks
         }
       }
     }
-    for (int r = r_begin + ty; r < r_end; r += TY) {
-      const int row = g * rpg + r;
-      const int b = row / d.L, l = row - b * d.L;
-      float4 out = make_float4(0, 0, 0, 0);
-      if (c0 < d.C) {
-        float4 zo = load4<T>(z + (int64_t)row * d.bn.ld + d.bn.coff + c0);
-        float4 dy = bn_bwd_dy<T>(d, aff, zo, b, l, c0);
+    for (int r = r_begin + ty; r < r_end; r += 2 * TY) {
+      float4 zo[2], dy[2];
+      int rowv[2];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          if (c0 + i < d.C) {
-            float zh = (f4(zo, i) - f4(mean4, i)) * f4(istd4, i);
-            if (PASS == 1) {
-              f4(acc_a, i) += f4(dy, i);
-              f4(acc_b, i) += f4(dy, i) * zh;
-            } else {
-              float dz = f4(sg4, i) * (f4(dy, i) - f4(mdy, i) - zh * f4(mdyz, i));
-              float dp = dz * act_bwd(f4(zo, i), d.act);
-              f4(out, i) = dp;
-              f4(acc_a, i) += dp;
+      for (int u = 0; u < 2; ++u) {
+        const int rr = r + u * TY;
+        rowv[u] = rr < r_end ? g * rpg + rr : -1;
+        zo[u] = dy[u] = make_float4(0, 0, 0, 0);
+        if (rowv[u] >= 0 && live) {
+          const int b = rowv[u] / d.L, l = rowv[u] - b * d.L;
+          zo[u] = load4<T>(z + (int64_t)rowv[u] * d.bn.ld + d.bn.coff + c0);
+          dy[u] = bn_bwd_dy<T>(d, aff, zo[u], b, l, c0);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (rowv[u] < 0) continue;
+        float4 out = make_float4(0, 0, 0, 0);
+        if (live) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (c0 + i < d.C) {
+              float zh = (f4(zo[u], i) - f4(mean4, i)) * f4(istd4, i);
+              if (PASS == 1) {
+                f4(acc_a, i) += f4(dy[u], i);
+                f4(acc_b, i) = fmaf(f4(dy[u], i), zh, f4(acc_b, i));
+              } else {
+                float dz = f4(sg4, i) * (f4(dy[u], i) - f4(mdy, i) - zh * f4(mdyz, i));
+                float dp = dz * act_bwd(f4(zo[u], i), d.act);
+                f4(out, i) = dp;
+                f4(acc_a, i) += dp;
+              }
             }
           }
         }
+        if (PASS == 2) store4<T>(dpre + (int64_t)rowv[u] * d.ld_dpre + c0, out);
       }
-      if (PASS == 2) store4<T>(dpre + (int64_t)row * d.ld_dpre + c0, out);
     }
   }
-  const int sidx = ty * TXp + tx;
-  s_a[sidx] = acc_a;
-  s_b[sidx] = acc_b;
-  __syncthreads();
+  reduce_over_ty(s_red, acc_a, tx, ty, TXp, TY);
+  if (PASS == 1) reduce_over_ty(s_red, acc_b, tx, ty, TXp, TY);
   if (ty == 0 && c0 < d.C) {
-    for (int j = 1; j < TY; ++j) {
-      acc_a = add4(acc_a, s_a[j * TXp + tx]);
-      acc_b = add4(acc_b, s_b[j * TXp + tx]);
-    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       int c = c0 + i;
@@ -384,51 +461,65 @@ __global__ void __launch_bounds__(256) bn_bwd_kernel(b2h_bn_bwd_t d, int nchunks
   }
   if (!last_block_done(d.ticket, gridDim.x * gridDim.y)) return;
   const int tid = ty * TXp + tx;
-  for (int c = tid; c < d.C; c += 256) {
-    double tot_a = 0.0, tot_b = 0.0;
-    for (int gg = 0; gg < d.groups; ++gg) {
-      double sa = 0.0, sb = 0.0;
-      for (int ch = 0; ch < nchunks; ++ch) {
-        const float* p = d.partial + (((int64_t)ch * d.groups + gg) * d.C + c) * 2;
+  const FinalLanes fl(d.C, tid);
+  const bool act = fl.c < d.C && fl.lane < fl.NL;
+  double tot_a = 0.0, tot_b = 0.0;
+  for (int gg = 0; gg < d.groups; ++gg) {
+    double sa = 0.0, sb = 0.0;
+    if (act)
+      for (int ch = fl.lane; ch < nchunks; ch += fl.NL) {
+        const float* p = d.partial + (((int64_t)ch * d.groups + gg) * d.C + fl.c) * 2;
         sa += (double)__ldcg(p);
-        sb += (double)__ldcg(p + 1);
+        if (PASS == 1) sb += (double)__ldcg(p + 1);
+      }
+    __syncthreads();
+    s_dbl[0][tid] = sa;
+    s_dbl[1][tid] = sb;
+    __syncthreads();
+    if (act && fl.lane == 0) {
+      double ta = 0.0, tb = 0.0;
+      for (int l = 0; l < fl.NL; ++l) {
+        ta += s_dbl[0][l * fl.Cp2 + fl.c];
+        tb += s_dbl[1][l * fl.Cp2 + fl.c];
       }
       if (PASS == 1) {
-        d.sums[((int64_t)gg * d.C + c) * 2 + 0] = (float)sa;
-        d.sums[((int64_t)gg * d.C + c) * 2 + 1] = (float)sb;
+        d.sums[((int64_t)gg * d.C + fl.c) * 2 + 0] = (float)ta;
+        d.sums[((int64_t)gg * d.C + fl.c) * 2 + 1] = (float)tb;
       }
-      tot_a += sa;
-      tot_b += sb;
+      tot_a += ta;
+      tot_b += tb;
     }
+  }
+  if (act && fl.lane == 0) {
     if (PASS == 1) {
-      if (d.dbeta) d.dbeta[c] = (float)tot_a;
-      if (d.dgamma) d.dgamma[c] = (float)tot_b;
+      if (d.dbeta) d.dbeta[fl.c] = (float)tot_a;
+      if (d.dgamma) d.dgamma[fl.c] = (float)tot_b;
     } else {
-      if (d.dbias) d.dbias[c] = (float)tot_a;
+      if (d.dbias) d.dbias[fl.c] = (float)tot_a;
     }
   }
 }
 
 int launch_bn_bwd(const b2h_bn_bwd_t& d, int dtype, cudaStream_t s) {
-  B2H_CHECK_ARG(d.C > 0 && d.Cfill >= d.C && d.Cfill <= 1024 && d.groups >= 1 && d.ngsrc >= 1 && d.ngsrc <= 2,
+  B2H_CHECK_ARG(d.C > 0 && d.C <= 512 && d.Cfill >= d.C && d.Cfill <= 1024 && d.groups >= 1 && d.ngsrc >= 1 &&
+                    d.ngsrc <= 2,
                 B2H_ERR_SHAPE, "bn_bwd: bad shape C=%d Cfill=%d ngsrc=%d", d.C, d.Cfill, d.ngsrc);
   B2H_CHECK_ARG(d.Cfill % 4 == 0 && d.ld_dpre % 4 == 0 && d.bn.ld % 4 == 0 && d.bn.coff % 4 == 0, B2H_ERR_ALIGN,
                 "bn_bwd: alignment");
   B2H_CHECK_ARG((d.B * d.L) % d.groups == 0, B2H_ERR_SHAPE, "bn_bwd: rows not divisible by groups");
   B2H_CHECK_ARG(!d.bn.use_running, B2H_ERR_ARG, "bn_bwd: backward is only defined for batch statistics");
   B2H_CHECK_ARG(d.bn.coff == 0 && d.bn.C_total == d.C, B2H_ERR_SHAPE, "bn_bwd: bn source must cover the whole layer");
-  BlockShape bs = block_shape(d.Cfill);
   int rpg = d.B * d.L / d.groups;
-  int nchunks = bn_nchunks(rpg);
-  dim3 grid(nchunks, d.groups), block(bs.txp, bs.ty);
+  RedShape rs = red_shape(d.Cfill, rpg, kRedThreads);
+  dim3 grid(rs.nchunks, d.groups), block(rs.txp, rs.ty);
   if (dtype == B2H_BF16) {
-    bn_bwd_kernel<__nv_bfloat16, 1><<<grid, block, 0, s>>>(d, nchunks);
+    bn_bwd_kernel<__nv_bfloat16, 1><<<grid, block, 0, s>>>(d, rs.nchunks, rs.rows_per_chunk);
     B2H_LAUNCH_CHECK("bn_bwd pass 1");
-    bn_bwd_kernel<__nv_bfloat16, 2><<<grid, block, 0, s>>>(d, nchunks);
+    bn_bwd_kernel<__nv_bfloat16, 2><<<grid, block, 0, s>>>(d, rs.nchunks, rs.rows_per_chunk);
   } else {
-    bn_bwd_kernel<float, 1><<<grid, block, 0, s>>>(d, nchunks);
+    bn_bwd_kernel<float, 1><<<grid, block, 0, s>>>(d, rs.nchunks, rs.rows_per_chunk);
     B2H_LAUNCH_CHECK("bn_bwd pass 1");
-    bn_bwd_kernel<float, 2><<<grid, block, 0, s>>>(d, nchunks);
+    bn_bwd_kernel<float, 2><<<grid, block, 0, s>>>(d, rs.nchunks, rs.rows_per_chunk);
   }
   B2H_LAUNCH_CHECK("bn_bwd pass 2");
   return B2H_OK;
@@ -438,41 +529,48 @@ int launch_bn_bwd(const b2h_bn_bwd_t& d, int dtype, cudaStream_t s) {
 // colsum: out[c] = sum over rows of src[row][c] (bias gradients of layers without BN)
 // ---------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(256) colsum_kernel(b2h_colsum_t d, int nchunks) {
-  __shared__ float4 s_a[256];
+__global__ void __launch_bounds__(kRedThreads) colsum_kernel(b2h_colsum_t d, int nchunks, int R) {
+  __shared__ float4 s_red[kRedThreads];
+  __shared__ double s_dbl[kRedThreads];
   const int tx = threadIdx.x, ty = threadIdx.y, TXp = blockDim.x, TY = blockDim.y;
   const int c0 = tx * 4;
-  const int r_begin = blockIdx.x * kBnChunkRows;
-  const int r_end = min(r_begin + kBnChunkRows, d.rows);
+  const int r_begin = blockIdx.x * R;
+  const int r_end = min(r_begin + R, d.rows);
   float4 acc = make_float4(0, 0, 0, 0);
   if (c0 < d.C)
     for (int r = r_begin + ty; r < r_end; r += TY)
       acc = add4(acc, load4<T>(reinterpret_cast<const T*>(d.src) + (int64_t)r * d.ld + c0));
-  s_a[ty * TXp + tx] = acc;
-  __syncthreads();
+  reduce_over_ty(s_red, acc, tx, ty, TXp, TY);
   if (ty == 0 && c0 < d.C) {
-    for (int j = 1; j < TY; ++j) acc = add4(acc, s_a[j * TXp + tx]);
 #pragma unroll
     for (int i = 0; i < 4; ++i)
       if (c0 + i < d.C) d.partial[(int64_t)blockIdx.x * d.C + c0 + i] = f4(acc, i);
   }
   if (!last_block_done(d.ticket, gridDim.x)) return;
-  for (int c = ty * TXp + tx; c < d.C; c += 256) {
-    double sa = 0.0;
-    for (int ch = 0; ch < nchunks; ++ch) sa += (double)__ldcg(d.partial + (int64_t)ch * d.C + c);
-    d.out[c] = (float)sa;
+  const int tid = ty * TXp + tx;
+  const FinalLanes fl(d.C, tid);
+  const bool act = fl.c < d.C && fl.lane < fl.NL;
+  double sa = 0.0;
+  if (act)
+    for (int ch = fl.lane; ch < nchunks; ch += fl.NL) sa += (double)__ldcg(d.partial + (int64_t)ch * d.C + fl.c);
+  __syncthreads();
+  s_dbl[tid] = sa;
+  __syncthreads();
+  if (act && fl.lane == 0) {
+    double t = 0.0;
+    for (int l = 0; l < fl.NL; ++l) t += s_dbl[l * fl.Cp2 + fl.c];
+    d.out[fl.c] = (float)t;
   }
 }
 
 int launch_colsum(const b2h_colsum_t& d, int dtype, cudaStream_t s) {
-  B2H_CHECK_ARG(d.C > 0 && d.C <= 1024 && d.rows > 0 && d.ld % 4 == 0, B2H_ERR_SHAPE, "colsum: bad shape");
-  BlockShape bs = block_shape(d.C);
-  int nchunks = ceil_div(d.rows, kBnChunkRows);
-  dim3 grid(nchunks), block(bs.txp, bs.ty);
+  B2H_CHECK_ARG(d.C > 0 && d.C <= 512 && d.rows > 0 && d.ld % 4 == 0, B2H_ERR_SHAPE, "colsum: bad shape");
+  RedShape rs = red_shape(d.C, d.rows, kRedThreads);
+  dim3 grid(rs.nchunks), block(rs.txp, rs.ty);
   if (dtype == B2H_BF16 && !d.f32)
-    colsum_kernel<__nv_bfloat16><<<grid, block, 0, s>>>(d, nchunks);
+    colsum_kernel<__nv_bfloat16><<<grid, block, 0, s>>>(d, rs.nchunks, rs.rows_per_chunk);
   else
-    colsum_kernel<float><<<grid, block, 0, s>>>(d, nchunks);
+    colsum_kernel<float><<<grid, block, 0, s>>>(d, rs.nchunks, rs.rows_per_chunk);
   B2H_LAUNCH_CHECK("colsum");
   return B2H_OK;
 }

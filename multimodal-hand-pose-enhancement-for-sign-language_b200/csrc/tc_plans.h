@@ -11,6 +11,7 @@ namespace b2h {
 struct TcGemmParams {
   int B, Lo, Kc, stride;
   int tl, tb, n_lchunks;  // M tile = tb samples x tl rows (tl * tb = 128)
+  int tl_log2;
   int ntaps;
   int tap_map[B2H_MAX_TAPS];    // 0: base / even-row view, 1: odd-row view
   int tap_coord[B2H_MAX_TAPS];  // row coordinate offset inside that view

@@ -478,8 +478,10 @@ class NetPlan:
         self.out = self._zeros(B, ol.cout, olb.Lz, dtype=torch.float32)   # (B, C_out, T) NCL
 
         with P.segment("pack"):
+            self._pack_items: List[dict] = []
             for l in spec.layers:
                 self._emit_pack(l)
+            self._emit_pack_table()
         with P.segment("fwd"):
             for l in spec.layers:
                 self._emit_input(l)
@@ -507,6 +509,25 @@ class NetPlan:
         self._pending_partial.append((idx, fld))
 
     # ---- pack --------------------------------------------------------------------------------
+    def _add_pack(self, tag: str, **fields):
+        fields["_tag"] = tag
+        self._pack_items.append(fields)
+
+    def _emit_pack_table(self):
+        """All weight repacks of the network as ONE launch: a device array of b2h_pack_t descriptors."""
+        import ctypes as C
+        from .program import _fill_struct
+        n = len(self._pack_items)
+        raw = bytearray()
+        max_elems = 0
+        for it in self._pack_items:
+            st = _fill_struct(L.Pack(), {k: v for k, v in it.items() if not k.startswith("_")})
+            raw += bytes(st)
+            max_elems = max(max_elems, it["nphase"] * it["Opad"] * it["ntaps"] * it["Ipad"])
+        self.pack_table = torch.frombuffer(raw, dtype=torch.uint8).clone().to(self.device)
+        self.prog.add(L.OP_PACK_MULTI, "pack_multi", descs=self.pack_table, n=n, max_elems=max_elems,
+                      _items=self._pack_items)
+
     def _emit_pack(self, l: Layer):
         P, st, lb = self.prog, self.store, self.bufs[l.name]
         W = st.p(l.wkey + ".weight")
@@ -516,7 +537,7 @@ class NetPlan:
         if l.kind in ("conv", "linear"):
             lb.fwd_taps = [t - l.pad for t in range(k)]
             lb.wf = self._zeros(lb.Cp, k, lb.Kc)
-            P.add(L.OP_PACK, f"pack.{l.name}.fwd", W=W, out=lb.wf, O=l.cout, I=l.cin, Opad=lb.Cp, Ipad=lb.Kc,
+            self._add_pack(f"pack.{l.name}.fwd", W=W, out=lb.wf, O=l.cout, I=l.cin, Opad=lb.Cp, Ipad=lb.Kc,
                   ntaps=k, nphase=1, o_stride=l.cin * k, i_stride=k, k_stride=1,
                   tapmap=[list(range(k)) + [-1] * (L.MAX_TAPS - k), [-1] * L.MAX_TAPS], bias=bias, out_bias=lb.bias)
         else:  # convT k7 s2 p3 op1 as a 2-phase sub-pixel conv over taps {-1, 0, 1, 2}
@@ -525,7 +546,7 @@ class NetPlan:
             lb.wf = self._zeros(2 * lb.Cp, 4, lb.Kc)
             tm = [[3 - 2 * o for o in lb.fwd_taps], [4 - 2 * o for o in lb.fwd_taps]]
             tm = [[kk if 0 <= kk < k else -1 for kk in row] + [-1] * 4 for row in tm]
-            P.add(L.OP_PACK, f"pack.{l.name}.fwd", W=W, out=lb.wf, O=l.cout, I=l.cin, Opad=lb.Cp, Ipad=lb.Kc,
+            self._add_pack(f"pack.{l.name}.fwd", W=W, out=lb.wf, O=l.cout, I=l.cin, Opad=lb.Cp, Ipad=lb.Kc,
                   ntaps=4, nphase=2, o_stride=k, i_stride=l.cout * k, k_stride=1, tapmap=tm, bias=bias,
                   out_bias=lb.bias)
         if not (self.train and self._needs_dgrad(l)):
@@ -535,7 +556,7 @@ class NetPlan:
             lb.bwd_taps = [kk - l.pad for kk in range(k)]
             lb.bwd_stride, lb.bwd_nphase = 2, 1
             lb.wb = self._zeros(lb.Kc, k, lb.Cp)
-            P.add(L.OP_PACK, f"pack.{l.name}.bwd", W=W, out=lb.wb, O=l.cin, I=l.cout, Opad=lb.Kc, Ipad=lb.Cp,
+            self._add_pack(f"pack.{l.name}.bwd", W=W, out=lb.wb, O=l.cin, I=l.cout, Opad=lb.Kc, Ipad=lb.Cp,
                   ntaps=k, nphase=1, o_stride=l.cout * k, i_stride=k, k_stride=1,
                   tapmap=[list(range(k)) + [-1] * (L.MAX_TAPS - k), [-1] * L.MAX_TAPS], bias=None, out_bias=None)
         elif l.stride == 1:
@@ -543,7 +564,7 @@ class NetPlan:
             offs = [t - (k - 1 - l.pad) for t in range(k)]
             lb.bwd_taps, lb.bwd_stride, lb.bwd_nphase = offs, 1, 1
             lb.wb = self._zeros(lb.Kc, k, lb.Cp)
-            P.add(L.OP_PACK, f"pack.{l.name}.bwd", W=W, out=lb.wb, O=l.cin, I=l.cout, Opad=lb.Kc, Ipad=lb.Cp,
+            self._add_pack(f"pack.{l.name}.bwd", W=W, out=lb.wb, O=l.cin, I=l.cout, Opad=lb.Kc, Ipad=lb.Cp,
                   ntaps=k, nphase=1, o_stride=k, i_stride=l.cin * k, k_stride=1,
                   tapmap=[[l.pad - o for o in offs] + [-1] * (L.MAX_TAPS - k), [-1] * L.MAX_TAPS], bias=None,
                   out_bias=None)
@@ -555,7 +576,7 @@ class NetPlan:
             tm = [[(ph + l.pad - 2 * o) for o in cand] for ph in (0, 1)]
             tm = [[kk if 0 <= kk < k else -1 for kk in row] + [-1] * (L.MAX_TAPS - len(cand)) for row in tm]
             lb.wb = self._zeros(2 * lb.Kc, len(cand), lb.Cp)
-            P.add(L.OP_PACK, f"pack.{l.name}.bwd", W=W, out=lb.wb, O=l.cin, I=l.cout, Opad=lb.Kc, Ipad=lb.Cp,
+            self._add_pack(f"pack.{l.name}.bwd", W=W, out=lb.wb, O=l.cin, I=l.cout, Opad=lb.Kc, Ipad=lb.Cp,
                   ntaps=len(cand), nphase=2, o_stride=k, i_stride=l.cin * k, k_stride=1, tapmap=tm, bias=None,
                   out_bias=None)
 
@@ -648,7 +669,7 @@ class NetPlan:
             # dpre is provided by the loss (or by an external output gradient); bias grad = column sums
             i = P.add(L.OP_COLSUM, f"dbias.{l.name}", src=lb.dpre, out=st.g(l.wkey + ".bias"), partial=None,
                       ticket=self._ticket(), rows=rows, ld=lb.Cp, C=l.cout, f32=0)
-            self._need_partial(i, _ceil_div(rows, 64) * l.cout)
+            self._need_partial(i, 128 * l.cout)
         else:
             lb.dpre = self._zeros(B, lb.Lz, lb.Cp)
             gs = []
@@ -716,8 +737,7 @@ def _ceil_div(a, b):
 
 
 def _bn_partial_floats(rows, C, groups):
-    rpg = rows // groups
-    return _ceil_div(rpg, 64) * groups * C * 2
+    return 128 * groups * C * 2   # kMaxChunks partials of (a, b) per group and channel
 
 
 def _wgrad_ws_bytes(rec, dtype) -> int:

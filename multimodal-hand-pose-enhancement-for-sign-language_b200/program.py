@@ -68,7 +68,7 @@ def _fill_struct(st, fields: dict):
 
 def lower(rec: OpRec):
     st = L.OP_STRUCT[rec.kind]()
-    unknown = set(rec.f) - {n for n, _ in st._fields_}
+    unknown = {k for k in rec.f if not k.startswith("_")} - {n for n, _ in st._fields_}
     if unknown:
         raise KeyError(f"{rec}: unknown fields {sorted(unknown)}")
     return _fill_struct(st, rec.f)

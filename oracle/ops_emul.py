@@ -22,7 +22,7 @@ ROW_IDENT, ROW_UP2, ROW_POOL2, ROW_BCAST = 0, 1, 2, 3
 SRC_NCL, SRC_ROWS, SRC_BCAST, SRC_MOTION = 0, 1, 2, 3
 DROP_NONE, DROP_MASK, DROP_PHILOX = 0, 1, 2
 (OP_GEMM, OP_WGRAD, OP_BN_STATS, OP_BN_APPLY, OP_BN_BWD, OP_PREP, OP_TO_NCL, OP_L1, OP_MSE, OP_COLSUM,
- OP_ADAM, OP_PACK, OP_BN_FOLD, OP_ROT6D, OP_FILL) = range(1, 16)
+ OP_ADAM, OP_PACK, OP_BN_FOLD, OP_ROT6D, OP_FILL, OP_PACK_MULTI) = range(1, 17)
 
 
 def _act(x, act):
@@ -356,6 +356,11 @@ def pack(f: Dict):
             f["out_bias"][: f["O"]] = f["bias"]
 
 
+def pack_multi(f: Dict):
+    for item in f["_items"]:
+        pack(item)
+
+
 def bn_fold(f: Dict):
     C = f["C"]
     invstd = 1.0 / torch.sqrt(f["running_var"][:C] + f["eps"])
@@ -387,7 +392,8 @@ def fill(f: Dict):
 
 DISPATCH = {OP_GEMM: gemm, OP_WGRAD: wgrad, OP_BN_STATS: bn_stats, OP_BN_APPLY: bn_apply, OP_BN_BWD: bn_bwd,
             OP_PREP: prep, OP_TO_NCL: to_ncl, OP_L1: l1, OP_MSE: mse, OP_COLSUM: colsum, OP_ADAM: adam,
-            OP_PACK: pack, OP_BN_FOLD: bn_fold, OP_ROT6D: rot6d, OP_FILL: fill}
+            OP_PACK: pack, OP_BN_FOLD: bn_fold, OP_ROT6D: rot6d, OP_FILL: fill,
+            OP_PACK_MULTI: pack_multi}
 
 
 def run_records(recs, first=0, end=None):
