@@ -68,6 +68,8 @@ typedef struct {
   int32_t site;
   const uint8_t* mask;   /* MASK: [rows][C] keep flags, C = drop_C of the op */
   const uint64_t* state; /* PHILOX: device {seed, step} */
+  uint8_t* save;         /* forward ops, optional: the keep flags this op applied are also written here
+                            ([rows][C]) so that the backward replays them in MASK mode */
 } b2h_dropout_t;
 
 /* ------------------------------------------------------------------------------------------- */

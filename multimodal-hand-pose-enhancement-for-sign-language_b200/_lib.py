@@ -21,7 +21,7 @@ i32, i64, f32, f64, vp = C.c_int32, C.c_int64, C.c_float, C.c_double, C.c_void_p
 
 
 class Dropout(C.Structure):
-    _fields_ = [("mode", i32), ("site", i32), ("mask", vp), ("state", vp)]
+    _fields_ = [("mode", i32), ("site", i32), ("mask", vp), ("state", vp), ("save", vp)]
 
 
 class Gemm(C.Structure):

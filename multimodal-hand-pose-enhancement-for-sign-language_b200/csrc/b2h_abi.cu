@@ -1,6 +1,7 @@
 // C ABI of libb2h.so: error state, one-shot entry points and recorded programs.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>

@@ -3,6 +3,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/b2h_abi.h"
 
@@ -26,6 +27,21 @@ extern thread_local int64_t g_launch_count;
     ::b2h::g_launch_count++;                                     \
     cudaError_t e__ = cudaGetLastError();                        \
     if (e__ != cudaSuccess) return ::b2h::cuda_fail(e__, what);  \
+  } while (0)
+
+// Every kernel asks for the maximum shared-memory carveout so that consecutive launches never force the SM
+// to re-partition L1/shared memory (the tensor-core kernels need ~100-200 KB; the elementwise ones need none).
+#define B2H_CARVE(...)                                                                                     \
+  do {                                                                                                     \
+    static bool done__ = false;                                                                            \
+    if (!done__) {                                                                                         \
+      done__ = true;                                                                                       \
+      if (!getenv("B2H_NO_CARVEOUT")) {                                                                    \
+        cudaFuncSetAttribute(__VA_ARGS__, cudaFuncAttributePreferredSharedMemoryCarveout,                  \
+                             (int)cudaSharedmemCarveoutMaxShared);                                         \
+        cudaGetLastError();                                                                                \
+      }                                                                                                    \
+    }                                                                                                      \
   } while (0)
 
 constexpr float kLeakySlope = 0.2f;  // nn.LeakyReLU(0.2, True), modelZoo.py:195
@@ -98,12 +114,14 @@ struct DropCtx {
   int mode;
   uint32_t site;
   const uint8_t* mask;
+  uint8_t* save;
   uint2 key;      // seed
   uint32_t step;  // low 32 bits of the step counter
   __device__ __forceinline__ void init(const b2h_dropout_t& d) {
     mode = d.mode;
     site = (uint32_t)d.site;
     mask = d.mask;
+    save = d.save;
     key = make_uint2(0u, 0u);
     step = 0u;
     if (mode == B2H_DROP_PHILOX) {
@@ -131,6 +149,16 @@ struct DropCtx {
                          (r.w >> 31) ? 2.f : 0.f);
     }
     return make_float4(scale1(idx), scale1(idx + 1), scale1(idx + 2), scale1(idx + 3));
+  }
+  // record the keep flags of elements idx .. idx+n-1 (n <= 4) for the backward pass
+  __device__ __forceinline__ void save4(uint64_t idx, float4 m, int n) const {
+    if (!save) return;
+    if (n == 4 && (idx & 3) == 0) {
+      uchar4 k = make_uchar4(m.x != 0.f, m.y != 0.f, m.z != 0.f, m.w != 0.f);
+      *reinterpret_cast<uchar4*>(save + idx) = k;
+    } else {
+      for (int i = 0; i < n; ++i) save[idx + i] = (&m.x)[i] != 0.f;
+    }
   }
 };
 

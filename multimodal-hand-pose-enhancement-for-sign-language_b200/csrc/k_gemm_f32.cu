@@ -115,6 +115,7 @@ static int check_gemm(const b2h_gemm_t& d) {
 }
 
 int launch_gemm_f32(const b2h_gemm_t& d, cudaStream_t s) {
+  B2H_CARVE(gemm_f32_kernel);
   int rc = check_gemm(d);
   if (rc) return rc;
   dim3 grid(ceil_div(d.B * d.Lo, F_BM), d.Npad / F_BN);
@@ -227,6 +228,7 @@ int wgrad_choose_splits(const b2h_wgrad_t& d, int dtype) {
 }
 
 int launch_wgrad_reduce(const b2h_wgrad_t& d, int splits, cudaStream_t s) {
+  B2H_CARVE(wgrad_reduce_kernel);
   int64_t total = (int64_t)d.ntaps * d.Mvalid * d.Nvalid;
   int blocks = (int)std::min<int64_t>(ceil_div64(total, 256), (int64_t)sm_count() * 8);
   wgrad_reduce_kernel<<<blocks, 256, 0, s>>>(d, splits);
@@ -235,6 +237,7 @@ int launch_wgrad_reduce(const b2h_wgrad_t& d, int splits, cudaStream_t s) {
 }
 
 int launch_wgrad_f32(const b2h_wgrad_t& d, cudaStream_t s) {
+  B2H_CARVE(wgrad_simt_kernel<float>);
   int rc = check_wgrad(d);
   if (rc) return rc;
   int splits = wgrad_choose_splits(d, B2H_F32);

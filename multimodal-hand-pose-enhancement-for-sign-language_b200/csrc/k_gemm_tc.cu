@@ -37,8 +37,40 @@ struct FpropCfg {
   static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
   static constexpr int EPI_BYTES = 128 * EPI_PITCH_MAX;
   static constexpr int MAIN_BYTES = PIPE_BYTES > EPI_BYTES ? PIPE_BYTES : EPI_BYTES;
-  static constexpr int SMEM_BYTES = MAIN_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = MAIN_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + BN * 4 /*bias*/;
 };
+
+constexpr int TC_THREADS = 64 + 256;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (2 per TMEM sub-partition)
+
+// specialised epilogues (everything else falls back to EPI_GENERIC)
+enum { EPI_GENERIC = 0, EPI_BIAS_LEAKY = 1, EPI_BIAS_RELU = 2, EPI_BIAS_F32 = 3, EPI_MASK = 4, EPI_PLAIN = 5 };
+
+template <int KIND>
+__device__ __forceinline__ void epi_fast8(const float* s_bias, const uint8_t* mask_row, int col, int nn,
+                                          const uint32_t* acc_bits, float* v) {
+  float4 b0 = make_float4(0, 0, 0, 0), b1 = b0;
+  if (KIND == EPI_BIAS_LEAKY || KIND == EPI_BIAS_RELU || KIND == EPI_BIAS_F32) {
+    b0 = *reinterpret_cast<const float4*>(s_bias + col);
+    b1 = *reinterpret_cast<const float4*>(s_bias + col + 4);
+  }
+  const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+  uint32_t m0 = 0x01010101u, m1 = 0x01010101u;
+  if (KIND == EPI_MASK) {
+    m0 = *reinterpret_cast<const uint32_t*>(mask_row + nn);
+    m1 = *reinterpret_cast<const uint32_t*>(mask_row + nn + 4);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float x = __uint_as_float(acc_bits[j]) + bb[j];
+    if (KIND == EPI_BIAS_LEAKY) x = x > 0.f ? x : x * kLeakySlope;
+    if (KIND == EPI_BIAS_RELU) x = x > 0.f ? x : 0.f;
+    if (KIND == EPI_MASK) {
+      uint32_t byte = ((j < 4 ? m0 : m1) >> (8 * (j & 3))) & 0xFFu;
+      x = byte ? 2.f * x : 0.f;
+    }
+    v[j] = x;
+  }
+}
 
 // finish 8 accumulator columns [nn, nn+8) of one output row: bias -> act -> eval-BN -> dropout keep*2
 __device__ __forceinline__ void epi_finish8(const EpiParams& e, const DropCtx& drop, uint64_t drop_row_base, int nn,
@@ -66,8 +98,8 @@ __device__ __forceinline__ void epi_finish8(const EpiParams& e, const DropCtx& d
   }
 }
 
-template <int BN>
-__global__ void __launch_bounds__(192, FpropCfg<BN>::OCC)
+template <int BN, int KIND>
+__global__ void __launch_bounds__(TC_THREADS, FpropCfg<BN>::OCC)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmB, TcGemmParams p, EpiParams e) {
   using Cfg = FpropCfg<BN>;
@@ -78,6 +110,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  float* s_bias = reinterpret_cast<float*>(smem + Cfg::MAIN_BYTES + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mt = blockIdx.x, nt = blockIdx.y;
@@ -143,16 +176,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       umma_commit(tmem_full_bar);
     }
   } else {
-    // epilogue warps 2..5 -> TMEM sub-partitions (warp % 4).
+    // epilogue warps 2..9: TMEM sub-partition = warp % 4 (hardware rule), two warps per sub-partition split
+    // the tile columns.
     // stage 1: thread == tile row: tcgen05.ld -> bias/act/BN/dropout -> own row of a padded smem tile
-    // stage 2: the warp copies its 32 rows out with row-contiguous 16-byte accesses (coalesced)
+    // stage 2: the two warps of a sub-partition copy its 32 rows out with row-contiguous 16-byte accesses
     const int sub = warp & 3;
+    const int chalf = (warp - 2) >> 2;
     const int ph = n0 / e.half;           // a tile never straddles a sub-pixel phase
     const int nn0 = n0 - ph * e.half;     // first channel (within the phase) of this tile
     const int valid_cols = min(BN, e.Nvalid - nn0);
     const int esz = e.out_f32 ? 4 : 2;
     const int pitch = BN * esz + 16;
     uint8_t* stage = smem + (size_t)sub * 32 * pitch;
+    const int et = threadIdx.x - 64;      // 0..255
+    if (KIND == EPI_BIAS_LEAKY || KIND == EPI_BIAS_RELU || KIND == EPI_BIAS_F32) {
+      for (int i = et; i < BN; i += 256) s_bias[i] = e.bias[nn0 + i];
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
     DropCtx drop;
     drop.init(e.drop);
     {
@@ -161,19 +201,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const int b = b0 + bi, lo = l0 + li;
       const int64_t grow = (int64_t)b * e.Lo_actual + (int64_t)lo * e.nphase + ph;
       const uint64_t drop_row_base = (uint64_t)grow * (uint64_t)e.drop_C;
+      const bool row_in = (b < p.B) && (lo < p.Lo) && (lo * e.nphase + ph < e.Lo_actual);
+      const uint8_t* mask_row = (KIND == EPI_MASK && row_in) ? e.drop.mask + drop_row_base : nullptr;
       uint8_t* my = stage + (size_t)lane * pitch;
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
+      constexpr int CH = BN / 2;  // columns per epilogue warp
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
+      for (int c = chalf * CH; c < (chalf + 1) * CH; c += 32) {
         uint32_t acc[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)c, acc);
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
           float v[8];
-          epi_finish8(e, drop, drop_row_base, nn0 + c + j, acc + j, v);
-          if (e.out_f32) {
+          if (KIND == EPI_GENERIC) {
+            epi_finish8(e, drop, drop_row_base, nn0 + c + j, acc + j, v);
+          } else if (KIND == EPI_MASK) {
+            if (row_in && nn0 + c + j + 8 <= e.drop_C) {
+              epi_fast8<EPI_MASK>(s_bias, mask_row, c + j, nn0 + c + j, acc + j, v);
+            } else {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const int cc = nn0 + c + j + k;
+                const bool keep = row_in && cc < e.drop_C && mask_row[cc];
+                v[k] = keep ? 2.f * __uint_as_float(acc[j + k]) : 0.f;
+              }
+            }
+          } else {
+            epi_fast8<KIND>(s_bias, nullptr, c + j, nn0 + c + j, acc + j, v);
+          }
+          if (KIND == EPI_BIAS_F32 || (KIND == EPI_GENERIC && e.out_f32)) {
             float4* dst = reinterpret_cast<float4*>(my + (size_t)(c + j) * 4);
             dst[0] = make_float4(v[0], v[1], v[2], v[3]);
             dst[1] = make_float4(v[4], v[5], v[6], v[7]);
@@ -190,12 +248,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
       }
     }
-    __syncwarp();
+    // both warps of this sub-partition have written their column halves
+    asm volatile("bar.sync %0, 64;" ::"r"(2 + sub) : "memory");
     if (valid_cols > 0) {
       const int row_bytes = valid_cols * esz;
       const int full16 = row_bytes >> 4;  // 16-byte chunks that are entirely valid
 #pragma unroll 1
-      for (int rr = 0; rr < 32; ++rr) {
+      for (int rr = chalf * 16; rr < chalf * 16 + 16; ++rr) {
         const int r = sub * 32 + rr;
         const int bi = r >> p.tl_log2, li = r & (p.tl - 1);
         const int b = b0 + bi, lo = l0 + li;
@@ -544,27 +603,56 @@ int plan_gemm_bf16(const b2h_gemm_t& d, TcGemmPlan* plan) {
   return rc;
 }
 
-template <int BN>
+static int epi_kind(const b2h_gemm_t& d) {
+  if (getenv("B2H_GENERIC_EPI")) return EPI_GENERIC;
+  if (d.post_scale) return EPI_GENERIC;
+  const bool nodrop = d.drop.mode == B2H_DROP_NONE;
+  if (d.bias && nodrop && !d.out_f32 && d.act == B2H_ACT_LEAKY) return EPI_BIAS_LEAKY;
+  if (d.bias && nodrop && !d.out_f32 && d.act == B2H_ACT_RELU) return EPI_BIAS_RELU;
+  if (d.bias && nodrop && d.out_f32 && d.act == B2H_ACT_NONE) return EPI_BIAS_F32;
+  if (!d.bias && !d.out_f32 && d.act == B2H_ACT_NONE && d.drop.mode == B2H_DROP_MASK && d.drop_C % 4 == 0 &&
+      ((uintptr_t)d.drop.mask % 4) == 0)
+    return EPI_MASK;
+  if (!d.bias && !d.out_f32 && d.act == B2H_ACT_NONE && nodrop) return EPI_PLAIN;
+  return EPI_GENERIC;
+}
+
+template <int BN, int KIND>
 static int launch_fprop(const TcGemmPlan& plan, const EpiParams& e, cudaStream_t s) {
   using Cfg = FpropCfg<BN>;
+  B2H_CARVE(gemm_tc_kernel<BN, KIND>);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t er = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t er = cudaFuncSetAttribute(gemm_tc_kernel<BN, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          Cfg::SMEM_BYTES);
     if (er != cudaSuccess) return cuda_fail(er, "gemm_tc smem attribute");
     attr_set = true;
   }
   dim3 grid(plan.grid_x, plan.grid_y);
-  gemm_tc_kernel<BN><<<grid, 192, Cfg::SMEM_BYTES, s>>>(plan.tmA0, plan.tmA1, plan.tmB, plan.p, e);
+  gemm_tc_kernel<BN, KIND><<<grid, TC_THREADS, Cfg::SMEM_BYTES, s>>>(plan.tmA0, plan.tmA1, plan.tmB, plan.p, e);
   B2H_LAUNCH_CHECK("gemm_tc");
   return B2H_OK;
 }
 
+template <int BN>
+static int launch_fprop_kind(const TcGemmPlan& plan, const EpiParams& e, int kind, cudaStream_t s) {
+  switch (kind) {
+    case EPI_BIAS_LEAKY: return launch_fprop<BN, EPI_BIAS_LEAKY>(plan, e, s);
+    case EPI_BIAS_RELU: return launch_fprop<BN, EPI_BIAS_RELU>(plan, e, s);
+    case EPI_BIAS_F32: return launch_fprop<BN, EPI_BIAS_F32>(plan, e, s);
+    case EPI_MASK: return launch_fprop<BN, EPI_MASK>(plan, e, s);
+    case EPI_PLAIN: return launch_fprop<BN, EPI_PLAIN>(plan, e, s);
+    default: return launch_fprop<BN, EPI_GENERIC>(plan, e, s);
+  }
+}
+
 int run_gemm_bf16(const TcGemmPlan& plan, const b2h_gemm_t& d, cudaStream_t s) {
   EpiParams e = make_epi(d);
+  const int kind = epi_kind(d);
   switch (plan.BN) {
-    case 256: return launch_fprop<256>(plan, e, s);
-    case 128: return launch_fprop<128>(plan, e, s);
-    default: return launch_fprop<64>(plan, e, s);
+    case 256: return launch_fprop_kind<256>(plan, e, kind, s);
+    case 128: return launch_fprop_kind<128>(plan, e, kind, s);
+    default: return launch_fprop_kind<64>(plan, e, kind, s);
   }
 }
 
@@ -607,6 +695,7 @@ int plan_wgrad_bf16(const b2h_wgrad_t& d, TcWgradPlan* plan) {
 
 template <int WN>
 static int launch_wg(const TcWgradPlan& plan, float* partial, cudaStream_t s) {
+  B2H_CARVE(wgrad_tc_kernel<WN>);
   using Cfg = WgradCfg<WN>;
   static bool attr_set = false;
   if (!attr_set) {

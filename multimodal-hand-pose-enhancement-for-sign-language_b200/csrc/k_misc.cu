@@ -43,10 +43,15 @@ __global__ void __launch_bounds__(256) prep_ncl_kernel(b2h_prep_t d) {
         if (c + 3 < d.C) {
           float4 m = drop.scale4(idx);
           v.x *= m.x, v.y *= m.y, v.z *= m.z, v.w *= m.w;
+          drop.save4(idx, m, 4);
         } else {
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            if (c + k < d.C) f4(v, k) *= drop.scale1(idx + k);
+            if (c + k < d.C) {
+              float mk = drop.scale1(idx + k);
+              f4(v, k) *= mk;
+              if (drop.save) drop.save[idx + k] = mk != 0.f;
+            }
         }
       }
     }
@@ -84,10 +89,15 @@ __global__ void __launch_bounds__(256) prep_rows_kernel(b2h_prep_t d) {
       if (c0 + 3 < d.C) {
         float4 m = drop.scale4(idx);
         v.x *= m.x, v.y *= m.y, v.z *= m.z, v.w *= m.w;
+        drop.save4(idx, m, 4);
       } else {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          if (c0 + k < d.C) f4(v, k) *= drop.scale1(idx + k);
+          if (c0 + k < d.C) {
+            float mk = drop.scale1(idx + k);
+            f4(v, k) *= mk;
+            if (drop.save) drop.save[idx + k] = mk != 0.f;
+          }
       }
     }
     if (d.out_f32)
@@ -98,6 +108,10 @@ __global__ void __launch_bounds__(256) prep_rows_kernel(b2h_prep_t d) {
 }
 
 int launch_prep(const b2h_prep_t& d, int dtype, cudaStream_t s) {
+  B2H_CARVE(prep_ncl_kernel<__nv_bfloat16>);
+  B2H_CARVE(prep_ncl_kernel<float>);
+  B2H_CARVE(prep_rows_kernel<__nv_bfloat16>);
+  B2H_CARVE(prep_rows_kernel<float>);
   B2H_CHECK_ARG(d.B > 0 && d.L > 0 && d.C > 0 && d.Cfill >= d.C && d.ld >= d.Cfill, B2H_ERR_SHAPE,
                 "prep: bad shape B=%d L=%d C=%d Cfill=%d ld=%d", d.B, d.L, d.C, d.Cfill, d.ld);
   if (d.kind == B2H_SRC_NCL || d.kind == B2H_SRC_MOTION) {
@@ -143,6 +157,8 @@ __global__ void __launch_bounds__(256) to_ncl_kernel(b2h_to_ncl_t d) {
 }
 
 int launch_to_ncl(const b2h_to_ncl_t& d, int dtype, cudaStream_t s) {
+  B2H_CARVE(to_ncl_kernel<__nv_bfloat16>);
+  B2H_CARVE(to_ncl_kernel<float>);
   B2H_CHECK_ARG(d.B > 0 && d.B <= 65535 && d.L > 0 && d.C > 0 && d.ld >= d.C, B2H_ERR_SHAPE, "to_ncl: bad shape");
   dim3 grid(ceil_div(d.L, 32), ceil_div(d.C, 32), d.B), block(32, 8);
   if (dtype == B2H_BF16 && !d.src_f32)
@@ -219,6 +235,8 @@ __global__ void __launch_bounds__(256) l1_kernel(b2h_l1_t d, int cext) {
 }
 
 int launch_l1(const b2h_l1_t& d, int dtype, cudaStream_t s) {
+  B2H_CARVE(l1_kernel<__nv_bfloat16>);
+  B2H_CARVE(l1_kernel<float>);
   B2H_CHECK_ARG(d.B > 0 && d.B <= 65535 && d.C > 0 && d.L > 0, B2H_ERR_SHAPE, "l1: bad shape");
   B2H_CHECK_ARG(!d.dout || (d.ld >= d.Cfill && d.Cfill >= d.C && d.Cfill % 4 == 0 && d.ld % 4 == 0), B2H_ERR_SHAPE,
                 "l1: bad dout shape");
@@ -262,6 +280,7 @@ __global__ void __launch_bounds__(256) mse_kernel(b2h_mse_t d) {
 }
 
 int launch_mse(const b2h_mse_t& d, cudaStream_t s) {
+  B2H_CARVE(mse_kernel);
   B2H_CHECK_ARG(d.groups >= 1 && d.groups <= 2 && d.n > 0 && d.ld >= 1, B2H_ERR_SHAPE, "mse: bad shape");
   mse_kernel<<<1, 256, 0, s>>>(d);
   B2H_LAUNCH_CHECK("mse");
@@ -318,6 +337,8 @@ __global__ void __launch_bounds__(256) adam_kernel(b2h_adam_t d) {
 }
 
 int launch_adam(const b2h_adam_t& d, cudaStream_t s) {
+  B2H_CARVE(adam_step_kernel);
+  B2H_CARVE(adam_kernel);
   B2H_CHECK_ARG(d.n > 0 && d.step, B2H_ERR_ARG, "adam: bad args");
   B2H_CHECK_ARG(((uintptr_t)d.p % 16 == 0) && ((uintptr_t)d.g % 16 == 0) && ((uintptr_t)d.m % 16 == 0) &&
                     ((uintptr_t)d.v % 16 == 0),
@@ -369,6 +390,8 @@ __global__ void __launch_bounds__(256) pack_multi_kernel(b2h_pack_multi_t m) {
 }
 
 int launch_pack_multi(const b2h_pack_multi_t& m, int dtype, cudaStream_t s) {
+  B2H_CARVE(pack_multi_kernel<__nv_bfloat16>);
+  B2H_CARVE(pack_multi_kernel<float>);
   B2H_CHECK_ARG(m.descs && m.n > 0 && m.n <= 65535 && m.max_elems > 0, B2H_ERR_ARG, "pack_multi: bad args");
   static_assert(sizeof(b2h_pack_t) % 4 == 0 && sizeof(b2h_pack_t) / 4 <= 256, "descriptor staging");
   int bx = (int)std::min<int64_t>(ceil_div64(m.max_elems, 256 * 8), 64);
@@ -382,6 +405,8 @@ int launch_pack_multi(const b2h_pack_multi_t& m, int dtype, cudaStream_t s) {
 }
 
 int launch_pack(const b2h_pack_t& d, int dtype, cudaStream_t s) {
+  B2H_CARVE(pack_kernel<__nv_bfloat16>);
+  B2H_CARVE(pack_kernel<float>);
   B2H_CHECK_ARG(d.O > 0 && d.I > 0 && d.Opad >= d.O && d.Ipad >= d.I && d.ntaps >= 1 && d.ntaps <= B2H_MAX_TAPS &&
                     d.nphase >= 1 && d.nphase <= 2,
                 B2H_ERR_SHAPE, "pack: bad shape");
@@ -418,6 +443,7 @@ __global__ void __launch_bounds__(256) rot6d_kernel(b2h_rot6d_t d) {
 }
 
 int launch_rot6d(const b2h_rot6d_t& d, cudaStream_t s) {
+  B2H_CARVE(rot6d_kernel);
   B2H_CHECK_ARG(d.n > 0, B2H_ERR_SHAPE, "rot6d: n must be positive");
   B2H_CHECK_ARG((uintptr_t)d.r6d % 8 == 0, B2H_ERR_ALIGN, "rot6d: input must be 8-byte aligned");
   int blocks = (int)std::min<int64_t>(ceil_div64(d.n, 256), (int64_t)sm_count() * 8);

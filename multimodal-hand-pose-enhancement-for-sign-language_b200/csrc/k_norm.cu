@@ -16,7 +16,7 @@ namespace b2h {
 // 4*tx .. 4*tx+3 and rows ty, ty+TY, ... of the CTA's row chunk.  Reduction kernels use 512 threads and at
 // most kMaxChunks chunks per group so that the ordered final merge by the last CTA stays short.
 constexpr int kRedThreads = 512;
-constexpr int kMaxChunks = 128;
+constexpr int kMaxChunks = 64;
 struct RedShape {
   int txp, ty, rows_per_chunk, nchunks;
 };
@@ -48,6 +48,23 @@ __device__ __forceinline__ void reduce_over_ty(float4* sm, float4& v, int tx, in
     __syncthreads();
   }
   v = sm[tx];
+}
+
+// lane-strided sum over chunks of the float2 partial[(chunk*groups + g)*C + c], 8 independent loads in flight
+template <typename F>
+__device__ __forceinline__ void lane_chunk_loop(const float* partial, int nchunks, int groups, int g, int C, int c,
+                                                int lane, int NL, F&& f) {
+  int ch = lane;
+  for (; ch + 7 * NL < nchunks; ch += 8 * NL) {
+    float2 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      v[u] = __ldcg(reinterpret_cast<const float2*>(partial + (((int64_t)(ch + u * NL) * groups + g) * C + c) * 2));
+#pragma unroll
+    for (int u = 0; u < 8; ++u) f(ch + u * NL, v[u]);
+  }
+  for (; ch < nchunks; ch += NL)
+    f(ch, __ldcg(reinterpret_cast<const float2*>(partial + (((int64_t)ch * groups + g) * C + c) * 2)));
 }
 
 // ordered sum over chunks of partial[(chunk*groups + g)*C + c][which] by the last CTA:
@@ -186,41 +203,28 @@ __global__ void __launch_bounds__(kRedThreads) bn_stats_kernel(b2h_bn_stats_t d,
   const FinalLanes fl(d.C, tid);
   const bool act = fl.c < d.C && fl.lane < fl.NL;
   for (int gg = 0; gg < d.groups; ++gg) {
-    // pass A: mean = sum n_c mean_c / N
-    double acc = 0.0;
+    // single pass in double: S0 = sum n_c mean_c, S1 = sum (M2_c + n_c mean_c^2); M2 = S1 - S0^2 / N
+    double s0 = 0.0, s1 = 0.0;
     if (act)
-      for (int ch = fl.lane; ch < nchunks; ch += fl.NL) {
-        double nb = (double)(min(ch * R + R, rpg) - ch * R);
-        acc += nb * (double)__ldcg(d.partial + (((int64_t)ch * d.groups + gg) * d.C + fl.c) * 2);
-      }
+      lane_chunk_loop(d.partial, nchunks, d.groups, gg, d.C, fl.c, fl.lane, fl.NL, [&](int ch, float2 v) {
+        const double nb = (double)(min(ch * R + R, rpg) - ch * R), m = (double)v.x;
+        s0 += nb * m;
+        s1 += (double)v.y + nb * m * m;
+      });
     __syncthreads();
-    s_dbl[tid] = acc;
-    __syncthreads();
-    if (act && fl.lane == 0) {
-      double t = 0.0;
-      for (int l = 0; l < fl.NL; ++l) t += s_dbl[l * fl.Cp2 + fl.c];
-      s_mean[fl.c] = t / (double)rpg;
-    }
-    __syncthreads();
-    // pass B: M2 = sum M2_c + n_c (mean_c - mean)^2
-    acc = 0.0;
-    if (act) {
-      const double mean = s_mean[fl.c];
-      for (int ch = fl.lane; ch < nchunks; ch += fl.NL) {
-        double nb = (double)(min(ch * R + R, rpg) - ch * R);
-        const float* p = d.partial + (((int64_t)ch * d.groups + gg) * d.C + fl.c) * 2;
-        double dm = (double)__ldcg(p) - mean;
-        acc += (double)__ldcg(p + 1) + nb * dm * dm;
-      }
-    }
-    __syncthreads();
-    s_dbl[tid] = acc;
+    s_dbl[tid] = s0;
+    s_mean[tid] = s1;
     __syncthreads();
     if (act && fl.lane == 0) {
-      double m2 = 0.0;
-      for (int l = 0; l < fl.NL; ++l) m2 += s_dbl[l * fl.Cp2 + fl.c];
+      double t0 = 0.0, t1 = 0.0;
+      for (int l = 0; l < fl.NL; ++l) {
+        t0 += s_dbl[l * fl.Cp2 + fl.c];
+        t1 += s_mean[l * fl.Cp2 + fl.c];
+      }
       const int c = fl.c;
-      const double mean = s_mean[c];
+      const double mean = t0 / (double)rpg;
+      double m2 = t1 - t0 * mean;
+      if (m2 < 0.0) m2 = 0.0;
       const double var_b = m2 / (double)rpg;
       d.mean[gg * d.C + c] = (float)mean;
       d.invstd[gg * d.C + c] = (float)(1.0 / sqrt(var_b + (double)d.eps));
@@ -238,10 +242,12 @@ __global__ void __launch_bounds__(kRedThreads) bn_stats_kernel(b2h_bn_stats_t d,
 
 int64_t bn_partial_floats(int rows, int C, int groups) {
   (void)rows;
-  return (int64_t)kMaxChunks * (groups > 0 ? groups : 1) * C * 2;
+  return (int64_t)128 * (groups > 0 ? groups : 1) * C * 2;
 }
 
 int launch_bn_stats(const b2h_bn_stats_t& d, int dtype, cudaStream_t s) {
+  B2H_CARVE(bn_stats_kernel<__nv_bfloat16>);
+  B2H_CARVE(bn_stats_kernel<float>);
   B2H_CHECK_ARG(d.C > 0 && d.C <= 512 && d.groups >= 1 && d.rows_per_group > 0, B2H_ERR_SHAPE,
                 "bn_stats: bad shape C=%d groups=%d rows=%d", d.C, d.groups, d.rows_per_group);
   B2H_CHECK_ARG(d.ld % 4 == 0 && d.ld >= ((d.C + 3) & ~3), B2H_ERR_ALIGN, "bn_stats: ld=%d C=%d", d.ld, d.C);
@@ -296,8 +302,10 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(b2h_bn_apply_t d) {
     if (row >= rows) continue;
     if (live) {
       if (drop.mode != B2H_DROP_NONE) {
-        float4 m = drop.scale4((uint64_t)row * d.drop_C + d.drop_coff + c0);
+        const uint64_t di = (uint64_t)row * d.drop_C + d.drop_coff + c0;
+        float4 m = drop.scale4(di);
         y[u].x *= m.x, y[u].y *= m.y, y[u].z *= m.z, y[u].w *= m.w;
+        drop.save4(di, m, min(4, d.C - c0));
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i)
@@ -308,6 +316,8 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(b2h_bn_apply_t d) {
 }
 
 int launch_bn_apply(const b2h_bn_apply_t& d, int dtype, cudaStream_t s) {
+  B2H_CARVE(bn_apply_kernel<__nv_bfloat16>);
+  B2H_CARVE(bn_apply_kernel<float>);
   B2H_CHECK_ARG(d.nsrc >= 1 && d.nsrc <= 2 && d.C > 0 && d.Cfill >= d.C && d.Cfill <= 1024 && d.groups >= 1,
                 B2H_ERR_SHAPE, "bn_apply: bad shape C=%d Cfill=%d nsrc=%d", d.C, d.Cfill, d.nsrc);
   B2H_CHECK_ARG(d.Cfill % 4 == 0 && d.out_ld % 4 == 0 && d.out_coff % 4 == 0, B2H_ERR_ALIGN,
@@ -467,11 +477,10 @@ __global__ void __launch_bounds__(kRedThreads) bn_bwd_kernel(b2h_bn_bwd_t d, int
   for (int gg = 0; gg < d.groups; ++gg) {
     double sa = 0.0, sb = 0.0;
     if (act)
-      for (int ch = fl.lane; ch < nchunks; ch += fl.NL) {
-        const float* p = d.partial + (((int64_t)ch * d.groups + gg) * d.C + fl.c) * 2;
-        sa += (double)__ldcg(p);
-        if (PASS == 1) sb += (double)__ldcg(p + 1);
-      }
+      lane_chunk_loop(d.partial, nchunks, d.groups, gg, d.C, fl.c, fl.lane, fl.NL, [&](int, float2 v) {
+        sa += (double)v.x;
+        sb += (double)v.y;
+      });
     __syncthreads();
     s_dbl[0][tid] = sa;
     s_dbl[1][tid] = sb;
@@ -501,6 +510,10 @@ __global__ void __launch_bounds__(kRedThreads) bn_bwd_kernel(b2h_bn_bwd_t d, int
 }
 
 int launch_bn_bwd(const b2h_bn_bwd_t& d, int dtype, cudaStream_t s) {
+  B2H_CARVE(bn_bwd_kernel<__nv_bfloat16, 1>);
+  B2H_CARVE(bn_bwd_kernel<__nv_bfloat16, 2>);
+  B2H_CARVE(bn_bwd_kernel<float, 1>);
+  B2H_CARVE(bn_bwd_kernel<float, 2>);
   B2H_CHECK_ARG(d.C > 0 && d.C <= 512 && d.Cfill >= d.C && d.Cfill <= 1024 && d.groups >= 1 && d.ngsrc >= 1 &&
                     d.ngsrc <= 2,
                 B2H_ERR_SHAPE, "bn_bwd: bad shape C=%d Cfill=%d ngsrc=%d", d.C, d.Cfill, d.ngsrc);
@@ -564,6 +577,8 @@ __global__ void __launch_bounds__(kRedThreads) colsum_kernel(b2h_colsum_t d, int
 }
 
 int launch_colsum(const b2h_colsum_t& d, int dtype, cudaStream_t s) {
+  B2H_CARVE(colsum_kernel<__nv_bfloat16>);
+  B2H_CARVE(colsum_kernel<float>);
   B2H_CHECK_ARG(d.C > 0 && d.C <= 512 && d.rows > 0 && d.ld % 4 == 0, B2H_ERR_SHAPE, "colsum: bad shape");
   RedShape rs = red_shape(d.C, d.rows, kRedThreads);
   dim3 grid(rs.nchunks), block(rs.txp, rs.ty);
@@ -592,6 +607,7 @@ __global__ void bn_fold_kernel(b2h_bn_fold_t d) {
 }
 
 int launch_bn_fold(const b2h_bn_fold_t& d, cudaStream_t s) {
+  B2H_CARVE(bn_fold_kernel);
   B2H_CHECK_ARG(d.C > 0 && d.Cpad >= d.C, B2H_ERR_SHAPE, "bn_fold: bad shape");
   bn_fold_kernel<<<ceil_div(d.Cpad, 128), 128, 0, s>>>(d);
   B2H_LAUNCH_CHECK("bn_fold");

@@ -348,6 +348,7 @@ class NetPlan:
         self.prog = Program(dtype, self.device)
         self.bufs: Dict[str, LayerBufs] = {}
         self.masks: Dict[str, torch.Tensor] = {}
+        self.saved_masks: Dict[str, torch.Tensor] = {}
         self.site_ids: Dict[str, int] = {}
         self.drop_state = drop_state
         if self.drop_mode == "philox" and drop_state is None:
@@ -373,8 +374,10 @@ class NetPlan:
         self._tickets[-1][1] = n + 1
         return t[n:n + 1]
 
-    def _drop(self, site: str, shape: Tuple[int, int, int]):
-        """Dropout descriptor of a site whose tensor is (B, L, C) in BLC order."""
+    def _drop(self, site: str, shape: Tuple[int, int, int], backward: bool = False, save: bool = False):
+        """Dropout descriptor of a site whose tensor is (B, L, C) in BLC order.  In Philox mode the forward
+        op of a site whose gradient is needed also stores the keep flags it drew (`save`), and the
+        backward replays them in MASK mode (cheaper than regenerating Philox in the GEMM epilogue)."""
         if self.drop_mode == "none":
             return no_drop()
         sid = self.site_ids.setdefault(site, self._site_base + len(self.site_ids) + 1)
@@ -382,8 +385,13 @@ class NetPlan:
             if site not in self.masks:
                 self.masks[site] = torch.ones(shape, dtype=torch.uint8, device=self.device)
             assert tuple(self.masks[site].shape) == tuple(shape), (site, self.masks[site].shape, shape)
-            return {"mode": L.DROP_MASK, "site": sid, "mask": self.masks[site], "state": None}
-        return {"mode": L.DROP_PHILOX, "site": sid, "mask": None, "state": self.drop_state}
+            return {"mode": L.DROP_MASK, "site": sid, "mask": self.masks[site], "state": None, "save": None}
+        if backward:
+            return {"mode": L.DROP_MASK, "site": sid, "mask": self.saved_masks[site], "state": None, "save": None}
+        buf = None
+        if save:
+            buf = self.saved_masks.setdefault(site, torch.zeros(shape, dtype=torch.uint8, device=self.device))
+        return {"mode": L.DROP_PHILOX, "site": sid, "mask": None, "state": self.drop_state, "save": buf}
 
     def set_masks(self, masks_ncl: Dict[str, torch.Tensor], group: Optional[int] = None):
         """Install keep-masks given in the reference's layout: (B, C, L) per conv site, (rows, C) per
@@ -616,7 +624,7 @@ class NetPlan:
         # BN outputs of producer layers (+ residual / up-sampling / pooling), then this block's dropout
         cuts = sorted({f.dst_coff for f in l.feeds} | {f.dst_coff + f.src.cout for f in l.feeds})
         assert cuts[0] == 0 and cuts[-1] == l.cin, (l.name, cuts, l.cin)
-        drop = self._drop(l.drop_site, site_shape)
+        drop = self._drop(l.drop_site, site_shape, save=self.train and self._needs_dgrad(l))
         for s, e in zip(cuts[:-1], cuts[1:]):
             srcs = [f for f in l.feeds if f.dst_coff <= s and e <= f.dst_coff + f.src.cout]
             assert 1 <= len(srcs) <= 2, (l.name, s, e)
@@ -703,7 +711,7 @@ class NetPlan:
             return
         lb.g = self._zeros(B, l.La, lb.Kc)
         taps = lb.bwd_taps
-        drop = self._drop(l.drop_site, (B, l.La, l.cin))
+        drop = self._drop(l.drop_site, (B, l.La, l.cin), backward=True)
         common = dict(A=lb.dpre, W=lb.wb, bias=None, out=lb.g, B=B, La=lb.Lz, lda=lb.Cp, ldo=lb.Kc, out_coff=0,
                       Kc=lb.Cp, Nvalid=l.cin, ntaps=len(taps), tap_off=taps + [0] * (L.MAX_TAPS - len(taps)),
                       act=L.ACT_NONE, post_scale=None, post_shift=None, out_f32=0, drop=drop, drop_C=l.cin)

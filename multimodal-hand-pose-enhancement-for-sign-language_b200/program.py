@@ -75,7 +75,7 @@ def lower(rec: OpRec):
 
 
 def no_drop():
-    return {"mode": L.DROP_NONE, "site": 0, "mask": None, "state": None}
+    return {"mode": L.DROP_NONE, "site": 0, "mask": None, "state": None, "save": None}
 
 
 class Program:
