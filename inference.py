@@ -1,0 +1,121 @@
+#!/usr/bin/env python
+"""Kept entry point of the reference's `inference.py` (same flags) on the B200 path: load a checkpoint, run the
+batched eval forward (inference.py:96-121), de-standardise (inference.py:134) and save the predicted 6-D
+rotations plus their rotation matrices (libb2h `rot6d_to_mat`, utils/conversion_utils.py:86-107).
+
+One process per GPU (`torchrun --nproc-per-node N inference.py ...` shards the clips; no collective is needed),
+replacing the reference's nn.DataParallel wrap (inference.py:45-47).  The axis-angle / xyz forward kinematics
+and GIF rendering of `save_results` (utils/utils.py:388-427) are outside the hot path.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import modelZoo  # noqa: E402
+from b2h_b200 import _lib as L  # noqa: E402
+from b2h_b200 import data as b2h_data  # noqa: E402
+
+
+def rot6d_to_mat(r6d: torch.Tensor) -> torch.Tensor:
+    """(..., 6) fp32 CUDA tensor -> (..., 9) rotation matrices through the C ABI."""
+    flat = r6d.reshape(-1, 6).contiguous().float()
+    out = torch.empty(flat.shape[0], 9, device=flat.device, dtype=torch.float32)
+    L.run_oneshot(L.Rot6d(r6d=flat.data_ptr(), mat=out.data_ptr(), n=flat.shape[0]), L.F32,
+                  torch.cuda.current_stream(flat.device).cuda_stream)
+    return out.reshape(*r6d.shape[:-1], 9)
+
+
+def main(args):
+    if not torch.cuda.is_available():
+        raise SystemExit("inference.py (B200 build) needs a CUDA device: there is no CPU fallback")
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(device)
+    cin, cout = b2h_data.FEATURE_MAP[args.pipeline]
+    mod = b2h_data.MODELS[args.model]
+    model = getattr(modelZoo, mod)()
+    if mod == "regressor_fcn_bn_32_b2h":
+        model.build_net(cin, cout, require_image=args.require_image)
+    else:
+        model.build_net(cin, cout, require_text=args.require_text)
+    model.precision = args.precision
+    if args.checkpoint and os.path.exists(args.checkpoint):
+        st = torch.load(args.checkpoint, map_location="cpu")
+        model.load_state_dict(st["state_dict"], strict=False)      # inference.py:41-43
+    model.to(device).eval()
+    kind = "text" if args.require_text else ("image" if args.require_image else None)
+    if args.synthetic:
+        clips = b2h_data.synthetic_r6d(args.synthetic, args.frames, seed=99)
+        feats = b2h_data.synthetic_feats(kind, args.synthetic, args.frames, seed=98)
+    else:
+        path = os.path.join(args.base_path, args.data_dir, b2h_data.DATA_PATHS_r6d["test"])
+        clips = b2h_data.make_equal_len(b2h_data._load_pickle(path))
+        feats = None   # loading of test embeddings follows train_gan.load_data
+    X, Y = b2h_data.split_pipeline(clips, args.pipeline)
+    X, Y, feats = b2h_data.rmv_clips_nan(X, Y, feats)
+    X, Y = np.swapaxes(X, 1, 2).astype(np.float32), np.swapaxes(Y, 1, 2).astype(np.float32)
+    stats_path = os.path.join(args.model_path, f"{args.exp_name}{args.pipeline}_preprocess_core.npz")
+    if os.path.exists(stats_path):                                   # inference.py:80-87
+        c = np.load(stats_path)
+        mX, sX, mY, sY = c["body_mean_X"], c["body_std_X"], c["body_mean_Y"], c["body_std_Y"]
+    else:
+        mX, sX, mY, sY = b2h_data.calc_standard(X, Y, args.pipeline)
+    X = ((X - mX) / sX).astype(np.float32)
+    Yn = ((Y - mY) / sY).astype(np.float32)
+    X, Yn = X[rank::world], Yn[rank::world]
+    feats = feats[rank::world] if feats is not None else None
+    outs, err, steps = [], 0.0, 0
+    bs = args.batch_size
+    with torch.no_grad():
+        for s in range(0, min(X.shape[0], args.num_samples), bs):    # inference.py:96-105 (last batch may be short)
+            x = torch.from_numpy(X[s:s + bs]).to(device)
+            f = torch.from_numpy(feats[s:s + bs]).to(device) if feats is not None else None
+            out = model(x, feats_=f)
+            err += torch.nn.functional.l1_loss(out, torch.from_numpy(Yn[s:s + bs]).to(device)).item() * bs
+            steps += 1
+            outs.append(out)
+    out = torch.cat(outs, 0)
+    print(f">>> TOTAL ERROR: {err / max(steps * bs, 1)}", flush=True)
+    pred = out * torch.from_numpy(sY).to(device) + torch.from_numpy(mY).to(device)   # inference.py:134
+    r6d = pred.permute(0, 2, 1).contiguous()                                         # (N, T, 6*J)
+    mats = rot6d_to_mat(r6d.reshape(r6d.shape[0], r6d.shape[1], -1, 6))
+    os.makedirs(args.results_dir, exist_ok=True)
+    tag = f"{args.exp_name}_rank{rank}" if world > 1 else args.exp_name
+    np.save(os.path.join(args.results_dir, f"{tag}_r6d.npy"), r6d.cpu().numpy())
+    np.save(os.path.join(args.results_dir, f"{tag}_rotmat.npy"), mats.cpu().numpy())
+    print(f"saved {tuple(r6d.shape)} r6d and {tuple(mats.shape)} rotation matrices to {args.results_dir}", flush=True)
+
+
+def build_parser():
+    p = argparse.ArgumentParser()
+    p.add_argument("--checkpoint", type=str, default="")
+    p.add_argument("--base_path", type=str, default="./")
+    p.add_argument("--data_dir", type=str, default="video_data")
+    p.add_argument("--pipeline", type=str, default="arm2wh")
+    p.add_argument("--require_text", action="store_true")
+    p.add_argument("--require_image", action="store_true")
+    p.add_argument("--embeds_type", type=str, default="normal")
+    p.add_argument("--tag", type=str, default="")
+    p.add_argument("--exp_name", type=str, default="experiment")
+    p.add_argument("--model_path", type=str, default="models/")
+    p.add_argument("--model", type=str, default="v1")
+    p.add_argument("--batch_size", type=int, default=64)
+    p.add_argument("--num_samples", type=int, default=10 ** 9)
+    p.add_argument("--results_dir", type=str, default="results/")
+    p.add_argument("--precision", type=str, default="fp32", choices=["fp32", "bf16"])
+    p.add_argument("--synthetic", type=int, default=0)
+    p.add_argument("--frames", type=int, default=192)
+    return p
+
+
+if __name__ == "__main__":
+    main(build_parser().parse_args())

@@ -163,17 +163,20 @@ def generator_spec(variant: str, in_dim: int, out_dim: int, require_feats: bool 
                    dead)
 
 
-def discriminator_spec(in_dim: int) -> NetSpec:
+def discriminator_spec(in_dim: int, motion_input: bool = True) -> NetSpec:
+    """`motion_input`: the plan computes calc_motion of an NCL tensor itself (trainer); otherwise the
+    input already is the motion tensor (drop-in module, modelZoo.py:815-817)."""
     chans = [in_dim, 64, 64, 32, 32, 16, 16, 8]
     layers = []
-    prev: Union[Layer, str] = "motion"
+    prev: Union[Layer, str] = "motion" if motion_input else "x"
     for i in range(7):
         lay = _blk(f"convs.{4 * i + 1}", "convs", 4 * i + 1, chans[i], chans[i + 1], 5, stride=2, pad=2,
                    feeds=[Feed(prev)])
         layers.append(lay)
         prev = lay
     layers.append(_blk("convs.29", "convs", 29, 8, 1, 3, act=L.ACT_NONE, bn=False, feeds=[Feed(prev)]))
-    return NetSpec("discriminator", layers, ["convs"], in_dim, 1, None, [], input_kind="motion")
+    return NetSpec("discriminator", layers, ["convs"], in_dim, 1, None, [],
+                   input_kind="motion" if motion_input else "x")
 
 
 # ------------------------------------------------------------------------------------------------

@@ -80,7 +80,7 @@ class GanTrainer:
     def __init__(self, variant: str = "v1", in_dim: int = 36, out_dim: int = 252, require_feats: bool = False,
                  batch_size: int = 256, T: int = 64, precision: str = "bf16", device="cuda", lr: float = 1e-4,
                  seed: int = 23456, drop_mode: str = "philox", label_smooth: bool = False,
-                 world_size: int = 1, process_group=None, n_buckets: int = 2):
+                 world_size: int = 1, process_group=None, n_buckets: int = 2, stores=None):
         self.device = torch.device(device)
         self.B, self.T, self.precision = batch_size, T, precision
         self.dtype = dtype_of(precision)
@@ -91,8 +91,11 @@ class GanTrainer:
         self.g_spec = nets.generator_spec(variant, in_dim, out_dim, require_feats, train=True)
         self.g_spec_eval = nets.generator_spec(variant, in_dim, out_dim, require_feats, train=False)
         self.d_spec = nets.discriminator_spec(out_dim)
-        self.g_store = nets.ParamStore(self.g_spec, dev, seed=seed)
-        self.d_store = nets.ParamStore(self.d_spec, dev, seed=seed + 1)
+        if stores is not None:      # share the flat buffers of existing modelZoo modules
+            self.g_store, self.d_store = stores
+        else:
+            self.g_store = nets.ParamStore(self.g_spec, dev, seed=seed)
+            self.d_store = nets.ParamStore(self.d_spec, dev, seed=seed + 1)
         self.g_opt = FlatAdam(self.g_store, lr)
         self.d_opt = FlatAdam(self.d_store, lr)
         self.drop_state = torch.zeros(2, dtype=torch.int64, device=dev)
@@ -115,6 +118,24 @@ class GanTrainer:
         self._build_loss_programs(label_smooth)
         self._graphs: Dict[str, torch.cuda.CUDAGraph] = {}
         self._comm_stream = None
+
+    @classmethod
+    def from_modules(cls, generator, discriminator, batch_size: int, T: int, precision: str = "fp32", **kw):
+        """Fused trainer over the parameters of drop-in modelZoo modules: the modules' parameters and BN buffers
+        ARE the trainer's flat buffers, so state_dict() / checkpoints / eval forwards see every update."""
+        dev = next(generator.parameters()).device
+        g_store = generator._materialize(dev)
+        d_store = discriminator._materialize(dev)
+        v, cin, cout, rf, D = generator._spec_args
+        assert D == 256, "the fused trainer is built for default_size=256"
+        return cls(v, cin, cout, rf, batch_size, T, precision=precision, device=dev, stores=(g_store, d_store), **kw)
+
+    def load_batch(self, x, y, feats=None):
+        """Copy one batch (device or pinned-host tensors in the reference layouts) into the static buffers."""
+        self.x.copy_(x, non_blocking=True)
+        self.y.copy_(y, non_blocking=True)
+        if self.feats is not None:
+            self.feats.copy_(feats.reshape(self.feats.shape), non_blocking=True)
 
     @staticmethod
     def _alias_inputs(dst: nets.NetPlan, src: nets.NetPlan):

@@ -1,0 +1,55 @@
+"""Host data path (b2h_b200/data.py) against the reference's utils (where /root/reference is mounted)."""
+import sys
+
+import numpy as np
+import pytest
+
+import b2h_b200  # noqa: F401
+from b2h_b200 import data
+
+pytestmark = pytest.mark.reference
+
+
+@pytest.fixture(scope="module")
+def ref_utils():
+    sys.path.insert(0, "/root/reference/utils")
+    try:
+        import constants
+        import postprocess_utils
+        import standardization_utils
+    finally:
+        sys.path.pop(0)
+    return constants, postprocess_utils, standardization_utils
+
+
+def test_tables(ref_utils):
+    constants = ref_utils[0]
+    assert data.FEATURE_MAP == {k: tuple(v) for k, v in constants.FEATURE_MAP.items()}
+    assert data.MODELS == constants.MODELS
+    assert data.DATA_PATHS_r6d == constants.DATA_PATHS_r6d
+
+
+@pytest.mark.parametrize("pipeline", ["arm2wh", "wh2wh", "arm_wh2finger3"])
+def test_calc_standard(ref_utils, pipeline):
+    std = ref_utils[2]
+    rng = np.random.RandomState(0)
+    cin, cout = data.FEATURE_MAP[pipeline]
+    X = rng.randn(7, cin, 20).astype(np.float32) * 3 + 1
+    Y = rng.randn(7, cout, 20).astype(np.float32) * 0.5 - 2
+    for a, b in zip(std.calc_standard(X, Y, pipeline), data.calc_standard(X, Y, pipeline)):
+        np.testing.assert_array_equal(a, b)
+
+
+def test_windows_and_nan_removal(ref_utils):
+    pp = ref_utils[1]
+    rng = np.random.RandomState(1)
+    clips = [rng.randn(n, 12) for n in (250, 100, 192, 30)]
+    np.testing.assert_array_equal(pp.make_equal_len(clips, method="cutting+reflect"), data.make_equal_len(clips))
+    X = rng.randn(6, 10, 4)
+    Y = rng.randn(6, 10, 5)
+    F = rng.randn(6, 8)
+    X[1, 2, 3] = np.nan
+    Y[4, 0, 0] = np.nan
+    F[5, 7] = np.nan
+    for a, b in zip(pp.rmv_clips_nan(X.copy(), Y.copy(), F.copy()), data.rmv_clips_nan(X, Y, F)):
+        np.testing.assert_array_equal(a, b)
