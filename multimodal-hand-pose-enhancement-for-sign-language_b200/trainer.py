@@ -185,10 +185,37 @@ class GanTrainer:
             import torch.distributed as dist
             dist.all_reduce(store.grad, op=dist.ReduceOp.SUM, group=self.pg)
 
+    def bucket_plan(self, plan: nets.NetPlan):
+        """Split the backward segment into `n_buckets` contiguous op ranges.  Parameters are laid out in forward
+        order and the backward runs in reverse, so the gradients finished after bucket i form a suffix
+        [lo_i, hi_i) of the flat buffer; the ranges tile [0, n) exactly once.
+        Returns [(op_first, op_end, lo, hi)]."""
+        st = plan.store
+        first, end = plan.prog.segments["bwd"]
+        marks = plan.bwd_marks
+        nb = min(self.n_buckets, len(marks))
+        per = math.ceil(len(marks) / nb)
+        out = []
+        hi = st.n
+        for bi in range(nb):
+            names = marks[bi * per:(bi + 1) * per]
+            if not names:
+                break
+            s = names[0][1]
+            last = (bi + 1) * per >= len(marks)
+            e = end if last else marks[(bi + 1) * per][1]
+            layer_names = {n for n, _ in names}
+            # smallest parameter offset among the layers of this bucket (a layer's block holds conv + BN params)
+            lo = 0 if last else min(min(st.offsets[l.wkey + ".weight"], st.offsets[l.wkey + ".bias"])
+                                    for l in plan.spec.layers if l.name in layer_names)
+            lo = min(lo, hi)
+            out.append((s, e, lo, hi))
+            hi = lo
+        return out
+
     def _bwd_bucketed(self, plan: nets.NetPlan):
-        """Backward in `n_buckets` pieces; each piece's flat-gradient range is all-reduced on a side
-        stream while the next piece computes (parameters are laid out in forward order, the backward
-        runs in reverse, so finished gradients form a suffix of the flat buffer)."""
+        """Backward in buckets; each bucket's flat-gradient range is all-reduced over NCCL on a side stream while
+        the next bucket computes."""
         if self.world_size == 1:
             plan.prog.run("bwd")
             return
@@ -196,29 +223,17 @@ class GanTrainer:
         if self._comm_stream is None:
             self._comm_stream = torch.cuda.Stream(self.device)
         st = plan.store
-        first, end = plan.prog.segments["bwd"]
-        marks = plan.bwd_marks
-        nb = min(self.n_buckets, len(marks))
-        per = math.ceil(len(marks) / nb)
         cur = torch.cuda.current_stream(self.device)
-        hi = st.n
         pending = []
-        for bi in range(nb):
-            names = marks[bi * per:(bi + 1) * per]
-            if not names:
-                break
-            s = names[0][1]
-            e = marks[(bi + 1) * per][1] if (bi + 1) * per < len(marks) else end
+        for (s, e, lo, hi) in self.bucket_plan(plan):
             plan.prog.run_range(s, e, cur.cuda_stream)
-            last = bi == nb - 1 or (bi + 1) * per >= len(marks)
-            layer_names = {n for n, _ in names}
-            lo = 0 if last else min(st.offsets[l.wkey + ".weight"] for l in plan.spec.layers if l.name in layer_names)
+            if hi <= lo:
+                continue
             ev = torch.cuda.Event()
             ev.record(cur)
             self._comm_stream.wait_event(ev)
             with torch.cuda.stream(self._comm_stream):
                 dist.all_reduce(st.grad[lo:hi], op=dist.ReduceOp.SUM, group=self.pg)
-            hi = lo
             done = torch.cuda.Event()
             done.record(self._comm_stream)
             pending.append(done)
