@@ -341,8 +341,12 @@ def main():
                                               f"restatement of train_gan (torch CPU fp32, {cores} threads)"}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        # CUDA graphs that captured NCCL kernels keep the communicator busy at interpreter teardown: leave
+        # without destroying the process group (every rank has finished its work and its output by now)
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
