@@ -121,30 +121,32 @@ typedef struct {
 typedef struct {
   const void* z;  /* post-activation, pre-BN tensor [rows][ld], act dtype */
   int32_t ld, coff, rowmap, L_src;
-  int32_t C_total;      /* channel count of the source layer: the per-channel arrays below are
-                           indexed by (coff + c), the batch statistics by g*C_total + coff + c */
-  const float* mean;    /* [groups][C_total] batch mean          (train)  */
-  const float* invstd;  /* [groups][C_total] 1/sqrt(var_b + eps) (train)  */
-  const float* running_mean; /* eval: y = (z - rm)/sqrt(rv + eps)*gamma + beta */
-  const float* running_var;
-  const float* gamma;
-  const float* beta;
-  float eps;
-  int32_t use_running;
+  int32_t Cs;           /* row stride of the per-channel arrays below = channels of the source layer padded
+                           to a multiple of 64; entries beyond the layer's channels are 0 */
+  const float* scale;   /* [groups][Cs]  gamma * invstd              y = z * scale + shift          */
+  const float* shift;   /* [groups][Cs]  beta - mean * scale                                         */
+  const float* mean;    /* [groups][Cs]  batch mean          (backward only)                        */
+  const float* invstd;  /* [groups][Cs]  1/sqrt(var_b + eps) (backward only)                        */
 } b2h_bn_src_t;
 
-/* batch statistics of z over (rows of one group): mean, biased var -> invstd; running update
+/* batch statistics of z over (rows of one group): mean, biased var -> invstd, and the folded affine
+ * scale = gamma*invstd, shift = beta - mean*scale; running update
  * running = (1-m)*running + m*batch (unbiased var), num_batches_tracked += 1. */
 typedef struct {
   const void* z;
   int32_t ld, C, rows_per_group, groups;
-  float* mean;   /* [groups][C] */
-  float* invstd; /* [groups][C] */
-  float* running_mean; /* may be NULL (no update); updated from group `running_group` */
+  int32_t Cs;    /* stride of the [groups][Cs] outputs */
+  float* mean;
+  float* invstd;
+  float* scale;
+  float* shift;
+  const float* gamma; /* [C] */
+  const float* beta;  /* [C] */
+  float* running_mean; /* may be NULL (no update) */
   float* running_var;
   int64_t* num_batches_tracked;
   float momentum, eps;
-  float* partial;        /* workspace [nchunks][groups][C][2] */
+  float* partial;        /* workspace >= b2h_bn_partial_floats() */
   uint32_t* ticket;      /* workspace, zero-initialised, self-resetting */
   int32_t update_all_groups; /* 1: apply the running update once per group in order (two D forwards) */
 } b2h_bn_stats_t;
@@ -171,7 +173,7 @@ typedef struct {
 typedef struct {
   b2h_grad_src_t gsrc[2];
   int32_t ngsrc;
-  b2h_bn_src_t bn; /* z, mean, invstd, gamma of THIS layer (rowmap IDENT) */
+  b2h_bn_src_t bn; /* z, mean, invstd, scale, shift of THIS layer (rowmap IDENT, coff 0) */
   /* for POOL2 grad sources the pooled tensor was max over BN(z) pairs of this layer */
   void* dpre;      /* [rows][ld_dpre] act dtype, zero filled up to Cfill */
   int32_t ld_dpre, Cfill;
@@ -245,7 +247,8 @@ typedef struct {
   int64_t n;
   double lr, beta1, beta2, eps; /* Python-float hyper-parameters, as torch.optim.Adam holds them */
   float gscale;
-  int64_t* step; /* device; incremented by this op BEFORE use (t = ++step) */
+  int64_t* step;  /* device; incremented by this op BEFORE use (t = ++step) */
+  float* scalars; /* device workspace, 2 floats: the step's bias-correction scalars */
 } b2h_adam_t;
 
 /* weight repack: out[(ph*Opad + o)][t][i] = W[o*o_stride + i*i_stride + tapmap[ph][t]*k_stride]

@@ -40,16 +40,15 @@ class Wgrad(C.Structure):
 
 
 class BnSrc(C.Structure):
-    _fields_ = [("z", vp), ("ld", i32), ("coff", i32), ("rowmap", i32), ("L_src", i32), ("C_total", i32),
-                ("mean", vp), ("invstd", vp), ("running_mean", vp), ("running_var", vp),
-                ("gamma", vp), ("beta", vp), ("eps", f32), ("use_running", i32)]
+    _fields_ = [("z", vp), ("ld", i32), ("coff", i32), ("rowmap", i32), ("L_src", i32), ("Cs", i32),
+                ("scale", vp), ("shift", vp), ("mean", vp), ("invstd", vp)]
 
 
 class BnStats(C.Structure):
-    _fields_ = [("z", vp), ("ld", i32), ("C", i32), ("rows_per_group", i32), ("groups", i32),
-                ("mean", vp), ("invstd", vp), ("running_mean", vp), ("running_var", vp),
-                ("num_batches_tracked", vp), ("momentum", f32), ("eps", f32),
-                ("partial", vp), ("ticket", vp), ("update_all_groups", i32)]
+    _fields_ = [("z", vp), ("ld", i32), ("C", i32), ("rows_per_group", i32), ("groups", i32), ("Cs", i32),
+                ("mean", vp), ("invstd", vp), ("scale", vp), ("shift", vp), ("gamma", vp), ("beta", vp),
+                ("running_mean", vp), ("running_var", vp), ("num_batches_tracked", vp),
+                ("momentum", f32), ("eps", f32), ("partial", vp), ("ticket", vp), ("update_all_groups", i32)]
 
 
 class BnApply(C.Structure):
@@ -95,7 +94,7 @@ class Colsum(C.Structure):
 
 class Adam(C.Structure):
     _fields_ = [("p", vp), ("g", vp), ("m", vp), ("v", vp), ("n", i64),
-                ("lr", f64), ("beta1", f64), ("beta2", f64), ("eps", f64), ("gscale", f32), ("step", vp)]
+                ("lr", f64), ("beta1", f64), ("beta2", f64), ("eps", f64), ("gscale", f32), ("step", vp), ("scalars", vp)]
 
 
 class Pack(C.Structure):

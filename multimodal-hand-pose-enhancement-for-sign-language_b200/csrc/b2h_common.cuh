@@ -91,15 +91,60 @@ __device__ __forceinline__ float from_f<float>(float v) { return v; }
 template <>
 __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
+// 8 consecutive channels: one 16-byte access in bf16, two in fp32
+struct F8 {
+  float v[8];
+};
+template <typename T>
+__device__ __forceinline__ F8 load8(const T* p);
+template <>
+__device__ __forceinline__ F8 load8<float>(const float* p) {
+  float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  F8 r;
+  r.v[0] = a.x, r.v[1] = a.y, r.v[2] = a.z, r.v[3] = a.w, r.v[4] = b.x, r.v[5] = b.y, r.v[6] = b.z, r.v[7] = b.w;
+  return r;
+}
+template <>
+__device__ __forceinline__ F8 load8<__nv_bfloat16>(const __nv_bfloat16* p) {
+  uint4 u = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+  F8 r;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {  // bf16 -> fp32 is a 16-bit shift
+    r.v[2 * i] = __uint_as_float(w[i] << 16);
+    r.v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+  }
+  return r;
+}
+template <typename T>
+__device__ __forceinline__ void store8(T* p, const F8& r);
+template <>
+__device__ __forceinline__ void store8<float>(float* p, const F8& r) {
+  *reinterpret_cast<float4*>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+template <>
+__device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16* p, const F8& r) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 q = __floats2bfloat162_rn(r.v[2 * i], r.v[2 * i + 1]);
+    w[i] = *reinterpret_cast<uint32_t*>(&q);
+  }
+  *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 __device__ __forceinline__ float& f4(float4& v, int i) { return (&v.x)[i]; }
 __device__ __forceinline__ float f4c(const float4& v, int i) { return (&v.x)[i]; }
 
 // ---------------------------------------------------------------------------------------------
 // Dropout: explicit keep-mask or Philox4x32-10 keyed by (seed, step, site, element index)
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+// out of line and rolled on purpose: one small copy per kernel instead of ~1 KB per call site (these
+// kernels are instruction-fetch bound when their straight-line code outgrows the instruction caches)
+static __device__ __noinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
   const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
+#pragma unroll 2
   for (int r = 0; r < 10; ++r) {
     uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
     uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
@@ -110,6 +155,11 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
   return ctr;
 }
 
+// Dropout keep flags of a site whose tensor is [rows][C].
+//   MASK:   explicit uint8 flags mask[row*C + c]
+//   PHILOX: one Philox4x32-10 call yields the 128 keep bits of a (16 rows x 8 channels) block:
+//           counter = (row >> 4) * ceil(C/8) + (c >> 3), bit = (row & 15) * 8 + (c & 7),
+//           keyed by (seed, step, site) -> a thread that owns 8 channels of 8 consecutive rows needs ONE call.
 struct DropCtx {
   int mode;
   uint32_t site;
@@ -117,36 +167,66 @@ struct DropCtx {
   uint8_t* save;
   uint2 key;      // seed
   uint32_t step;  // low 32 bits of the step counter
-  __device__ __forceinline__ void init(const b2h_dropout_t& d) {
+  uint32_t C, Cq; // row length of the site's tensor, ceil(C / 8)
+  __device__ __forceinline__ void init(const b2h_dropout_t& d, int row_len) {
     mode = d.mode;
     site = (uint32_t)d.site;
     mask = d.mask;
     save = d.save;
     key = make_uint2(0u, 0u);
     step = 0u;
+    C = (uint32_t)max(row_len, 1);
+    Cq = (C + 7u) >> 3;
     if (mode == B2H_DROP_PHILOX) {
       uint64_t seed = d.state[0], st = d.state[1];
       key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
       step = (uint32_t)st;
     }
   }
-  // dropout multiplier (0 or 2) of element `idx` of the site's tensor
+  // PHILOX: the 64 keep bits of rows 8*rb8 .. 8*rb8+7 for channel octet cq (byte j = row 8*rb8+j)
+  __device__ __forceinline__ uint2 philox_rows8(uint32_t rb8, uint32_t cq) const {
+    const uint64_t c = (uint64_t)(rb8 >> 1) * Cq + cq;
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), site, step), key);
+    return (rb8 & 1u) ? make_uint2(r.z, r.w) : make_uint2(r.x, r.y);
+  }
+  // keep bits (bit i = channel c0 + i) of 8 channels of one row; c0 % 8 == 0
+  __device__ __forceinline__ uint32_t keep8_rc(uint32_t row, uint32_t c0) const {
+    if (mode == B2H_DROP_NONE) return 0xFFu;
+    if (mode == B2H_DROP_PHILOX) {
+      const uint2 w = philox_rows8(row >> 3, c0 >> 3);
+      const uint32_t j = row & 7u;
+      return ((j < 4u ? w.x : w.y) >> ((j & 3u) * 8u)) & 0xFFu;
+    }
+    const uint64_t idx = (uint64_t)row * C + c0;
+    uint32_t b = 0;
+    const uint32_t n = min(8u, C - c0);
+    if (n == 8u && (idx & 3u) == 0u) {
+      const uint32_t m0 = *reinterpret_cast<const uint32_t*>(mask + idx);
+      const uint32_t m1 = *reinterpret_cast<const uint32_t*>(mask + idx + 4);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        b |= ((m0 >> (8 * i)) & 0xFFu) ? (1u << i) : 0u;
+        b |= ((m1 >> (8 * i)) & 0xFFu) ? (16u << i) : 0u;
+      }
+      return b;
+    }
+#pragma unroll 1
+    for (uint32_t i = 0; i < n; ++i) b |= mask[idx + i] ? (1u << i) : 0u;
+    return b;
+  }
+  // generic element access by flat index idx = row*C + c (rare paths: one division)
   __device__ __forceinline__ float scale1(uint64_t idx) const {
     if (mode == B2H_DROP_NONE) return 1.f;
     if (mode == B2H_DROP_MASK) return mask[idx] ? 2.f : 0.f;
-    uint64_t c = idx >> 2;
-    uint4 r = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), site, step), key);
-    uint32_t w = (idx & 3) == 0 ? r.x : (idx & 3) == 1 ? r.y : (idx & 3) == 2 ? r.z : r.w;
-    return (w & 0x80000000u) ? 2.f : 0.f;
+    const uint32_t row = (uint32_t)(idx / C), c = (uint32_t)(idx - (uint64_t)row * C);
+    return ((keep8_rc(row, c & ~7u) >> (c & 7u)) & 1u) ? 2.f : 0.f;
   }
-  // multipliers of elements idx .. idx+3
   __device__ __forceinline__ float4 scale4(uint64_t idx) const {
     if (mode == B2H_DROP_NONE) return make_float4(1.f, 1.f, 1.f, 1.f);
-    if (mode == B2H_DROP_PHILOX && (idx & 3) == 0) {
-      uint64_t c = idx >> 2;
-      uint4 r = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), site, step), key);
-      return make_float4((r.x >> 31) ? 2.f : 0.f, (r.y >> 31) ? 2.f : 0.f, (r.z >> 31) ? 2.f : 0.f,
-                         (r.w >> 31) ? 2.f : 0.f);
+    if (mode == B2H_DROP_PHILOX && (C & 3u) == 0u && (idx & 3u) == 0u) {
+      const uint32_t row = (uint32_t)(idx / C), c = (uint32_t)(idx - (uint64_t)row * C);
+      const uint32_t b = keep8_rc(row, c & ~7u) >> (c & 7u);
+      return make_float4((b & 1u) ? 2.f : 0.f, (b & 2u) ? 2.f : 0.f, (b & 4u) ? 2.f : 0.f, (b & 8u) ? 2.f : 0.f);
     }
     return make_float4(scale1(idx), scale1(idx + 1), scale1(idx + 2), scale1(idx + 3));
   }
@@ -158,6 +238,18 @@ struct DropCtx {
       *reinterpret_cast<uchar4*>(save + idx) = k;
     } else {
       for (int i = 0; i < n; ++i) save[idx + i] = (&m.x)[i] != 0.f;
+    }
+  }
+  // record the keep flags of n <= 8 elements (bit i = element idx + i)
+  __device__ __forceinline__ void save8(uint64_t idx, uint32_t bits, int n) const {
+    if (!save) return;
+    if (n == 8 && (idx & 7) == 0) {
+      uint2 w;
+      w.x = (bits & 1u) | ((bits & 2u) << 7) | ((bits & 4u) << 14) | ((bits & 8u) << 21);
+      w.y = ((bits >> 4) & 1u) | ((bits & 32u) << 3) | ((bits & 64u) << 10) | ((bits & 128u) << 17);
+      *reinterpret_cast<uint2*>(save + idx) = w;
+    } else {
+      for (int i = 0; i < n; ++i) save[idx + i] = (bits >> i) & 1u;
     }
   }
 };

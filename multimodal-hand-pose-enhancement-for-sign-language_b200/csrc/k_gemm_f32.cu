@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(b2h_gemm_t d, EpiParams e
     }
   }
   DropCtx drop;
-  drop.init(e.drop);
+  drop.init(e.drop, e.drop_C);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     int m = m0 + ty * 8 + i;

@@ -194,7 +194,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       asm volatile("bar.sync 1, 256;" ::: "memory");
     }
     DropCtx drop;
-    drop.init(e.drop);
+    drop.init(e.drop, e.drop_C);
     {
       const int r = sub * 32 + lane;  // tile row == TMEM lane
       const int bi = r >> p.tl_log2, li = r & (p.tl - 1);

@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(256) prep_ncl_kernel(b2h_prep_t d) {
   }
   __syncthreads();
   DropCtx drop;
-  drop.init(d.drop);
+  drop.init(d.drop, d.C);
   // write phase: each thread stores 4 consecutive channels of one time step (8 B bf16 / 16 B fp32)
   const int tid = ty * 32 + tx;
   const int l = l0 + (tid >> 3), c = c0 + (tid & 7) * 4;
@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(256) prep_rows_kernel(b2h_prep_t d) {
   const int64_t rows = (int64_t)d.B * d.L;
   const int nq = d.Cfill / 4;
   DropCtx drop;
-  drop.init(d.drop);
+  drop.init(d.drop, d.C);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rows * nq;
        i += (int64_t)gridDim.x * blockDim.x) {
     int64_t row = i / nq;
@@ -293,15 +293,20 @@ int launch_mse(const b2h_mse_t& d, cudaStream_t s) {
 //   p -= (lr / (1 - b1^t)) * m / (sqrt(v)/sqrt(1 - b2^t) + eps)
 // 28 B/param: reads p,g,m,v, writes p,m,v.
 // ---------------------------------------------------------------------------------------------
-__global__ void adam_step_kernel(int64_t* step) { *step += 1; }
-
-__global__ void __launch_bounds__(256) adam_kernel(b2h_adam_t d) {
-  // scalar prologue mirrors torch/optim/adam.py (_single_tensor_adam): Python-double arithmetic
-  const int64_t t = *d.step;
+// one thread: advance the step counter and evaluate the Python-double scalar prologue of
+// torch/optim/adam.py (_single_tensor_adam) once, so the element-wise kernel stays tiny
+__global__ void adam_step_kernel(b2h_adam_t d) {
+  const int64_t t = *d.step + 1;
+  *d.step = t;
   const double bc1 = 1.0 - pow(d.beta1, (double)t);
   const double bc2 = 1.0 - pow(d.beta2, (double)t);
-  const float neg_step = (float)(-(d.lr / bc1));
-  const float bc2_sqrt = (float)sqrt(bc2);
+  d.scalars[0] = (float)(-(d.lr / bc1));   // -step_size
+  d.scalars[1] = (float)sqrt(bc2);         // bias_correction2_sqrt
+}
+
+__global__ void __launch_bounds__(256) adam_kernel(b2h_adam_t d) {
+  const float neg_step = d.scalars[0];
+  const float bc2_sqrt = d.scalars[1];
   const float w1 = (float)(1.0 - d.beta1), w2 = (float)(1.0 - d.beta2);
   const float b2 = (float)d.beta2, eps = (float)d.eps, gs = d.gscale;
   const int64_t n4 = d.n / 4;
@@ -311,7 +316,7 @@ __global__ void __launch_bounds__(256) adam_kernel(b2h_adam_t d) {
     float4 g = reinterpret_cast<const float4*>(d.g)[i];
     float4 m = reinterpret_cast<float4*>(d.m)[i];
     float4 v = reinterpret_cast<float4*>(d.v)[i];
-#pragma unroll
+#pragma unroll 2
     for (int k = 0; k < 4; ++k) {
       float gk = f4(g, k) * gs;
       float mk = f4(m, k) + w1 * (gk - f4(m, k));         // exp_avg.lerp_(grad, 1 - beta1)
@@ -339,11 +344,11 @@ __global__ void __launch_bounds__(256) adam_kernel(b2h_adam_t d) {
 int launch_adam(const b2h_adam_t& d, cudaStream_t s) {
   B2H_CARVE(adam_step_kernel);
   B2H_CARVE(adam_kernel);
-  B2H_CHECK_ARG(d.n > 0 && d.step, B2H_ERR_ARG, "adam: bad args");
+  B2H_CHECK_ARG(d.n > 0 && d.step && d.scalars, B2H_ERR_ARG, "adam: bad args");
   B2H_CHECK_ARG(((uintptr_t)d.p % 16 == 0) && ((uintptr_t)d.g % 16 == 0) && ((uintptr_t)d.m % 16 == 0) &&
                     ((uintptr_t)d.v % 16 == 0),
                 B2H_ERR_ALIGN, "adam: buffers must be 16-byte aligned");
-  adam_step_kernel<<<1, 1, 0, s>>>(d.step);
+  adam_step_kernel<<<1, 1, 0, s>>>(d);
   B2H_LAUNCH_CHECK("adam_step");
   int blocks = (int)std::min<int64_t>(ceil_div64(d.n / 4 + 1, 256), (int64_t)sm_count() * 8);
   adam_kernel<<<blocks, 256, 0, s>>>(d);

@@ -322,8 +322,10 @@ def _conv_out_len(La, k, stride, pad):
 class LayerBufs:
     a: torch.Tensor = None        # (B, La, Kc)    conv input after dropout
     z: torch.Tensor = None        # (B, Lo_act, Cp) post-activation, pre-BN
-    mean: torch.Tensor = None
+    mean: torch.Tensor = None     # (groups, Cp) batch statistics and the folded affine y = z*scale + shift
     invstd: torch.Tensor = None
+    scale: torch.Tensor = None
+    shift: torch.Tensor = None
     dpre: torch.Tensor = None     # (B, Lo_act, Cp)
     g: torch.Tensor = None        # (B, La, Kc) gradient w.r.t. the pre-dropout input (mask applied)
     wf: torch.Tensor = None       # packed forward weights
@@ -411,16 +413,9 @@ class NetPlan:
 
     def _bn_src(self, l: Layer, rowmap=L.ROW_IDENT, coff=0):
         lb = self.bufs[l.name]
-        st = self.store
-        d = {"z": lb.z, "ld": lb.Cp, "coff": coff, "rowmap": rowmap, "L_src": lb.Lz if rowmap != L.ROW_BCAST else 1,
-             "C_total": l.cout,
-             "gamma": st.p(l.bnkey + ".weight"), "beta": st.p(l.bnkey + ".bias"), "eps": BN_EPS}
-        if self.train:
-            d.update(mean=lb.mean, invstd=lb.invstd, running_mean=None, running_var=None, use_running=0)
-        else:
-            d.update(mean=None, invstd=None, running_mean=st.b(l.bnkey + ".running_mean"),
-                     running_var=st.b(l.bnkey + ".running_var"), use_running=1)
-        return d
+        return {"z": lb.z, "ld": lb.Cp, "coff": coff, "rowmap": rowmap, "L_src": lb.Lz if rowmap != L.ROW_BCAST else 1,
+                "Cs": lb.Cp, "scale": lb.scale, "shift": lb.shift,
+                "mean": lb.mean if self.train else None, "invstd": lb.invstd if self.train else None}
 
     # ---- build -------------------------------------------------------------------------------
     def _build(self):
@@ -460,8 +455,11 @@ class NetPlan:
             lb.a = self._zeros(B, l.La, lb.Kc)
             if l.bn:
                 lb.z = self._zeros(B, Lz, lb.Cp)
-                lb.mean = self._zeros(self.groups, l.cout, dtype=torch.float32)
-                lb.invstd = self._zeros(self.groups, l.cout, dtype=torch.float32)
+                # per-channel arrays padded to Cp (zeros beyond the layer's channels)
+                lb.mean = self._zeros(self.groups, lb.Cp, dtype=torch.float32)
+                lb.invstd = self._zeros(self.groups, lb.Cp, dtype=torch.float32)
+                lb.scale = self._zeros(self.groups, lb.Cp, dtype=torch.float32)
+                lb.shift = self._zeros(self.groups, lb.Cp, dtype=torch.float32)
             self.bufs[l.name] = lb
         self.out_layer = spec.layers[-1]
         ol = self.out_layer
@@ -493,6 +491,15 @@ class NetPlan:
             for l in spec.layers:
                 self._emit_pack(l)
             self._emit_pack_table()
+            if not self.train:
+                st = self.store
+                for l in spec.layers:
+                    if l.bn:
+                        lb = self.bufs[l.name]
+                        P.add(L.OP_BN_FOLD, f"fold.{l.name}", gamma=st.p(l.bnkey + ".weight"),
+                              beta=st.p(l.bnkey + ".bias"), running_mean=st.b(l.bnkey + ".running_mean"),
+                              running_var=st.b(l.bnkey + ".running_var"), scale=lb.scale, shift=lb.shift,
+                              C=l.cout, Cpad=lb.Cp, eps=BN_EPS)
         with P.segment("fwd"):
             for l in spec.layers:
                 self._emit_input(l)
@@ -666,7 +673,9 @@ class NetPlan:
         P, st, lb = self.prog, self.store, self.bufs[l.name]
         rows = self.B * lb.Lz
         i = P.add(L.OP_BN_STATS, f"stats.{l.name}", z=lb.z, ld=lb.Cp, C=l.cout, rows_per_group=rows // self.groups,
-                  groups=self.groups, mean=lb.mean, invstd=lb.invstd, running_mean=st.b(l.bnkey + ".running_mean"),
+                  groups=self.groups, Cs=lb.Cp, mean=lb.mean, invstd=lb.invstd, scale=lb.scale, shift=lb.shift,
+                  gamma=st.p(l.bnkey + ".weight"), beta=st.p(l.bnkey + ".bias"),
+                  running_mean=st.b(l.bnkey + ".running_mean"),
                   running_var=st.b(l.bnkey + ".running_var"),
                   num_batches_tracked=st.nbt_view(l.bnkey + ".num_batches_tracked"), momentum=l.momentum, eps=BN_EPS,
                   partial=None, ticket=self._ticket(), update_all_groups=1 if self.groups > 1 else 0)
@@ -680,7 +689,7 @@ class NetPlan:
             # dpre is provided by the loss (or by an external output gradient); bias grad = column sums
             i = P.add(L.OP_COLSUM, f"dbias.{l.name}", src=lb.dpre, out=st.g(l.wkey + ".bias"), partial=None,
                       ticket=self._ticket(), rows=rows, ld=lb.Cp, C=l.cout, f32=0)
-            self._need_partial(i, 128 * l.cout)
+            self._need_partial(i, 128 * l.cout * 2)
         else:
             lb.dpre = self._zeros(B, lb.Lz, lb.Cp)
             gs = []

@@ -38,11 +38,12 @@ class FlatAdam:
         self.m = torch.zeros_like(store.flat)
         self.v = torch.zeros_like(store.flat)
         self.step = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.scalars = torch.zeros(2, dtype=torch.float32, device=dev)
 
     def record(self, prog: Program, gscale: float = 1.0):
         return prog.add(L.OP_ADAM, "adam", p=self.store.flat, g=self.store.grad, m=self.m, v=self.v, n=self.store.n,
                         lr=self.lr, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, gscale=float(gscale),
-                        step=self.step)
+                        step=self.step, scalars=self.scalars)
 
     def state_dict(self):
         st = self.store

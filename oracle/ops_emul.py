@@ -120,11 +120,16 @@ def wgrad(f: Dict):
 def bn_stats(f: Dict):
     C, G, rpg = f["C"], f["groups"], f["rows_per_group"]
     z = _rows2d(f["z"]).to(torch.float32)[:, :C].reshape(G, rpg, C)
+    gamma = f["gamma"][:C] if f.get("gamma") is not None else torch.ones(C)
+    beta = f["beta"][:C] if f.get("beta") is not None else torch.zeros(C)
     for g in range(G):
         mean = z[g].mean(0)
         var_b = z[g].var(0, unbiased=False)
-        f["mean"][g] = mean
-        f["invstd"][g] = 1.0 / torch.sqrt(var_b + f["eps"])
+        invstd = 1.0 / torch.sqrt(var_b + f["eps"])
+        f["mean"][g, :C] = mean
+        f["invstd"][g, :C] = invstd
+        f["scale"][g, :C] = invstd * gamma
+        f["shift"][g, :C] = beta - mean * (invstd * gamma)
         if f.get("running_mean") is not None and (g == 0 or f["update_all_groups"]):
             var_u = z[g].var(0, unbiased=True) if rpg > 1 else var_b
             m = f["momentum"]
@@ -134,27 +139,16 @@ def bn_stats(f: Dict):
         f["num_batches_tracked"] += G if f["update_all_groups"] else 1
 
 
-def _affine(src, C, g):
-    gamma = src["gamma"][:C] if src.get("gamma") is not None else torch.ones(C)
-    beta = src["beta"][:C] if src.get("beta") is not None else torch.zeros(C)
-    if src["use_running"]:
-        mean, invstd = src["running_mean"][:C], 1.0 / torch.sqrt(src["running_var"][:C] + src["eps"])
-    else:
-        mean, invstd = src["mean"][g, :C], src["invstd"][g, :C]
-    s = invstd * gamma
-    return s, beta - mean * s
-
-
-def _bn_src_eval(src, B, L, C, groups, Cs=None):
-    """(B, L, C) tensor of BN(src) under the source's row map."""
+def _bn_src_eval(src, B, L, C, groups):
+    """(B, L, C) tensor of BN(src) = z*scale + shift under the source's row map."""
     z = src["z"].to(torch.float32)
     Ls = src["L_src"]
-    z = z.reshape(B, Ls, -1)[:, :, src["coff"]: src["coff"] + C]
+    o = src["coff"]
+    z = z.reshape(B, Ls, -1)[:, :, o: o + C]
     Bg = B // groups
     y = torch.empty_like(z)
-    # the affine of the SOURCE layer is indexed by the source's own channel index: callers pass slices
     for g in range(groups):
-        s, t = _affine(_slice_affine(src, C), C, g)
+        s, t = src["scale"][g, o:o + C], src["shift"][g, o:o + C]
         y[g * Bg:(g + 1) * Bg] = z[g * Bg:(g + 1) * Bg] * s + t
     rm = src["rowmap"]
     if rm == ROW_IDENT:
@@ -169,20 +163,6 @@ def _bn_src_eval(src, B, L, C, groups, Cs=None):
     if rm == ROW_BCAST:
         return y[:, :1].expand(B, L, C)
     raise ValueError(rm)
-
-
-def _slice_affine(src, C):
-    """The per-channel BN arrays of a source are stored for ALL its channels; a consumer segment that
-    starts at channel `coff` of the source must read them at the same offset."""
-    o = src["coff"]
-    d = dict(src)
-    for k in ("gamma", "beta", "running_mean", "running_var"):
-        if d.get(k) is not None:
-            d[k] = d[k][o:o + C]
-    for k in ("mean", "invstd"):
-        if d.get(k) is not None:
-            d[k] = d[k][:, o:o + C]
-    return d
 
 
 def bn_apply(f: Dict):
@@ -236,10 +216,7 @@ def bn_bwd(f: Dict):
     for g in range(G):
         sl = slice(g * Bg, (g + 1) * Bg)
         mean, invstd = bn["mean"][g, :C], bn["invstd"][g, :C]
-        gamma = bn["gamma"][:C] if bn.get("gamma") is not None else torch.ones(C)
-        beta = bn["beta"][:C] if bn.get("beta") is not None else torch.zeros(C)
-        s = invstd * gamma
-        t = beta - mean * s
+        s, t = bn["scale"][g, :C], bn["shift"][g, :C]
         zg = z[sl]
         dy = torch.zeros(Bg, L, C)
         for i in range(f["ngsrc"]):
@@ -365,10 +342,11 @@ def bn_fold(f: Dict):
     C = f["C"]
     invstd = 1.0 / torch.sqrt(f["running_var"][:C] + f["eps"])
     s = invstd * (f["gamma"][:C] if f.get("gamma") is not None else 1.0)
-    f["scale"].zero_()
-    f["shift"].zero_()
-    f["scale"][:C] = s
-    f["shift"][:C] = (f["beta"][:C] if f.get("beta") is not None else 0.0) - f["running_mean"][:C] * s
+    scale, shift = f["scale"].reshape(-1), f["shift"].reshape(-1)
+    scale[: f["Cpad"]] = 0
+    shift[: f["Cpad"]] = 0
+    scale[:C] = s
+    shift[:C] = (f["beta"][:C] if f.get("beta") is not None else 0.0) - f["running_mean"][:C] * s
 
 
 def rot6d(f: Dict):

@@ -220,13 +220,14 @@ def test_adam_matches_torch():
     m, v = torch.zeros_like(p), torch.zeros_like(p)
     grad = torch.zeros_like(p)
     step = torch.zeros(1, dtype=torch.int64, device="cuda")
+    scalars = torch.zeros(2, device="cuda")
     for it in range(12):
         gr = torch.randn(n, generator=g) * (10.0 ** ((it % 5) - 4))
         ref.grad = gr.clone()
         opt.step()
         grad.copy_(gr)
         d = L.Adam(p=p.data_ptr(), g=grad.data_ptr(), m=m.data_ptr(), v=v.data_ptr(), n=n, lr=1e-3, beta1=0.9,
-                   beta2=0.999, eps=1e-8, gscale=1.0, step=step.data_ptr())
+                   beta2=0.999, eps=1e-8, gscale=1.0, step=step.data_ptr(), scalars=scalars.data_ptr())
         L.run_oneshot(d, L.F32, torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     assert int(step.item()) == 12
