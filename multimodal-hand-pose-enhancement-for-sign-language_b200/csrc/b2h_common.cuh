@@ -5,6 +5,8 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include <utility>
+
 #include "../../include/b2h_abi.h"
 
 namespace b2h {
@@ -43,6 +45,39 @@ extern thread_local int64_t g_launch_count;
       }                                                                                                    \
     }                                                                                                      \
   } while (0)
+
+// Programmatic dependent launch: every kernel of the library is launched with the programmatic-stream-
+// serialization attribute, so inside a stream (or a captured graph) kernel N+1 is scheduled while kernel N
+// still runs.  Each kernel executes pdl_sync() before its first global-memory access: it blocks until the
+// preceding grid has completed and flushed, then lets the next grid start its own launch/prologue.  What
+// overlaps is launch latency, CTA scheduling and the per-CTA prologue (barrier init, TMEM alloc, descriptor
+// prefetch) — no data is touched early.  B2H_NO_PDL=1 launches plainly (pdl_sync() is then a no-op).
+__device__ __forceinline__ void pdl_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+inline bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) on = getenv("B2H_NO_PDL") ? 0 : 1;
+  return on == 1;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                          Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 constexpr float kLeakySlope = 0.2f;  // nn.LeakyReLU(0.2, True), modelZoo.py:195
 

@@ -13,6 +13,7 @@ namespace b2h {
 constexpr int F_BM = 128, F_BN = 64, F_BK = 16;
 
 __global__ void __launch_bounds__(256) gemm_f32_kernel(b2h_gemm_t d, EpiParams e) {
+  pdl_sync();
   __shared__ __align__(16) float As[F_BK][F_BM + 4];
   __shared__ __align__(16) float Bs[F_BK][F_BN + 4];
   const int tid = threadIdx.x;
@@ -119,7 +120,7 @@ int launch_gemm_f32(const b2h_gemm_t& d, cudaStream_t s) {
   int rc = check_gemm(d);
   if (rc) return rc;
   dim3 grid(ceil_div(d.B * d.Lo, F_BM), d.Npad / F_BN);
-  gemm_f32_kernel<<<grid, 256, 0, s>>>(d, make_epi(d));
+  launch(gemm_f32_kernel, grid, 256, 0, s, d, make_epi(d));
   B2H_LAUNCH_CHECK("gemm_f32");
   return B2H_OK;
 }
@@ -132,6 +133,7 @@ constexpr int W_BM = 64, W_BN = 64, W_BK = 16;
 
 template <typename T>
 __global__ void __launch_bounds__(256) wgrad_simt_kernel(b2h_wgrad_t d, int splits, int rows_per_split) {
+  pdl_sync();
   __shared__ __align__(16) float As[W_BK][W_BM];
   __shared__ __align__(16) float Bs[W_BK][W_BN];
   const int tid = threadIdx.x;
@@ -186,6 +188,7 @@ __global__ void __launch_bounds__(256) wgrad_simt_kernel(b2h_wgrad_t d, int spli
 
 // dW[m][n][t] = sum_split partial[split][t][m][n]   (fixed order -> deterministic)
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(b2h_wgrad_t d, int splits) {
+  pdl_sync();
   const int64_t total = (int64_t)d.ntaps * d.Mvalid * d.Nvalid;
   const int64_t plane = (int64_t)d.Mpad * d.Npad;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -231,7 +234,7 @@ int launch_wgrad_reduce(const b2h_wgrad_t& d, int splits, cudaStream_t s) {
   B2H_CARVE(wgrad_reduce_kernel);
   int64_t total = (int64_t)d.ntaps * d.Mvalid * d.Nvalid;
   int blocks = (int)std::min<int64_t>(ceil_div64(total, 256), (int64_t)sm_count() * 8);
-  wgrad_reduce_kernel<<<blocks, 256, 0, s>>>(d, splits);
+  launch(wgrad_reduce_kernel, blocks, 256, 0, s, d, splits);
   B2H_LAUNCH_CHECK("wgrad_reduce");
   return B2H_OK;
 }
@@ -245,7 +248,7 @@ int launch_wgrad_f32(const b2h_wgrad_t& d, cudaStream_t s) {
   int rows_per_split = ceil_div(ceil_div(rows, splits), W_BK) * W_BK;
   splits = ceil_div(rows, rows_per_split);
   dim3 grid((d.Mpad / W_BM) * (d.Npad / W_BN), d.ntaps, splits);
-  wgrad_simt_kernel<float><<<grid, 256, 0, s>>>(d, splits, rows_per_split);
+  launch(wgrad_simt_kernel<float>, grid, 256, 0, s, d, splits, rows_per_split);
   B2H_LAUNCH_CHECK("wgrad_f32");
   return launch_wgrad_reduce(d, splits, s);
 }

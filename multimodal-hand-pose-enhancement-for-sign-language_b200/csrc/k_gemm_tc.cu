@@ -138,6 +138,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_sync();  // barriers, TMEM and descriptor prefetch above overlap the previous kernel's tail
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
@@ -349,6 +350,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_sync();  // barriers, TMEM and descriptor prefetch above overlap the previous kernel's tail
   const uint32_t tmem_base = *tmem_ptr;
 
   if (dead_tap) {
@@ -629,7 +631,7 @@ static int launch_fprop(const TcGemmPlan& plan, const EpiParams& e, cudaStream_t
     attr_set = true;
   }
   dim3 grid(plan.grid_x, plan.grid_y);
-  gemm_tc_kernel<BN, KIND><<<grid, TC_THREADS, Cfg::SMEM_BYTES, s>>>(plan.tmA0, plan.tmA1, plan.tmB, plan.p, e);
+  launch(gemm_tc_kernel<BN, KIND>, grid, TC_THREADS, Cfg::SMEM_BYTES, s, plan.tmA0, plan.tmA1, plan.tmB, plan.p, e);
   B2H_LAUNCH_CHECK("gemm_tc");
   return B2H_OK;
 }
@@ -704,7 +706,7 @@ static int launch_wg(const TcWgradPlan& plan, float* partial, cudaStream_t s) {
     attr_set = true;
   }
   dim3 grid(plan.grid_x, plan.p.ntaps, plan.splits);
-  wgrad_tc_kernel<WN><<<grid, 192, Cfg::SMEM_BYTES, s>>>(plan.tmP, plan.tmQ0, plan.tmQ1, plan.p, partial);
+  launch(wgrad_tc_kernel<WN>, grid, 192, Cfg::SMEM_BYTES, s, plan.tmP, plan.tmQ0, plan.tmQ1, plan.p, partial);
   B2H_LAUNCH_CHECK("wgrad_tc");
   return B2H_OK;
 }

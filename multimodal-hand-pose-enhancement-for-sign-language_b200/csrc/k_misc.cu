@@ -10,6 +10,7 @@ namespace b2h {
 // ---------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) prep_ncl_kernel(b2h_prep_t d) {
+  pdl_sync();
   // tile: 32 channels x 32 time steps of sample blockIdx.z
   __shared__ float tile[32][33];
   const int b = blockIdx.z, l0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -65,6 +66,7 @@ __global__ void __launch_bounds__(256) prep_ncl_kernel(b2h_prep_t d) {
 
 template <typename T>
 __global__ void __launch_bounds__(256) prep_rows_kernel(b2h_prep_t d) {
+  pdl_sync();
   // one thread per 4 channels; rows = B*L
   const int64_t rows = (int64_t)d.B * d.L;
   const int nq = d.Cfill / 4;
@@ -119,17 +121,17 @@ int launch_prep(const b2h_prep_t& d, int dtype, cudaStream_t s) {
     B2H_CHECK_ARG(d.Cfill % 4 == 0 && d.ld % 4 == 0, B2H_ERR_ALIGN, "prep: Cfill/ld must be multiples of 4");
     dim3 grid(ceil_div(d.L, 32), ceil_div(d.Cfill, 32), d.B), block(32, 8);
     if (dtype == B2H_BF16)
-      prep_ncl_kernel<__nv_bfloat16><<<grid, block, 0, s>>>(d);
+      launch(prep_ncl_kernel<__nv_bfloat16>, grid, block, 0, s, d);
     else
-      prep_ncl_kernel<float><<<grid, block, 0, s>>>(d);
+      launch(prep_ncl_kernel<float>, grid, block, 0, s, d);
   } else {
     B2H_CHECK_ARG(d.Cfill % 4 == 0 && d.ld % 4 == 0, B2H_ERR_ALIGN, "prep: Cfill/ld must be multiples of 4");
     int64_t work = (int64_t)d.B * d.L * (d.Cfill / 4);
     int blocks = (int)std::min<int64_t>(ceil_div64(work, 256), (int64_t)sm_count() * 16);
     if (dtype == B2H_BF16)
-      prep_rows_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>(d);
+      launch(prep_rows_kernel<__nv_bfloat16>, blocks, 256, 0, s, d);
     else
-      prep_rows_kernel<float><<<blocks, 256, 0, s>>>(d);
+      launch(prep_rows_kernel<float>, blocks, 256, 0, s, d);
   }
   B2H_LAUNCH_CHECK("prep");
   return B2H_OK;
@@ -140,6 +142,7 @@ int launch_prep(const b2h_prep_t& d, int dtype, cudaStream_t s) {
 // ---------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) to_ncl_kernel(b2h_to_ncl_t d) {
+  pdl_sync();
   __shared__ float tile[32][33];
   const int b = blockIdx.z, l0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   const int tx = threadIdx.x, ty = threadIdx.y;
@@ -162,9 +165,9 @@ int launch_to_ncl(const b2h_to_ncl_t& d, int dtype, cudaStream_t s) {
   B2H_CHECK_ARG(d.B > 0 && d.B <= 65535 && d.L > 0 && d.C > 0 && d.ld >= d.C, B2H_ERR_SHAPE, "to_ncl: bad shape");
   dim3 grid(ceil_div(d.L, 32), ceil_div(d.C, 32), d.B), block(32, 8);
   if (dtype == B2H_BF16 && !d.src_f32)
-    to_ncl_kernel<__nv_bfloat16><<<grid, block, 0, s>>>(d);
+    launch(to_ncl_kernel<__nv_bfloat16>, grid, block, 0, s, d);
   else
-    to_ncl_kernel<float><<<grid, block, 0, s>>>(d);
+    launch(to_ncl_kernel<float>, grid, block, 0, s, d);
   B2H_LAUNCH_CHECK("to_ncl");
   return B2H_OK;
 }
@@ -180,6 +183,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 template <typename T>
 __global__ void __launch_bounds__(256) l1_kernel(b2h_l1_t d, int cext) {
+  pdl_sync();
   __shared__ float tile[32][33];
   __shared__ double s_part[256];
   const int b = blockIdx.y, l0 = blockIdx.x * 32;
@@ -243,9 +247,9 @@ int launch_l1(const b2h_l1_t& d, int dtype, cudaStream_t s) {
   int cext = d.dout ? d.Cfill : d.C;
   dim3 grid(ceil_div(d.L, 32), d.B), block(32, 8);
   if (dtype == B2H_BF16)
-    l1_kernel<__nv_bfloat16><<<grid, block, 0, s>>>(d, cext);
+    launch(l1_kernel<__nv_bfloat16>, grid, block, 0, s, d, cext);
   else
-    l1_kernel<float><<<grid, block, 0, s>>>(d, cext);
+    launch(l1_kernel<float>, grid, block, 0, s, d, cext);
   B2H_LAUNCH_CHECK("l1");
   return B2H_OK;
 }
@@ -255,6 +259,7 @@ int64_t l1_partial_floats(const b2h_l1_t& d) { return (int64_t)ceil_div(d.L, 32)
 // MSE on discriminator scores (nn.MSELoss, train_gan.py:93): tiny, one CTA
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) mse_kernel(b2h_mse_t d) {
+  pdl_sync();
   __shared__ double s_red[256];
   double total = 0.0;
   for (int g = 0; g < d.groups; ++g) {
@@ -282,7 +287,7 @@ __global__ void __launch_bounds__(256) mse_kernel(b2h_mse_t d) {
 int launch_mse(const b2h_mse_t& d, cudaStream_t s) {
   B2H_CARVE(mse_kernel);
   B2H_CHECK_ARG(d.groups >= 1 && d.groups <= 2 && d.n > 0 && d.ld >= 1, B2H_ERR_SHAPE, "mse: bad shape");
-  mse_kernel<<<1, 256, 0, s>>>(d);
+  launch(mse_kernel, 1, 256, 0, s, d);
   B2H_LAUNCH_CHECK("mse");
   return B2H_OK;
 }
@@ -296,6 +301,7 @@ int launch_mse(const b2h_mse_t& d, cudaStream_t s) {
 // one thread: advance the step counter and evaluate the Python-double scalar prologue of
 // torch/optim/adam.py (_single_tensor_adam) once, so the element-wise kernel stays tiny
 __global__ void adam_step_kernel(b2h_adam_t d) {
+  pdl_sync();
   const int64_t t = *d.step + 1;
   *d.step = t;
   const double bc1 = 1.0 - pow(d.beta1, (double)t);
@@ -305,6 +311,7 @@ __global__ void adam_step_kernel(b2h_adam_t d) {
 }
 
 __global__ void __launch_bounds__(256) adam_kernel(b2h_adam_t d) {
+  pdl_sync();
   const float neg_step = d.scalars[0];
   const float bc2_sqrt = d.scalars[1];
   const float w1 = (float)(1.0 - d.beta1), w2 = (float)(1.0 - d.beta2);
@@ -348,10 +355,10 @@ int launch_adam(const b2h_adam_t& d, cudaStream_t s) {
   B2H_CHECK_ARG(((uintptr_t)d.p % 16 == 0) && ((uintptr_t)d.g % 16 == 0) && ((uintptr_t)d.m % 16 == 0) &&
                     ((uintptr_t)d.v % 16 == 0),
                 B2H_ERR_ALIGN, "adam: buffers must be 16-byte aligned");
-  adam_step_kernel<<<1, 1, 0, s>>>(d);
+  launch(adam_step_kernel, 1, 1, 0, s, d);
   B2H_LAUNCH_CHECK("adam_step");
   int blocks = (int)std::min<int64_t>(ceil_div64(d.n / 4 + 1, 256), (int64_t)sm_count() * 8);
-  adam_kernel<<<blocks, 256, 0, s>>>(d);
+  launch(adam_kernel, blocks, 256, 0, s, d);
   B2H_LAUNCH_CHECK("adam");
   return B2H_OK;
 }
@@ -382,11 +389,13 @@ __device__ __forceinline__ void pack_body(const b2h_pack_t& d, int64_t first, in
 
 template <typename T>
 __global__ void __launch_bounds__(256) pack_kernel(b2h_pack_t d) {
+  pdl_sync();
   pack_body<T>(d, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x);
 }
 
 template <typename T>
 __global__ void __launch_bounds__(256) pack_multi_kernel(b2h_pack_multi_t m) {
+  pdl_sync();
   __shared__ b2h_pack_t d;
   if (threadIdx.x < sizeof(b2h_pack_t) / 4)
     reinterpret_cast<uint32_t*>(&d)[threadIdx.x] = reinterpret_cast<const uint32_t*>(m.descs + blockIdx.y)[threadIdx.x];
@@ -402,9 +411,9 @@ int launch_pack_multi(const b2h_pack_multi_t& m, int dtype, cudaStream_t s) {
   int bx = (int)std::min<int64_t>(ceil_div64(m.max_elems, 256 * 8), 64);
   dim3 grid(std::max(bx, 1), m.n);
   if (dtype == B2H_BF16)
-    pack_multi_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(m);
+    launch(pack_multi_kernel<__nv_bfloat16>, grid, 256, 0, s, m);
   else
-    pack_multi_kernel<float><<<grid, 256, 0, s>>>(m);
+    launch(pack_multi_kernel<float>, grid, 256, 0, s, m);
   B2H_LAUNCH_CHECK("pack_multi");
   return B2H_OK;
 }
@@ -418,9 +427,9 @@ int launch_pack(const b2h_pack_t& d, int dtype, cudaStream_t s) {
   int64_t total = (int64_t)d.nphase * d.Opad * d.ntaps * d.Ipad;
   int blocks = (int)std::min<int64_t>(ceil_div64(total, 256), (int64_t)sm_count() * 8);
   if (dtype == B2H_BF16)
-    pack_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>(d);
+    launch(pack_kernel<__nv_bfloat16>, blocks, 256, 0, s, d);
   else
-    pack_kernel<float><<<blocks, 256, 0, s>>>(d);
+    launch(pack_kernel<float>, blocks, 256, 0, s, d);
   B2H_LAUNCH_CHECK("pack");
   return B2H_OK;
 }
@@ -430,6 +439,7 @@ int launch_pack(const b2h_pack_t& d, int dtype, cudaStream_t s) {
 //   x = a/(|a|+1e-6); z = x X b; z /= (|z|+1e-6); y = z X x; M = [x y z] as columns, row-major
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) rot6d_kernel(b2h_rot6d_t d) {
+  pdl_sync();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < d.n; i += (int64_t)gridDim.x * blockDim.x) {
     const float2* p = reinterpret_cast<const float2*>(d.r6d + i * 6);
     float2 p0 = p[0], p1 = p[1], p2 = p[2];
@@ -452,7 +462,7 @@ int launch_rot6d(const b2h_rot6d_t& d, cudaStream_t s) {
   B2H_CHECK_ARG(d.n > 0, B2H_ERR_SHAPE, "rot6d: n must be positive");
   B2H_CHECK_ARG((uintptr_t)d.r6d % 8 == 0, B2H_ERR_ALIGN, "rot6d: input must be 8-byte aligned");
   int blocks = (int)std::min<int64_t>(ceil_div64(d.n, 256), (int64_t)sm_count() * 8);
-  rot6d_kernel<<<blocks, 256, 0, s>>>(d);
+  launch(rot6d_kernel, blocks, 256, 0, s, d);
   B2H_LAUNCH_CHECK("rot6d");
   return B2H_OK;
 }

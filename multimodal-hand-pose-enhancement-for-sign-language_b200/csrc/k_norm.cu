@@ -68,6 +68,7 @@ constexpr int kCopies = 16;  // accumulator copies: CTA i adds into copy i % 16 
 
 template <typename T>
 __global__ void __launch_bounds__(kRowThreads) bn_stats_kernel(b2h_bn_stats_t d, int ctas_per_group) {
+  pdl_sync();
   __shared__ float4 s_red[kRowThreads];
   const int tx = threadIdx.x, ty = threadIdx.y, TXp = blockDim.x, TY = blockDim.y;
   const int g = blockIdx.y;
@@ -174,9 +175,9 @@ int launch_bn_stats(const b2h_bn_stats_t& d, int dtype, cudaStream_t s) {
   RowGrid rg = row_grid(d.C, d.rows_per_group);
   dim3 grid(rg.ctas, d.groups), block(rg.txp, rg.ty);
   if (dtype == B2H_BF16)
-    bn_stats_kernel<__nv_bfloat16><<<grid, block, 0, s>>>(d, rg.ctas);
+    launch(bn_stats_kernel<__nv_bfloat16>, grid, block, 0, s, d, rg.ctas);
   else
-    bn_stats_kernel<float><<<grid, block, 0, s>>>(d, rg.ctas);
+    launch(bn_stats_kernel<float>, grid, block, 0, s, d, rg.ctas);
   B2H_LAUNCH_CHECK("bn_stats");
   return B2H_OK;
 }
@@ -202,6 +203,7 @@ __device__ __forceinline__ int64_t src_row_of(const SrcRows& s, int row, int L) 
 
 template <typename T>
 __global__ void __launch_bounds__(256) bn_apply_kernel(b2h_bn_apply_t d) {
+  pdl_sync();
   const int tx = threadIdx.x, ty = threadIdx.y, TY = blockDim.y;
   const int c0 = tx * 8;
   if (c0 >= d.Cfill) return;
@@ -315,9 +317,9 @@ int launch_bn_apply(const b2h_bn_apply_t& d, int dtype, cudaStream_t s) {
   const int rows = d.B * d.L;
   dim3 grid(ceil_div(ceil_div(rows, 4), ty)), block(txp, ty);
   if (dtype == B2H_BF16)
-    bn_apply_kernel<__nv_bfloat16><<<grid, block, 0, s>>>(d);
+    launch(bn_apply_kernel<__nv_bfloat16>, grid, block, 0, s, d);
   else
-    bn_apply_kernel<float><<<grid, block, 0, s>>>(d);
+    launch(bn_apply_kernel<float>, grid, block, 0, s, d);
   B2H_LAUNCH_CHECK("bn_apply");
   return B2H_OK;
 }
@@ -384,6 +386,7 @@ __device__ __forceinline__ void add_grad_src8(const b2h_bn_bwd_t& d, const b2h_g
 
 template <typename T, int PASS>
 __global__ void __launch_bounds__(kRowThreads) bn_bwd_kernel(b2h_bn_bwd_t d) {
+  pdl_sync();
   __shared__ float4 s_red[kRowThreads];
   const int tx = threadIdx.x, ty = threadIdx.y, TXp = blockDim.x, TY = blockDim.y;
   const int g = blockIdx.y;
@@ -519,13 +522,13 @@ int launch_bn_bwd(const b2h_bn_bwd_t& d, int dtype, cudaStream_t s) {
   RowGrid rg = row_grid(d.Cfill, rpg);
   dim3 grid(rg.ctas, d.groups), block(rg.txp, rg.ty);
   if (dtype == B2H_BF16) {
-    bn_bwd_kernel<__nv_bfloat16, 1><<<grid, block, 0, s>>>(d);
+    launch(bn_bwd_kernel<__nv_bfloat16, 1>, grid, block, 0, s, d);
     B2H_LAUNCH_CHECK("bn_bwd pass 1");
-    bn_bwd_kernel<__nv_bfloat16, 2><<<grid, block, 0, s>>>(d);
+    launch(bn_bwd_kernel<__nv_bfloat16, 2>, grid, block, 0, s, d);
   } else {
-    bn_bwd_kernel<float, 1><<<grid, block, 0, s>>>(d);
+    launch(bn_bwd_kernel<float, 1>, grid, block, 0, s, d);
     B2H_LAUNCH_CHECK("bn_bwd pass 1");
-    bn_bwd_kernel<float, 2><<<grid, block, 0, s>>>(d);
+    launch(bn_bwd_kernel<float, 2>, grid, block, 0, s, d);
   }
   B2H_LAUNCH_CHECK("bn_bwd pass 2");
   return B2H_OK;
@@ -536,6 +539,7 @@ int launch_bn_bwd(const b2h_bn_bwd_t& d, int dtype, cudaStream_t s) {
 // ---------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(kRowThreads) colsum_kernel(b2h_colsum_t d) {
+  pdl_sync();
   __shared__ float4 s_red[kRowThreads];
   const int tx = threadIdx.x, ty = threadIdx.y, TXp = blockDim.x, TY = blockDim.y;
   const int c0 = tx * 8;
@@ -580,9 +584,9 @@ int launch_colsum(const b2h_colsum_t& d, int dtype, cudaStream_t s) {
   RowGrid rg = row_grid(d.C, d.rows);
   dim3 grid(rg.ctas), block(rg.txp, rg.ty);
   if (dtype == B2H_BF16 && !d.f32)
-    colsum_kernel<__nv_bfloat16><<<grid, block, 0, s>>>(d);
+    launch(colsum_kernel<__nv_bfloat16>, grid, block, 0, s, d);
   else
-    colsum_kernel<float><<<grid, block, 0, s>>>(d);
+    launch(colsum_kernel<float>, grid, block, 0, s, d);
   B2H_LAUNCH_CHECK("colsum");
   return B2H_OK;
 }
@@ -591,6 +595,7 @@ int launch_colsum(const b2h_colsum_t& d, int dtype, cudaStream_t s) {
 // bn_fold: eval-mode BN as a per-channel scale/shift (consumed by bn_apply sources and GEMM epilogues)
 // ---------------------------------------------------------------------------------------------
 __global__ void bn_fold_kernel(b2h_bn_fold_t d) {
+  pdl_sync();
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= d.Cpad) return;
   float s = 0.f, t = 0.f;
@@ -606,7 +611,7 @@ __global__ void bn_fold_kernel(b2h_bn_fold_t d) {
 int launch_bn_fold(const b2h_bn_fold_t& d, cudaStream_t s) {
   B2H_CARVE(bn_fold_kernel);
   B2H_CHECK_ARG(d.C > 0 && d.Cpad >= d.C, B2H_ERR_SHAPE, "bn_fold: bad shape");
-  bn_fold_kernel<<<ceil_div(d.Cpad, 128), 128, 0, s>>>(d);
+  launch(bn_fold_kernel, ceil_div(d.Cpad, 128), 128, 0, s, d);
   B2H_LAUNCH_CHECK("bn_fold");
   return B2H_OK;
 }
