@@ -280,6 +280,13 @@ typedef struct {
   float eps;
 } b2h_bn_fold_t;
 
+/* many BN folds in ONE launch: `descs` is a DEVICE array of n descriptors (all BN layers of an eval network) */
+typedef struct {
+  const b2h_bn_fold_t* descs;
+  int32_t n;
+  int32_t max_cpad; /* largest Cpad among the descriptors */
+} b2h_bn_fold_multi_t;
+
 /* 6D rotation -> 3x3 matrix, row-major 9 floats per joint (utils/conversion_utils.py:86-107) */
 typedef struct {
   const float* r6d; /* [n][6] */
@@ -322,6 +329,7 @@ int b2h_adam(const b2h_adam_t* d, b2h_stream_t s);
 int b2h_pack(const b2h_pack_t* d, int dtype, b2h_stream_t s);
 int b2h_pack_multi(const b2h_pack_multi_t* d, int dtype, b2h_stream_t s);
 int b2h_bn_fold(const b2h_bn_fold_t* d, b2h_stream_t s);
+int b2h_bn_fold_multi(const b2h_bn_fold_multi_t* d, b2h_stream_t s);
 int b2h_rot6d_to_mat(const b2h_rot6d_t* d, b2h_stream_t s);
 int b2h_fill(const b2h_fill_t* d, b2h_stream_t s);
 
@@ -331,7 +339,7 @@ typedef struct b2h_program b2h_program;
 enum b2h_op_kind {
   B2H_OP_GEMM = 1, B2H_OP_WGRAD, B2H_OP_BN_STATS, B2H_OP_BN_APPLY, B2H_OP_BN_BWD, B2H_OP_PREP,
   B2H_OP_TO_NCL, B2H_OP_L1, B2H_OP_MSE, B2H_OP_COLSUM, B2H_OP_ADAM, B2H_OP_PACK, B2H_OP_BN_FOLD,
-  B2H_OP_ROT6D, B2H_OP_FILL, B2H_OP_PACK_MULTI
+  B2H_OP_ROT6D, B2H_OP_FILL, B2H_OP_PACK_MULTI, B2H_OP_BN_FOLD_MULTI
 };
 b2h_program* b2h_program_create(int dtype);
 void b2h_program_destroy(b2h_program* p);

@@ -15,7 +15,7 @@ ROW_IDENT, ROW_UP2, ROW_POOL2, ROW_BCAST = 0, 1, 2, 3
 SRC_NCL, SRC_ROWS, SRC_BCAST, SRC_MOTION = 0, 1, 2, 3
 DROP_NONE, DROP_MASK, DROP_PHILOX = 0, 1, 2
 (OP_GEMM, OP_WGRAD, OP_BN_STATS, OP_BN_APPLY, OP_BN_BWD, OP_PREP, OP_TO_NCL, OP_L1, OP_MSE, OP_COLSUM,
- OP_ADAM, OP_PACK, OP_BN_FOLD, OP_ROT6D, OP_FILL, OP_PACK_MULTI) = range(1, 17)
+ OP_ADAM, OP_PACK, OP_BN_FOLD, OP_ROT6D, OP_FILL, OP_PACK_MULTI, OP_BN_FOLD_MULTI) = range(1, 18)
 
 i32, i64, f32, f64, vp = C.c_int32, C.c_int64, C.c_float, C.c_double, C.c_void_p
 
@@ -112,6 +112,10 @@ class BnFold(C.Structure):
                 ("scale", vp), ("shift", vp), ("C", i32), ("Cpad", i32), ("eps", f32)]
 
 
+class BnFoldMulti(C.Structure):
+    _fields_ = [("descs", vp), ("n", i32), ("max_cpad", i32)]
+
+
 class Rot6d(C.Structure):
     _fields_ = [("r6d", vp), ("mat", vp), ("n", i64)]
 
@@ -122,7 +126,8 @@ class Fill(C.Structure):
 
 OP_STRUCT = {OP_GEMM: Gemm, OP_WGRAD: Wgrad, OP_BN_STATS: BnStats, OP_BN_APPLY: BnApply, OP_BN_BWD: BnBwd,
              OP_PREP: Prep, OP_TO_NCL: ToNcl, OP_L1: L1, OP_MSE: Mse, OP_COLSUM: Colsum, OP_ADAM: Adam,
-             OP_PACK: Pack, OP_BN_FOLD: BnFold, OP_ROT6D: Rot6d, OP_FILL: Fill, OP_PACK_MULTI: PackMulti}
+             OP_PACK: Pack, OP_BN_FOLD: BnFold, OP_ROT6D: Rot6d, OP_FILL: Fill, OP_PACK_MULTI: PackMulti,
+             OP_BN_FOLD_MULTI: BnFoldMulti}
 KIND_OF = {v: k for k, v in OP_STRUCT.items()}
 
 # every symbol include/b2h_abi.h declares: name -> (restype, argtypes)
@@ -149,6 +154,7 @@ SYMBOLS = {
     "b2h_pack": (C.c_int, [C.POINTER(Pack), C.c_int, vp]),
     "b2h_pack_multi": (C.c_int, [C.POINTER(PackMulti), C.c_int, vp]),
     "b2h_bn_fold": (C.c_int, [C.POINTER(BnFold), vp]),
+    "b2h_bn_fold_multi": (C.c_int, [C.POINTER(BnFoldMulti), vp]),
     "b2h_rot6d_to_mat": (C.c_int, [C.POINTER(Rot6d), vp]),
     "b2h_fill": (C.c_int, [C.POINTER(Fill), vp]),
     "b2h_program_create": (vp, [C.c_int]),
@@ -164,7 +170,7 @@ ONESHOT = {OP_GEMM: ("b2h_gemm", True), OP_WGRAD: ("b2h_wgrad", True), OP_BN_STA
            OP_TO_NCL: ("b2h_to_ncl", True), OP_L1: ("b2h_l1", True), OP_MSE: ("b2h_mse", False),
            OP_COLSUM: ("b2h_colsum", True), OP_ADAM: ("b2h_adam", False), OP_PACK: ("b2h_pack", True),
            OP_BN_FOLD: ("b2h_bn_fold", False), OP_ROT6D: ("b2h_rot6d_to_mat", False), OP_FILL: ("b2h_fill", False),
-           OP_PACK_MULTI: ("b2h_pack_multi", True)}
+           OP_PACK_MULTI: ("b2h_pack_multi", True), OP_BN_FOLD_MULTI: ("b2h_bn_fold_multi", False)}
 
 
 class B2HError(RuntimeError):

@@ -71,6 +71,7 @@ union OpDesc {
   b2h_rot6d_t rot6d;
   b2h_fill_t fill;
   b2h_pack_multi_t pack_multi;
+  b2h_bn_fold_multi_t bn_fold_multi;
   OpDesc() { memset(this, 0, sizeof(*this)); }
 };
 
@@ -92,6 +93,7 @@ static size_t desc_size(int kind) {
     case B2H_OP_ROT6D: return sizeof(b2h_rot6d_t);
     case B2H_OP_FILL: return sizeof(b2h_fill_t);
     case B2H_OP_PACK_MULTI: return sizeof(b2h_pack_multi_t);
+    case B2H_OP_BN_FOLD_MULTI: return sizeof(b2h_bn_fold_multi_t);
     default: return 0;
   }
 }
@@ -123,6 +125,7 @@ static int run_op(const Op& op, int dtype, cudaStream_t s) {
     case B2H_OP_ROT6D: return launch_rot6d(op.d.rot6d, s);
     case B2H_OP_FILL: return launch_fill(op.d.fill, s);
     case B2H_OP_PACK_MULTI: return launch_pack_multi(op.d.pack_multi, dtype, s);
+    case B2H_OP_BN_FOLD_MULTI: return launch_bn_fold_multi(op.d.bn_fold_multi, s);
     default: set_error("unknown op kind %d", op.kind); return B2H_ERR_ARG;
   }
 }
@@ -195,6 +198,10 @@ int b2h_adam(const b2h_adam_t* d, b2h_stream_t s) {
 int b2h_bn_fold(const b2h_bn_fold_t* d, b2h_stream_t s) {
   const int dtype = B2H_F32;
   B2H_ONESHOT(B2H_OP_BN_FOLD, bn_fold, d)
+}
+int b2h_bn_fold_multi(const b2h_bn_fold_multi_t* d, b2h_stream_t s) {
+  const int dtype = B2H_F32;
+  B2H_ONESHOT(B2H_OP_BN_FOLD_MULTI, bn_fold_multi, d)
 }
 int b2h_rot6d_to_mat(const b2h_rot6d_t* d, b2h_stream_t s) {
   const int dtype = B2H_F32;

@@ -341,6 +341,7 @@ int launch_adam(const b2h_adam_t& d, cudaStream_t s);
 int launch_pack(const b2h_pack_t& d, int dtype, cudaStream_t s);
 int launch_pack_multi(const b2h_pack_multi_t& d, int dtype, cudaStream_t s);
 int launch_bn_fold(const b2h_bn_fold_t& d, cudaStream_t s);
+int launch_bn_fold_multi(const b2h_bn_fold_multi_t& d, cudaStream_t s);
 int launch_rot6d(const b2h_rot6d_t& d, cudaStream_t s);
 int launch_fill(const b2h_fill_t& d, cudaStream_t s);
 

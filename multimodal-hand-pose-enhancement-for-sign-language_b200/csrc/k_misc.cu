@@ -366,31 +366,48 @@ int launch_adam(const b2h_adam_t& d, cudaStream_t s) {
 // ---------------------------------------------------------------------------------------------
 // weight repack (PyTorch layout fp32 -> GEMM operand layout [Opad*nphase][ntaps][Ipad], act dtype)
 // ---------------------------------------------------------------------------------------------
+// One thread writes 8 consecutive `i` of one (phase, o, tap) — a single 16 B store in bf16.  The lane-fast index
+// is whichever of i / o is closer to contiguous in W, so the fp32 gathers of a warp share sectors: i for the
+// forward layouts (W is [o][i][k]), o for the transposed dgrad layouts (W is [i][o][k]).
 template <typename T>
-__device__ __forceinline__ void pack_body(const b2h_pack_t& d, int64_t first, int64_t stride) {
-  const int64_t total = (int64_t)d.nphase * d.Opad * d.ntaps * d.Ipad;
+__device__ __forceinline__ void pack_body(const b2h_pack_t& d, uint32_t first, uint32_t stride) {
+  const uint32_t I8 = (uint32_t)d.Ipad >> 3, Opad = (uint32_t)d.Opad, ntaps = (uint32_t)d.ntaps;
+  const uint32_t total = (uint32_t)d.nphase * Opad * ntaps * I8;
+  const bool o_fast = d.o_stride < d.i_stride;
   T* out = reinterpret_cast<T*>(d.out);
-  for (int64_t idx = first; idx < total; idx += stride) {
-    int i = (int)(idx % d.Ipad);
-    int64_t r = idx / d.Ipad;
-    int t = (int)(r % d.ntaps);
-    r /= d.ntaps;
-    int o = (int)(r % d.Opad);
-    int ph = (int)(r / d.Opad);
-    int k = d.tapmap[ph][t];
-    float v = 0.f;
-    if (k >= 0 && o < d.O && i < d.I) v = d.W[(int64_t)o * d.o_stride + (int64_t)i * d.i_stride + (int64_t)k * d.k_stride];
-    out[idx] = from_f<T>(v);
+  for (uint32_t idx = first; idx < total; idx += stride) {
+    uint32_t i8, t, o, ph, r;
+    if (o_fast) {
+      o = idx % Opad, r = idx / Opad;
+      t = r % ntaps, r /= ntaps;
+      i8 = r % I8, ph = r / I8;
+    } else {
+      i8 = idx % I8, r = idx / I8;
+      t = r % ntaps, r /= ntaps;
+      o = r % Opad, ph = r / Opad;
+    }
+    const int k = d.tapmap[ph][t];
+    F8 v;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v.v[j] = 0.f;
+    if (k >= 0 && (int)o < d.O) {
+      const float* w = d.W + (int64_t)o * d.o_stride + (int64_t)k * d.k_stride;
+      const int i0 = (int)i8 * 8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (i0 + j < d.I) v.v[j] = __ldg(w + (int64_t)(i0 + j) * d.i_stride);
+    }
+    store8<T>(out + (((int64_t)ph * Opad + o) * ntaps + t) * d.Ipad + i8 * 8, v);
   }
   if (d.out_bias) {
-    for (int64_t o = first; o < (int64_t)d.Opad; o += stride) d.out_bias[o] = (d.bias && o < d.O) ? d.bias[o] : 0.f;
+    for (uint32_t o = first; o < Opad; o += stride) d.out_bias[o] = (d.bias && (int)o < d.O) ? d.bias[o] : 0.f;
   }
 }
 
 template <typename T>
 __global__ void __launch_bounds__(256) pack_kernel(b2h_pack_t d) {
   pdl_sync();
-  pack_body<T>(d, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x);
+  pack_body<T>(d, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
 }
 
 template <typename T>
@@ -400,7 +417,7 @@ __global__ void __launch_bounds__(256) pack_multi_kernel(b2h_pack_multi_t m) {
   if (threadIdx.x < sizeof(b2h_pack_t) / 4)
     reinterpret_cast<uint32_t*>(&d)[threadIdx.x] = reinterpret_cast<const uint32_t*>(m.descs + blockIdx.y)[threadIdx.x];
   __syncthreads();
-  pack_body<T>(d, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x);
+  pack_body<T>(d, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
 }
 
 int launch_pack_multi(const b2h_pack_multi_t& m, int dtype, cudaStream_t s) {
@@ -408,7 +425,7 @@ int launch_pack_multi(const b2h_pack_multi_t& m, int dtype, cudaStream_t s) {
   B2H_CARVE(pack_multi_kernel<float>);
   B2H_CHECK_ARG(m.descs && m.n > 0 && m.n <= 65535 && m.max_elems > 0, B2H_ERR_ARG, "pack_multi: bad args");
   static_assert(sizeof(b2h_pack_t) % 4 == 0 && sizeof(b2h_pack_t) / 4 <= 256, "descriptor staging");
-  int bx = (int)std::min<int64_t>(ceil_div64(m.max_elems, 256 * 8), 64);
+  int bx = (int)std::min<int64_t>(ceil_div64(m.max_elems, 256 * 8 * 2), 64);
   dim3 grid(std::max(bx, 1), m.n);
   if (dtype == B2H_BF16)
     launch(pack_multi_kernel<__nv_bfloat16>, grid, 256, 0, s, m);
@@ -424,8 +441,10 @@ int launch_pack(const b2h_pack_t& d, int dtype, cudaStream_t s) {
   B2H_CHECK_ARG(d.O > 0 && d.I > 0 && d.Opad >= d.O && d.Ipad >= d.I && d.ntaps >= 1 && d.ntaps <= B2H_MAX_TAPS &&
                     d.nphase >= 1 && d.nphase <= 2,
                 B2H_ERR_SHAPE, "pack: bad shape");
+  B2H_CHECK_ARG(d.Ipad % 8 == 0, B2H_ERR_ALIGN, "pack: Ipad must be a multiple of 8");
   int64_t total = (int64_t)d.nphase * d.Opad * d.ntaps * d.Ipad;
-  int blocks = (int)std::min<int64_t>(ceil_div64(total, 256), (int64_t)sm_count() * 8);
+  B2H_CHECK_ARG(total < ((int64_t)1 << 31), B2H_ERR_SHAPE, "pack: operand too large");
+  int blocks = (int)std::min<int64_t>(ceil_div64(total, 256 * 8), (int64_t)sm_count() * 8);
   if (dtype == B2H_BF16)
     launch(pack_kernel<__nv_bfloat16>, blocks, 256, 0, s, d);
   else

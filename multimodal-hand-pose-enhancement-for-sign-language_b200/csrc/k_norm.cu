@@ -594,9 +594,7 @@ int launch_colsum(const b2h_colsum_t& d, int dtype, cudaStream_t s) {
 // ---------------------------------------------------------------------------------------------
 // bn_fold: eval-mode BN as a per-channel scale/shift (consumed by bn_apply sources and GEMM epilogues)
 // ---------------------------------------------------------------------------------------------
-__global__ void bn_fold_kernel(b2h_bn_fold_t d) {
-  pdl_sync();
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void bn_fold_body(const b2h_bn_fold_t& d, int c) {
   if (c >= d.Cpad) return;
   float s = 0.f, t = 0.f;
   if (c < d.C) {
@@ -607,12 +605,33 @@ __global__ void bn_fold_kernel(b2h_bn_fold_t d) {
   d.scale[c] = s;
   d.shift[c] = t;
 }
+__global__ void bn_fold_kernel(b2h_bn_fold_t d) {
+  pdl_sync();
+  bn_fold_body(d, blockIdx.x * blockDim.x + threadIdx.x);
+}
+__global__ void bn_fold_multi_kernel(b2h_bn_fold_multi_t m) {
+  pdl_sync();
+  __shared__ b2h_bn_fold_t d;
+  if (threadIdx.x < sizeof(b2h_bn_fold_t) / 4)
+    reinterpret_cast<uint32_t*>(&d)[threadIdx.x] = reinterpret_cast<const uint32_t*>(m.descs + blockIdx.y)[threadIdx.x];
+  __syncthreads();
+  bn_fold_body(d, blockIdx.x * blockDim.x + threadIdx.x);
+}
 
 int launch_bn_fold(const b2h_bn_fold_t& d, cudaStream_t s) {
   B2H_CARVE(bn_fold_kernel);
   B2H_CHECK_ARG(d.C > 0 && d.Cpad >= d.C, B2H_ERR_SHAPE, "bn_fold: bad shape");
   launch(bn_fold_kernel, ceil_div(d.Cpad, 128), 128, 0, s, d);
   B2H_LAUNCH_CHECK("bn_fold");
+  return B2H_OK;
+}
+
+int launch_bn_fold_multi(const b2h_bn_fold_multi_t& m, cudaStream_t s) {
+  B2H_CARVE(bn_fold_multi_kernel);
+  static_assert(sizeof(b2h_bn_fold_t) % 4 == 0 && sizeof(b2h_bn_fold_t) / 4 <= 128, "descriptor staging");
+  B2H_CHECK_ARG(m.descs && m.n > 0 && m.n <= 65535 && m.max_cpad > 0, B2H_ERR_ARG, "bn_fold_multi: bad args");
+  launch(bn_fold_multi_kernel, dim3(ceil_div(m.max_cpad, 128), m.n), 128, 0, s, m);
+  B2H_LAUNCH_CHECK("bn_fold_multi");
   return B2H_OK;
 }
 

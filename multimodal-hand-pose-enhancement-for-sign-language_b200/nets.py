@@ -343,8 +343,14 @@ class NetPlan:
     def __init__(self, spec: NetSpec, store: ParamStore, B: int, T: int, dtype: int, device,
                  train: bool, groups: int = 1, drop_mode: str = "philox",
                  drop_state: Optional[torch.Tensor] = None, site_base: int = 0,
-                 motion_src: Optional[Sequence[torch.Tensor]] = None):
+                 motion_src: Optional[Sequence[torch.Tensor]] = None,
+                 weights_from: Optional["NetPlan"] = None):
+        """`weights_from`: another plan of the SAME store and dtype whose packed forward weights / biases this
+        plan reads instead of packing its own (the eval twin of a train plan: one repack per optimizer step
+        serves both)."""
         assert drop_mode in ("none", "mask", "philox")
+        assert weights_from is None or (weights_from.store is store and weights_from.dtype == dtype and not train)
+        self.weights_from = weights_from
         self.spec, self.store, self.B, self.T, self.dtype = spec, store, B, T, dtype
         self.device = torch.device(device)
         self.train, self.groups = train, groups
@@ -490,16 +496,10 @@ class NetPlan:
             self._pack_items: List[dict] = []
             for l in spec.layers:
                 self._emit_pack(l)
-            self._emit_pack_table()
+            if self._pack_items:
+                self._emit_pack_table()
             if not self.train:
-                st = self.store
-                for l in spec.layers:
-                    if l.bn:
-                        lb = self.bufs[l.name]
-                        P.add(L.OP_BN_FOLD, f"fold.{l.name}", gamma=st.p(l.bnkey + ".weight"),
-                              beta=st.p(l.bnkey + ".bias"), running_mean=st.b(l.bnkey + ".running_mean"),
-                              running_var=st.b(l.bnkey + ".running_var"), scale=lb.scale, shift=lb.shift,
-                              C=l.cout, Cpad=lb.Cp, eps=BN_EPS)
+                self._emit_fold_table()
         with P.segment("fwd"):
             for l in spec.layers:
                 self._emit_input(l)
@@ -546,8 +546,32 @@ class NetPlan:
         self.prog.add(L.OP_PACK_MULTI, "pack_multi", descs=self.pack_table, n=n, max_elems=max_elems,
                       _items=self._pack_items)
 
+    def _emit_fold_table(self):
+        """Eval-mode BN of every layer folded to scale/shift in ONE launch (device array of b2h_bn_fold_t)."""
+        from .program import _fill_struct
+        st, items = self.store, []
+        for l in self.spec.layers:
+            if l.bn:
+                lb = self.bufs[l.name]
+                items.append(dict(_tag=f"fold.{l.name}", gamma=st.p(l.bnkey + ".weight"), beta=st.p(l.bnkey + ".bias"),
+                                  running_mean=st.b(l.bnkey + ".running_mean"),
+                                  running_var=st.b(l.bnkey + ".running_var"), scale=lb.scale, shift=lb.shift,
+                                  C=l.cout, Cpad=lb.Cp, eps=BN_EPS))
+        if not items:
+            return
+        raw = bytearray()
+        for it in items:
+            raw += bytes(_fill_struct(L.BnFold(), {k: v for k, v in it.items() if not k.startswith("_")}))
+        self.fold_table = torch.frombuffer(raw, dtype=torch.uint8).clone().to(self.device)
+        self.prog.add(L.OP_BN_FOLD_MULTI, "fold_multi", descs=self.fold_table, n=len(items),
+                      max_cpad=max(it["Cpad"] for it in items), _items=items)
+
     def _emit_pack(self, l: Layer):
         P, st, lb = self.prog, self.store, self.bufs[l.name]
+        src = self.weights_from.bufs.get(l.name) if self.weights_from is not None else None
+        if src is not None and src.wf is not None and (src.Kc, src.Cp) == (lb.Kc, lb.Cp):
+            lb.wf, lb.bias, lb.fwd_taps = src.wf, src.bias, src.fwd_taps
+            return
         W = st.p(l.wkey + ".weight")
         bias = st.p(l.wkey + ".bias")
         k = l.k
@@ -741,6 +765,8 @@ class NetPlan:
         self._packed_version = self.store.version
 
     def ensure_packed(self):
+        if self.weights_from is not None:
+            self.weights_from.ensure_packed()
         if getattr(self, "_packed_version", None) != self.store.version:
             self.pack()
 

@@ -104,17 +104,18 @@ class GanTrainer:
         kw = dict(drop_mode=drop_mode, drop_state=self.drop_state)
         # generator: train plan (G step) and eval plan (D step / inference)
         self.G_train = nets.NetPlan(self.g_spec, self.g_store, B, T, self.dtype, dev, train=True, site_base=0, **kw)
-        self.G_eval = nets.NetPlan(self.g_spec_eval, self.g_store, B, T, self.dtype, dev, train=False)
+        self.G_eval = nets.NetPlan(self.g_spec_eval, self.g_store, B, T, self.dtype, dev, train=False,
+                                   weights_from=self.G_train)
         self.y = torch.zeros(B, out_dim, T, dtype=torch.float32, device=dev)
         # the eval plan shares the input buffers of the train plan
         self.x = self.G_train.x
         self.feats = self.G_train.feats
         self._alias_inputs(self.G_eval, self.G_train)
         # discriminator: eval plan scoring calc_motion(G_train.out); grouped train plan on (fake, real)
-        self.D_eval = nets.NetPlan(self.d_spec, self.d_store, B, T, self.dtype, dev, train=False,
-                                   motion_src=[self.G_train.out])
         self.D_train = nets.NetPlan(self.d_spec, self.d_store, 2 * B, T, self.dtype, dev, train=True, groups=2,
                                     motion_src=[self.G_eval.out, self.y], site_base=100, **kw)
+        self.D_eval = nets.NetPlan(self.d_spec, self.d_store, B, T, self.dtype, dev, train=False,
+                                   motion_src=[self.G_train.out], weights_from=self.D_train)
         self.losses = torch.zeros(8, dtype=torch.float32, device=dev)  # [l1, adv, g_total, d_loss]
         self._build_loss_programs(label_smooth)
         self._graphs: Dict[str, torch.cuda.CUDAGraph] = {}
@@ -242,25 +243,45 @@ class GanTrainer:
             cur.wait_event(ev)
 
     # ---- steps ---------------------------------------------------------------------------------
-    def _g_step_body(self):
-        self.G_train.pack()
-        self.D_eval.ensure_packed()
+    # The packed (GEMM-layout) weights of a network are refreshed right after its Adam update, once per
+    # step, and shared by its train and eval plans; the eval plan's only per-step preparation is folding the
+    # running BN statistics (one launch).
+    def _g_ops(self):
+        self.D_eval.prog.run("pack")      # fold D's running statistics
         self.G_train.prog.run("fwd")
         self.D_eval.prog.run("fwd")
         self.g_loss_prog.run("loss")
         self._bwd_bucketed(self.G_train)
         self.g_loss_prog.run("opt")
-        self.g_store.version += 1
+        self.G_train.prog.run("pack")     # repack the updated generator weights
 
-    def _d_step_body(self):
-        self.G_eval.ensure_packed()
-        self.D_train.pack()
+    def _d_ops(self):
+        self.G_eval.prog.run("pack")      # fold G's running statistics
         self.G_eval.prog.run("fwd")
         self.D_train.prog.run("fwd")
         self.d_loss_prog.run("loss")
         self._bwd_bucketed(self.D_train)
         self.d_loss_prog.run("opt")
-        self.d_store.version += 1
+        self.D_train.prog.run("pack")
+
+    def _ensure_packed(self):
+        """Weights changed from outside (load_state_dict, user edits): repack before the step."""
+        self.G_train.ensure_packed()
+        self.D_train.ensure_packed()
+
+    def _mark_stepped(self, key):
+        if key == "g":
+            self.g_store.version += 1
+            self.G_train._packed_version = self.g_store.version
+        else:
+            self.d_store.version += 1
+            self.D_train._packed_version = self.d_store.version
+
+    def _g_step_body(self):
+        self._g_ops()
+
+    def _d_step_body(self):
+        self._d_ops()
 
     def _bump_step(self):
         self.drop_state[1] += 1
@@ -274,41 +295,26 @@ class GanTrainer:
         self._run("d", self._d_step_body, graph)
 
     def _run(self, key, body, graph):
+        self._ensure_packed()
         if not graph:
             body()
+            self._mark_stepped(key)
             self._bump_step()
             return
-        # the frozen network of the step is re-packed outside the graph, only when its weights changed
-        (self.D_eval if key == "g" else self.G_eval).ensure_packed()
         g = self._graphs.get(key)
         if g is None:
             body()   # warm up eagerly (finalises programs, sets kernel attributes)
+            self._mark_stepped(key)
             self._bump_step()
             torch.cuda.synchronize(self.device)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                if key == "g":
-                    self.G_train.prog.run("pack")
-                    self.G_train.prog.run("fwd")
-                    self.D_eval.prog.run("fwd")
-                    self.g_loss_prog.run("loss")
-                    self._bwd_bucketed(self.G_train)
-                    self.g_loss_prog.run("opt")
-                else:
-                    self.D_train.prog.run("pack")
-                    self.G_eval.prog.run("fwd")
-                    self.D_train.prog.run("fwd")
-                    self.d_loss_prog.run("loss")
-                    self._bwd_bucketed(self.D_train)
-                    self.d_loss_prog.run("opt")
+                body()
                 self.drop_state[1] += 1
             self._graphs[key] = g
             return
         g.replay()
-        if key == "g":
-            self.g_store.version += 1
-        else:
-            self.d_store.version += 1
+        self._mark_stepped(key)
 
     # ---- inference -----------------------------------------------------------------------------
     def infer(self):
@@ -319,8 +325,8 @@ class GanTrainer:
     def launches_per_gan_step(self) -> int:
         """Kernel launches of one generator step + one discriminator step (measured from the programs)."""
         n = 0
-        for p, segs in ((self.G_train.prog, ("pack", "fwd", "bwd")), (self.D_eval.prog, ("fwd",)),
-                        (self.g_loss_prog, ("loss", "opt")), (self.G_eval.prog, ("fwd",)),
+        for p, segs in ((self.G_train.prog, ("pack", "fwd", "bwd")), (self.D_eval.prog, ("pack", "fwd")),
+                        (self.g_loss_prog, ("loss", "opt")), (self.G_eval.prog, ("pack", "fwd")),
                         (self.D_train.prog, ("pack", "fwd", "bwd")), (self.d_loss_prog, ("loss", "opt"))):
             n += sum(p.segment_launches.get(s, 0) for s in segs)
         return n

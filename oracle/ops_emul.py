@@ -22,7 +22,7 @@ ROW_IDENT, ROW_UP2, ROW_POOL2, ROW_BCAST = 0, 1, 2, 3
 SRC_NCL, SRC_ROWS, SRC_BCAST, SRC_MOTION = 0, 1, 2, 3
 DROP_NONE, DROP_MASK, DROP_PHILOX = 0, 1, 2
 (OP_GEMM, OP_WGRAD, OP_BN_STATS, OP_BN_APPLY, OP_BN_BWD, OP_PREP, OP_TO_NCL, OP_L1, OP_MSE, OP_COLSUM,
- OP_ADAM, OP_PACK, OP_BN_FOLD, OP_ROT6D, OP_FILL, OP_PACK_MULTI) = range(1, 17)
+ OP_ADAM, OP_PACK, OP_BN_FOLD, OP_ROT6D, OP_FILL, OP_PACK_MULTI, OP_BN_FOLD_MULTI) = range(1, 18)
 
 
 def _act(x, act):
@@ -349,6 +349,11 @@ def bn_fold(f: Dict):
     shift[:C] = (f["beta"][:C] if f.get("beta") is not None else 0.0) - f["running_mean"][:C] * s
 
 
+def bn_fold_multi(f: Dict):
+    for item in f["_items"]:
+        bn_fold(item)
+
+
 def rot6d(f: Dict):
     f["mat"].reshape(-1, 9).copy_(rot6d_to_mat(f["r6d"].reshape(-1, 6)))
 
@@ -371,7 +376,7 @@ def fill(f: Dict):
 DISPATCH = {OP_GEMM: gemm, OP_WGRAD: wgrad, OP_BN_STATS: bn_stats, OP_BN_APPLY: bn_apply, OP_BN_BWD: bn_bwd,
             OP_PREP: prep, OP_TO_NCL: to_ncl, OP_L1: l1, OP_MSE: mse, OP_COLSUM: colsum, OP_ADAM: adam,
             OP_PACK: pack, OP_BN_FOLD: bn_fold, OP_ROT6D: rot6d, OP_FILL: fill,
-            OP_PACK_MULTI: pack_multi}
+            OP_PACK_MULTI: pack_multi, OP_BN_FOLD_MULTI: bn_fold_multi}
 
 
 def run_records(recs, first=0, end=None):

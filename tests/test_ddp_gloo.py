@@ -53,7 +53,8 @@ def _worker(rank, port, ret):
     masks = R.make_masks(G, xs, seed=100 + rank)
     tr.G_train.set_masks(masks)
     run = lambda prog, seg: E.run_records(prog.recs, *prog.segments[seg])  # noqa: E731
-    for prog, seg in ((tr.G_train.prog, "pack"), (tr.D_eval.prog, "pack"), (tr.G_train.prog, "fwd"),
+    for prog, seg in ((tr.G_train.prog, "pack"), (tr.D_train.prog, "pack"), (tr.D_eval.prog, "pack"),
+                      (tr.G_train.prog, "fwd"),
                       (tr.D_eval.prog, "fwd"), (tr.g_loss_prog, "loss")):
         run(prog, seg)
     buckets = tr.bucket_plan(tr.G_train)

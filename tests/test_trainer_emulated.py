@@ -64,13 +64,16 @@ def emul(prog, seg):
 
 
 def emul_g_step(tr):
-    for p, s in ((tr.G_train.prog, "pack"), (tr.D_eval.prog, "pack"), (tr.G_train.prog, "fwd"), (tr.D_eval.prog, "fwd"),
+    # (the eval plans read the packed weights of their train twins: pack those first)
+    for p, s in ((tr.G_train.prog, "pack"), (tr.D_train.prog, "pack"), (tr.D_eval.prog, "pack"),
+                 (tr.G_train.prog, "fwd"), (tr.D_eval.prog, "fwd"),
                  (tr.g_loss_prog, "loss"), (tr.G_train.prog, "bwd"), (tr.g_loss_prog, "opt")):
         emul(p, s)
 
 
 def emul_d_step(tr):
-    for p, s in ((tr.G_eval.prog, "pack"), (tr.D_train.prog, "pack"), (tr.G_eval.prog, "fwd"), (tr.D_train.prog, "fwd"),
+    for p, s in ((tr.G_train.prog, "pack"), (tr.G_eval.prog, "pack"), (tr.D_train.prog, "pack"),
+                 (tr.G_eval.prog, "fwd"), (tr.D_train.prog, "fwd"),
                  (tr.d_loss_prog, "loss"), (tr.D_train.prog, "bwd"), (tr.d_loss_prog, "opt")):
         emul(p, s)
 

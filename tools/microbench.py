@@ -27,7 +27,7 @@ progs = [("G_train", tr.G_train.prog), ("D_eval", tr.D_eval.prog), ("g_loss", tr
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 from b2h_b200 import _lib as L  # noqa: E402
 by_kind = {}
-STEP_SEGS = {"G_train": ("pack", "fwd", "bwd"), "D_eval": ("fwd",), "g_loss": ("loss", "opt"), "G_eval": ("pack", "fwd"),
+STEP_SEGS = {"G_train": ("pack", "fwd", "bwd"), "D_eval": ("pack", "fwd"), "g_loss": ("loss", "opt"), "G_eval": ("pack", "fwd"),
              "D_train": ("pack", "fwd", "bwd"), "d_loss": ("loss", "opt")}
 for pname, prog in progs:
     for i, rec in enumerate(prog.recs):

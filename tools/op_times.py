@@ -39,8 +39,8 @@ e1.record()
 e1.synchronize()
 g_ms = e0.elapsed_time(e1) / 20
 rows = []
-seq = [("G_train", tr.G_train.prog, ("pack", "fwd", "bwd")), ("D_eval", tr.D_eval.prog, ("fwd",)),
-       ("g_loss", tr.g_loss_prog, ("loss", "opt")), ("G_eval", tr.G_eval.prog, ("fwd",)),
+seq = [("G_train", tr.G_train.prog, ("pack", "fwd", "bwd")), ("D_eval", tr.D_eval.prog, ("pack", "fwd")),
+       ("g_loss", tr.g_loss_prog, ("loss", "opt")), ("G_eval", tr.G_eval.prog, ("pack", "fwd")),
        ("D_train", tr.D_train.prog, ("pack", "fwd", "bwd")), ("d_loss", tr.d_loss_prog, ("loss", "opt"))]
 for pname, prog, segs in seq:
     for seg in segs:
