@@ -72,6 +72,29 @@ typedef struct {
                             ([rows][C]) so that the backward replays them in MASK mode */
 } b2h_dropout_t;
 
+/* train-mode BatchNorm1d statistics (declared here because a GEMM can produce them in its epilogue) */
+/* batch statistics of z over (rows of one group): mean, biased var -> invstd, and the folded affine
+ * scale = gamma*invstd, shift = beta - mean*scale; running update
+ * running = (1-m)*running + m*batch (unbiased var), num_batches_tracked += 1. */
+typedef struct {
+  const void* z;
+  int32_t ld, C, rows_per_group, groups;
+  int32_t Cs;    /* stride of the [groups][Cs] outputs */
+  float* mean;
+  float* invstd;
+  float* scale;
+  float* shift;
+  const float* gamma; /* [C] */
+  const float* beta;  /* [C] */
+  float* running_mean; /* may be NULL (no update) */
+  float* running_var;
+  int64_t* num_batches_tracked;
+  float momentum, eps;
+  float* partial;        /* workspace >= b2h_bn_partial_floats() */
+  uint32_t* ticket;      /* workspace, zero-initialised, self-resetting */
+  int32_t update_all_groups; /* 1: apply the running update once per group in order (two D forwards) */
+} b2h_bn_stats_t;
+
 /* ------------------------------------------------------------------------------------------- */
 /* tap-GEMM: every contraction of the path (Conv1d, its dgrad, ConvTranspose1d as a 2-phase     */
 /* sub-pixel conv, its dgrad as a strided conv, Linear) is                                       */
@@ -99,6 +122,9 @@ typedef struct {
   int32_t out_f32;
   b2h_dropout_t drop; /* dgrad: multiply by keep*2 of the dropout site that produced A_prev    */
   int32_t drop_C;     /* valid channel count of that site (mask row length)                    */
+  b2h_bn_stats_t stats; /* optional (stats.z != NULL, must equal `out`): also compute the train-mode BatchNorm
+                           statistics of the output, exactly as b2h_bn_stats(&stats) right after this op would
+                           (on the tensor-core path inside the GEMM epilogue, without re-reading `out`) */
 } b2h_gemm_t;
 
 /* wgrad: dW[m][n][t] = sum_{b,r} P[b, r, m] * Q[b, r*stride + tap_off[t], n]   (PyTorch weight layout)
@@ -128,28 +154,6 @@ typedef struct {
   const float* mean;    /* [groups][Cs]  batch mean          (backward only)                        */
   const float* invstd;  /* [groups][Cs]  1/sqrt(var_b + eps) (backward only)                        */
 } b2h_bn_src_t;
-
-/* batch statistics of z over (rows of one group): mean, biased var -> invstd, and the folded affine
- * scale = gamma*invstd, shift = beta - mean*scale; running update
- * running = (1-m)*running + m*batch (unbiased var), num_batches_tracked += 1. */
-typedef struct {
-  const void* z;
-  int32_t ld, C, rows_per_group, groups;
-  int32_t Cs;    /* stride of the [groups][Cs] outputs */
-  float* mean;
-  float* invstd;
-  float* scale;
-  float* shift;
-  const float* gamma; /* [C] */
-  const float* beta;  /* [C] */
-  float* running_mean; /* may be NULL (no update) */
-  float* running_var;
-  int64_t* num_batches_tracked;
-  float momentum, eps;
-  float* partial;        /* workspace >= b2h_bn_partial_floats() */
-  uint32_t* ticket;      /* workspace, zero-initialised, self-resetting */
-  int32_t update_all_groups; /* 1: apply the running update once per group in order (two D forwards) */
-} b2h_bn_stats_t;
 
 /* out[b,l,coff+c] = dropout( BN0(src0) [+ BN1(src1)] ), zero fill up to Cfill */
 typedef struct {

@@ -24,12 +24,20 @@ class Dropout(C.Structure):
     _fields_ = [("mode", i32), ("site", i32), ("mask", vp), ("state", vp), ("save", vp)]
 
 
+class BnStats(C.Structure):
+    _fields_ = [("z", vp), ("ld", i32), ("C", i32), ("rows_per_group", i32), ("groups", i32), ("Cs", i32),
+                ("mean", vp), ("invstd", vp), ("scale", vp), ("shift", vp), ("gamma", vp), ("beta", vp),
+                ("running_mean", vp), ("running_var", vp), ("num_batches_tracked", vp),
+                ("momentum", f32), ("eps", f32), ("partial", vp), ("ticket", vp), ("update_all_groups", i32)]
+
+
 class Gemm(C.Structure):
     _fields_ = [("A", vp), ("W", vp), ("bias", vp), ("out", vp),
                 ("B", i32), ("La", i32), ("Lo", i32), ("lda", i32), ("ldo", i32), ("out_coff", i32),
                 ("Kc", i32), ("Npad", i32), ("Nvalid", i32), ("ntaps", i32), ("stride", i32),
                 ("tap_off", i32 * MAX_TAPS), ("nphase", i32), ("Lo_actual", i32), ("act", i32),
-                ("post_scale", vp), ("post_shift", vp), ("out_f32", i32), ("drop", Dropout), ("drop_C", i32)]
+                ("post_scale", vp), ("post_shift", vp), ("out_f32", i32), ("drop", Dropout), ("drop_C", i32),
+                ("stats", BnStats)]
 
 
 class Wgrad(C.Structure):
@@ -42,13 +50,6 @@ class Wgrad(C.Structure):
 class BnSrc(C.Structure):
     _fields_ = [("z", vp), ("ld", i32), ("coff", i32), ("rowmap", i32), ("L_src", i32), ("Cs", i32),
                 ("scale", vp), ("shift", vp), ("mean", vp), ("invstd", vp)]
-
-
-class BnStats(C.Structure):
-    _fields_ = [("z", vp), ("ld", i32), ("C", i32), ("rows_per_group", i32), ("groups", i32), ("Cs", i32),
-                ("mean", vp), ("invstd", vp), ("scale", vp), ("shift", vp), ("gamma", vp), ("beta", vp),
-                ("running_mean", vp), ("running_var", vp), ("num_batches_tracked", vp),
-                ("momentum", f32), ("eps", f32), ("partial", vp), ("ticket", vp), ("update_all_groups", i32)]
 
 
 class BnApply(C.Structure):

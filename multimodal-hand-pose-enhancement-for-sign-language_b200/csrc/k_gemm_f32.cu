@@ -122,6 +122,10 @@ int launch_gemm_f32(const b2h_gemm_t& d, cudaStream_t s) {
   dim3 grid(ceil_div(d.B * d.Lo, F_BM), d.Npad / F_BN);
   launch(gemm_f32_kernel, grid, 256, 0, s, d, make_epi(d));
   B2H_LAUNCH_CHECK("gemm_f32");
+  if (d.stats.z) {   // fp32 path: the statistics of the output are a separate pass
+    B2H_CHECK_ARG(d.stats.z == d.out && d.out_coff == 0, B2H_ERR_ARG, "gemm: stats must describe the output tensor");
+    return launch_bn_stats(d.stats, B2H_F32, s);
+  }
   return B2H_OK;
 }
 
@@ -186,21 +190,38 @@ __global__ void __launch_bounds__(256) wgrad_simt_kernel(b2h_wgrad_t d, int spli
   }
 }
 
-// dW[m][n][t] = sum_split partial[split][t][m][n]   (fixed order -> deterministic)
+// dW[m][n][t] = sum_split partial[split][t][m][n]   (fixed order -> deterministic).
+// A warp owns 32 consecutive n of one (t, m): lane = (split group sg = lane / 8, float4 column c8 = lane % 8);
+// each lane sums the splits sg, sg+4, ... with independent float4 loads, two shuffles combine the 4 groups.
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(b2h_wgrad_t d, int splits) {
   pdl_sync();
-  const int64_t total = (int64_t)d.ntaps * d.Mvalid * d.Nvalid;
+  const int lane = threadIdx.x & 31, sg = lane >> 3, c8 = lane & 7;
+  const int n32s = (d.Nvalid + 31) >> 5;
+  const int total = d.ntaps * d.Mvalid * n32s;
   const int64_t plane = (int64_t)d.Mpad * d.Npad;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    int n = (int)(idx % d.Nvalid);
-    int64_t r = idx / d.Nvalid;
-    int m = (int)(r % d.Mvalid);
-    int t = (int)(r / d.Mvalid);
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < total; w += warps) {
+    const int nb = w % n32s;
+    int r = w / n32s;
+    const int m = r % d.Mvalid, t = r / d.Mvalid;
+    const int n = nb * 32 + c8 * 4;   // < Npad (a multiple of 64): the loads stay inside the plane
     const float* p = d.partial + (int64_t)t * plane + (int64_t)m * d.Npad + n;
-    float acc = 0.f;
-    for (int sp = 0; sp < splits; ++sp) acc += p[(int64_t)sp * d.ntaps * plane];
-    d.dW[((int64_t)m * d.Nvalid + n) * d.ntaps + t] = acc;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+    for (int sp = sg; sp < splits; sp += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(p + (int64_t)sp * d.ntaps * plane);
+      acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+    }
+#pragma unroll
+    for (int off = 8; off < 32; off <<= 1) {
+      acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);
+      acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
+      acc.z += __shfl_xor_sync(0xffffffffu, acc.z, off);
+      acc.w += __shfl_xor_sync(0xffffffffu, acc.w, off);
+    }
+    // lane (sg, c8) writes column n + sg
+    const float v = sg == 0 ? acc.x : sg == 1 ? acc.y : sg == 2 ? acc.z : acc.w;
+    if (n + sg < d.Nvalid) d.dW[((int64_t)m * d.Nvalid + n + sg) * d.ntaps + t] = v;
   }
 }
 
@@ -214,6 +235,7 @@ static int check_wgrad(const b2h_wgrad_t& d) {
                 "wgrad: ldp=%d ldq=%d", d.ldp, d.ldq);
   B2H_CHECK_ARG(d.stride == 1 || d.stride == 2, B2H_ERR_SHAPE, "wgrad: stride must be 1 or 2");
   B2H_CHECK_ARG(d.partial && d.dW, B2H_ERR_ARG, "wgrad: null output/workspace");
+  B2H_CHECK_ARG(((uintptr_t)d.partial % 16) == 0, B2H_ERR_ALIGN, "wgrad: workspace must be 16-byte aligned");
   return B2H_OK;
 }
 
@@ -232,8 +254,8 @@ int wgrad_choose_splits(const b2h_wgrad_t& d, int dtype) {
 
 int launch_wgrad_reduce(const b2h_wgrad_t& d, int splits, cudaStream_t s) {
   B2H_CARVE(wgrad_reduce_kernel);
-  int64_t total = (int64_t)d.ntaps * d.Mvalid * d.Nvalid;
-  int blocks = (int)std::min<int64_t>(ceil_div64(total, 256), (int64_t)sm_count() * 8);
+  int64_t total_warps = (int64_t)d.ntaps * d.Mvalid * ((d.Nvalid + 31) / 32);
+  int blocks = (int)std::min<int64_t>(ceil_div64(total_warps, 8), (int64_t)sm_count() * 8);
   launch(wgrad_reduce_kernel, blocks, 256, 0, s, d, splits);
   B2H_LAUNCH_CHECK("wgrad_reduce");
   return B2H_OK;

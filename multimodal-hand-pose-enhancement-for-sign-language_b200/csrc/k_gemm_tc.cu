@@ -11,6 +11,7 @@
 
 #include "gemm_epilogue.cuh"
 #include "ptx_sm100.cuh"
+#include "bn_finalize.cuh"
 #include "tc_plans.h"
 
 namespace b2h {
@@ -37,7 +38,7 @@ struct FpropCfg {
   static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
   static constexpr int EPI_BYTES = 128 * EPI_PITCH_MAX;
   static constexpr int MAIN_BYTES = PIPE_BYTES > EPI_BYTES ? PIPE_BYTES : EPI_BYTES;
-  static constexpr int SMEM_BYTES = MAIN_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + BN * 4 /*bias*/;
+  static constexpr int SMEM_BYTES = MAIN_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 2 * BN * 4 /*bias, pivot*/;
 };
 
 constexpr int TC_THREADS = 64 + 256;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (2 per TMEM sub-partition)
@@ -98,10 +99,12 @@ __device__ __forceinline__ void epi_finish8(const EpiParams& e, const DropCtx& d
   }
 }
 
-template <int BN, int KIND>
+// STATS: the epilogue also produces the train-mode BatchNorm statistics of the tile it stores (per-column
+// shifted sums of the bf16-rounded outputs -> fp64 atomics -> the last CTA finalises), see bn_finalize.cuh.
+template <int BN, int KIND, bool STATS>
 __global__ void __launch_bounds__(TC_THREADS, FpropCfg<BN>::OCC)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-               const __grid_constant__ CUtensorMap tmB, TcGemmParams p, EpiParams e) {
+               const __grid_constant__ CUtensorMap tmB, TcGemmParams p, EpiParams e, b2h_bn_stats_t st) {
   using Cfg = FpropCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -111,6 +114,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
   float* s_bias = reinterpret_cast<float*>(smem + Cfg::MAIN_BYTES + 256);
+  float* s_piv = s_bias + BN;
+  int* s_flag = reinterpret_cast<int*>(tmem_ptr + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mt = blockIdx.x, nt = blockIdx.y;
@@ -191,7 +196,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     uint8_t* stage = smem + (size_t)sub * 32 * pitch;
     const int et = threadIdx.x - 64;      // 0..255
     if (KIND == EPI_BIAS_LEAKY || KIND == EPI_BIAS_RELU || KIND == EPI_BIAS_F32) {
-      for (int i = et; i < BN; i += 256) s_bias[i] = e.bias[nn0 + i];
+      for (int i = et; i < BN; i += 256) {
+        s_bias[i] = e.bias[nn0 + i];
+        if (STATS) s_piv[i] = (st.running_mean && nn0 + i < st.C) ? st.running_mean[nn0 + i] : 0.f;
+      }
       asm volatile("bar.sync 1, 256;" ::: "memory");
     }
     DropCtx drop;
@@ -251,6 +259,78 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
     // both warps of this sub-partition have written their column halves
     asm volatile("bar.sync %0, 64;" ::"r"(2 + sub) : "memory");
+    if (STATS) {
+      // lane <-> fixed 16-byte column chunk; the lanes left over take further rows of the same iteration
+      constexpr int CHUNKS = BN / 8;
+      constexpr int LPR = CHUNKS < 32 ? CHUNKS : 32;
+      constexpr int RPI = 32 / LPR;
+      const int ch = lane % LPR, rsub = lane / LPR;
+      const bool ch_ok = ch * 8 < valid_cols;   // Nvalid % 8 == 0 (planner)
+      float piv[8], a1[8], a2[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) piv[i] = s_piv[ch * 8 + i], a1[i] = 0.f, a2[i] = 0.f;
+      if (ch_ok) {
+#pragma unroll 1
+        for (int rr = chalf * 16 + rsub; rr < chalf * 16 + 16; rr += RPI) {
+          const int r = sub * 32 + rr;
+          const int bi = r >> p.tl_log2, li = r & (p.tl - 1);
+          const int b = b0 + bi, lo = l0 + li;
+          const int ris = lo * e.nphase + ph;
+          if (b >= p.B || lo >= p.Lo || ris >= e.Lo_actual) continue;
+          const int64_t grow = (int64_t)b * e.Lo_actual + ris;
+          uint8_t* gdst = reinterpret_cast<uint8_t*>(e.out) + ((size_t)grow * e.ldo + e.out_coff + nn0) * 2;
+          const uint4 u = *reinterpret_cast<const uint4*>(stage + (size_t)rr * pitch + ch * 16);
+          *reinterpret_cast<uint4*>(gdst + ch * 16) = u;
+          const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+            const float d0 = f.x - piv[2 * i], d1 = f.y - piv[2 * i + 1];
+            a1[2 * i] += d0, a1[2 * i + 1] += d1;
+            a2[2 * i] = fmaf(d0, d0, a2[2 * i]), a2[2 * i + 1] = fmaf(d1, d1, a2[2 * i + 1]);
+          }
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int off = LPR; off < 32; off <<= 1) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          a1[i] += __shfl_xor_sync(0xffffffffu, a1[i], off);
+          a2[i] += __shfl_xor_sync(0xffffffffu, a2[i], off);
+        }
+      }
+      // per-warp partials -> fixed-order sum over the 8 epilogue warps -> fp64 atomics
+      float2* s_part = reinterpret_cast<float2*>(smem + (size_t)128 * pitch);   // [8][BN], pipeline buffers are idle
+      if (rsub == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s_part[(warp - 2) * BN + ch * 8 + i] = make_float2(a1[i], a2[i]);
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const int grp = b0 / (p.B / st.groups);
+      for (int c = et; c < valid_cols; c += 256) {
+        float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+        for (int w8 = 0; w8 < 8; ++w8) {
+          const float2 v = s_part[w8 * BN + c];
+          t1 += v.x, t2 += v.y;
+        }
+        bn_stats_accumulate(st, blockIdx.x % kCopies, grp, nn0 + c, t1, t2);
+      }
+      __threadfence();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (et == 0) {
+        const uint32_t t = atomicAdd(st.ticket, 1u);
+        const int last = (t == gridDim.x * gridDim.y - 1u);
+        if (last) *st.ticket = 0u;
+        *s_flag = last;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (*s_flag) {
+        __threadfence();
+        bn_stats_finalize(st, et, 256);
+      }
+    } else
     if (valid_cols > 0) {
       const int row_bytes = valid_cols * esz;
       const int full16 = row_bytes >> 4;  // 16-byte chunks that are entirely valid
@@ -549,6 +629,8 @@ static int make_row_views(CUtensorMap* m0, CUtensorMap* m1, bool* has1, const vo
   return B2H_OK;
 }
 
+static int epi_kind(const b2h_gemm_t& d);
+
 int plan_gemm_bf16(const b2h_gemm_t& d, TcGemmPlan* plan) {
   TcGemmParams& p = plan->p;
   p.B = d.B;
@@ -602,7 +684,19 @@ int plan_gemm_bf16(const b2h_gemm_t& d, TcGemmPlan* plan) {
   plan->grid_x = m_tiles;
   plan->grid_y = d.Npad / best_bn;
   rc = make_map_2d(&plan->tmB, d.W, (int64_t)d.ntaps * d.Kc, d.Npad, (int64_t)d.ntaps * d.Kc, 64, best_bn);
-  return rc;
+  if (rc) return rc;
+  plan->fuse_stats = 0;
+  if (d.stats.z) {
+    const b2h_bn_stats_t& st = d.stats;
+    B2H_CHECK_ARG(st.z == d.out && d.out_coff == 0 && st.ld == d.ldo && st.C == d.Nvalid && st.groups >= 1 &&
+                      d.B % st.groups == 0 && st.rows_per_group == (d.B / st.groups) * d.Lo_actual,
+                  B2H_ERR_ARG, "gemm: stats must describe the output tensor of the op");
+    const int kind = epi_kind(d);
+    plan->fuse_stats = (kind == EPI_BIAS_LEAKY || kind == EPI_BIAS_RELU) && d.Nvalid % 8 == 0 &&
+                       (d.B / st.groups) % p.tb == 0 && st.partial && ((uintptr_t)st.partial % 16) == 0 &&
+                       st.ticket && st.Cs >= st.C && !getenv("B2H_NO_FUSED_STATS");
+  }
+  return B2H_OK;
 }
 
 static int epi_kind(const b2h_gemm_t& d) {
@@ -619,25 +713,32 @@ static int epi_kind(const b2h_gemm_t& d) {
   return EPI_GENERIC;
 }
 
-template <int BN, int KIND>
-static int launch_fprop(const TcGemmPlan& plan, const EpiParams& e, cudaStream_t s) {
+template <int BN, int KIND, bool STATS = false>
+static int launch_fprop(const TcGemmPlan& plan, const EpiParams& e, cudaStream_t s,
+                        const b2h_bn_stats_t& st = b2h_bn_stats_t()) {
   using Cfg = FpropCfg<BN>;
-  B2H_CARVE(gemm_tc_kernel<BN, KIND>);
+  B2H_CARVE(gemm_tc_kernel<BN, KIND, STATS>);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t er = cudaFuncSetAttribute(gemm_tc_kernel<BN, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t er = cudaFuncSetAttribute(gemm_tc_kernel<BN, KIND, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           Cfg::SMEM_BYTES);
     if (er != cudaSuccess) return cuda_fail(er, "gemm_tc smem attribute");
     attr_set = true;
   }
   dim3 grid(plan.grid_x, plan.grid_y);
-  launch(gemm_tc_kernel<BN, KIND>, grid, TC_THREADS, Cfg::SMEM_BYTES, s, plan.tmA0, plan.tmA1, plan.tmB, plan.p, e);
+  launch(gemm_tc_kernel<BN, KIND, STATS>, grid, TC_THREADS, Cfg::SMEM_BYTES, s, plan.tmA0, plan.tmA1, plan.tmB, plan.p, e,
+         st);
   B2H_LAUNCH_CHECK("gemm_tc");
   return B2H_OK;
 }
 
 template <int BN>
-static int launch_fprop_kind(const TcGemmPlan& plan, const EpiParams& e, int kind, cudaStream_t s) {
+static int launch_fprop_kind(const TcGemmPlan& plan, const EpiParams& e, int kind, cudaStream_t s,
+                             const b2h_bn_stats_t& st) {
+  if (plan.fuse_stats) {
+    if (kind == EPI_BIAS_LEAKY) return launch_fprop<BN, EPI_BIAS_LEAKY, true>(plan, e, s, st);
+    return launch_fprop<BN, EPI_BIAS_RELU, true>(plan, e, s, st);
+  }
   switch (kind) {
     case EPI_BIAS_LEAKY: return launch_fprop<BN, EPI_BIAS_LEAKY>(plan, e, s);
     case EPI_BIAS_RELU: return launch_fprop<BN, EPI_BIAS_RELU>(plan, e, s);
@@ -651,11 +752,14 @@ static int launch_fprop_kind(const TcGemmPlan& plan, const EpiParams& e, int kin
 int run_gemm_bf16(const TcGemmPlan& plan, const b2h_gemm_t& d, cudaStream_t s) {
   EpiParams e = make_epi(d);
   const int kind = epi_kind(d);
+  int rc;
   switch (plan.BN) {
-    case 256: return launch_fprop_kind<256>(plan, e, kind, s);
-    case 128: return launch_fprop_kind<128>(plan, e, kind, s);
-    default: return launch_fprop_kind<64>(plan, e, kind, s);
+    case 256: rc = launch_fprop_kind<256>(plan, e, kind, s, d.stats); break;
+    case 128: rc = launch_fprop_kind<128>(plan, e, kind, s, d.stats); break;
+    default: rc = launch_fprop_kind<64>(plan, e, kind, s, d.stats); break;
   }
+  if (rc || !d.stats.z || plan.fuse_stats) return rc;
+  return launch_bn_stats(d.stats, B2H_BF16, s);   // shapes the epilogue cannot cover: separate pass
 }
 
 int plan_wgrad_bf16(const b2h_wgrad_t& d, TcWgradPlan* plan) {

@@ -15,7 +15,7 @@
 // and out-of-line Philox.
 #include <algorithm>
 
-#include "b2h_common.cuh"
+#include "bn_finalize.cuh"
 
 namespace b2h {
 
@@ -64,7 +64,6 @@ __device__ __forceinline__ void block_sum8(float4* sm, F8& v, int tx, int ty, in
   v.v[0] = lo.x, v.v[1] = lo.y, v.v[2] = lo.z, v.v[3] = lo.w, v.v[4] = hi.x, v.v[5] = hi.y, v.v[6] = hi.z, v.v[7] = hi.w;
 }
 constexpr int kRPT = 4;   // rows per thread of the reduction kernels (all loads issued before use)
-constexpr int kCopies = 16;  // accumulator copies: CTA i adds into copy i % 16 (same-address atomics serialise in L2)
 
 template <typename T>
 __global__ void __launch_bounds__(kRowThreads) bn_stats_kernel(b2h_bn_stats_t d, int ctas_per_group) {
@@ -104,49 +103,12 @@ __global__ void __launch_bounds__(kRowThreads) bn_stats_kernel(b2h_bn_stats_t d,
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       if (c0 + i < d.C) {
-        double* a = accum + (((int64_t)(blockIdx.x % kCopies) * d.groups + g) * d.C + c0 + i) * 2;
-        atomicAdd(a + 0, (double)s1.v[i]);
-        atomicAdd(a + 1, (double)s2.v[i]);
+        bn_stats_accumulate(d, blockIdx.x % kCopies, g, c0 + i, s1.v[i], s2.v[i]);
       }
     }
   }
   if (!last_block_done(d.ticket, gridDim.x * gridDim.y)) return;
-  const int tid = ty * TXp + tx;
-#pragma unroll 1
-  for (int c = tid; c < d.C; c += kRowThreads) {
-    const double p = d.running_mean ? (double)d.running_mean[c] : 0.0;
-#pragma unroll 1
-    for (int gg = 0; gg < d.groups; ++gg) {
-      double t0 = 0.0, t1 = 0.0;
-#pragma unroll
-      for (int k = 0; k < kCopies; ++k) {   // fixed order over the copies
-        double2* acc = reinterpret_cast<double2*>(accum + (((int64_t)k * d.groups + gg) * d.C + c) * 2);
-        const double2 v = __ldcg(acc);
-        *acc = make_double2(0.0, 0.0);
-        t0 += v.x;
-        t1 += v.y;
-      }
-      const double dm = t0 / (double)rpg;      // mean - pivot
-      const double mean = p + dm;
-      double m2 = t1 - t0 * dm;
-      if (m2 < 0.0) m2 = 0.0;
-      const double var_b = m2 / (double)rpg;
-      const float invstd = (float)(1.0 / sqrt(var_b + (double)d.eps));
-      const float scale = invstd * (d.gamma ? d.gamma[c] : 1.f);
-      d.mean[gg * d.Cs + c] = (float)mean;
-      d.invstd[gg * d.Cs + c] = invstd;
-      d.scale[gg * d.Cs + c] = scale;
-      d.shift[gg * d.Cs + c] = (d.beta ? d.beta[c] : 0.f) - (float)mean * scale;
-      if (d.running_mean && (gg == 0 || d.update_all_groups)) {
-        const double var_u = rpg > 1 ? m2 / (double)(rpg - 1) : var_b;
-        const float mom = d.momentum;
-        d.running_mean[c] = (1.f - mom) * d.running_mean[c] + mom * (float)mean;
-        d.running_var[c] = (1.f - mom) * d.running_var[c] + mom * (float)var_u;
-      }
-    }
-  }
-  if (tid == 0 && d.running_mean && d.num_batches_tracked)
-    *d.num_batches_tracked += d.update_all_groups ? d.groups : 1;
+  bn_stats_finalize(d, ty * TXp + tx, kRowThreads);
 }
 
 int64_t bn_partial_floats(int rows, int C, int groups) {

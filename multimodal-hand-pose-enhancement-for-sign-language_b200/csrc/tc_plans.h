@@ -22,6 +22,7 @@ struct alignas(64) TcGemmPlan {
   CUtensorMap tmA0, tmA1, tmB;
   TcGemmParams p;
   int BN, grid_x, grid_y;
+  int fuse_stats;  // BatchNorm statistics of the output produced by the epilogue
 };
 
 struct TcWgradParams {

@@ -504,8 +504,6 @@ class NetPlan:
             for l in spec.layers:
                 self._emit_input(l)
                 self._emit_fwd_gemm(l)
-                if l.bn and self.train:
-                    self._emit_bn_stats(l)
             if spec.input_kind == "x":
                 P.add(L.OP_TO_NCL, "out", src=self.out_blc, dst=self.out, B=B, L=olb.Lz, C=ol.cout,
                       ld=self.out_blc.shape[-1], src_f32=1)
@@ -520,7 +518,10 @@ class NetPlan:
         self.partial = self._zeros(self._partial_need, dtype=torch.float32)
         self.wg_partial = self._zeros(self._wg_need // 4 + 4, dtype=torch.float32)
         for i, fld in self._pending_partial:
-            self.prog.recs[i].f[fld] = self.wg_partial if self.prog.recs[i].kind == L.OP_WGRAD else self.partial
+            f = self.prog.recs[i].f
+            if isinstance(fld, tuple):   # nested descriptor, e.g. the statistics of a GEMM output
+                f, fld = f[fld[0]], fld[1]
+            f[fld] = self.wg_partial if self.prog.recs[i].kind == L.OP_WGRAD else self.partial
 
     def _need_partial(self, idx: int, floats: int, fld: str = "partial"):
         self._partial_need = max(self._partial_need, int(floats))
@@ -680,12 +681,17 @@ class NetPlan:
         common = dict(A=lb.a, W=lb.wf, bias=lb.bias, out=out, B=B, La=l.La, lda=lb.Kc, ldo=ldo, out_coff=0, Kc=lb.Kc,
                       Nvalid=l.cout, ntaps=len(taps), tap_off=taps + [0] * (L.MAX_TAPS - len(taps)), act=l.act,
                       post_scale=None, post_shift=None, out_f32=1 if is_out else 0, drop=no_drop(), drop_C=0)
+        if l.bn and self.train:
+            # the GEMM also produces the batch statistics of its output (tensor-core path: in the epilogue)
+            common["stats"] = self._bn_stats_desc(l)
         if l.kind == "convT":
             i = P.add(L.OP_GEMM, f"gemm.{l.name}", Lo=l.La, Npad=2 * lb.Cp, stride=1, nphase=2, Lo_actual=2 * l.La,
                       **common)
         else:
             i = P.add(L.OP_GEMM, f"gemm.{l.name}", Lo=l.Lo, Npad=lb.Cp, stride=l.stride, nphase=1, Lo_actual=l.Lo,
                       **common)
+        if l.bn and self.train:
+            self._need_partial(i, _bn_partial_floats(B * lb.Lz, l.cout, self.groups), fld=("stats", "partial"))
         self.op_macs[i] = self._layer_macs(l)
 
     def _layer_macs(self, l: Layer) -> int:
@@ -693,17 +699,16 @@ class NetPlan:
         rows = self.B * (l.La if l.kind == "convT" else l.Lo)
         return rows * l.cin * l.cout * l.k
 
-    def _emit_bn_stats(self, l: Layer):
-        P, st, lb = self.prog, self.store, self.bufs[l.name]
+    def _bn_stats_desc(self, l: Layer) -> dict:
+        st, lb = self.store, self.bufs[l.name]
         rows = self.B * lb.Lz
-        i = P.add(L.OP_BN_STATS, f"stats.{l.name}", z=lb.z, ld=lb.Cp, C=l.cout, rows_per_group=rows // self.groups,
-                  groups=self.groups, Cs=lb.Cp, mean=lb.mean, invstd=lb.invstd, scale=lb.scale, shift=lb.shift,
-                  gamma=st.p(l.bnkey + ".weight"), beta=st.p(l.bnkey + ".bias"),
-                  running_mean=st.b(l.bnkey + ".running_mean"),
-                  running_var=st.b(l.bnkey + ".running_var"),
-                  num_batches_tracked=st.nbt_view(l.bnkey + ".num_batches_tracked"), momentum=l.momentum, eps=BN_EPS,
-                  partial=None, ticket=self._ticket(), update_all_groups=1 if self.groups > 1 else 0)
-        self._need_partial(i, _bn_partial_floats(rows, l.cout, self.groups))
+        return dict(z=lb.z, ld=lb.Cp, C=l.cout, rows_per_group=rows // self.groups,
+                    groups=self.groups, Cs=lb.Cp, mean=lb.mean, invstd=lb.invstd, scale=lb.scale, shift=lb.shift,
+                    gamma=st.p(l.bnkey + ".weight"), beta=st.p(l.bnkey + ".bias"),
+                    running_mean=st.b(l.bnkey + ".running_mean"),
+                    running_var=st.b(l.bnkey + ".running_var"),
+                    num_batches_tracked=st.nbt_view(l.bnkey + ".num_batches_tracked"), momentum=l.momentum,
+                    eps=BN_EPS, partial=None, ticket=self._ticket(), update_all_groups=1 if self.groups > 1 else 0)
 
     # ---- backward ----------------------------------------------------------------------------
     def _emit_bwd(self, l: Layer):

@@ -98,6 +98,9 @@ def gemm(f: Dict):
             v = v.clone()
             v[:, :, :nn] = v[:, :, :nn] * m[:, :, :nn]
         out2[:, ra, f["out_coff"]: f["out_coff"] + Nv] = v.to(out.dtype)
+    st = f.get("stats")
+    if st and st.get("z") is not None:   # the op also produces the batch statistics of its output
+        bn_stats(st)
 
 
 def wgrad(f: Dict):

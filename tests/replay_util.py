@@ -59,8 +59,11 @@ def replay_pair(prog_gpu, prog_cpu, segments, teacher_force=True):
             prog_gpu.run_range(i, i + 1)
             torch.cuda.synchronize()
             E.DISPATCH[rc.kind](rc.f)
-            for fld in OUT_FIELDS[rc.kind]:
-                vc, vg = rc.f.get(fld), rg.f.get(fld)
+            fields = [(fld, rc.f, rg.f) for fld in OUT_FIELDS[rc.kind]]
+            if rc.kind == L.OP_GEMM and (rc.f.get("stats") or {}).get("z") is not None:
+                fields += [("stats." + fld, rc.f["stats"], rg.f["stats"]) for fld in OUT_FIELDS[L.OP_BN_STATS]]
+            for fld, fc, fg in fields:
+                vc, vg = fc.get(fld.split(".")[-1]), fg.get(fld.split(".")[-1])
                 if vc is None:
                     continue
                 got = vg.detach().to("cpu")

@@ -262,3 +262,41 @@ def test_missing_device_or_bad_args_fail_loudly():
     with pytest.raises(L.B2HError):
         nets.NetPlan(nets.discriminator_spec(252), nets.ParamStore(nets.discriminator_spec(252), "cpu"), 4, 16, L.F32,
                      "cpu", train=False).forward()
+
+
+def test_gemm_epilogue_statistics_equal_separate_pass(monkeypatch):
+    """bf16: the BatchNorm statistics produced in the tcgen05 GEMM epilogue equal those of the stand-alone
+    bn_stats pass over the same (bf16-rounded) output, for every BN layer of G (k3 / k5-stride-2 / convT tiles)
+    and of the grouped (fake | real) discriminator batch."""
+    torch.manual_seed(0)
+    B, T = 32, 64
+    res = []
+    for fused in (True, False):
+        if fused:
+            monkeypatch.delenv("B2H_NO_FUSED_STATS", raising=False)
+        else:
+            monkeypatch.setenv("B2H_NO_FUSED_STATS", "1")
+        out = {}
+        for name, spec, Bn, groups in (("G", nets.generator_spec("v1", 36, 252), B, 1),
+                                       ("D", nets.discriminator_spec(252), 2 * B, 2)):
+            store = nets.ParamStore(spec, "cuda", seed=3)
+            plan = nets.NetPlan(spec, store, Bn, T, L.BF16, "cuda", train=True, groups=groups, drop_mode="none")
+            g = torch.Generator().manual_seed(5)
+            if name == "G":
+                plan.x.copy_(torch.randn(Bn, 36, T, generator=g))
+            else:
+                for t in plan.motion_src:
+                    t.copy_(torch.randn(t.shape, generator=g))
+            plan.forward()
+            torch.cuda.synchronize()
+            out[name] = {l.name: (plan.bufs[l.name].mean.clone(), plan.bufs[l.name].invstd.clone(),
+                                  store.b(l.bnkey + ".running_var").clone()) for l in spec.layers if l.bn}
+            out[name + "_launches"] = plan.prog.segment_launches["fwd"]
+        res.append(out)
+    for name in ("G", "D"):
+        assert res[0][name + "_launches"] < res[1][name + "_launches"]   # the fused plan really fused
+        for lname, (m0, i0, v0) in res[0][name].items():
+            m1, i1, v1 = res[1][name][lname]
+            # (deep layers see bf16 rounding flips of their inputs: differences compound with depth;
+            # the per-layer comparison on identical inputs is test_gpu_replay.py)
+            assert rel_err(m0, m1) < 2e-3 and rel_err(i0, i1) < 2e-3 and rel_err(v0, v1) < 2e-3, (name, lname)
