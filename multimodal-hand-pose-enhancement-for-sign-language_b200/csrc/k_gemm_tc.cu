@@ -265,7 +265,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       constexpr int LPR = CHUNKS < 32 ? CHUNKS : 32;
       constexpr int RPI = 32 / LPR;
       const int ch = lane % LPR, rsub = lane / LPR;
-      const bool ch_ok = ch * 8 < valid_cols;   // Nvalid % 8 == 0 (planner)
+      const bool ch_ok = ch * 8 < valid_cols;   // a ragged last chunk is stored whole (zeros in the padding)
       float piv[8], a1[8], a2[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) piv[i] = s_piv[ch * 8 + i], a1[i] = 0.f, a2[i] = 0.f;
@@ -692,7 +692,9 @@ int plan_gemm_bf16(const b2h_gemm_t& d, TcGemmPlan* plan) {
                       d.B % st.groups == 0 && st.rows_per_group == (d.B / st.groups) * d.Lo_actual,
                   B2H_ERR_ARG, "gemm: stats must describe the output tensor of the op");
     const int kind = epi_kind(d);
-    plan->fuse_stats = (kind == EPI_BIAS_LEAKY || kind == EPI_BIAS_RELU) && d.Nvalid % 8 == 0 &&
+    // (a ragged last 16-byte chunk is stored whole: the weight rows / bias beyond Nvalid are zero, so the
+    // pad columns of z receive zeros; its statistics cover the valid columns only)
+    plan->fuse_stats = (kind == EPI_BIAS_LEAKY || kind == EPI_BIAS_RELU) && d.ldo >= ((d.Nvalid + 7) & ~7) &&
                        (d.B / st.groups) % p.tb == 0 && st.partial && ((uintptr_t)st.partial % 16) == 0 &&
                        st.ticket && st.Cs >= st.C && !getenv("B2H_NO_FUSED_STATS");
   }

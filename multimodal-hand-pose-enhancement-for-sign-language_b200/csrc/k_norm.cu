@@ -297,6 +297,20 @@ __device__ __forceinline__ F8 load_g8(const b2h_grad_src_t& gs, int64_t row, int
   return load8<T>(reinterpret_cast<const T*>(gs.g) + row * gs.ld + gs.coff + c0);
 }
 
+// IDENT or regular UP2 (even consumer length == 2*L): the source row is a pure function of `row`
+template <typename T>
+__device__ __forceinline__ void add_grad_simple8(const b2h_grad_src_t& gs, int row, int c0, F8& dy) {
+  if (gs.rowmap == B2H_ROW_IDENT) {
+    const F8 g = load_g8<T>(gs, row, c0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dy.v[i] += g.v[i];
+  } else {
+    const F8 g0 = load_g8<T>(gs, 2 * (int64_t)row, c0), g1 = load_g8<T>(gs, 2 * (int64_t)row + 1, c0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dy.v[i] += g0.v[i] + g1.v[i];
+  }
+}
+
 // contribution of ONE gradient source to dy(row, c0..c0+7); zown = z(row); sc/sh = forward affine of this layer.
 // `reg`: the source row is a pure function of `row` (IDENT, or UP2 with an even consumer length == 2*L)
 template <typename T>
@@ -346,11 +360,20 @@ __device__ __forceinline__ void add_grad_src8(const b2h_bn_bwd_t& d, const b2h_g
   }
 }
 
-template <typename T, int PASS>
-__global__ void __launch_bounds__(kRowThreads) bn_bwd_kernel(b2h_bn_bwd_t d) {
+// Pass 1 only accumulates (fp64 atomics into kCopiesBwd1 copies, no ticket: its CTAs retire as soon as their
+// reds are issued).  Pass 2 starts by summing those copies for the channels of its CTA, writes dpre, accumulates
+// the bias gradient the same way, and its LAST CTA (ticket) writes dgamma / dbeta / dbias / sums and re-zeroes
+// both accumulator regions.  SIMPLE: every gradient source is IDENT or a regular UP2 (no per-row div / pooling
+// branches in the code).
+constexpr int kCopiesBwd1 = 8;
+
+template <typename T, int PASS, bool SIMPLE>
+__global__ void __launch_bounds__(kRowThreads, 2) bn_bwd_kernel(b2h_bn_bwd_t d) {
   pdl_sync();
   __shared__ float4 s_red[kRowThreads];
+  __shared__ float2 s_m[PASS == 2 ? 512 : 1];
   const int tx = threadIdx.x, ty = threadIdx.y, TXp = blockDim.x, TY = blockDim.y;
+  const int tid = ty * TXp + tx;
   const int g = blockIdx.y;
   const int c0 = tx * 8;
   const int rows = d.B * d.L;
@@ -358,7 +381,23 @@ __global__ void __launch_bounds__(kRowThreads) bn_bwd_kernel(b2h_bn_bwd_t d) {
   const int r0 = (blockIdx.x * TY + ty) * kRPT;   // within the group
   const T* z = reinterpret_cast<const T*>(d.bn.z) + d.bn.coff + c0;
   T* dpre = reinterpret_cast<T*>(d.dpre) + c0;
-  double* accum = reinterpret_cast<double*>(d.partial);   // [groups][C][2], zero between launches
+  // accumulators, zero between launches: region 1 [kCopiesBwd1][groups][C][2] (sum dy, sum dy*zhat),
+  // region 2 [kCopies][groups][C] (sum dpre)
+  double* accum1 = reinterpret_cast<double*>(d.partial);
+  double* accum2 = accum1 + (int64_t)kCopiesBwd1 * d.groups * d.C * 2;
+  if (PASS == 2) {
+    const double inv_n = 1.0 / (double)rpg;
+    for (int c = tid; c < d.C; c += kRowThreads) {
+      double a = 0.0, b = 0.0;
+#pragma unroll
+      for (int k = 0; k < kCopiesBwd1; ++k) {   // fixed order over the copies
+        const double2 v = __ldcg(reinterpret_cast<const double2*>(accum1 + (((int64_t)k * d.groups + g) * d.C + c) * 2));
+        a += v.x, b += v.y;
+      }
+      s_m[c] = make_float2((float)(a * inv_n), (float)(b * inv_n));
+    }
+    __syncthreads();
+  }
   F8 acc_a = zero8(), acc_b = zero8();
   if (c0 < d.Cfill && r0 < rpg) {
     const bool live = c0 < d.C;
@@ -376,13 +415,12 @@ __global__ void __launch_bounds__(kRowThreads) bn_bwd_kernel(b2h_bn_bwd_t d) {
       mean8 = ld8f(d.bn.mean + o);
       istd8 = ld8f(d.bn.invstd + o);
       if (PASS == 2) {
-        const float inv_n = 1.f / (float)rpg;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           if (c0 + i < d.C) {
-            const float2 sm = *reinterpret_cast<const float2*>(d.sums + ((int64_t)g * d.C + c0 + i) * 2);
-            mdy.v[i] = sm.x * inv_n;
-            mdyz.v[i] = sm.y * inv_n;
+            const float2 sm = s_m[c0 + i];
+            mdy.v[i] = sm.x;
+            mdyz.v[i] = sm.y;
           }
         }
       }
@@ -394,8 +432,13 @@ __global__ void __launch_bounds__(kRowThreads) bn_bwd_kernel(b2h_bn_bwd_t d) {
       if (r0 + u < rpg && live) {
         const int row = g * rpg + r0 + u;
         zo[u] = load8<T>(z + (int64_t)row * d.bn.ld);
-        add_grad_src8<T>(d, d.gsrc[0], reg0, sc, sh, zo[u], row, c0, dy[u]);
-        if (two) add_grad_src8<T>(d, d.gsrc[1], reg1, sc, sh, zo[u], row, c0, dy[u]);
+        if (SIMPLE) {
+          add_grad_simple8<T>(d.gsrc[0], row, c0, dy[u]);
+          if (two) add_grad_simple8<T>(d.gsrc[1], row, c0, dy[u]);
+        } else {
+          add_grad_src8<T>(d, d.gsrc[0], reg0, sc, sh, zo[u], row, c0, dy[u]);
+          if (two) add_grad_src8<T>(d, d.gsrc[1], reg1, sc, sh, zo[u], row, c0, dy[u]);
+        }
       }
     }
 #pragma unroll
@@ -426,49 +469,77 @@ __global__ void __launch_bounds__(kRowThreads) bn_bwd_kernel(b2h_bn_bwd_t d) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       if (c0 + i < d.C) {
-        double* a = accum + (((int64_t)(blockIdx.x % kCopies) * d.groups + g) * d.C + c0 + i) * 2;
-        atomicAdd(a + 0, (double)acc_a.v[i]);
-        if (PASS == 1) atomicAdd(a + 1, (double)acc_b.v[i]);
+        if (PASS == 1) {
+          double* a = accum1 + (((int64_t)(blockIdx.x % kCopiesBwd1) * d.groups + g) * d.C + c0 + i) * 2;
+          atomicAdd(a + 0, (double)acc_a.v[i]);
+          atomicAdd(a + 1, (double)acc_b.v[i]);
+        } else {
+          atomicAdd(accum2 + ((int64_t)(blockIdx.x % kCopies) * d.groups + g) * d.C + c0 + i, (double)acc_a.v[i]);
+        }
       }
     }
   }
+  if (PASS == 1) return;
   if (!last_block_done(d.ticket, gridDim.x * gridDim.y)) return;
-  const int tid = ty * TXp + tx;
 #pragma unroll 1
   for (int c = tid; c < d.C; c += kRowThreads) {
-    double tot_a = 0.0, tot_b = 0.0;
+    double tot_a = 0.0, tot_b = 0.0, tot_c = 0.0;
 #pragma unroll 1
     for (int gg = 0; gg < d.groups; ++gg) {
       double ta = 0.0, tb = 0.0;
 #pragma unroll
-      for (int k = 0; k < kCopies; ++k) {   // fixed order over the copies
-        double2* acc = reinterpret_cast<double2*>(accum + (((int64_t)k * d.groups + gg) * d.C + c) * 2);
+      for (int k = 0; k < kCopiesBwd1; ++k) {
+        double2* acc = reinterpret_cast<double2*>(accum1 + (((int64_t)k * d.groups + gg) * d.C + c) * 2);
         const double2 v = __ldcg(acc);
         *acc = make_double2(0.0, 0.0);
-        ta += v.x;
-        tb += v.y;
+        ta += v.x, tb += v.y;
       }
-      if (PASS == 1) {
+#pragma unroll
+      for (int k = 0; k < kCopies; ++k) {
+        double* acc = accum2 + ((int64_t)k * d.groups + gg) * d.C + c;
+        tot_c += __ldcg(acc);
+        *acc = 0.0;
+      }
+      if (d.sums) {
         d.sums[((int64_t)gg * d.C + c) * 2 + 0] = (float)ta;
         d.sums[((int64_t)gg * d.C + c) * 2 + 1] = (float)tb;
       }
-      tot_a += ta;
-      tot_b += tb;
+      tot_a += ta, tot_b += tb;
     }
-    if (PASS == 1) {
-      if (d.dbeta) d.dbeta[c] = (float)tot_a;
-      if (d.dgamma) d.dgamma[c] = (float)tot_b;
-    } else {
-      if (d.dbias) d.dbias[c] = (float)tot_a;
-    }
+    if (d.dbeta) d.dbeta[c] = (float)tot_a;
+    if (d.dgamma) d.dgamma[c] = (float)tot_b;
+    if (d.dbias) d.dbias[c] = (float)tot_c;
+  }
+}
+
+static bool grad_src_simple(const b2h_grad_src_t& gs, int L) {
+  return gs.rowmap == B2H_ROW_IDENT || (gs.rowmap == B2H_ROW_UP2 && (gs.L_src & 1) == 0 && gs.L_src == 2 * L);
+}
+
+template <typename T>
+static void launch_bn_bwd_t(const b2h_bn_bwd_t& d, dim3 grid, dim3 block, bool simple, int pass, cudaStream_t s) {
+  if (pass == 1) {
+    if (simple)
+      launch(bn_bwd_kernel<T, 1, true>, grid, block, 0, s, d);
+    else
+      launch(bn_bwd_kernel<T, 1, false>, grid, block, 0, s, d);
+  } else {
+    if (simple)
+      launch(bn_bwd_kernel<T, 2, true>, grid, block, 0, s, d);
+    else
+      launch(bn_bwd_kernel<T, 2, false>, grid, block, 0, s, d);
   }
 }
 
 int launch_bn_bwd(const b2h_bn_bwd_t& d, int dtype, cudaStream_t s) {
-  B2H_CARVE(bn_bwd_kernel<__nv_bfloat16, 1>);
-  B2H_CARVE(bn_bwd_kernel<__nv_bfloat16, 2>);
-  B2H_CARVE(bn_bwd_kernel<float, 1>);
-  B2H_CARVE(bn_bwd_kernel<float, 2>);
+  B2H_CARVE(bn_bwd_kernel<__nv_bfloat16, 1, true>);
+  B2H_CARVE(bn_bwd_kernel<__nv_bfloat16, 2, true>);
+  B2H_CARVE(bn_bwd_kernel<__nv_bfloat16, 1, false>);
+  B2H_CARVE(bn_bwd_kernel<__nv_bfloat16, 2, false>);
+  B2H_CARVE(bn_bwd_kernel<float, 1, true>);
+  B2H_CARVE(bn_bwd_kernel<float, 2, true>);
+  B2H_CARVE(bn_bwd_kernel<float, 1, false>);
+  B2H_CARVE(bn_bwd_kernel<float, 2, false>);
   B2H_CHECK_ARG(d.C > 0 && d.C <= 512 && d.Cfill >= d.C && d.Cfill <= 1024 && d.groups >= 1 && d.ngsrc >= 1 &&
                     d.ngsrc <= 2,
                 B2H_ERR_SHAPE, "bn_bwd: bad shape C=%d Cfill=%d ngsrc=%d", d.C, d.Cfill, d.ngsrc);
@@ -483,16 +554,14 @@ int launch_bn_bwd(const b2h_bn_bwd_t& d, int dtype, cudaStream_t s) {
   const int rpg = d.B * d.L / d.groups;
   RowGrid rg = row_grid(d.Cfill, rpg);
   dim3 grid(rg.ctas, d.groups), block(rg.txp, rg.ty);
-  if (dtype == B2H_BF16) {
-    launch(bn_bwd_kernel<__nv_bfloat16, 1>, grid, block, 0, s, d);
-    B2H_LAUNCH_CHECK("bn_bwd pass 1");
-    launch(bn_bwd_kernel<__nv_bfloat16, 2>, grid, block, 0, s, d);
-  } else {
-    launch(bn_bwd_kernel<float, 1>, grid, block, 0, s, d);
-    B2H_LAUNCH_CHECK("bn_bwd pass 1");
-    launch(bn_bwd_kernel<float, 2>, grid, block, 0, s, d);
+  bool simple = grad_src_simple(d.gsrc[0], d.L) && (d.ngsrc < 2 || grad_src_simple(d.gsrc[1], d.L));
+  for (int pass = 1; pass <= 2; ++pass) {
+    if (dtype == B2H_BF16)
+      launch_bn_bwd_t<__nv_bfloat16>(d, grid, block, simple, pass, s);
+    else
+      launch_bn_bwd_t<float>(d, grid, block, simple, pass, s);
+    B2H_LAUNCH_CHECK(pass == 1 ? "bn_bwd pass 1" : "bn_bwd pass 2");
   }
-  B2H_LAUNCH_CHECK("bn_bwd pass 2");
   return B2H_OK;
 }
 
