@@ -154,8 +154,10 @@ struct SrcRows {
   int ld, rowmap, L_src;
   bool regular;   // source row is a pure function of the output row (no per-clip wrap needed)
 };
+template <bool SIMPLE>
 __device__ __forceinline__ int64_t src_row_of(const SrcRows& s, int row, int L) {
   if (s.rowmap == B2H_ROW_IDENT) return row;
+  if (SIMPLE) return row >> 1;
   if (s.regular) return s.rowmap == B2H_ROW_UP2 ? (row >> 1) : 2 * (int64_t)row;
   const int b = row / L, l = row - b * L;
   if (s.rowmap == B2H_ROW_UP2) return (int64_t)b * s.L_src + (l >> 1);
@@ -163,8 +165,10 @@ __device__ __forceinline__ int64_t src_row_of(const SrcRows& s, int row, int L) 
   return b;  // BCAST
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256) bn_apply_kernel(b2h_bn_apply_t d) {
+// SIMPLE: no pooled source, every source IDENT or a regular UP2, the 4 rows of a thread in one group (the common
+// case; keeps the pooling / per-row division code and its registers out of the kernel).
+template <typename T, bool SIMPLE>
+__global__ void __launch_bounds__(256, 2) bn_apply_kernel(b2h_bn_apply_t d) {
   pdl_sync();
   const int tx = threadIdx.x, ty = threadIdx.y, TY = blockDim.y;
   const int c0 = tx * 8;
@@ -190,7 +194,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(b2h_bn_apply_t d) {
     sr[k].regular = (src.rowmap == B2H_ROW_UP2 && (d.L & 1) == 0 && src.L_src * 2 == d.L) ||
                     (src.rowmap == B2H_ROW_POOL2 && src.L_src == 2 * d.L);
   }
-  const bool pool0 = sr[0].rowmap == B2H_ROW_POOL2;   // (a pooled SECOND source is rejected by the launcher)
+  const bool pool0 = !SIMPLE && sr[0].rowmap == B2H_ROW_POOL2;   // (a pooled SECOND source is rejected by the launcher)
   // folded affine of the group (a block of 8 rows never straddles groups when rows_per_group % 8 == 0)
   F8 s0 = zero8(), t0 = zero8(), s1 = zero8(), t1 = zero8();
   int gcur = -1;
@@ -202,11 +206,11 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(b2h_bn_apply_t d) {
     for (int u = 0; u < 4; ++u) {
       const int row = row0 + u;
       if (row < rows && live) {
-        const T* p0 = reinterpret_cast<const T*>(sr[0].z) + src_row_of(sr[0], row, d.L) * sr[0].ld;
+        const T* p0 = reinterpret_cast<const T*>(sr[0].z) + src_row_of<SIMPLE>(sr[0], row, d.L) * sr[0].ld;
         za[u] = load8<T>(p0);
         if (pool0) zb[u] = load8<T>(p0 + sr[0].ld);
         if (two) {
-          const T* p1 = reinterpret_cast<const T*>(sr[1].z) + src_row_of(sr[1], row, d.L) * sr[1].ld;
+          const T* p1 = reinterpret_cast<const T*>(sr[1].z) + src_row_of<SIMPLE>(sr[1], row, d.L) * sr[1].ld;
           zc[u] = load8<T>(p1);
         }
       }
@@ -218,7 +222,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(b2h_bn_apply_t d) {
       if (row >= rows) break;
       F8 y = zero8();
       if (live) {
-        const int g = d.groups == 1 ? 0 : row / rpg;
+        const int g = d.groups == 1 ? 0 : (SIMPLE ? row0 / rpg : row / rpg);
         if (g != gcur) {
           gcur = g;
           s0 = ld8f(d.src[0].scale + g * d.src[0].Cs + d.src[0].coff + c0);
@@ -260,8 +264,10 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(b2h_bn_apply_t d) {
 }
 
 int launch_bn_apply(const b2h_bn_apply_t& d, int dtype, cudaStream_t s) {
-  B2H_CARVE(bn_apply_kernel<__nv_bfloat16>);
-  B2H_CARVE(bn_apply_kernel<float>);
+  B2H_CARVE(bn_apply_kernel<__nv_bfloat16, true>);
+  B2H_CARVE(bn_apply_kernel<__nv_bfloat16, false>);
+  B2H_CARVE(bn_apply_kernel<float, true>);
+  B2H_CARVE(bn_apply_kernel<float, false>);
   B2H_CHECK_ARG(d.nsrc >= 1 && d.nsrc <= 2 && d.C > 0 && d.Cfill >= d.C && d.Cfill <= 1024 && d.groups >= 1,
                 B2H_ERR_SHAPE, "bn_apply: bad shape C=%d Cfill=%d nsrc=%d", d.C, d.Cfill, d.nsrc);
   B2H_CHECK_ARG(d.Cfill % 8 == 0 && d.out_ld % 8 == 0 && d.out_coff % 8 == 0 && d.drop_coff % 8 == 0, B2H_ERR_ALIGN,
@@ -278,10 +284,23 @@ int launch_bn_apply(const b2h_bn_apply_t& d, int dtype, cudaStream_t s) {
   const int ty = 256 / txp;
   const int rows = d.B * d.L;
   dim3 grid(ceil_div(ceil_div(rows, 4), ty)), block(txp, ty);
-  if (dtype == B2H_BF16)
-    launch(bn_apply_kernel<__nv_bfloat16>, grid, block, 0, s, d);
-  else
-    launch(bn_apply_kernel<float>, grid, block, 0, s, d);
+  bool simple = d.groups == 1 || (rows / d.groups) % 4 == 0;
+  for (int i = 0; i < d.nsrc; ++i) {
+    const b2h_bn_src_t& sc = d.src[i];
+    simple = simple && (sc.rowmap == B2H_ROW_IDENT ||
+                        (sc.rowmap == B2H_ROW_UP2 && (d.L & 1) == 0 && sc.L_src * 2 == d.L));
+  }
+  if (dtype == B2H_BF16) {
+    if (simple)
+      launch(bn_apply_kernel<__nv_bfloat16, true>, grid, block, 0, s, d);
+    else
+      launch(bn_apply_kernel<__nv_bfloat16, false>, grid, block, 0, s, d);
+  } else {
+    if (simple)
+      launch(bn_apply_kernel<float, true>, grid, block, 0, s, d);
+    else
+      launch(bn_apply_kernel<float, false>, grid, block, 0, s, d);
+  }
   B2H_LAUNCH_CHECK("bn_apply");
   return B2H_OK;
 }
