@@ -13,6 +13,7 @@ the generator loss adds a value but no gradient; there is no velocity term.
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -120,6 +121,8 @@ class GanTrainer:
         self._build_loss_programs(label_smooth)
         self._graphs: Dict[str, torch.cuda.CUDAGraph] = {}
         self._comm_stream = None
+        self._wgrad_stream = None
+        self.overlap_wgrad = os.environ.get("B2H_NO_WGRAD_OVERLAP") is None
 
     @classmethod
     def from_modules(cls, generator, discriminator, batch_size: int, T: int, precision: str = "fp32", **kw):
@@ -215,31 +218,71 @@ class GanTrainer:
             hi = lo
         return out
 
+    def _run_bwd_ops(self, plan: nets.NetPlan, s: int, e: int, cur) -> bool:
+        """Ops [s, e) of a backward segment.  The weight-gradient GEMMs (+ their split-K reduce) only feed the
+        optimizer, so they go to a side stream and overlap the bn_bwd -> dgrad chain of the following layers
+        (both fit on an SM together).  Returns True if the side stream was used."""
+        if not self.overlap_wgrad:
+            plan.prog.run_range(s, e, cur.cuda_stream)
+            return False
+        if self._wgrad_stream is None:
+            self._wgrad_stream = torch.cuda.Stream(self.device)
+        side, recs, used, i = self._wgrad_stream, plan.prog.recs, False, s
+        while i < e:
+            is_w = recs[i].kind == L.OP_WGRAD
+            j = i
+            while j < e and (recs[j].kind == L.OP_WGRAD) == is_w:
+                j += 1
+            if is_w:
+                ev = torch.cuda.Event()
+                ev.record(cur)             # dpre of this layer is complete
+                side.wait_event(ev)
+                plan.prog.run_range(i, j, side.cuda_stream)
+                used = True
+            else:
+                plan.prog.run_range(i, j, cur.cuda_stream)
+            i = j
+        return used
+
     def _bwd_bucketed(self, plan: nets.NetPlan):
         """Backward in buckets; each bucket's flat-gradient range is all-reduced over NCCL on a side stream while
         the next bucket computes."""
+        cur = torch.cuda.current_stream(self.device)
         if self.world_size == 1:
-            plan.prog.run("bwd")
+            s, e = plan.prog.segments["bwd"]
+            if self._run_bwd_ops(plan, s, e, cur):
+                ev = torch.cuda.Event()
+                ev.record(self._wgrad_stream)
+                cur.wait_event(ev)
             return
         import torch.distributed as dist
         if self._comm_stream is None:
             self._comm_stream = torch.cuda.Stream(self.device)
         st = plan.store
-        cur = torch.cuda.current_stream(self.device)
         pending = []
+        any_side = False
         for (s, e, lo, hi) in self.bucket_plan(plan):
-            plan.prog.run_range(s, e, cur.cuda_stream)
+            used_side = self._run_bwd_ops(plan, s, e, cur)
+            any_side = any_side or used_side
             if hi <= lo:
                 continue
             ev = torch.cuda.Event()
             ev.record(cur)
             self._comm_stream.wait_event(ev)
+            if used_side:
+                evw = torch.cuda.Event()
+                evw.record(self._wgrad_stream)
+                self._comm_stream.wait_event(evw)
             with torch.cuda.stream(self._comm_stream):
                 dist.all_reduce(st.grad[lo:hi], op=dist.ReduceOp.SUM, group=self.pg)
             done = torch.cuda.Event()
             done.record(self._comm_stream)
             pending.append(done)
         for ev in pending:
+            cur.wait_event(ev)
+        if any_side:
+            ev = torch.cuda.Event()
+            ev.record(self._wgrad_stream)
             cur.wait_event(ev)
 
     # ---- steps ---------------------------------------------------------------------------------
