@@ -274,11 +274,10 @@ def main():
     h_loss = torch.empty(8, dtype=torch.float32).pin_memory()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
+    tr.prefetch_batch(hx, hy, hf)          # batch 0; every later batch is copied while the previous one trains
     for _ in range(a.steps):
-        tr.x.copy_(hx, non_blocking=True)
-        tr.y.copy_(hy, non_blocking=True)
-        if hf is not None:
-            tr.feats.copy_(hf, non_blocking=True)
+        tr.swap_batch()
+        tr.prefetch_batch(hx, hy, hf)      # H2D of the next step's inputs, pinned host -> staging, copy stream
         step()
         if a.mode == "train":
             h_loss.copy_(tr.losses, non_blocking=True)

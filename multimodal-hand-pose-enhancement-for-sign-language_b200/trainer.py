@@ -121,6 +121,7 @@ class GanTrainer:
         self._build_loss_programs(label_smooth)
         self._graphs: Dict[str, torch.cuda.CUDAGraph] = {}
         self._comm_stream = None
+        self._copy_stream = None
         self._wgrad_stream = None
         self.overlap_wgrad = os.environ.get("B2H_NO_WGRAD_OVERLAP") is None
 
@@ -141,6 +142,36 @@ class GanTrainer:
         self.y.copy_(y, non_blocking=True)
         if self.feats is not None:
             self.feats.copy_(feats.reshape(self.feats.shape), non_blocking=True)
+
+    def prefetch_batch(self, x, y, feats=None):
+        """Start the host->device copy of the NEXT batch (pinned host tensors) on a copy stream, into staging
+        buffers: it overlaps the steps running on the current batch.  swap_batch() makes it current."""
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+            self._stage = [torch.empty_like(self.x), torch.empty_like(self.y),
+                           torch.empty_like(self.feats) if self.feats is not None else None]
+            self._swap_done = None
+        cs = self._copy_stream
+        if self._swap_done is not None:
+            cs.wait_event(self._swap_done)     # the previous swap has finished reading the staging buffers
+        with torch.cuda.stream(cs):
+            self._stage[0].copy_(x, non_blocking=True)
+            self._stage[1].copy_(y, non_blocking=True)
+            if self.feats is not None:
+                self._stage[2].copy_(feats.reshape(self.feats.shape), non_blocking=True)
+        self._prefetch_done = torch.cuda.Event()
+        self._prefetch_done.record(cs)
+
+    def swap_batch(self):
+        """Make the prefetched batch the current one (device-to-device copies into the static step inputs)."""
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(self._prefetch_done)
+        self.x.copy_(self._stage[0], non_blocking=True)
+        self.y.copy_(self._stage[1], non_blocking=True)
+        if self.feats is not None:
+            self.feats.copy_(self._stage[2], non_blocking=True)
+        self._swap_done = torch.cuda.Event()
+        self._swap_done.record(cur)
 
     @staticmethod
     def _alias_inputs(dst: nets.NetPlan, src: nets.NetPlan):
