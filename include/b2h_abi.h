@@ -312,6 +312,8 @@ const char* b2h_last_error(void);
 /* 0 if a CUDA device of compute capability 10.x is current, else B2H_ERR_ARCH / B2H_ERR_CUDA */
 int b2h_check_device(void);
 int b2h_sm_count(void);
+/* kernels launched by the calling thread through this library so far (one-shots and program runs) */
+int64_t b2h_launch_count(void);
 /* sizeof() of the descriptor struct of an op kind (b2h_op_kind), for binding self-checks */
 int b2h_desc_size(int kind);
 

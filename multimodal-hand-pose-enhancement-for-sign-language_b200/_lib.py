@@ -137,6 +137,7 @@ SYMBOLS = {
     "b2h_last_error": (C.c_char_p, []),
     "b2h_check_device": (C.c_int, []),
     "b2h_sm_count": (C.c_int, []),
+    "b2h_launch_count": (i64, []),
     "b2h_desc_size": (C.c_int, [C.c_int]),
     "b2h_gemm": (C.c_int, [C.POINTER(Gemm), C.c_int, vp]),
     "b2h_wgrad": (C.c_int, [C.POINTER(Wgrad), C.c_int, vp]),

@@ -267,5 +267,6 @@ int b2h_program_run(b2h_program* p, int first, int count, b2h_stream_t s) {
 }
 
 int64_t b2h_program_launches(const b2h_program* p) { return p ? p->launches : 0; }
+int64_t b2h_launch_count(void) { return g_launch_count; }
 
 }  // extern "C"

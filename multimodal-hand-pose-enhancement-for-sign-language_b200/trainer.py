@@ -123,6 +123,8 @@ class GanTrainer:
         self._comm_stream = None
         self._copy_stream = None
         self._wgrad_stream = None
+        self._adv_stream = None
+        self.overlap_adv = os.environ.get("B2H_NO_ADV_OVERLAP") is None
         self.overlap_wgrad = os.environ.get("B2H_NO_WGRAD_OVERLAP") is None
 
     @classmethod
@@ -321,13 +323,43 @@ class GanTrainer:
     # step, and shared by its train and eval plans; the eval plan's only per-step preparation is folding the
     # running BN statistics (one launch).
     def _g_ops(self):
-        self.D_eval.prog.run("pack")      # fold D's running statistics
+        if not self.overlap_adv:
+            self.D_eval.prog.run("pack")      # fold D's running statistics
+            self.G_train.prog.run("fwd")
+            self.D_eval.prog.run("fwd")
+            self.g_loss_prog.run("loss")
+            self._bwd_bucketed(self.G_train)
+            self.g_loss_prog.run("opt")
+            self.G_train.prog.run("pack")     # repack the updated generator weights
+            return
+        # The adversarial term of the generator loss carries no gradient (train_gan.py:285-287 detaches the
+        # score): scoring the fake with D only produces a reported VALUE.  It runs as a parallel
+        # branch (side stream) next to L1 -> backward -> Adam instead of in front of them.
+        cur = torch.cuda.current_stream(self.device)
+        if self._adv_stream is None:
+            self._adv_stream = torch.cuda.Stream(self.device)
+        adv = self._adv_stream
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        adv.wait_event(fork)
+        self.D_eval.prog.run("pack", adv.cuda_stream)        # fold D's running statistics
         self.G_train.prog.run("fwd")
-        self.D_eval.prog.run("fwd")
-        self.g_loss_prog.run("loss")
+        fwd_done = torch.cuda.Event()
+        fwd_done.record(cur)
+        adv.wait_event(fwd_done)
+        self.D_eval.prog.run("fwd", adv.cuda_stream)
+        s, e = self.g_loss_prog.segments["loss"]             # [l1, adv]
+        self.g_loss_prog.run_range(s, s + 1, cur.cuda_stream)
+        l1_done = torch.cuda.Event()
+        l1_done.record(cur)
+        adv.wait_event(l1_done)                              # total = l1 + adv
+        self.g_loss_prog.run_range(s + 1, e, adv.cuda_stream)
         self._bwd_bucketed(self.G_train)
         self.g_loss_prog.run("opt")
         self.G_train.prog.run("pack")     # repack the updated generator weights
+        join = torch.cuda.Event()
+        join.record(adv)
+        cur.wait_event(join)
 
     def _d_ops(self):
         self.G_eval.prog.run("pack")      # fold G's running statistics
@@ -397,10 +429,11 @@ class GanTrainer:
         return self.G_eval.out
 
     def launches_per_gan_step(self) -> int:
-        """Kernel launches of one generator step + one discriminator step (measured from the programs)."""
-        n = 0
-        for p, segs in ((self.G_train.prog, ("pack", "fwd", "bwd")), (self.D_eval.prog, ("pack", "fwd")),
-                        (self.g_loss_prog, ("loss", "opt")), (self.G_eval.prog, ("pack", "fwd")),
-                        (self.D_train.prog, ("pack", "fwd", "bwd")), (self.d_loss_prog, ("loss", "opt"))):
-            n += sum(p.segment_launches.get(s, 0) for s in segs)
-        return n
+        """Kernel launches of one generator step + one discriminator step: the library's launch counter around
+        one EAGER pass of both steps (the graphs replay exactly this sequence).  Trains one step."""
+        lib = L.load()
+        n0 = int(lib.b2h_launch_count())
+        self.generator_step(graph=False)
+        self.discriminator_step(graph=False)
+        torch.cuda.synchronize(self.device)
+        return int(lib.b2h_launch_count()) - n0
