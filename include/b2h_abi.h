@@ -95,6 +95,22 @@ typedef struct {
   int32_t update_all_groups; /* 1: apply the running update once per group in order (two D forwards) */
 } b2h_bn_stats_t;
 
+/* First pass of the BatchNorm backward of the layer whose BN output a dgrad GEMM differentiates, produced by
+ * that GEMM (tensor-core path: in its epilogue, from the tile it stores and a TMA-staged tile of z):
+ *   accum[copy][group][c] += ( sum_rows out[row, c],  sum_rows out[row, c] * (z[map(row), c] - mean[c]) * invstd[c] )
+ * over the rows this GEMM writes; several GEMMs (the consumers of one layer) may add into the same accumulators.
+ * b2h_bn_bwd with the same `accum` then runs its second pass only. */
+#define B2H_BWD_COPIES 8
+typedef struct {
+  const void* z;      /* producer's post-activation tensor [B][Lz][ld], act dtype; NULL = disabled */
+  int32_t ld, Lz;     /* row pitch / rows per sample of z */
+  int32_t rowmap;     /* B2H_ROW_IDENT: z row (b, l) (Lz == Lo_actual);  B2H_ROW_UP2: z row (b, l/2) (Lo_actual == 2*Lz) */
+  int32_t C, Cs, groups;
+  const float* mean;   /* [groups][Cs] batch statistics of the producer's forward */
+  const float* invstd;
+  double* accum;      /* [B2H_BWD_COPIES][groups][C][2], zero before the first contribution */
+} b2h_bwd_sums_t;
+
 /* ------------------------------------------------------------------------------------------- */
 /* tap-GEMM: every contraction of the path (Conv1d, its dgrad, ConvTranspose1d as a 2-phase     */
 /* sub-pixel conv, its dgrad as a strided conv, Linear) is                                       */
@@ -125,6 +141,7 @@ typedef struct {
   b2h_bn_stats_t stats; /* optional (stats.z != NULL, must equal `out`): also compute the train-mode BatchNorm
                            statistics of the output, exactly as b2h_bn_stats(&stats) right after this op would
                            (on the tensor-core path inside the GEMM epilogue, without re-reading `out`) */
+  b2h_bwd_sums_t bwd_sums; /* optional (bwd_sums.z != NULL), dgrad ops: see b2h_bwd_sums_t */
 } b2h_gemm_t;
 
 /* wgrad: dW[m][n][t] = sum_{b,r} P[b, r, m] * Q[b, r*stride + tap_off[t], n]   (PyTorch weight layout)
@@ -188,6 +205,8 @@ typedef struct {
   float* sums;    /* workspace [groups][C][2]  (sum dy, sum dy*zhat) */
   float* partial; /* workspace [nchunks][groups][C][2] (shared by both passes) */
   uint32_t* ticket;
+  double* accum;  /* optional: the first-pass sums were already accumulated here by the GEMMs that produced the
+                     gradient sources (b2h_gemm_t.bwd_sums); the op then runs its second pass only and re-zeroes it */
 } b2h_bn_bwd_t;
 
 /* ------------------------------------------------------------------------------------------- */

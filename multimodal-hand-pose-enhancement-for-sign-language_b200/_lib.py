@@ -31,13 +31,21 @@ class BnStats(C.Structure):
                 ("momentum", f32), ("eps", f32), ("partial", vp), ("ticket", vp), ("update_all_groups", i32)]
 
 
+BWD_COPIES = 8
+
+
+class BwdSums(C.Structure):
+    _fields_ = [("z", vp), ("ld", i32), ("Lz", i32), ("rowmap", i32), ("C", i32), ("Cs", i32), ("groups", i32),
+                ("mean", vp), ("invstd", vp), ("accum", vp)]
+
+
 class Gemm(C.Structure):
     _fields_ = [("A", vp), ("W", vp), ("bias", vp), ("out", vp),
                 ("B", i32), ("La", i32), ("Lo", i32), ("lda", i32), ("ldo", i32), ("out_coff", i32),
                 ("Kc", i32), ("Npad", i32), ("Nvalid", i32), ("ntaps", i32), ("stride", i32),
                 ("tap_off", i32 * MAX_TAPS), ("nphase", i32), ("Lo_actual", i32), ("act", i32),
                 ("post_scale", vp), ("post_shift", vp), ("out_f32", i32), ("drop", Dropout), ("drop_C", i32),
-                ("stats", BnStats)]
+                ("stats", BnStats), ("bwd_sums", BwdSums)]
 
 
 class Wgrad(C.Structure):
@@ -66,7 +74,7 @@ class BnBwd(C.Structure):
     _fields_ = [("gsrc", GradSrc * 2), ("ngsrc", i32), ("bn", BnSrc), ("dpre", vp),
                 ("ld_dpre", i32), ("Cfill", i32), ("B", i32), ("L", i32), ("C", i32), ("groups", i32),
                 ("act", i32), ("dgamma", vp), ("dbeta", vp), ("dbias", vp), ("sums", vp), ("partial", vp),
-                ("ticket", vp)]
+                ("ticket", vp), ("accum", vp)]
 
 
 class Prep(C.Structure):

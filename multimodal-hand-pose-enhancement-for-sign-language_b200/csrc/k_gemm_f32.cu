@@ -124,8 +124,10 @@ int launch_gemm_f32(const b2h_gemm_t& d, cudaStream_t s) {
   B2H_LAUNCH_CHECK("gemm_f32");
   if (d.stats.z) {   // fp32 path: the statistics of the output are a separate pass
     B2H_CHECK_ARG(d.stats.z == d.out && d.out_coff == 0, B2H_ERR_ARG, "gemm: stats must describe the output tensor");
-    return launch_bn_stats(d.stats, B2H_F32, s);
+    int rc2 = launch_bn_stats(d.stats, B2H_F32, s);
+    if (rc2) return rc2;
   }
+  if (d.bwd_sums.z) return launch_bwd_sums_separate(d, B2H_F32, s);
   return B2H_OK;
 }
 

@@ -101,10 +101,28 @@ __device__ __forceinline__ void epi_finish8(const EpiParams& e, const DropCtx& d
 
 // STATS: the epilogue also produces the train-mode BatchNorm statistics of the tile it stores (per-column
 // shifted sums of the bf16-rounded outputs -> fp64 atomics -> the last CTA finalises), see bn_finalize.cuh.
-template <int BN, int KIND, bool STATS>
+// BWDSUM (dgrad): the store phase also accumulates the first pass of the producer layer's BatchNorm backward,
+// sum(g) and sum(g * zhat) per column, against a tile of the producer's z that one TMA brings into the idle
+// pipeline buffers while the accumulator is being staged (b2h_bwd_sums_t).
+enum { MODE_PLAIN = 0, MODE_STATS = 1, MODE_BWDSUM = 2 };
+
+struct BwdSumsDev {
+  const float* mean;
+  const float* invstd;
+  double* accum;
+  int C, Cs, groups;
+  int up2;      // z row = tile row / 2 (x2 nearest up-sampling between the producer and this GEMM's rows)
+  int zbytes;   // bytes of the z box
+};
+
+template <int BN, int KIND, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, FpropCfg<BN>::OCC)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-               const __grid_constant__ CUtensorMap tmB, TcGemmParams p, EpiParams e, b2h_bn_stats_t st) {
+               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmZ0,
+               const __grid_constant__ CUtensorMap tmZ1, TcGemmParams p, EpiParams e, b2h_bn_stats_t st,
+               BwdSumsDev bs) {
+  constexpr bool STATS = MODE == MODE_STATS;
+  constexpr bool BWDSUM = MODE == MODE_BWDSUM;
   using Cfg = FpropCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -116,6 +134,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   float* s_bias = reinterpret_cast<float*>(smem + Cfg::MAIN_BYTES + 256);
   float* s_piv = s_bias + BN;
   int* s_flag = reinterpret_cast<int*>(tmem_ptr + 1);
+  uint64_t* z_bar = reinterpret_cast<uint64_t*>(tmem_ptr + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mt = blockIdx.x, nt = blockIdx.y;
@@ -134,6 +153,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       mbar_init(&empty_bar[i], 1);
     }
     mbar_init(tmem_full_bar, 1);
+    if (BWDSUM) {
+      prefetch_tmap(&tmZ0);
+      prefetch_tmap(&tmZ1);
+      mbar_init(z_bar, 1);
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -202,6 +226,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
     }
+    const int grp = (STATS || BWDSUM) ? b0 / (p.B / (STATS ? st.groups : bs.groups)) : 0;
+    if (BWDSUM) {
+      for (int i = et; i < BN; i += 256) {
+        const bool in = nn0 + i < bs.C;
+        s_piv[i] = in ? bs.mean[grp * bs.Cs + nn0 + i] : 0.f;
+        s_bias[i] = in ? bs.invstd[grp * bs.Cs + nn0 + i] : 0.f;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
+    // z tile (BWDSUM): behind the staging tile and the per-warp partials; the pipeline buffers are idle by then
+    uint8_t* zs = smem + (((size_t)128 * pitch + (size_t)8 * BN * 8 + 127) & ~(size_t)127);
     DropCtx drop;
     drop.init(e.drop, e.drop_C);
     {
@@ -215,6 +250,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       uint8_t* my = stage + (size_t)lane * pitch;
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
+      if (BWDSUM && et == 0) {   // every MMA has retired: the stage buffers are free
+        mbar_arrive_expect_tx(z_bar, (uint32_t)bs.zbytes);
+        tma_load_3d(zs, ph ? &tmZ1 : &tmZ0, z_bar, nn0, bs.up2 ? (l0 >> 1) : l0, b0);
+      }
       constexpr int CH = BN / 2;  // columns per epilogue warp
 #pragma unroll 1
       for (int c = chalf * CH; c < (chalf + 1) * CH; c += 32) {
@@ -259,16 +298,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
     // both warps of this sub-partition have written their column halves
     asm volatile("bar.sync %0, 64;" ::"r"(2 + sub) : "memory");
-    if (STATS) {
+    if (STATS || BWDSUM) {
       // lane <-> fixed 16-byte column chunk; the lanes left over take further rows of the same iteration
       constexpr int CHUNKS = BN / 8;
       constexpr int LPR = CHUNKS < 32 ? CHUNKS : 32;
       constexpr int RPI = 32 / LPR;
       const int ch = lane % LPR, rsub = lane / LPR;
       const bool ch_ok = ch * 8 < valid_cols;   // a ragged last chunk is stored whole (zeros in the padding)
-      float piv[8], a1[8], a2[8];
+      // STATS: piv = pivot of the shifted sums.  BWDSUM: piv = mean, sc = invstd of the producer layer
+      float piv[8], sc[8], a1[8], a2[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) piv[i] = s_piv[ch * 8 + i], a1[i] = 0.f, a2[i] = 0.f;
+      for (int i = 0; i < 8; ++i) {
+        piv[i] = s_piv[ch * 8 + i], a1[i] = 0.f, a2[i] = 0.f;
+        sc[i] = BWDSUM ? s_bias[ch * 8 + i] : 1.f;
+      }
+      if (BWDSUM) mbar_wait(z_bar, 0);
       if (ch_ok) {
 #pragma unroll 1
         for (int rr = chalf * 16 + rsub; rr < chalf * 16 + 16; rr += RPI) {
@@ -282,12 +326,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           const uint4 u = *reinterpret_cast<const uint4*>(stage + (size_t)rr * pitch + ch * 16);
           *reinterpret_cast<uint4*>(gdst + ch * 16) = u;
           const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+          if (STATS) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
-            const float d0 = f.x - piv[2 * i], d1 = f.y - piv[2 * i + 1];
-            a1[2 * i] += d0, a1[2 * i + 1] += d1;
-            a2[2 * i] = fmaf(d0, d0, a2[2 * i]), a2[2 * i + 1] = fmaf(d1, d1, a2[2 * i + 1]);
+            for (int i = 0; i < 4; ++i) {
+              const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+              const float d0 = f.x - piv[2 * i], d1 = f.y - piv[2 * i + 1];
+              a1[2 * i] += d0, a1[2 * i + 1] += d1;
+              a2[2 * i] = fmaf(d0, d0, a2[2 * i]), a2[2 * i + 1] = fmaf(d1, d1, a2[2 * i + 1]);
+            }
+          } else {
+            const int zr = bs.up2 ? bi * (p.tl >> 1) + (li >> 1) : r;
+            const uint4 zq = *reinterpret_cast<const uint4*>(zs + ((size_t)zr * BN + ch * 8) * 2);
+            const uint32_t zw[4] = {zq.x, zq.y, zq.z, zq.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+              const float2 zf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&zw[i]));
+              const float h0 = (zf.x - piv[2 * i]) * sc[2 * i], h1 = (zf.y - piv[2 * i + 1]) * sc[2 * i + 1];
+              a1[2 * i] += f.x, a1[2 * i + 1] += f.y;
+              a2[2 * i] = fmaf(f.x, h0, a2[2 * i]), a2[2 * i + 1] = fmaf(f.y, h1, a2[2 * i + 1]);
+            }
           }
         }
       }
@@ -307,7 +365,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         for (int i = 0; i < 8; ++i) s_part[(warp - 2) * BN + ch * 8 + i] = make_float2(a1[i], a2[i]);
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      const int grp = b0 / (p.B / st.groups);
       for (int c = et; c < valid_cols; c += 256) {
         float t1 = 0.f, t2 = 0.f;
 #pragma unroll
@@ -315,20 +372,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           const float2 v = s_part[w8 * BN + c];
           t1 += v.x, t2 += v.y;
         }
-        bn_stats_accumulate(st, blockIdx.x % kCopies, grp, nn0 + c, t1, t2);
+        if (STATS) {
+          bn_stats_accumulate(st, blockIdx.x % kCopies, grp, nn0 + c, t1, t2);
+        } else {
+          double* a = bs.accum + (((int64_t)(blockIdx.x % B2H_BWD_COPIES) * bs.groups + grp) * bs.C + nn0 + c) * 2;
+          atomicAdd(a + 0, (double)t1);
+          atomicAdd(a + 1, (double)t2);
+        }
       }
-      __threadfence();
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (et == 0) {
-        const uint32_t t = atomicAdd(st.ticket, 1u);
-        const int last = (t == gridDim.x * gridDim.y - 1u);
-        if (last) *st.ticket = 0u;
-        *s_flag = last;
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (*s_flag) {
+      if (STATS) {
         __threadfence();
-        bn_stats_finalize(st, et, 256);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (et == 0) {
+          const uint32_t t = atomicAdd(st.ticket, 1u);
+          const int last = (t == gridDim.x * gridDim.y - 1u);
+          if (last) *st.ticket = 0u;
+          *s_flag = last;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (*s_flag) {
+          __threadfence();
+          bn_stats_finalize(st, et, 256);
+        }
       }
     } else
     if (valid_cols > 0) {
@@ -545,7 +610,7 @@ static EncodeTiledFn get_encode_fn() {
 
 // bf16 tensor map over a (C, L, B) view: element (c, l, b) at base + (b*sample_pitch + l*row_pitch + c)*2 bytes
 static int make_map_3d(CUtensorMap* m, const void* base, int64_t C, int64_t L, int64_t B, int64_t row_pitch,
-                       int64_t sample_pitch, int box_c, int box_l, int box_b) {
+                       int64_t sample_pitch, int box_c, int box_l, int box_b, bool swizzle128 = true) {
   EncodeTiledFn fn = get_encode_fn();
   B2H_CHECK_ARG(fn != nullptr, B2H_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
   cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)L, (cuuint64_t)B};
@@ -555,8 +620,8 @@ static int make_map_3d(CUtensorMap* m, const void* base, int64_t C, int64_t L, i
   B2H_CHECK_ARG(((uintptr_t)base % 16) == 0 && strides[0] % 16 == 0 && strides[1] % 16 == 0, B2H_ERR_ALIGN,
                 "tensor map: base/strides must be 16-byte aligned");
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   B2H_CHECK_ARG(r == CUDA_SUCCESS, B2H_ERR_CUDA, "cuTensorMapEncodeTiled(3d) failed: %d (C=%lld L=%lld B=%lld)", (int)r,
                 (long long)C, (long long)L, (long long)B);
   return B2H_OK;
@@ -698,6 +763,47 @@ int plan_gemm_bf16(const b2h_gemm_t& d, TcGemmPlan* plan) {
                        (d.B / st.groups) % p.tb == 0 && st.partial && ((uintptr_t)st.partial % 16) == 0 &&
                        st.ticket && st.Cs >= st.C && !getenv("B2H_NO_FUSED_STATS");
   }
+  plan->fuse_bwd = 0;
+  if (d.bwd_sums.z) {
+    const b2h_bwd_sums_t& bs = d.bwd_sums;
+    const int kind = epi_kind(d);
+    const bool up2 = bs.rowmap == B2H_ROW_UP2;
+    bool ok = (kind == EPI_MASK || kind == EPI_PLAIN) && !plan->fuse_stats && bs.C == d.Nvalid && d.out_coff == 0 &&
+              d.ldo >= ((d.Nvalid + 7) & ~7) && bs.groups >= 1 && d.B % bs.groups == 0 &&
+              (d.B / bs.groups) % p.tb == 0 && bs.accum && ((uintptr_t)bs.accum % 16) == 0 && bs.mean && bs.invstd &&
+              bs.ld % 8 == 0 && bs.ld >= d.Npad / d.nphase && !getenv("B2H_NO_FUSED_BWD");
+    if (up2)
+      ok = ok && d.nphase == 1 && p.tl >= 2 && d.Lo_actual == 2 * bs.Lz;
+    else
+      ok = ok && bs.rowmap == B2H_ROW_IDENT && d.Lo_actual == bs.Lz;
+    if (ok) {
+      const __nv_bfloat16* z = reinterpret_cast<const __nv_bfloat16*>(bs.z);
+      const int box_l = up2 ? p.tl / 2 : p.tl;
+      if (d.nphase == 1) {
+        rc = make_map_3d(&plan->tmZ0, z, bs.ld, bs.Lz, d.B, bs.ld, (int64_t)bs.Lz * bs.ld, best_bn, box_l, p.tb, false);
+        plan->tmZ1 = plan->tmZ0;
+      } else {   // output row 2*lo + ph <-> the even / odd rows of z
+        const int Le = (bs.Lz + 1) / 2, Lod = bs.Lz / 2;
+        rc = make_map_3d(&plan->tmZ0, z, bs.ld, Le, d.B, 2 * (int64_t)bs.ld, (int64_t)bs.Lz * bs.ld, best_bn, box_l, p.tb,
+                         false);
+        if (!rc && Lod > 0)
+          rc = make_map_3d(&plan->tmZ1, z + bs.ld, bs.ld, Lod, d.B, 2 * (int64_t)bs.ld, (int64_t)bs.Lz * bs.ld, best_bn,
+                           box_l, p.tb, false);
+        else   // no odd rows: the odd-phase tiles have no valid row and ignore what they load
+          plan->tmZ1 = plan->tmZ0;
+      }
+      if (rc) return rc;
+      plan->fuse_bwd = 1;
+      plan->bs_mean = bs.mean;
+      plan->bs_invstd = bs.invstd;
+      plan->bs_accum = bs.accum;
+      plan->bs_C = bs.C;
+      plan->bs_Cs = bs.Cs;
+      plan->bs_groups = bs.groups;
+      plan->bs_up2 = up2 ? 1 : 0;
+      plan->bs_zbytes = best_bn * 2 * box_l * p.tb;
+    }
+  }
   return B2H_OK;
 }
 
@@ -715,21 +821,35 @@ static int epi_kind(const b2h_gemm_t& d) {
   return EPI_GENERIC;
 }
 
-template <int BN, int KIND, bool STATS = false>
+template <int BN, int KIND, int MODE = MODE_PLAIN>
 static int launch_fprop(const TcGemmPlan& plan, const EpiParams& e, cudaStream_t s,
                         const b2h_bn_stats_t& st = b2h_bn_stats_t()) {
   using Cfg = FpropCfg<BN>;
-  B2H_CARVE(gemm_tc_kernel<BN, KIND, STATS>);
+  static_assert(((128 * (BN * 2 + 16) + 64 * BN + 127) & ~127) + 128 * BN * 2 <= Cfg::MAIN_BYTES, "z tile placement");
+  B2H_CARVE(gemm_tc_kernel<BN, KIND, MODE>);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t er = cudaFuncSetAttribute(gemm_tc_kernel<BN, KIND, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t er = cudaFuncSetAttribute(gemm_tc_kernel<BN, KIND, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           Cfg::SMEM_BYTES);
     if (er != cudaSuccess) return cuda_fail(er, "gemm_tc smem attribute");
     attr_set = true;
   }
   dim3 grid(plan.grid_x, plan.grid_y);
-  launch(gemm_tc_kernel<BN, KIND, STATS>, grid, TC_THREADS, Cfg::SMEM_BYTES, s, plan.tmA0, plan.tmA1, plan.tmB, plan.p, e,
-         st);
+  BwdSumsDev bs;
+  memset(&bs, 0, sizeof(bs));
+  if (MODE == MODE_BWDSUM) {
+    bs.mean = plan.bs_mean;
+    bs.invstd = plan.bs_invstd;
+    bs.accum = plan.bs_accum;
+    bs.C = plan.bs_C;
+    bs.Cs = plan.bs_Cs;
+    bs.groups = plan.bs_groups;
+    bs.up2 = plan.bs_up2;
+    bs.zbytes = plan.bs_zbytes;
+  }
+  const bool z = MODE == MODE_BWDSUM;
+  launch(gemm_tc_kernel<BN, KIND, MODE>, grid, TC_THREADS, Cfg::SMEM_BYTES, s, plan.tmA0, plan.tmA1, plan.tmB,
+         z ? plan.tmZ0 : plan.tmA0, z ? plan.tmZ1 : plan.tmA0, plan.p, e, st, bs);
   B2H_LAUNCH_CHECK("gemm_tc");
   return B2H_OK;
 }
@@ -738,8 +858,12 @@ template <int BN>
 static int launch_fprop_kind(const TcGemmPlan& plan, const EpiParams& e, int kind, cudaStream_t s,
                              const b2h_bn_stats_t& st) {
   if (plan.fuse_stats) {
-    if (kind == EPI_BIAS_LEAKY) return launch_fprop<BN, EPI_BIAS_LEAKY, true>(plan, e, s, st);
-    return launch_fprop<BN, EPI_BIAS_RELU, true>(plan, e, s, st);
+    if (kind == EPI_BIAS_LEAKY) return launch_fprop<BN, EPI_BIAS_LEAKY, MODE_STATS>(plan, e, s, st);
+    return launch_fprop<BN, EPI_BIAS_RELU, MODE_STATS>(plan, e, s, st);
+  }
+  if (plan.fuse_bwd) {
+    if (kind == EPI_MASK) return launch_fprop<BN, EPI_MASK, MODE_BWDSUM>(plan, e, s);
+    return launch_fprop<BN, EPI_PLAIN, MODE_BWDSUM>(plan, e, s);
   }
   switch (kind) {
     case EPI_BIAS_LEAKY: return launch_fprop<BN, EPI_BIAS_LEAKY>(plan, e, s);
@@ -760,8 +884,11 @@ int run_gemm_bf16(const TcGemmPlan& plan, const b2h_gemm_t& d, cudaStream_t s) {
     case 128: rc = launch_fprop_kind<128>(plan, e, kind, s, d.stats); break;
     default: rc = launch_fprop_kind<64>(plan, e, kind, s, d.stats); break;
   }
-  if (rc || !d.stats.z || plan.fuse_stats) return rc;
-  return launch_bn_stats(d.stats, B2H_BF16, s);   // shapes the epilogue cannot cover: separate pass
+  if (rc) return rc;
+  // shapes the epilogue cannot cover: separate passes with the same results
+  if (d.stats.z && !plan.fuse_stats) rc = launch_bn_stats(d.stats, B2H_BF16, s);
+  if (!rc && d.bwd_sums.z && !plan.fuse_bwd) rc = launch_bwd_sums_separate(d, B2H_BF16, s);
+  return rc;
 }
 
 int plan_wgrad_bf16(const b2h_wgrad_t& d, TcWgradPlan* plan) {

@@ -14,6 +14,7 @@
 // does not fit the instruction caches is bound by instruction fetch.  Hence small loop bodies, rolled loops
 // and out-of-line Philox.
 #include <algorithm>
+#include <string.h>
 
 #include "bn_finalize.cuh"
 
@@ -384,7 +385,7 @@ __device__ __forceinline__ void add_grad_src8(const b2h_bn_bwd_t& d, const b2h_g
 // the bias gradient the same way, and its LAST CTA (ticket) writes dgamma / dbeta / dbias / sums and re-zeroes
 // both accumulator regions.  SIMPLE: every gradient source is IDENT or a regular UP2 (no per-row div / pooling
 // branches in the code).
-constexpr int kCopiesBwd1 = 8;
+constexpr int kCopiesBwd1 = B2H_BWD_COPIES;
 
 template <typename T, int PASS, bool SIMPLE>
 __global__ void __launch_bounds__(kRowThreads, 2) bn_bwd_kernel(b2h_bn_bwd_t d) {
@@ -402,8 +403,8 @@ __global__ void __launch_bounds__(kRowThreads, 2) bn_bwd_kernel(b2h_bn_bwd_t d) 
   T* dpre = reinterpret_cast<T*>(d.dpre) + c0;
   // accumulators, zero between launches: region 1 [kCopiesBwd1][groups][C][2] (sum dy, sum dy*zhat),
   // region 2 [kCopies][groups][C] (sum dpre)
-  double* accum1 = reinterpret_cast<double*>(d.partial);
-  double* accum2 = accum1 + (int64_t)kCopiesBwd1 * d.groups * d.C * 2;
+  double* accum1 = d.accum ? d.accum : reinterpret_cast<double*>(d.partial);
+  double* accum2 = reinterpret_cast<double*>(d.partial) + (int64_t)kCopiesBwd1 * d.groups * d.C * 2;
   if (PASS == 2) {
     const double inv_n = 1.0 / (double)rpg;
     for (int c = tid; c < d.C; c += kRowThreads) {
@@ -550,7 +551,7 @@ static void launch_bn_bwd_t(const b2h_bn_bwd_t& d, dim3 grid, dim3 block, bool s
   }
 }
 
-int launch_bn_bwd(const b2h_bn_bwd_t& d, int dtype, cudaStream_t s) {
+static int launch_bn_bwd_passes(const b2h_bn_bwd_t& d, int dtype, int first_pass, int last_pass, cudaStream_t s) {
   B2H_CARVE(bn_bwd_kernel<__nv_bfloat16, 1, true>);
   B2H_CARVE(bn_bwd_kernel<__nv_bfloat16, 2, true>);
   B2H_CARVE(bn_bwd_kernel<__nv_bfloat16, 1, false>);
@@ -563,7 +564,7 @@ int launch_bn_bwd(const b2h_bn_bwd_t& d, int dtype, cudaStream_t s) {
                     d.ngsrc <= 2,
                 B2H_ERR_SHAPE, "bn_bwd: bad shape C=%d Cfill=%d ngsrc=%d", d.C, d.Cfill, d.ngsrc);
   B2H_CHECK_ARG(d.Cfill % 8 == 0 && d.ld_dpre % 8 == 0 && d.bn.ld % 8 == 0 && d.bn.coff == 0 && d.bn.Cs % 8 == 0 &&
-                    d.bn.Cs >= d.Cfill && ((uintptr_t)d.partial % 16) == 0,
+                    d.bn.Cs >= d.Cfill && ((uintptr_t)d.partial % 16) == 0 && ((uintptr_t)d.accum % 16) == 0,
                 B2H_ERR_ALIGN, "bn_bwd: alignment / padded per-channel arrays");
   for (int i = 0; i < d.ngsrc; ++i)
     B2H_CHECK_ARG(d.gsrc[i].ld % 8 == 0 && d.gsrc[i].coff % 8 == 0, B2H_ERR_ALIGN, "bn_bwd: grad source alignment");
@@ -574,7 +575,7 @@ int launch_bn_bwd(const b2h_bn_bwd_t& d, int dtype, cudaStream_t s) {
   RowGrid rg = row_grid(d.Cfill, rpg);
   dim3 grid(rg.ctas, d.groups), block(rg.txp, rg.ty);
   bool simple = grad_src_simple(d.gsrc[0], d.L) && (d.ngsrc < 2 || grad_src_simple(d.gsrc[1], d.L));
-  for (int pass = 1; pass <= 2; ++pass) {
+  for (int pass = first_pass; pass <= last_pass; ++pass) {
     if (dtype == B2H_BF16)
       launch_bn_bwd_t<__nv_bfloat16>(d, grid, block, simple, pass, s);
     else
@@ -582,6 +583,46 @@ int launch_bn_bwd(const b2h_bn_bwd_t& d, int dtype, cudaStream_t s) {
     B2H_LAUNCH_CHECK(pass == 1 ? "bn_bwd pass 1" : "bn_bwd pass 2");
   }
   return B2H_OK;
+}
+
+int launch_bn_bwd(const b2h_bn_bwd_t& d, int dtype, cudaStream_t s) {
+  // with `accum` the first pass was produced by the GEMMs that wrote the gradient sources
+  return launch_bn_bwd_passes(d, dtype, d.accum ? 2 : 1, 2, s);
+}
+
+// b2h_gemm_t.bwd_sums for GEMMs whose epilogue cannot produce it (fp32 path, unsupported tilings): the first
+// pass of bn_bwd restricted to this GEMM's output as the only gradient source.
+int launch_bwd_sums_separate(const b2h_gemm_t& g, int dtype, cudaStream_t s) {
+  const b2h_bwd_sums_t& bs = g.bwd_sums;
+  B2H_CHECK_ARG(bs.rowmap == B2H_ROW_IDENT || bs.rowmap == B2H_ROW_UP2, B2H_ERR_ARG, "bwd_sums: rowmap");
+  B2H_CHECK_ARG(bs.accum && bs.mean && bs.invstd && bs.C == g.Nvalid && !g.out_f32, B2H_ERR_ARG,
+                "bwd_sums: must describe the layer that produced the rows this GEMM differentiates");
+  b2h_bn_bwd_t d;
+  memset(&d, 0, sizeof(d));
+  d.gsrc[0].g = g.out;
+  d.gsrc[0].ld = g.ldo;
+  d.gsrc[0].coff = g.out_coff;
+  d.gsrc[0].rowmap = bs.rowmap;
+  d.gsrc[0].L_src = g.Lo_actual;
+  d.ngsrc = 1;
+  d.bn.z = bs.z;
+  d.bn.ld = bs.ld;
+  d.bn.Cs = bs.Cs;
+  d.bn.mean = bs.mean;
+  d.bn.invstd = bs.invstd;
+  d.bn.scale = bs.mean;   // only read by the pooling path, which a bwd_sums source never takes
+  d.bn.shift = bs.mean;
+  d.ld_dpre = 8;
+  d.Cfill = (bs.C + 7) & ~7;
+  d.B = g.B;
+  d.L = bs.Lz;
+  d.C = bs.C;
+  d.groups = bs.groups;
+  d.accum = bs.accum;
+  d.partial = reinterpret_cast<float*>(bs.accum);
+  B2H_CHECK_ARG(grad_src_simple(d.gsrc[0], d.L), B2H_ERR_SHAPE, "bwd_sums: Lo_actual=%d does not match Lz=%d",
+                g.Lo_actual, bs.Lz);
+  return launch_bn_bwd_passes(d, dtype, 1, 1, s);
 }
 
 // ---------------------------------------------------------------------------------------------

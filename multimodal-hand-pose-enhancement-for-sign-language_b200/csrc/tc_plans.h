@@ -20,9 +20,15 @@ struct TcGemmParams {
 
 struct alignas(64) TcGemmPlan {
   CUtensorMap tmA0, tmA1, tmB;
+  CUtensorMap tmZ0, tmZ1;  // fuse_bwd: the producer layer's z (all rows / even rows, odd rows), not swizzled
   TcGemmParams p;
   int BN, grid_x, grid_y;
   int fuse_stats;  // BatchNorm statistics of the output produced by the epilogue
+  int fuse_bwd;    // first pass of the producer's BatchNorm backward produced by the epilogue
+  const float* bs_mean;
+  const float* bs_invstd;
+  double* bs_accum;
+  int bs_C, bs_Cs, bs_groups, bs_up2, bs_zbytes;
 };
 
 struct TcWgradParams {

@@ -331,6 +331,7 @@ class LayerBufs:
     wf: torch.Tensor = None       # packed forward weights
     wb: torch.Tensor = None       # packed dgrad weights
     bias: torch.Tensor = None     # packed bias
+    bwd_accum: torch.Tensor = None  # fp64 (copies, groups, C, 2): first-pass sums of this layer's BN backward
     Kc: int = 0
     Cp: int = 0
     Lz: int = 0                   # rows per sample of z (2*La for convT)
@@ -510,6 +511,7 @@ class NetPlan:
         if self.train:
             # gradient of the loss w.r.t. the output layer's pre-activation, BLC act dtype
             olb.dpre = self._zeros(B, olb.Lz, olb.Cp)
+            self._plan_bwd_fusion()
             with P.segment("bwd"):
                 for l in reversed(spec.layers):
                     self.bwd_marks.append((l.name, len(P.recs)))
@@ -711,6 +713,30 @@ class NetPlan:
                     eps=BN_EPS, partial=None, ticket=self._ticket(), update_all_groups=1 if self.groups > 1 else 0)
 
     # ---- backward ----------------------------------------------------------------------------
+    def _plan_bwd_fusion(self):
+        """Layers whose BN-backward first pass (sum dy, sum dy*zhat) is produced by the dgrad GEMMs of their
+        consumers (b2h_gemm_t.bwd_sums).  A dgrad GEMM can serve one producer: its output must be exactly the
+        gradient of that producer's BN output (one feed over all columns, IDENT or regular x2 up-sampling)."""
+        import os
+        self.dgrad_target: Dict[str, Tuple[Layer, Feed]] = {}
+        self.bwd_fused = set()
+        if os.environ.get("B2H_NO_FUSED_BWD"):
+            return
+        cands = [p for p in self.spec.layers if p.bn and p is not self.out_layer and self.consumers[p.name]]
+        for p in sorted(cands, key=lambda q: len(self.consumers[q.name])):   # single-consumer layers first
+            pb = self.bufs[p.name]
+            ok = True
+            for (c, f) in self.consumers[p.name]:
+                covers = f.dst_coff == 0 and p.cout == c.cin and self.bufs[c.name].Kc == pb.Cp
+                simple = (f.rowmap == L.ROW_IDENT and c.La == pb.Lz) or (f.rowmap == L.ROW_UP2 and c.La == 2 * pb.Lz)
+                ok = ok and covers and simple and c.name not in self.dgrad_target and self._needs_dgrad(c)
+            if not ok:
+                continue
+            for (c, f) in self.consumers[p.name]:
+                self.dgrad_target[c.name] = (p, f)
+            self.bwd_fused.add(p.name)
+            pb.bwd_accum = torch.zeros(L.BWD_COPIES, self.groups, p.cout, 2, dtype=torch.float64, device=self.device)
+
     def _emit_bwd(self, l: Layer):
         P, st, B, lb = self.prog, self.store, self.B, self.bufs[l.name]
         rows = B * lb.Lz
@@ -732,7 +758,8 @@ class NetPlan:
             i = P.add(L.OP_BN_BWD, f"bn_bwd.{l.name}", gsrc=gs, ngsrc=len(self.consumers[l.name]),
                       bn=self._bn_src(l), dpre=lb.dpre, ld_dpre=lb.Cp, Cfill=lb.Cp, B=B, L=lb.Lz, C=l.cout,
                       groups=self.groups, act=l.act, dgamma=st.g(l.bnkey + ".weight"), dbeta=st.g(l.bnkey + ".bias"),
-                      dbias=st.g(l.wkey + ".bias"), sums=lb.sums, partial=None, ticket=self._ticket())
+                      dbias=st.g(l.wkey + ".bias"), sums=lb.sums, partial=None, ticket=self._ticket(),
+                      accum=lb.bwd_accum if l.name in self.bwd_fused else None)
             self._need_partial(i, _bn_partial_floats(rows, l.cout, self.groups))
         # weight gradient
         k = l.k
@@ -756,6 +783,11 @@ class NetPlan:
         common = dict(A=lb.dpre, W=lb.wb, bias=None, out=lb.g, B=B, La=lb.Lz, lda=lb.Cp, ldo=lb.Kc, out_coff=0,
                       Kc=lb.Cp, Nvalid=l.cin, ntaps=len(taps), tap_off=taps + [0] * (L.MAX_TAPS - len(taps)),
                       act=L.ACT_NONE, post_scale=None, post_shift=None, out_f32=0, drop=drop, drop_C=l.cin)
+        if l.name in self.dgrad_target:
+            p, f = self.dgrad_target[l.name]
+            pb = self.bufs[p.name]
+            common["bwd_sums"] = dict(z=pb.z, ld=pb.Cp, Lz=pb.Lz, rowmap=f.rowmap, C=p.cout, Cs=pb.Cp,
+                                      groups=self.groups, mean=pb.mean, invstd=pb.invstd, accum=pb.bwd_accum)
         if lb.bwd_nphase == 2:
             i = P.add(L.OP_GEMM, f"dgrad.{l.name}", Lo=_ceil_div(l.La, 2), Npad=2 * lb.Kc, stride=1, nphase=2,
                       Lo_actual=l.La, **common)

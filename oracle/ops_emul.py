@@ -101,6 +101,24 @@ def gemm(f: Dict):
     st = f.get("stats")
     if st and st.get("z") is not None:   # the op also produces the batch statistics of its output
         bn_stats(st)
+    bs = f.get("bwd_sums")
+    if bs and bs.get("z") is not None:   # first pass of the producer layer's BN backward over this op's output
+        C, G, Lz = bs["C"], bs["groups"], bs["Lz"]
+        assert f["out_coff"] == 0 and not f["out_f32"] and nph * 0 == 0
+        g = out2[:, :, :C].to(torch.float32)                           # (B, Lo_actual, C) as stored
+        z = bs["z"].to(torch.float32).reshape(B, Lz, -1)[:, :, :C]
+        if bs["rowmap"] == ROW_UP2:
+            assert Lact == 2 * Lz
+            z = z.repeat_interleave(2, dim=1)
+        else:
+            assert bs["rowmap"] == ROW_IDENT and Lact == Lz
+        Bg = B // G
+        acc = bs["accum"].reshape(-1, G, C, 2)
+        for gi in range(G):
+            sl = slice(gi * Bg, (gi + 1) * Bg)
+            zh = (z[sl] - bs["mean"][gi, :C]) * bs["invstd"][gi, :C]
+            acc[0, gi, :, 0] += g[sl].sum((0, 1)).double()
+            acc[0, gi, :, 1] += (g[sl] * zh).sum((0, 1)).double()
 
 
 def wgrad(f: Dict):
@@ -231,6 +249,9 @@ def bn_bwd(f: Dict):
         n = Bg * L
         sdy = dy.sum((0, 1))
         sdyz = (dy * zh).sum((0, 1))
+        if f.get("accum") is not None:   # the first-pass sums come from the GEMMs that wrote the sources
+            acc = f["accum"].reshape(-1, G, C, 2)
+            sdy, sdyz = acc[:, g, :, 0].sum(0).float(), acc[:, g, :, 1].sum(0).float()
         dz = s * (dy - sdy / n - zh * (sdyz / n))
         dp = dz * _dact(zg, f["act"])
         dpre[sl, :, :C] = dp.to(dpre.dtype)
@@ -238,6 +259,8 @@ def bn_bwd(f: Dict):
         dgamma += sdyz
         dbeta += sdy
         dbias += dp.sum((0, 1))
+    if f.get("accum") is not None:
+        f["accum"].zero_()
     if f.get("dgamma") is not None:
         f["dgamma"].copy_(dgamma)
     if f.get("dbeta") is not None:

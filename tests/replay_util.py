@@ -62,11 +62,21 @@ def replay_pair(prog_gpu, prog_cpu, segments, teacher_force=True):
             fields = [(fld, rc.f, rg.f) for fld in OUT_FIELDS[rc.kind]]
             if rc.kind == L.OP_GEMM and (rc.f.get("stats") or {}).get("z") is not None:
                 fields += [("stats." + fld, rc.f["stats"], rg.f["stats"]) for fld in OUT_FIELDS[L.OP_BN_STATS]]
+            if rc.kind == L.OP_GEMM and (rc.f.get("bwd_sums") or {}).get("z") is not None:
+                fields += [("bwd_sums.accum", rc.f["bwd_sums"], rg.f["bwd_sums"])]
             for fld, fc, fg in fields:
                 vc, vg = fc.get(fld.split(".")[-1]), fg.get(fld.split(".")[-1])
                 if vc is None:
                     continue
                 got = vg.detach().to("cpu")
+                if fld.endswith("accum"):   # the GPU spreads its contributions over the copies: compare the sums
+                    n_copies = vc.shape[0]
+                    got = got.reshape(n_copies, -1).sum(0)
+                    vc_cmp = vc.reshape(n_copies, -1).sum(0)
+                    report.append((i, rc.tag, fld, rel_err(got.float(), vc_cmp.float())))
+                    if teacher_force:
+                        vg.copy_(vc)
+                    continue
                 if not torch.isfinite(got.float()).all():
                     report.append((i, rc.tag, fld, float("inf")))
                 else:
