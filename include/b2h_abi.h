@@ -317,6 +317,27 @@ typedef struct {
   int64_t n;
 } b2h_rot6d_t;
 
+/* inference post-processing behind save_results (utils/utils.py:388-427): per frame, the 6-D rotations of the
+ * nbones-1 joints -> rotation matrix (conversion_utils.py:86-107) -> axis-angle (conversion_utils.py:33-41)
+ * -> forward kinematics over the bone tree (conversion_utils.py:117-137): bone i starts at joint `joint[i]`,
+ * ends at joint i+1, and is the Rodrigues rotation, by the i-th axis-angle, of the unit direction from joint
+ * `before[i]` to joint `joint[i]`, scaled by bone_len[i].  Bone 0 is the root bone (joints 0 and 1 = `root`). */
+#define B2H_FK_MAX_BONES 64
+typedef struct {
+  const float* r6d;  /* [n][ld] fp32, (nbones-1)*6 values per frame */
+  int32_t ld;
+  const float* mean; /* optional per-channel de-standardisation r6d*std + mean ((nbones-1)*6 values), or NULL */
+  const float* std;
+  float* aa;         /* optional out [n][(nbones-1)*3] axis-angles, or NULL */
+  float* xyz;        /* out [n][(nbones+1)*3] */
+  int64_t n;
+  int32_t nbones;    /* <= B2H_FK_MAX_BONES */
+  int8_t joint[B2H_FK_MAX_BONES];
+  int8_t before[B2H_FK_MAX_BONES];
+  float bone_len[B2H_FK_MAX_BONES];
+  float root[6];
+} b2h_fk_t;
+
 typedef struct {
   void* ptr;
   int64_t bytes;
@@ -357,6 +378,7 @@ int b2h_bn_fold(const b2h_bn_fold_t* d, b2h_stream_t s);
 int b2h_bn_fold_multi(const b2h_bn_fold_multi_t* d, b2h_stream_t s);
 int b2h_rot6d_to_mat(const b2h_rot6d_t* d, b2h_stream_t s);
 int b2h_fill(const b2h_fill_t* d, b2h_stream_t s);
+int b2h_fk(const b2h_fk_t* d, b2h_stream_t s);
 
 /* recorded programs: the whole-graph entry points (generator forward / step, discriminator step)
  * are programs built by the host-side mirror of modelZoo and replayed with ONE call. */
@@ -364,7 +386,7 @@ typedef struct b2h_program b2h_program;
 enum b2h_op_kind {
   B2H_OP_GEMM = 1, B2H_OP_WGRAD, B2H_OP_BN_STATS, B2H_OP_BN_APPLY, B2H_OP_BN_BWD, B2H_OP_PREP,
   B2H_OP_TO_NCL, B2H_OP_L1, B2H_OP_MSE, B2H_OP_COLSUM, B2H_OP_ADAM, B2H_OP_PACK, B2H_OP_BN_FOLD,
-  B2H_OP_ROT6D, B2H_OP_FILL, B2H_OP_PACK_MULTI, B2H_OP_BN_FOLD_MULTI
+  B2H_OP_ROT6D, B2H_OP_FILL, B2H_OP_PACK_MULTI, B2H_OP_BN_FOLD_MULTI, B2H_OP_FK
 };
 b2h_program* b2h_program_create(int dtype);
 void b2h_program_destroy(b2h_program* p);

@@ -15,7 +15,7 @@ ROW_IDENT, ROW_UP2, ROW_POOL2, ROW_BCAST = 0, 1, 2, 3
 SRC_NCL, SRC_ROWS, SRC_BCAST, SRC_MOTION = 0, 1, 2, 3
 DROP_NONE, DROP_MASK, DROP_PHILOX = 0, 1, 2
 (OP_GEMM, OP_WGRAD, OP_BN_STATS, OP_BN_APPLY, OP_BN_BWD, OP_PREP, OP_TO_NCL, OP_L1, OP_MSE, OP_COLSUM,
- OP_ADAM, OP_PACK, OP_BN_FOLD, OP_ROT6D, OP_FILL, OP_PACK_MULTI, OP_BN_FOLD_MULTI) = range(1, 18)
+ OP_ADAM, OP_PACK, OP_BN_FOLD, OP_ROT6D, OP_FILL, OP_PACK_MULTI, OP_BN_FOLD_MULTI, OP_FK) = range(1, 19)
 
 i32, i64, f32, f64, vp = C.c_int32, C.c_int64, C.c_float, C.c_double, C.c_void_p
 
@@ -129,6 +129,15 @@ class Rot6d(C.Structure):
     _fields_ = [("r6d", vp), ("mat", vp), ("n", i64)]
 
 
+FK_MAX_BONES = 64
+
+
+class Fk(C.Structure):
+    _fields_ = [("r6d", vp), ("ld", i32), ("mean", vp), ("std", vp), ("aa", vp), ("xyz", vp), ("n", i64),
+                ("nbones", i32), ("joint", C.c_int8 * FK_MAX_BONES), ("before", C.c_int8 * FK_MAX_BONES),
+                ("bone_len", f32 * FK_MAX_BONES), ("root", f32 * 6)]
+
+
 class Fill(C.Structure):
     _fields_ = [("ptr", vp), ("bytes", i64), ("value", i32)]
 
@@ -136,7 +145,7 @@ class Fill(C.Structure):
 OP_STRUCT = {OP_GEMM: Gemm, OP_WGRAD: Wgrad, OP_BN_STATS: BnStats, OP_BN_APPLY: BnApply, OP_BN_BWD: BnBwd,
              OP_PREP: Prep, OP_TO_NCL: ToNcl, OP_L1: L1, OP_MSE: Mse, OP_COLSUM: Colsum, OP_ADAM: Adam,
              OP_PACK: Pack, OP_BN_FOLD: BnFold, OP_ROT6D: Rot6d, OP_FILL: Fill, OP_PACK_MULTI: PackMulti,
-             OP_BN_FOLD_MULTI: BnFoldMulti}
+             OP_BN_FOLD_MULTI: BnFoldMulti, OP_FK: Fk}
 KIND_OF = {v: k for k, v in OP_STRUCT.items()}
 
 # every symbol include/b2h_abi.h declares: name -> (restype, argtypes)
@@ -167,6 +176,7 @@ SYMBOLS = {
     "b2h_bn_fold_multi": (C.c_int, [C.POINTER(BnFoldMulti), vp]),
     "b2h_rot6d_to_mat": (C.c_int, [C.POINTER(Rot6d), vp]),
     "b2h_fill": (C.c_int, [C.POINTER(Fill), vp]),
+    "b2h_fk": (C.c_int, [C.POINTER(Fk), vp]),
     "b2h_program_create": (vp, [C.c_int]),
     "b2h_program_destroy": (None, [vp]),
     "b2h_program_add": (C.c_int, [vp, C.c_int, vp]),
@@ -180,7 +190,7 @@ ONESHOT = {OP_GEMM: ("b2h_gemm", True), OP_WGRAD: ("b2h_wgrad", True), OP_BN_STA
            OP_TO_NCL: ("b2h_to_ncl", True), OP_L1: ("b2h_l1", True), OP_MSE: ("b2h_mse", False),
            OP_COLSUM: ("b2h_colsum", True), OP_ADAM: ("b2h_adam", False), OP_PACK: ("b2h_pack", True),
            OP_BN_FOLD: ("b2h_bn_fold", False), OP_ROT6D: ("b2h_rot6d_to_mat", False), OP_FILL: ("b2h_fill", False),
-           OP_PACK_MULTI: ("b2h_pack_multi", True), OP_BN_FOLD_MULTI: ("b2h_bn_fold_multi", False)}
+           OP_PACK_MULTI: ("b2h_pack_multi", True), OP_BN_FOLD_MULTI: ("b2h_bn_fold_multi", False), OP_FK: ("b2h_fk", False)}
 
 
 class B2HError(RuntimeError):

@@ -72,6 +72,7 @@ union OpDesc {
   b2h_fill_t fill;
   b2h_pack_multi_t pack_multi;
   b2h_bn_fold_multi_t bn_fold_multi;
+  b2h_fk_t fk;
   OpDesc() { memset(this, 0, sizeof(*this)); }
 };
 
@@ -94,6 +95,7 @@ static size_t desc_size(int kind) {
     case B2H_OP_FILL: return sizeof(b2h_fill_t);
     case B2H_OP_PACK_MULTI: return sizeof(b2h_pack_multi_t);
     case B2H_OP_BN_FOLD_MULTI: return sizeof(b2h_bn_fold_multi_t);
+    case B2H_OP_FK: return sizeof(b2h_fk_t);
     default: return 0;
   }
 }
@@ -126,6 +128,7 @@ static int run_op(const Op& op, int dtype, cudaStream_t s) {
     case B2H_OP_FILL: return launch_fill(op.d.fill, s);
     case B2H_OP_PACK_MULTI: return launch_pack_multi(op.d.pack_multi, dtype, s);
     case B2H_OP_BN_FOLD_MULTI: return launch_bn_fold_multi(op.d.bn_fold_multi, s);
+    case B2H_OP_FK: return launch_fk(op.d.fk, s);
     default: set_error("unknown op kind %d", op.kind); return B2H_ERR_ARG;
   }
 }
@@ -202,6 +205,10 @@ int b2h_bn_fold(const b2h_bn_fold_t* d, b2h_stream_t s) {
 int b2h_bn_fold_multi(const b2h_bn_fold_multi_t* d, b2h_stream_t s) {
   const int dtype = B2H_F32;
   B2H_ONESHOT(B2H_OP_BN_FOLD_MULTI, bn_fold_multi, d)
+}
+int b2h_fk(const b2h_fk_t* d, b2h_stream_t s) {
+  const int dtype = B2H_F32;
+  B2H_ONESHOT(B2H_OP_FK, fk, d)
 }
 int b2h_rot6d_to_mat(const b2h_rot6d_t* d, b2h_stream_t s) {
   const int dtype = B2H_F32;

@@ -332,6 +332,7 @@ int launch_wgrad_reduce(const b2h_wgrad_t& d, int splits, cudaStream_t s);
 int launch_bn_stats(const b2h_bn_stats_t& d, int dtype, cudaStream_t s);
 int launch_bn_apply(const b2h_bn_apply_t& d, int dtype, cudaStream_t s);
 int launch_bn_bwd(const b2h_bn_bwd_t& d, int dtype, cudaStream_t s);
+int launch_fk(const b2h_fk_t& d, cudaStream_t s);
 int launch_bwd_sums_separate(const b2h_gemm_t& g, int dtype, cudaStream_t s);
 int launch_prep(const b2h_prep_t& d, int dtype, cudaStream_t s);
 int launch_to_ncl(const b2h_to_ncl_t& d, int dtype, cudaStream_t s);

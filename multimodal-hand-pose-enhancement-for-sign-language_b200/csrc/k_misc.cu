@@ -486,6 +486,108 @@ int launch_rot6d(const b2h_rot6d_t& d, cudaStream_t s) {
   return B2H_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// fk: 6-D rotations -> rotation matrix -> axis-angle -> forward kinematics, one frame per thread
+// (conversion_utils.py:33-41 log map as scipy's as_rotvec: unit quaternion, angle = 2 atan2(|v|, w), series for
+// small angles; conversion_utils.py:117-137 Rodrigues step per bone)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void r6d_to_rotvec(const float* r, float* aa) {
+  const float ax = r[0], ay = r[1], az = r[2], bx = r[3], by = r[4], bz = r[5];
+  const float na = sqrtf(ax * ax + ay * ay + az * az) + 1e-6f;
+  const float xx = ax / na, xy = ay / na, xz = az / na;
+  float zx = xy * bz - xz * by, zy = xz * bx - xx * bz, zz = xx * by - xy * bx;
+  const float nz = sqrtf(zx * zx + zy * zy + zz * zz) + 1e-6f;
+  zx /= nz, zy /= nz, zz /= nz;
+  const float yx = zy * xz - zz * xy, yy = zz * xx - zx * xz, yz = zx * xy - zy * xx;
+  // M = [x y z] as columns
+  const float m00 = xx, m01 = yx, m02 = zx, m10 = xy, m11 = yy, m12 = zy, m20 = xz, m21 = yz, m22 = zz;
+  float w, qx, qy, qz;
+  const float tr = m00 + m11 + m22;
+  if (tr > 0.f) {
+    const float s = sqrtf(tr + 1.f) * 2.f;
+    w = 0.25f * s, qx = (m21 - m12) / s, qy = (m02 - m20) / s, qz = (m10 - m01) / s;
+  } else if (m00 > m11 && m00 > m22) {
+    const float s = sqrtf(1.f + m00 - m11 - m22) * 2.f;
+    w = (m21 - m12) / s, qx = 0.25f * s, qy = (m01 + m10) / s, qz = (m02 + m20) / s;
+  } else if (m11 > m22) {
+    const float s = sqrtf(1.f + m11 - m00 - m22) * 2.f;
+    w = (m02 - m20) / s, qx = (m01 + m10) / s, qy = 0.25f * s, qz = (m12 + m21) / s;
+  } else {
+    const float s = sqrtf(1.f + m22 - m00 - m11) * 2.f;
+    w = (m10 - m01) / s, qx = (m02 + m20) / s, qy = (m12 + m21) / s, qz = 0.25f * s;
+  }
+  const float qn = rsqrtf(w * w + qx * qx + qy * qy + qz * qz);
+  w *= qn, qx *= qn, qy *= qn, qz *= qn;
+  if (w < 0.f) w = -w, qx = -qx, qy = -qy, qz = -qz;
+  const float vn = sqrtf(qx * qx + qy * qy + qz * qz);
+  const float angle = 2.f * atan2f(vn, w);
+  const float a2 = angle * angle;
+  const float scale = angle <= 1e-3f ? 2.f + a2 / 12.f + 7.f * a2 * a2 / 2880.f : angle / sinf(0.5f * angle);
+  aa[0] = scale * qx, aa[1] = scale * qy, aa[2] = scale * qz;
+}
+
+__global__ void __launch_bounds__(128) fk_kernel(b2h_fk_t d) {
+  pdl_sync();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= d.n) return;
+  float xyz[(B2H_FK_MAX_BONES + 1) * 3];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) xyz[k] = d.root[k];
+  const float* row = d.r6d + i * d.ld;
+  for (int b = 1; b < d.nbones; ++b) {
+    float r[6], aa[3];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const int c = (b - 1) * 6 + k;
+      float v = row[c];
+      if (d.mean) v = fmaf(v, d.std[c], d.mean[c]);
+      r[k] = v;
+    }
+    r6d_to_rotvec(r, aa);
+    if (d.aa) {
+      float* o = d.aa + i * (int64_t)(d.nbones - 1) * 3 + (b - 1) * 3;
+      o[0] = aa[0], o[1] = aa[1], o[2] = aa[2];
+    }
+    const int j = d.joint[b], pb = d.before[b];
+    const float jx = xyz[j * 3], jy = xyz[j * 3 + 1], jz = xyz[j * 3 + 2];
+    float ux = jx - xyz[pb * 3], uy = jy - xyz[pb * 3 + 1], uz = jz - xyz[pb * 3 + 2];
+    const float un = rsqrtf(ux * ux + uy * uy + uz * uz);
+    ux *= un, uy *= un, uz *= un;
+    const float th = sqrtf(aa[0] * aa[0] + aa[1] * aa[1] + aa[2] * aa[2]);
+    float vx = ux, vy = uy, vz = uz;
+    if (th > 0.f) {
+      const float ex = aa[0] / th, ey = aa[1] / th, ez = aa[2] / th;
+      float sn, cs;
+      sincosf(th, &sn, &cs);
+      const float dot = ex * ux + ey * uy + ez * uz;
+      const float cx = ey * uz - ez * uy, cy = ez * ux - ex * uz, cz = ex * uy - ey * ux;
+      vx = ux * cs + cx * sn + ex * dot * (1.f - cs);
+      vy = uy * cs + cy * sn + ey * dot * (1.f - cs);
+      vz = uz * cs + cz * sn + ez * dot * (1.f - cs);
+    }
+    const float len = d.bone_len[b];
+    xyz[(b + 1) * 3] = jx + len * vx;
+    xyz[(b + 1) * 3 + 1] = jy + len * vy;
+    xyz[(b + 1) * 3 + 2] = jz + len * vz;
+  }
+  float* o = d.xyz + i * (int64_t)(d.nbones + 1) * 3;
+  for (int k = 0; k < (d.nbones + 1) * 3; ++k) o[k] = xyz[k];
+}
+
+int launch_fk(const b2h_fk_t& d, cudaStream_t s) {
+  B2H_CARVE(fk_kernel);
+  B2H_CHECK_ARG(d.n > 0 && d.nbones >= 2 && d.nbones <= B2H_FK_MAX_BONES && d.ld >= (d.nbones - 1) * 6,
+                B2H_ERR_SHAPE, "fk: n=%lld nbones=%d ld=%d", (long long)d.n, d.nbones, d.ld);
+  B2H_CHECK_ARG(d.r6d && d.xyz && ((d.mean == nullptr) == (d.std == nullptr)), B2H_ERR_ARG, "fk: null pointers");
+  for (int b = 1; b < d.nbones; ++b)
+    B2H_CHECK_ARG(d.joint[b] >= 0 && d.joint[b] <= b && d.before[b] >= 0 && d.before[b] <= b &&
+                      d.joint[b] != d.before[b],
+                  B2H_ERR_ARG, "fk: bone %d must hang off joints that are already placed", b);
+  launch(fk_kernel, (unsigned)ceil_div64(d.n, 128), 128, 0, s, d);
+  B2H_LAUNCH_CHECK("fk");
+  return B2H_OK;
+}
+
 int launch_fill(const b2h_fill_t& d, cudaStream_t s) {
   B2H_CHECK_ARG(d.ptr && d.bytes >= 0, B2H_ERR_ARG, "fill: bad args");
   cudaError_t e = cudaMemsetAsync(d.ptr, d.value, (size_t)d.bytes, s);

@@ -22,7 +22,7 @@ ROW_IDENT, ROW_UP2, ROW_POOL2, ROW_BCAST = 0, 1, 2, 3
 SRC_NCL, SRC_ROWS, SRC_BCAST, SRC_MOTION = 0, 1, 2, 3
 DROP_NONE, DROP_MASK, DROP_PHILOX = 0, 1, 2
 (OP_GEMM, OP_WGRAD, OP_BN_STATS, OP_BN_APPLY, OP_BN_BWD, OP_PREP, OP_TO_NCL, OP_L1, OP_MSE, OP_COLSUM,
- OP_ADAM, OP_PACK, OP_BN_FOLD, OP_ROT6D, OP_FILL, OP_PACK_MULTI, OP_BN_FOLD_MULTI) = range(1, 18)
+ OP_ADAM, OP_PACK, OP_BN_FOLD, OP_ROT6D, OP_FILL, OP_PACK_MULTI, OP_BN_FOLD_MULTI, OP_FK) = range(1, 19)
 
 
 def _act(x, act):

@@ -1,0 +1,136 @@
+"""Post-processing path: the oracle restatement of rot6d -> axis-angle -> forward kinematics is
+pinned to the reference's own functions (where /root/reference exists) and to golden vectors produced by them; the
+CUDA op b2h_fk is checked against the oracle; and the bf16 bar of the task — MPJPE delta < 0.5 mm against the fp32
+oracle forward on a fixed anthropometric skeleton — is measured on the eval forward."""
+import importlib.util
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import fk
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = "/root/reference"
+G = np.load(os.path.join(HERE, "golden", "fk.npz"))
+
+
+def test_skeleton_tables_match_golden():
+    assert list(G["J"]) == fk.SKEL_J and list(G["B"]) == fk.SKEL_B
+
+
+def test_oracle_fk_matches_golden_vectors():
+    r6d = G["r6d"].reshape(-1, 288)
+    aa = fk.frames_to_aa(r6d)
+    assert np.abs(aa - G["aa"].reshape(-1, 144)).max() < 1e-9
+    xyz = fk.aa_to_xyz(aa, G["root"], G["bone_len"])
+    # the reference accumulates the chain in float32 (xyz_clip dtype, conversion_utils.py:122)
+    assert np.abs(xyz - G["xyz"].reshape(-1, 150)).max() < 2e-3 * 1.0   # mm, on bones of 20-300 mm
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference sources not present on this box")
+def test_oracle_fk_matches_reference_functions():
+    def load(path, name):
+        spec = importlib.util.spec_from_file_location(name, os.path.join(REF, path))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod
+    conv = load("utils/conversion_utils.py", "_ref_conv_t")
+    skel = load("3DposeEstimator/skeletalModel.py", "_ref_skel_t")
+    st = skel.getSkeletalModelStructure()
+    assert [t[0] for t in st] == fk.SKEL_J and [t[3] for t in st] == fk.SKEL_B and all(t[1] == i + 1 for i, t in enumerate(st))
+    rng = np.random.RandomState(3)
+    clip = rng.randn(5, 288)
+    aa_ref = conv.clip_rot6d_to_aa(clip)
+    assert np.abs(fk.frames_to_aa(clip) - aa_ref).max() < 1e-9
+    root, bone = fk.synthetic_skeleton_mm()
+    xyz_ref = conv.aa_to_xyz(np.array([aa_ref]), root, bone, st)[0]
+    assert np.abs(fk.aa_to_xyz(aa_ref, root, bone) - xyz_ref).max() < 2e-3
+    mats = np.stack([conv.np_rot6d_to_mat(clip[:, :6][i:i + 1])[0] for i in range(5)])
+    assert np.abs(fk.rot6d_to_mat(clip[:, :6]) - mats).max() < 1e-12
+
+
+@pytest.mark.gpu
+def test_fk_kernel_matches_oracle_and_golden():
+    from b2h_b200 import postprocess as PP
+    root, bone = G["root"], G["bone_len"]
+    r6d = G["r6d"].reshape(-1, 288)
+    xyz, aa = PP.r6d_to_xyz(r6d, root, bone, return_aa=True)
+    assert np.abs(aa.cpu().numpy() - G["aa"].reshape(-1, 144)).max() < 5e-5          # radians, fp32 log map
+    assert np.abs(xyz.cpu().numpy() - G["xyz"].reshape(-1, 150)).max() < 5e-2          # mm
+    # larger random set, with de-standardisation folded in, against the oracle
+    rng = np.random.RandomState(5)
+    z = rng.randn(4096, 288).astype(np.float32)
+    mean, std = rng.randn(288).astype(np.float32) * 0.1, (0.5 + rng.rand(288)).astype(np.float32)
+    ref = fk.r6d_to_xyz(z.astype(np.float64) * std + mean, root, bone)
+    got = PP.r6d_to_xyz(z, root, bone, mean=mean, std=std).cpu().numpy()
+    # near-antipodal rotations (angle ~ pi) are ill-conditioned in the log map but not in the positions
+    assert np.abs(got - ref).max() < 0.1, np.abs(got - ref).max()
+    assert fk.mpjpe(got, ref) < 5e-3
+    # drop-in list API of conversion_utils.rot6d_to_aa
+    clips = [z[:7, :36], z[7:12, :36]]
+    aa_list = PP.rot6d_to_aa(clips)
+    for c, a in zip(clips, aa_list):
+        ref_aa = fk.frames_to_aa(c.astype(np.float64))
+        near_pi = np.linalg.norm(ref_aa.reshape(-1, 3), axis=1) > 3.0
+        d = np.abs(a - ref_aa).reshape(-1, 3)[~near_pi]
+        assert d.max() < 1e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant,rf", [("v1", False), ("v1", True)])
+def test_bf16_eval_forward_mpjpe_below_half_millimetre(variant, rf):
+    """north_star bar: bf16 mode within 2e-2 relative AND < 0.5 mm MPJPE delta against the fp32 reference path."""
+    from b2h_b200 import data as D
+    from b2h_b200 import postprocess as PP
+    from b2h_b200.trainer import GanTrainer
+    from oracle import ref_models as R
+    torch.manual_seed(23456)
+    B, T = 16, 64
+    data = D.synthetic_r6d(64, T, seed=23456)            # (N, T, 288) raw 6-D rotations, 6 arm + 42 hand joints
+    X, Y = np.swapaxes(data[:, :, :36], 1, 2), np.swapaxes(data[:, :, 36:], 1, 2)
+    mx, sx = D.mean_std("arm", X)
+    my, sy = D.mean_std("wh", Y)
+    x = torch.from_numpy(((X[:B] - mx) / sx).astype(np.float32))
+    feats = None
+    if rf:
+        f = np.random.RandomState(1).randn(B, 512).astype(np.float32)
+        feats = torch.from_numpy(f / np.linalg.norm(f, axis=1, keepdims=True))
+    Gm = R.build_generator(variant, 36, 252, rf)
+    # a generator that predicts plausible poses: a few hundred oracle steps of L1 regression on the synthetic set
+    opt = torch.optim.Adam(Gm.parameters(), lr=1e-3)
+    xs = torch.from_numpy(((X - mx) / sx).astype(np.float32))
+    ys = torch.from_numpy(((Y - my) / sy).astype(np.float32))
+    fs = feats[:1].expand(64, -1) if rf else None
+    Gm.train()
+    for it in range(30):
+        opt.zero_grad()
+        torch.nn.functional.l1_loss(Gm(xs, feats_=fs), ys).backward()
+        opt.step()
+    Gm.eval()
+    with torch.no_grad():
+        ref = Gm(x, feats_=feats)
+    tr = GanTrainer(variant, 36, 252, rf, B, T, precision="bf16", device="cuda")
+    tr.g_store.load_state_dict(Gm.state_dict())
+    tr.load_batch(x.cuda(), torch.zeros(B, 252, T).cuda(), feats.cuda() if rf else None)
+    out = tr.infer().float().cpu()
+    assert float((out - ref).abs().max() / ref.abs().max()) < 2e-2
+    root, bone = fk.synthetic_skeleton_mm()
+    mean = np.concatenate([mx.reshape(-1), my.reshape(-1)])
+    std = np.concatenate([sx.reshape(-1), sy.reshape(-1)])
+
+    def frames(o):   # (B, 252, T) + the arm input -> (B*T, 288) standardised rows
+        full = torch.cat([x, o], dim=1)
+        return full.permute(0, 2, 1).reshape(B * T, 288).contiguous()
+    xyz_ref = PP.r6d_to_xyz(frames(ref), root, bone, mean=mean, std=std)
+    xyz_new = PP.r6d_to_xyz(frames(out), root, bone, mean=mean, std=std)
+    delta = PP.mpjpe(xyz_new, xyz_ref)
+    # the same number through the CPU oracle FK (checks the metric, not just the kernel against itself)
+    cpu_ref = fk.r6d_to_xyz(frames(ref).numpy().astype(np.float64) * std + mean, root, bone)
+    cpu_new = fk.r6d_to_xyz(frames(out).numpy().astype(np.float64) * std + mean, root, bone)
+    delta_cpu = fk.mpjpe(cpu_new, cpu_ref)
+    print(f"MPJPE delta bf16 vs fp32 oracle: {delta:.4f} mm (GPU FK), {delta_cpu:.4f} mm (oracle FK)")
+    assert abs(delta - delta_cpu) < 0.05
+    assert delta_cpu < 0.5
