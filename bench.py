@@ -73,33 +73,41 @@ def synth_batch(B, T, cin, cout, feats_kind, seed=23456):
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle restatement of train_gan's step bodies on host cores
 # ------------------------------------------------------------------------------------------------
-def run_cpu_reference(a, steps, warmup):
+def run_cpu_reference(a, steps, warmup, device="cpu", autocast=False):
+    """The oracle restatement of the reference step through stock PyTorch: on the host cores (the baseline), or —
+    device="cuda" — through PyTorch eager / cuDNN on this GPU ("the honest bar to beat")."""
     from oracle import ref_models as R
     torch.set_num_threads(os.cpu_count() or 1)
     torch.manual_seed(23456)
     cin, cout = 36, 252
     feats_kind = None if not a.feats else ("image" if a.variant == "b2h" else "text")
-    G = R.build_generator(a.variant, cin, cout, a.feats)
-    D = R.build_discriminator(cout)
+    G = R.build_generator(a.variant, cin, cout, a.feats).to(device)
+    D = R.build_discriminator(cout).to(device)
     x, y, f = synth_batch(a.batch, a.frames, cin, cout, feats_kind)
+    x, y = x.to(device), y.to(device)
+    f = f.to(device) if f is not None else None
+    sync = (lambda: torch.cuda.synchronize()) if device != "cpu" else (lambda: None)
     g_opt = torch.optim.Adam(G.parameters(), lr=1e-4)
     d_opt = torch.optim.Adam(D.parameters(), lr=1e-4)
 
     def step():
-        if a.mode == "train":
-            R.generator_step(G, D, g_opt, x, y, f)
-            R.discriminator_step(G, D, d_opt, x, y, f)
-        else:
-            G.eval()
-            with torch.no_grad():
-                G(x, feats_=f)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            if a.mode == "train":
+                R.generator_step(G, D, g_opt, x, y, f)
+                R.discriminator_step(G, D, d_opt, x, y, f)
+            else:
+                G.eval()
+                with torch.no_grad():
+                    G(x, feats_=f)
 
     for _ in range(warmup):
         step()
+    sync()
     times = []
     for _ in range(steps):
         t0 = time.perf_counter()
         step()
+        sync()
         times.append(time.perf_counter() - t0)
     med = statistics.median(times)
     return a.batch * a.frames / med, med, os.cpu_count() or 1
@@ -392,6 +400,14 @@ def main():
             line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                                     "sample": f"5 steps (+2 warm-up) of the full {B}x{T} batch through the oracle "
                                               f"restatement of train_gan (torch CPU fp32, {cores} threads)"}
+            try:   # the same port through stock PyTorch eager (cuDNN) on this GPU: the honest bar
+                e32, _, _ = run_cpu_reference(a, steps=20, warmup=5, device="cuda")
+                e16, _, _ = run_cpu_reference(a, steps=20, warmup=5, device="cuda", autocast=True)
+                line["cpu_baseline"]["same_port_torch_eager_on_this_gpu"] = {
+                    "fp32_frames_per_s": e32, "bf16_autocast_frames_per_s": e16,
+                    "note": "oracle restatement, torch eager + cuDNN, host-timed with a sync per step, 20 steps"}
+            except Exception as ex:   # never let the extra baseline break the bench line
+                line["cpu_baseline"]["same_port_torch_eager_on_this_gpu"] = {"error": str(ex)[:200]}
         print(json.dumps(line), flush=True)
     if world > 1:
         # CUDA graphs that captured NCCL kernels keep the communicator busy at interpreter teardown: leave

@@ -4,8 +4,9 @@ batched eval forward (inference.py:96-121), de-standardise (inference.py:134) an
 rotations plus their rotation matrices (libb2h `rot6d_to_mat`, utils/conversion_utils.py:86-107).
 
 One process per GPU (`torchrun --nproc-per-node N inference.py ...` shards the clips; no collective is needed),
-replacing the reference's nn.DataParallel wrap (inference.py:45-47).  The axis-angle / xyz forward kinematics
-and GIF rendering of `save_results` (utils/utils.py:388-427) are outside the hot path.
+replacing the reference's nn.DataParallel wrap (inference.py:45-47).  The axis-angle / xyz forward kinematics of
+`save_results` (utils/utils.py:388-427) run on the GPU too (libb2h `b2h_fk`, one launch); GIF rendering is out of
+scope.
 """
 from __future__ import annotations
 
@@ -93,6 +94,26 @@ def main(args):
     np.save(os.path.join(args.results_dir, f"{tag}_r6d.npy"), r6d.cpu().numpy())
     np.save(os.path.join(args.results_dir, f"{tag}_rotmat.npy"), mats.cpu().numpy())
     print(f"saved {tuple(r6d.shape)} r6d and {tuple(mats.shape)} rotation matrices to {args.results_dir}", flush=True)
+    # save_results (utils/utils.py:388-427): input + prediction -> axis-angle -> xyz over the 49-bone skeleton, with
+    # the root bone / bone lengths the reference pickles next to the data (utils/utils.py:412-419)
+    if cin + cout == 48 * 6:
+        from b2h_b200 import postprocess as PP
+        root_p, bone_p = os.path.join(args.base_path, "root.pkl"), os.path.join(args.base_path, "bone_len.pkl")
+        if os.path.exists(root_p) and os.path.exists(bone_p):
+            root, bone = b2h_data._load_pickle(root_p), b2h_data._load_pickle(bone_p)
+        elif args.synthetic:
+            bone = np.array([250, 190, 300, 260, 190, 300, 260] + 2 * ([35] + 5 * [40, 30, 25, 20]), dtype=np.float32)
+            root = np.array([0, 0, 0, 0, bone[0], 0], dtype=np.float32)
+        else:
+            root = None
+        if root is not None:
+            n = out.shape[0]
+            x_raw = torch.from_numpy(X[:n]).to(device) * torch.from_numpy(sX.astype(np.float32)).to(device) + \
+                torch.from_numpy(mX.astype(np.float32)).to(device)
+            frames = torch.cat([x_raw, pred], dim=1).permute(0, 2, 1).reshape(-1, 288).contiguous()
+            xyz = PP.r6d_to_xyz(frames, root, bone).reshape(n, -1, 150)
+            np.save(os.path.join(args.results_dir, f"{tag}_xyz.npy"), xyz.cpu().numpy())
+            print(f"saved {tuple(xyz.shape)} joint positions (b2h_fk)", flush=True)
 
 
 def build_parser():

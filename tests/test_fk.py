@@ -134,3 +134,21 @@ def test_bf16_eval_forward_mpjpe_below_half_millimetre(variant, rf):
     print(f"MPJPE delta bf16 vs fp32 oracle: {delta:.4f} mm (GPU FK), {delta_cpu:.4f} mm (oracle FK)")
     assert abs(delta - delta_cpu) < 0.05
     assert delta_cpu < 0.5
+
+
+@pytest.mark.gpu
+def test_inference_entry_point_writes_r6d_rotmat_xyz(tmp_path):
+    """inference.py end to end on synthetic clips: eval forward -> de-standardise -> rotmat + FK, all on the GPU."""
+    sys.path.insert(0, os.path.dirname(HERE))
+    import inference
+    args = inference.build_parser().parse_args(
+        ["--synthetic", "8", "--frames", "64", "--batch_size", "4", "--results_dir", str(tmp_path), "--precision", "bf16"])
+    inference.main(args)
+    r6d = np.load(tmp_path / "experiment_r6d.npy")
+    mat = np.load(tmp_path / "experiment_rotmat.npy")
+    xyz = np.load(tmp_path / "experiment_xyz.npy")
+    assert r6d.shape == (8, 64, 252) and mat.shape == (8, 64, 42, 9) and xyz.shape == (8, 64, 150)
+    assert np.isfinite(xyz).all()
+    # bone lengths are preserved by the kinematic chain
+    j = xyz.reshape(8, 64, 50, 3)
+    assert np.allclose(np.linalg.norm(j[:, :, 4] - j[:, :, 3], axis=-1), 260.0, rtol=1e-4)
