@@ -38,6 +38,9 @@ def parse():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--frames", type=int, default=64)
     ap.add_argument("--mode", default="train", choices=["train", "infer"])
+    ap.add_argument("--schedule", default="pipelined", choices=["pipelined", "sequential"],
+                    help="pipelined: each discriminator step overlaps the next generator step (GanTrainer.gan_step); "
+                         "sequential: generator_step then discriminator_step on the same batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-breakdown", action="store_true")
     return ap.parse_args()
@@ -296,13 +299,20 @@ def main():
 
     use_graph = True
 
+    pipelined = a.mode == "train" and a.schedule == "pipelined"
+
     def step():
-        if a.mode == "train":
+        if pipelined:
+            tr.gan_step(graph=use_graph)      # D step on the previous batch || G step on the current one
+        elif a.mode == "train":
             tr.generator_step(graph=use_graph)
             tr.discriminator_step(graph=use_graph)
         else:
             tr.infer()
 
+    if pipelined:                             # pipeline prologue: G0; every timed step is then [D_k || G_k+1]
+        tr.generator_step(graph=use_graph)
+        tr._sync_d_batch()
     for _ in range(max(a.warmup, 3)):
         step()
     torch.cuda.synchronize()
@@ -329,7 +339,7 @@ def main():
     h_loss = torch.empty(8, dtype=torch.float32).pin_memory()
     for _ in range(2):                     # untimed: creates the copy stream and the staging buffers
         tr.prefetch_batch(hx, hy, hf)
-        tr.swap_batch()
+        tr.swap_batch(pipelined=pipelined)
         step()
     torch.cuda.synchronize()
     if world > 1:
@@ -338,7 +348,7 @@ def main():
     t0 = time.perf_counter()
     tr.prefetch_batch(hx, hy, hf)          # batch 0; every later batch is copied while the previous one trains
     for _ in range(a.steps):
-        tr.swap_batch()
+        tr.swap_batch(pipelined=pipelined)
         tr.prefetch_batch(hx, hy, hf)      # H2D of the next step's inputs, pinned host -> staging, copy stream
         step()
         if a.mode == "train":
@@ -366,7 +376,10 @@ def main():
         "config": {"workload": workload_name(a), "global_batch": B * world, "frames": T,
                    "parallelism": f"dp{world}" if world > 1 else "single",
                    "timing": "CUDA events per step on the launch stream, 256 MiB L2 flush before every timed step, "
-                             "CUDA-graph replay, dropout = Philox"},
+                             "CUDA-graph replay, dropout = Philox",
+                   "schedule": ("pipelined: every timed step = discriminator step k overlapped with generator step "
+                                "k+1 (independent work: same results as the alternating order)") if pipelined else
+                               "sequential: generator step then discriminator step"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches) * a.steps,

@@ -100,21 +100,31 @@ class GanTrainer:
             self.d_store = nets.ParamStore(self.d_spec, dev, seed=seed + 1)
         self.g_opt = FlatAdam(self.g_store, lr)
         self.d_opt = FlatAdam(self.d_store, lr)
+        # Philox (seed, step): the generator steps use the even steps 0, 2, 4, ..., the discriminator steps the
+        # odd ones — the same numbers as one counter bumped after every step, but each network owns its
+        # counter, so a discriminator step and the next generator step can run side by side (gan_step)
         self.drop_state = torch.zeros(2, dtype=torch.int64, device=dev)
         self.drop_state[0] = seed
+        self.drop_state_d = torch.zeros(2, dtype=torch.int64, device=dev)
+        self.drop_state_d[0] = seed
+        self.drop_state_d[1] = 1
         kw = dict(drop_mode=drop_mode, drop_state=self.drop_state)
+        kw_d = dict(drop_mode=drop_mode, drop_state=self.drop_state_d)
         # generator: train plan (G step) and eval plan (D step / inference)
         self.G_train = nets.NetPlan(self.g_spec, self.g_store, B, T, self.dtype, dev, train=True, site_base=0, **kw)
         self.G_eval = nets.NetPlan(self.g_spec_eval, self.g_store, B, T, self.dtype, dev, train=False,
                                    weights_from=self.G_train)
         self.y = torch.zeros(B, out_dim, T, dtype=torch.float32, device=dev)
-        # the eval plan shares the input buffers of the train plan
+        # x / y / feats: the batch of the generator step.  xd / yd / featsd: the batch of the discriminator step
+        # (and of infer()); load_batch() fills both with the same batch, advance_batch() shifts x -> xd.
         self.x = self.G_train.x
         self.feats = self.G_train.feats
-        self._alias_inputs(self.G_eval, self.G_train)
+        self.xd = self.G_eval.x
+        self.featsd = self.G_eval.feats
+        self.yd = torch.zeros(B, out_dim, T, dtype=torch.float32, device=dev)
         # discriminator: eval plan scoring calc_motion(G_train.out); grouped train plan on (fake, real)
         self.D_train = nets.NetPlan(self.d_spec, self.d_store, 2 * B, T, self.dtype, dev, train=True, groups=2,
-                                    motion_src=[self.G_eval.out, self.y], site_base=100, **kw)
+                                    motion_src=[self.G_eval.out, self.yd], site_base=100, **kw_d)
         self.D_eval = nets.NetPlan(self.d_spec, self.d_store, B, T, self.dtype, dev, train=False,
                                    motion_src=[self.G_train.out], weights_from=self.D_train)
         self.losses = torch.zeros(8, dtype=torch.float32, device=dev)  # [l1, adv, g_total, d_loss]
@@ -123,7 +133,9 @@ class GanTrainer:
         self._comm_stream = None
         self._copy_stream = None
         self._wgrad_stream = None
+        self._wgrad_stream_d = None
         self._adv_stream = None
+        self._d_stream = None
         self.overlap_adv = os.environ.get("B2H_NO_ADV_OVERLAP") is None
         self.overlap_wgrad = os.environ.get("B2H_NO_WGRAD_OVERLAP") is None
 
@@ -139,7 +151,23 @@ class GanTrainer:
         return cls(v, cin, cout, rf, batch_size, T, precision=precision, device=dev, stores=(g_store, d_store), **kw)
 
     def load_batch(self, x, y, feats=None):
-        """Copy one batch (device or pinned-host tensors in the reference layouts) into the static buffers."""
+        """Copy one batch (device or pinned-host tensors in the reference layouts) into the static buffers: it is
+        the batch of the next generator_step(), discriminator_step() and infer()."""
+        self.x.copy_(x, non_blocking=True)
+        self.y.copy_(y, non_blocking=True)
+        if self.feats is not None:
+            self.feats.copy_(feats.reshape(self.feats.shape), non_blocking=True)
+
+    def _sync_d_batch(self):
+        self.xd.copy_(self.x, non_blocking=True)
+        self.yd.copy_(self.y, non_blocking=True)
+        if self.feats is not None:
+            self.featsd.copy_(self.feats, non_blocking=True)
+
+    def advance_batch(self, x, y, feats=None):
+        """Pipelined feeding for gan_step(): the current batch becomes the discriminator's batch, (x, y, feats)
+        the generator's."""
+        self._sync_d_batch()
         self.x.copy_(x, non_blocking=True)
         self.y.copy_(y, non_blocking=True)
         if self.feats is not None:
@@ -164,10 +192,13 @@ class GanTrainer:
         self._prefetch_done = torch.cuda.Event()
         self._prefetch_done.record(cs)
 
-    def swap_batch(self):
-        """Make the prefetched batch the current one (device-to-device copies into the static step inputs)."""
+    def swap_batch(self, pipelined: bool = False):
+        """Make the prefetched batch the current one (device-to-device copies into the static step inputs).
+        pipelined=True (gan_step feeding): the previous batch moves to the discriminator's inputs first."""
         cur = torch.cuda.current_stream(self.device)
         cur.wait_event(self._prefetch_done)
+        if pipelined:
+            self._sync_d_batch()          # the batch the generator just trained on goes to the discriminator
         self.x.copy_(self._stage[0], non_blocking=True)
         self.y.copy_(self._stage[1], non_blocking=True)
         if self.feats is not None:
@@ -258,9 +289,7 @@ class GanTrainer:
         if not self.overlap_wgrad:
             plan.prog.run_range(s, e, cur.cuda_stream)
             return False
-        if self._wgrad_stream is None:
-            self._wgrad_stream = torch.cuda.Stream(self.device)
-        side, recs, used, i = self._wgrad_stream, plan.prog.recs, False, s
+        side, recs, used, i = self._side_stream_for(plan), plan.prog.recs, False, s
         while i < e:
             is_w = recs[i].kind == L.OP_WGRAD
             j = i
@@ -277,6 +306,16 @@ class GanTrainer:
             i = j
         return used
 
+    def _side_stream_for(self, plan: nets.NetPlan):
+        """The wgrad stream of a train plan (one per network: the two backward passes of gan_step overlap)."""
+        if plan is self.D_train:
+            if self._wgrad_stream_d is None:
+                self._wgrad_stream_d = torch.cuda.Stream(self.device)
+            return self._wgrad_stream_d
+        if self._wgrad_stream is None:
+            self._wgrad_stream = torch.cuda.Stream(self.device)
+        return self._wgrad_stream
+
     def _bwd_bucketed(self, plan: nets.NetPlan):
         """Backward in buckets; each bucket's flat-gradient range is all-reduced over NCCL on a side stream while
         the next bucket computes."""
@@ -285,7 +324,7 @@ class GanTrainer:
             s, e = plan.prog.segments["bwd"]
             if self._run_bwd_ops(plan, s, e, cur):
                 ev = torch.cuda.Event()
-                ev.record(self._wgrad_stream)
+                ev.record(self._side_stream_for(plan))
                 cur.wait_event(ev)
             return
         import torch.distributed as dist
@@ -304,7 +343,7 @@ class GanTrainer:
             self._comm_stream.wait_event(ev)
             if used_side:
                 evw = torch.cuda.Event()
-                evw.record(self._wgrad_stream)
+                evw.record(self._side_stream_for(plan))
                 self._comm_stream.wait_event(evw)
             with torch.cuda.stream(self._comm_stream):
                 dist.all_reduce(st.grad[lo:hi], op=dist.ReduceOp.SUM, group=self.pg)
@@ -315,15 +354,19 @@ class GanTrainer:
             cur.wait_event(ev)
         if any_side:
             ev = torch.cuda.Event()
-            ev.record(self._wgrad_stream)
+            ev.record(self._side_stream_for(plan))
             cur.wait_event(ev)
 
     # ---- steps ---------------------------------------------------------------------------------
     # The packed (GEMM-layout) weights of a network are refreshed right after its Adam update, once per
     # step, and shared by its train and eval plans; the eval plan's only per-step preparation is folding the
     # running BN statistics (one launch).
-    def _g_ops(self):
+    def _g_ops(self, pack_after=None, adv_after=None):
+        """pack_after / adv_after: events of a concurrent discriminator step (gan_step) that the weight repack
+        (it overwrites what the D step's eval generator reads) and the D scoring branch (it wants the updated
+        discriminator) have to wait for."""
         if not self.overlap_adv:
+            assert pack_after is None and adv_after is None
             self.D_eval.prog.run("pack")      # fold D's running statistics
             self.G_train.prog.run("fwd")
             self.D_eval.prog.run("fwd")
@@ -342,6 +385,8 @@ class GanTrainer:
         fork = torch.cuda.Event()
         fork.record(cur)
         adv.wait_event(fork)
+        if adv_after is not None:
+            adv.wait_event(adv_after)
         self.D_eval.prog.run("pack", adv.cuda_stream)        # fold D's running statistics
         self.G_train.prog.run("fwd")
         fwd_done = torch.cuda.Event()
@@ -356,6 +401,8 @@ class GanTrainer:
         self.g_loss_prog.run_range(s + 1, e, adv.cuda_stream)
         self._bwd_bucketed(self.G_train)
         self.g_loss_prog.run("opt")
+        if pack_after is not None:
+            cur.wait_event(pack_after)
         self.G_train.prog.run("pack")     # repack the updated generator weights
         join = torch.cuda.Event()
         join.record(adv)
@@ -369,6 +416,64 @@ class GanTrainer:
         self._bwd_bucketed(self.D_train)
         self.d_loss_prog.run("opt")
         self.D_train.prog.run("pack")
+
+    def _gan_ops(self):
+        """[discriminator step on xd / yd] side by side with [generator step on x / y], see gan_step()."""
+        assert self.overlap_adv, "gan_step needs the adversarial scoring branch on its own stream"
+        cur = torch.cuda.current_stream(self.device)
+        if self._d_stream is None:
+            self._d_stream = torch.cuda.Stream(self.device)
+        sd = self._d_stream
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        sd.wait_event(fork)
+        with torch.cuda.stream(sd):
+            self.G_eval.prog.run("pack")      # fold G's running statistics (before the G branch updates them)
+            folded = torch.cuda.Event()
+            folded.record(sd)
+            self.G_eval.prog.run("fwd")
+            geval_done = torch.cuda.Event()   # the packed generator weights have been read
+            geval_done.record(sd)
+            self.D_train.prog.run("fwd")
+            self.d_loss_prog.run("loss")
+            self._bwd_bucketed(self.D_train)
+            self.d_loss_prog.run("opt")
+            self.D_train.prog.run("pack")
+            d_done = torch.cuda.Event()
+            d_done.record(sd)
+        cur.wait_event(folded)
+        self._g_ops(pack_after=geval_done, adv_after=d_done)
+        cur.wait_event(d_done)
+
+    def gan_step(self, graph: bool = False):
+        """One discriminator step on the batch in xd / yd / featsd — with the generator as it is now — side by
+        side with one generator step on the batch in x / y / feats.  The two are independent (the adversarial
+        term of the generator loss has no gradient; only its reported value waits for the new discriminator), so
+        generator_step(); [advance_batch(); gan_step()] * n  computes exactly the alternating schedule
+        G0, D0, G1, D1, ... of n+1 generator and n discriminator steps, each D_k on the batch of G_k with the
+        generator after G_k — with D_k overlapped with G_k+1."""
+        self._ensure_packed()
+        g = self._graphs.get("gan") if graph else None
+        if g is not None:
+            g.replay()
+        else:
+            self._gan_ops()
+            if graph:   # the eager pass above was the warm-up; capture for the next calls
+                for key in ("d", "g"):
+                    self._mark_stepped(key)
+                    self._bump_step(key)
+                torch.cuda.synchronize(self.device)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._gan_ops()
+                    self._bump_step("d")
+                    self._bump_step("g")
+                self._graphs["gan"] = g
+                return
+            self._bump_step("d")
+            self._bump_step("g")
+        for key in ("d", "g"):
+            self._mark_stepped(key)
 
     def _ensure_packed(self):
         """Weights changed from outside (load_state_dict, user edits): repack before the step."""
@@ -389,15 +494,16 @@ class GanTrainer:
     def _d_step_body(self):
         self._d_ops()
 
-    def _bump_step(self):
-        self.drop_state[1] += 1
+    def _bump_step(self, key):
+        (self.drop_state if key == "g" else self.drop_state_d)[1] += 2
 
     def generator_step(self, graph: bool = False):
         """One train_generator iteration on the batch currently in x / y / feats (train_gan.py:266-299)."""
         self._run("g", self._g_step_body, graph)
 
     def discriminator_step(self, graph: bool = False):
-        """One train_discriminator iteration (train_gan.py:221-251)."""
+        """One train_discriminator iteration (train_gan.py:221-251) on the batch currently in x / y / feats."""
+        self._sync_d_batch()
         self._run("d", self._d_step_body, graph)
 
     def _run(self, key, body, graph):
@@ -405,18 +511,18 @@ class GanTrainer:
         if not graph:
             body()
             self._mark_stepped(key)
-            self._bump_step()
+            self._bump_step(key)
             return
         g = self._graphs.get(key)
         if g is None:
             body()   # warm up eagerly (finalises programs, sets kernel attributes)
             self._mark_stepped(key)
-            self._bump_step()
+            self._bump_step(key)
             torch.cuda.synchronize(self.device)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 body()
-                self.drop_state[1] += 1
+                self._bump_step(key)
             self._graphs[key] = g
             return
         g.replay()
@@ -425,6 +531,9 @@ class GanTrainer:
     # ---- inference -----------------------------------------------------------------------------
     def infer(self):
         """Eval forward of the generator on the batch in x / feats; result in G_eval.out (inference.py:115)."""
+        self.xd.copy_(self.x, non_blocking=True)
+        if self.feats is not None:
+            self.featsd.copy_(self.feats, non_blocking=True)
         self.G_eval.forward()
         return self.G_eval.out
 

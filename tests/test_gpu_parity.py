@@ -300,3 +300,47 @@ def test_gemm_epilogue_statistics_equal_separate_pass(monkeypatch):
             # (deep layers see bf16 rounding flips of their inputs: differences compound with depth;
             # the per-layer comparison on identical inputs is test_gpu_replay.py)
             assert rel_err(m0, m1) < 2e-3 and rel_err(i0, i1) < 2e-3 and rel_err(v0, v1) < 2e-3, (name, lname)
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_pipelined_gan_step_equals_alternating_schedule(graph):
+    """gan_step() overlaps discriminator step k with generator step k+1; the two are independent, so the losses and
+    the parameters must equal those of the alternating order G0, D0, G1, D1, ... (Philox dropout included: each
+    network owns its counter)."""
+    torch.manual_seed(0)
+    B, T, n = 16, 64, 4
+    G = R.build_generator("v1", 36, 252)
+    D = R.build_discriminator(252)
+    g = torch.Generator().manual_seed(1)
+    xs = [torch.randn(B, 36, T, generator=g).cuda() for _ in range(n + 1)]
+    ys = [torch.randn(B, 252, T, generator=g).cuda() for _ in range(n + 1)]
+    # alternating reference order
+    a = make_trainer("v1", False, B, T, "fp32", G, D, drop_mode="philox")
+    l1_a, d_a = [], []
+    for k in range(n + 1):
+        a.load_batch(xs[k], ys[k])
+        a.generator_step(graph=graph)
+        l1_a.append(float(a.losses[0]))
+        if k < n:
+            a.discriminator_step(graph=graph)
+            d_a.append(float(a.losses[3]))
+    # pipelined
+    p = make_trainer("v1", False, B, T, "fp32", G, D, drop_mode="philox")
+    l1_p, d_p = [], []
+    p.load_batch(xs[0], ys[0])
+    p.generator_step(graph=graph)
+    l1_p.append(float(p.losses[0]))
+    for k in range(n):
+        p.advance_batch(xs[k + 1], ys[k + 1])
+        p.gan_step(graph=graph)
+        l1_p.append(float(p.losses[0]))
+        d_p.append(float(p.losses[3]))
+    torch.cuda.synchronize()
+    assert l1_a == pytest.approx(l1_p, rel=1e-5) and d_a == pytest.approx(d_p, rel=1e-5)
+    # parameters: equal up to the accumulation-order noise of the fp64 atomics amplified by Adam at |g| ~ 0
+    for sa, sp in ((a.g_store, p.g_store), (a.d_store, p.d_store)):
+        diff = (sa.flat - sp.flat).abs()
+        assert float(diff.max()) <= 2.05e-3 * (n + 1)          # never more than the Adam step bound (lr = 1e-3)
+        assert float((diff > 1e-6).float().mean()) < 5e-3      # and only on a handful of ~zero-gradient entries
+    # the value of the adversarial term is computed with the discriminator after D_k, as in the alternating order
+    assert float(a.losses[1]) == pytest.approx(float(p.losses[1]), rel=1e-4)

@@ -72,6 +72,7 @@ def emul_g_step(tr):
 
 
 def emul_d_step(tr):
+    tr._sync_d_batch()   # the discriminator step reads its own copy of the batch (xd / yd)
     for p, s in ((tr.G_train.prog, "pack"), (tr.G_eval.prog, "pack"), (tr.D_train.prog, "pack"),
                  (tr.G_eval.prog, "fwd"), (tr.D_train.prog, "fwd"),
                  (tr.d_loss_prog, "loss"), (tr.D_train.prog, "bwd"), (tr.d_loss_prog, "opt")):
