@@ -361,12 +361,14 @@ class GanTrainer:
     # The packed (GEMM-layout) weights of a network are refreshed right after its Adam update, once per
     # step, and shared by its train and eval plans; the eval plan's only per-step preparation is folding the
     # running BN statistics (one launch).
-    def _g_ops(self, pack_after=None, adv_after=None):
+    def _g_ops(self, pack_after=None, adv_after=None, deferred_adv=None):
         """pack_after / adv_after: events of a concurrent discriminator step (gan_step) that the weight repack
         (it overwrites what the D step's eval generator reads) and the D scoring branch (it wants the updated
-        discriminator) have to wait for."""
+        discriminator) have to wait for.  deferred_adv = (prep_done, adv_done): the scoring of THIS step is left
+        to the next gan_step; the scoring of the previous step is in flight on the adv stream and must have read
+        G_train.out (prep_done) before this forward overwrites it and losses[0] (adv_done) before L1 does."""
         if not self.overlap_adv:
-            assert pack_after is None and adv_after is None
+            assert pack_after is None and adv_after is None and deferred_adv is None
             self.D_eval.prog.run("pack")      # fold D's running statistics
             self.G_train.prog.run("fwd")
             self.D_eval.prog.run("fwd")
@@ -379,9 +381,23 @@ class GanTrainer:
         # score): scoring the fake with D only produces a reported VALUE.  It runs as a parallel
         # branch (side stream) next to L1 -> backward -> Adam instead of in front of them.
         cur = torch.cuda.current_stream(self.device)
-        if self._adv_stream is None:
-            self._adv_stream = torch.cuda.Stream(self.device)
-        adv = self._adv_stream
+        ls, le = self.g_loss_prog.segments["loss"]             # [l1, adv]
+        if deferred_adv is not None:
+            prep_done, adv_done = deferred_adv
+            fs, fe = self.G_train.prog.segments["fwd"]
+            assert self.G_train.prog.recs[fe - 1].kind == L.OP_TO_NCL
+            self.G_train.prog.run_range(fs, fe - 1, cur.cuda_stream)
+            cur.wait_event(prep_done)
+            self.G_train.prog.run_range(fe - 1, fe, cur.cuda_stream)   # writes G_train.out
+            cur.wait_event(adv_done)
+            self.g_loss_prog.run_range(ls, ls + 1, cur.cuda_stream)
+            self._bwd_bucketed(self.G_train)
+            self.g_loss_prog.run("opt")
+            if pack_after is not None:
+                cur.wait_event(pack_after)
+            self.G_train.prog.run("pack")
+            return
+        adv = self._get_adv_stream()
         fork = torch.cuda.Event()
         fork.record(cur)
         adv.wait_event(fork)
@@ -393,12 +409,11 @@ class GanTrainer:
         fwd_done.record(cur)
         adv.wait_event(fwd_done)
         self.D_eval.prog.run("fwd", adv.cuda_stream)
-        s, e = self.g_loss_prog.segments["loss"]             # [l1, adv]
-        self.g_loss_prog.run_range(s, s + 1, cur.cuda_stream)
+        self.g_loss_prog.run_range(ls, ls + 1, cur.cuda_stream)
         l1_done = torch.cuda.Event()
         l1_done.record(cur)
         adv.wait_event(l1_done)                              # total = l1 + adv
-        self.g_loss_prog.run_range(s + 1, e, adv.cuda_stream)
+        self.g_loss_prog.run_range(ls + 1, le, adv.cuda_stream)
         self._bwd_bucketed(self.G_train)
         self.g_loss_prog.run("opt")
         if pack_after is not None:
@@ -407,6 +422,29 @@ class GanTrainer:
         join = torch.cuda.Event()
         join.record(adv)
         cur.wait_event(join)
+
+    def _get_adv_stream(self):
+        if self._adv_stream is None:
+            self._adv_stream = torch.cuda.Stream(self.device)
+        return self._adv_stream
+
+    def _score_previous_g_step(self, adv):
+        """On stream `adv`: the adversarial value of the generator step whose output is in G_train.out, with the
+        discriminator as it is now.  Returns (folded, prep_done, done) events."""
+        self.D_eval.prog.run("pack", adv.cuda_stream)
+        folded = torch.cuda.Event()
+        folded.record(adv)
+        s, e = self.D_eval.prog.segments["fwd"]
+        assert self.D_eval.prog.recs[s].kind == L.OP_PREP
+        self.D_eval.prog.run_range(s, s + 1, adv.cuda_stream)      # reads G_train.out
+        prep_done = torch.cuda.Event()
+        prep_done.record(adv)
+        self.D_eval.prog.run_range(s + 1, e, adv.cuda_stream)
+        ls, le = self.g_loss_prog.segments["loss"]
+        self.g_loss_prog.run_range(ls + 1, le, adv.cuda_stream)    # adv, total = losses[0] + adv
+        done = torch.cuda.Event()
+        done.record(adv)
+        return folded, prep_done, done
 
     def _d_ops(self):
         self.G_eval.prog.run("pack")      # fold G's running statistics
@@ -417,7 +455,7 @@ class GanTrainer:
         self.d_loss_prog.run("opt")
         self.D_train.prog.run("pack")
 
-    def _gan_ops(self):
+    def _gan_ops(self, lag_adv: bool):
         """[discriminator step on xd / yd] side by side with [generator step on x / y], see gan_step()."""
         assert self.overlap_adv, "gan_step needs the adversarial scoring branch on its own stream"
         cur = torch.cuda.current_stream(self.device)
@@ -427,6 +465,13 @@ class GanTrainer:
         fork = torch.cuda.Event()
         fork.record(cur)
         sd.wait_event(fork)
+        adv_folded = adv_prep = adv_done = None
+        if lag_adv:
+            # third branch: the adversarial VALUE of the previous generator step (D is exactly what that step's
+            # alternating-order scoring would see: the discriminator step before this one has completed)
+            adv = self._get_adv_stream()
+            adv.wait_event(fork)
+            adv_folded, adv_prep, adv_done = self._score_previous_g_step(adv)
         with torch.cuda.stream(sd):
             self.G_eval.prog.run("pack")      # fold G's running statistics (before the G branch updates them)
             folded = torch.cuda.Event()
@@ -434,30 +479,50 @@ class GanTrainer:
             self.G_eval.prog.run("fwd")
             geval_done = torch.cuda.Event()   # the packed generator weights have been read
             geval_done.record(sd)
+            if lag_adv:
+                sd.wait_event(adv_folded)     # D_train's forward updates the running statistics the fold reads
             self.D_train.prog.run("fwd")
             self.d_loss_prog.run("loss")
             self._bwd_bucketed(self.D_train)
+            if lag_adv:
+                sd.wait_event(adv_done)       # Adam / repack change what the scoring branch reads
             self.d_loss_prog.run("opt")
             self.D_train.prog.run("pack")
             d_done = torch.cuda.Event()
             d_done.record(sd)
         cur.wait_event(folded)
-        self._g_ops(pack_after=geval_done, adv_after=d_done)
+        if lag_adv:
+            self._g_ops(pack_after=geval_done, deferred_adv=(adv_prep, adv_done))
+        else:
+            self._g_ops(pack_after=geval_done, adv_after=d_done)
         cur.wait_event(d_done)
 
-    def gan_step(self, graph: bool = False):
+    def flush_adv(self):
+        """gan_step(lag_adv=True) leaves the adversarial value of its generator step to the next call; this
+        computes it now (losses[1], losses[2]) — call after the last gan_step of a sequence."""
+        cur = torch.cuda.current_stream(self.device)
+        self._score_previous_g_step(cur)
+
+    def gan_step(self, graph: bool = False, lag_adv: bool = True):
         """One discriminator step on the batch in xd / yd / featsd — with the generator as it is now — side by
         side with one generator step on the batch in x / y / feats.  The two are independent (the adversarial
         term of the generator loss has no gradient; only its reported value waits for the new discriminator), so
         generator_step(); [advance_batch(); gan_step()] * n  computes exactly the alternating schedule
         G0, D0, G1, D1, ... of n+1 generator and n discriminator steps, each D_k on the batch of G_k with the
-        generator after G_k — with D_k overlapped with G_k+1."""
+        generator after G_k — with D_k overlapped with G_k+1.
+
+        lag_adv (default): the reported VALUE of the adversarial term of a generator step (losses[1], and
+        losses[2] = l1 + adv) needs the discriminator step that runs beside it, so it is computed at the start of
+        the NEXT gan_step (or by flush_adv()) instead of at the end of this one: after the call losses[0] / [3]
+        belong to this call's steps, losses[1] / [2] to the previous generator step.  lag_adv=False keeps all
+        four current at the price of a serial tail."""
         self._ensure_packed()
-        g = self._graphs.get("gan") if graph else None
+        gkey = "gan_lag" if lag_adv else "gan"
+        g = self._graphs.get(gkey) if graph else None
         if g is not None:
             g.replay()
         else:
-            self._gan_ops()
+            self._gan_ops(lag_adv)
             if graph:   # the eager pass above was the warm-up; capture for the next calls
                 for key in ("d", "g"):
                     self._mark_stepped(key)
@@ -465,10 +530,10 @@ class GanTrainer:
                 torch.cuda.synchronize(self.device)
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
-                    self._gan_ops()
+                    self._gan_ops(lag_adv)
                     self._bump_step("d")
                     self._bump_step("g")
-                self._graphs["gan"] = g
+                self._graphs[gkey] = g
                 return
             self._bump_step("d")
             self._bump_step("g")

@@ -302,11 +302,11 @@ def test_gemm_epilogue_statistics_equal_separate_pass(monkeypatch):
             assert rel_err(m0, m1) < 2e-3 and rel_err(i0, i1) < 2e-3 and rel_err(v0, v1) < 2e-3, (name, lname)
 
 
-@pytest.mark.parametrize("graph", [False, True])
-def test_pipelined_gan_step_equals_alternating_schedule(graph):
+@pytest.mark.parametrize("graph,lag", [(False, False), (True, False), (False, True), (True, True)])
+def test_pipelined_gan_step_equals_alternating_schedule(graph, lag):
     """gan_step() overlaps discriminator step k with generator step k+1; the two are independent, so the losses and
     the parameters must equal those of the alternating order G0, D0, G1, D1, ... (Philox dropout included: each
-    network owns its counter)."""
+    network owns its counter).  With lag_adv the adversarial value of a generator step arrives one call later."""
     torch.manual_seed(0)
     B, T, n = 16, 64, 4
     G = R.build_generator("v1", 36, 252)
@@ -316,31 +316,38 @@ def test_pipelined_gan_step_equals_alternating_schedule(graph):
     ys = [torch.randn(B, 252, T, generator=g).cuda() for _ in range(n + 1)]
     # alternating reference order
     a = make_trainer("v1", False, B, T, "fp32", G, D, drop_mode="philox")
-    l1_a, d_a = [], []
+    l1_a, d_a, adv_a = [], [], []
     for k in range(n + 1):
         a.load_batch(xs[k], ys[k])
         a.generator_step(graph=graph)
         l1_a.append(float(a.losses[0]))
+        adv_a.append(float(a.losses[1]))
         if k < n:
             a.discriminator_step(graph=graph)
             d_a.append(float(a.losses[3]))
     # pipelined
     p = make_trainer("v1", False, B, T, "fp32", G, D, drop_mode="philox")
-    l1_p, d_p = [], []
+    l1_p, d_p, adv_p = [], [], []
     p.load_batch(xs[0], ys[0])
     p.generator_step(graph=graph)
     l1_p.append(float(p.losses[0]))
+    if not lag:
+        adv_p.append(float(p.losses[1]))
     for k in range(n):
         p.advance_batch(xs[k + 1], ys[k + 1])
-        p.gan_step(graph=graph)
+        p.gan_step(graph=graph, lag_adv=lag)
         l1_p.append(float(p.losses[0]))
         d_p.append(float(p.losses[3]))
+        adv_p.append(float(p.losses[1]))          # lag: the value of generator step k, else of step k+1
+    if lag:
+        p.flush_adv()
+        adv_p.append(float(p.losses[1]))
+        assert float(p.losses[2]) == pytest.approx(l1_p[-1] + adv_p[-1], rel=1e-6)
     torch.cuda.synchronize()
     assert l1_a == pytest.approx(l1_p, rel=1e-5) and d_a == pytest.approx(d_p, rel=1e-5)
+    assert adv_a == pytest.approx(adv_p, rel=1e-4)
     # parameters: equal up to the accumulation-order noise of the fp64 atomics amplified by Adam at |g| ~ 0
     for sa, sp in ((a.g_store, p.g_store), (a.d_store, p.d_store)):
         diff = (sa.flat - sp.flat).abs()
         assert float(diff.max()) <= 2.05e-3 * (n + 1)          # never more than the Adam step bound (lr = 1e-3)
         assert float((diff > 1e-6).float().mean()) < 5e-3      # and only on a handful of ~zero-gradient entries
-    # the value of the adversarial term is computed with the discriminator after D_k, as in the alternating order
-    assert float(a.losses[1]) == pytest.approx(float(p.losses[1]), rel=1e-4)
