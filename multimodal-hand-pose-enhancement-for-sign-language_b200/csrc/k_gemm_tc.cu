@@ -919,7 +919,12 @@ int plan_wgrad_bf16(const b2h_wgrad_t& d, TcWgradPlan* plan) {
   while (wn > 64 && (int64_t)ceil_div(d.Mpad, WG_BM) * (d.Npad / wn) * d.ntaps * std::max(1, p.total_kb / 8) < sms) wn >>= 1;
   plan->WN = wn;
   int64_t tiles = (int64_t)ceil_div(d.Mpad, WG_BM) * (d.Npad / wn) * d.ntaps;
-  int splits = d.splits > 0 ? d.splits : (int)std::max<int64_t>(1, (sms + tiles - 1) / tiles);
+  // split-K target: CTAs per launch.  The weight gradients run beside the dgrad chain, so the launch does not
+  // have to fill the machine on its own; fewer, longer CTAs cost less SM time (fixed per-CTA overhead, fp32
+  // partial planes) at the price of a longer launch.
+  int target = sms;
+  if (const char* e = getenv("B2H_WGRAD_CTAS")) target = std::min(sms, std::max(1, atoi(e)));
+  int splits = d.splits > 0 ? d.splits : (int)std::max<int64_t>(1, (target + tiles - 1) / tiles);
   if (splits > p.total_kb) splits = p.total_kb;
   if (splits > 64) splits = 64;
   p.kb_per_split = ceil_div(p.total_kb, splits);

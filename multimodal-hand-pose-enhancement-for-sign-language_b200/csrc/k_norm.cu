@@ -335,7 +335,7 @@ __device__ __forceinline__ void add_grad_simple8(const b2h_grad_src_t& gs, int r
 // `reg`: the source row is a pure function of `row` (IDENT, or UP2 with an even consumer length == 2*L)
 template <typename T>
 __device__ __forceinline__ void add_grad_src8(const b2h_bn_bwd_t& d, const b2h_grad_src_t& gs, bool reg, const F8& sc,
-                                              const F8& sh, const F8& zown, int row, int c0, F8& dy) {
+                                              const F8& sh, const F8& zown, const F8& zpart, int row, int c0, F8& dy) {
   if (gs.rowmap == B2H_ROW_IDENT) {
     const F8 g = load_g8<T>(gs, row, c0);
 #pragma unroll
@@ -346,6 +346,20 @@ __device__ __forceinline__ void add_grad_src8(const b2h_bn_bwd_t& d, const b2h_g
     const F8 g0 = load_g8<T>(gs, 2 * (int64_t)row, c0), g1 = load_g8<T>(gs, 2 * (int64_t)row + 1, c0);
 #pragma unroll
     for (int i = 0; i < 8; ++i) dy.v[i] += g0.v[i] + g1.v[i];
+    return;
+  }
+  if (gs.rowmap == B2H_ROW_POOL2 && reg) {
+    // regular pooling (L even, L_src == L/2): pooled row = row/2, pair partner = row^1 (a row this thread holds
+    // already: zpart) — no per-row division, no second z load
+    const F8& zp = zpart;
+    const F8 g = load_g8<T>(gs, (int64_t)(row >> 1), c0);
+    const bool even = (row & 1) == 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float yo = fmaf(zown.v[i], sc.v[i], sh.v[i]), yp = fmaf(zp.v[i], sc.v[i], sh.v[i]);
+      const bool sel = even ? !(yp > yo) : (yo > yp);
+      if (sel) dy.v[i] += g.v[i];
+    }
     return;
   }
   const int b = row / d.L, l = row - b * d.L;
@@ -381,10 +395,11 @@ __device__ __forceinline__ void add_grad_src8(const b2h_bn_bwd_t& d, const b2h_g
 }
 
 // Pass 1 only accumulates (fp64 atomics into kCopiesBwd1 copies, no ticket: its CTAs retire as soon as their
-// reds are issued).  Pass 2 starts by summing those copies for the channels of its CTA, writes dpre, accumulates
-// the bias gradient the same way, and its LAST CTA (ticket) writes dgamma / dbeta / dbias / sums and re-zeroes
-// both accumulator regions.  SIMPLE: every gradient source is IDENT or a regular UP2 (no per-row div / pooling
-// branches in the code).
+// reds are issued) — or is skipped altogether when the dgrad GEMMs that wrote the gradient sources produced the
+// sums (b2h_gemm_t.bwd_sums -> d.accum).  Pass 2 starts by summing those copies for the channels of its CTA,
+// writes dpre, accumulates the bias gradient the same way, and its LAST CTA (ticket) writes dgamma / dbeta /
+// dbias / sums and re-zeroes both accumulator regions.  SIMPLE: every gradient source is IDENT or a regular UP2
+// (no per-row div / pooling branches in the code).
 constexpr int kCopiesBwd1 = B2H_BWD_COPIES;
 
 template <typename T, int PASS, bool SIMPLE>
@@ -423,9 +438,11 @@ __global__ void __launch_bounds__(kRowThreads, 2) bn_bwd_kernel(b2h_bn_bwd_t d) 
     const bool live = c0 < d.C;
     const bool two = d.ngsrc > 1;
     const bool reg0 = d.gsrc[0].rowmap == B2H_ROW_IDENT ||
-                      (d.gsrc[0].rowmap == B2H_ROW_UP2 && (d.gsrc[0].L_src & 1) == 0 && d.gsrc[0].L_src == 2 * d.L);
+                      (d.gsrc[0].rowmap == B2H_ROW_UP2 && (d.gsrc[0].L_src & 1) == 0 && d.gsrc[0].L_src == 2 * d.L) ||
+                      (d.gsrc[0].rowmap == B2H_ROW_POOL2 && (d.L & 1) == 0 && 2 * d.gsrc[0].L_src == d.L);
     const bool reg1 = d.gsrc[1].rowmap == B2H_ROW_IDENT ||
-                      (d.gsrc[1].rowmap == B2H_ROW_UP2 && (d.gsrc[1].L_src & 1) == 0 && d.gsrc[1].L_src == 2 * d.L);
+                      (d.gsrc[1].rowmap == B2H_ROW_UP2 && (d.gsrc[1].L_src & 1) == 0 && d.gsrc[1].L_src == 2 * d.L) ||
+                      (d.gsrc[1].rowmap == B2H_ROW_POOL2 && (d.L & 1) == 0 && 2 * d.gsrc[1].L_src == d.L);
     // all per-channel arrays are zero in the channel padding -> no per-element guards below
     F8 sc = zero8(), sh = zero8(), mean8 = zero8(), istd8 = zero8(), mdy = zero8(), mdyz = zero8();
     if (live) {
@@ -449,15 +466,19 @@ __global__ void __launch_bounds__(kRowThreads, 2) bn_bwd_kernel(b2h_bn_bwd_t d) 
 #pragma unroll
     for (int u = 0; u < kRPT; ++u) {
       zo[u] = dy[u] = zero8();
+      if (r0 + u < rpg && live) zo[u] = load8<T>(z + (int64_t)(g * rpg + r0 + u) * d.bn.ld);
+    }
+#pragma unroll
+    for (int u = 0; u < kRPT; ++u) {
       if (r0 + u < rpg && live) {
         const int row = g * rpg + r0 + u;
-        zo[u] = load8<T>(z + (int64_t)row * d.bn.ld);
         if (SIMPLE) {
           add_grad_simple8<T>(d.gsrc[0], row, c0, dy[u]);
           if (two) add_grad_simple8<T>(d.gsrc[1], row, c0, dy[u]);
         } else {
-          add_grad_src8<T>(d, d.gsrc[0], reg0, sc, sh, zo[u], row, c0, dy[u]);
-          if (two) add_grad_src8<T>(d, d.gsrc[1], reg1, sc, sh, zo[u], row, c0, dy[u]);
+          // (regular pooling: rows per group and r0 are even, so the pair partner row^1 is zo[u^1])
+          add_grad_src8<T>(d, d.gsrc[0], reg0, sc, sh, zo[u], zo[u ^ 1], row, c0, dy[u]);
+          if (two) add_grad_src8<T>(d, d.gsrc[1], reg1, sc, sh, zo[u], zo[u ^ 1], row, c0, dy[u]);
         }
       }
     }
