@@ -924,7 +924,9 @@ int plan_wgrad_bf16(const b2h_wgrad_t& d, TcWgradPlan* plan) {
   // partial planes) at the price of a longer launch.
   int target = sms;
   if (const char* e = getenv("B2H_WGRAD_CTAS")) target = std::min(sms, std::max(1, atoi(e)));
-  int splits = d.splits > 0 ? d.splits : (int)std::max<int64_t>(1, (target + tiles - 1) / tiles);
+  // WN = 256 runs one CTA per SM: a grid of target+1 CTAs would take two waves, so round the split count down
+  int splits = d.splits > 0 ? d.splits
+               : (int)std::max<int64_t>(1, wn == 256 ? target / tiles : (target + tiles - 1) / tiles);
   if (splits > p.total_kb) splits = p.total_kb;
   if (splits > 64) splits = 64;
   p.kb_per_split = ceil_div(p.total_kb, splits);
