@@ -365,8 +365,9 @@ def main():
     frames = B * T * world * a.steps
     value = frames / (dev_ms * 1e-3)
     e2e_value = frames / (e2e_ms * 1e-3)
-    h2d = hx.numel() * 4 + hy.numel() * 4 + (hf.numel() * 4 if hf is not None else 0)
-    d2h = 32 if a.mode == "train" else tr.G_eval.out.numel() * 4
+    # whole-job bytes per step (every rank copies its own batch)
+    h2d = (hx.numel() * 4 + hy.numel() * 4 + (hf.numel() * 4 if hf is not None else 0)) * world
+    d2h = (32 if a.mode == "train" else tr.G_eval.out.numel() * 4) * world
     launches = tr.launches_per_gan_step() if a.mode == "train" else tr.G_eval.prog.segment_launches.get("fwd", 0)
     line = {
         "metric": "training frames/sec" if a.mode == "train" else "inference frames/sec",
