@@ -914,6 +914,7 @@ int plan_wgrad_bf16(const b2h_wgrad_t& d, TcWgradPlan* plan) {
     wn = 256;
   else if (d.Npad % 128 == 0)
     wn = 128;
+  if (const char* e = getenv("B2H_WGRAD_MAX_WN")) wn = std::min(wn, std::max(64, atoi(e)));   // tuning aid
   // prefer more tiles over wider tiles when the grid would not fill the machine
   const int sms = sm_count();
   while (wn > 64 && (int64_t)ceil_div(d.Mpad, WG_BM) * (d.Npad / wn) * d.ntaps * std::max(1, p.total_kb / 8) < sms) wn >>= 1;
