@@ -272,6 +272,9 @@ typedef struct {
   float gscale;
   int64_t* step;  /* device; incremented by this op BEFORE use (t = ++step) */
   float* scalars; /* device workspace, 2 floats: the step's bias-correction scalars */
+  int32_t phase;  /* 0: whole update (advance the step, then update n elements);  1: only advance the step and
+                     refresh `scalars` (n ignored);  2: only update n elements with the current `scalars` — one
+                     phase-1 call followed by phase-2 calls over disjoint ranges (gradient buckets) is phase 0 */
 } b2h_adam_t;
 
 /* weight repack: out[(ph*Opad + o)][t][i] = W[o*o_stride + i*i_stride + tapmap[ph][t]*k_stride]

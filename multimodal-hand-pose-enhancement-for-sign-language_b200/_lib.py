@@ -103,7 +103,7 @@ class Colsum(C.Structure):
 
 class Adam(C.Structure):
     _fields_ = [("p", vp), ("g", vp), ("m", vp), ("v", vp), ("n", i64),
-                ("lr", f64), ("beta1", f64), ("beta2", f64), ("eps", f64), ("gscale", f32), ("step", vp), ("scalars", vp)]
+                ("lr", f64), ("beta1", f64), ("beta2", f64), ("eps", f64), ("gscale", f32), ("step", vp), ("scalars", vp), ("phase", i32)]
 
 
 class Pack(C.Structure):

@@ -351,12 +351,16 @@ __global__ void __launch_bounds__(256) adam_kernel(b2h_adam_t d) {
 int launch_adam(const b2h_adam_t& d, cudaStream_t s) {
   B2H_CARVE(adam_step_kernel);
   B2H_CARVE(adam_kernel);
-  B2H_CHECK_ARG(d.n > 0 && d.step && d.scalars, B2H_ERR_ARG, "adam: bad args");
+  B2H_CHECK_ARG(d.step && d.scalars && d.phase >= 0 && d.phase <= 2 && (d.phase == 1 || d.n > 0), B2H_ERR_ARG,
+                "adam: bad args");
+  if (d.phase != 2) {
+    launch(adam_step_kernel, 1, 1, 0, s, d);
+    B2H_LAUNCH_CHECK("adam_step");
+    if (d.phase == 1) return B2H_OK;
+  }
   B2H_CHECK_ARG(((uintptr_t)d.p % 16 == 0) && ((uintptr_t)d.g % 16 == 0) && ((uintptr_t)d.m % 16 == 0) &&
                     ((uintptr_t)d.v % 16 == 0),
                 B2H_ERR_ALIGN, "adam: buffers must be 16-byte aligned");
-  launch(adam_step_kernel, 1, 1, 0, s, d);
-  B2H_LAUNCH_CHECK("adam_step");
   int blocks = (int)std::min<int64_t>(ceil_div64(d.n / 4 + 1, 256), (int64_t)sm_count() * 8);
   launch(adam_kernel, blocks, 256, 0, s, d);
   B2H_LAUNCH_CHECK("adam");

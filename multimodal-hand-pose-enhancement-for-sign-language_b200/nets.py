@@ -569,6 +569,27 @@ class NetPlan:
         self.prog.add(L.OP_BN_FOLD_MULTI, "fold_multi", descs=self.fold_table, n=len(items),
                       max_cpad=max(it["Cpad"] for it in items), _items=items)
 
+    def add_pack_buckets(self, layer_sets) -> List[str]:
+        """One extra repack op per set of layer names (segments 'pack_b0', 'pack_b1', ...): the buckets of a
+        bucketed optimizer step repack their own layers as soon as their parameters are updated."""
+        from .program import _fill_struct
+        segs = []
+        for bi, names in enumerate(layer_sets):
+            items = [it for it in self._pack_items if it["_tag"].split(".", 1)[1].rsplit(".", 1)[0] in names]
+            seg = f"pack_b{bi}"
+            with self.prog.segment(seg):
+                if items:
+                    raw = bytearray()
+                    for it in items:
+                        raw += bytes(_fill_struct(L.Pack(), {k: v for k, v in it.items() if not k.startswith("_")}))
+                    table = torch.frombuffer(raw, dtype=torch.uint8).clone().to(self.device)
+                    self._bucket_tables = getattr(self, "_bucket_tables", []) + [table]
+                    self.prog.add(L.OP_PACK_MULTI, seg, descs=table, n=len(items),
+                                  max_elems=max(it["nphase"] * it["Opad"] * it["ntaps"] * it["Ipad"] for it in items),
+                                  _items=items)
+            segs.append(seg)
+        return segs
+
     def _emit_pack(self, l: Layer):
         P, st, lb = self.prog, self.store, self.bufs[l.name]
         src = self.weights_from.bufs.get(l.name) if self.weights_from is not None else None

@@ -41,10 +41,15 @@ class FlatAdam:
         self.step = torch.zeros(1, dtype=torch.int64, device=dev)
         self.scalars = torch.zeros(2, dtype=torch.float32, device=dev)
 
-    def record(self, prog: Program, gscale: float = 1.0):
-        return prog.add(L.OP_ADAM, "adam", p=self.store.flat, g=self.store.grad, m=self.m, v=self.v, n=self.store.n,
-                        lr=self.lr, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, gscale=float(gscale),
-                        step=self.step, scalars=self.scalars)
+    def record(self, prog: Program, gscale: float = 1.0, lo: int = 0, hi: Optional[int] = None, phase: int = 0,
+               tag: str = "adam"):
+        """phase 0: the whole update.  phase 1: only advance the step / bias corrections.  phase 2: update the
+        flat range [lo, hi) with the current bias corrections (gradient buckets)."""
+        hi = self.store.n if hi is None else hi
+        return prog.add(L.OP_ADAM, tag, p=self.store.flat[lo:hi], g=self.store.grad[lo:hi], m=self.m[lo:hi],
+                        v=self.v[lo:hi], n=max(hi - lo, 0 if phase == 1 else 1), lr=self.lr, beta1=self.betas[0],
+                        beta2=self.betas[1], eps=self.eps, gscale=float(gscale), step=self.step, scalars=self.scalars,
+                        phase=phase)
 
     def state_dict(self):
         st = self.store
@@ -82,7 +87,7 @@ class GanTrainer:
     def __init__(self, variant: str = "v1", in_dim: int = 36, out_dim: int = 252, require_feats: bool = False,
                  batch_size: int = 256, T: int = 64, precision: str = "bf16", device="cuda", lr: float = 1e-4,
                  seed: int = 23456, drop_mode: str = "philox", label_smooth: bool = False,
-                 world_size: int = 1, process_group=None, n_buckets: int = 2, stores=None):
+                 world_size: int = 1, process_group=None, n_buckets: int = 3, stores=None):
         self.device = torch.device(device)
         self.B, self.T, self.precision = batch_size, T, precision
         self.dtype = dtype_of(precision)
@@ -129,6 +134,7 @@ class GanTrainer:
                                    motion_src=[self.G_train.out], weights_from=self.D_train)
         self.losses = torch.zeros(8, dtype=torch.float32, device=dev)  # [l1, adv, g_total, d_loss]
         self._build_loss_programs(label_smooth)
+        self._build_bucket_programs()
         self._graphs: Dict[str, torch.cuda.CUDAGraph] = {}
         self._comm_stream = None
         self._copy_stream = None
@@ -137,6 +143,8 @@ class GanTrainer:
         self._adv_stream = None
         self._d_stream = None
         self._g_stream = None
+        self._opt_streams = {}
+        self.bucketed_opt = os.environ.get("B2H_NO_BUCKETED_OPT") is None
         self.overlap_adv = os.environ.get("B2H_NO_ADV_OVERLAP") is None
         self.overlap_wgrad = os.environ.get("B2H_NO_WGRAD_OVERLAP") is None
 
@@ -249,6 +257,77 @@ class GanTrainer:
         with P.segment("opt"):
             self.d_opt.record(P, gscale=1.0 / self.world_size)
 
+    def _build_bucket_programs(self):
+        """Per network: the optimizer step split along the gradient buckets of the backward (Adam over the flat
+        range of a bucket + the repack of its layers), so that the update of the late layers runs beside the
+        backward of the early ones; only the last bucket's update stays on the dependency chain."""
+        self._buckets = {}
+        for key, plan, opt in (("g", self.G_train, self.g_opt), ("d", self.D_train, self.d_opt)):
+            bp = self.bucket_plan(plan)
+            P = Program(self.dtype, self.device)
+            with P.segment("step"):
+                opt.record(P, phase=1, tag="adam_step")
+            for i, (_, _, lo, hi, _) in enumerate(bp):
+                with P.segment(f"b{i}"):
+                    if hi > lo:
+                        opt.record(P, gscale=1.0 / self.world_size, lo=lo, hi=hi, phase=2, tag=f"adam_b{i}")
+            packs = plan.add_pack_buckets([names for *_, names in bp])
+            self._buckets[key] = (bp, P, packs)
+
+    def _bwd_update(self, key: str, pack_after=None, opt_after=None):
+        """Backward + optimizer step + weight repack of one network, bucket by bucket (see
+        _build_bucket_programs).  pack_after / opt_after: events the repack / the parameter update must wait for
+        (a concurrent reader of the packed weights / parameters in gan_step)."""
+        plan, loss_prog = (self.G_train, self.g_loss_prog) if key == "g" else (self.D_train, self.d_loss_prog)
+        cur = torch.cuda.current_stream(self.device)
+        extra = [ev for ev in (opt_after, pack_after) if ev is not None]
+        if not self.bucketed_opt:
+            self._bwd_bucketed(plan)
+            for ev in extra:
+                cur.wait_event(ev)
+            loss_prog.run("opt")
+            plan.prog.run("pack")
+            return
+        bp, P, packs = self._buckets[key]
+        if key not in self._opt_streams:
+            self._opt_streams[key] = torch.cuda.Stream(self.device)
+        opt_stream, side = self._opt_streams[key], self._side_stream_for(plan)
+        P.run("step")                                   # advance the Adam step / bias corrections once
+        used_opt = False
+        for i, (s, e, lo, hi, _) in enumerate(bp):
+            used_side = self._run_bwd_ops(plan, s, e, cur)
+            last = i == len(bp) - 1
+            target = cur if last else opt_stream
+            deps = []
+            if not last or self.world_size > 1:
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                deps.append(ev)
+            if used_side:
+                evw = torch.cuda.Event()
+                evw.record(side)
+                deps.append(evw)
+            if self.world_size > 1 and hi > lo:
+                import torch.distributed as dist
+                if self._comm_stream is None:
+                    self._comm_stream = torch.cuda.Stream(self.device)
+                for d in deps:
+                    self._comm_stream.wait_event(d)
+                with torch.cuda.stream(self._comm_stream):
+                    dist.all_reduce(plan.store.grad[lo:hi], op=dist.ReduceOp.SUM, group=self.pg)
+                done = torch.cuda.Event()
+                done.record(self._comm_stream)
+                deps = [done]
+            for d in deps + extra:
+                target.wait_event(d)
+            P.run(f"b{i}", target.cuda_stream)
+            plan.prog.run(packs[i], target.cuda_stream)
+            used_opt = used_opt or not last
+        if used_opt:
+            ev = torch.cuda.Event()
+            ev.record(opt_stream)
+            cur.wait_event(ev)
+
     # ---- gradient all-reduce (data parallel) ---------------------------------------------------
     def _allreduce(self, store: nets.ParamStore):
         if self.world_size > 1:
@@ -259,7 +338,7 @@ class GanTrainer:
         """Split the backward segment into `n_buckets` contiguous op ranges.  Parameters are laid out in forward
         order and the backward runs in reverse, so the gradients finished after bucket i form a suffix
         [lo_i, hi_i) of the flat buffer; the ranges tile [0, n) exactly once.
-        Returns [(op_first, op_end, lo, hi)]."""
+        Returns [(op_first, op_end, lo, hi, layer names)]."""
         st = plan.store
         first, end = plan.prog.segments["bwd"]
         marks = plan.bwd_marks
@@ -279,7 +358,7 @@ class GanTrainer:
             lo = 0 if last else min(min(st.offsets[l.wkey + ".weight"], st.offsets[l.wkey + ".bias"])
                                     for l in plan.spec.layers if l.name in layer_names)
             lo = min(lo, hi)
-            out.append((s, e, lo, hi))
+            out.append((s, e, lo, hi, layer_names))
             hi = lo
         return out
 
@@ -374,9 +453,7 @@ class GanTrainer:
             self.G_train.prog.run("fwd")
             self.D_eval.prog.run("fwd")
             self.g_loss_prog.run("loss")
-            self._bwd_bucketed(self.G_train)
-            self.g_loss_prog.run("opt")
-            self.G_train.prog.run("pack")     # repack the updated generator weights
+            self._bwd_update("g")             # backward, Adam, repack of the updated generator weights
             return
         # The adversarial term of the generator loss carries no gradient (train_gan.py:285-287 detaches the
         # score): scoring the fake with D only produces a reported VALUE.  It runs as a parallel
@@ -392,11 +469,7 @@ class GanTrainer:
             self.G_train.prog.run_range(fe - 1, fe, cur.cuda_stream)   # writes G_train.out
             cur.wait_event(adv_done)
             self.g_loss_prog.run_range(ls, ls + 1, cur.cuda_stream)
-            self._bwd_bucketed(self.G_train)
-            self.g_loss_prog.run("opt")
-            if pack_after is not None:
-                cur.wait_event(pack_after)
-            self.G_train.prog.run("pack")
+            self._bwd_update("g", pack_after=pack_after)
             return
         adv = self._get_adv_stream()
         fork = torch.cuda.Event()
@@ -415,11 +488,7 @@ class GanTrainer:
         l1_done.record(cur)
         adv.wait_event(l1_done)                              # total = l1 + adv
         self.g_loss_prog.run_range(ls + 1, le, adv.cuda_stream)
-        self._bwd_bucketed(self.G_train)
-        self.g_loss_prog.run("opt")
-        if pack_after is not None:
-            cur.wait_event(pack_after)
-        self.G_train.prog.run("pack")     # repack the updated generator weights
+        self._bwd_update("g", pack_after=pack_after)   # backward, Adam, repack of the updated weights
         join = torch.cuda.Event()
         join.record(adv)
         cur.wait_event(join)
@@ -452,9 +521,7 @@ class GanTrainer:
         self.G_eval.prog.run("fwd")
         self.D_train.prog.run("fwd")
         self.d_loss_prog.run("loss")
-        self._bwd_bucketed(self.D_train)
-        self.d_loss_prog.run("opt")
-        self.D_train.prog.run("pack")
+        self._bwd_update("d")
 
     def _gan_ops(self, lag_adv: bool):
         """[discriminator step on xd / yd] side by side with [generator step on x / y], see gan_step()."""
@@ -490,11 +557,8 @@ class GanTrainer:
                 sd.wait_event(adv_folded)     # D_train's forward updates the running statistics the fold reads
             self.D_train.prog.run("fwd")
             self.d_loss_prog.run("loss")
-            self._bwd_bucketed(self.D_train)
-            if lag_adv:
-                sd.wait_event(adv_done)       # Adam / repack change what the scoring branch reads
-            self.d_loss_prog.run("opt")
-            self.D_train.prog.run("pack")
+            # (Adam / repack change what the scoring branch reads: they wait for it)
+            self._bwd_update("d", opt_after=adv_done if lag_adv else None)
             d_done = torch.cuda.Event()
             d_done.record(sd)
         with torch.cuda.stream(sg):

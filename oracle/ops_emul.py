@@ -328,7 +328,11 @@ def colsum(f: Dict):
 
 
 def adam(f: Dict):
-    f["step"] += 1
+    phase = f.get("phase", 0)
+    if phase != 2:
+        f["step"] += 1
+    if phase == 1:
+        return
     t = int(f["step"][0])
     b1, b2, lr, eps = f["beta1"], f["beta2"], f["lr"], f["eps"]
     g = f["g"] * f["gscale"]

@@ -63,7 +63,7 @@ def _worker(rank, port, ret):
     assert all(a[2] == b[3] for a, b in zip(buckets, buckets[1:]))
     first, end = tr.G_train.prog.segments["bwd"]
     assert buckets[0][0] == first and buckets[-1][1] == end and all(a[1] == b[0] for a, b in zip(buckets, buckets[1:]))
-    for (s, e, lo, hi) in buckets:
+    for (s, e, lo, hi, _names) in buckets:
         E.run_records(tr.G_train.prog.recs, s, e)
         if hi > lo:
             dist.all_reduce(tr.g_store.grad[lo:hi], op=dist.ReduceOp.SUM)
