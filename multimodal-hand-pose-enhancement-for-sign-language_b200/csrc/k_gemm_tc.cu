@@ -7,7 +7,10 @@
 //     epilogue (tcgen05.ld -> bias / activation / eval-BN / dropout -> global);
 //   * wgrad contracts over the row dimension, i.e. both operands are MN-major in shared memory:
 //     the same TMA boxes, described to the MMA with MN-major descriptors (no transposes).
+#include <stdio.h>
 #include <stdlib.h>
+
+#include <algorithm>
 
 #include "gemm_epilogue.cuh"
 #include "ptx_sm100.cuh"
@@ -39,6 +42,12 @@ struct FpropCfg {
   static constexpr int EPI_BYTES = 128 * EPI_PITCH_MAX;
   static constexpr int MAIN_BYTES = PIPE_BYTES > EPI_BYTES ? PIPE_BYTES : EPI_BYTES;
   static constexpr int SMEM_BYTES = MAIN_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 2 * BN * 4 /*bias, pivot*/;
+  // tap-merged main loop: the A ring holds (tl + ntaps - 1) x tb rows of 64 channels once per channel chunk (all
+  // taps read it through shifted descriptors), the B ring one (BN x 64) weight tile per (chunk, tap)
+  static constexpr int SA = 2;
+  static constexpr int A_STAGE = 24 * 1024;
+  static constexpr int SB = (BN == 256) ? 4 : (BN == 128 ? 3 : 4);
+  static_assert(SA * A_STAGE + SB * B_BYTES <= MAIN_BYTES, "merged rings must fit the pipeline buffers");
 };
 
 constexpr int TC_THREADS = 64 + 256;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (2 per TMEM sub-partition)
@@ -115,7 +124,11 @@ struct BwdSumsDev {
   int zbytes;   // bytes of the z box
 };
 
-template <int BN, int KIND, int MODE>
+// MERGED (stride-1 convolutions with consecutive taps): the M tile is ordered (row-in-sample, sample) with
+// tb >= 8 samples, so the A box — tl + ntaps - 1 rows of tb samples, loaded ONCE per 64-channel chunk — serves
+// every tap through a descriptor shifted by tap * tb rows (a multiple of the 8-row swizzle atom): A traffic and
+// TMA issue drop by the tap count.
+template <int BN, int KIND, int MODE, bool MERGED>
 __global__ void __launch_bounds__(TC_THREADS, FpropCfg<BN>::OCC)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmZ0,
@@ -135,6 +148,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   float* s_piv = s_bias + BN;
   int* s_flag = reinterpret_cast<int*>(tmem_ptr + 1);
   uint64_t* z_bar = reinterpret_cast<uint64_t*>(tmem_ptr + 2);
+  uint64_t* a_full = z_bar + 1;            // MERGED: the A ring (full_bar / empty_bar are the B ring)
+  uint64_t* a_empty = a_full + Cfg::SA;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mt = blockIdx.x, nt = blockIdx.y;
@@ -151,6 +166,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
+    }
+    if (MERGED) {
+      for (int i = 0; i < Cfg::SA; ++i) {
+        mbar_init(&a_full[i], 1);
+        mbar_init(&a_empty[i], 1);
+      }
     }
     mbar_init(tmem_full_bar, 1);
     if (BWDSUM) {
@@ -170,7 +191,51 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   pdl_sync();  // barriers, TMEM and descriptor prefetch above overlap the previous kernel's tail
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp == 0) {
+  if (MERGED && warp == 0) {
+    if (lane == 0) {
+      uint8_t* ringB = smem + Cfg::SA * Cfg::A_STAGE;
+      int ib = 0;
+      for (int kc = 0; kc < kpt; ++kc) {
+        const int sa = kc % Cfg::SA;
+        mbar_wait(&a_empty[sa], ((kc / Cfg::SA) & 1) ^ 1);
+        mbar_arrive_expect_tx(&a_full[sa], (uint32_t)p.a_box_bytes);
+        // tensor map dims (C, B, L): rows land as [row-in-sample][sample], zero outside [0, La)
+        tma_load_3d(smem + sa * Cfg::A_STAGE, &tmA0, &a_full[sa], kc * TC_BK, b0, l0 + p.tap_lo);
+        for (int t = 0; t < p.ntaps; ++t, ++ib) {
+          const int sb = ib % Cfg::SB;
+          mbar_wait(&empty_bar[sb], ((ib / Cfg::SB) & 1) ^ 1);
+          mbar_arrive_expect_tx(&full_bar[sb], Cfg::B_BYTES);
+          tma_load_2d(ringB + sb * Cfg::B_BYTES, &tmB, &full_bar[sb], p.tap_w[t] * p.Kc + kc * TC_BK, n0);
+        }
+      }
+    }
+  } else if (MERGED && warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = idesc_bf16(TC_BM, BN, 0, 0);
+      const uint32_t ringB = smem_u32(smem + Cfg::SA * Cfg::A_STAGE);
+      int ib = 0;
+      for (int kc = 0; kc < kpt; ++kc) {
+        const int sa = kc % Cfg::SA;
+        mbar_wait(&a_full[sa], (kc / Cfg::SA) & 1);
+        tc_fence_after();
+        const uint32_t sA = smem_u32(smem + sa * Cfg::A_STAGE);
+        for (int t = 0; t < p.ntaps; ++t, ++ib) {
+          const int sb = ib % Cfg::SB;
+          mbar_wait(&full_bar[sb], (ib / Cfg::SB) & 1);
+          tc_fence_after();
+          // tap t reads the rows [t*tb, t*tb + 128) of the A box: t*tb rows = a whole number of 8-row atoms
+          const uint64_t adesc = smem_desc_sw128(sA + (uint32_t)(t * p.tb) * 128u, 16, 1024);
+          const uint64_t bdesc = smem_desc_sw128(ringB + sb * Cfg::B_BYTES, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k)
+            umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kc | t | k) != 0);
+          umma_commit(&empty_bar[sb]);
+        }
+        umma_commit(&a_empty[sa]);
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else if (warp == 0) {
     if (lane == 0) {
       for (int kb = 0; kb < nkb; ++kb) {
         const int stage = kb % STAGES;
@@ -241,7 +306,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     drop.init(e.drop, e.drop_C);
     {
       const int r = sub * 32 + lane;  // tile row == TMEM lane
-      const int bi = r >> p.tl_log2, li = r & (p.tl - 1);
+      const int bi = MERGED ? (r & (p.tb - 1)) : (r >> p.tl_log2), li = MERGED ? (r >> p.tb_log2) : (r & (p.tl - 1));
       const int b = b0 + bi, lo = l0 + li;
       const int64_t grow = (int64_t)b * e.Lo_actual + (int64_t)lo * e.nphase + ph;
       const uint64_t drop_row_base = (uint64_t)grow * (uint64_t)e.drop_C;
@@ -252,7 +317,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       tc_fence_after();
       if (BWDSUM && et == 0) {   // every MMA has retired: the stage buffers are free
         mbar_arrive_expect_tx(z_bar, (uint32_t)bs.zbytes);
-        tma_load_3d(zs, ph ? &tmZ1 : &tmZ0, z_bar, nn0, bs.up2 ? (l0 >> 1) : l0, b0);
+        if (MERGED)   // z maps of a merged plan are (C, B, L) too
+          tma_load_3d(zs, ph ? &tmZ1 : &tmZ0, z_bar, nn0, b0, bs.up2 ? (l0 >> 1) : l0);
+        else
+          tma_load_3d(zs, ph ? &tmZ1 : &tmZ0, z_bar, nn0, bs.up2 ? (l0 >> 1) : l0, b0);
       }
       constexpr int CH = BN / 2;  // columns per epilogue warp
 #pragma unroll 1
@@ -317,7 +385,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll 1
         for (int rr = chalf * 16 + rsub; rr < chalf * 16 + 16; rr += RPI) {
           const int r = sub * 32 + rr;
-          const int bi = r >> p.tl_log2, li = r & (p.tl - 1);
+          const int bi = MERGED ? (r & (p.tb - 1)) : (r >> p.tl_log2), li = MERGED ? (r >> p.tb_log2) : (r & (p.tl - 1));
           const int b = b0 + bi, lo = l0 + li;
           const int ris = lo * e.nphase + ph;
           if (b >= p.B || lo >= p.Lo || ris >= e.Lo_actual) continue;
@@ -335,7 +403,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               a2[2 * i] = fmaf(d0, d0, a2[2 * i]), a2[2 * i + 1] = fmaf(d1, d1, a2[2 * i + 1]);
             }
           } else {
-            const int zr = bs.up2 ? bi * (p.tl >> 1) + (li >> 1) : r;
+            const int zr = !bs.up2 ? r : (MERGED ? (li >> 1) * p.tb + bi : bi * (p.tl >> 1) + (li >> 1));
             const uint4 zq = *reinterpret_cast<const uint4*>(zs + ((size_t)zr * BN + ch * 8) * 2);
             const uint32_t zw[4] = {zq.x, zq.y, zq.z, zq.w};
 #pragma unroll
@@ -402,7 +470,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll 1
       for (int rr = chalf * 16; rr < chalf * 16 + 16; ++rr) {
         const int r = sub * 32 + rr;
-        const int bi = r >> p.tl_log2, li = r & (p.tl - 1);
+        const int bi = MERGED ? (r & (p.tb - 1)) : (r >> p.tl_log2), li = MERGED ? (r >> p.tb_log2) : (r & (p.tl - 1));
         const int b = b0 + bi, lo = l0 + li;
         const int ris = lo * e.nphase + ph;
         if (b >= p.B || lo >= p.Lo || ris >= e.Lo_actual) continue;
@@ -702,29 +770,68 @@ int plan_gemm_bf16(const b2h_gemm_t& d, TcGemmPlan* plan) {
   p.Lo = d.Lo;
   p.Kc = d.Kc;
   p.stride = d.stride;
-  p.tl = choose_tl(d.Lo, TC_BM);
-  p.tl_log2 = 0;
-  while ((1 << p.tl_log2) < p.tl) ++p.tl_log2;
-  p.tb = TC_BM / p.tl;
-  p.n_lchunks = ceil_div(d.Lo, p.tl);
-  const int m_tiles = ceil_div(d.B, p.tb) * p.n_lchunks;
   B2H_CHECK_ARG(d.ldo % 8 == 0 && d.out_coff % 8 == 0 && ((uintptr_t)d.out % 16) == 0, B2H_ERR_ALIGN,
                 "gemm_bf16: out/ldo/out_coff must allow 16-byte row stores (ldo=%d coff=%d)", d.ldo, d.out_coff);
-  bool has1 = false;
-  int rc = make_row_views(&plan->tmA0, &plan->tmA1, &has1, d.A, d.Kc, d.La, d.B, d.lda, d.stride, p.tl, p.tb);
-  if (rc) return rc;
-  // taps that only ever read the (empty) odd view contribute nothing: drop them
-  p.ntaps = 0;
-  for (int t = 0; t < d.ntaps; ++t) {
-    int map, coord;
-    tap_view(d.stride, d.tap_off[t], &map, &coord);
-    if (map == 1 && !has1) continue;
-    p.tap_map[p.ntaps] = map;
-    p.tap_coord[p.ntaps] = coord;
-    p.tap_w[p.ntaps] = t;
-    p.ntaps++;
+  int rc;
+  // tap-merged main loop: stride 1, taps forming a run of consecutive row offsets, and a tile of tl <= 16 rows x
+  // tb >= 8 samples whose A box (tl + ntaps - 1 rows) fits the A stage
+  p.merged = 0;
+  int order[B2H_MAX_TAPS];
+  for (int t = 0; t < d.ntaps; ++t) order[t] = t;
+  std::sort(order, order + d.ntaps, [&](int a, int b) { return d.tap_off[a] < d.tap_off[b]; });
+  bool run = d.stride == 1 && d.ntaps >= 2 && !getenv("B2H_NO_TAP_MERGE");
+  for (int t = 1; t < d.ntaps && run; ++t) run = d.tap_off[order[t]] == d.tap_off[order[t - 1]] + 1;
+  if (run) {
+    const int h = d.ntaps - 1;
+    int best = 0;
+    int64_t best_pad = 0;
+    for (int tl = 1; tl <= 16; tl <<= 1) {
+      if ((tl + h) * (TC_BM / tl) * 128 > FpropCfg<64>::A_STAGE) continue;
+      const int64_t pad = (int64_t)ceil_div(d.Lo, tl) * tl;
+      if (!best || pad <= best_pad) best = tl, best_pad = pad;
+    }
+    // (do not trade more than 1/8 of padded rows for the merged loop)
+    if (best && best_pad * 8 <= (int64_t)ceil_div(d.Lo, choose_tl(d.Lo, TC_BM)) * choose_tl(d.Lo, TC_BM) * 9) {
+      p.merged = 1;
+      p.tl = best;
+      p.tb = TC_BM / best;
+      p.tap_lo = d.tap_off[order[0]];
+      p.a_box_bytes = (best + h) * p.tb * 128;
+      p.ntaps = d.ntaps;
+      for (int t = 0; t < d.ntaps; ++t) p.tap_w[t] = order[t], p.tap_map[t] = 0, p.tap_coord[t] = d.tap_off[order[t]];
+      // dims (C, B, L): the box lands as [row][sample][64 channels]
+      rc = make_map_3d(&plan->tmA0, d.A, d.Kc, d.B, d.La, (int64_t)d.La * d.lda, d.lda, 64, p.tb, best + h);
+      if (rc) return rc;
+      plan->tmA1 = plan->tmA0;
+    }
   }
-  B2H_CHECK_ARG(p.ntaps >= 1, B2H_ERR_SHAPE, "gemm_bf16: no tap reads inside the input (La=%d)", d.La);
+  if (!p.merged) {
+    p.tl = choose_tl(d.Lo, TC_BM);
+    p.tb = TC_BM / p.tl;
+    bool has1 = false;
+    rc = make_row_views(&plan->tmA0, &plan->tmA1, &has1, d.A, d.Kc, d.La, d.B, d.lda, d.stride, p.tl, p.tb);
+    if (rc) return rc;
+    // taps that only ever read the (empty) odd view contribute nothing: drop them
+    p.ntaps = 0;
+    for (int t = 0; t < d.ntaps; ++t) {
+      int map, coord;
+      tap_view(d.stride, d.tap_off[t], &map, &coord);
+      if (map == 1 && !has1) continue;
+      p.tap_map[p.ntaps] = map;
+      p.tap_coord[p.ntaps] = coord;
+      p.tap_w[p.ntaps] = t;
+      p.ntaps++;
+    }
+    B2H_CHECK_ARG(p.ntaps >= 1, B2H_ERR_SHAPE, "gemm_bf16: no tap reads inside the input (La=%d)", d.La);
+    p.tap_lo = 0;
+    p.a_box_bytes = 0;
+  }
+  p.tl_log2 = 0;
+  while ((1 << p.tl_log2) < p.tl) ++p.tl_log2;
+  p.tb_log2 = 0;
+  while ((1 << p.tb_log2) < p.tb) ++p.tb_log2;
+  p.n_lchunks = ceil_div(d.Lo, p.tl);
+  const int m_tiles = ceil_div(d.B, p.tb) * p.n_lchunks;
   // tile width: the largest BN (dividing one phase) that minimises the estimated wave time
   const int half = d.Npad / d.nphase;
   const int nkb = p.ntaps * (d.Kc / TC_BK);
@@ -745,6 +852,9 @@ int plan_gemm_bf16(const b2h_gemm_t& d, TcGemmPlan* plan) {
     int bn = atoi(f);
     if ((bn == 64 || bn == 128 || bn == 256) && half % bn == 0) best_bn = bn;
   }
+  if (getenv("B2H_DEBUG_PLAN"))
+    fprintf(stderr, "[b2h] gemm plan: B=%d Lo=%d Kc=%d Npad=%d ntaps=%d stride=%d nphase=%d -> merged=%d tl=%d tb=%d BN=%d tiles=%dx%d\n",
+            d.B, d.Lo, d.Kc, d.Npad, d.ntaps, d.stride, d.nphase, p.merged, p.tl, p.tb, best_bn, m_tiles, d.Npad / best_bn);
   plan->BN = best_bn;
   plan->grid_x = m_tiles;
   plan->grid_y = d.Npad / best_bn;
@@ -779,7 +889,18 @@ int plan_gemm_bf16(const b2h_gemm_t& d, TcGemmPlan* plan) {
     if (ok) {
       const __nv_bfloat16* z = reinterpret_cast<const __nv_bfloat16*>(bs.z);
       const int box_l = up2 ? p.tl / 2 : p.tl;
-      if (d.nphase == 1) {
+      const int64_t zs_b = (int64_t)bs.Lz * bs.ld;   // sample pitch of z
+      if (p.merged && d.nphase == 1) {   // (C, B, L) like the A operand of a merged plan
+        rc = make_map_3d(&plan->tmZ0, z, bs.ld, d.B, bs.Lz, zs_b, bs.ld, best_bn, p.tb, box_l, false);
+        plan->tmZ1 = plan->tmZ0;
+      } else if (p.merged) {
+        const int Le = (bs.Lz + 1) / 2, Lod = bs.Lz / 2;
+        rc = make_map_3d(&plan->tmZ0, z, bs.ld, d.B, Le, zs_b, 2 * (int64_t)bs.ld, best_bn, p.tb, box_l, false);
+        if (!rc && Lod > 0)
+          rc = make_map_3d(&plan->tmZ1, z + bs.ld, bs.ld, d.B, Lod, zs_b, 2 * (int64_t)bs.ld, best_bn, p.tb, box_l, false);
+        else
+          plan->tmZ1 = plan->tmZ0;
+      } else if (d.nphase == 1) {
         rc = make_map_3d(&plan->tmZ0, z, bs.ld, bs.Lz, d.B, bs.ld, (int64_t)bs.Lz * bs.ld, best_bn, box_l, p.tb, false);
         plan->tmZ1 = plan->tmZ0;
       } else {   // output row 2*lo + ph <-> the even / odd rows of z
@@ -821,15 +942,24 @@ static int epi_kind(const b2h_gemm_t& d) {
   return EPI_GENERIC;
 }
 
+template <int BN, int KIND, int MODE, bool MERGED>
+static int launch_fprop_m(const TcGemmPlan& plan, const EpiParams& e, cudaStream_t s, const b2h_bn_stats_t& st);
+
 template <int BN, int KIND, int MODE = MODE_PLAIN>
 static int launch_fprop(const TcGemmPlan& plan, const EpiParams& e, cudaStream_t s,
                         const b2h_bn_stats_t& st = b2h_bn_stats_t()) {
+  return plan.p.merged ? launch_fprop_m<BN, KIND, MODE, true>(plan, e, s, st)
+                       : launch_fprop_m<BN, KIND, MODE, false>(plan, e, s, st);
+}
+
+template <int BN, int KIND, int MODE, bool MERGED>
+static int launch_fprop_m(const TcGemmPlan& plan, const EpiParams& e, cudaStream_t s, const b2h_bn_stats_t& st) {
   using Cfg = FpropCfg<BN>;
   static_assert(((128 * (BN * 2 + 16) + 64 * BN + 127) & ~127) + 128 * BN * 2 <= Cfg::MAIN_BYTES, "z tile placement");
-  B2H_CARVE(gemm_tc_kernel<BN, KIND, MODE>);
+  B2H_CARVE(gemm_tc_kernel<BN, KIND, MODE, MERGED>);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t er = cudaFuncSetAttribute(gemm_tc_kernel<BN, KIND, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t er = cudaFuncSetAttribute(gemm_tc_kernel<BN, KIND, MODE, MERGED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           Cfg::SMEM_BYTES);
     if (er != cudaSuccess) return cuda_fail(er, "gemm_tc smem attribute");
     attr_set = true;
@@ -848,7 +978,7 @@ static int launch_fprop(const TcGemmPlan& plan, const EpiParams& e, cudaStream_t
     bs.zbytes = plan.bs_zbytes;
   }
   const bool z = MODE == MODE_BWDSUM;
-  launch(gemm_tc_kernel<BN, KIND, MODE>, grid, TC_THREADS, Cfg::SMEM_BYTES, s, plan.tmA0, plan.tmA1, plan.tmB,
+  launch(gemm_tc_kernel<BN, KIND, MODE, MERGED>, grid, TC_THREADS, Cfg::SMEM_BYTES, s, plan.tmA0, plan.tmA1, plan.tmB,
          z ? plan.tmZ0 : plan.tmA0, z ? plan.tmZ1 : plan.tmA0, plan.p, e, st, bs);
   B2H_LAUNCH_CHECK("gemm_tc");
   return B2H_OK;

@@ -16,6 +16,8 @@ struct TcGemmParams {
   int tap_map[B2H_MAX_TAPS];    // 0: base / even-row view, 1: odd-row view
   int tap_coord[B2H_MAX_TAPS];  // row coordinate offset inside that view
   int tap_w[B2H_MAX_TAPS];      // tap index inside the packed weight (K offset = tap_w * Kc)
+  // tap-merged main loop (stride 1, consecutive taps): tile rows ordered (row, sample), A box loaded once per chunk
+  int merged, tb_log2, tap_lo, a_box_bytes;
 };
 
 struct alignas(64) TcGemmPlan {

@@ -33,3 +33,28 @@ timeit("generator_step", lambda: tr.generator_step(graph=True))
 timeit("discriminator_step", lambda: tr.discriminator_step(graph=True))
 timeit("gan_step(lag_adv=False)", lambda: tr.gan_step(graph=True, lag_adv=False))
 timeit("gan_step(lag_adv=True)", lambda: tr.gan_step(graph=True, lag_adv=True))
+
+# experiment: the two sequential-step graphs replayed concurrently on two streams (ignores the cross-step
+# dependencies; timing only) — an upper bound of what branch overlap can give without intra-graph events
+s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+gg, gd = tr._graphs["g"], tr._graphs["d"]
+
+
+def both():
+    ev = torch.cuda.Event()
+    ev.record()
+    s1.wait_event(ev)
+    s2.wait_event(ev)
+    with torch.cuda.stream(s1):
+        gg.replay()
+        e1_ = torch.cuda.Event()
+        e1_.record()
+    with torch.cuda.stream(s2):
+        gd.replay()
+        e2_ = torch.cuda.Event()
+        e2_.record()
+    torch.cuda.current_stream().wait_event(e1_)
+    torch.cuda.current_stream().wait_event(e2_)
+
+
+timeit("two graphs on two streams", both)
