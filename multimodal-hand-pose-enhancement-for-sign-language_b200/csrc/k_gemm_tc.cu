@@ -41,7 +41,7 @@ struct FpropCfg {
   static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
   static constexpr int EPI_BYTES = 128 * EPI_PITCH_MAX;
   static constexpr int MAIN_BYTES = PIPE_BYTES > EPI_BYTES ? PIPE_BYTES : EPI_BYTES;
-  static constexpr int SMEM_BYTES = MAIN_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 2 * BN * 4 /*bias, pivot*/;
+  static constexpr int SMEM_BYTES = MAIN_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 3 * BN * 4 /*bias, pivot | scale, shift*/;
   // tap-merged main loop: the A ring holds (tl + ntaps - 1) x tb rows of 64 channels once per channel chunk (all
   // taps read it through shifted descriptors), the B ring one (BN x 64) weight tile per (chunk, tap)
   static constexpr int SA = 2;
@@ -53,17 +53,29 @@ struct FpropCfg {
 constexpr int TC_THREADS = 64 + 256;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (2 per TMEM sub-partition)
 
 // specialised epilogues (everything else falls back to EPI_GENERIC)
-enum { EPI_GENERIC = 0, EPI_BIAS_LEAKY = 1, EPI_BIAS_RELU = 2, EPI_BIAS_F32 = 3, EPI_MASK = 4, EPI_PLAIN = 5 };
+enum {
+  EPI_GENERIC = 0, EPI_BIAS_LEAKY = 1, EPI_BIAS_RELU = 2, EPI_BIAS_F32 = 3, EPI_MASK = 4, EPI_PLAIN = 5,
+  EPI_BIAS_LEAKY_BN = 6, EPI_BIAS_RELU_BN = 7   // + eval-mode BatchNorm folded to a per-channel affine
+};
+constexpr bool epi_has_bias(int k) {
+  return k == EPI_BIAS_LEAKY || k == EPI_BIAS_RELU || k == EPI_BIAS_F32 || k == EPI_BIAS_LEAKY_BN || k == EPI_BIAS_RELU_BN;
+}
+constexpr bool epi_has_bn(int k) { return k == EPI_BIAS_LEAKY_BN || k == EPI_BIAS_RELU_BN; }
 
 template <int KIND>
-__device__ __forceinline__ void epi_fast8(const float* s_bias, const uint8_t* mask_row, int col, int nn,
-                                          const uint32_t* acc_bits, float* v) {
+__device__ __forceinline__ void epi_fast8(const float* s_bias, const float* s_scale, const float* s_shift,
+                                          const uint8_t* mask_row, int col, int nn, const uint32_t* acc_bits, float* v) {
   float4 b0 = make_float4(0, 0, 0, 0), b1 = b0;
-  if (KIND == EPI_BIAS_LEAKY || KIND == EPI_BIAS_RELU || KIND == EPI_BIAS_F32) {
+  if (epi_has_bias(KIND)) {
     b0 = *reinterpret_cast<const float4*>(s_bias + col);
     b1 = *reinterpret_cast<const float4*>(s_bias + col + 4);
   }
   const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+  float sc[8], sh[8];
+  if (epi_has_bn(KIND)) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sc[j] = s_scale[col + j], sh[j] = s_shift[col + j];
+  }
   uint32_t m0 = 0x01010101u, m1 = 0x01010101u;
   if (KIND == EPI_MASK) {
     m0 = *reinterpret_cast<const uint32_t*>(mask_row + nn);
@@ -72,8 +84,9 @@ __device__ __forceinline__ void epi_fast8(const float* s_bias, const uint8_t* ma
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     float x = __uint_as_float(acc_bits[j]) + bb[j];
-    if (KIND == EPI_BIAS_LEAKY) x = x > 0.f ? x : x * kLeakySlope;
-    if (KIND == EPI_BIAS_RELU) x = x > 0.f ? x : 0.f;
+    if (KIND == EPI_BIAS_LEAKY || KIND == EPI_BIAS_LEAKY_BN) x = x > 0.f ? x : x * kLeakySlope;
+    if (KIND == EPI_BIAS_RELU || KIND == EPI_BIAS_RELU_BN) x = x > 0.f ? x : 0.f;
+    if (epi_has_bn(KIND)) x = fmaf(x, sc[j], sh[j]);
     if (KIND == EPI_MASK) {
       uint32_t byte = ((j < 4 ? m0 : m1) >> (8 * (j & 3))) & 0xFFu;
       x = byte ? 2.f * x : 0.f;
@@ -145,7 +158,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
   float* s_bias = reinterpret_cast<float*>(smem + Cfg::MAIN_BYTES + 256);
-  float* s_piv = s_bias + BN;
+  float* s_piv = s_bias + BN;     // STATS / BWDSUM: pivot / mean;  *_BN kinds: folded BN scale
+  float* s_shift = s_piv + BN;    // *_BN kinds: folded BN shift
   int* s_flag = reinterpret_cast<int*>(tmem_ptr + 1);
   uint64_t* z_bar = reinterpret_cast<uint64_t*>(tmem_ptr + 2);
   uint64_t* a_full = z_bar + 1;            // MERGED: the A ring (full_bar / empty_bar are the B ring)
@@ -284,9 +298,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const int pitch = BN * esz + 16;
     uint8_t* stage = smem + (size_t)sub * 32 * pitch;
     const int et = threadIdx.x - 64;      // 0..255
-    if (KIND == EPI_BIAS_LEAKY || KIND == EPI_BIAS_RELU || KIND == EPI_BIAS_F32) {
+    if (epi_has_bias(KIND)) {
       for (int i = et; i < BN; i += 256) {
         s_bias[i] = e.bias[nn0 + i];
+        if (epi_has_bn(KIND)) s_piv[i] = e.post_scale[nn0 + i], s_shift[i] = e.post_shift[nn0 + i];
         if (STATS) s_piv[i] = (st.running_mean && nn0 + i < st.C) ? st.running_mean[nn0 + i] : 0.f;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -335,7 +350,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             epi_finish8(e, drop, drop_row_base, nn0 + c + j, acc + j, v);
           } else if (KIND == EPI_MASK) {
             if (row_in && nn0 + c + j + 8 <= e.drop_C) {
-              epi_fast8<EPI_MASK>(s_bias, mask_row, c + j, nn0 + c + j, acc + j, v);
+              epi_fast8<EPI_MASK>(s_bias, s_piv, s_shift, mask_row, c + j, nn0 + c + j, acc + j, v);
             } else {
 #pragma unroll
               for (int k = 0; k < 8; ++k) {
@@ -345,7 +360,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               }
             }
           } else {
-            epi_fast8<KIND>(s_bias, nullptr, c + j, nn0 + c + j, acc + j, v);
+            epi_fast8<KIND>(s_bias, s_piv, s_shift, nullptr, c + j, nn0 + c + j, acc + j, v);
           }
           if (KIND == EPI_BIAS_F32 || (KIND == EPI_GENERIC && e.out_f32)) {
             float4* dst = reinterpret_cast<float4*>(my + (size_t)(c + j) * 4);
@@ -930,8 +945,10 @@ int plan_gemm_bf16(const b2h_gemm_t& d, TcGemmPlan* plan) {
 
 static int epi_kind(const b2h_gemm_t& d) {
   if (getenv("B2H_GENERIC_EPI")) return EPI_GENERIC;
-  if (d.post_scale) return EPI_GENERIC;
   const bool nodrop = d.drop.mode == B2H_DROP_NONE;
+  if (d.post_scale && d.bias && nodrop && !d.out_f32 && d.act == B2H_ACT_LEAKY) return EPI_BIAS_LEAKY_BN;
+  if (d.post_scale && d.bias && nodrop && !d.out_f32 && d.act == B2H_ACT_RELU) return EPI_BIAS_RELU_BN;
+  if (d.post_scale) return EPI_GENERIC;
   if (d.bias && nodrop && !d.out_f32 && d.act == B2H_ACT_LEAKY) return EPI_BIAS_LEAKY;
   if (d.bias && nodrop && !d.out_f32 && d.act == B2H_ACT_RELU) return EPI_BIAS_RELU;
   if (d.bias && nodrop && d.out_f32 && d.act == B2H_ACT_NONE) return EPI_BIAS_F32;
@@ -1001,6 +1018,8 @@ static int launch_fprop_kind(const TcGemmPlan& plan, const EpiParams& e, int kin
     case EPI_BIAS_F32: return launch_fprop<BN, EPI_BIAS_F32>(plan, e, s);
     case EPI_MASK: return launch_fprop<BN, EPI_MASK>(plan, e, s);
     case EPI_PLAIN: return launch_fprop<BN, EPI_PLAIN>(plan, e, s);
+    case EPI_BIAS_LEAKY_BN: return launch_fprop<BN, EPI_BIAS_LEAKY_BN>(plan, e, s);
+    case EPI_BIAS_RELU_BN: return launch_fprop<BN, EPI_BIAS_RELU_BN>(plan, e, s);
     default: return launch_fprop<BN, EPI_GENERIC>(plan, e, s);
   }
 }

@@ -501,6 +501,18 @@ class NetPlan:
                 self._emit_pack_table()
             if not self.train:
                 self._emit_fold_table()
+        # eval mode: a BN layer whose only consumer reads BN(z) as it is (one identity feed over all its columns) gets
+        # its folded BatchNorm applied in the GEMM epilogue, which then writes the consumer's input directly
+        self.eval_fused: Dict[str, Layer] = {}
+        import os as _os
+        if not self.train and not _os.environ.get("B2H_NO_EVAL_FUSE"):
+            for pl in spec.layers:
+                cons = self.consumers[pl.name]
+                if pl.bn and len(cons) == 1:
+                    c, f = cons[0]
+                    if (len(c.feeds) == 1 and f.rowmap == L.ROW_IDENT and f.dst_coff == 0 and pl.cout == c.cin and
+                            c.La == self.bufs[pl.name].Lz and self.groups == 1):
+                        self.eval_fused[pl.name] = c
         with P.segment("fwd"):
             for l in spec.layers:
                 self._emit_input(l)
@@ -679,6 +691,8 @@ class NetPlan:
                 P.add(L.OP_PREP, f"prep.{l.name}", src=self.feats, out=lb.a, kind=L.SRC_BCAST, B=B, L=l.La, C=l.cin,
                       ld=lb.Kc, Cfill=lb.Kc, src_ld=l.cin, drop=self._drop(l.drop_site, site_shape), out_f32=0)
             return
+        if isinstance(f0.src, Layer) and self.eval_fused.get(f0.src.name) is l:
+            return   # the producer's GEMM epilogue wrote BN(z) into lb.a
         # BN outputs of producer layers (+ residual / up-sampling / pooling), then this block's dropout
         cuts = sorted({f.dst_coff for f in l.feeds} | {f.dst_coff + f.src.cout for f in l.feeds})
         assert cuts[0] == 0 and cuts[-1] == l.cin, (l.name, cuts, l.cin)
@@ -707,6 +721,9 @@ class NetPlan:
         if l.bn and self.train:
             # the GEMM also produces the batch statistics of its output (tensor-core path: in the epilogue)
             common["stats"] = self._bn_stats_desc(l)
+        if l.name in self.eval_fused:
+            cb = self.bufs[self.eval_fused[l.name].name]
+            common.update(out=cb.a, ldo=cb.Kc, post_scale=lb.scale, post_shift=lb.shift)
         if l.kind == "convT":
             i = P.add(L.OP_GEMM, f"gemm.{l.name}", Lo=l.La, Npad=2 * lb.Cp, stride=1, nphase=2, Lo_actual=2 * l.La,
                       **common)

@@ -85,7 +85,7 @@ def gemm(f: Dict):
             v = v + f["bias"][:Nv]
         v = _act(v, f["act"])
         if f.get("post_scale") is not None:
-            v = v * f["post_scale"][:Nv] + f["post_shift"][:Nv]
+            v = v * f["post_scale"].reshape(-1)[:Nv] + f["post_shift"].reshape(-1)[:Nv]
         rows_act = lo * nph + ph
         ok = rows_act < Lact
         v = v[:, ok]
