@@ -237,19 +237,27 @@ typedef struct {
   uint32_t* ticket;
   int32_t B, C, L, ld, Cfill;
   float gscale;
+  float* dbias;        /* optional: column sums of dout as stored = bias gradient of the output layer [C] */
+  double* dbias_accum; /* workspace for dbias: [16][C] doubles, zero-initialised, self-resetting */
 } b2h_l1_t;
 
 /* nn.MSELoss(score, target) (train_gan.py:93,247,292) on (groups, n) scores, one target per group;
  * loss[0] = sum_g mean((s_g - t_g)^2); dscore = 2*(s - t)/n (NULL: forward only);
- * optionally total[0] = loss[0] + add[0]. */
+ * optionally total[0] = loss[0] + add[0].
+ * Optionally the gradient goes straight into the backward of the (1-channel) score layer: dpre[(g*n + i)*dpre_ld]
+ * = dscore in the activation dtype (column 0 of the layer's dpre rows; the padding columns stay as they are) and
+ * dbias[0] = the sum of those stored values (the layer's bias gradient). */
 typedef struct {
   const float* score; /* element (g, i) at score[(g*n + i)*ld] */
-  float* dscore;      /* same addressing */
+  float* dscore;      /* same addressing; may be NULL */
   float* loss;
   const float* add;
   float* total;
   int32_t groups, n, ld;
   float target[2];
+  void* dpre;         /* optional */
+  int32_t dpre_ld, dpre_bf16;
+  float* dbias;       /* optional, needs dpre */
 } b2h_mse_t;
 
 typedef struct {

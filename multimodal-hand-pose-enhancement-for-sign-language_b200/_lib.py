@@ -88,12 +88,13 @@ class ToNcl(C.Structure):
 
 class L1(C.Structure):
     _fields_ = [("out", vp), ("gt", vp), ("dout", vp), ("loss", vp), ("partial", vp), ("ticket", vp),
-                ("B", i32), ("C", i32), ("L", i32), ("ld", i32), ("Cfill", i32), ("gscale", f32)]
+                ("B", i32), ("C", i32), ("L", i32), ("ld", i32), ("Cfill", i32), ("gscale", f32), ("dbias", vp), ("dbias_accum", vp)]
 
 
 class Mse(C.Structure):
     _fields_ = [("score", vp), ("dscore", vp), ("loss", vp), ("add", vp), ("total", vp),
-                ("groups", i32), ("n", i32), ("ld", i32), ("target", f32 * 2)]
+                ("groups", i32), ("n", i32), ("ld", i32), ("target", f32 * 2),
+                ("dpre", vp), ("dpre_ld", i32), ("dpre_bf16", i32), ("dbias", vp)]
 
 
 class Colsum(C.Structure):

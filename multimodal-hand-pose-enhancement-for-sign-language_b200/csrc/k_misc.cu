@@ -191,6 +191,8 @@ __global__ void __launch_bounds__(256) l1_kernel(b2h_l1_t d, int cext) {
   const int tid = ty * 32 + tx;
   const int64_t numel = (int64_t)d.B * d.C * d.L;
   const float gval = d.gscale / (float)numel;
+  const uint32_t nblocks = gridDim.x * gridDim.y;
+  const uint32_t bid = blockIdx.y * gridDim.x + blockIdx.x;
   float acc = 0.f;
   for (int c0 = 0; c0 < cext; c0 += 32) {
     for (int j = ty; j < 32; j += 8) {
@@ -203,6 +205,10 @@ __global__ void __launch_bounds__(256) l1_kernel(b2h_l1_t d, int cext) {
         sg = diff > 0.f ? gval : (diff < 0.f ? -gval : 0.f);  // sign(diff)/numel, sign(0) = 0
       }
       tile[j][tx] = sg;
+      if (d.dbias) {   // column sum over this tile's 32 time steps, of the value as it is stored
+        const float cs = warp_sum(to_f<T>(from_f<T>(sg)));
+        if (tx == 0 && c < d.C) atomicAdd(d.dbias_accum + (int64_t)(bid % 16) * d.C + c, (double)cs);
+      }
     }
     __syncthreads();
     if (d.dout) {
@@ -222,10 +228,20 @@ __global__ void __launch_bounds__(256) l1_kernel(b2h_l1_t d, int cext) {
     if (tid < o) s_part[tid] += s_part[tid + o];
     __syncthreads();
   }
-  const uint32_t nblocks = gridDim.x * gridDim.y;
-  const uint32_t bid = blockIdx.y * gridDim.x + blockIdx.x;
   if (tid == 0) d.partial[bid] = (float)s_part[0];
   if (!last_block_done(d.ticket, nblocks)) return;
+  if (d.dbias) {
+    for (int c = tid; c < d.C; c += 256) {
+      double t = 0.0;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        double* a = d.dbias_accum + (int64_t)k * d.C + c;
+        t += __ldcg(a);
+        *a = 0.0;
+      }
+      d.dbias[c] = (float)t;
+    }
+  }
   double t = 0.0;
   for (uint32_t k = tid; k < nblocks; k += 256) t += (double)__ldcg(d.partial + k);
   __syncthreads();
@@ -244,6 +260,7 @@ int launch_l1(const b2h_l1_t& d, int dtype, cudaStream_t s) {
   B2H_CHECK_ARG(d.B > 0 && d.B <= 65535 && d.C > 0 && d.L > 0, B2H_ERR_SHAPE, "l1: bad shape");
   B2H_CHECK_ARG(!d.dout || (d.ld >= d.Cfill && d.Cfill >= d.C && d.Cfill % 4 == 0 && d.ld % 4 == 0), B2H_ERR_SHAPE,
                 "l1: bad dout shape");
+  B2H_CHECK_ARG(!d.dbias || (d.dout && d.dbias_accum), B2H_ERR_ARG, "l1: dbias needs dout and its workspace");
   int cext = d.dout ? d.Cfill : d.C;
   dim3 grid(ceil_div(d.L, 32), d.B), block(32, 8);
   if (dtype == B2H_BF16)
@@ -262,12 +279,25 @@ __global__ void __launch_bounds__(256) mse_kernel(b2h_mse_t d) {
   pdl_sync();
   __shared__ double s_red[256];
   double total = 0.0;
+  double bsum = 0.0;
   for (int g = 0; g < d.groups; ++g) {
     double acc = 0.0;
     for (int i = threadIdx.x; i < d.n; i += 256) {
       float diff = d.score[((int64_t)g * d.n + i) * d.ld] - d.target[g];
       acc += (double)diff * (double)diff;
-      if (d.dscore) d.dscore[((int64_t)g * d.n + i) * d.ld] = 2.0f * diff / (float)d.n;
+      const float gr = 2.0f * diff / (float)d.n;
+      if (d.dscore) d.dscore[((int64_t)g * d.n + i) * d.ld] = gr;
+      if (d.dpre) {
+        const int64_t o = ((int64_t)g * d.n + i) * d.dpre_ld;
+        if (d.dpre_bf16) {
+          const __nv_bfloat16 q = __float2bfloat16_rn(gr);
+          reinterpret_cast<__nv_bfloat16*>(d.dpre)[o] = q;
+          bsum += (double)__bfloat162float(q);
+        } else {
+          reinterpret_cast<float*>(d.dpre)[o] = gr;
+          bsum += (double)gr;
+        }
+      }
     }
     s_red[threadIdx.x] = acc;
     __syncthreads();
@@ -278,6 +308,15 @@ __global__ void __launch_bounds__(256) mse_kernel(b2h_mse_t d) {
     total += s_red[0] / (double)d.n;
     __syncthreads();
   }
+  if (d.dbias) {   // bias gradient of the score layer = column sum of the gradient rows just written
+    s_red[threadIdx.x] = bsum;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if (threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) d.dbias[0] = (float)s_red[0];
+  }
   if (threadIdx.x == 0) {
     d.loss[0] = (float)total;
     if (d.total) d.total[0] = (float)total + (d.add ? d.add[0] : 0.f);
@@ -287,6 +326,7 @@ __global__ void __launch_bounds__(256) mse_kernel(b2h_mse_t d) {
 int launch_mse(const b2h_mse_t& d, cudaStream_t s) {
   B2H_CARVE(mse_kernel);
   B2H_CHECK_ARG(d.groups >= 1 && d.groups <= 2 && d.n > 0 && d.ld >= 1, B2H_ERR_SHAPE, "mse: bad shape");
+  B2H_CHECK_ARG((!d.dpre || d.dpre_ld >= 1) && (!d.dbias || d.dpre), B2H_ERR_ARG, "mse: dpre / dbias");
   launch(mse_kernel, 1, 256, 0, s, d);
   B2H_LAUNCH_CHECK("mse");
   return B2H_OK;

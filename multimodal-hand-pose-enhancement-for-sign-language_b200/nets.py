@@ -345,13 +345,15 @@ class NetPlan:
                  train: bool, groups: int = 1, drop_mode: str = "philox",
                  drop_state: Optional[torch.Tensor] = None, site_base: int = 0,
                  motion_src: Optional[Sequence[torch.Tensor]] = None,
-                 weights_from: Optional["NetPlan"] = None):
+                 weights_from: Optional["NetPlan"] = None, out_dbias_external: bool = False):
         """`weights_from`: another plan of the SAME store and dtype whose packed forward weights / biases this
         plan reads instead of packing its own (the eval twin of a train plan: one repack per optimizer step
         serves both)."""
         assert drop_mode in ("none", "mask", "philox")
         assert weights_from is None or (weights_from.store is store and weights_from.dtype == dtype and not train)
         self.weights_from = weights_from
+        # the op that writes the output layer's dpre (the loss) also produces that layer's bias gradient
+        self.out_dbias_external = out_dbias_external
         self.spec, self.store, self.B, self.T, self.dtype = spec, store, B, T, dtype
         self.device = torch.device(device)
         self.train, self.groups = train, groups
@@ -778,7 +780,9 @@ class NetPlan:
     def _emit_bwd(self, l: Layer):
         P, st, B, lb = self.prog, self.store, self.B, self.bufs[l.name]
         rows = B * lb.Lz
-        if l is self.out_layer:
+        if l is self.out_layer and self.out_dbias_external:
+            pass   # dpre AND the bias gradient come from the loss op
+        elif l is self.out_layer:
             # dpre is provided by the loss (or by an external output gradient); bias grad = column sums
             i = P.add(L.OP_COLSUM, f"dbias.{l.name}", src=lb.dpre, out=st.g(l.wkey + ".bias"), partial=None,
                       ticket=self._ticket(), rows=rows, ld=lb.Cp, C=l.cout, f32=0)

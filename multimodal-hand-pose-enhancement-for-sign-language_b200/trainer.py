@@ -116,7 +116,8 @@ class GanTrainer:
         kw = dict(drop_mode=drop_mode, drop_state=self.drop_state)
         kw_d = dict(drop_mode=drop_mode, drop_state=self.drop_state_d)
         # generator: train plan (G step) and eval plan (D step / inference)
-        self.G_train = nets.NetPlan(self.g_spec, self.g_store, B, T, self.dtype, dev, train=True, site_base=0, **kw)
+        self.G_train = nets.NetPlan(self.g_spec, self.g_store, B, T, self.dtype, dev, train=True, site_base=0,
+                                    out_dbias_external=True, **kw)
         self.G_eval = nets.NetPlan(self.g_spec_eval, self.g_store, B, T, self.dtype, dev, train=False,
                                    weights_from=self.G_train)
         self.y = torch.zeros(B, out_dim, T, dtype=torch.float32, device=dev)
@@ -129,7 +130,8 @@ class GanTrainer:
         self.yd = torch.zeros(B, out_dim, T, dtype=torch.float32, device=dev)
         # discriminator: eval plan scoring calc_motion(G_train.out); grouped train plan on (fake, real)
         self.D_train = nets.NetPlan(self.d_spec, self.d_store, 2 * B, T, self.dtype, dev, train=True, groups=2,
-                                    motion_src=[self.G_eval.out, self.yd], site_base=100, **kw_d)
+                                    motion_src=[self.G_eval.out, self.yd], site_base=100, out_dbias_external=True,
+                                    **kw_d)
         self.D_eval = nets.NetPlan(self.d_spec, self.d_store, B, T, self.dtype, dev, train=False,
                                    motion_src=[self.G_train.out], weights_from=self.D_train)
         self.losses = torch.zeros(8, dtype=torch.float32, device=dev)  # [l1, adv, g_total, d_loss]
@@ -238,8 +240,10 @@ class GanTrainer:
         self.l1_partial = torch.zeros(nblk, dtype=torch.float32, device=dev)
         Ld = De.bufs[De.out_layer.name].Lz
         with P.segment("loss"):
+            self.l1_dbias_accum = torch.zeros(16, out_dim, dtype=torch.float64, device=dev)
             P.add(L.OP_L1, "l1", out=Gt.out, gt=self.y, dout=olb.dpre, loss=self.losses[0:1], partial=self.l1_partial,
-                  ticket=self.ticket[0:1], B=B, C=out_dim, L=T, ld=olb.Cp, Cfill=olb.Cp, gscale=1.0)
+                  ticket=self.ticket[0:1], B=B, C=out_dim, L=T, ld=olb.Cp, Cfill=olb.Cp, gscale=1.0,
+                  dbias=self.g_store.g(Gt.out_layer.wkey + ".bias"), dbias_accum=self.l1_dbias_accum)
             P.add(L.OP_MSE, "adv", score=De.out_blc, dscore=None, loss=self.losses[1:2], add=self.losses[0:1],
                   total=self.losses[2:3], groups=1, n=B * Ld, ld=De.out_blc.shape[-1], target=[1.0, 0.0])
         with P.segment("opt"):
@@ -250,10 +254,11 @@ class GanTrainer:
         dlb = Dt.bufs[Dt.out_layer.name]
         self.dscore = torch.zeros_like(Dt.out_blc)
         with P.segment("loss"):
+            # the loss writes its gradient straight into the score layer's dpre rows (column 0; the padding stays
+            # zero) and that layer's bias gradient (their sum): no separate row copy / column sum
             P.add(L.OP_MSE, "d_mse", score=Dt.out_blc, dscore=self.dscore, loss=self.losses[3:4], add=None, total=None,
-                  groups=2, n=B * Ld, ld=Dt.out_blc.shape[-1], target=[tf, tr])
-            P.add(L.OP_PREP, "dscore", src=self.dscore, out=dlb.dpre, kind=L.SRC_ROWS, B=2 * B, L=Ld, C=1, ld=dlb.Cp,
-                  Cfill=dlb.Cp, src_ld=self.dscore.shape[-1], drop=None, out_f32=0)
+                  groups=2, n=B * Ld, ld=Dt.out_blc.shape[-1], target=[tf, tr], dpre=dlb.dpre, dpre_ld=dlb.Cp,
+                  dpre_bf16=1 if self.dtype == L.BF16 else 0, dbias=self.d_store.g(Dt.out_layer.wkey + ".bias"))
         with P.segment("opt"):
             self.d_opt.record(P, gscale=1.0 / self.world_size)
 

@@ -306,6 +306,8 @@ def l1(f: Dict):
         dout = f["dout"].reshape(B, L, -1)
         dout[:, :, :C] = (torch.sign(d) * gv).permute(0, 2, 1).to(dout.dtype)
         dout[:, :, C:f["Cfill"]] = 0
+        if f.get("dbias") is not None:   # bias gradient of the output layer: column sums of dout as stored
+            f["dbias"].copy_(dout[:, :, :C].double().sum((0, 1)).float())
 
 
 def mse(f: Dict):
@@ -317,6 +319,12 @@ def mse(f: Dict):
         total += float((diff.double() ** 2).mean())
         if f.get("dscore") is not None:
             f["dscore"].reshape(-1)[g * n * ld:(g + 1) * n * ld: ld] = 2.0 * diff / n
+        if f.get("dpre") is not None:
+            pl = f["dpre_ld"]
+            f["dpre"].reshape(-1)[g * n * pl:(g + 1) * n * pl: pl] = (2.0 * diff / n).to(f["dpre"].dtype)
+    if f.get("dbias") is not None:
+        pl = f["dpre_ld"]
+        f["dbias"][0] = float(f["dpre"].reshape(-1)[: G * n * pl: pl].double().sum())
     f["loss"][0] = total
     if f.get("total") is not None:
         f["total"][0] = total + (float(f["add"][0]) if f.get("add") is not None else 0.0)

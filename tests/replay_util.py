@@ -11,7 +11,7 @@ OUT_FIELDS = {
     L.OP_GEMM: ["out"], L.OP_WGRAD: ["dW"],
     L.OP_BN_STATS: ["mean", "invstd", "scale", "shift", "running_mean", "running_var", "num_batches_tracked"],
     L.OP_BN_APPLY: ["out"], L.OP_BN_BWD: ["dpre", "dgamma", "dbeta", "dbias"], L.OP_PREP: ["out"],
-    L.OP_TO_NCL: ["dst"], L.OP_L1: ["loss", "dout"], L.OP_MSE: ["loss", "dscore", "total"], L.OP_COLSUM: ["out"],
+    L.OP_TO_NCL: ["dst"], L.OP_L1: ["loss", "dout", "dbias"], L.OP_MSE: ["loss", "dscore", "total", "dbias"], L.OP_COLSUM: ["out"],
     L.OP_ADAM: ["p", "m", "v", "step"], L.OP_PACK: ["out", "out_bias"], L.OP_BN_FOLD: ["scale", "shift"],
     L.OP_ROT6D: ["mat"], L.OP_PACK_MULTI: [], L.OP_BN_FOLD_MULTI: [],
 }
