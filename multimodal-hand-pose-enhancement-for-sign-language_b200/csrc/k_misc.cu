@@ -181,19 +181,28 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// grid (L/32, B/spc): a CTA walks `spc` clips so that its per-channel partial sums of the bias gradient (kept in
+// shared memory; channel c is owned by one warp) cost one fp64 atomic per channel per CTA
 template <typename T>
-__global__ void __launch_bounds__(256) l1_kernel(b2h_l1_t d, int cext) {
+__global__ void __launch_bounds__(256) l1_kernel(b2h_l1_t d, int cext, int spc) {
   pdl_sync();
   __shared__ float tile[32][33];
   __shared__ double s_part[256];
-  const int b = blockIdx.y, l0 = blockIdx.x * 32;
+  __shared__ float s_col[1024];
+  const int l0 = blockIdx.x * 32;
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int tid = ty * 32 + tx;
+  if (d.dbias) {
+    for (int c = tid; c < d.C; c += 256) s_col[c] = 0.f;
+    __syncthreads();
+  }
   const int64_t numel = (int64_t)d.B * d.C * d.L;
   const float gval = d.gscale / (float)numel;
   const uint32_t nblocks = gridDim.x * gridDim.y;
   const uint32_t bid = blockIdx.y * gridDim.x + blockIdx.x;
   float acc = 0.f;
+  for (int si = 0; si < spc; ++si) {
+  const int b = blockIdx.y * spc + si;
   for (int c0 = 0; c0 < cext; c0 += 32) {
     for (int j = ty; j < 32; j += 8) {
       int c = c0 + j, l = l0 + tx;
@@ -207,7 +216,7 @@ __global__ void __launch_bounds__(256) l1_kernel(b2h_l1_t d, int cext) {
       tile[j][tx] = sg;
       if (d.dbias) {   // column sum over this tile's 32 time steps, of the value as it is stored
         const float cs = warp_sum(to_f<T>(from_f<T>(sg)));
-        if (tx == 0 && c < d.C) atomicAdd(d.dbias_accum + (int64_t)(bid % 16) * d.C + c, (double)cs);
+        if (tx == 0 && c < d.C) s_col[c] += cs;
       }
     }
     __syncthreads();
@@ -221,6 +230,10 @@ __global__ void __launch_bounds__(256) l1_kernel(b2h_l1_t d, int cext) {
       }
     }
     __syncthreads();
+  }
+  }
+  if (d.dbias) {
+    for (int c = tid; c < d.C; c += 256) atomicAdd(d.dbias_accum + (int64_t)(bid % 16) * d.C + c, (double)s_col[c]);
   }
   s_part[tid] = (double)acc;
   __syncthreads();
@@ -261,12 +274,14 @@ int launch_l1(const b2h_l1_t& d, int dtype, cudaStream_t s) {
   B2H_CHECK_ARG(!d.dout || (d.ld >= d.Cfill && d.Cfill >= d.C && d.Cfill % 4 == 0 && d.ld % 4 == 0), B2H_ERR_SHAPE,
                 "l1: bad dout shape");
   B2H_CHECK_ARG(!d.dbias || (d.dout && d.dbias_accum), B2H_ERR_ARG, "l1: dbias needs dout and its workspace");
+  B2H_CHECK_ARG(!d.dbias || d.C <= 1024, B2H_ERR_SHAPE, "l1: dbias supports up to 1024 channels");
   int cext = d.dout ? d.Cfill : d.C;
-  dim3 grid(ceil_div(d.L, 32), d.B), block(32, 8);
+  const int spc = 1;   // clips per CTA (more than one was measured slower: the kernel is latency-bound per CTA)
+  dim3 grid(ceil_div(d.L, 32), d.B / spc), block(32, 8);
   if (dtype == B2H_BF16)
-    launch(l1_kernel<__nv_bfloat16>, grid, block, 0, s, d, cext);
+    launch(l1_kernel<__nv_bfloat16>, grid, block, 0, s, d, cext, spc);
   else
-    launch(l1_kernel<float>, grid, block, 0, s, d, cext);
+    launch(l1_kernel<float>, grid, block, 0, s, d, cext, spc);
   B2H_LAUNCH_CHECK("l1");
   return B2H_OK;
 }
