@@ -584,7 +584,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__
   if (dead_tap) {
     if (warp >= 2) {
       const int m = m0 + (warp & 3) * 32 + lane;
-      if (m < p.Mpad) {
+      if (p.direct) {
+        if (m < p.Mvalid)
+          for (int c = 0; c < WN && n0 + c < p.Nvalid; ++c) partial[((int64_t)m * p.Nvalid + n0 + c) * p.ntaps + t] = 0.f;
+      } else if (m < p.Mpad) {
         float* dst = partial + (((int64_t)split * p.ntaps + t) * p.Mpad + m) * p.Npad + n0;
         for (int c = 0; c < WN; c += 4) *reinterpret_cast<float4*>(dst + c) = make_float4(0.f, 0.f, 0.f, 0.f);
       }
@@ -652,6 +655,17 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__
       }
     }
     __syncwarp();
+    if (p.direct) {
+      // one split: this tile IS the gradient of tap t -> PyTorch layout dW[m][n][t] (`partial` is dW here)
+#pragma unroll 1
+      for (int rr = 0; rr < 32; ++rr) {
+        const int m = m0 + sub * 32 + rr;
+        if (m >= p.Mvalid) break;
+        const float* src = reinterpret_cast<const float*>(stage + (size_t)rr * pitch);
+        float* dst = partial + ((int64_t)m * p.Nvalid + n0) * p.ntaps + t;
+        for (int n = lane; n < WN && n0 + n < p.Nvalid; n += 32) dst[(int64_t)n * p.ntaps] = src[n];
+      }
+    } else
 #pragma unroll 1
     for (int rr = 0; rr < 32; ++rr) {
       const int m = m0 + sub * 32 + rr;
@@ -1081,6 +1095,9 @@ int plan_wgrad_bf16(const b2h_wgrad_t& d, TcWgradPlan* plan) {
   if (splits > 64) splits = 64;
   p.kb_per_split = ceil_div(p.total_kb, splits);
   plan->splits = ceil_div(p.total_kb, p.kb_per_split);
+  p.direct = plan->splits == 1 ? 1 : 0;
+  p.Mvalid = d.Mvalid;
+  p.Nvalid = d.Nvalid;
   plan->grid_x = ceil_div(d.Mpad, WG_BM) * (d.Npad / wn);
   return B2H_OK;
 }
@@ -1102,13 +1119,14 @@ static int launch_wg(const TcWgradPlan& plan, float* partial, cudaStream_t s) {
 }
 
 int run_wgrad_bf16(const TcWgradPlan& plan, const b2h_wgrad_t& d, cudaStream_t s) {
+  float* out = plan.p.direct ? d.dW : d.partial;   // one split: straight into dW, no reduce launch
   int rc;
   switch (plan.WN) {
-    case 256: rc = launch_wg<256>(plan, d.partial, s); break;
-    case 128: rc = launch_wg<128>(plan, d.partial, s); break;
-    default: rc = launch_wg<64>(plan, d.partial, s); break;
+    case 256: rc = launch_wg<256>(plan, out, s); break;
+    case 128: rc = launch_wg<128>(plan, out, s); break;
+    default: rc = launch_wg<64>(plan, out, s); break;
   }
-  if (rc) return rc;
+  if (rc || plan.p.direct) return rc;
   return launch_wgrad_reduce(d, plan.splits, s);
 }
 

@@ -39,6 +39,7 @@ struct TcWgradParams {
   int total_kb, kb_per_split;
   int tap_map[B2H_MAX_TAPS];
   int tap_coord[B2H_MAX_TAPS];
+  int direct, Mvalid, Nvalid;   // direct: one split, the epilogue writes dW[m][n][t] itself (no partial planes)
 };
 
 struct alignas(64) TcWgradPlan {

@@ -345,7 +345,8 @@ class NetPlan:
                  train: bool, groups: int = 1, drop_mode: str = "philox",
                  drop_state: Optional[torch.Tensor] = None, site_base: int = 0,
                  motion_src: Optional[Sequence[torch.Tensor]] = None,
-                 weights_from: Optional["NetPlan"] = None, out_dbias_external: bool = False):
+                 weights_from: Optional["NetPlan"] = None, out_dbias_external: bool = False,
+                 wgrad_direct: bool = False):
         """`weights_from`: another plan of the SAME store and dtype whose packed forward weights / biases this
         plan reads instead of packing its own (the eval twin of a train plan: one repack per optimizer step
         serves both)."""
@@ -354,6 +355,11 @@ class NetPlan:
         self.weights_from = weights_from
         # the op that writes the output layer's dpre (the loss) also produces that layer's bias gradient
         self.out_dbias_external = out_dbias_external
+        # bf16: weight gradients without split-K (one CTA per output tile and tap walks all rows and writes dW
+        # itself: no partial planes, no reduce launch, a fraction of the SM time) for every layer whose wgrad has
+        # slack behind it, i.e. all but the first two layers of the network (the last two of the backward); meant
+        # for callers that run the wgrads on several side streams (GanTrainer)
+        self.wgrad_direct = wgrad_direct and dtype == L.BF16
         self.spec, self.store, self.B, self.T, self.dtype = spec, store, B, T, dtype
         self.device = torch.device(device)
         self.train, self.groups = train, groups
@@ -812,7 +818,9 @@ class NetPlan:
             wg = dict(P=lb.dpre, Q=lb.a, Lp=lb.Lz, Lq=l.La, ldp=lb.Cp, ldq=lb.Kc, Mpad=lb.Cp, Npad=lb.Kc, Mvalid=l.cout,
                       Nvalid=l.cin, ntaps=k, stride=l.stride,
                       tap_off=[t - l.pad for t in range(k)] + [0] * (L.MAX_TAPS - k))
-        i = P.add(L.OP_WGRAD, f"wgrad.{l.name}", dW=st.g(l.wkey + ".weight"), partial=None, B=B, splits=0, **wg)
+        direct = self.wgrad_direct and l not in self.spec.layers[:2]
+        i = P.add(L.OP_WGRAD, f"wgrad.{l.name}", dW=st.g(l.wkey + ".weight"), partial=None, B=B,
+                  splits=1 if direct else 0, **wg)
         self.op_macs[i] = self._layer_macs(l)
         self._wg_need = max(self._wg_need, _wgrad_ws_bytes(self.prog.recs[i], self.dtype))
         self._pending_partial.append((i, "partial"))

@@ -116,7 +116,9 @@ class GanTrainer:
         kw = dict(drop_mode=drop_mode, drop_state=self.drop_state)
         kw_d = dict(drop_mode=drop_mode, drop_state=self.drop_state_d)
         # generator: train plan (G step) and eval plan (D step / inference)
-        self.G_train = nets.NetPlan(self.g_spec, self.g_store, B, T, self.dtype, dev, train=True, site_base=0, **kw)
+        direct = os.environ.get("B2H_NO_WGRAD_DIRECT") is None
+        self.G_train = nets.NetPlan(self.g_spec, self.g_store, B, T, self.dtype, dev, train=True, site_base=0,
+                                    wgrad_direct=direct, **kw)
         self.G_eval = nets.NetPlan(self.g_spec_eval, self.g_store, B, T, self.dtype, dev, train=False,
                                    weights_from=self.G_train)
         self.y = torch.zeros(B, out_dim, T, dtype=torch.float32, device=dev)
@@ -130,7 +132,7 @@ class GanTrainer:
         # discriminator: eval plan scoring calc_motion(G_train.out); grouped train plan on (fake, real)
         self.D_train = nets.NetPlan(self.d_spec, self.d_store, 2 * B, T, self.dtype, dev, train=True, groups=2,
                                     motion_src=[self.G_eval.out, self.yd], site_base=100, out_dbias_external=True,
-                                    **kw_d)
+                                    wgrad_direct=direct, **kw_d)
         self.D_eval = nets.NetPlan(self.d_spec, self.d_store, B, T, self.dtype, dev, train=False,
                                    motion_src=[self.G_train.out], weights_from=self.D_train)
         self.losses = torch.zeros(8, dtype=torch.float32, device=dev)  # [l1, adv, g_total, d_loss]
@@ -139,8 +141,8 @@ class GanTrainer:
         self._graphs: Dict[str, torch.cuda.CUDAGraph] = {}
         self._comm_stream = None
         self._copy_stream = None
-        self._wgrad_stream = None
-        self._wgrad_stream_d = None
+        self._wgrad_streams = {}
+        self._wgrad_rr = {}
         self._adv_stream = None
         self._d_stream = None
         self._g_stream = None
@@ -296,11 +298,11 @@ class GanTrainer:
         bp, P, packs = self._buckets[key]
         if key not in self._opt_streams:
             self._opt_streams[key] = torch.cuda.Stream(self.device)
-        opt_stream, side = self._opt_streams[key], self._side_stream_for(plan)
+        opt_stream = self._opt_streams[key]
         P.run("step")                                   # advance the Adam step / bias corrections once
         used_opt = False
         for i, (s, e, lo, hi, _) in enumerate(bp):
-            used_side = self._run_bwd_ops(plan, s, e, cur)
+            used_sides = self._run_bwd_ops(plan, s, e, cur)
             last = i == len(bp) - 1
             target = cur if last else opt_stream
             deps = []
@@ -308,7 +310,7 @@ class GanTrainer:
                 ev = torch.cuda.Event()
                 ev.record(cur)
                 deps.append(ev)
-            if used_side:
+            for side in used_sides:
                 evw = torch.cuda.Event()
                 evw.record(side)
                 deps.append(evw)
@@ -367,14 +369,15 @@ class GanTrainer:
             hi = lo
         return out
 
-    def _run_bwd_ops(self, plan: nets.NetPlan, s: int, e: int, cur) -> bool:
+    def _run_bwd_ops(self, plan: nets.NetPlan, s: int, e: int, cur) -> list:
         """Ops [s, e) of a backward segment.  The weight-gradient GEMMs (+ their split-K reduce) only feed the
-        optimizer, so they go to a side stream and overlap the bn_bwd -> dgrad chain of the following layers
-        (both fit on an SM together).  Returns True if the side stream was used."""
+        optimizer, so they go to side streams and overlap the bn_bwd -> dgrad chain of the following layers.
+        Returns the side streams that were used."""
         if not self.overlap_wgrad:
             plan.prog.run_range(s, e, cur.cuda_stream)
-            return False
-        side, recs, used, i = self._side_stream_for(plan), plan.prog.recs, False, s
+            return []
+        key = "d" if plan is self.D_train else "g"
+        sides, recs, used, i = self._side_streams_for(plan), plan.prog.recs, [], s
         while i < e:
             is_w = recs[i].kind == L.OP_WGRAD
             j = i
@@ -383,63 +386,59 @@ class GanTrainer:
             if is_w:
                 ev = torch.cuda.Event()
                 ev.record(cur)             # dpre of this layer is complete
-                side.wait_event(ev)
-                plan.prog.run_range(i, j, side.cuda_stream)
-                used = True
+                for k in range(i, j):
+                    side = sides[self._wgrad_rr[key] % len(sides)]
+                    self._wgrad_rr[key] += 1
+                    side.wait_event(ev)
+                    plan.prog.run_range(k, k + 1, side.cuda_stream)
+                    if side not in used:
+                        used.append(side)
             else:
                 plan.prog.run_range(i, j, cur.cuda_stream)
             i = j
         return used
 
-    def _side_stream_for(self, plan: nets.NetPlan):
-        """The wgrad stream of a train plan (one per network: the two backward passes of gan_step overlap)."""
-        if plan is self.D_train:
-            if self._wgrad_stream_d is None:
-                self._wgrad_stream_d = torch.cuda.Stream(self.device)
-            return self._wgrad_stream_d
-        if self._wgrad_stream is None:
-            self._wgrad_stream = torch.cuda.Stream(self.device)
-        return self._wgrad_stream
+    def _side_streams_for(self, plan: nets.NetPlan):
+        """The wgrad streams of a train plan: the weight gradients of successive layers go round-robin to a few
+        streams (a split-free wgrad keeps only a dozen SMs busy for tens of microseconds; several run side by
+        side) — one set per network, the two backward passes of gan_step overlap."""
+        key = "d" if plan is self.D_train else "g"
+        if key not in self._wgrad_streams:
+            k = max(1, int(os.environ.get("B2H_WGRAD_STREAMS", "4")))
+            self._wgrad_streams[key] = [torch.cuda.Stream(self.device) for _ in range(k)]
+            self._wgrad_rr[key] = 0
+        return self._wgrad_streams[key]
 
     def _bwd_bucketed(self, plan: nets.NetPlan):
         """Backward in buckets; each bucket's flat-gradient range is all-reduced over NCCL on a side stream while
-        the next bucket computes."""
+        the next bucket computes (the variant without the bucketed optimizer step)."""
         cur = torch.cuda.current_stream(self.device)
-        if self.world_size == 1:
-            s, e = plan.prog.segments["bwd"]
-            if self._run_bwd_ops(plan, s, e, cur):
-                ev = torch.cuda.Event()
-                ev.record(self._side_stream_for(plan))
-                cur.wait_event(ev)
-            return
-        import torch.distributed as dist
-        if self._comm_stream is None:
-            self._comm_stream = torch.cuda.Stream(self.device)
         st = plan.store
         pending = []
-        any_side = False
-        for (s, e, lo, hi) in self.bucket_plan(plan):
-            used_side = self._run_bwd_ops(plan, s, e, cur)
-            any_side = any_side or used_side
-            if hi <= lo:
-                continue
-            ev = torch.cuda.Event()
-            ev.record(cur)
-            self._comm_stream.wait_event(ev)
-            if used_side:
-                evw = torch.cuda.Event()
-                evw.record(self._side_stream_for(plan))
-                self._comm_stream.wait_event(evw)
-            with torch.cuda.stream(self._comm_stream):
-                dist.all_reduce(st.grad[lo:hi], op=dist.ReduceOp.SUM, group=self.pg)
-            done = torch.cuda.Event()
-            done.record(self._comm_stream)
-            pending.append(done)
+        for (s, e, lo, hi, _) in (self.bucket_plan(plan) if self.world_size > 1 else
+                                  [plan.prog.segments["bwd"] + (0, 0, None)]):
+            used = self._run_bwd_ops(plan, s, e, cur)
+            evs = []
+            for side in used:
+                ev = torch.cuda.Event()
+                ev.record(side)
+                evs.append(ev)
+            if self.world_size > 1 and hi > lo:
+                import torch.distributed as dist
+                if self._comm_stream is None:
+                    self._comm_stream = torch.cuda.Stream(self.device)
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                for d in evs + [ev]:
+                    self._comm_stream.wait_event(d)
+                with torch.cuda.stream(self._comm_stream):
+                    dist.all_reduce(st.grad[lo:hi], op=dist.ReduceOp.SUM, group=self.pg)
+                done = torch.cuda.Event()
+                done.record(self._comm_stream)
+                pending.append(done)
+            else:
+                pending += evs
         for ev in pending:
-            cur.wait_event(ev)
-        if any_side:
-            ev = torch.cuda.Event()
-            ev.record(self._side_stream_for(plan))
             cur.wait_event(ev)
 
     # ---- steps ---------------------------------------------------------------------------------

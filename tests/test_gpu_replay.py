@@ -53,8 +53,8 @@ def test_generator_train_replay(variant, rf, cin, cout, B, T, dtype):
     st_c = nets.ParamStore(spec_c, "cpu", seed=0)
     st_g = nets.ParamStore(spec_g, "cuda", seed=0)
     st_c.load_state_dict(G.state_dict())
-    pc = nets.NetPlan(spec_c, st_c, B, T, dtype, "cpu", train=True, drop_mode="mask")
-    pg = nets.NetPlan(spec_g, st_g, B, T, dtype, "cuda", train=True, drop_mode="mask")
+    pc = nets.NetPlan(spec_c, st_c, B, T, dtype, "cpu", train=True, drop_mode="mask", wgrad_direct=True)
+    pg = nets.NetPlan(spec_g, st_g, B, T, dtype, "cuda", train=True, drop_mode="mask", wgrad_direct=True)
     pc.set_masks(masks)
     pc.x.copy_(x)
     if f is not None:
