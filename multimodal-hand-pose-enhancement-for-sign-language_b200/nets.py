@@ -818,7 +818,8 @@ class NetPlan:
             wg = dict(P=lb.dpre, Q=lb.a, Lp=lb.Lz, Lq=l.La, ldp=lb.Cp, ldq=lb.Kc, Mpad=lb.Cp, Npad=lb.Kc, Mvalid=l.cout,
                       Nvalid=l.cin, ntaps=k, stride=l.stride,
                       tap_off=[t - l.pad for t in range(k)] + [0] * (L.MAX_TAPS - k))
-        direct = self.wgrad_direct and l not in self.spec.layers[:2]
+        import os as _os
+        direct = self.wgrad_direct and l not in self.spec.layers[:int(_os.environ.get("B2H_WGRAD_DIRECT_SKIP", "2"))]
         i = P.add(L.OP_WGRAD, f"wgrad.{l.name}", dW=st.g(l.wkey + ".weight"), partial=None, B=B,
                   splits=1 if direct else 0, **wg)
         self.op_macs[i] = self._layer_macs(l)
