@@ -35,7 +35,7 @@ __device__ __forceinline__ F8 zero8() {
 __device__ __forceinline__ F8 ld8f(const float* p) { return load8<float>(p); }
 
 // ---------------------------------------------------------------------------------------------
-// bn_stats: thread = 8 channels x 8 consecutive rows (4 rows of loads in flight), shifted sums around a pivot
+// bn_stats: thread = 8 channels x 4 consecutive rows (all loads issued before use), shifted sums around a pivot
 // common to the whole launch (the running mean), per-CTA fp32 partials combined with fp64 atomics; the last
 // CTA (ticket) turns the accumulators into mean / invstd / scale / shift, updates the running statistics and
 // re-zeroes the accumulators for the next launch.
@@ -308,8 +308,8 @@ int launch_bn_apply(const b2h_bn_apply_t& d, int dtype, cudaStream_t s) {
 
 // ---------------------------------------------------------------------------------------------
 // bn_bwd: two passes (reduce, apply); dy is recomputed from the gradient sources in both.
-// Thread = 8 channels x 8 consecutive rows, 2 rows of loads in flight; per-CTA partial sums are combined with
-// fp64 atomics and finished by the last CTA (ticket), which also re-zeroes the accumulators.
+// Thread = 8 channels x 4 consecutive rows, all loads issued before use; per-CTA partial sums are combined with
+// fp64 atomics over a few accumulator copies (see the kernel comment below for who sums / re-zeroes them).
 // ---------------------------------------------------------------------------------------------
 template <typename T>
 __device__ __forceinline__ F8 load_g8(const b2h_grad_src_t& gs, int64_t row, int c0) {

@@ -218,17 +218,6 @@ class GanTrainer:
         self._swap_done = torch.cuda.Event()
         self._swap_done.record(cur)
 
-    @staticmethod
-    def _alias_inputs(dst: nets.NetPlan, src: nets.NetPlan):
-        """Make `dst` read the same static input tensors as `src` (records hold tensor references)."""
-        for rec in dst.prog.recs:
-            if rec.kind == L.OP_PREP:
-                if rec.f["src"] is dst.x:
-                    rec.f["src"] = src.x
-                elif dst.feats is not None and rec.f["src"] is dst.feats:
-                    rec.f["src"] = src.feats
-        dst.x, dst.feats = src.x, src.feats
-
     def _build_loss_programs(self, label_smooth: bool):
         B, T, dev = self.B, self.T, self.device
         Gt, De, Dt = self.G_train, self.D_eval, self.D_train
@@ -241,7 +230,6 @@ class GanTrainer:
         self.l1_partial = torch.zeros(nblk, dtype=torch.float32, device=dev)
         Ld = De.bufs[De.out_layer.name].Lz
         with P.segment("loss"):
-            self.l1_dbias_accum = torch.zeros(16, out_dim, dtype=torch.float64, device=dev)
             P.add(L.OP_L1, "l1", out=Gt.out, gt=self.y, dout=olb.dpre, loss=self.losses[0:1], partial=self.l1_partial,
                   ticket=self.ticket[0:1], B=B, C=out_dim, L=T, ld=olb.Cp, Cfill=olb.Cp, gscale=1.0,
                   dbias=None, dbias_accum=None)   # (l1 can also emit the bias gradient of the output layer, but
@@ -254,11 +242,10 @@ class GanTrainer:
         P = self.d_loss_prog = Program(self.dtype, dev)
         tf, tr = (0.1, 0.9) if label_smooth else (0.0, 1.0)   # train_gan.py:244-245
         dlb = Dt.bufs[Dt.out_layer.name]
-        self.dscore = torch.zeros_like(Dt.out_blc)
         with P.segment("loss"):
             # the loss writes its gradient straight into the score layer's dpre rows (column 0; the padding stays
             # zero) and that layer's bias gradient (their sum): no separate row copy / column sum
-            P.add(L.OP_MSE, "d_mse", score=Dt.out_blc, dscore=self.dscore, loss=self.losses[3:4], add=None, total=None,
+            P.add(L.OP_MSE, "d_mse", score=Dt.out_blc, dscore=None, loss=self.losses[3:4], add=None, total=None,
                   groups=2, n=B * Ld, ld=Dt.out_blc.shape[-1], target=[tf, tr], dpre=dlb.dpre, dpre_ld=dlb.Cp,
                   dpre_bf16=1 if self.dtype == L.BF16 else 0, dbias=self.d_store.g(Dt.out_layer.wkey + ".bias"))
         with P.segment("opt"):
@@ -336,11 +323,6 @@ class GanTrainer:
             cur.wait_event(ev)
 
     # ---- gradient all-reduce (data parallel) ---------------------------------------------------
-    def _allreduce(self, store: nets.ParamStore):
-        if self.world_size > 1:
-            import torch.distributed as dist
-            dist.all_reduce(store.grad, op=dist.ReduceOp.SUM, group=self.pg)
-
     def bucket_plan(self, plan: nets.NetPlan):
         """Split the backward segment into `n_buckets` contiguous op ranges.  Parameters are laid out in forward
         order and the backward runs in reverse, so the gradients finished after bucket i form a suffix
