@@ -790,9 +790,11 @@ class NetPlan:
             pass   # dpre AND the bias gradient come from the loss op
         elif l is self.out_layer:
             # dpre is provided by the loss (or by an external output gradient); bias grad = column sums
-            i = P.add(L.OP_COLSUM, f"dbias.{l.name}", src=lb.dpre, out=st.g(l.wkey + ".bias"), partial=None,
-                      ticket=self._ticket(), rows=rows, ld=lb.Cp, C=l.cout, f32=0)
-            self._need_partial(i, 128 * l.cout * 2)
+            # (own workspace: like the weight gradients this op only feeds the optimizer and may run beside the
+            # BN kernels of the backward chain, which share `partial`)
+            self.colsum_partial = self._zeros(128 * l.cout * 2, dtype=torch.float32)
+            P.add(L.OP_COLSUM, f"dbias.{l.name}", src=lb.dpre, out=st.g(l.wkey + ".bias"),
+                  partial=self.colsum_partial, ticket=self._ticket(), rows=rows, ld=lb.Cp, C=l.cout, f32=0)
         else:
             lb.dpre = self._zeros(B, lb.Lz, lb.Cp)
             gs = []

@@ -361,16 +361,23 @@ class GanTrainer:
         key = "d" if plan is self.D_train else "g"
         sides, recs, used, i = self._side_streams_for(plan), plan.prog.recs, [], s
         while i < e:
-            is_w = recs[i].kind == L.OP_WGRAD
+            # weight gradients and the bias gradient of the output layer: off the chain
+            is_w = recs[i].kind in (L.OP_WGRAD, L.OP_COLSUM)
             j = i
-            while j < e and (recs[j].kind == L.OP_WGRAD) == is_w:
+            while j < e and (recs[j].kind in (L.OP_WGRAD, L.OP_COLSUM)) == is_w:
                 j += 1
             if is_w:
                 ev = torch.cuda.Event()
                 ev.record(cur)             # dpre of this layer is complete
                 for k in range(i, j):
-                    side = sides[self._wgrad_rr[key] % len(sides)]
-                    self._wgrad_rr[key] += 1
+                    # split-K wgrads share the plan's partial-plane workspace: they all go to stream 0, in order;
+                    # the split-free ones (and the bias column sum) own their outputs and rotate over the rest
+                    shared_ws = recs[k].kind == L.OP_WGRAD and not (plan.wgrad_direct and recs[k].f["splits"] == 1)
+                    if shared_ws or len(sides) == 1:
+                        side = sides[0]
+                    else:
+                        side = sides[1 + self._wgrad_rr[key] % (len(sides) - 1)]
+                        self._wgrad_rr[key] += 1
                     side.wait_event(ev)
                     plan.prog.run_range(k, k + 1, side.cuda_stream)
                     if side not in used:
