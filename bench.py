@@ -253,8 +253,13 @@ def kernel_breakdown(tr, flush, reps=5):
                 e1.synchronize()
                 ts.append(e0.elapsed_time(e1))
             ms = statistics.median(ts)
-            rows.append({"op": f"{pname}.{rec.tag}", "ms": ms, "gflop": 2 * macs / 1e9,
-                         "tflops": 2 * macs / (ms * 1e-3) / 1e12 if ms > 0 else 0.0})
+            row = {"op": f"{pname}.{rec.tag}", "ms": ms, "gflop": 2 * macs / 1e9,
+                   "tflops": 2 * macs / (ms * 1e-3) / 1e12 if ms > 0 else 0.0}
+            if rec.kind == L.OP_WGRAD and plan.wgrad_direct and rec.f.get("splits") == 1:
+                # split-free weight gradient: a dozen CTAs by design (it runs beside the backward chain on a side
+                # stream); its duration alone says nothing about the GPU's tensor throughput
+                row["side_stream_few_ctas"] = True
+            rows.append(row)
     return rows
 
 
@@ -414,7 +419,7 @@ def main():
         if not a.no_kernel_breakdown and a.mode == "train":
             rows = kernel_breakdown(tr, flush)
             rows.sort(key=lambda r: -r["ms"])
-            dom = rows[0]
+            dom = [r for r in rows if not r.get("side_stream_few_ctas")][0]   # dominant full-grid GEMM launch
             peak = peaks.get("bf16_tflops", 1590.0)
             which = "measured burst (MEASURED_PEAKS.json bf16_tflops)" if "bf16_tflops" in peaks else "fallback 1.59 PF"
             traffic = None
@@ -424,7 +429,10 @@ def main():
                 pass
             line["roofline"] = {"bound": "tensor", "kernel": dom["op"], "achieved": dom["tflops"], "peak": peak,
                                 "unit": "TFLOP/s", "frac": dom["tflops"] / peak, "traffic": traffic,
-                                "peak_source": which, "launch_ms": dom["ms"], "algorithmic_gflop": dom["gflop"]}
+                                "peak_source": which, "launch_ms": dom["ms"], "algorithmic_gflop": dom["gflop"],
+                                "how": "CUDA events around the launch alone, L2 flushed before it (cold operands; in "
+                                       "the step they are L2-resident), median of 5; the split-free side-stream "
+                                       "wgrads (a dozen CTAs by design) are excluded from the choice"}
             line["kernel_breakdown"] = [{k: (round(v, 5) if isinstance(v, float) else v) for k, v in r.items()}
                                         for r in rows[:12]]
             line["gemm_ms_sum"] = sum(r["ms"] for r in rows)
