@@ -284,8 +284,11 @@ def main():
     cin, cout = 36, 252
     feats_kind = None if not a.feats else ("image" if a.variant == "b2h" else "text")
     B, T = a.batch, a.frames
+    kw = {}
+    if os.environ.get("B2H_BUCKETS"):
+        kw["n_buckets"] = int(os.environ["B2H_BUCKETS"])
     tr = GanTrainer(a.variant, cin, cout, a.feats, B, T, precision=a.precision, device=dev, lr=1e-4, seed=23456 + rank,
-                    drop_mode="philox", world_size=world, process_group=pg)
+                    drop_mode="philox", world_size=world, process_group=pg, **kw)
     if world > 1:   # identical initial weights on every rank (DDP convention)
         for st in (tr.g_store, tr.d_store):
             dist.broadcast(st.flat, 0)

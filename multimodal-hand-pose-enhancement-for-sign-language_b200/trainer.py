@@ -87,11 +87,16 @@ class GanTrainer:
     def __init__(self, variant: str = "v1", in_dim: int = 36, out_dim: int = 252, require_feats: bool = False,
                  batch_size: int = 256, T: int = 64, precision: str = "bf16", device="cuda", lr: float = 1e-4,
                  seed: int = 23456, drop_mode: str = "philox", label_smooth: bool = False,
-                 world_size: int = 1, process_group=None, n_buckets: int = 3, stores=None):
+                 world_size: int = 1, process_group=None, n_buckets: Optional[int] = None, stores=None):
         self.device = torch.device(device)
         self.B, self.T, self.precision = batch_size, T, precision
         self.dtype = dtype_of(precision)
         self.variant, self.require_feats = variant, require_feats
+        # gradient / optimizer buckets per network: 3 on one GPU (the update of the late layers runs beside the
+        # backward of the early ones); 1 under data parallelism, where every bucket is a collective and a
+        # collective costs more than the overlap buys (8 GPUs: 1.01 ms per step with 1 bucket, 1.16 ms with 3)
+        if n_buckets is None:
+            n_buckets = 3 if world_size == 1 else 1
         self.world_size, self.pg, self.n_buckets = world_size, process_group, max(1, n_buckets)
         B = batch_size
         dev = self.device
