@@ -151,11 +151,15 @@ typedef struct {
   const void* Q; /* [B][Lq][ldq] act dtype */
   float* dW;     /* [Mvalid][Nvalid][ntaps] fp32 */
   float* partial; /* workspace: >= b2h_wgrad_workspace_bytes() */
+  int64_t partial_bytes; /* size of `partial`; checked against the plan when > 0 (0 = caller vouches for it) */
   int32_t B, Lp, Lq, ldp, ldq;
   int32_t Mpad, Npad, Mvalid, Nvalid; /* pads are multiples of 64 */
   int32_t ntaps, stride;
   int32_t tap_off[B2H_MAX_TAPS];
-  int32_t splits; /* 0 = let the library choose */
+  int32_t splits; /* split-K slices over the rows: 0 = let the library choose (fills the GPU; fp32 partial planes in
+                     `partial` + an ordered reduce launch);  1 on the tensor-core path = split-free: one CTA per
+                     output tile and tap walks all rows and writes dW itself (no workspace traffic, no reduce
+                     launch, a fraction of the SM time, a longer launch — for callers that run it beside other work) */
 } b2h_wgrad_t;
 
 /* ------------------------------------------------------------------------------------------- */

@@ -49,7 +49,7 @@ class Gemm(C.Structure):
 
 
 class Wgrad(C.Structure):
-    _fields_ = [("P", vp), ("Q", vp), ("dW", vp), ("partial", vp),
+    _fields_ = [("P", vp), ("Q", vp), ("dW", vp), ("partial", vp), ("partial_bytes", i64),
                 ("B", i32), ("Lp", i32), ("Lq", i32), ("ldp", i32), ("ldq", i32),
                 ("Mpad", i32), ("Npad", i32), ("Mvalid", i32), ("Nvalid", i32),
                 ("ntaps", i32), ("stride", i32), ("tap_off", i32 * MAX_TAPS), ("splits", i32)]

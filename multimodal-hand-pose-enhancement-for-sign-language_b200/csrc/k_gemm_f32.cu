@@ -271,6 +271,9 @@ int launch_wgrad_f32(const b2h_wgrad_t& d, cudaStream_t s) {
   const int rows = d.B * d.Lp;
   int rows_per_split = ceil_div(ceil_div(rows, splits), W_BK) * W_BK;
   splits = ceil_div(rows, rows_per_split);
+  B2H_CHECK_ARG(d.partial_bytes <= 0 ||
+                    (int64_t)splits * d.ntaps * d.Mpad * d.Npad * (int64_t)sizeof(float) <= d.partial_bytes,
+                B2H_ERR_ARG, "wgrad: workspace of %lld bytes is too small for %d splits", (long long)d.partial_bytes, splits);
   dim3 grid((d.Mpad / W_BM) * (d.Npad / W_BN), d.ntaps, splits);
   launch(wgrad_simt_kernel<float>, grid, 256, 0, s, d, splits, rows_per_split);
   B2H_LAUNCH_CHECK("wgrad_f32");

@@ -1095,6 +1095,10 @@ int plan_wgrad_bf16(const b2h_wgrad_t& d, TcWgradPlan* plan) {
   if (splits > 64) splits = 64;
   p.kb_per_split = ceil_div(p.total_kb, splits);
   plan->splits = ceil_div(p.total_kb, p.kb_per_split);
+  B2H_CHECK_ARG(plan->splits == 1 || d.partial_bytes <= 0 ||
+                    (int64_t)plan->splits * d.ntaps * d.Mpad * d.Npad * (int64_t)sizeof(float) <= d.partial_bytes,
+                B2H_ERR_ARG, "wgrad: workspace of %lld bytes is too small for %d splits x %d taps x %d x %d",
+                (long long)d.partial_bytes, plan->splits, d.ntaps, d.Mpad, d.Npad);
   p.direct = plan->splits == 1 ? 1 : 0;
   p.Mvalid = d.Mvalid;
   p.Nvalid = d.Nvalid;

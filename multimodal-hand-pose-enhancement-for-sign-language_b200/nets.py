@@ -544,6 +544,8 @@ class NetPlan:
             if isinstance(fld, tuple):   # nested descriptor, e.g. the statistics of a GEMM output
                 f, fld = f[fld[0]], fld[1]
             f[fld] = self.wg_partial if self.prog.recs[i].kind == L.OP_WGRAD else self.partial
+            if self.prog.recs[i].kind == L.OP_WGRAD:
+                f["partial_bytes"] = self.wg_partial.numel() * 4   # checked by the library against its plan
 
     def _need_partial(self, idx: int, floats: int, fld: str = "partial"):
         self._partial_need = max(self._partial_need, int(floats))
@@ -880,6 +882,17 @@ def _wgrad_ws_bytes(rec, dtype) -> int:
     """Upper bound of the wgrad split-K workspace (mirrors b2h_wgrad_workspace_bytes: <= 65 planes)."""
     f = rec.f
     planes = f["ntaps"] * f["Mpad"] * f["Npad"] * 4
-    rows = f["B"] * f["Lp"]
-    max_splits = min(64, max(1, rows // 64))
+    # the split count is bounded by the number of 64-row k-blocks of the (tb clips x tl rows) tiling, which
+    # exceeds rows // 64 when the tiles are ragged (odd lengths: tl = 1, tb = 64 -> one k-block per time step)
+    Lp, B = f["Lp"], f["B"]
+    tl, best_pad = 1, Lp
+    t = 1
+    while t <= 64:
+        pad = -(-Lp // t) * t
+        if pad <= best_pad:
+            tl, best_pad = t, pad
+        t *= 2
+    tb = 64 // tl
+    total_kb = -(-B // tb) * -(-Lp // tl)
+    max_splits = min(64, max(1, total_kb, B * Lp // 64))
     return (max_splits + 1) * planes
