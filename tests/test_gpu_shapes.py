@@ -56,3 +56,35 @@ def test_odd_shapes_forward_and_step(B, T, precision, tol):
         # comparison is ill-conditioned, and torch itself refuses B = 1)
         d_loss = R.discriminator_step(G, D, d_opt, x, y)
         assert abs(float(tr.losses[3]) - float(d_loss[0])) <= 20 * tol * abs(float(d_loss[0])) + 1e-6
+
+
+@pytest.mark.parametrize("variant,B,T", [("v1", 6, 20), ("b2h", 4, 12), ("v4", 9, 36), ("v2", 7, 28), ("v4_deeper", 5, 44)])
+def test_odd_shapes_conditioned_variants(variant, B, T):
+    """Text / image conditioned generators at ragged sizes, fp32: eval forward and the output of a train step."""
+    from b2h_b200.trainer import GanTrainer
+    torch.manual_seed(7 * B + T)
+    G = R.build_generator(variant, 36, 252, True)
+    D = R.build_discriminator(252)
+    x, y = torch.randn(B, 36, T), torch.randn(B, 252, T)
+    f = torch.randn(B, T, 2000) * 2 if variant == "b2h" else torch.nn.functional.normalize(torch.randn(B, 512), dim=1)
+    tr = GanTrainer(variant, 36, 252, True, B, T, precision="fp32", device="cuda", lr=1e-3, drop_mode="none")
+    tr.g_store.load_state_dict(G.state_dict())
+    tr.d_store.load_state_dict(D.state_dict())
+    tr.load_batch(x.cuda(), y.cuda(), f.cuda())
+    G.eval()
+    with torch.no_grad():
+        ref = G(x, feats_=f)
+    assert rel_err(tr.infer(), ref) <= 1e-5
+    for m in (G, D):
+        for mod in m.modules():
+            if isinstance(mod, R.ReplayDropout):
+                mod.p = 0.0
+    g_opt = torch.optim.Adam(G.parameters(), lr=1e-3)
+    _, l1, _, out = R.generator_step(G, D, g_opt, x, y, f)
+    tr.generator_step()
+    assert rel_err(tr.G_train.out, out) <= 1e-5
+    assert abs(float(tr.losses[0]) - float(l1)) <= 1e-5 * abs(float(l1))
+    tr.discriminator_step()
+    tr.gan_step()
+    torch.cuda.synchronize()
+    assert torch.isfinite(tr.losses[:4]).all() and torch.isfinite(tr.g_store.flat).all()
