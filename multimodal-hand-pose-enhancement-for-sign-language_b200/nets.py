@@ -879,8 +879,20 @@ def _bn_partial_floats(rows, C, groups):
 
 
 def _wgrad_ws_bytes(rec, dtype) -> int:
-    """Upper bound of the wgrad split-K workspace (mirrors b2h_wgrad_workspace_bytes: <= 65 planes)."""
+    """Size of the wgrad split-K workspace: the library's own b2h_wgrad_workspace_bytes (an upper bound that does not
+    need a GPU); the formula below only serves CPU-side plan emulation when the library cannot be loaded."""
     f = rec.f
+    try:
+        import ctypes as C
+        from .program import _fill_struct
+        lib = L.load()
+        desc = _fill_struct(L.Wgrad(), {k: v for k, v in f.items()
+                                        if not k.startswith("_") and k not in ("P", "Q", "dW", "partial")})
+        need = int(lib.b2h_wgrad_workspace_bytes(C.byref(desc), dtype))
+        if need > 0:
+            return need
+    except (OSError, L.B2HError):
+        pass
     planes = f["ntaps"] * f["Mpad"] * f["Npad"] * 4
     # the split count is bounded by the number of 64-row k-blocks of the (tb clips x tl rows) tiling, which
     # exceeds rows // 64 when the tiles are ragged (odd lengths: tl = 1, tb = 64 -> one k-block per time step)

@@ -182,3 +182,24 @@ def test_discriminator(T, groups):
     E.run_records(recs, *plan.prog.segments["bwd"])
     for k, p in D.named_parameters():
         assert rel_err(store.g(k), p.grad) < 5e-5, k
+
+
+@pytest.mark.parametrize("B,T", [(10, 38), (5, 10), (24, 64), (3, 21)])
+def test_wgrad_workspace_covers_the_library_bound(B, T):
+    """The split-K workspace a plan allocates (and declares in partial_bytes) is the library's own bound for every
+    weight-gradient op, ragged tilings included (odd lengths make more k-blocks than rows / 64)."""
+    import ctypes as C
+    from b2h_b200.program import _fill_struct
+    lib = L.load()
+    for spec, groups in ((nets.discriminator_spec(252), 2), (nets.generator_spec("v1", 36, 252, False, train=True), 1)):
+        for dtype in (L.F32, L.BF16):
+            plan = nets.NetPlan(spec, nets.ParamStore(spec, "cpu", seed=0), B * groups, T, dtype, "cpu", train=True,
+                                groups=groups, drop_mode="none")
+            have = plan.wg_partial.numel() * 4
+            for rec in plan.prog.recs:
+                if rec.kind != L.OP_WGRAD:
+                    continue
+                assert rec.f["partial_bytes"] == have
+                desc = _fill_struct(L.Wgrad(), {k: v for k, v in rec.f.items()
+                                                if not k.startswith("_") and k not in ("P", "Q", "dW", "partial")})
+                assert lib.b2h_wgrad_workspace_bytes(C.byref(desc), dtype) <= have, rec.tag
