@@ -386,8 +386,16 @@ def main():
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop()
     t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    ranks_in_sync = None
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        # data-parallel sanity: identical initial weights + summed gradients -> identical weights on every rank
+        chk = torch.stack([tr.g_store.flat.double().sum(), tr.g_store.flat.double().abs().sum(),
+                           tr.d_store.flat.double().sum(), tr.d_store.flat.double().abs().sum()])
+        hi, lo = chk.clone(), chk.clone()
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        ranks_in_sync = bool(((hi - lo).abs() <= 1e-9 * hi.abs()).all()) and bool(torch.isfinite(chk).all())
     dev_ms, e2e_ms = float(t[0]), float(t[1])
     frames = B * T * world * a.steps
     value = frames / (dev_ms * 1e-3)
@@ -411,6 +419,7 @@ def main():
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches) * a.steps,
+        "ranks_in_sync": ranks_in_sync,
         "wall_s": t_wall,
     }
     if rank == 0:

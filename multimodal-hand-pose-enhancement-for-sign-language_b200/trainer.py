@@ -108,6 +108,14 @@ class GanTrainer:
         else:
             self.g_store = nets.ParamStore(self.g_spec, dev, seed=seed)
             self.d_store = nets.ParamStore(self.d_spec, dev, seed=seed + 1)
+        # data parallel: both networks' gradients live in ONE buffer, so the pipelined gan_step needs a single
+        # collective per step (a collective costs ~0.1 ms at 8 GPUs, whatever its size here)
+        self._joint_grad = None
+        if world_size > 1 and stores is None and os.environ.get("B2H_NO_JOINT_ALLREDUCE") is None:
+            gn = (self.g_store.n + 63) // 64 * 64
+            self._joint_grad = torch.zeros(gn + self.d_store.n, dtype=torch.float32, device=dev)
+            self.g_store.grad = self._joint_grad[:self.g_store.n]
+            self.d_store.grad = self._joint_grad[gn:gn + self.d_store.n]
         self.g_opt = FlatAdam(self.g_store, lr)
         self.d_opt = FlatAdam(self.d_store, lr)
         # Philox (seed, step): the generator steps use the even steps 0, 2, 4, ..., the discriminator steps the
@@ -273,12 +281,24 @@ class GanTrainer:
             packs = plan.add_pack_buckets([names for *_, names in bp])
             self._buckets[key] = (bp, P, packs)
 
-    def _bwd_update(self, key: str, pack_after=None, opt_after=None):
+    def _bwd_update(self, key: str, pack_after=None, opt_after=None, joint=None):
         """Backward + optimizer step + weight repack of one network, bucket by bucket (see
         _build_bucket_programs).  pack_after / opt_after: events the repack / the parameter update must wait for
-        (a concurrent reader of the packed weights / parameters in gan_step)."""
+        (a concurrent reader of the packed weights / parameters in gan_step).  joint (a list): backward only —
+        the events that complete this network's gradients are appended and the caller issues one collective
+        for both networks, then _apply_update()."""
         plan, loss_prog = (self.G_train, self.g_loss_prog) if key == "g" else (self.D_train, self.d_loss_prog)
         cur = torch.cuda.current_stream(self.device)
+        if joint is not None:
+            for (s, e, _, _, _) in self._buckets[key][0]:
+                for side in self._run_bwd_ops(plan, s, e, cur):
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                    joint.append(ev)
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            joint.append(ev)
+            return
         extra = [ev for ev in (opt_after, pack_after) if ev is not None]
         if not self.bucketed_opt:
             self._bwd_bucketed(plan)
@@ -326,6 +346,15 @@ class GanTrainer:
             ev = torch.cuda.Event()
             ev.record(opt_stream)
             cur.wait_event(ev)
+
+    def _apply_update(self, key: str):
+        """Adam over the whole flat buffer + repack, on the current stream (after the caller's collective)."""
+        plan = self.G_train if key == "g" else self.D_train
+        bp, P, packs = self._buckets[key]
+        P.run("step")
+        for i in range(len(bp)):
+            P.run(f"b{i}")
+            plan.prog.run(packs[i])
 
     # ---- gradient all-reduce (data parallel) ---------------------------------------------------
     def bucket_plan(self, plan: nets.NetPlan):
@@ -439,7 +468,7 @@ class GanTrainer:
     # The packed (GEMM-layout) weights of a network are refreshed right after its Adam update, once per
     # step, and shared by its train and eval plans; the eval plan's only per-step preparation is folding the
     # running BN statistics (one launch).
-    def _g_ops(self, pack_after=None, adv_after=None, deferred_adv=None):
+    def _g_ops(self, pack_after=None, adv_after=None, deferred_adv=None, joint=None):
         """pack_after / adv_after: events of a concurrent discriminator step (gan_step) that the weight repack
         (it overwrites what the D step's eval generator reads) and the D scoring branch (it wants the updated
         discriminator) have to wait for.  deferred_adv = (prep_done, adv_done): the scoring of THIS step is left
@@ -467,8 +496,9 @@ class GanTrainer:
             self.G_train.prog.run_range(fe - 1, fe, cur.cuda_stream)   # writes G_train.out
             cur.wait_event(adv_done)
             self.g_loss_prog.run_range(ls, ls + 1, cur.cuda_stream)
-            self._bwd_update("g", pack_after=pack_after)
+            self._bwd_update("g", pack_after=pack_after, joint=joint)
             return
+        assert joint is None
         adv = self._get_adv_stream()
         fork = torch.cuda.Event()
         fork.record(cur)
@@ -556,17 +586,42 @@ class GanTrainer:
             self.D_train.prog.run("fwd")
             self.d_loss_prog.run("loss")
             # (Adam / repack change what the scoring branch reads: they wait for it)
-            self._bwd_update("d", opt_after=adv_done if lag_adv else None)
+            joint = [] if (self._joint_grad is not None and lag_adv) else None
+            self._bwd_update("d", opt_after=adv_done if lag_adv else None, joint=joint)
             d_done = torch.cuda.Event()
-            d_done.record(sd)
+            if joint is None:
+                d_done.record(sd)
         with torch.cuda.stream(sg):
             sg.wait_event(folded)
             if lag_adv:
-                self._g_ops(pack_after=geval_done, deferred_adv=(adv_prep, adv_done))
+                self._g_ops(pack_after=geval_done, deferred_adv=(adv_prep, adv_done), joint=joint)
             else:
                 self._g_ops(pack_after=geval_done, adv_after=d_done)
             g_done = torch.cuda.Event()
-            g_done.record(sg)
+            if joint is None:
+                g_done.record(sg)
+        if joint is not None:
+            # one collective over the joint gradient buffer of both networks, then the two updates side by side
+            import torch.distributed as dist
+            if self._comm_stream is None:
+                self._comm_stream = torch.cuda.Stream(self.device)
+            comm = self._comm_stream
+            for ev in joint:
+                comm.wait_event(ev)
+            with torch.cuda.stream(comm):
+                dist.all_reduce(self._joint_grad, op=dist.ReduceOp.SUM, group=self.pg)
+            reduced = torch.cuda.Event()
+            reduced.record(comm)
+            with torch.cuda.stream(sd):
+                sd.wait_event(reduced)
+                sd.wait_event(adv_done)
+                self._apply_update("d")
+                d_done.record(sd)
+            with torch.cuda.stream(sg):
+                sg.wait_event(reduced)
+                sg.wait_event(geval_done)
+                self._apply_update("g")
+                g_done.record(sg)
         outer.wait_event(d_done)
         outer.wait_event(g_done)
         if lag_adv:
