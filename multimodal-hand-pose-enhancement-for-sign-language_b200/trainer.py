@@ -108,10 +108,11 @@ class GanTrainer:
         else:
             self.g_store = nets.ParamStore(self.g_spec, dev, seed=seed)
             self.d_store = nets.ParamStore(self.d_spec, dev, seed=seed + 1)
-        # data parallel: both networks' gradients live in ONE buffer, so the pipelined gan_step needs a single
-        # collective per step (a collective costs ~0.1 ms at 8 GPUs, whatever its size here)
+        # data parallel, optional (B2H_JOINT_ALLREDUCE=1): both networks' gradients in ONE buffer, so the pipelined
+        # gan_step needs a single collective per step.  Measured: 2 GPUs 0.80 ms vs 0.82 ms per step with one
+        # collective per network, but 8 GPUs 1.11 ms vs 1.01 ms (single samples) -> off by default
         self._joint_grad = None
-        if world_size > 1 and stores is None and os.environ.get("B2H_NO_JOINT_ALLREDUCE") is None:
+        if world_size > 1 and stores is None and os.environ.get("B2H_JOINT_ALLREDUCE"):
             gn = (self.g_store.n + 63) // 64 * 64
             self._joint_grad = torch.zeros(gn + self.d_store.n, dtype=torch.float32, device=dev)
             self.g_store.grad = self._joint_grad[:self.g_store.n]
