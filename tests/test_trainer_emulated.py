@@ -160,3 +160,46 @@ def test_gan_steps_match_oracle(variant, rf, label_smooth):
         assert rel_err(sd["state"][i]["exp_avg"], s["exp_avg"]) < stol
         assert rel_err(sd["state"][i]["exp_avg_sq"], s["exp_avg_sq"]) < stol
         assert float(sd["state"][i]["step"]) == float(s["step"]) == 2.0
+
+
+def test_bucketed_optimizer_programs_equal_the_whole_update():
+    """The optimizer step split along the gradient buckets (Adam phase 1 once, phase 2 per flat range, repack per
+    bucket) must equal the single Adam op + the single repack: ranges tile the flat buffer, bias corrections are
+    advanced exactly once, every packed operand is rewritten by exactly one bucket."""
+    torch.manual_seed(3)
+    B, T = 4, 16
+    outs = []
+    for bucketed in (False, True):
+        tr = GanTrainer("v1", 36, 252, False, B, T, precision="fp32", device="cpu", lr=1e-3, drop_mode="none",
+                        n_buckets=3)
+        g = torch.Generator().manual_seed(5)
+        for key, store, opt, plan, loss_prog in (("g", tr.g_store, tr.g_opt, tr.G_train, tr.g_loss_prog),
+                                                 ("d", tr.d_store, tr.d_opt, tr.D_train, tr.d_loss_prog)):
+            store.grad.copy_(torch.randn(store.n, generator=g) * 1e-2)
+            opt.m.copy_(torch.randn(store.n, generator=g) * 1e-3)
+            opt.v.copy_(torch.rand(store.n, generator=g) * 1e-4)
+            opt.step.fill_(7)
+            bp, P, packs = tr._buckets[key]
+            # the buckets tile [0, n) exactly once
+            assert bp[0][3] == store.n and bp[-1][2] == 0 and all(a[2] == b[3] for a, b in zip(bp, bp[1:]))
+            if bucketed:
+                E.run_records(P.recs, *P.segments["step"])
+                for i in range(len(bp)):
+                    E.run_records(P.recs, *P.segments[f"b{i}"])
+                    E.run_records(plan.prog.recs, *plan.prog.segments[packs[i]])
+            else:
+                E.run_records(loss_prog.recs, *loss_prog.segments["opt"])
+                E.run_records(plan.prog.recs, *plan.prog.segments["pack"])
+            assert int(opt.step) == 8
+        outs.append({"g": tr.g_store.flat.clone(), "d": tr.d_store.flat.clone(),
+                     "gm": tr.g_opt.m.clone(), "gv": tr.g_opt.v.clone(),
+                     "wf": {n: b.wf.clone() for n, b in tr.G_train.bufs.items() if b.wf is not None},
+                     "wb": {n: b.wb.clone() for n, b in tr.D_train.bufs.items() if b.wb is not None},
+                     "bias": {n: b.bias.clone() for n, b in tr.D_train.bufs.items() if b.bias is not None}})
+    a, b = outs
+    for k in ("g", "d", "gm", "gv"):
+        assert torch.equal(a[k], b[k]), k
+    for k in ("wf", "wb", "bias"):
+        assert a[k].keys() == b[k].keys() and len(a[k]) > 0
+        for n in a[k]:
+            assert torch.equal(a[k][n], b[k][n]), (k, n)
