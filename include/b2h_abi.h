@@ -230,8 +230,18 @@ typedef struct {
   int32_t B, L, C, ld, src_f32;
 } b2h_to_ncl_t;
 
-/* L1Loss(out, gt) forward + backward in one pass (utils/constants.py:55, train_gan.py:292):
- *   loss[0] = mean|out - gt| ; dout = sign(out - gt) * gscale / numel written BLC act dtype. */
+/* Regression criterion of the generator step, forward + backward in one pass (LOSSES, utils/constants.py:53-58;
+ * train_gan.py:286-292).  With d = out - gt, n = numel, g = gscale / n:
+ *   B2H_LOSS_L1     nn.L1Loss():             loss = mean|d|            dout = sign(d) * g
+ *   B2H_LOSS_L2     nn.MSELoss():            loss = mean d^2           dout = 2 d * g
+ *   B2H_LOSS_HUBER1 nn.HuberLoss(delta=1.0): loss = mean(|d| < 1 ? d^2/2 : |d| - 1/2)
+ *                                            dout = clamp(d, -1, 1) * g
+ *   B2H_LOSS_ROBUST robust_loss AdaptiveLossFunction as train_gan.py:74-77,286-290 uses it: its latent alpha / scale
+ *                   are never handed to the optimiser (train_gan.py:69), so they stay at their initial values
+ *                   alpha = 2, scale = 1/2 (utils/robust_loss/adaptive.py:55-59) and the negative log-likelihood is
+ *                   mean(2 d^2) + log(1/2) + log sqrt(2 pi);  dout = 4 d * g
+ * dout is written BLC in the activation dtype. */
+enum { B2H_LOSS_L1 = 0, B2H_LOSS_L2 = 1, B2H_LOSS_HUBER1 = 2, B2H_LOSS_ROBUST = 3 };
 typedef struct {
   const float* out; /* NCL fp32 */
   const float* gt;  /* NCL fp32 */
@@ -241,6 +251,7 @@ typedef struct {
   uint32_t* ticket;
   int32_t B, C, L, ld, Cfill;
   float gscale;
+  int32_t kind;        /* B2H_LOSS_* (0 = L1) */
   float* dbias;        /* optional: column sums of dout as stored = bias gradient of the output layer [C] */
   double* dbias_accum; /* workspace for dbias: [16][C] doubles, zero-initialised, self-resetting */
 } b2h_l1_t;

@@ -14,6 +14,9 @@ ACT_NONE, ACT_LEAKY, ACT_RELU = 0, 1, 2
 ROW_IDENT, ROW_UP2, ROW_POOL2, ROW_BCAST = 0, 1, 2, 3
 SRC_NCL, SRC_ROWS, SRC_BCAST, SRC_MOTION = 0, 1, 2, 3
 DROP_NONE, DROP_MASK, DROP_PHILOX = 0, 1, 2
+# regression criterion of the generator step (b2h_l1_t.kind; --loss of train_gan.py, utils/constants.py:53-58)
+LOSS_L1, LOSS_L2, LOSS_HUBER1, LOSS_ROBUST = 0, 1, 2, 3
+LOSS_KINDS = {"L1": LOSS_L1, "L2": LOSS_L2, "Huber1": LOSS_HUBER1, "RobustLoss": LOSS_ROBUST}
 (OP_GEMM, OP_WGRAD, OP_BN_STATS, OP_BN_APPLY, OP_BN_BWD, OP_PREP, OP_TO_NCL, OP_L1, OP_MSE, OP_COLSUM,
  OP_ADAM, OP_PACK, OP_BN_FOLD, OP_ROT6D, OP_FILL, OP_PACK_MULTI, OP_BN_FOLD_MULTI, OP_FK) = range(1, 19)
 
@@ -88,7 +91,8 @@ class ToNcl(C.Structure):
 
 class L1(C.Structure):
     _fields_ = [("out", vp), ("gt", vp), ("dout", vp), ("loss", vp), ("partial", vp), ("ticket", vp),
-                ("B", i32), ("C", i32), ("L", i32), ("ld", i32), ("Cfill", i32), ("gscale", f32), ("dbias", vp), ("dbias_accum", vp)]
+                ("B", i32), ("C", i32), ("L", i32), ("ld", i32), ("Cfill", i32), ("gscale", f32), ("kind", i32),
+                ("dbias", vp), ("dbias_accum", vp)]
 
 
 class Mse(C.Structure):

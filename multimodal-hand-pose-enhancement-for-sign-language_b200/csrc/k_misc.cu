@@ -173,7 +173,7 @@ int launch_to_ncl(const b2h_to_ncl_t& d, int dtype, cudaStream_t s) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// L1 loss forward + backward (nn.L1Loss, utils/constants.py:55): one pass over out and gt
+// Regression criterion forward + backward (LOSSES, utils/constants.py:53-58; default nn.L1Loss): one pass over out, gt
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -210,8 +210,18 @@ __global__ void __launch_bounds__(256) l1_kernel(b2h_l1_t d, int cext, int spc) 
       if (c < d.C && l < d.L) {
         int64_t i = ((int64_t)b * d.C + c) * d.L + l;
         float diff = d.out[i] - d.gt[i];
-        acc += fabsf(diff);
-        sg = diff > 0.f ? gval : (diff < 0.f ? -gval : 0.f);  // sign(diff)/numel, sign(0) = 0
+        if (d.kind == B2H_LOSS_L1) {
+          acc += fabsf(diff);
+          sg = diff > 0.f ? gval : (diff < 0.f ? -gval : 0.f);  // sign(diff)/numel, sign(0) = 0
+        } else if (d.kind == B2H_LOSS_HUBER1) {                 // nn.HuberLoss(delta = 1)
+          const float a = fabsf(diff);
+          acc += a < 1.f ? 0.5f * diff * diff : a - 0.5f;
+          sg = fminf(fmaxf(diff, -1.f), 1.f) * gval;
+        } else {                                                // L2: d^2 ; ROBUST (alpha 2, scale 1/2): 2 d^2
+          const float w = d.kind == B2H_LOSS_ROBUST ? 2.f : 1.f;
+          acc += w * diff * diff;
+          sg = 2.f * w * diff * gval;
+        }
       }
       tile[j][tx] = sg;
       if (d.dbias) {   // column sum over this tile's 32 time steps, of the value as it is stored
@@ -264,13 +274,15 @@ __global__ void __launch_bounds__(256) l1_kernel(b2h_l1_t d, int cext, int spc) 
     if (tid < o) s_part[tid] += s_part[tid + o];
     __syncthreads();
   }
-  if (tid == 0) d.loss[0] = (float)(s_part[0] / (double)numel);
+  // ROBUST: the constant of the negative log-likelihood, log(scale) + log Z(alpha) = log(1/2) + log sqrt(2 pi)
+  if (tid == 0) d.loss[0] = (float)(s_part[0] / (double)numel + (d.kind == B2H_LOSS_ROBUST ? 0.22579135264472743 : 0.0));
 }
 
 int launch_l1(const b2h_l1_t& d, int dtype, cudaStream_t s) {
   B2H_CARVE(l1_kernel<__nv_bfloat16>);
   B2H_CARVE(l1_kernel<float>);
   B2H_CHECK_ARG(d.B > 0 && d.B <= 65535 && d.C > 0 && d.L > 0, B2H_ERR_SHAPE, "l1: bad shape");
+  B2H_CHECK_ARG(d.kind >= B2H_LOSS_L1 && d.kind <= B2H_LOSS_ROBUST, B2H_ERR_ARG, "l1: unknown loss kind");
   B2H_CHECK_ARG(!d.dout || (d.ld >= d.Cfill && d.Cfill >= d.C && d.Cfill % 4 == 0 && d.ld % 4 == 0), B2H_ERR_SHAPE,
                 "l1: bad dout shape");
   B2H_CHECK_ARG(!d.dbias || (d.dout && d.dbias_accum), B2H_ERR_ARG, "l1: dbias needs dout and its workspace");

@@ -87,8 +87,12 @@ class GanTrainer:
     def __init__(self, variant: str = "v1", in_dim: int = 36, out_dim: int = 252, require_feats: bool = False,
                  batch_size: int = 256, T: int = 64, precision: str = "bf16", device="cuda", lr: float = 1e-4,
                  seed: int = 23456, drop_mode: str = "philox", label_smooth: bool = False,
-                 world_size: int = 1, process_group=None, n_buckets: Optional[int] = None, stores=None):
+                 world_size: int = 1, process_group=None, n_buckets: Optional[int] = None, stores=None,
+                 loss: str = "L1"):
         self.device = torch.device(device)
+        if loss not in L.LOSS_KINDS:   # --loss of train_gan.py (LOSSES, utils/constants.py:53-58)
+            raise KeyError(f"loss must be one of {sorted(L.LOSS_KINDS)}, got {loss!r}")
+        self.loss = loss
         self.B, self.T, self.precision = batch_size, T, precision
         self.dtype = dtype_of(precision)
         self.variant, self.require_feats = variant, require_feats
@@ -246,8 +250,9 @@ class GanTrainer:
         with P.segment("loss"):
             P.add(L.OP_L1, "l1", out=Gt.out, gt=self.y, dout=olb.dpre, loss=self.losses[0:1], partial=self.l1_partial,
                   ticket=self.ticket[0:1], B=B, C=out_dim, L=T, ld=olb.Cp, Cfill=olb.Cp, gscale=1.0,
-                  dbias=None, dbias_accum=None)   # (l1 can also emit the bias gradient of the output layer, but
-            # the in-kernel column sums cost more than the separate 8 us colsum launch: 29.9 vs 13.4 + 7.7 us)
+                  kind=L.LOSS_KINDS[self.loss], dbias=None, dbias_accum=None)
+            # (l1 can also emit the bias gradient of the output layer, but the in-kernel column sums cost more than
+            # the separate 8 us colsum launch: 29.9 vs 13.4 + 7.7 us)
             P.add(L.OP_MSE, "adv", score=De.out_blc, dscore=None, loss=self.losses[1:2], add=self.losses[0:1],
                   total=self.losses[2:3], groups=1, n=B * Ld, ld=De.out_blc.shape[-1], target=[1.0, 0.0])
         with P.segment("opt"):

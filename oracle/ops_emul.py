@@ -300,11 +300,20 @@ def l1(f: Dict):
     B, C, L = f["B"], f["C"], f["L"]
     o, g = f["out"].reshape(B, C, L), f["gt"].reshape(B, C, L)
     d = o - g
-    f["loss"][0] = d.abs().double().mean().float()
+    kind = f.get("kind", 0)   # B2H_LOSS_* of include/b2h_abi.h: 0 L1, 1 L2, 2 Huber(delta 1), 3 frozen adaptive loss
+    if kind == 0:
+        val, grad = d.abs(), torch.sign(d)
+    elif kind == 2:
+        val, grad = torch.where(d.abs() < 1, 0.5 * d * d, d.abs() - 0.5), d.clamp(-1, 1)
+    else:
+        w = 2.0 if kind == 3 else 1.0
+        val, grad = w * d * d, 2.0 * w * d
+    const = 0.22579135264472743 if kind == 3 else 0.0   # log(1/2) + log sqrt(2 pi)
+    f["loss"][0] = (val.double().mean() + const).float()
     if f.get("dout") is not None:
         gv = f["gscale"] / d.numel()
         dout = f["dout"].reshape(B, L, -1)
-        dout[:, :, :C] = (torch.sign(d) * gv).permute(0, 2, 1).to(dout.dtype)
+        dout[:, :, :C] = (grad * gv).permute(0, 2, 1).to(dout.dtype)
         dout[:, :, C:f["Cfill"]] = 0
         if f.get("dbias") is not None:   # bias gradient of the output layer: column sums of dout as stored
             f["dbias"].copy_(dout[:, :, :C].double().sum((0, 1)).float())

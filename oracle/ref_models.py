@@ -266,8 +266,27 @@ def calc_motion(t):  # train_gan.py:209-211 (frame 0 minus frames 0..T-2; reprod
     return t[:, :, :1] - t[:, :, :-1]
 
 
-def generator_step(G, D, g_opt, x, y, feats=None, g_masks=None):
-    """train_gan.py:260-299 for one batch. Returns (g_loss, l1, adv, output)."""
+def reg_criterion(loss: str, out, y):
+    """LOSSES[--loss] as train_gan.py:74-77,286-292 evaluates it (utils/constants.py:53-58).  "RobustLoss": the
+    AdaptiveLossFunction's latent alpha / scale never reach the optimiser (train_gan.py:69 is built from
+    generator.parameters() only), so they keep their initial values alpha = 2, scale = 1/2
+    (utils/robust_loss/adaptive.py:55-59) and general.lossfun reduces to (d / scale)^2 / 2, to which
+    lossfun adds log(scale) + log Z(2) = log(1/2) + log sqrt(2 pi).  tests/test_oracle_vs_reference.py pins this
+    against the real class."""
+    if loss == "L1":
+        return nn.functional.l1_loss(out, y)
+    if loss == "L2":
+        return nn.functional.mse_loss(out, y)
+    if loss == "Huber1":
+        return nn.functional.huber_loss(out, y, delta=1.0)
+    if loss == "RobustLoss":
+        d = (out - y).reshape(out.shape[0], -1)
+        return torch.mean(0.5 * (d / 0.5) ** 2 + (math.log(0.5) + 0.5 * math.log(2.0 * math.pi)))
+    raise KeyError(loss)
+
+
+def generator_step(G, D, g_opt, x, y, feats=None, g_masks=None, loss="L1"):
+    """train_gan.py:260-299 for one batch. Returns (g_loss, l1, adv, output); `l1` is the regression term."""
     D.eval()
     G.train()
     G.set_masks(g_masks)
@@ -276,7 +295,7 @@ def generator_step(G, D, g_opt, x, y, feats=None, g_masks=None):
     with torch.no_grad():
         fake_score = D(fake_motion)
     fake_score = fake_score.detach()
-    l1 = nn.functional.l1_loss(out, y)
+    l1 = reg_criterion(loss, out, y)
     adv = nn.functional.mse_loss(fake_score, torch.ones_like(fake_score))
     g_loss = l1 + adv
     g_opt.zero_grad()

@@ -351,3 +351,51 @@ def test_pipelined_gan_step_equals_alternating_schedule(graph, lag):
         diff = (sa.flat - sp.flat).abs()
         assert float(diff.max()) <= 2.05e-3 * (n + 1)          # never more than the Adam step bound (lr = 1e-3)
         assert float((diff > 1e-6).float().mean()) < 5e-3      # and only on a handful of ~zero-gradient entries
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("loss", ["L2", "Huber1", "RobustLoss"])
+def test_generator_step_other_regression_losses(loss, precision):
+    """--loss {L2, Huber1, RobustLoss} (utils/constants.py:53-58; train_gan.py:286-292): the other kinds of the b2h_l1
+    kernel through one generator step with replayed dropout masks: loss value, the loss gradient as stored, and
+    (fp32) every parameter gradient against the oracle."""
+    torch.manual_seed(0)
+    B, T, cin, cout, lr = 16, 64, 36, 252, 1e-3
+    G = R.build_generator("v1", cin, cout, False)
+    D = R.build_discriminator(cout)
+    randomize_bn(G, 5)
+    randomize_bn(D, 6)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(B, cin, T, generator=g)
+    y = torch.randn(B, cout, T, generator=g) * 1.5    # |out - y| on both sides of Huber's delta = 1
+    tr = make_trainer("v1", False, B, T, precision, G, D, lr=lr, loss=loss)
+    tr.x.copy_(x)
+    tr.y.copy_(y)
+    g_opt = torch.optim.Adam(G.parameters(), lr=lr)
+    g_acts, _ = activation_hooks(G)
+    fp32 = precision == "fp32"
+    tol = FP32_TOL if fp32 else BF16_TOL
+    g_masks = R.make_masks(G, x, seed=100)
+    tr.G_train.set_masks(g_masks)
+    g_loss, reg, adv, out = R.generator_step(G, D, g_opt, x, y, None, g_masks, loss=loss)
+    tr.generator_step()
+    torch.cuda.synchronize()
+    assert rel_err(tr.G_train.out, out) <= tol
+    losses = tr.losses.cpu()
+    assert abs(float(losses[0]) - float(reg)) <= tol * abs(float(reg))
+    assert abs(float(losses[2]) - float(g_loss)) <= 20 * tol * abs(float(g_loss))
+    # the loss gradient the kernel stored (BLC rows of the output layer's dpre, activation dtype) against autograd's
+    # d reg / d out at the output the kernel read
+    o = tr.G_train.out.detach().float().cpu().reshape(B, cout, T).clone().requires_grad_(True)
+    dref, = torch.autograd.grad(R.reg_criterion(loss, o, y), o)
+    olb = tr.G_train.bufs[tr.G_train.out_layer.name]
+    dours = olb.dpre.reshape(B, T, -1)[:, :, :cout].permute(0, 2, 1).float().cpu()
+    assert rel_err(dours, dref) <= (FP32_TOL if fp32 else 2.0 ** -8)   # bf16: one rounding of the stored value
+    assert float(olb.dpre.reshape(B, T, -1)[:, :, cout:].float().abs().max()) == 0.0
+    if fp32:
+        flips = count_kink_flips(tr.G_train, g_acts)
+        gtol = 5e-5 if flips == 0 else 0.2
+        for k, p in G.named_parameters():
+            if p.grad is not None:
+                assert grads_close(tr.g_store.g(k).cpu(), p.grad, gtol), (k, flips)
+            check_adam_params(tr.g_store.p(k).cpu(), p, lr, k, tight=flips == 0)

@@ -114,3 +114,32 @@ def test_mac_counts_match_survey():
     assert abs(R.macs_per_clip(R.build_generator("v1", 36, 252, True), 64, "text") - 214.310e6) < 1e3
     assert abs(R.macs_per_clip(R.build_generator("b2h", 36, 252, True), 64, "image") - 238.689e6) < 1e3
     assert abs(R.macs_per_clip(R.build_discriminator(252), 63) - 3.018e6) < 1e3
+
+
+@pytest.mark.parametrize("loss", ["L1", "L2", "Huber1", "RobustLoss"])
+def test_reg_criterion_matches_reference_losses(loss):
+    """R.reg_criterion against LOSSES[--loss] evaluated exactly as train_gan.py:74-77,286-292 does, values and
+    gradients; "RobustLoss" = the real AdaptiveLossFunction at its (never optimised) initial alpha / scale."""
+    import sys
+    sys.path.insert(0, "/root/reference/utils")
+    try:
+        import constants
+    finally:
+        sys.path.pop(0)
+    g = torch.Generator().manual_seed(11)
+    B, C, T = 4, 252, 16
+    out = (torch.randn(B, C, T, generator=g) * 1.5).requires_grad_(True)
+    gt = torch.randn(B, C, T, generator=g)
+    crit = constants.LOSSES[loss]
+    if loss == "RobustLoss":
+        crit = crit(num_dims=C * T, float_dtype=torch.float32, device="cpu")
+        assert float(crit.alpha().min()) == float(crit.alpha().max()) == 2.0
+        assert abs(float(crit.scale().min()) - 0.5) < 1e-7 and abs(float(crit.scale().max()) - 0.5) < 1e-7
+        ref = torch.mean(crit.lossfun(torch.reshape(out, (B, -1)) - torch.reshape(gt, (B, -1))))
+    else:
+        ref = crit(out, gt)
+    ref_grad, = torch.autograd.grad(ref, out)
+    ours = R.reg_criterion(loss, out, gt)
+    our_grad, = torch.autograd.grad(ours, out)
+    assert abs(float(ours) - float(ref)) <= 1e-6 * abs(float(ref))
+    assert float((our_grad - ref_grad).abs().max()) <= 1e-6 * float(ref_grad.abs().max())

@@ -203,3 +203,43 @@ def test_bucketed_optimizer_programs_equal_the_whole_update():
         assert a[k].keys() == b[k].keys() and len(a[k]) > 0
         for n in a[k]:
             assert torch.equal(a[k][n], b[k][n]), (k, n)
+
+
+@pytest.mark.parametrize("loss", ["L2", "Huber1", "RobustLoss"])
+def test_generator_step_with_other_regression_losses(loss):
+    """--loss {L2, Huber1, RobustLoss} (utils/constants.py:53-58): the b2h_l1 op's other kinds, through one emulated
+    generator step against the oracle (loss value, every gradient, Adam update)."""
+    torch.manual_seed(0)
+    B, T, cin, cout, lr = 8, 16, 36, 252, 1e-3
+    G = R.build_generator("v1", cin, cout, False)
+    D = R.build_discriminator(cout)
+    randomize_bn(G, 5)
+    randomize_bn(D, 6)
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(B, cin, T, generator=g)
+    y = torch.randn(B, cout, T, generator=g) * 1.5   # |out - y| on both sides of Huber's delta = 1
+    tr = GanTrainer("v1", cin, cout, False, B, T, precision="fp32", device="cpu", lr=lr, drop_mode="mask", loss=loss)
+    tr.g_store.load_state_dict(G.state_dict())
+    tr.d_store.load_state_dict(D.state_dict())
+    tr.x.copy_(x)
+    tr.y.copy_(y)
+    g_opt = torch.optim.Adam(G.parameters(), lr=lr)
+    g_acts, _ = activation_hooks(G)
+    g_masks = R.make_masks(G, x, seed=100)
+    tr.G_train.set_masks(g_masks)
+    g_loss, reg, adv, out = R.generator_step(G, D, g_opt, x, y, None, g_masks, loss=loss)
+    emul_g_step(tr)
+    assert ((out - y).abs() > 1).any() and ((out - y).abs() < 1).any()
+    assert abs(float(tr.losses[0]) - float(reg)) < 2e-5 * abs(float(reg))
+    assert abs(float(tr.losses[2]) - float(g_loss)) < 1e-4 * abs(float(g_loss))
+    flips = count_kink_flips(tr.G_train, g_acts)
+    gtol = 5e-5 if flips == 0 else 0.2
+    for k, p in G.named_parameters():
+        if p.grad is not None:
+            assert grads_close(tr.g_store.g(k), p.grad, gtol), (k, flips)
+        check_adam_params(tr.g_store.p(k), p, lr, k, tight=flips == 0)
+
+
+def test_unknown_loss_is_rejected():
+    with pytest.raises(KeyError):
+        GanTrainer("v1", 36, 252, False, 4, 16, precision="fp32", device="cpu", loss="L3")

@@ -50,6 +50,20 @@ def _log(d):
         wandb.log(d)
 
 
+class FrozenAdaptiveLoss(nn.Module):
+    """`--loss RobustLoss` as the reference evaluates it (train_gan.py:74-77,286-290,336-339): the
+    AdaptiveLossFunction's alpha / scale are never given to an optimiser, so they stay at their initial values
+    alpha = 2, scale = 1/2 (utils/robust_loss/adaptive.py:55-59) and the loss is mean(2 d^2) + log(1/2) + log sqrt(2 pi)
+    (the fused path computes exactly this in b2h_l1, B2H_LOSS_ROBUST)."""
+
+    def forward(self, out, gt):
+        return 2.0 * torch.mean((out - gt) ** 2) + (np.log(0.5) + 0.5 * np.log(2.0 * np.pi))
+
+
+# utils/constants.py:53-58
+LOSSES = {"L1": nn.L1Loss(), "L2": nn.MSELoss(), "Huber1": nn.HuberLoss(delta=1.0), "RobustLoss": FrozenAdaptiveLoss()}
+
+
 def calc_motion(tensor):  # train_gan.py:209-211
     return tensor[:, :, :1] - tensor[:, :, :-1]
 
@@ -207,9 +221,9 @@ def main(args):
     discriminator.build_net(feature_out_dim)
     discriminator.precision = args.precision
     discriminator.to(device)
-    reg_criterion, gan_criterion = nn.L1Loss(), nn.MSELoss()
-    if args.loss != "L1":
-        raise SystemExit("the B200 path implements the reference's default --loss L1 (SURVEY.md 8f row 4)")
+    if args.loss not in LOSSES:
+        raise SystemExit(f"--loss must be one of {sorted(LOSSES)}")
+    reg_criterion, gan_criterion = LOSSES[args.loss], nn.MSELoss()
     trainer = None
     if args.autograd:
         g_optimizer = torch.optim.Adam(generator.parameters(), lr=args.learning_rate, weight_decay=0)
@@ -218,7 +232,8 @@ def main(args):
         T = train_X.shape[2]
         trainer = GanTrainer.from_modules(generator, discriminator, batch_size=args.batch_size, T=T,
                                           precision=args.precision, lr=args.learning_rate,
-                                          label_smooth=args.disc_label_smooth, world_size=world, process_group=pg)
+                                          label_smooth=args.disc_label_smooth, world_size=world, process_group=pg,
+                                          loss=args.loss)
         g_optimizer, d_optimizer = trainer.g_opt, trainer.d_opt
     if args.use_checkpoint:
         st = torch.load(os.path.join(args.model_path, f"lastCheckpoint_{args.exp_name}.pth"), map_location="cpu")
