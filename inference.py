@@ -55,21 +55,29 @@ def main(args):
     model.to(device).eval()
     kind = "text" if args.require_text else ("image" if args.require_image else None)
     if args.synthetic:
-        clips = b2h_data.synthetic_r6d(args.synthetic, args.frames, seed=99)
+        X, Y = b2h_data.split_pipeline(b2h_data.synthetic_r6d(args.synthetic, args.frames, seed=99), args.pipeline)
         feats = b2h_data.synthetic_feats(kind, args.synthetic, args.frames, seed=98)
-    else:
-        path = os.path.join(args.base_path, args.data_dir, b2h_data.DATA_PATHS_r6d["test"])
-        clips = b2h_data.make_equal_len(b2h_data._load_pickle(path))
-        feats = None   # loading of test embeddings follows train_gan.load_data
-    X, Y = b2h_data.split_pipeline(clips, args.pipeline)
+    else:                                                            # inference.py:52-60
+        text_path, image_path = b2h_data.feature_paths(args.data_dir, args.infer_set, args.embeds_type)
+        X, Y, feats = b2h_data.load_windows(f"{args.data_dir}/r6d_{args.infer_set}.pkl", args.pipeline,
+                                            kind == "text", text_path, kind == "image", image_path)
     X, Y, feats = b2h_data.rmv_clips_nan(X, Y, feats)
+    input_feats = X                       # arms + hands as loaded: the FK post-processing needs all 48 bones
+    if args.pipeline == "wh2wh":          # inference.py:72-73
+        X = X[:, :, 6 * 6:]
     X, Y = np.swapaxes(X, 1, 2).astype(np.float32), np.swapaxes(Y, 1, 2).astype(np.float32)
-    stats_path = os.path.join(args.model_path, f"{args.exp_name}{args.pipeline}_preprocess_core.npz")
-    if os.path.exists(stats_path):                                   # inference.py:80-87
+    feats = feats.astype(np.float32) if feats is not None else None
+    # the statistics train_gan.py saved next to the checkpoint (inference.py:79-87)
+    stats_name = f"{args.exp_name}{args.pipeline}_preprocess_core.npz"
+    stats_path = next((p for p in (os.path.join(os.path.split(args.checkpoint)[0], stats_name),
+                                   os.path.join(args.model_path, stats_name)) if os.path.exists(p)), None)
+    if stats_path is not None:
         c = np.load(stats_path)
         mX, sX, mY, sY = c["body_mean_X"], c["body_std_X"], c["body_mean_Y"], c["body_std_Y"]
-    else:
+    elif args.synthetic:
         mX, sX, mY, sY = b2h_data.calc_standard(X, Y, args.pipeline)
+    else:
+        raise SystemExit(f"{stats_name} not found next to the checkpoint or under --model_path")
     X = ((X - mX) / sX).astype(np.float32)
     Yn = ((Y - mY) / sY).astype(np.float32)
     X, Yn = X[rank::world], Yn[rank::world]
@@ -86,7 +94,8 @@ def main(args):
             outs.append(out)
     out = torch.cat(outs, 0)
     print(f">>> TOTAL ERROR: {err / max(steps * bs, 1)}", flush=True)
-    pred = out * torch.from_numpy(sY).to(device) + torch.from_numpy(mY).to(device)   # inference.py:134
+    sY_d, mY_d = (torch.from_numpy(np.asarray(a, dtype=np.float32)).to(device) for a in (sY, mY))
+    pred = out * sY_d + mY_d                                                         # inference.py:134
     r6d = pred.permute(0, 2, 1).contiguous()                                         # (N, T, 6*J)
     mats = rot6d_to_mat(r6d.reshape(r6d.shape[0], r6d.shape[1], -1, 6))
     os.makedirs(args.results_dir, exist_ok=True)
@@ -96,7 +105,10 @@ def main(args):
     print(f"saved {tuple(r6d.shape)} r6d and {tuple(mats.shape)} rotation matrices to {args.results_dir}", flush=True)
     # save_results (utils/utils.py:388-427): input + prediction -> axis-angle -> xyz over the 49-bone skeleton, with
     # the root bone / bone lengths the reference pickles next to the data (utils/utils.py:412-419)
-    if cin + cout == 48 * 6:
+    inp = input_feats[rank::world][:out.shape[0]]
+    if args.pipeline in ("arm_wh2wh", "wh2wh"):
+        inp = inp[:, :, :6 * 6]                                      # keep arms (utils/utils.py:396-397)
+    if inp.shape[2] + cout == 48 * 6:
         from b2h_b200 import postprocess as PP
         root_p, bone_p = os.path.join(args.base_path, "root.pkl"), os.path.join(args.base_path, "bone_len.pkl")
         if os.path.exists(root_p) and os.path.exists(bone_p):
@@ -108,9 +120,8 @@ def main(args):
             root = None
         if root is not None:
             n = out.shape[0]
-            x_raw = torch.from_numpy(X[:n]).to(device) * torch.from_numpy(sX.astype(np.float32)).to(device) + \
-                torch.from_numpy(mX.astype(np.float32)).to(device)
-            frames = torch.cat([x_raw, pred], dim=1).permute(0, 2, 1).reshape(-1, 288).contiguous()
+            frames = torch.cat([torch.from_numpy(np.ascontiguousarray(inp, dtype=np.float32)).to(device), r6d],
+                               dim=2).reshape(-1, 288).contiguous()   # np.concatenate((input, output), axis=2)
             xyz = PP.r6d_to_xyz(frames, root, bone).reshape(n, -1, 150)
             np.save(os.path.join(args.results_dir, f"{tag}_xyz.npy"), xyz.cpu().numpy())
             print(f"saved {tuple(xyz.shape)} joint positions (b2h_fk)", flush=True)
@@ -129,8 +140,10 @@ def build_parser():
     p.add_argument("--exp_name", type=str, default="experiment")
     p.add_argument("--model_path", type=str, default="models/")
     p.add_argument("--model", type=str, default="v1")
-    p.add_argument("--batch_size", type=int, default=64)
-    p.add_argument("--num_samples", type=int, default=10 ** 9)
+    p.add_argument("--infer_set", type=str, default="test")
+    p.add_argument("--batch_size", type=int, default=128)
+    p.add_argument("--seqs_to_viz", type=int, default=2, help="accepted for compatibility: GIF rendering is out of scope")
+    p.add_argument("--num_samples", type=int, default=3000)
     p.add_argument("--results_dir", type=str, default="results/")
     p.add_argument("--precision", type=str, default="fp32", choices=["fp32", "bf16"])
     p.add_argument("--synthetic", type=int, default=0)

@@ -99,6 +99,25 @@ def _load_pickle(path):
         return pickle.load(fh)
 
 
+def load_windows(data_path, pipeline, require_text=False, text_path=None, require_image=False, image_path=None):
+    """utils/load_save_utils.py:37-58: the r6d pickle cut / reflect-padded to 192 frames and split into the pipeline's
+    input / output joints, plus the sentence embeddings (N, 512) or the per-frame video features (N, T, 2000).
+    Returns (X, Y, feats) with feats None for body-only models (the reference returns `(X, feats)` in X's place)."""
+    X, Y = split_pipeline(make_equal_len(_load_pickle(data_path)), pipeline)
+    feats = None
+    if require_text and not require_image:
+        feats = np.asarray(_load_pickle(text_path))
+    elif require_image and not require_text:
+        feats = make_equal_len(_load_pickle(image_path))
+    return X, Y, feats
+
+
+def feature_paths(data_dir, split, embeds_type="normal"):
+    """train_gan.py:140-160 / inference.py:54-59: (text embeddings, video features) pickles of a split."""
+    pre = "" if embeds_type == "normal" else "average_"
+    return f"{data_dir}/{pre}{split}_sentence_embeddings.pkl", f"{data_dir}/{split}_vid_feats.pkl"
+
+
 def load_train_val(args, rng, data_dir):
     """train_gan.py:129-205.  Returns (train_X, train_Y, val_X, val_Y, train_feats, val_feats), X/Y as
     standardised (N, C, T) float32; the statistics are written to {exp}{pipeline}_preprocess_core.npz."""
@@ -107,18 +126,12 @@ def load_train_val(args, rng, data_dir):
     for name in ("train", "val"):
         if getattr(args, "synthetic", 0):
             n = args.synthetic if name == "train" else max(args.synthetic // 8, args.batch_size)
-            data = synthetic_r6d(n, args.frames, seed=23456 + (name == "val"))
+            X, Y = split_pipeline(synthetic_r6d(n, args.frames, seed=23456 + (name == "val")), args.pipeline)
             feats = synthetic_feats(kind, n, args.frames, seed=7 + (name == "val"))
         else:
-            path = os.path.join(args.base_path, data_dir, DATA_PATHS_r6d[name])
-            data = make_equal_len(_load_pickle(path))
-            feats = None
-            if kind == "text":
-                pre = "" if args.embeds_type == "normal" else "average_"
-                feats = np.asarray(_load_pickle(f"{data_dir}/{pre}{name}_sentence_embeddings.pkl"))
-            elif kind == "image":
-                feats = make_equal_len(_load_pickle(f"{data_dir}/{name}_vid_feats.pkl"))
-        X, Y = split_pipeline(data, args.pipeline)
+            text_path, image_path = feature_paths(data_dir, name, args.embeds_type)
+            X, Y, feats = load_windows(os.path.join(args.base_path, data_dir, DATA_PATHS_r6d[name]), args.pipeline,
+                                       kind == "text", text_path, kind == "image", image_path)
         if args.pipeline == "wh2wh":
             X = X[:, :, 6 * 6:]
         X, Y, feats = rmv_clips_nan(X, Y, feats)

@@ -53,3 +53,32 @@ def test_windows_and_nan_removal(ref_utils):
     F[5, 7] = np.nan
     for a, b in zip(pp.rmv_clips_nan(X.copy(), Y.copy(), F.copy()), data.rmv_clips_nan(X, Y, F)):
         np.testing.assert_array_equal(a, b)
+
+
+@pytest.mark.parametrize("pipeline,kind", [("arm2wh", None), ("arm_wh2wh", "text"), ("wh2wh", "image"),
+                                           ("arm_wh2finger7", None)])
+def test_load_windows(ref_utils, tmp_path, pipeline, kind):
+    """data.load_windows against utils/load_save_utils.py:37-58 on pickles of ragged clips (+ embeddings / video features)."""
+    import pickle
+    sys.path.insert(0, "/root/reference/utils")
+    try:
+        import load_save_utils
+    finally:
+        sys.path.pop(0)
+    rng = np.random.RandomState(2)
+    lens = (250, 100, 192, 40)
+    r6d, txt, img = tmp_path / "r6d_test.pkl", tmp_path / "txt.pkl", tmp_path / "img.pkl"
+    pickle.dump([rng.randn(n, 288).astype(np.float32) for n in lens], open(r6d, "wb"))
+    pickle.dump(rng.randn(len(lens), 512).astype(np.float32), open(txt, "wb"))
+    pickle.dump([rng.randn(n, 2000).astype(np.float32) for n in lens], open(img, "wb"))
+    ref = load_save_utils.load_windows(str(r6d), pipeline, require_text=kind == "text", text_path=str(txt),
+                                       require_image=kind == "image", image_path=str(img))
+    X, Y, F = data.load_windows(str(r6d), pipeline, kind == "text", str(txt), kind == "image", str(img))
+    ref_X, ref_F = ref[0] if kind else (ref[0], None)
+    np.testing.assert_array_equal(ref_X, X)
+    np.testing.assert_array_equal(ref[1], Y)
+    if kind:
+        np.testing.assert_array_equal(ref_F, F)
+    else:
+        assert F is None
+    assert X.shape == (len(lens), 192, 288 if pipeline in ("arm_wh2wh", "wh2wh") else data.FEATURE_MAP[pipeline][0])
