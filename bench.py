@@ -411,6 +411,9 @@ def main():
         "dtype": a.precision if a.precision == "bf16" else "f32", "data": "synthetic",
         "config": {"workload": workload_name(a), "global_batch": B * world, "frames": T,
                    "parallelism": f"dp{world}" if world > 1 else "single",
+                   **({"dp_exchange": "b2h_dp_adam: reduce-scatter + Adam + all-gather in one kernel over peer memory"
+                       if getattr(tr, "fused_dp", False) else "ncclAllReduce of the flat gradient, then b2h_adam"}
+                      if world > 1 else {}),
                    "timing": "CUDA events per step on the launch stream, 256 MiB L2 flush before every timed step, "
                              "CUDA-graph replay, dropout = Philox",
                    "schedule": ("pipelined: every timed step = discriminator step k overlapped with generator step "

@@ -406,13 +406,46 @@ int b2h_rot6d_to_mat(const b2h_rot6d_t* d, b2h_stream_t s);
 int b2h_fill(const b2h_fill_t* d, b2h_stream_t s);
 int b2h_fk(const b2h_fk_t* d, b2h_stream_t s);
 
+/* Data-parallel optimiser step as ONE kernel over NVLink peer memory (the gradient all-reduce of
+ * `train_gan.py`'s step under one process per GPU): reduce-scatter of the flat gradients, Adam on the owned slice,
+ * all-gather of the updated parameters — replaces ncclAllReduce(grad) + b2h_adam(phase 2) of a bucket.
+ *   entry barrier   every rank's gradients of the range are complete, and nobody still reads the old parameters
+ *   rank r, slice r g = sum_q g[q][i] in rank order (peer loads; or one multimem.ld_reduce through the NVSwitch
+ *                   when g_mc is given), Adam with the current `scalars` (b2h_adam phase 1 ran before) on the local
+ *                   moments m / v, which only hold meaningful values for the owned slice, new parameter stored to
+ *                   every rank's buffer (peer stores, or one multimem.st when p_mc is given)
+ *   exit barrier    every rank's parameters are complete and its gradients may be overwritten
+ * Every rank must call it with the same n / world and its own rank, in the same order on every rank; all pointers
+ * are peer-mapped device addresses of symmetric allocations (cudaIpc / cuMem fabric handles or
+ * torch.distributed._symmetric_memory).  `signal[q]` is rank q's signal pad for THIS call site:
+ * B2H_DP_MAX_BLOCKS * world uint32, zero-initialised once, self-resetting.  A peer that never arrives makes the
+ * kernel trap after `timeout_ms` (0: 10 s) instead of hanging the device.  CUDA-graph capturable. */
+#define B2H_DP_MAX_PEERS 16
+#define B2H_DP_MAX_BLOCKS 32
+typedef struct {
+  float* p[B2H_DP_MAX_PEERS];          /* every rank's parameter range [n] (own rank included) */
+  const float* g[B2H_DP_MAX_PEERS];    /* every rank's gradient range [n] */
+  uint32_t* signal[B2H_DP_MAX_PEERS];  /* every rank's signal pad */
+  const float* g_mc;                   /* optional multicast address of the gradient ranges (NVLS), else NULL */
+  float* p_mc;                         /* optional multicast address of the parameter ranges, else NULL */
+  float* m;                            /* local Adam moments [n] */
+  float* v;
+  int64_t n;                           /* multiple of 4; ranges 16-byte aligned */
+  int32_t rank, world;
+  double beta1, beta2, eps;
+  float gscale;                        /* 1 / world for the mean gradient of DDP */
+  const float* scalars;                /* the step's bias-correction scalars written by b2h_adam phase 1 */
+  int32_t timeout_ms;
+} b2h_dp_adam_t;
+int b2h_dp_adam(const b2h_dp_adam_t* d, b2h_stream_t s);
+
 /* recorded programs: the whole-graph entry points (generator forward / step, discriminator step)
  * are programs built by the host-side mirror of modelZoo and replayed with ONE call. */
 typedef struct b2h_program b2h_program;
 enum b2h_op_kind {
   B2H_OP_GEMM = 1, B2H_OP_WGRAD, B2H_OP_BN_STATS, B2H_OP_BN_APPLY, B2H_OP_BN_BWD, B2H_OP_PREP,
   B2H_OP_TO_NCL, B2H_OP_L1, B2H_OP_MSE, B2H_OP_COLSUM, B2H_OP_ADAM, B2H_OP_PACK, B2H_OP_BN_FOLD,
-  B2H_OP_ROT6D, B2H_OP_FILL, B2H_OP_PACK_MULTI, B2H_OP_BN_FOLD_MULTI, B2H_OP_FK
+  B2H_OP_ROT6D, B2H_OP_FILL, B2H_OP_PACK_MULTI, B2H_OP_BN_FOLD_MULTI, B2H_OP_FK, B2H_OP_DP_ADAM
 };
 b2h_program* b2h_program_create(int dtype);
 void b2h_program_destroy(b2h_program* p);

@@ -18,7 +18,7 @@ DROP_NONE, DROP_MASK, DROP_PHILOX = 0, 1, 2
 LOSS_L1, LOSS_L2, LOSS_HUBER1, LOSS_ROBUST = 0, 1, 2, 3
 LOSS_KINDS = {"L1": LOSS_L1, "L2": LOSS_L2, "Huber1": LOSS_HUBER1, "RobustLoss": LOSS_ROBUST}
 (OP_GEMM, OP_WGRAD, OP_BN_STATS, OP_BN_APPLY, OP_BN_BWD, OP_PREP, OP_TO_NCL, OP_L1, OP_MSE, OP_COLSUM,
- OP_ADAM, OP_PACK, OP_BN_FOLD, OP_ROT6D, OP_FILL, OP_PACK_MULTI, OP_BN_FOLD_MULTI, OP_FK) = range(1, 19)
+ OP_ADAM, OP_PACK, OP_BN_FOLD, OP_ROT6D, OP_FILL, OP_PACK_MULTI, OP_BN_FOLD_MULTI, OP_FK, OP_DP_ADAM) = range(1, 20)
 
 i32, i64, f32, f64, vp = C.c_int32, C.c_int64, C.c_float, C.c_double, C.c_void_p
 
@@ -147,10 +147,20 @@ class Fill(C.Structure):
     _fields_ = [("ptr", vp), ("bytes", i64), ("value", i32)]
 
 
+DP_MAX_PEERS, DP_MAX_BLOCKS = 16, 32
+
+
+class DpAdam(C.Structure):
+    """b2h_dp_adam_t: reduce-scatter(grad) + Adam + all-gather(param) over peer memory in one kernel."""
+    _fields_ = [("p", vp * DP_MAX_PEERS), ("g", vp * DP_MAX_PEERS), ("signal", vp * DP_MAX_PEERS),
+                ("g_mc", vp), ("p_mc", vp), ("m", vp), ("v", vp), ("n", i64), ("rank", i32), ("world", i32),
+                ("beta1", f64), ("beta2", f64), ("eps", f64), ("gscale", f32), ("scalars", vp), ("timeout_ms", i32)]
+
+
 OP_STRUCT = {OP_GEMM: Gemm, OP_WGRAD: Wgrad, OP_BN_STATS: BnStats, OP_BN_APPLY: BnApply, OP_BN_BWD: BnBwd,
              OP_PREP: Prep, OP_TO_NCL: ToNcl, OP_L1: L1, OP_MSE: Mse, OP_COLSUM: Colsum, OP_ADAM: Adam,
              OP_PACK: Pack, OP_BN_FOLD: BnFold, OP_ROT6D: Rot6d, OP_FILL: Fill, OP_PACK_MULTI: PackMulti,
-             OP_BN_FOLD_MULTI: BnFoldMulti, OP_FK: Fk}
+             OP_BN_FOLD_MULTI: BnFoldMulti, OP_FK: Fk, OP_DP_ADAM: DpAdam}
 KIND_OF = {v: k for k, v in OP_STRUCT.items()}
 
 # every symbol include/b2h_abi.h declares: name -> (restype, argtypes)
@@ -182,6 +192,7 @@ SYMBOLS = {
     "b2h_rot6d_to_mat": (C.c_int, [C.POINTER(Rot6d), vp]),
     "b2h_fill": (C.c_int, [C.POINTER(Fill), vp]),
     "b2h_fk": (C.c_int, [C.POINTER(Fk), vp]),
+    "b2h_dp_adam": (C.c_int, [C.POINTER(DpAdam), vp]),
     "b2h_program_create": (vp, [C.c_int]),
     "b2h_program_destroy": (None, [vp]),
     "b2h_program_add": (C.c_int, [vp, C.c_int, vp]),
@@ -195,7 +206,8 @@ ONESHOT = {OP_GEMM: ("b2h_gemm", True), OP_WGRAD: ("b2h_wgrad", True), OP_BN_STA
            OP_TO_NCL: ("b2h_to_ncl", True), OP_L1: ("b2h_l1", True), OP_MSE: ("b2h_mse", False),
            OP_COLSUM: ("b2h_colsum", True), OP_ADAM: ("b2h_adam", False), OP_PACK: ("b2h_pack", True),
            OP_BN_FOLD: ("b2h_bn_fold", False), OP_ROT6D: ("b2h_rot6d_to_mat", False), OP_FILL: ("b2h_fill", False),
-           OP_PACK_MULTI: ("b2h_pack_multi", True), OP_BN_FOLD_MULTI: ("b2h_bn_fold_multi", False), OP_FK: ("b2h_fk", False)}
+           OP_PACK_MULTI: ("b2h_pack_multi", True), OP_BN_FOLD_MULTI: ("b2h_bn_fold_multi", False), OP_FK: ("b2h_fk", False),
+           OP_DP_ADAM: ("b2h_dp_adam", False)}
 
 
 class B2HError(RuntimeError):

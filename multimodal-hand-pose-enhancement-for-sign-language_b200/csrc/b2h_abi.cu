@@ -73,6 +73,7 @@ union OpDesc {
   b2h_pack_multi_t pack_multi;
   b2h_bn_fold_multi_t bn_fold_multi;
   b2h_fk_t fk;
+  b2h_dp_adam_t dp_adam;
   OpDesc() { memset(this, 0, sizeof(*this)); }
 };
 
@@ -96,6 +97,7 @@ static size_t desc_size(int kind) {
     case B2H_OP_PACK_MULTI: return sizeof(b2h_pack_multi_t);
     case B2H_OP_BN_FOLD_MULTI: return sizeof(b2h_bn_fold_multi_t);
     case B2H_OP_FK: return sizeof(b2h_fk_t);
+    case B2H_OP_DP_ADAM: return sizeof(b2h_dp_adam_t);
     default: return 0;
   }
 }
@@ -129,6 +131,7 @@ static int run_op(const Op& op, int dtype, cudaStream_t s) {
     case B2H_OP_PACK_MULTI: return launch_pack_multi(op.d.pack_multi, dtype, s);
     case B2H_OP_BN_FOLD_MULTI: return launch_bn_fold_multi(op.d.bn_fold_multi, s);
     case B2H_OP_FK: return launch_fk(op.d.fk, s);
+    case B2H_OP_DP_ADAM: return launch_dp_adam(op.d.dp_adam, s);
     default: set_error("unknown op kind %d", op.kind); return B2H_ERR_ARG;
   }
 }
@@ -205,6 +208,10 @@ int b2h_bn_fold(const b2h_bn_fold_t* d, b2h_stream_t s) {
 int b2h_bn_fold_multi(const b2h_bn_fold_multi_t* d, b2h_stream_t s) {
   const int dtype = B2H_F32;
   B2H_ONESHOT(B2H_OP_BN_FOLD_MULTI, bn_fold_multi, d)
+}
+int b2h_dp_adam(const b2h_dp_adam_t* d, b2h_stream_t s) {
+  const int dtype = B2H_F32;
+  B2H_ONESHOT(B2H_OP_DP_ADAM, dp_adam, d)
 }
 int b2h_fk(const b2h_fk_t* d, b2h_stream_t s) {
   const int dtype = B2H_F32;

@@ -346,6 +346,7 @@ int launch_bn_fold(const b2h_bn_fold_t& d, cudaStream_t s);
 int launch_bn_fold_multi(const b2h_bn_fold_multi_t& d, cudaStream_t s);
 int launch_rot6d(const b2h_rot6d_t& d, cudaStream_t s);
 int launch_fill(const b2h_fill_t& d, cudaStream_t s);
+int launch_dp_adam(const b2h_dp_adam_t& d, cudaStream_t s);
 
 constexpr int kBnChunkRows = 64;  // rows per CTA of the BN / colsum reductions
 inline int bn_nchunks(int rows_per_group) { return ceil_div(rows_per_group, kBnChunkRows); }

@@ -51,6 +51,23 @@ class FlatAdam:
                         beta2=self.betas[1], eps=self.eps, gscale=float(gscale), step=self.step, scalars=self.scalars,
                         phase=phase)
 
+    def record_dp(self, prog: Program, pb: "PeerBuffers", site: int, gscale: float, lo: int, hi: int,
+                  tag: str = "dp_adam"):
+        """The phase-2 update of the flat range [lo, hi) fused with its collective: gradients summed over the ranks
+        through peer memory, Adam on the slice this rank owns, parameters stored to every rank (b2h_dp_adam)."""
+        assert self.store.flat.data_ptr() == pb.flat.data_ptr() and self.store.grad.data_ptr() == pb.grad.data_ptr()
+        assert lo % 4 == 0 and (hi - lo) % 4 == 0 and hi > lo
+        sig_off = 4 * site * PeerBuffers.SITE_WORDS
+        return prog.add(L.OP_DP_ADAM, tag, p=[a + 4 * lo for a in pb.p_ptrs], g=[a + 4 * lo for a in pb.g_ptrs],
+                        signal=[a + sig_off for a in pb.sig_ptrs],
+                        g_mc=pb.g_mc + 4 * lo if pb.g_mc else None, p_mc=pb.p_mc + 4 * lo if pb.p_mc else None,
+                        m=self.m[lo:hi], v=self.v[lo:hi], n=hi - lo, rank=pb.rank, world=pb.world,
+                        beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, gscale=float(gscale),
+                        scalars=self.scalars, timeout_ms=int(os.environ.get("B2H_DP_TIMEOUT_MS", "0")),
+                        _p=[t[lo:hi] for t in pb.p_tensors] if pb.p_tensors else None,
+                        _g=[t[lo:hi] for t in pb.g_tensors] if pb.g_tensors else None,
+                        _step=self.step, _lr=self.lr)
+
     def state_dict(self):
         st = self.store
         state = {}
@@ -81,6 +98,55 @@ class FlatAdam:
         self.lr, self.betas, self.eps = float(g["lr"]), tuple(g["betas"]), float(g["eps"])
 
 
+class PeerBuffers:
+    """Peer-mapped (symmetric) flat parameter / gradient buffers and signal pads of ONE network for the fused
+    data-parallel optimizer step (b2h_dp_adam, include/b2h_abi.h): every rank can load the other ranks' gradients
+    and store into their parameters over NVLink, so reduce-scatter + Adam + all-gather is one kernel."""
+    SITE_WORDS = L.DP_MAX_BLOCKS * L.DP_MAX_PEERS      # uint32 per call site (gradient bucket)
+
+    def __init__(self, rank, world, flat, grad, signals, p_ptrs, g_ptrs, sig_ptrs, p_mc=0, g_mc=0,
+                 p_tensors=None, g_tensors=None, handles=()):
+        assert 1 <= world <= L.DP_MAX_PEERS and len(p_ptrs) == len(g_ptrs) == len(sig_ptrs) == world
+        self.rank, self.world = rank, world
+        self.flat, self.grad, self.signals = flat, grad, signals
+        self.p_ptrs, self.g_ptrs, self.sig_ptrs = list(p_ptrs), list(g_ptrs), list(sig_ptrs)
+        self.p_mc, self.g_mc = int(p_mc or 0), int(g_mc or 0)
+        self.p_tensors, self.g_tensors = p_tensors, g_tensors   # every rank's buffers as tensors (in-process only)
+        self._handles = handles                                 # keeps the symmetric-memory handles alive
+
+    @classmethod
+    def symmetric(cls, n: int, n_sites: int, device, group, multicast: bool = True):
+        """One process per GPU: allocate through torch.distributed._symmetric_memory (cuMem + fabric / fd handles,
+        multicast object when the NVSwitch supports it) and exchange the peer mappings — a collective call."""
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        bufs, hdls = [], []
+        for numel, dt in ((n, torch.float32), (n, torch.float32), (n_sites * cls.SITE_WORDS, torch.int32)):
+            t = symm.empty(numel, dtype=dt, device=device)
+            t.zero_()
+            bufs.append(t)
+            hdls.append(symm.rendezvous(t, group))
+        torch.cuda.synchronize(device)
+        dist.barrier(group=group)          # every pad is zero before anybody signals
+        mc = [int(h.multicast_ptr or 0) if multicast else 0 for h in hdls[:2]]   # 0: no NVLS multicast object
+        if not all(mc):
+            mc = [0, 0]
+        return cls(hdls[0].rank, hdls[0].world_size, bufs[0], bufs[1], bufs[2], hdls[0].buffer_ptrs,
+                   hdls[1].buffer_ptrs, hdls[2].buffer_ptrs, p_mc=mc[0], g_mc=mc[1], handles=tuple(hdls))
+
+    @classmethod
+    def in_process(cls, n: int, n_sites: int, devices):
+        """All "ranks" inside one process (tests): CPU tensors for the emulated programs, or one CUDA device per
+        rank with peer access enabled (plain cudaMalloc memory is peer-addressable once access is on)."""
+        world = len(devices)
+        flats = [torch.zeros(n, dtype=torch.float32, device=d) for d in devices]
+        grads = [torch.zeros(n, dtype=torch.float32, device=d) for d in devices]
+        sigs = [torch.zeros(n_sites * cls.SITE_WORDS, dtype=torch.int32, device=d) for d in devices]
+        return [cls(r, world, flats[r], grads[r], sigs[r], [t.data_ptr() for t in flats],
+                    [t.data_ptr() for t in grads], [t.data_ptr() for t in sigs], p_tensors=flats, g_tensors=grads)
+                for r in range(world)]
+
+
 class GanTrainer:
     """One process = one GPU.  Static device buffers `x`, `y`, `feats` hold the current batch."""
 
@@ -88,7 +154,7 @@ class GanTrainer:
                  batch_size: int = 256, T: int = 64, precision: str = "bf16", device="cuda", lr: float = 1e-4,
                  seed: int = 23456, drop_mode: str = "philox", label_smooth: bool = False,
                  world_size: int = 1, process_group=None, n_buckets: Optional[int] = None, stores=None,
-                 loss: str = "L1"):
+                 loss: str = "L1", fused_dp: Optional[bool] = None, peer_buffers=None, rank: Optional[int] = None):
         self.device = torch.device(device)
         if loss not in L.LOSS_KINDS:   # --loss of train_gan.py (LOSSES, utils/constants.py:53-58)
             raise KeyError(f"loss must be one of {sorted(L.LOSS_KINDS)}, got {loss!r}")
@@ -121,6 +187,24 @@ class GanTrainer:
             self._joint_grad = torch.zeros(gn + self.d_store.n, dtype=torch.float32, device=dev)
             self.g_store.grad = self._joint_grad[:self.g_store.n]
             self.d_store.grad = self._joint_grad[gn:gn + self.d_store.n]
+        # data parallel, optional (fused_dp=True or B2H_FUSED_DP=1): parameters and gradients live in peer-mapped
+        # memory and the optimizer step of a bucket is ONE kernel that also does the exchange over NVLink
+        # (reduce-scatter of the gradients, Adam on the owned slice, all-gather of the parameters) instead of
+        # ncclAllReduce + Adam.  Not yet measured on hardware -> off by default.
+        if fused_dp is None:
+            fused_dp = world_size > 1 and bool(os.environ.get("B2H_FUSED_DP"))
+        self.fused_dp = bool(fused_dp)
+        self._peer = {}
+        if self.fused_dp:
+            if world_size <= 1 or stores is not None or self._joint_grad is not None:
+                raise ValueError("fused_dp needs world_size > 1, trainer-owned parameter stores and no joint all-reduce")
+            for key, store in (("g", self.g_store), ("d", self.d_store)):
+                pb = peer_buffers[key] if peer_buffers is not None else PeerBuffers.symmetric(
+                    store.n, self.n_buckets, dev, process_group, multicast=not os.environ.get("B2H_DP_NO_MULTICAST"))
+                assert pb.world == world_size and pb.flat.numel() == store.n and (rank is None or pb.rank == rank)
+                pb.flat.copy_(store.flat)
+                store.flat, store.grad = pb.flat, pb.grad
+                self._peer[key] = pb
         self.g_opt = FlatAdam(self.g_store, lr)
         self.d_opt = FlatAdam(self.d_store, lr)
         # Philox (seed, step): the generator steps use the even steps 0, 2, 4, ..., the discriminator steps the
@@ -282,7 +366,9 @@ class GanTrainer:
                 opt.record(P, phase=1, tag="adam_step")
             for i, (_, _, lo, hi, _) in enumerate(bp):
                 with P.segment(f"b{i}"):
-                    if hi > lo:
+                    if hi > lo and self.fused_dp:
+                        opt.record_dp(P, self._peer[key], i, 1.0 / self.world_size, lo, hi, tag=f"dp_adam_b{i}")
+                    elif hi > lo:
                         opt.record(P, gscale=1.0 / self.world_size, lo=lo, hi=hi, phase=2, tag=f"adam_b{i}")
             packs = plan.add_pack_buckets([names for *_, names in bp])
             self._buckets[key] = (bp, P, packs)
@@ -306,6 +392,7 @@ class GanTrainer:
             joint.append(ev)
             return
         extra = [ev for ev in (opt_after, pack_after) if ev is not None]
+        assert self.bucketed_opt or not self.fused_dp, "fused_dp runs through the bucketed optimizer programs"
         if not self.bucketed_opt:
             self._bwd_bucketed(plan)
             for ev in extra:
@@ -332,7 +419,7 @@ class GanTrainer:
                 evw = torch.cuda.Event()
                 evw.record(side)
                 deps.append(evw)
-            if self.world_size > 1 and hi > lo:
+            if self.world_size > 1 and hi > lo and not self.fused_dp:   # (fused: the exchange is inside b{i})
                 import torch.distributed as dist
                 if self._comm_stream is None:
                     self._comm_stream = torch.cuda.Stream(self.device)

@@ -22,7 +22,7 @@ ROW_IDENT, ROW_UP2, ROW_POOL2, ROW_BCAST = 0, 1, 2, 3
 SRC_NCL, SRC_ROWS, SRC_BCAST, SRC_MOTION = 0, 1, 2, 3
 DROP_NONE, DROP_MASK, DROP_PHILOX = 0, 1, 2
 (OP_GEMM, OP_WGRAD, OP_BN_STATS, OP_BN_APPLY, OP_BN_BWD, OP_PREP, OP_TO_NCL, OP_L1, OP_MSE, OP_COLSUM,
- OP_ADAM, OP_PACK, OP_BN_FOLD, OP_ROT6D, OP_FILL, OP_PACK_MULTI, OP_BN_FOLD_MULTI, OP_FK) = range(1, 19)
+ OP_ADAM, OP_PACK, OP_BN_FOLD, OP_ROT6D, OP_FILL, OP_PACK_MULTI, OP_BN_FOLD_MULTI, OP_FK, OP_DP_ADAM) = range(1, 20)
 
 
 def _act(x, act):
@@ -360,6 +360,38 @@ def adam(f: Dict):
     f["p"].addcdiv_(f["m"], denom, value=-(lr / bc1))
 
 
+def dp_slice(n: int, world: int, rank: int):
+    """The element range of the flat buffer that `rank` owns in b2h_dp_adam: ceil(n/4 / world) float4s per rank."""
+    n4 = n // 4
+    chunk = -(-n4 // world)
+    lo = min(chunk * rank, n4)
+    return 4 * lo, 4 * min(lo + chunk, n4)
+
+
+def dp_adam(f: Dict):
+    """b2h_dp_adam_t as ONE rank executes it: gradient slice summed over the ranks in rank order, Adam phase 2 on the
+    owned slice (local moments), the new parameters stored into every rank's buffer.  `_p` / `_g` hold every rank's
+    range as tensors (the descriptor itself carries peer pointers), `_step` / `_lr` what b2h_adam phase 1 turned into
+    `scalars`.  Interpreting the op of every rank, in any order, is the whole collective."""
+    lo, hi = dp_slice(f["n"], f["world"], f["rank"])
+    if hi <= lo:
+        return
+    g = torch.zeros(hi - lo)
+    for q in range(f["world"]):
+        g = g + f["_g"][q][lo:hi]
+    g = g * f["gscale"]
+    t = int(f["_step"][0])
+    b1, b2, lr, eps = f["beta1"], f["beta2"], f["_lr"], f["eps"]
+    m, v = f["m"][lo:hi], f["v"][lo:hi]
+    m.lerp_(g, 1 - b1)
+    v.mul_(b2).addcmul_(g, g, value=1 - b2)
+    bc1, bc2 = 1 - b1 ** t, 1 - b2 ** t
+    denom = (v.sqrt() / math.sqrt(bc2)).add_(eps)
+    newp = f["_p"][f["rank"]][lo:hi].addcdiv(m, denom, value=-(lr / bc1))
+    for q in range(f["world"]):
+        f["_p"][q][lo:hi] = newp
+
+
 def pack(f: Dict):
     W = f["W"].reshape(-1)
     nph, Op, nt, Ip = f["nphase"], f["Opad"], f["ntaps"], f["Ipad"]
@@ -423,7 +455,7 @@ def fill(f: Dict):
 DISPATCH = {OP_GEMM: gemm, OP_WGRAD: wgrad, OP_BN_STATS: bn_stats, OP_BN_APPLY: bn_apply, OP_BN_BWD: bn_bwd,
             OP_PREP: prep, OP_TO_NCL: to_ncl, OP_L1: l1, OP_MSE: mse, OP_COLSUM: colsum, OP_ADAM: adam,
             OP_PACK: pack, OP_BN_FOLD: bn_fold, OP_ROT6D: rot6d, OP_FILL: fill,
-            OP_PACK_MULTI: pack_multi, OP_BN_FOLD_MULTI: bn_fold_multi}
+            OP_PACK_MULTI: pack_multi, OP_BN_FOLD_MULTI: bn_fold_multi, OP_DP_ADAM: dp_adam}
 
 
 def run_records(recs, first=0, end=None):
