@@ -192,7 +192,8 @@ class GanTrainer:
         # (reduce-scatter of the gradients, Adam on the owned slice, all-gather of the parameters) instead of
         # ncclAllReduce + Adam.  Not yet measured on hardware -> off by default.
         if fused_dp is None:
-            fused_dp = world_size > 1 and bool(os.environ.get("B2H_FUSED_DP"))
+            fused_dp = world_size > 1 and stores is None and self._joint_grad is None and \
+                bool(os.environ.get("B2H_FUSED_DP"))
         self.fused_dp = bool(fused_dp)
         self._peer = {}
         if self.fused_dp:
