@@ -139,6 +139,9 @@ def test_descriptor_lowering():
 def test_dp_adam_kernel_two_devices():
     """The CUDA kernel with one rank per device inside one process (peer access on plain cudaMalloc memory): both
     launches are asynchronous, the CTAs of the two devices meet in the kernel's barriers.  Needs >= 2 GPUs."""
+    import os
+    if not os.environ.get("B2H_TEST_MULTI_GPU"):
+        pytest.skip("opt-in (B2H_TEST_MULTI_GPU=1): first hardware run of the kernel is the next round's, under a timeout")
     if torch.cuda.device_count() < 2 or not torch.cuda.can_device_access_peer(0, 1):
         pytest.skip("needs two peer-accessible GPUs")
     world, n = 2, 4 * 50021
