@@ -205,8 +205,9 @@ def main(args):
     torch.cuda.manual_seed(23456)
     data = load_data(args, rng, args.data_dir)
     train_X, train_Y, val_X, val_Y, train_feats, val_feats = data
-    if world > 1:   # shard clips across ranks (one process per GPU)
-        sl = slice(rank, None, world)
+    if world > 1:   # shard clips across ranks (one process per GPU); every rank gets the same number of clips, so
+        # every rank runs the same number of steps (each step holds a collective)
+        sl = slice(rank, (train_X.shape[0] // world) * world, world)
         train_X, train_Y = train_X[sl], train_Y[sl]
         train_feats = train_feats[sl] if train_feats is not None else None
     mod = MODELS[args.model]
