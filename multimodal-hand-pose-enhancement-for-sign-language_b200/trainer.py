@@ -196,6 +196,7 @@ class GanTrainer:
                 bool(os.environ.get("B2H_FUSED_DP"))
         self.fused_dp = bool(fused_dp)
         self._peer = {}
+        self._dp_order = None     # event after the last fused exchange kernel enqueued in the current step
         if self.fused_dp:
             if world_size <= 1 or stores is not None or self._joint_grad is not None:
                 raise ValueError("fused_dp needs world_size > 1, trainer-owned parameter stores and no joint all-reduce")
@@ -433,7 +434,15 @@ class GanTrainer:
                 deps = [done]
             for d in deps + extra:
                 target.wait_event(d)
+            fused = self.fused_dp and hi > lo
+            if fused and self._dp_order is not None:
+                # the fused exchange kernels of a step wait on their peers: chain them in enqueue order (the same
+                # on every rank), so that no rank can run two of them in the opposite order of another rank
+                target.wait_event(self._dp_order)
             P.run(f"b{i}", target.cuda_stream)
+            if fused:
+                self._dp_order = torch.cuda.Event()
+                self._dp_order.record(target)
             plan.prog.run(packs[i], target.cuda_stream)
             used_opt = used_opt or not last
         if used_opt:
@@ -648,6 +657,7 @@ class GanTrainer:
     def _gan_ops(self, lag_adv: bool):
         """[discriminator step on xd / yd] side by side with [generator step on x / y], see gan_step()."""
         assert self.overlap_adv, "gan_step needs the adversarial scoring branch on its own stream"
+        self._dp_order = None
         cur = torch.cuda.current_stream(self.device)
         if self._d_stream is None:
             # (raising the priority of the two dependency chains over the wgrad / scoring branches was measured
@@ -778,9 +788,11 @@ class GanTrainer:
             self.D_train._packed_version = self.d_store.version
 
     def _g_step_body(self):
+        self._dp_order = None
         self._g_ops()
 
     def _d_step_body(self):
+        self._dp_order = None
         self._d_ops()
 
     def _bump_step(self, key):
