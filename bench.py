@@ -38,6 +38,8 @@ def parse():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--frames", type=int, default=64)
     ap.add_argument("--mode", default="train", choices=["train", "infer"])
+    ap.add_argument("--pipeline", default="arm2wh", help="FEATURE_MAP row (utils/constants.py:11-27): arm2wh, "
+                    "arm_wh2wh, wh2wh, arm_wh2finger1..12 -- the incremental-fingers models of BASELINE config 5")
     ap.add_argument("--schedule", default="pipelined", choices=["pipelined", "sequential"],
                     help="pipelined: each discriminator step overlaps the next generator step (GanTrainer.gan_step); "
                          "sequential: generator_step then discriminator_step on the same batch")
@@ -51,7 +53,13 @@ def workload_name(a):
     if a.feats:
         cond = "+image" if a.variant == "b2h" else "+text"
     what = "GAN training step (1 generator step + 1 discriminator step)" if a.mode == "train" else "eval forward"
-    return f"{a.variant}{cond} arm2wh 36->252, {what}, batch {a.batch} x {a.frames} frames per GPU"
+    cin, cout = pipeline_dims(a)
+    return f"{a.variant}{cond} {a.pipeline} {cin}->{cout}, {what}, batch {a.batch} x {a.frames} frames per GPU"
+
+
+def pipeline_dims(a):
+    from b2h_b200.data import FEATURE_MAP
+    return FEATURE_MAP[a.pipeline]
 
 
 def synth_batch(B, T, cin, cout, feats_kind, seed=23456):
@@ -82,7 +90,7 @@ def run_cpu_reference(a, steps, warmup, device="cpu", autocast=False):
     from oracle import ref_models as R
     torch.set_num_threads(os.cpu_count() or 1)
     torch.manual_seed(23456)
-    cin, cout = 36, 252
+    cin, cout = pipeline_dims(a)
     feats_kind = None if not a.feats else ("image" if a.variant == "b2h" else "text")
     G = R.build_generator(a.variant, cin, cout, a.feats).to(device)
     D = R.build_discriminator(cout).to(device)
@@ -281,7 +289,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
         pg = dist.group.WORLD
-    cin, cout = 36, 252
+    cin, cout = pipeline_dims(a)
     feats_kind = None if not a.feats else ("image" if a.variant == "b2h" else "text")
     B, T = a.batch, a.frames
     kw = {}

@@ -11,6 +11,11 @@ run --mode infer --batch 1024 --frames 64
 run --mode infer --batch 4096 --frames 64
 run --mode infer --batch 256 --frames 1024
 run --mode infer --variant v2 --feats --batch 1024 --frames 64
+# incremental-fingers models (launch_exp_incr_fingers.sh: v2 + text, one model per pipeline)
+run --mode infer --variant v2 --feats --pipeline arm_wh2finger1 --batch 1024 --frames 64
+run --mode infer --variant v2 --feats --pipeline arm_wh2finger6 --batch 1024 --frames 64
+run --mode infer --variant v2 --feats --pipeline arm_wh2finger11 --batch 1024 --frames 64
+run --variant v2 --feats --pipeline arm_wh2finger6
 } > gpurun_out/bench_matrix_r01.jsonl
 python - <<'PY'
 import json
