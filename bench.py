@@ -38,6 +38,9 @@ def parse():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--frames", type=int, default=64)
     ap.add_argument("--mode", default="train", choices=["train", "infer"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default): --batch clips per GPU; strong: --batch clips in total, split over the GPUs "
+                         "(SURVEY 8d C3: strong scaling at global B = 256)")
     ap.add_argument("--pipeline", default="arm2wh", help="FEATURE_MAP row (utils/constants.py:11-27): arm2wh, "
                     "arm_wh2wh, wh2wh, arm_wh2finger1..12 -- the incremental-fingers models of BASELINE config 5")
     ap.add_argument("--schedule", default="pipelined", choices=["pipelined", "sequential"],
@@ -291,6 +294,9 @@ def main():
         pg = dist.group.WORLD
     cin, cout = pipeline_dims(a)
     feats_kind = None if not a.feats else ("image" if a.variant == "b2h" else "text")
+    if a.scaling == "strong":
+        assert a.batch % world == 0, "--scaling strong: --batch must be divisible by the number of GPUs"
+        a.batch //= world                     # from here on a.batch is the per-GPU batch
     B, T = a.batch, a.frames
     kw = {}
     if os.environ.get("B2H_BUCKETS"):
@@ -415,7 +421,7 @@ def main():
     line = {
         "metric": "training frames/sec" if a.mode == "train" else "inference frames/sec",
         "value": value, "unit": "frames/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
-        "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
         "dtype": a.precision if a.precision == "bf16" else "f32", "data": "synthetic",
         "config": {"workload": workload_name(a), "global_batch": B * world, "frames": T,
                    "parallelism": f"dp{world}" if world > 1 else "single",
