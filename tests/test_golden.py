@@ -118,3 +118,28 @@ def test_cuda_rot6d_matches_golden():
                   torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     assert rel_err(out, gold["mat"]) < 1e-5
+
+
+@pytest.mark.parametrize("loss", ["L1", "L2", "Huber1", "RobustLoss"])
+def test_loss_table_matches_golden(loss):
+    """tests/golden/losses.npz (tools/make_golden_losses.py: the reference's LOSSES table, "RobustLoss" through the real
+    AdaptiveLossFunction) against the oracle's reg_criterion and against the restatement of the b2h_l1 op
+    (value, gradient in the BLC layout, zero padding)."""
+    gold = np.load(os.path.join(GOLD, "losses.npz"))
+    out, gt = torch.from_numpy(gold["out"]), torch.from_numpy(gold["gt"])
+    ref_loss, ref_grad = float(gold[loss + "_loss"]), torch.from_numpy(gold[loss + "_grad"])
+    if loss == "RobustLoss":
+        assert np.all(gold["robust_alpha"] == 2.0) and np.allclose(gold["robust_scale"], 0.5, atol=1e-7)
+    o = out.clone().requires_grad_(True)
+    val = R.reg_criterion(loss, o, gt)
+    grad, = torch.autograd.grad(val, o)
+    assert abs(float(val) - ref_loss) <= 1e-6 * abs(ref_loss)
+    assert float((grad - ref_grad).abs().max()) <= 1e-6 * float(ref_grad.abs().max())
+    B, C, T = out.shape
+    Cp = 256
+    f = dict(out=out.contiguous(), gt=gt.contiguous(), dout=torch.full((B, T, Cp), 7.0), loss=torch.zeros(1), B=B, C=C, L=T,
+             ld=Cp, Cfill=Cp, gscale=1.0, kind={"L1": 0, "L2": 1, "Huber1": 2, "RobustLoss": 3}[loss])
+    E.l1(f)
+    assert abs(float(f["loss"][0]) - ref_loss) <= 1e-6 * abs(ref_loss)
+    assert float((f["dout"][:, :, :C].permute(0, 2, 1) - ref_grad).abs().max()) <= 1e-6 * float(ref_grad.abs().max())
+    assert float(f["dout"][:, :, C:].abs().max()) == 0.0
