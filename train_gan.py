@@ -78,7 +78,23 @@ def _batches(n, bs):
 
 
 def _to_dev(a):
+    if torch.is_tensor(a):          # device-resident dataset (fused path): a slice is already where it is needed
+        return a.to(device)
     return torch.from_numpy(np.ascontiguousarray(a)).to(device)
+
+
+class LossMeter:
+    """`avgLoss += loss.item() * batch_size` (train_gan.py:251,299) without a host synchronisation per step: the
+    running sum lives on the device in float64 and is read only where the reference prints it."""
+
+    def __init__(self, dev):
+        self.acc = torch.zeros((), dtype=torch.float64, device=dev)
+
+    def add(self, loss, weight):
+        self.acc += loss.detach().double().reshape(()) * weight
+
+    def value(self):
+        return float(self.acc)
 
 
 def train_discriminator(args, generator, discriminator, gan_criterion, d_optimizer, train_X, train_Y, epoch,
@@ -86,7 +102,7 @@ def train_discriminator(args, generator, discriminator, gan_criterion, d_optimiz
     generator.eval()
     discriminator.train()
     batchinds = _batches(train_X.shape[0], args.batch_size)
-    avg = 0.0
+    meter = LossMeter(device)
     for bi in batchinds:
         s = bi * args.batch_size
         x, y = _to_dev(train_X[s:s + args.batch_size]), _to_dev(train_Y[s:s + args.batch_size])
@@ -94,7 +110,7 @@ def train_discriminator(args, generator, discriminator, gan_criterion, d_optimiz
         if trainer is not None:
             trainer.load_batch(x, y, f)
             trainer.discriminator_step(graph=True)
-            d_loss = float(trainer.losses[3])
+            d_loss = trainer.losses[3]
         else:
             with torch.no_grad():
                 fake = generator(x, feats_=f).detach()
@@ -106,8 +122,9 @@ def train_discriminator(args, generator, discriminator, gan_criterion, d_optimiz
             d_optimizer.zero_grad()
             loss.backward()
             d_optimizer.step()
-            d_loss = loss.item()
-        avg += d_loss * args.batch_size
+            d_loss = loss
+        meter.add(d_loss, args.batch_size)
+    avg = meter.value()
     n = max(len(batchinds) * args.batch_size, 1)
     print(f"Epoch [{epoch}/{args.num_epochs - 1}], Tr. Disc. Loss: {avg / n}", flush=True)
     _log({"epoch": epoch, "loss_train_disc": avg / n})
@@ -119,7 +136,7 @@ def train_generator(args, generator, discriminator, reg_criterion, gan_criterion
     generator.train()
     batchinds = _batches(train_X.shape[0], args.batch_size)
     total = len(batchinds)
-    avg = 0.0
+    meter = LossMeter(device)
     for bii, bi in enumerate(batchinds):
         s = bi * args.batch_size
         x, y = _to_dev(train_X[s:s + args.batch_size]), _to_dev(train_Y[s:s + args.batch_size])
@@ -127,7 +144,7 @@ def train_generator(args, generator, discriminator, reg_criterion, gan_criterion
         if trainer is not None:
             trainer.load_batch(x, y, f)
             trainer.generator_step(graph=True)
-            g_loss = float(trainer.losses[2])
+            g_loss = trainer.losses[2]
         else:
             out = generator(x, feats_=f)
             with torch.no_grad():
@@ -138,13 +155,13 @@ def train_generator(args, generator, discriminator, reg_criterion, gan_criterion
             if clip_grad:
                 torch.nn.utils.clip_grad_norm_(generator.parameters(), 1)
             g_optimizer.step()
-            g_loss = loss.item()
-        avg += g_loss * args.batch_size
+            g_loss = loss
+        meter.add(g_loss, args.batch_size)
         if bii % args.log_step == 0:
-            m = avg / (total * args.batch_size)
+            m = meter.value() / (total * args.batch_size)
             print("Epoch [{}/{}], Step [{}/{}], Tr. Loss: {:.4f}, Tr. Perplexity: {:5.4f}".format(
                 epoch, args.num_epochs - 1, bii + 1, total, m, np.exp(m)), flush=True)
-    m = avg / max(total * args.batch_size, 1)
+    m = meter.value() / max(total * args.batch_size, 1)
     print("Epoch [{}/{}], Tr. Loss: {:.4f}, Tr. Perplexity: {:5.4f}".format(epoch, args.num_epochs - 1, m, np.exp(m)),
           flush=True)
     _log({"epoch": epoch, "loss_train_gen": m})
@@ -243,6 +260,12 @@ def main(args):
         st = torch.load(os.path.join(args.model_path, f"discriminator_{args.exp_name}.pth"), map_location="cpu")
         discriminator.load_state_dict(st["state_dict"], strict=False)
         d_optimizer.load_state_dict(st["d_optimizer"])
+    if trainer is not None and not args.host_data:
+        # the training set stays on the GPU (How2Sign r6d at T = 192 is ~7 GB of fp32); a batch is
+        # a device-to-device copy into the trainer's static buffers and the epoch shuffle is a device gather with
+        # the reference's permutation
+        train_X, train_Y = torch.from_numpy(train_X).to(device), torch.from_numpy(train_Y).to(device)
+        train_feats = torch.from_numpy(train_feats).to(device) if train_feats is not None else None
     currBestLoss, prev_save_epoch = 1e9, 0
     for epoch in range(args.num_epochs):
         args.epoch = epoch
@@ -259,7 +282,9 @@ def main(args):
                                                           d_optimizer, val_X, val_Y, currBestLoss, prev_save_epoch,
                                                           epoch, val_feats=val_feats)
         I = np.arange(len(train_X))
-        rng.shuffle(I)
+        rng.shuffle(I)                                        # train_gan.py:113-118, same generator, same order
+        if torch.is_tensor(train_X):
+            I = torch.from_numpy(I).to(train_X.device)
         train_X, train_Y = train_X[I], train_Y[I]
         if train_feats is not None:
             train_feats = train_feats[I]
@@ -291,6 +316,7 @@ def build_parser():
     # additions (defaults keep the reference's behaviour)
     p.add_argument("--precision", type=str, default="fp32", choices=["fp32", "bf16"])
     p.add_argument("--autograd", action="store_true", help="literal reference flow: torch autograd + torch.optim.Adam")
+    p.add_argument("--host_data", action="store_true", help="keep the training set in host memory (default: on the GPU)")
     p.add_argument("--synthetic", type=int, default=0, help="use N synthetic How2Sign-shaped clips instead of the pickles")
     p.add_argument("--frames", type=int, default=192, help="window length of the synthetic clips (reference: 192)")
     return p
