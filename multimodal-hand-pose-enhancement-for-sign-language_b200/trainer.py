@@ -128,11 +128,20 @@ class PeerBuffers:
             hdls.append(symm.rendezvous(t, group))
         torch.cuda.synchronize(device)
         dist.barrier(group=group)          # every pad is zero before anybody signals
-        mc = [int(h.multicast_ptr or 0) if multicast else 0 for h in hdls[:2]]   # 0: no NVLS multicast object
+        # a tensor may sit at an offset inside its symmetric block: peer addresses = block bases + that offset
+        offs = [int(getattr(h, "offset", 0) or 0) for h in hdls]
+        ptrs = [[int(a) + o for a in h.buffer_ptrs] for h, o in zip(hdls, offs)]
+        rank = hdls[0].rank
+        for t, pp in zip(bufs, ptrs):
+            if pp[rank] != t.data_ptr():
+                raise L.B2HError("symmetric memory: this rank's peer address does not match its local tensor "
+                                 f"({pp[rank]:#x} vs {t.data_ptr():#x})")
+        mc = [int(h.multicast_ptr or 0) + o if multicast and h.multicast_ptr else 0
+              for h, o in zip(hdls[:2], offs[:2])]                                  # 0: no NVLS multicast object
         if not all(mc):
             mc = [0, 0]
-        return cls(hdls[0].rank, hdls[0].world_size, bufs[0], bufs[1], bufs[2], hdls[0].buffer_ptrs,
-                   hdls[1].buffer_ptrs, hdls[2].buffer_ptrs, p_mc=mc[0], g_mc=mc[1], handles=tuple(hdls))
+        return cls(rank, hdls[0].world_size, bufs[0], bufs[1], bufs[2], ptrs[0], ptrs[1], ptrs[2],
+                   p_mc=mc[0], g_mc=mc[1], handles=tuple(hdls))
 
     @classmethod
     def in_process(cls, n: int, n_sites: int, devices):
