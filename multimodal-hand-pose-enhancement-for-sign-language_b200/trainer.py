@@ -144,6 +144,37 @@ class PeerBuffers:
                    p_mc=mc[0], g_mc=mc[1], handles=tuple(hdls))
 
     @classmethod
+    def ipc(cls, n: int, n_sites: int, device, group):
+        """One process per GPU, without torch's symmetric memory (`B2H_DP_PEER=ipc`): plain caching-allocator
+        tensors exported through CUDA IPC handles (torch.multiprocessing.reductions), opened by every peer, peer
+        access switched on by one tiny copy in each direction.  No multicast address in this mode.  Collective."""
+        import torch.distributed as dist
+        from torch.multiprocessing.reductions import reduce_tensor
+        device = torch.device(device)
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        own = [torch.zeros(n, dtype=torch.float32, device=device), torch.zeros(n, dtype=torch.float32, device=device),
+               torch.zeros(n_sites * cls.SITE_WORDS, dtype=torch.int32, device=device)]
+        torch.cuda.synchronize(device)
+        exported = [None] * world
+        dist.all_gather_object(exported, [reduce_tensor(t) for t in own], group=group)
+        opened, ptrs = [], [[], [], []]
+        for q in range(world):
+            for j in range(3):
+                if q == rank:
+                    t = own[j]
+                else:
+                    fn, args = exported[q][j]
+                    t = fn(*args)                    # the peer's tensor, mapped into this process
+                    probe = torch.zeros(1, dtype=t.dtype, device=device)
+                    probe.copy_(t[:1])               # either direction once: torch enables peer access for the pair
+                    t[:1].copy_(probe.zero_())       # (the buffers are still all zero)
+                opened.append(t)
+                ptrs[j].append(t.data_ptr())
+        torch.cuda.synchronize(device)
+        dist.barrier(group=group)
+        return cls(rank, world, own[0], own[1], own[2], ptrs[0], ptrs[1], ptrs[2], handles=tuple(opened))
+
+    @classmethod
     def in_process(cls, n: int, n_sites: int, devices):
         """All "ranks" inside one process (tests): CPU tensors for the emulated programs, or one CUDA device per
         rank with peer access enabled (plain cudaMalloc memory is peer-addressable once access is on)."""
@@ -210,8 +241,13 @@ class GanTrainer:
             if world_size <= 1 or stores is not None or self._joint_grad is not None:
                 raise ValueError("fused_dp needs world_size > 1, trainer-owned parameter stores and no joint all-reduce")
             for key, store in (("g", self.g_store), ("d", self.d_store)):
-                pb = peer_buffers[key] if peer_buffers is not None else PeerBuffers.symmetric(
-                    store.n, self.n_buckets, dev, process_group, multicast=not os.environ.get("B2H_DP_NO_MULTICAST"))
+                if peer_buffers is not None:
+                    pb = peer_buffers[key]
+                elif os.environ.get("B2H_DP_PEER") == "ipc":
+                    pb = PeerBuffers.ipc(store.n, self.n_buckets, dev, process_group)
+                else:
+                    pb = PeerBuffers.symmetric(store.n, self.n_buckets, dev, process_group,
+                                               multicast=not os.environ.get("B2H_DP_NO_MULTICAST"))
                 assert pb.world == world_size and pb.flat.numel() == store.n and (rank is None or pb.rank == rank)
                 pb.flat.copy_(store.flat)
                 store.flat, store.grad = pb.flat, pb.grad

@@ -7,7 +7,8 @@
 Per rank: two trainers with identical weights and batches, one per exchange; K pipelined GAN steps each; the
 parameters must agree to fp32 summation-order noise, every rank must hold the same parameters, and the device time
 per step of both is printed (CUDA events, max over ranks).  B2H_DP_NO_MULTICAST=1 forces the peer load / store
-path instead of multimem (NVLS).  The kernel traps after B2H_DP_TIMEOUT_MS (default 10 s) if a peer never arrives.
+path instead of multimem (NVLS); B2H_DP_PEER=ipc maps the peers through CUDA IPC handles instead of torch's symmetric
+memory.  The kernel traps after B2H_DP_TIMEOUT_MS (default 10 s) if a peer never arrives.
 """
 import os
 import sys
