@@ -185,3 +185,62 @@ def test_dp_adam_kernel_two_devices():
         assert float((pb.flat.cpu() - p).abs().max()) <= 1e-6 * float(p.abs().max())
         assert int(pb.signals.abs().max()) == 0
     assert torch.equal(pbs[0].flat.cpu(), pbs[1].flat.cpu())
+
+
+def test_signal_protocol_model():
+    """Randomised interleaving model of the kernel's barrier protocol (k_dp.cu: thread q of a CTA puts = CAS 0->1 on peer
+    q's slot [rank], then waits = CAS 1->0 on the own slot [q]; bar.sync around; the same slots serve the entry barrier,
+    the exit barrier and the next call): no deadlock, the pads end reset, no rank passes the entry barrier of call k
+    before every rank has finished call k-1's data phase and entered call k, nobody passes the exit barrier of call k
+    before every rank has finished its data phase — over several back-to-back calls (pads never re-initialised)."""
+    import random
+
+    def signal_thread(r, q, pads):
+        while pads[q][r] != 0:           # put: CAS(peer q's slot for me, 0 -> 1), spin while the last one is unconsumed
+            yield
+        pads[q][r] = 1
+        yield
+        while pads[r][q] != 1:           # wait: CAS(my slot for peer q, 1 -> 0)
+            yield
+        pads[r][q] = 0
+
+    for world in (2, 3, 8):
+        for seed in range(25):
+            rnd = random.Random(seed * 100 + world)
+            pads = [[0] * world for _ in range(world)]
+            calls, log = 4, []
+            phase = [0] * world          # per rank: 2 * call + (0 entry barrier | 1 exit barrier)
+            live = {r: [signal_thread(r, q, pads) for q in range(world)] for r in range(world)}
+            log += [("entered", r, 0) for r in range(world)]
+            steps = 0
+            while live:
+                r = rnd.choice(list(live))
+                for _ in range(rnd.choice((1, 1, 1, 7, 60))):      # bursts let one rank run far ahead
+                    if not live[r]:
+                        break
+                    t = rnd.choice(live[r])
+                    try:
+                        next(t)
+                    except StopIteration:
+                        live[r].remove(t)
+                if not live[r]:                                     # bar.sync: every signalling thread is through
+                    k, which = divmod(phase[r], 2)
+                    log.append(("passed_exit" if which else "passed_entry", r, k))
+                    phase[r] += 1
+                    if which == 0:
+                        log.append(("data_done", r, k))             # (the data phase itself has no synchronisation)
+                    elif k + 1 < calls:
+                        log.append(("entered", r, k + 1))
+                    if phase[r] < 2 * calls:
+                        live[r] = [signal_thread(r, q, pads) for q in range(world)]
+                    else:
+                        del live[r]
+                steps += 1
+                assert steps < 3_000_000, "deadlock / livelock in the signal protocol"
+            assert all(v == 0 for row in pads for v in row)
+            pos = {e: i for i, e in enumerate(log)}
+            for k in range(calls):
+                first_entry = min(pos[("passed_entry", r, k)] for r in range(world))
+                assert all(pos[("entered", r, k)] < first_entry for r in range(world))
+                first_exit = min(pos[("passed_exit", r, k)] for r in range(world))
+                assert all(pos[("data_done", r, k)] < first_exit for r in range(world))
