@@ -199,6 +199,11 @@ class GanTrainer:
         if loss not in L.LOSS_KINDS:   # --loss of train_gan.py (LOSSES, utils/constants.py:53-58)
             raise KeyError(f"loss must be one of {sorted(L.LOSS_KINDS)}, got {loss!r}")
         self.loss = loss
+        if T < 2 or T % 2:
+            # MaxPool1d(2) + ConvTranspose1d(stride 2) return 2 * floor(T / 2) frames (modelZoo.py:197,262): for odd T
+            # the reference's L1Loss(output, outputGT) (train_gan.py:292) fails on mismatched lengths as well
+            raise ValueError(f"the training step needs an even number of frames >= 2 per clip, got T = {T} "
+                             "(eval forwards of odd lengths go through the modelZoo modules)")
         self.B, self.T, self.precision = batch_size, T, precision
         self.dtype = dtype_of(precision)
         self.variant, self.require_feats = variant, require_feats

@@ -243,3 +243,17 @@ def test_generator_step_with_other_regression_losses(loss):
 def test_unknown_loss_is_rejected():
     with pytest.raises(KeyError):
         GanTrainer("v1", 36, 252, False, 4, 16, precision="fp32", device="cpu", loss="L3")
+
+
+def test_odd_window_length_is_rejected_like_the_reference():
+    """modelZoo's generator returns 2 * floor(T / 2) frames: the reference's L1Loss(output, outputGT) fails for odd T
+    (shape mismatch); the fused trainer says so at construction."""
+    G = R.build_generator("v1", 36, 252)
+    x, y = torch.randn(2, 36, 7), torch.randn(2, 252, 7)
+    G.eval()
+    with torch.no_grad():
+        assert G(x).shape[-1] == 6
+    with pytest.raises(RuntimeError):
+        torch.nn.L1Loss()(G(x), y)
+    with pytest.raises(ValueError):
+        GanTrainer("v1", 36, 252, False, 2, 7, precision="fp32", device="cpu")
