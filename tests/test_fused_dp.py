@@ -244,3 +244,51 @@ def test_signal_protocol_model():
                 assert all(pos[("entered", r, k)] < first_entry for r in range(world))
                 first_exit = min(pos[("passed_exit", r, k)] for r in range(world))
                 assert all(pos[("data_done", r, k)] < first_exit for r in range(world))
+
+
+def test_two_rank_fused_discriminator_step_equals_averaged_replicas():
+    """The discriminator's optimizer programs under fused_dp (grouped fake / real batch, one bucket): both ranks'
+    emulated steps against two reference replicas with averaged gradients + one torch.optim.Adam step."""
+    import copy
+    G, D, x, y, trs = _trainers(1)
+    run = lambda prog, seg: E.run_records(prog.recs, *prog.segments[seg])  # noqa: E731
+    G.eval()
+    masks = []
+    for r, tr in enumerate(trs):
+        xs, ys = x[r * B:(r + 1) * B], y[r * B:(r + 1) * B]
+        with torch.no_grad():
+            fake = G(xs)
+        mf = R.make_masks(D, R.calc_motion(fake), seed=200 + r)
+        mr = R.make_masks(D, R.calc_motion(ys), seed=300 + r)
+        masks.append((mf, mr))
+        tr.D_train.set_masks(mf, group=0)
+        tr.D_train.set_masks(mr, group=1)
+        tr._sync_d_batch()
+        for prog, seg in ((tr.G_train.prog, "pack"), (tr.G_eval.prog, "pack"), (tr.D_train.prog, "pack"),
+                          (tr.G_eval.prog, "fwd"), (tr.D_train.prog, "fwd"), (tr.d_loss_prog, "loss")):
+            run(prog, seg)
+    (s, e, lo, hi, _), = trs[0]._buckets["d"][0]
+    assert (lo, hi) == (0, trs[0].d_store.n)
+    for tr in trs:
+        run(tr._buckets["d"][1], "step")
+        E.run_records(tr.D_train.prog.recs, s, e)
+    sums = sum(tr.d_store.grad.clone() for tr in trs)
+    for tr in trs:
+        run(tr._buckets["d"][1], "b0")
+        run(tr.D_train.prog, tr._buckets["d"][2][0])
+    assert torch.equal(trs[0].d_store.flat, trs[1].d_store.flat)
+    # oracle
+    replicas = []
+    for r in range(WORLD):
+        Dr = copy.deepcopy(D)
+        xs, ys = x[r * B:(r + 1) * B], y[r * B:(r + 1) * B]
+        R.discriminator_step(G, Dr, torch.optim.SGD(Dr.parameters(), lr=0.0), xs, ys, None, masks[r][0], masks[r][1], False)
+        replicas.append(Dr)
+    opt = torch.optim.Adam(D.parameters(), lr=LR)
+    for (k, p), *rs in zip(D.named_parameters(), *[rep.named_parameters() for rep in replicas]):
+        p.grad = sum(q.grad for _, q in rs) / WORLD
+    opt.step()
+    st = trs[0].d_store
+    for k, p in D.named_parameters():
+        assert grads_close(st._view(sums, k, st.param_shapes, st.offsets) / WORLD, p.grad, 5e-4), k
+        check_adam_params(st.p(k), p, LR, k)
