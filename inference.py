@@ -35,24 +35,10 @@ def rot6d_to_mat(r6d: torch.Tensor) -> torch.Tensor:
     return out.reshape(*r6d.shape[:-1], 9)
 
 
-def main(args):
-    if not torch.cuda.is_available():
-        raise SystemExit("inference.py (B200 build) needs a CUDA device: there is no CPU fallback")
-    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
-    device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
-    torch.cuda.set_device(device)
-    cin, cout = b2h_data.FEATURE_MAP[args.pipeline]
-    mod = b2h_data.MODELS[args.model]
-    model = getattr(modelZoo, mod)()
-    if mod == "regressor_fcn_bn_32_b2h":
-        model.build_net(cin, cout, require_image=args.require_image)
-    else:
-        model.build_net(cin, cout, require_text=args.require_text)
-    model.precision = args.precision
-    if args.checkpoint and os.path.exists(args.checkpoint):
-        st = torch.load(args.checkpoint, map_location="cpu")
-        model.load_state_dict(st["state_dict"], strict=False)      # inference.py:41-43
-    model.to(device).eval()
+def prepare_inputs(args, rank: int = 0, world: int = 1):
+    """inference.py:50-87 of the reference: load the windows of the inference split (+ text / video features), drop
+    clips with NaNs, standardise with the statistics train_gan.py saved next to the checkpoint.  Returns
+    (X, Yn, feats, input_feats, (mX, sX, mY, sY)) with X / Yn standardised (N, C, T) float32, this rank's clips only."""
     kind = "text" if args.require_text else ("image" if args.require_image else None)
     if args.synthetic:
         X, Y = b2h_data.split_pipeline(b2h_data.synthetic_r6d(args.synthetic, args.frames, seed=99), args.pipeline)
@@ -80,8 +66,30 @@ def main(args):
         raise SystemExit(f"{stats_name} not found next to the checkpoint or under --model_path")
     X = ((X - mX) / sX).astype(np.float32)
     Yn = ((Y - mY) / sY).astype(np.float32)
-    X, Yn = X[rank::world], Yn[rank::world]
+    X, Yn, input_feats = X[rank::world], Yn[rank::world], input_feats[rank::world]
     feats = feats[rank::world] if feats is not None else None
+    return X, Yn, feats, input_feats, (mX, sX, mY, sY)
+
+
+def main(args):
+    if not torch.cuda.is_available():
+        raise SystemExit("inference.py (B200 build) needs a CUDA device: there is no CPU fallback")
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(device)
+    cin, cout = b2h_data.FEATURE_MAP[args.pipeline]
+    mod = b2h_data.MODELS[args.model]
+    model = getattr(modelZoo, mod)()
+    if mod == "regressor_fcn_bn_32_b2h":
+        model.build_net(cin, cout, require_image=args.require_image)
+    else:
+        model.build_net(cin, cout, require_text=args.require_text)
+    model.precision = args.precision
+    if args.checkpoint and os.path.exists(args.checkpoint):
+        st = torch.load(args.checkpoint, map_location="cpu")
+        model.load_state_dict(st["state_dict"], strict=False)      # inference.py:41-43
+    model.to(device).eval()
+    X, Yn, feats, input_feats, (mX, sX, mY, sY) = prepare_inputs(args, rank, world)
     outs, err, steps = [], 0.0, 0
     bs = args.batch_size
     with torch.no_grad():
@@ -105,7 +113,7 @@ def main(args):
     print(f"saved {tuple(r6d.shape)} r6d and {tuple(mats.shape)} rotation matrices to {args.results_dir}", flush=True)
     # save_results (utils/utils.py:388-427): input + prediction -> axis-angle -> xyz over the 49-bone skeleton, with
     # the root bone / bone lengths the reference pickles next to the data (utils/utils.py:412-419)
-    inp = input_feats[rank::world][:out.shape[0]]
+    inp = input_feats[:out.shape[0]]
     if args.pipeline in ("arm_wh2wh", "wh2wh"):
         inp = inp[:, :, :6 * 6]                                      # keep arms (utils/utils.py:396-397)
     if inp.shape[2] + cout == 48 * 6:

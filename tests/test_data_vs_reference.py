@@ -82,3 +82,70 @@ def test_load_windows(ref_utils, tmp_path, pipeline, kind):
     else:
         assert F is None
     assert X.shape == (len(lens), 192, 288 if pipeline in ("arm_wh2wh", "wh2wh") else data.FEATURE_MAP[pipeline][0])
+
+
+@pytest.mark.parametrize("pipeline,kind", [("arm2wh", None), ("wh2wh", "text"), ("arm_wh2finger9", "image")])
+def test_inference_prepare_inputs(ref_utils, tmp_path, pipeline, kind):
+    """inference.prepare_inputs (the kept inference.py, lines 50-87 of the reference) on real-format files: pickles of
+    ragged clips with a NaN clip, embeddings / video features, the *_preprocess_core.npz next to the checkpoint —
+    against the reference's own load_windows / rmv_clips_nan / standardisation lines; and the rank sharding."""
+    import os
+    import pickle
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import inference
+    sys.path.insert(0, "/root/reference/utils")
+    try:
+        import load_save_utils
+    finally:
+        sys.path.pop(0)
+    pp = ref_utils[1]
+    rng = np.random.RandomState(3)
+    lens = (250, 100, 192, 40, 300)
+    clips = [rng.randn(n, 288).astype(np.float32) for n in lens]
+    clips[1][5, 7] = np.nan
+    data_dir, ckpt_dir = tmp_path / "video_data", tmp_path / "models"
+    data_dir.mkdir()
+    ckpt_dir.mkdir()
+    pickle.dump(clips, open(data_dir / "r6d_val.pkl", "wb"))
+    pickle.dump(rng.randn(len(lens), 512).astype(np.float32), open(data_dir / "val_sentence_embeddings.pkl", "wb"))
+    pickle.dump([rng.randn(n, 2000).astype(np.float32) for n in lens], open(data_dir / "val_vid_feats.pkl", "wb"))
+    cin, cout = data.FEATURE_MAP[pipeline]
+    stats = dict(body_mean_X=rng.randn(1, cin, 1).astype(np.float32), body_std_X=rng.rand(1, cin, 1).astype(np.float32) + 0.5,
+                 body_mean_Y=rng.randn(1, cout, 1).astype(np.float32), body_std_Y=rng.rand(1, cout, 1).astype(np.float32) + 0.5)
+    np.savez_compressed(ckpt_dir / f"exp7{pipeline}_preprocess_core.npz", **stats)
+    argv = ["--checkpoint", str(ckpt_dir / "lastCheckpoint_exp7.pth"), "--data_dir", str(data_dir), "--pipeline", pipeline,
+            "--exp_name", "exp7", "--infer_set", "val", "--model_path", str(tmp_path / "nowhere")]
+    argv += {"text": ["--require_text"], "image": ["--require_image"], None: []}[kind]
+    args = inference.build_parser().parse_args(argv)
+    X, Yn, F, input_feats, st = inference.prepare_inputs(args)
+    # the reference's lines
+    tX, tY = load_save_utils.load_windows(str(data_dir / "r6d_val.pkl"), pipeline, require_text=kind == "text",
+                                          text_path=str(data_dir / "val_sentence_embeddings.pkl"),
+                                          require_image=kind == "image", image_path=str(data_dir / "val_vid_feats.pkl"))
+    tF = None
+    if kind:
+        tX, tF = tX
+    tX, tY, tF = pp.rmv_clips_nan(tX, tY, tF)
+    ref_input_feats = tX.copy()
+    if pipeline == "wh2wh":
+        tX = tX[:, :, 6 * 6:]
+    tX = np.swapaxes(tX, 1, 2).astype(np.float32)
+    tY = np.swapaxes(tY, 1, 2).astype(np.float32)
+    tX = (tX - stats["body_mean_X"]) / stats["body_std_X"]
+    tY = (tY - stats["body_mean_Y"]) / stats["body_std_Y"]
+    assert X.shape == (4, cin, 192)
+    np.testing.assert_array_equal(X, tX.astype(np.float32))
+    np.testing.assert_array_equal(Yn, tY.astype(np.float32))
+    np.testing.assert_array_equal(input_feats, ref_input_feats)
+    if kind:
+        np.testing.assert_array_equal(F, np.asarray(tF, dtype=np.float32))
+    else:
+        assert F is None
+    # two ranks partition the clips
+    parts = [inference.prepare_inputs(args, r, 2) for r in range(2)]
+    assert sorted(np.concatenate([p[0][:, 0, 0] for p in parts]).tolist()) == sorted(X[:, 0, 0].tolist())
+    assert all(p[0].shape[0] == p[3].shape[0] == 2 for p in parts)
+    # statistics are required for real data
+    args.checkpoint = str(tmp_path / "elsewhere" / "x.pth")
+    with pytest.raises(SystemExit):
+        inference.prepare_inputs(args)
