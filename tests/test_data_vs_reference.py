@@ -149,3 +149,53 @@ def test_inference_prepare_inputs(ref_utils, tmp_path, pipeline, kind):
     args.checkpoint = str(tmp_path / "elsewhere" / "x.pth")
     with pytest.raises(SystemExit):
         inference.prepare_inputs(args)
+
+
+@pytest.mark.parametrize("pipeline,kind", [("arm2wh", None), ("wh2wh", None), ("arm2wh", "text"), ("arm_wh2finger4", "image")])
+def test_load_train_val_matches_reference_load_data(tmp_path, pipeline, kind):
+    """data.load_train_val (behind the kept train_gan.load_data) against the REAL train_gan.load_data
+    (train_gan.py:127-205) on real-format pickles: standardised train / val arrays, the shuffle drawn from the same
+    RandomState, the feature arrays and the saved *_preprocess_core.npz."""
+    import argparse
+    import importlib.util
+    import os
+    import pickle
+    os.environ.setdefault("WANDB_MODE", "disabled")
+    saved = list(sys.path)
+    sys.path[:0] = ["/root/reference", "/root/reference/utils"]
+    try:
+        spec = importlib.util.spec_from_file_location("_ref_train_gan", "/root/reference/train_gan.py")
+        ref = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(ref)
+    finally:
+        sys.path[:] = saved
+    rng = np.random.RandomState(4)
+    data_dir = tmp_path / "video_data"
+    data_dir.mkdir()
+    for split, lens in (("train", (250, 100, 192, 40, 300, 192, 191)), ("val", (200, 64, 192))):
+        clips = [rng.randn(n, 288).astype(np.float32) * 0.7 + 0.1 for n in lens]
+        if split == "train":
+            clips[3][2, 100] = np.nan
+        pickle.dump(clips, open(data_dir / f"r6d_{split}.pkl", "wb"))
+        pickle.dump(rng.randn(len(lens), 512).astype(np.float32), open(data_dir / f"{split}_sentence_embeddings.pkl", "wb"))
+        pickle.dump([rng.randn(n, 2000).astype(np.float32) for n in lens], open(data_dir / f"{split}_vid_feats.pkl", "wb"))
+    outs = []
+    for which in ("ref", "ours"):
+        args = argparse.Namespace(base_path="", pipeline=pipeline, require_text=kind == "text", require_image=kind == "image",
+                                  embeds_type="normal", model_path=str(tmp_path / f"models_{which}") + "/", exp_name="e1",
+                                  synthetic=0, batch_size=2, frames=192)
+        r = np.random.RandomState(23456)
+        res = ref.load_data(args, r, str(data_dir)) if which == "ref" else data.load_train_val(args, r, str(data_dir))
+        outs.append((res, dict(np.load(os.path.join(args.model_path, f"e1{pipeline}_preprocess_core.npz"))), r.rand()))
+    (a, sa, ra), (b, sb, rb) = outs
+    assert ra == rb                                   # the generators were advanced identically
+    for k in sa:
+        np.testing.assert_array_equal(sa[k], sb[k])
+    for i in range(4):
+        assert a[i].dtype == b[i].dtype == np.float32
+        np.testing.assert_array_equal(a[i], b[i])
+    if kind:
+        np.testing.assert_array_equal(np.asarray(a[4], dtype=np.float32), b[4])
+        np.testing.assert_array_equal(np.asarray(a[5], dtype=np.float32), b[5])
+    else:
+        assert len(a) == 4 and b[4] is None and b[5] is None
