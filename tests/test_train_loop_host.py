@@ -90,3 +90,47 @@ def test_epoch_shuffle_order_is_the_references():
         rng_b.shuffle(J)
         b = b[torch.from_numpy(J)]
         np.testing.assert_array_equal(a, b.numpy())
+
+
+class _Gen(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.lin = torch.nn.Conv1d(6, 7, 1)
+
+    def forward(self, x, audio_=None, percent_rand_=0.7, feats_=None):
+        return self.lin(x) + (0.0 if feats_ is None else feats_.mean())
+
+
+def test_val_generator_loss_and_checkpoints(tmp_path):
+    """train_gan.py:312-372: batches of batch_size // 2 (incomplete one dropped), mean of loss * vbs, checkpoint files
+    and their dictionary keys on improvement only."""
+    X, Y, F = _data(11)
+    torch.manual_seed(0)
+    gen, disc = _Gen(), torch.nn.Conv1d(7, 1, 1)
+    g_opt, d_opt = torch.optim.Adam(gen.parameters()), torch.optim.Adam(disc.parameters())
+    args = argparse.Namespace(batch_size=6, num_epochs=5, model_path=str(tmp_path / "m"), exp_name="e9")
+    crit = torch.nn.L1Loss()
+    best, saved = train_gan.val_generator(args, gen, disc, crit, g_opt, d_opt, X, Y, 1e9, 0, 3, val_feats=F)
+    with torch.no_grad():
+        expect = sum(crit(gen(torch.from_numpy(X[3 * i:3 * i + 3]), feats_=torch.from_numpy(F[3 * i:3 * i + 3])),
+                          torch.from_numpy(Y[3 * i:3 * i + 3])).item() * 3 for i in range(3)) / 9
+    assert abs(best - expect) < 1e-7 and saved == 3
+    ck = torch.load(tmp_path / "m" / "e9_checkpoint.pth")
+    assert set(ck) == {"epoch", "state_dict", "g_optimizer"} and ck["epoch"] == 3
+    assert set(ck["state_dict"]) == set(gen.state_dict())
+    dk = torch.load(tmp_path / "m" / "discriminator_e9.pth")
+    assert set(dk) == {"epoch", "state_dict", "d_optimizer"}
+    assert train_gan.lastCheckpoint == str(tmp_path / "m" / "e9_checkpoint.pth")
+    # no improvement: nothing is rewritten, the best loss and its epoch stay
+    os.remove(tmp_path / "m" / "e9_checkpoint.pth")
+    best2, saved2 = train_gan.val_generator(args, gen, disc, crit, g_opt, d_opt, X, Y, best - 1e-3, 3, 4, val_feats=F)
+    assert best2 == best - 1e-3 and saved2 == 3 and not os.path.exists(tmp_path / "m" / "e9_checkpoint.pth")
+
+
+def test_frozen_adaptive_loss_is_the_oracle_formula():
+    from oracle import ref_models as R
+    g = torch.Generator().manual_seed(0)
+    o, t = torch.randn(3, 7, 5, generator=g), torch.randn(3, 7, 5, generator=g)
+    assert abs(float(train_gan.LOSSES["RobustLoss"](o, t)) - float(R.reg_criterion("RobustLoss", o, t))) < 1e-6
+    for k in ("L1", "L2", "Huber1"):
+        assert abs(float(train_gan.LOSSES[k](o, t)) - float(R.reg_criterion(k, o, t))) < 1e-7
