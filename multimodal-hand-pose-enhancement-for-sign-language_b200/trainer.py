@@ -241,6 +241,7 @@ class GanTrainer:
                 bool(os.environ.get("B2H_FUSED_DP"))
         self.fused_dp = bool(fused_dp)
         self._peer = {}
+        self._watch = []          # (module, store) pairs whose torch-side versions are checked before a step
         self._dp_order = None     # event after the last fused exchange kernel enqueued in the current step
         if self.fused_dp:
             if world_size <= 1 or stores is not None or self._joint_grad is not None:
@@ -314,7 +315,19 @@ class GanTrainer:
         d_store = discriminator._materialize(dev)
         v, cin, cout, rf, D = generator._spec_args
         assert D == 256, "the fused trainer is built for default_size=256"
-        return cls(v, cin, cout, rf, batch_size, T, precision=precision, device=dev, stores=(g_store, d_store), **kw)
+        tr = cls(v, cin, cout, rf, batch_size, T, precision=precision, device=dev, stores=(g_store, d_store), **kw)
+        tr._watch = [(generator, g_store), (discriminator, d_store)]
+        return tr
+
+    def _sync_module_versions(self):
+        """from_modules: parameters changed through the modules' torch API since the last look (load_state_dict,
+        an in-place edit, a torch optimizer) must trigger a repack of the GEMM operand copies — the same bookkeeping
+        as the modules' own forward (modelzoo._B2HModule.forward)."""
+        for mod, store in self._watch:
+            v = mod._param_versions()
+            if v != mod._seen_versions:
+                store.version += 1
+                mod._seen_versions = v
 
     def load_batch(self, x, y, feats=None):
         """Copy one batch (device or pinned-host tensors in the reference layouts) into the static buffers: it is
@@ -826,6 +839,7 @@ class GanTrainer:
 
     def _ensure_packed(self):
         """Weights changed from outside (load_state_dict, user edits): repack before the step."""
+        self._sync_module_versions()
         self.G_train.ensure_packed()
         self.D_train.ensure_packed()
 

@@ -1,0 +1,86 @@
+"""The fused trainer over the parameters of drop-in modelZoo modules (GanTrainer.from_modules — what the kept
+train_gan.py builds), on CPU: the modules' parameters / BatchNorm buffers ARE the trainer's flat buffers, so one emulated
+generator step must show up in `generator.state_dict()`, match the oracle's step, and parameters loaded through the
+modules' torch API (`load_state_dict`, as `--use_checkpoint` does) must reach the trainer and trigger a repack.
+(The modules are bound to a CPU store through the test hook `_allow_cpu_store`; executing a program natively on CPU
+still raises.)"""
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+import modelZoo  # noqa: E402  (the drop-in at the repo root)
+from b2h_b200 import _lib as L  # noqa: E402
+from b2h_b200.trainer import GanTrainer  # noqa: E402
+from oracle import ref_models as R  # noqa: E402
+from tests.test_plan_emulated import randomize_bn, rel_err  # noqa: E402
+from tests.test_trainer_emulated import check_adam_params, emul_g_step, grads_close  # noqa: E402
+
+
+def _modules(cin=36, cout=252):
+    g = modelZoo.regressor_fcn_bn_32()
+    g.build_net(cin, cout, require_text=False)
+    d = modelZoo.regressor_fcn_bn_discriminator()
+    d.build_net(cout)
+    for m in (g, d):
+        m._allow_cpu_store = True
+    return g, d
+
+
+def test_fused_step_updates_the_modules_and_matches_the_oracle():
+    torch.manual_seed(0)
+    B, T, cin, cout, lr = 8, 16, 36, 252, 1e-3
+    Gm, Dm = _modules(cin, cout)
+    G, D = R.build_generator("v1", cin, cout), R.build_discriminator(cout)
+    randomize_bn(G, 5)
+    randomize_bn(D, 6)
+    tr = GanTrainer.from_modules(Gm, Dm, batch_size=B, T=T, precision="fp32", lr=lr, drop_mode="mask")
+    # the module tensors alias the flat buffers
+    k = "decoder.9.weight"
+    assert dict(Gm.named_parameters())[k].data_ptr() == tr.g_store.p(k).data_ptr()
+    assert dict(Gm.named_buffers())["encoder.3.running_mean"].data_ptr() == tr.g_store.b("encoder.3.running_mean").data_ptr()
+    # weights arrive through the torch API of the modules, as train_gan.py --use_checkpoint loads them
+    v0 = (tr.g_store.version, tr.d_store.version)
+    Gm.load_state_dict(G.state_dict(), strict=False)
+    Dm.load_state_dict(D.state_dict(), strict=False)
+    tr._sync_module_versions()
+    assert tr.g_store.version > v0[0] and tr.d_store.version > v0[1]
+    v1 = tr.g_store.version
+    tr._sync_module_versions()
+    assert tr.g_store.version == v1                   # nothing changed since: no further repack
+    assert rel_err(tr.g_store.p(k), G.state_dict()[k]) == 0.0
+    g = torch.Generator().manual_seed(1)
+    x, y = torch.randn(B, cin, T, generator=g), torch.randn(B, cout, T, generator=g)
+    tr.load_batch(x, y)
+    masks = R.make_masks(G, x, seed=100)
+    tr.G_train.set_masks(masks)
+    g_opt = torch.optim.Adam(G.parameters(), lr=lr)
+    g_loss, l1, adv, out = R.generator_step(G, D, g_opt, x, y, None, masks)
+    emul_g_step(tr)
+    assert rel_err(tr.G_train.out, out) < 3e-5
+    assert abs(float(tr.losses[2]) - float(g_loss)) < 1e-4 * abs(float(g_loss))
+    sd = Gm.state_dict()                                # what train_gan.py checkpoints
+    for name, p in G.named_parameters():
+        if p.grad is not None:
+            assert grads_close(tr.g_store.g(name), p.grad, 0.2), name
+        check_adam_params(sd[name], p, lr, name, tight=False)
+        assert float((sd[name] - tr.g_store.p(name)).abs().max()) == 0.0
+    for name, b in G.state_dict().items():
+        if name.endswith(("running_mean", "running_var")) and name.rsplit(".", 1)[0] in {l.bnkey for l in tr.g_spec.layers}:
+            assert rel_err(sd[name], b) < 5e-5, name
+    assert int(sd["encoder.3.num_batches_tracked"]) == int(G.state_dict()["encoder.3.num_batches_tracked"])
+    # the optimizer object train_gan.py checkpoints has torch.optim.Adam's layout
+    osd = tr.g_opt.state_dict()
+    assert osd["param_groups"][0]["params"] == g_opt.state_dict()["param_groups"][0]["params"]
+    assert float(osd["state"][0]["step"]) == 1.0
+
+
+def test_programs_still_refuse_to_run_on_cpu():
+    Gm, _ = _modules()
+    Gm.eval()
+    with pytest.raises(L.B2HError):
+        Gm(torch.randn(2, 36, 16))
