@@ -84,3 +84,56 @@ def test_programs_still_refuse_to_run_on_cpu():
     Gm.eval()
     with pytest.raises(L.B2HError):
         Gm(torch.randn(2, 36, 16))
+
+
+def test_train_generator_loop_over_an_emulated_trainer(capsys):
+    """The kept train_gan.train_generator / train_discriminator loops driving a module-backed trainer whose steps are
+    interpreted on CPU (dropout off): three batches of each, against the oracle's step bodies on the same batches."""
+    import argparse
+    os.environ.setdefault("WANDB_MODE", "disabled")
+    import train_gan
+    from tests.test_trainer_emulated import emul_d_step
+    torch.manual_seed(0)
+    B, T, cin, cout, lr = 8, 16, 36, 252, 1e-3
+    Gm, Dm = _modules(cin, cout)
+    G, D = R.build_generator("v1", cin, cout), R.build_discriminator(cout)
+    randomize_bn(G, 5)
+    randomize_bn(D, 6)
+    for m in (G, D):
+        for mod in m.modules():
+            if isinstance(mod, R.ReplayDropout):
+                mod.p = 0.0
+    tr = GanTrainer.from_modules(Gm, Dm, batch_size=B, T=T, precision="fp32", lr=lr, drop_mode="none")
+    Gm.load_state_dict(G.state_dict(), strict=False)
+    Dm.load_state_dict(D.state_dict(), strict=False)
+    tr.generator_step = lambda graph=False: emul_g_step(tr)
+    tr.discriminator_step = lambda graph=False: emul_d_step(tr)
+    g = torch.Generator().manual_seed(1)
+    X = torch.randn(3 * B + 3, cin, T, generator=g).numpy()
+    Y = torch.randn(3 * B + 3, cout, T, generator=g).numpy()
+    args = argparse.Namespace(batch_size=B, num_epochs=2, log_step=1, disc_label_smooth=False)
+    g_opt, d_opt = torch.optim.Adam(G.parameters(), lr=lr), torch.optim.Adam(D.parameters(), lr=lr)
+    train_gan.train_generator(args, Gm, Dm, None, None, tr.g_opt, X, Y, 0, trainer=tr)
+    out = capsys.readouterr().out
+    ref_losses = []
+    for i in range(3):
+        xs, ys = torch.from_numpy(X[i * B:(i + 1) * B]), torch.from_numpy(Y[i * B:(i + 1) * B])
+        ref_losses.append(float(R.generator_step(G, D, g_opt, xs, ys)[0]))
+    m = sum(l * B for l in ref_losses) / (3 * B)
+    assert "Epoch [0/1], Tr. Loss: {:.4f}".format(m) in out
+    assert float(tr.g_opt.step) == 3.0
+    sd = Gm.state_dict()
+    for name, p in G.named_parameters():
+        assert float((sd[name] - p.detach()).abs().max()) <= 3 * 2.05 * lr, name     # three Adam steps
+    # (Adam divides by sqrt(v) + eps: where a gradient is ~0, fp32 noise decides the direction of a step — hence the
+    # step-size bound above; the typical element agrees far better)
+    typical = float((sd["decoder.9.weight"] - G.state_dict()["decoder.9.weight"]).abs().median())
+    assert typical < 0.02 * lr, typical
+    train_gan.train_discriminator(args, Gm, Dm, None, tr.d_opt, X, Y, 1, trainer=tr)
+    out = capsys.readouterr().out
+    G.load_state_dict({k: v for k, v in sd.items() if k in G.state_dict()})       # same generator on both sides
+    ref_d = [float(R.discriminator_step(G, D, d_opt, torch.from_numpy(X[i * B:(i + 1) * B]),
+                                        torch.from_numpy(Y[i * B:(i + 1) * B]))[0]) for i in range(3)]
+    shown = float(out.split("Tr. Disc. Loss:")[1].split()[0])
+    assert abs(shown - sum(ref_d) / 3) < 2e-2 * abs(shown)
+    assert float(tr.d_opt.step) == 3.0
