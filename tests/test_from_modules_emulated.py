@@ -17,13 +17,20 @@ import modelZoo  # noqa: E402  (the drop-in at the repo root)
 from b2h_b200 import _lib as L  # noqa: E402
 from b2h_b200.trainer import GanTrainer  # noqa: E402
 from oracle import ref_models as R  # noqa: E402
-from tests.test_plan_emulated import randomize_bn, rel_err  # noqa: E402
+from tests.test_plan_emulated import feats_for, randomize_bn, rel_err  # noqa: E402
 from tests.test_trainer_emulated import check_adam_params, emul_g_step, grads_close  # noqa: E402
 
 
-def _modules(cin=36, cout=252):
-    g = modelZoo.regressor_fcn_bn_32()
-    g.build_net(cin, cout, require_text=False)
+CLASSES = {"v1": "regressor_fcn_bn_32", "b2h": "regressor_fcn_bn_32_b2h", "v2": "regressor_fcn_bn_32_v2",
+           "v4": "regressor_fcn_bn_32_v4", "v4_deeper": "regressor_fcn_bn_32_v4_deeper"}
+
+
+def _modules(cin=36, cout=252, variant="v1", rf=False):
+    g = getattr(modelZoo, CLASSES[variant])()
+    if variant == "b2h":
+        g.build_net(cin, cout, require_image=rf)
+    else:
+        g.build_net(cin, cout, require_text=rf)
     d = modelZoo.regressor_fcn_bn_discriminator()
     d.build_net(cout)
     for m in (g, d):
@@ -31,11 +38,13 @@ def _modules(cin=36, cout=252):
     return g, d
 
 
-def test_fused_step_updates_the_modules_and_matches_the_oracle():
+@pytest.mark.parametrize("variant,rf", [("v1", False), ("v1", True), ("b2h", True), ("v2", True), ("v4", True),
+                                        ("v4_deeper", False)])
+def test_fused_step_updates_the_modules_and_matches_the_oracle(variant, rf):
     torch.manual_seed(0)
     B, T, cin, cout, lr = 8, 16, 36, 252, 1e-3
-    Gm, Dm = _modules(cin, cout)
-    G, D = R.build_generator("v1", cin, cout), R.build_discriminator(cout)
+    Gm, Dm = _modules(cin, cout, variant, rf)
+    G, D = R.build_generator(variant, cin, cout, rf), R.build_discriminator(cout)
     randomize_bn(G, 5)
     randomize_bn(D, 6)
     tr = GanTrainer.from_modules(Gm, Dm, batch_size=B, T=T, precision="fp32", lr=lr, drop_mode="mask")
@@ -55,11 +64,12 @@ def test_fused_step_updates_the_modules_and_matches_the_oracle():
     assert rel_err(tr.g_store.p(k), G.state_dict()[k]) == 0.0
     g = torch.Generator().manual_seed(1)
     x, y = torch.randn(B, cin, T, generator=g), torch.randn(B, cout, T, generator=g)
-    tr.load_batch(x, y)
-    masks = R.make_masks(G, x, seed=100)
+    f = feats_for(variant, rf, B, T, g)
+    tr.load_batch(x, y, f)
+    masks = R.make_masks(G, x, seed=100, feats=f)
     tr.G_train.set_masks(masks)
     g_opt = torch.optim.Adam(G.parameters(), lr=lr)
-    g_loss, l1, adv, out = R.generator_step(G, D, g_opt, x, y, None, masks)
+    g_loss, l1, adv, out = R.generator_step(G, D, g_opt, x, y, f, masks)
     emul_g_step(tr)
     assert rel_err(tr.G_train.out, out) < 3e-5
     assert abs(float(tr.losses[2]) - float(g_loss)) < 1e-4 * abs(float(g_loss))
