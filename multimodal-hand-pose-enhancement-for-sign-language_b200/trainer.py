@@ -471,8 +471,11 @@ class GanTrainer:
         opt_stream = self._opt_streams[key]
         P.run("step")                                   # advance the Adam step / bias corrections once
         used_opt = False
+        carried = []     # side-stream gradients of earlier buckets that a LATER bucket's update consumes
+        g0 = plan.store.grad.data_ptr()
         for i, (s, e, lo, hi, _) in enumerate(bp):
-            used_sides = self._run_bwd_ops(plan, s, e, cur)
+            side_ops = []
+            used_sides = self._run_bwd_ops(plan, s, e, cur, side_ops)
             last = i == len(bp) - 1
             target = cur if last else opt_stream
             deps = []
@@ -480,10 +483,19 @@ class GanTrainer:
                 ev = torch.cuda.Event()
                 ev.record(cur)
                 deps.append(ev)
+            side_events = {}
             for side in used_sides:
                 evw = torch.cuda.Event()
                 evw.record(side)
                 deps.append(evw)
+                side_events[side] = evw
+            deps += carried
+            # a layer stored below this bucket's range (parameter order = the reference's registration order, not
+            # the backward order: v4's text branch) is updated by a later bucket, which must see its gradient
+            for side, rec in side_ops:
+                out = rec.f["dW"] if rec.kind == L.OP_WGRAD else rec.f["out"]
+                if (out.data_ptr() - g0) // 4 < lo and side_events[side] not in carried:
+                    carried.append(side_events[side])
             if self.world_size > 1 and hi > lo and not self.fused_dp:   # (fused: the exchange is inside b{i})
                 import torch.distributed as dist
                 if self._comm_stream is None:
@@ -527,13 +539,18 @@ class GanTrainer:
         """Split the backward segment into `n_buckets` contiguous op ranges.  Parameters are laid out in forward
         order and the backward runs in reverse, so the gradients finished after bucket i form a suffix
         [lo_i, hi_i) of the flat buffer; the ranges tile [0, n) exactly once.
-        Returns [(op_first, op_end, lo, hi, layer names)]."""
+        Returns [(op_first, op_end, lo, hi, names of the layers stored in [lo, hi))]."""
         st = plan.store
         first, end = plan.prog.segments["bwd"]
         marks = plan.bwd_marks
         nb = min(self.n_buckets, len(marks))
         per = math.ceil(len(marks) / nb)
-        out = []
+        # every layer that owns parameters, by the start of its block in the flat buffer (conv + BN parameters of a
+        # layer are contiguous); layers without backward ops (dead branches) keep zero gradients: always complete
+        start = {l.name: min(st.offsets[l.wkey + ".weight"], st.offsets[l.wkey + ".bias"]) for l in st.spec.all_layers()}
+        by_offset = sorted(start, key=start.get, reverse=True)
+        live = {n for n, _ in marks}
+        out, done = [], set()
         hi = st.n
         for bi in range(nb):
             names = marks[bi * per:(bi + 1) * per]
@@ -543,18 +560,30 @@ class GanTrainer:
             last = (bi + 1) * per >= len(marks)
             e = end if last else marks[(bi + 1) * per][1]
             layer_names = {n for n, _ in names}
-            # smallest parameter offset among the layers of this bucket (a layer's block holds conv + BN params)
-            lo = 0 if last else min(min(st.offsets[l.wkey + ".weight"], st.offsets[l.wkey + ".bias"])
-                                    for l in plan.spec.layers if l.name in layer_names)
+            done |= layer_names
+            # the longest suffix [lo, n) of the flat buffer whose gradients are ALL complete once this bucket's ops
+            # have run.  Usually that is "from this bucket's first layer on", but the parameter order is the
+            # reference's module registration order, not the order of the backward pass: a text branch registered
+            # early and used at the bottleneck (v4) finishes before the layers stored behind it
+            lo = 0 if last else st.n
+            if not last:
+                for name in by_offset:
+                    if name in done or name not in live:
+                        lo = start[name]
+                    else:
+                        break
             lo = min(lo, hi)
-            out.append((s, e, lo, hi, layer_names))
+            # the layers this bucket's optimizer step updates — whose GEMM operand copies it therefore repacks: those
+            # stored in [lo, hi), not necessarily the ones whose backward ops it runs
+            updated = {name for name, off in start.items() if lo <= off < hi}
+            out.append((s, e, lo, hi, updated))
             hi = lo
         return out
 
-    def _run_bwd_ops(self, plan: nets.NetPlan, s: int, e: int, cur) -> list:
+    def _run_bwd_ops(self, plan: nets.NetPlan, s: int, e: int, cur, side_ops: Optional[list] = None) -> list:
         """Ops [s, e) of a backward segment.  The weight-gradient GEMMs (+ their split-K reduce) only feed the
         optimizer, so they go to side streams and overlap the bn_bwd -> dgrad chain of the following layers.
-        Returns the side streams that were used."""
+        Returns the side streams that were used; side_ops (a list) collects (stream, record) of every op sent there."""
         if not self.overlap_wgrad:
             plan.prog.run_range(s, e, cur.cuda_stream)
             return []
@@ -580,6 +609,8 @@ class GanTrainer:
                         self._wgrad_rr[key] += 1
                     side.wait_event(ev)
                     plan.prog.run_range(k, k + 1, side.cuda_stream)
+                    if side_ops is not None:
+                        side_ops.append((side, recs[k]))
                     if side not in used:
                         used.append(side)
             else:

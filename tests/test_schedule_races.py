@@ -1,0 +1,217 @@
+"""Static race check of the multi-stream step schedules (GanTrainer._g_ops / _d_ops / _gan_ops: dependency chain, wgrad
+side streams, adversarial scoring branch, optimizer stream, D_k || G_k+1) without a GPU.
+
+CUDA streams and events are replaced by fakes that carry vector clocks, Program.run / run_range log every op with the
+clock of the stream it was enqueued on instead of launching it, and every pair of ops that touch overlapping bytes —
+at least one of them writing (outputs, statistics, accumulators, tickets, workspaces) — must be ordered by
+happens-before (same stream, or an event recorded after the first and waited for before the second).  This is the
+property a CUDA graph captured from the same enqueue order inherits; an unordered pair is a data race that the
+numerical tests on the device would only catch by luck."""
+import contextlib
+import itertools
+
+import pytest
+import torch
+
+import b2h_b200  # noqa: F401
+from b2h_b200 import _lib as L
+from b2h_b200 import program as program_mod
+from b2h_b200.trainer import GanTrainer
+
+# fields an op writes (everything else it references is read); scratch that is reset in place counts as written
+WRITES = {
+    L.OP_GEMM: {"out", "stats.mean", "stats.invstd", "stats.scale", "stats.shift", "stats.running_mean",
+                "stats.running_var", "stats.num_batches_tracked", "stats.partial", "stats.ticket", "stats.z",
+                "bwd_sums.accum", "drop.save"},
+    L.OP_WGRAD: {"dW", "partial"},
+    L.OP_BN_STATS: {"mean", "invstd", "scale", "shift", "running_mean", "running_var", "num_batches_tracked", "partial",
+                    "ticket"},
+    L.OP_BN_APPLY: {"out", "drop.save"},
+    L.OP_BN_BWD: {"dpre", "dgamma", "dbeta", "dbias", "accum", "partial", "ticket", "sums"},
+    L.OP_PREP: {"out", "drop.save"},
+    L.OP_TO_NCL: {"dst"},
+    L.OP_L1: {"loss", "dout", "dbias", "partial", "ticket", "dbias_accum"},
+    L.OP_MSE: {"loss", "total", "dscore", "dpre", "dbias"},
+    L.OP_COLSUM: {"out", "partial", "ticket"},
+    L.OP_ADAM: {"p", "m", "v", "step", "scalars"},
+    L.OP_PACK: {"out", "out_bias"},
+    L.OP_PACK_MULTI: {"_items[].out", "_items[].out_bias"},
+    L.OP_BN_FOLD: {"scale", "shift"},
+    L.OP_BN_FOLD_MULTI: {"_items[].scale", "_items[].shift"},
+}
+
+
+class FakeStream:
+    _ids = itertools.count(1)
+    registry = {}
+
+    def __init__(self, device=None, priority=0):
+        self.id = next(FakeStream._ids)
+        self.clock = {self.id: 0}
+        FakeStream.registry[self.id] = self
+
+    @property
+    def cuda_stream(self):
+        return self.id
+
+    def wait_event(self, ev):
+        if ev.clock is not None:
+            for k, v in ev.clock.items():
+                self.clock[k] = max(self.clock.get(k, 0), v)
+
+    def wait_stream(self, other):
+        for k, v in other.clock.items():
+            self.clock[k] = max(self.clock.get(k, 0), v)
+
+    def tick(self):
+        self.clock[self.id] += 1
+        return dict(self.clock)
+
+
+class FakeEvent:
+    def __init__(self, *a, **k):
+        self.clock = None
+
+    def record(self, stream=None):
+        self.clock = dict((stream or CURRENT[-1]).clock)
+
+
+CURRENT = []
+
+
+@contextlib.contextmanager
+def fake_stream_ctx(s):
+    CURRENT.append(s)
+    try:
+        yield
+    finally:
+        CURRENT.pop()
+
+
+def accesses(rec):
+    """[(start, end, is_write, path)] over every tensor the record references."""
+    out = []
+    writes = WRITES[rec.kind]
+
+    def walk(f, pre):
+        for k, v in f.items():
+            path = pre + k
+            if isinstance(v, torch.Tensor):
+                if v.numel():
+                    w = path in writes
+                    if rec.kind == L.OP_ADAM and k in ("step", "scalars") and rec.f.get("phase", 0) == 2:
+                        w = False
+                    if rec.kind == L.OP_ADAM and rec.f.get("phase", 0) == 1 and k in ("p", "m", "v", "g"):
+                        continue                       # phase 1 only advances the step
+                    if rec.kind == L.OP_WGRAD and k == "partial" and rec.f.get("splits") == 1:
+                        continue                       # split-free form (bf16 plans only): no workspace traffic
+                    out.append((v.data_ptr(), v.data_ptr() + v.numel() * v.element_size(), w, path))
+            elif isinstance(v, dict):
+                walk(v, path + ".")
+            elif isinstance(v, list) and v and isinstance(v[0], dict):
+                for item in v:
+                    walk(item, path + "[].")
+    walk(rec.f, "")
+    return out
+
+
+def find_races(log):
+    """log: [(op name, stream id, clock, accesses)] in enqueue order -> unordered conflicting pairs."""
+    items = []
+    for i, (_, _, _, acc) in enumerate(log):
+        for (a, b, w, path) in acc:
+            items.append((a, b, w, path, i))
+    items.sort()
+    races, active = [], []
+    for a, b, w, path, i in items:
+        active = [t for t in active if t[1] > a]
+        for (a2, b2, w2, path2, j) in active:
+            if i == j or not (w or w2):
+                continue
+            first, second = (j, i) if j < i else (i, j)
+            s1, c1 = log[first][1], log[first][2]
+            c2 = log[second][2]
+            if c2.get(s1, 0) < c1[s1]:
+                races.append((log[first][0], path2 if first == j else path, log[second][0], path if first == j else path2))
+        active.append((a, b, w, path, i))
+    return sorted(set(races))
+
+
+@pytest.fixture
+def schedule_log(monkeypatch):
+    log = []
+    base = FakeStream()
+    CURRENT.clear()
+    CURRENT.append(base)
+    monkeypatch.setattr(torch.cuda, "Stream", FakeStream)
+    monkeypatch.setattr(torch.cuda, "Event", FakeEvent)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda device=None: CURRENT[-1])
+    monkeypatch.setattr(torch.cuda, "stream", fake_stream_ctx)
+
+    def enqueue(self, first, end, stream):
+        s = FakeStream.registry[stream] if stream is not None else CURRENT[-1]
+        for rec in self.recs[first:end]:
+            log.append((f"{rec.tag or rec.kind}@s{s.id}", s.id, s.tick(), accesses(rec)))
+
+    def run(self, segment=None, stream=None):
+        first, end = self.segments[segment] if segment is not None else (0, len(self.recs))
+        enqueue(self, first, end, stream)
+
+    def run_range(self, first, end, stream=None):
+        enqueue(self, first, end, stream)
+
+    monkeypatch.setattr(program_mod.Program, "run", run)
+    monkeypatch.setattr(program_mod.Program, "run_range", run_range)
+    yield log
+    CURRENT.clear()
+
+
+def _trainer(variant="v1", rf=False, precision="bf16", **kw):
+    return GanTrainer(variant, 36, 252, rf, 8, 16, precision=precision, device="cpu", drop_mode="philox", **kw)
+
+
+def test_detector_finds_a_planted_race(schedule_log):
+    tr = _trainer()
+    side = torch.cuda.Stream()
+    tr.G_train.prog.run("fwd")                                  # base stream
+    tr.G_train.prog.run("fwd", side.cuda_stream)                # the same buffers from an unordered stream
+    assert find_races(schedule_log)
+    del schedule_log[:]
+    ev = torch.cuda.Event()
+    tr.G_train.prog.run("fwd")
+    ev.record(torch.cuda.current_stream())
+    side.wait_event(ev)
+    tr.G_train.prog.run("fwd", side.cuda_stream)
+    assert find_races(schedule_log) == []
+
+
+@pytest.mark.parametrize("variant,rf,precision", [("v1", False, "bf16"), ("v1", True, "bf16"), ("b2h", True, "bf16"),
+                                                  ("v4", True, "bf16"), ("v2", True, "fp32"), ("v1", False, "fp32")])
+def test_sequential_steps_have_no_unordered_conflicts(schedule_log, variant, rf, precision):
+    tr = _trainer(variant, rf, precision)
+    for _ in range(2):
+        tr.G_train.pack()
+        tr.D_train.pack()
+        tr._g_step_body()
+        tr._d_step_body()
+    assert len(schedule_log) > 200
+    assert len({e[1] for e in schedule_log}) >= 4               # dependency chain + wgrad / scoring / optimizer streams
+    races = find_races(schedule_log)
+    assert races == [], "\n".join(map(str, races[:20]))
+
+
+@pytest.mark.parametrize("lag_adv", [True, False])
+@pytest.mark.parametrize("variant,rf", [("v1", False), ("v1", True), ("b2h", True), ("v2", True), ("v4", True),
+                                        ("v4_deeper", True)])
+def test_pipelined_gan_step_has_no_unordered_conflicts(schedule_log, variant, rf, lag_adv):
+    tr = _trainer(variant, rf)
+    tr.G_train.pack()
+    tr.D_train.pack()
+    tr._g_step_body()                                           # pipeline prologue: G0
+    for _ in range(3):                                          # D_k || G_k+1, back to back
+        tr._gan_ops(lag_adv)
+    if lag_adv:
+        tr.flush_adv()
+    assert len({e[1] for e in schedule_log}) >= 6
+    races = find_races(schedule_log)
+    assert races == [], "\n".join(map(str, races[:20]))

@@ -257,3 +257,64 @@ def test_odd_window_length_is_rejected_like_the_reference():
         torch.nn.L1Loss()(G(x), y)
     with pytest.raises(ValueError):
         GanTrainer("v1", 36, 252, False, 2, 7, precision="fp32", device="cpu")
+
+
+@pytest.mark.parametrize("variant,rf", [("v4", True), ("v1", True), ("b2h", True), ("v4_deeper", True)])
+def test_bucket_by_bucket_update_order_matches_the_oracle(variant, rf):
+    """The optimizer step in the order GanTrainer._bwd_update issues it — backward ops of bucket i, then the Adam range
+    and the repack of bucket i, while later buckets' gradients do not exist yet — against the oracle's step.  The flat
+    parameter order is the reference's module registration order, not the backward order (v4 registers the text branch
+    first and uses it at the bottleneck): a bucket may only update parameters whose gradients are complete, and must
+    repack exactly the layers it updated (regression: v4 + text updated conv5 / encoder one bucket too early)."""
+    torch.manual_seed(0)
+    B, T, cin, cout, lr = 16, 16, 36, 252, 1e-3
+    G = R.build_generator(variant, cin, cout, rf)
+    D = R.build_discriminator(cout)
+    randomize_bn(G, 5)
+    randomize_bn(D, 6)
+    g = torch.Generator().manual_seed(1)
+    x, y = torch.randn(B, cin, T, generator=g), torch.randn(B, cout, T, generator=g)
+    f = feats_for(variant, rf, B, T, g)
+    tr = GanTrainer(variant, cin, cout, rf, B, T, precision="fp32", device="cpu", lr=lr, drop_mode="mask", n_buckets=3)
+    tr.g_store.load_state_dict(G.state_dict())
+    tr.d_store.load_state_dict(D.state_dict())
+    tr.x.copy_(x)
+    tr.y.copy_(y)
+    if f is not None:
+        tr.feats.copy_(f)
+    g_opt = torch.optim.Adam(G.parameters(), lr=lr)
+    masks = R.make_masks(G, x, seed=100, feats=f)
+    tr.G_train.set_masks(masks)
+    bp, P, packs = tr._buckets["g"]
+    st = tr.g_store
+    # ranges tile the buffer; every layer with parameters is repacked by exactly the bucket that updates it
+    assert bp[0][3] == st.n and bp[-1][2] == 0 and all(a[2] == b[3] for a, b in zip(bp, bp[1:]))
+    all_updated = [n for *_, names in bp for n in names]
+    assert len(all_updated) == len(set(all_updated)) == len({l.name for l in st.spec.all_layers()})
+    for steps in range(2):
+        R.generator_step(G, D, g_opt, x, y, f, masks)
+        for p_, s_ in ((tr.G_train.prog, "pack"), (tr.D_train.prog, "pack"), (tr.D_eval.prog, "pack"),
+                       (tr.G_train.prog, "fwd"), (tr.D_eval.prog, "fwd"), (tr.g_loss_prog, "loss")):
+            emul(p_, s_)
+        st.grad.fill_(float("nan"))                  # a gradient consumed before it is produced poisons the update
+        live = {n for n, _ in tr.G_train.bwd_marks}
+        for l in st.spec.all_layers():               # (dead branches never write theirs: they stay zero, as on the device)
+            if l.name not in live:
+                for key in [l.wkey + ".weight", l.wkey + ".bias"] + ([l.bnkey + ".weight", l.bnkey + ".bias"] if l.bn else []):
+                    st.g(key).zero_()
+        E.run_records(P.recs, *P.segments["step"])
+        for i, (s, e, lo, hi, _) in enumerate(bp):
+            E.run_records(tr.G_train.prog.recs, s, e)
+            assert torch.isfinite(st.grad[lo:hi]).all(), (i, lo, hi)
+            E.run_records(P.recs, *P.segments[f"b{i}"])
+            E.run_records(tr.G_train.prog.recs, *tr.G_train.prog.segments[packs[i]])
+        assert torch.isfinite(st.flat).all()
+        for k, p in G.named_parameters():
+            check_adam_params(st.p(k), p, lr, (steps, k), tight=False)
+        # the packed operands equal a full repack of the updated parameters
+        snap = {n: b.wf.clone() for n, b in tr.G_train.bufs.items() if b.wf is not None}
+        emul(tr.G_train.prog, "pack")
+        for n, w in snap.items():
+            assert torch.equal(w, tr.G_train.bufs[n].wf), n
+        tr.g_store.load_state_dict(G.state_dict())   # restart the next iteration from the oracle's exact state
+        tr.g_opt.load_state_dict(g_opt.state_dict())
