@@ -38,6 +38,7 @@ WRITES = {
     L.OP_PACK_MULTI: {"_items[].out", "_items[].out_bias"},
     L.OP_BN_FOLD: {"scale", "shift"},
     L.OP_BN_FOLD_MULTI: {"_items[].scale", "_items[].shift"},
+    L.OP_DP_ADAM: {"m", "v", "_p[T]"},          # (every rank's parameter range; reads every rank's gradient range)
 }
 
 
@@ -111,6 +112,10 @@ def accesses(rec):
             elif isinstance(v, list) and v and isinstance(v[0], dict):
                 for item in v:
                     walk(item, path + "[].")
+            elif isinstance(v, list) and v and isinstance(v[0], torch.Tensor):
+                for t in v:
+                    out.append((t.data_ptr(), t.data_ptr() + t.numel() * t.element_size(), path + "[T]" in writes,
+                                path + "[T]"))
     walk(rec.f, "")
     return out
 
@@ -160,6 +165,13 @@ def schedule_log(monkeypatch):
     def run_range(self, first, end, stream=None):
         enqueue(self, first, end, stream)
 
+    def all_reduce(t, op=None, group=None, async_op=False):      # in place on the stream it is enqueued on
+        cur = CURRENT[-1]
+        log.append((f"all_reduce@s{cur.id}", cur.id, cur.tick(),
+                    [(t.data_ptr(), t.data_ptr() + t.numel() * t.element_size(), True, "tensor")]))
+
+    import torch.distributed as dist
+    monkeypatch.setattr(dist, "all_reduce", all_reduce)
     monkeypatch.setattr(program_mod.Program, "run", run)
     monkeypatch.setattr(program_mod.Program, "run_range", run_range)
     yield log
@@ -213,5 +225,50 @@ def test_pipelined_gan_step_has_no_unordered_conflicts(schedule_log, variant, rf
     if lag_adv:
         tr.flush_adv()
     assert len({e[1] for e in schedule_log}) >= 6
+    races = find_races(schedule_log)
+    assert races == [], "\n".join(map(str, races[:20]))
+
+
+@pytest.mark.parametrize("n_buckets", [1, 3])
+@pytest.mark.parametrize("variant,rf", [("v1", False), ("v4", True)])
+def test_data_parallel_steps_have_no_unordered_conflicts(schedule_log, variant, rf, n_buckets):
+    """world_size 2: the gradient all-reduce of every bucket (comm stream) against the weight-gradient side streams
+    that feed it and the optimizer ranges that consume it, sequential and pipelined schedules."""
+    tr = _trainer(variant, rf, world_size=2, n_buckets=n_buckets)
+    tr.G_train.pack()
+    tr.D_train.pack()
+    tr._g_step_body()
+    tr._d_step_body()
+    for _ in range(2):
+        tr._gan_ops(True)
+    tr.flush_adv()
+    assert sum(1 for e in schedule_log if e[0].startswith("all_reduce")) == n_buckets * 2 * 3
+    races = find_races(schedule_log)
+    assert races == [], "\n".join(map(str, races[:20]))
+
+
+@pytest.mark.parametrize("n_buckets", [1, 3])
+def test_fused_exchange_schedule_has_no_unordered_conflicts(schedule_log, n_buckets):
+    """fused_dp (b2h_dp_adam instead of all-reduce + Adam): one rank's schedule — the exchange kernel reads the local
+    gradients that the side-stream weight gradients write and stores parameters that the repack reads."""
+    from b2h_b200.trainer import PeerBuffers
+    probe = _trainer()
+    peers = {"g": PeerBuffers.in_process(probe.g_store.n, n_buckets, ["cpu"] * 2),
+             "d": PeerBuffers.in_process(probe.d_store.n, n_buckets, ["cpu"] * 2)}
+    del schedule_log[:]
+    tr = _trainer(world_size=2, n_buckets=n_buckets, fused_dp=True, rank=0, peer_buffers={k: v[0] for k, v in peers.items()})
+    tr.G_train.pack()
+    tr.D_train.pack()
+    tr._g_step_body()
+    tr._d_step_body()
+    for _ in range(2):
+        tr._gan_ops(True)
+    tr.flush_adv()
+    assert sum(1 for e in schedule_log if e[0].startswith("dp_adam")) == n_buckets * 2 * 3
+    assert not any(e[0].startswith("all_reduce") for e in schedule_log)
+    # the exchange kernels of a step are chained in enqueue order (they spin on their peers)
+    dp = [e for e in schedule_log if e[0].startswith("dp_adam")]
+    for a, b in zip(dp, dp[1:]):                           # total order: no rank can run two of them the other way round
+        assert b[2].get(a[1], 0) >= a[2][a[1]], (a[0], b[0])
     races = find_races(schedule_log)
     assert races == [], "\n".join(map(str, races[:20]))
