@@ -259,8 +259,9 @@ def test_odd_window_length_is_rejected_like_the_reference():
         GanTrainer("v1", 36, 252, False, 2, 7, precision="fp32", device="cpu")
 
 
-@pytest.mark.parametrize("variant,rf", [("v4", True), ("v1", True), ("b2h", True), ("v4_deeper", True)])
-def test_bucket_by_bucket_update_order_matches_the_oracle(variant, rf):
+@pytest.mark.parametrize("variant,rf,precision", [("v4", True, "fp32"), ("v1", True, "fp32"), ("b2h", True, "fp32"),
+                                                  ("v4_deeper", True, "fp32"), ("v4", True, "bf16"), ("v1", False, "bf16")])
+def test_bucket_by_bucket_update_order_matches_the_oracle(variant, rf, precision):
     """The optimizer step in the order GanTrainer._bwd_update issues it — backward ops of bucket i, then the Adam range
     and the repack of bucket i, while later buckets' gradients do not exist yet — against the oracle's step.  The flat
     parameter order is the reference's module registration order, not the backward order (v4 registers the text branch
@@ -275,7 +276,7 @@ def test_bucket_by_bucket_update_order_matches_the_oracle(variant, rf):
     g = torch.Generator().manual_seed(1)
     x, y = torch.randn(B, cin, T, generator=g), torch.randn(B, cout, T, generator=g)
     f = feats_for(variant, rf, B, T, g)
-    tr = GanTrainer(variant, cin, cout, rf, B, T, precision="fp32", device="cpu", lr=lr, drop_mode="mask", n_buckets=3)
+    tr = GanTrainer(variant, cin, cout, rf, B, T, precision=precision, device="cpu", lr=lr, drop_mode="mask", n_buckets=3)
     tr.g_store.load_state_dict(G.state_dict())
     tr.d_store.load_state_dict(D.state_dict())
     tr.x.copy_(x)
@@ -285,7 +286,7 @@ def test_bucket_by_bucket_update_order_matches_the_oracle(variant, rf):
     g_opt = torch.optim.Adam(G.parameters(), lr=lr)
     masks = R.make_masks(G, x, seed=100, feats=f)
     tr.G_train.set_masks(masks)
-    bp, P, packs = tr._buckets["g"]
+    bp, P, packs = tr._buckets["g"]        # (bf16: the plans with fused statistics / backward sums / eval-BN epilogues)
     st = tr.g_store
     # ranges tile the buffer; every layer with parameters is repacked by exactly the bucket that updates it
     assert bp[0][3] == st.n and bp[-1][2] == 0 and all(a[2] == b[3] for a, b in zip(bp, bp[1:]))
