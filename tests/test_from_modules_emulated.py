@@ -147,3 +147,40 @@ def test_train_generator_loop_over_an_emulated_trainer(capsys):
     shown = float(out.split("Tr. Disc. Loss:")[1].split()[0])
     assert abs(shown - sum(ref_d) / 3) < 2e-2 * abs(shown)
     assert float(tr.d_opt.step) == 3.0
+
+
+def test_checkpoint_round_trip_through_the_modules(tmp_path):
+    """What train_gan.py writes on a validation improvement (train_gan.py:353-370) and reads back under
+    --use_checkpoint (:70-73): generator.state_dict() + the optimizer's torch-format state, through torch.save /
+    torch.load, into fresh modules and a fresh trainer — parameters, BatchNorm buffers, Adam moments and step."""
+    torch.manual_seed(0)
+    B, T, cin, cout, lr = 8, 16, 36, 252, 1e-3
+    Gm, Dm = _modules(cin, cout)
+    tr = GanTrainer.from_modules(Gm, Dm, batch_size=B, T=T, precision="fp32", lr=lr, drop_mode="none")
+    g = torch.Generator().manual_seed(1)
+    tr.load_batch(torch.randn(B, cin, T, generator=g), torch.randn(B, cout, T, generator=g))
+    for _ in range(2):
+        emul_g_step(tr)
+    path = tmp_path / "experiment_checkpoint.pth"
+    torch.save({"epoch": 7, "state_dict": Gm.state_dict(), "g_optimizer": tr.g_opt.state_dict()}, path)
+    G2, D2 = _modules(cin, cout)
+    tr2 = GanTrainer.from_modules(G2, D2, batch_size=B, T=T, precision="fp32", lr=lr, drop_mode="none")
+    assert not torch.equal(tr2.g_store.flat, tr.g_store.flat)
+    ck = torch.load(path, map_location="cpu")
+    G2.load_state_dict(ck["state_dict"], strict=False)
+    tr2.g_opt.load_state_dict(ck["g_optimizer"])
+    assert ck["epoch"] == 7
+    assert torch.equal(tr2.g_store.flat, tr.g_store.flat)
+    assert torch.equal(tr2.g_store.bufs, tr.g_store.bufs) and torch.equal(tr2.g_store.nbt, tr.g_store.nbt)
+    assert torch.equal(tr2.g_opt.m, tr.g_opt.m) and torch.equal(tr2.g_opt.v, tr.g_opt.v)
+    assert int(tr2.g_opt.step) == int(tr.g_opt.step) == 2
+    # the reference's own optimizer class accepts the same dictionary
+    Gr = R.build_generator("v1", cin, cout)
+    ref_opt = torch.optim.Adam(Gr.parameters(), lr=lr)
+    ref_opt.load_state_dict(ck["g_optimizer"])
+    assert float(ref_opt.state_dict()["state"][0]["step"]) == 2.0
+    # and the next step of the restored trainer equals the next step of the original
+    tr2.load_batch(tr.x, tr.y)
+    emul_g_step(tr)
+    emul_g_step(tr2)
+    assert torch.equal(tr2.g_store.flat, tr.g_store.flat)
