@@ -142,9 +142,13 @@ def find_races(log):
     return sorted(set(races))
 
 
+class _Log(list):
+    pass
+
+
 @pytest.fixture
 def schedule_log(monkeypatch):
-    log = []
+    log = _Log()
     base = FakeStream()
     CURRENT.clear()
     CURRENT.append(base)
@@ -170,6 +174,20 @@ def schedule_log(monkeypatch):
         log.append((f"all_reduce@s{cur.id}", cur.id, cur.tick(),
                     [(t.data_ptr(), t.data_ptr() + t.numel() * t.element_size(), True, "tensor")]))
 
+    real_copy = torch.Tensor.copy_
+
+    def copy_(dst, src, non_blocking=False):                     # batch feeding: tensor copies on the current stream
+        cur = CURRENT[-1]
+        acc = [(dst.data_ptr(), dst.data_ptr() + dst.numel() * dst.element_size(), True, "dst")]
+        if isinstance(src, torch.Tensor) and src.numel():
+            acc.append((src.data_ptr(), src.data_ptr() + src.numel() * src.element_size(), False, "src"))
+        log.append((f"copy@s{cur.id}", cur.id, cur.tick(), acc))
+        return real_copy(dst, src, non_blocking)
+
+    log_copies = []
+    monkeypatch.setattr(torch.Tensor, "copy_", lambda d, s_, non_blocking=False:
+                        copy_(d, s_, non_blocking) if log_copies else real_copy(d, s_, non_blocking))
+    log.log_copies = log_copies
     import torch.distributed as dist
     monkeypatch.setattr(dist, "all_reduce", all_reduce)
     monkeypatch.setattr(program_mod.Program, "run", run)
@@ -270,5 +288,29 @@ def test_fused_exchange_schedule_has_no_unordered_conflicts(schedule_log, n_buck
     dp = [e for e in schedule_log if e[0].startswith("dp_adam")]
     for a, b in zip(dp, dp[1:]):                           # total order: no rank can run two of them the other way round
         assert b[2].get(a[1], 0) >= a[2][a[1]], (a[0], b[0])
+    races = find_races(schedule_log)
+    assert races == [], "\n".join(map(str, races[:20]))
+
+
+@pytest.mark.parametrize("variant,rf", [("v1", False), ("b2h", True)])
+def test_batch_feeding_has_no_unordered_conflicts(schedule_log, variant, rf):
+    """bench.py's end-to-end loop: prefetch of batch k+1 (copy stream, staging buffers) under step k, swap into the
+    static step inputs, the previous batch moving to the discriminator's inputs — copies included in the check."""
+    tr = _trainer(variant, rf)
+    tr.G_train.pack()
+    tr.D_train.pack()
+    hx, hy = torch.randn_like(tr.x), torch.randn_like(tr.y)
+    hf = torch.randn_like(tr.feats) if tr.feats is not None else None
+    schedule_log.log_copies.append(True)
+    tr.load_batch(hx, hy, hf)
+    tr._g_step_body()
+    tr._sync_d_batch()
+    tr.prefetch_batch(hx, hy, hf)
+    for _ in range(3):
+        tr.swap_batch(pipelined=True)
+        tr.prefetch_batch(hx, hy, hf)
+        tr._gan_ops(True)
+    tr.flush_adv()
+    assert sum(1 for e in schedule_log if e[0].startswith("copy")) >= 3 * 4
     races = find_races(schedule_log)
     assert races == [], "\n".join(map(str, races[:20]))
