@@ -12,6 +12,8 @@ run() {  # name, timeout seconds, command...
   tail -6 gpurun_out/dpfirst_$name.log
 }
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
+# 0. the kept entry points end to end (single process)
+B2H_TEST_ENTRY=1 run entry_points 300 python -m pytest tests/test_entry_points_gpu.py -x -q
 # 1. the kernel alone, one rank per device inside one process (no torch.distributed, no symmetric memory)
 B2H_TEST_MULTI_GPU=1 run two_device_test 120 python -m pytest tests/test_fused_dp.py -x -q -k two_devices
 # 2. kernel-level timing: symmetric memory (peer loads / stores and, if available, multimem), then CUDA IPC mapping
