@@ -32,6 +32,7 @@ def test_every_record_lowers(variant, rf, cin, cout, precision):
     for name, prog in programs_of(tr).items():
         covered = sorted(prog.segments.values())
         assert covered and all(a[1] <= b[0] for a, b in zip(covered, covered[1:])), name   # segments do not overlap
+        assert sum(b - a for a, b in covered) == len(prog.recs), name                       # and no op is outside one
         for rec in prog.recs:
             st = lower(rec)
             assert C.sizeof(st) == lib.b2h_desc_size(rec.kind), rec
