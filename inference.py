@@ -85,7 +85,12 @@ def main(args):
     else:
         model.build_net(cin, cout, require_text=args.require_text)
     model.precision = args.precision
-    if args.checkpoint and os.path.exists(args.checkpoint):
+    if args.random_weights:
+        print("WARNING: --random_weights: no checkpoint is loaded, the predictions are meaningless", flush=True)
+    else:
+        if not os.path.exists(args.checkpoint):   # the reference's torch.load fails on a missing file as well
+            raise SystemExit(f"checkpoint {args.checkpoint!r} not found (pass --checkpoint, or --random_weights to "
+                             "run the pipeline on an untrained model)")
         st = torch.load(args.checkpoint, map_location="cpu")
         model.load_state_dict(st["state_dict"], strict=False)      # inference.py:41-43
     model.to(device).eval()
@@ -137,7 +142,7 @@ def main(args):
 
 def build_parser():
     p = argparse.ArgumentParser()
-    p.add_argument("--checkpoint", type=str, default="")
+    p.add_argument("--checkpoint", type=str, default="models/lastCheckpoint.pth")   # inference.py:157
     p.add_argument("--base_path", type=str, default="./")
     p.add_argument("--data_dir", type=str, default="video_data")
     p.add_argument("--pipeline", type=str, default="arm2wh")
@@ -156,6 +161,7 @@ def build_parser():
     p.add_argument("--precision", type=str, default="fp32", choices=["fp32", "bf16"])
     p.add_argument("--synthetic", type=int, default=0)
     p.add_argument("--frames", type=int, default=192)
+    p.add_argument("--random_weights", action="store_true", help="smoke runs only: skip the checkpoint")
     return p
 
 

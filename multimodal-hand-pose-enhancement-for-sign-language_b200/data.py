@@ -140,9 +140,10 @@ def load_train_val(args, rng, data_dir):
     tX, tY, tF = sets["train"]
     vX, vY, vF = sets["val"]
     mX, sX, mY, sY = calc_standard(tX, tY, args.pipeline)
-    os.makedirs(args.model_path, exist_ok=True)
-    np.savez_compressed(os.path.join(args.model_path, f"{args.exp_name}{args.pipeline}_preprocess_core.npz"),
-                        body_mean_X=mX, body_std_X=sX, body_mean_Y=mY, body_std_Y=sY)
+    if int(os.environ.get("RANK", "0")) == 0:      # data parallel: every rank computes the same statistics, one writes
+        os.makedirs(args.model_path, exist_ok=True)
+        np.savez_compressed(os.path.join(args.model_path, f"{args.exp_name}{args.pipeline}_preprocess_core.npz"),
+                            body_mean_X=mX, body_std_X=sX, body_mean_Y=mY, body_std_Y=sY)
     tX, vX = ((tX - mX) / sX).astype(np.float32), ((vX - mX) / sX).astype(np.float32)
     tY, vY = ((tY - mY) / sY).astype(np.float32), ((vY - mY) / sY).astype(np.float32)
     I = np.arange(len(tX))

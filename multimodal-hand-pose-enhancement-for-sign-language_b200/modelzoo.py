@@ -52,10 +52,11 @@ class _B2HModule(nn.Module):
         self.precision = _default_precision()
         self._spec_args: Optional[tuple] = None
         self._store: Optional[nets.ParamStore] = None
-        self._plans: Dict[Tuple, nets.NetPlan] = {}
+        self._plans: Dict[Tuple, list] = {}
         self._seen_versions = -1
         self._drop_state: Optional[torch.Tensor] = None
         self.seed = 23456
+        self.drop_mode = "philox"   # "none": no dropout in train mode (deterministic comparisons in tests)
 
     # ---- construction -------------------------------------------------------------------------
     def _make_spec(self, train: bool) -> nets.NetSpec:
@@ -119,22 +120,37 @@ class _B2HModule(nn.Module):
     def _param_versions(self) -> int:
         return sum(p._version for p in self.parameters()) + sum(b._version for b in self.buffers())
 
-    def _plan(self, B: int, T: int, train: bool) -> nets.NetPlan:
-        key = (B, T, train, self.precision)
-        plan = self._plans.get(key)
-        if plan is None:
+    MAX_LIVE_PLANS = 4   # grad-enabled forwards of one shape whose backward has not run yet
+
+    def _plan(self, B: int, T: int, train: bool, lease: bool = False) -> nets.NetPlan:
+        """The recorded plan of (B, T, mode, precision).  A plan owns the activations, batch statistics and dropout
+        masks its backward reads, so a grad-enabled forward takes a LEASE on it (`lease=True`) that its backward (or
+        the death of its autograd node) returns: a second forward of the same shape before that backward -- the
+        reference's discriminator step scores fake and real before one `d_loss.backward()`, train_gan.py:240-249 --
+        gets its own plan instead of overwriting the first one's saved state."""
+        key = (B, T, train, self.precision, self.drop_mode)
+        pool = self._plans.get(key)
+        if pool is None:
             if len(self._plans) >= 8:
                 self._plans.pop(next(iter(self._plans)))
+            pool = self._plans[key] = []
+        plan = next((p for p in pool if not p._leased), None) if lease else (pool[0] if pool else None)
+        if plan is None:
+            if len(pool) >= self.MAX_LIVE_PLANS:
+                raise RuntimeError(f"{len(pool)} train-mode forwards of shape ({B}, {T}) are waiting for their backward: "
+                                   "call backward() (or drop the outputs) before running more of them")
             dtype = L.BF16 if self.precision == "bf16" else L.F32
             plan = nets.NetPlan(self._make_spec(train), self._store, B, T, dtype, self._store.device, train=train,
-                                drop_mode="philox", drop_state=self._drop_state)
+                                drop_mode=self.drop_mode, drop_state=self._drop_state,
+                                weights_from=None)
+            plan._leased = False
             if train:
                 olb = plan.bufs[plan.out_layer.name]
                 plan.gout = torch.zeros_like(plan.out)
                 with plan.prog.segment("gout"):
                     plan.prog.add(L.OP_PREP, "gout", src=plan.gout, out=olb.dpre, kind=L.SRC_NCL, B=B, L=olb.Lz,
                                   C=plan.out_layer.cout, ld=olb.Cp, Cfill=olb.Cp, src_ld=0, drop=None, out_f32=0)
-            self._plans[key] = plan
+            pool.append(plan)
         return plan
 
     def _run(self, x: torch.Tensor, feats: Optional[torch.Tensor]):
@@ -146,7 +162,8 @@ class _B2HModule(nn.Module):
         if C != spec_in:
             raise RuntimeError(f"expected {spec_in} input channels, got {C}")
         train = self.training
-        plan = self._plan(B, T, train)
+        needs_grad = train and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        plan = self._plan(B, T, train, lease=needs_grad)
         v = self._param_versions()
         if v != self._seen_versions:
             st.version += 1
@@ -156,7 +173,6 @@ class _B2HModule(nn.Module):
             if feats is None:
                 raise RuntimeError("this model was built with require_text/require_image: feats_ is required")
             plan.feats.copy_(feats.detach().to(torch.float32).reshape(plan.feats.shape))
-        needs_grad = train and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
         if needs_grad:
             params = [p for _, p in self.named_parameters()]
             out = _NetFn.apply(self, plan, *params)
@@ -170,11 +186,29 @@ class _B2HModule(nn.Module):
         return out
 
 
+class _Lease:
+    """Held by the autograd node of one grad-enabled forward: the plan's saved state (activations, statistics, masks)
+    belongs to that node until its backward has run or the node dies (output dropped / graph freed)."""
+
+    def __init__(self, plan):
+        self.plan = plan
+        plan._leased = True
+
+    def release(self):
+        if self.plan is not None:
+            self.plan._leased = False
+            self.plan = None
+
+    def __del__(self):
+        self.release()
+
+
 class _NetFn(torch.autograd.Function):
     """Bridges the recorded forward / backward programs into torch.autograd (g_loss.backward(), train_gan.py:294)."""
 
     @staticmethod
     def forward(ctx, module, plan, *params):
+        ctx.lease = _Lease(plan)
         plan.forward()
         ctx.module, ctx.plan = module, plan
         return plan.out.clone()
@@ -182,6 +216,9 @@ class _NetFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gout):
         plan, st = ctx.plan, ctx.module._store
+        if ctx.lease.plan is None:
+            raise RuntimeError("backward through a b2h_b200 module a second time: its saved activations were released "
+                               "after the first backward (retain_graph is not supported)")
         plan.gout.copy_(gout.contiguous())
         plan.prog.run("gout")
         plan.backward()
@@ -190,6 +227,7 @@ class _NetFn(torch.autograd.Function):
         for k, _ in st.param_shapes:
             base = k.rsplit(".", 1)[0]
             grads.append(st.g(k).clone() if base in live else None)
+        ctx.lease.release()
         return (None, None, *grads)
 
 

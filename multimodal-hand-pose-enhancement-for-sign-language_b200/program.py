@@ -92,7 +92,7 @@ class Program:
         return torch.bfloat16 if self.dtype == L.BF16 else torch.float32
 
     def add(self, op_kind: int, tag: str = "", /, **fields) -> int:
-        assert self._handle is None, "program already finalized"
+        assert self._handle is None, "program already lowered: invalidate() it first"
         self.recs.append(OpRec(op_kind, tag, fields))
         return len(self.recs) - 1
 
@@ -118,6 +118,13 @@ class Program:
             rc = lib.b2h_program_add(self._handle, rec.kind, C.byref(st))
             L.check(rc, f"b2h_program_add[{rec}]")
         return self
+
+    def invalidate(self):
+        """A record changed after the program was lowered: destroy the native program; the next run lowers it again
+        (CUDA graphs that captured its launches keep the OLD arguments and must be re-captured by their owner)."""
+        if self._handle is not None:
+            L.load().b2h_program_destroy(self._handle)
+            self._handle = None
 
     def run(self, segment: Optional[str] = None, stream: Optional[int] = None):
         if self._handle is None:

@@ -40,16 +40,39 @@ class FlatAdam:
         self.v = torch.zeros_like(store.flat)
         self.step = torch.zeros(1, dtype=torch.int64, device=dev)
         self.scalars = torch.zeros(2, dtype=torch.float32, device=dev)
+        self._recorded = []     # (program, op index) of every optimizer op that carries the hyper-parameters
+        self.on_hparams_changed = []   # callbacks (the trainer drops its captured graphs)
 
     def record(self, prog: Program, gscale: float = 1.0, lo: int = 0, hi: Optional[int] = None, phase: int = 0,
                tag: str = "adam"):
         """phase 0: the whole update.  phase 1: only advance the step / bias corrections.  phase 2: update the
         flat range [lo, hi) with the current bias corrections (gradient buckets)."""
         hi = self.store.n if hi is None else hi
-        return prog.add(L.OP_ADAM, tag, p=self.store.flat[lo:hi], g=self.store.grad[lo:hi], m=self.m[lo:hi],
-                        v=self.v[lo:hi], n=max(hi - lo, 0 if phase == 1 else 1), lr=self.lr, beta1=self.betas[0],
-                        beta2=self.betas[1], eps=self.eps, gscale=float(gscale), step=self.step, scalars=self.scalars,
-                        phase=phase)
+        i = prog.add(L.OP_ADAM, tag, p=self.store.flat[lo:hi], g=self.store.grad[lo:hi], m=self.m[lo:hi],
+                     v=self.v[lo:hi], n=max(hi - lo, 0 if phase == 1 else 1), lr=self.lr, beta1=self.betas[0],
+                     beta2=self.betas[1], eps=self.eps, gscale=float(gscale), step=self.step, scalars=self.scalars,
+                     phase=phase)
+        self._recorded.append((prog, i))
+        return i
+
+    def set_hparams(self, lr: float, betas, eps: float):
+        """torch.optim.Adam.load_state_dict applies the checkpoint's lr / betas / eps (train_gan.py:72,91).  The
+        recorded optimizer ops carry them in their descriptors: patch the records, have the programs lowered again
+        on their next run and the captured graphs (which froze the old kernel arguments) dropped."""
+        lr, betas, eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
+        if (lr, betas, eps) == (self.lr, self.betas, self.eps):
+            return
+        self.lr, self.betas, self.eps = lr, betas, eps
+        for prog, i in self._recorded:
+            f = prog.recs[i].f
+            if "lr" in f:
+                f["lr"] = lr
+            if "_lr" in f:
+                f["_lr"] = lr
+            f["beta1"], f["beta2"], f["eps"] = betas[0], betas[1], eps
+            prog.invalidate()
+        for cb in self.on_hparams_changed:
+            cb()
 
     def record_dp(self, prog: Program, pb: "PeerBuffers", site: int, gscale: float, lo: int, hi: int,
                   tag: str = "dp_adam"):
@@ -58,15 +81,17 @@ class FlatAdam:
         assert self.store.flat.data_ptr() == pb.flat.data_ptr() and self.store.grad.data_ptr() == pb.grad.data_ptr()
         assert lo % 4 == 0 and (hi - lo) % 4 == 0 and hi > lo
         sig_off = 4 * site * PeerBuffers.SITE_WORDS
-        return prog.add(L.OP_DP_ADAM, tag, p=[a + 4 * lo for a in pb.p_ptrs], g=[a + 4 * lo for a in pb.g_ptrs],
-                        signal=[a + sig_off for a in pb.sig_ptrs],
-                        g_mc=pb.g_mc + 4 * lo if pb.g_mc else None, p_mc=pb.p_mc + 4 * lo if pb.p_mc else None,
-                        m=self.m[lo:hi], v=self.v[lo:hi], n=hi - lo, rank=pb.rank, world=pb.world,
-                        beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, gscale=float(gscale),
-                        scalars=self.scalars, timeout_ms=int(os.environ.get("B2H_DP_TIMEOUT_MS", "0")),
-                        _p=[t[lo:hi] for t in pb.p_tensors] if pb.p_tensors else None,
-                        _g=[t[lo:hi] for t in pb.g_tensors] if pb.g_tensors else None,
-                        _step=self.step, _lr=self.lr)
+        i = prog.add(L.OP_DP_ADAM, tag, p=[a + 4 * lo for a in pb.p_ptrs], g=[a + 4 * lo for a in pb.g_ptrs],
+                     signal=[a + sig_off for a in pb.sig_ptrs],
+                     g_mc=pb.g_mc + 4 * lo if pb.g_mc else None, p_mc=pb.p_mc + 4 * lo if pb.p_mc else None,
+                     m=self.m[lo:hi], v=self.v[lo:hi], n=hi - lo, rank=pb.rank, world=pb.world,
+                     beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, gscale=float(gscale),
+                     scalars=self.scalars, timeout_ms=int(os.environ.get("B2H_DP_TIMEOUT_MS", "0")),
+                     _p=[t[lo:hi] for t in pb.p_tensors] if pb.p_tensors else None,
+                     _g=[t[lo:hi] for t in pb.g_tensors] if pb.g_tensors else None,
+                     _step=self.step, _lr=self.lr)
+        self._recorded.append((prog, i))
+        return i
 
     def state_dict(self):
         st = self.store
@@ -95,7 +120,7 @@ class FlatAdam:
         if steps:
             self.step.fill_(max(steps))
         g = sd["param_groups"][0]
-        self.lr, self.betas, self.eps = float(g["lr"]), tuple(g["betas"]), float(g["eps"])
+        self.set_hparams(g["lr"], g["betas"], g["eps"])
 
 
 class PeerBuffers:
@@ -260,6 +285,8 @@ class GanTrainer:
                 self._peer[key] = pb
         self.g_opt = FlatAdam(self.g_store, lr)
         self.d_opt = FlatAdam(self.d_store, lr)
+        for opt in (self.g_opt, self.d_opt):
+            opt.on_hparams_changed.append(self.release_graphs)
         # Philox (seed, step): the generator steps use the even steps 0, 2, 4, ..., the discriminator steps the
         # odd ones — the same numbers as one counter bumped after every step, but each network owns its
         # counter, so a discriminator step and the next generator step can run side by side (gan_step)
@@ -867,6 +894,14 @@ class GanTrainer:
             self._bump_step("g")
         for key in ("d", "g"):
             self._mark_stepped(key)
+
+    def release_graphs(self):
+        """Drop the captured CUDA graphs (they are re-captured on the next graph=True step): after a change of what
+        they froze (optimizer hyper-parameters), and before the process group goes away -- a graph that captured
+        NCCL kernels keeps the communicator busy."""
+        if self._graphs:
+            torch.cuda.synchronize(self.device)
+        self._graphs.clear()
 
     def _ensure_packed(self):
         """Weights changed from outside (load_state_dict, user edits): repack before the step."""

@@ -125,3 +125,53 @@ def test_discriminator_module_on_gpu():
     sc = d(x.cuda())
     torch.nn.functional.mse_loss(sc, torch.ones_like(sc)).backward()
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in d.parameters())
+
+
+@pytest.mark.gpu
+def test_two_train_forwards_before_one_backward():
+    """The reference's discriminator step (train_gan.py:240-249): D(fake_motion), D(real_motion), then ONE
+    d_loss.backward().  Both forwards have the same shape; each must keep its own saved activations / batch
+    statistics (a plan lease), so the gradients equal the oracle's (dropout off on both sides)."""
+    torch.manual_seed(0)
+    ora = R.build_discriminator(252)
+    d = modelZoo.regressor_fcn_bn_discriminator()
+    d.build_net(252)
+    d.load_state_dict(ora.state_dict())
+    d.drop_mode = "none"
+    d.to("cuda")
+    for m in ora.modules():
+        if isinstance(m, R.ReplayDropout):
+            m.p = 0.0
+    g = torch.Generator().manual_seed(3)
+    fake, real = torch.randn(16, 252, 63, generator=g), torch.randn(16, 252, 63, generator=g) * 1.5 + 0.3
+    ora.train(), d.train()
+    fs, rs = ora(fake), ora(real)
+    (torch.nn.functional.mse_loss(fs, torch.zeros_like(fs)) + torch.nn.functional.mse_loss(rs, torch.ones_like(rs))).backward()
+    fs2, rs2 = d(fake.cuda()), d(real.cuda())
+    assert float((fs2.cpu() - fs).abs().max()) <= 1e-5 * float(fs.abs().max())
+    assert float((rs2.cpu() - rs).abs().max()) <= 1e-5 * float(rs.abs().max())
+    (torch.nn.functional.mse_loss(fs2, torch.zeros_like(fs2)) + torch.nn.functional.mse_loss(rs2, torch.ones_like(rs2))).backward()
+    for (k, p), (_, q) in zip(ora.named_parameters(), d.named_parameters()):
+        den = float(p.grad.abs().max()) + 1e-12
+        assert float((q.grad.cpu() - p.grad).abs().max()) <= 5e-4 * den, k
+    # both leases are back: a third and a fourth forward reuse the two plans
+    assert sum(len(v) for v in d._plans.values()) == 2
+    d(fake.cuda()), d(real.cuda())
+    assert sum(len(v) for v in d._plans.values()) == 2
+
+
+def test_plan_lease_bookkeeping():
+    """Leases without a device: a leased plan is not handed out again until released; dropping the autograd node
+    releases it."""
+    from b2h_b200.modelzoo import _Lease
+
+    class P:
+        _leased = False
+    a = P()
+    l1 = _Lease(a)
+    assert a._leased
+    l1.release()
+    assert not a._leased
+    l2 = _Lease(a)
+    del l2
+    assert not a._leased

@@ -134,3 +134,40 @@ def test_frozen_adaptive_loss_is_the_oracle_formula():
     assert abs(float(train_gan.LOSSES["RobustLoss"](o, t)) - float(R.reg_criterion("RobustLoss", o, t))) < 1e-6
     for k in ("L1", "L2", "Huber1"):
         assert abs(float(train_gan.LOSSES[k](o, t)) - float(R.reg_criterion(k, o, t))) < 1e-7
+
+
+def _val_worker(rank, port, model_path, ret):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), WORLD_SIZE="2", RANK=str(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=2)
+    train_gan.device = torch.device("cpu")
+    X, Y, F = _data(11)
+    torch.manual_seed(0)
+    gen, disc = _Gen(), torch.nn.Conv1d(7, 1, 1)
+    with torch.no_grad():
+        gen.lin.bias += 0.05 * rank          # ranks see different validation losses (their own BN statistics)
+    g_opt, d_opt = torch.optim.Adam(gen.parameters()), torch.optim.Adam(disc.parameters())
+    args = argparse.Namespace(batch_size=6, num_epochs=300, model_path=model_path, exp_name=f"r{rank}")
+    crit = torch.nn.L1Loss()
+    best, saved, hist = 1e9, 0, []
+    for epoch in (0, 1, 2):
+        with torch.no_grad():
+            gen.lin.weight *= 0.5 if epoch < 2 else 4.0    # improves twice, then gets worse
+        best, saved = train_gan.val_generator(args, gen, disc, crit, g_opt, d_opt, X, Y, best, saved, epoch, val_feats=F)
+        hist.append((best, saved))
+    ret[rank] = hist
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_val_generator_decides_once_for_all_ranks(tmp_path):
+    """Data parallel: the best loss and the epoch of the last improvement -- the inputs of the early-stopping
+    test train_gan.py:105-107 -- must be identical on every rank (rank 0's validation loss decides), or one rank leaves
+    the epoch loop alone and the others hang in the next gradient all-reduce; only rank 0 writes checkpoints."""
+    import torch.multiprocessing as mp
+    from tests.test_ddp_gloo import _free_port
+    ret = mp.Manager().dict()
+    mp.spawn(_val_worker, args=(_free_port(), str(tmp_path), ret), nprocs=2, join=True)
+    assert ret[0] == ret[1]
+    assert [s for _, s in ret[0]] == [0, 1, 1]
+    assert os.path.exists(tmp_path / "r0_checkpoint.pth") and not os.path.exists(tmp_path / "r1_checkpoint.pth")

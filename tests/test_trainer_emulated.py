@@ -319,3 +319,29 @@ def test_bucket_by_bucket_update_order_matches_the_oracle(variant, rf, precision
             assert torch.equal(w, tr.G_train.bufs[n].wf), n
         tr.g_store.load_state_dict(G.state_dict())   # restart the next iteration from the oracle's exact state
         tr.g_opt.load_state_dict(g_opt.state_dict())
+
+
+def test_optimizer_checkpoint_hyperparameters_reach_the_recorded_ops():
+    """torch.optim.Adam.load_state_dict applies the checkpoint's lr / betas / eps (train_gan.py:72,91); the recorded
+    Adam ops carry them in their descriptors, so FlatAdam.load_state_dict must patch every record."""
+    torch.manual_seed(0)
+    B, T = 4, 16
+    tr = GanTrainer("v1", 36, 252, False, B, T, precision="fp32", device="cpu", lr=1e-4, drop_mode="none")
+    ref = torch.optim.Adam([torch.nn.Parameter(torch.zeros(s)) for _, s in tr.g_store.param_shapes], lr=3e-3,
+                           betas=(0.8, 0.99), eps=1e-6)
+    sd = ref.state_dict()
+    dropped = []
+    tr.g_opt.on_hparams_changed.append(lambda: dropped.append(1))
+    tr.g_opt.load_state_dict(sd)
+    assert (tr.g_opt.lr, tr.g_opt.betas, tr.g_opt.eps) == (3e-3, (0.8, 0.99), 1e-6) and dropped
+    recs = [prog.recs[i].f for prog, i in tr.g_opt._recorded]
+    assert len(recs) >= 2 + tr.n_buckets
+    for f in recs:
+        assert f["lr"] == 3e-3 and (f["beta1"], f["beta2"], f["eps"]) == (0.8, 0.99, 1e-6)
+    # and the interpreted update really uses them: one step from zero moments moves every parameter by ~lr
+    tr.g_store.grad.fill_(1.0)
+    p0 = tr.g_store.flat.clone()
+    emul(tr.g_loss_prog, "opt")
+    assert torch.allclose(p0 - tr.g_store.flat, torch.full_like(p0, 3e-3), rtol=1e-3)
+    # the discriminator's optimizer kept its constructor values
+    assert all(prog.recs[i].f["lr"] == 1e-4 for prog, i in tr.d_opt._recorded)

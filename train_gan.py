@@ -183,21 +183,32 @@ def val_generator(args, generator, discriminator, reg_criterion, g_optimizer, d_
             f = _to_dev(val_feats[s:s + vbs]) if val_feats is not None else None
             test_loss += reg_criterion(generator(x, feats_=f), y).item() * vbs
     test_loss /= max(len(batchinds) * vbs, 1)
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    if world > 1:
+        # one decision for all ranks: every rank holds the same weights but its own BN running statistics (local
+        # batch statistics), so the validation losses differ slightly -- rank 0's value decides the
+        # checkpoint AND the early stop everywhere (a rank leaving the epoch loop alone would hang the others in the
+        # next gradient all-reduce)
+        import torch.distributed as dist
+        t = torch.tensor([test_loss], dtype=torch.float64, device=device)
+        dist.broadcast(t, 0)
+        test_loss = float(t.item())
     _log({"loss_val_gen": test_loss})
     print("Epoch [{}/{}], Val. Loss: {:.4f}, Val. Perplexity: {:5.4f}".format(epoch, args.num_epochs - 1, test_loss,
                                                                                np.exp(test_loss)), flush=True)
-    if test_loss < currBestLoss and int(os.environ.get("RANK", "0")) == 0:
-        prev_save_epoch = epoch
-        os.makedirs(args.model_path, exist_ok=True)
-        fileName = os.path.join(args.model_path, f"{args.exp_name}_checkpoint.pth")
-        torch.save({"epoch": epoch, "state_dict": generator.state_dict(), "g_optimizer": g_optimizer.state_dict()},
-                   fileName)
-        lastCheckpoint = fileName
-        torch.save({"epoch": epoch, "state_dict": discriminator.state_dict(),
-                    "d_optimizer": d_optimizer.state_dict()},
-                   os.path.join(args.model_path, f"discriminator_{args.exp_name}.pth"))
+    if test_loss < currBestLoss:
+        prev_save_epoch = epoch                         # on every rank (train_gan.py:350-352)
         currBestLoss = test_loss
-    return min(currBestLoss, test_loss), prev_save_epoch
+        if rank == 0:                                   # only the files are rank 0's business
+            os.makedirs(args.model_path, exist_ok=True)
+            fileName = os.path.join(args.model_path, f"{args.exp_name}_checkpoint.pth")
+            torch.save({"epoch": epoch, "state_dict": generator.state_dict(), "g_optimizer": g_optimizer.state_dict()},
+                       fileName)
+            lastCheckpoint = fileName
+            torch.save({"epoch": epoch, "state_dict": discriminator.state_dict(),
+                        "d_optimizer": d_optimizer.state_dict()},
+                       os.path.join(args.model_path, f"discriminator_{args.exp_name}.pth"))
+    return currBestLoss, prev_save_epoch
 
 
 def main(args):
@@ -243,6 +254,9 @@ def main(args):
         raise SystemExit(f"--loss must be one of {sorted(LOSSES)}")
     reg_criterion, gan_criterion = LOSSES[args.loss], nn.MSELoss()
     trainer = None
+    if args.autograd and world > 1:
+        raise SystemExit("--autograd is the single-process cross-check of the reference's literal flow: it has no "
+                         "gradient exchange.  Data-parallel training runs through the fused trainer (drop --autograd)")
     if args.autograd:
         g_optimizer = torch.optim.Adam(generator.parameters(), lr=args.learning_rate, weight_decay=0)
         d_optimizer = torch.optim.Adam(discriminator.parameters(), lr=args.learning_rate, weight_decay=0)
@@ -251,7 +265,7 @@ def main(args):
         trainer = GanTrainer.from_modules(generator, discriminator, batch_size=args.batch_size, T=T,
                                           precision=args.precision, lr=args.learning_rate,
                                           label_smooth=args.disc_label_smooth, world_size=world, process_group=pg,
-                                          loss=args.loss)
+                                          loss=args.loss, seed=23456 + rank)   # own dropout stream per rank
         g_optimizer, d_optimizer = trainer.g_opt, trainer.d_opt
     if args.use_checkpoint:
         st = torch.load(os.path.join(args.model_path, f"lastCheckpoint_{args.exp_name}.pth"), map_location="cpu")
@@ -290,6 +304,13 @@ def main(args):
             train_feats = train_feats[I]
     if lastCheckpoint and rank == 0:
         shutil.copyfile(lastCheckpoint, os.path.join(args.model_path, f"lastCheckpoint_{args.exp_name}.pth"))
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.synchronize()
+        if trainer is not None:
+            trainer.release_graphs()      # captured NCCL kernels hold the communicator: drop them first
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def build_parser():
