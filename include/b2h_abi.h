@@ -457,6 +457,22 @@ int b2h_program_size(const b2h_program* p);
 int b2h_program_run(b2h_program* p, int first, int count, b2h_stream_t s);
 /* number of kernel launches the last run issued (bench.py's gpu_launches) */
 int64_t b2h_program_launches(const b2h_program* p);
+/* How the library launches op `idx` of a program: tile shape, split-K and epilogue fusions of the tensor-core
+ * kernels (zeros for the other op kinds).  The parity tests use it to assert that every kernel template instance
+ * of the benchmarked shapes is exercised against the oracle. */
+typedef struct {
+  int32_t kind;        /* b2h_op_kind */
+  int32_t tensor_core; /* 1: the op runs a tcgen05 kernel */
+  int32_t tile_n;      /* gemm: BN;  wgrad: WN */
+  int32_t splits;      /* wgrad: split-K slices (1 = split-free, dW written by the GEMM itself) */
+  int32_t merged;      /* gemm: tap-merged main loop */
+  int32_t fuse_stats;  /* gemm: train-mode BatchNorm statistics produced by the epilogue */
+  int32_t fuse_bwd;    /* gemm: first pass of the producer's BatchNorm backward produced by the epilogue */
+  int32_t epilogue;    /* gemm: id of the specialised epilogue (0 = generic) */
+  int32_t grid[3];
+  int32_t reserved[5];
+} b2h_op_plan_t;
+int b2h_program_op_plan(const b2h_program* p, int idx, b2h_op_plan_t* out);
 
 #ifdef __cplusplus
 }

@@ -157,6 +157,12 @@ class DpAdam(C.Structure):
                 ("beta1", f64), ("beta2", f64), ("eps", f64), ("gscale", f32), ("scalars", vp), ("timeout_ms", i32)]
 
 
+class OpPlan(C.Structure):
+    """b2h_op_plan_t: how the library launches one op of a program."""
+    _fields_ = [("kind", i32), ("tensor_core", i32), ("tile_n", i32), ("splits", i32), ("merged", i32),
+                ("fuse_stats", i32), ("fuse_bwd", i32), ("epilogue", i32), ("grid", i32 * 3), ("reserved", i32 * 5)]
+
+
 OP_STRUCT = {OP_GEMM: Gemm, OP_WGRAD: Wgrad, OP_BN_STATS: BnStats, OP_BN_APPLY: BnApply, OP_BN_BWD: BnBwd,
              OP_PREP: Prep, OP_TO_NCL: ToNcl, OP_L1: L1, OP_MSE: Mse, OP_COLSUM: Colsum, OP_ADAM: Adam,
              OP_PACK: Pack, OP_BN_FOLD: BnFold, OP_ROT6D: Rot6d, OP_FILL: Fill, OP_PACK_MULTI: PackMulti,
@@ -199,6 +205,7 @@ SYMBOLS = {
     "b2h_program_size": (C.c_int, [vp]),
     "b2h_program_run": (C.c_int, [vp, C.c_int, C.c_int, vp]),
     "b2h_program_launches": (i64, [vp]),
+    "b2h_program_op_plan": (C.c_int, [vp, C.c_int, C.POINTER(OpPlan)]),
 }
 
 ONESHOT = {OP_GEMM: ("b2h_gemm", True), OP_WGRAD: ("b2h_wgrad", True), OP_BN_STATS: ("b2h_bn_stats", True),

@@ -281,6 +281,32 @@ int b2h_program_run(b2h_program* p, int first, int count, b2h_stream_t s) {
 }
 
 int64_t b2h_program_launches(const b2h_program* p) { return p ? p->launches : 0; }
+
+int b2h_program_op_plan(const b2h_program* p, int idx, b2h_op_plan_t* out) {
+  B2H_CHECK_ARG(p && out, B2H_ERR_ARG, "program_op_plan: null argument");
+  B2H_CHECK_ARG(idx >= 0 && idx < (int)p->ops.size(), B2H_ERR_ARG, "program_op_plan: op %d outside [0, %d)", idx,
+                (int)p->ops.size());
+  const Op& op = p->ops[idx];
+  memset(out, 0, sizeof(*out));
+  out->kind = op.kind;
+  if (p->dtype == B2H_BF16 && op.kind == B2H_OP_GEMM) {
+    const TcGemmPlan& g = op.gplan;
+    out->tensor_core = 1;
+    out->tile_n = g.BN;
+    out->merged = g.p.merged;
+    out->fuse_stats = g.fuse_stats;
+    out->fuse_bwd = g.fuse_bwd;
+    out->epilogue = g.epi;
+    out->grid[0] = g.grid_x, out->grid[1] = g.grid_y, out->grid[2] = 1;
+  } else if (p->dtype == B2H_BF16 && op.kind == B2H_OP_WGRAD) {
+    const TcWgradPlan& w = op.wplan;
+    out->tensor_core = 1;
+    out->tile_n = w.WN;
+    out->splits = w.splits;
+    out->grid[0] = w.grid_x, out->grid[1] = w.p.ntaps, out->grid[2] = w.splits;
+  }
+  return B2H_OK;
+}
 int64_t b2h_launch_count(void) { return g_launch_count; }
 
 }  // extern "C"

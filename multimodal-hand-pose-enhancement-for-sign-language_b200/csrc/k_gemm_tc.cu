@@ -885,6 +885,7 @@ int plan_gemm_bf16(const b2h_gemm_t& d, TcGemmPlan* plan) {
     fprintf(stderr, "[b2h] gemm plan: B=%d Lo=%d Kc=%d Npad=%d ntaps=%d stride=%d nphase=%d -> merged=%d tl=%d tb=%d BN=%d tiles=%dx%d\n",
             d.B, d.Lo, d.Kc, d.Npad, d.ntaps, d.stride, d.nphase, p.merged, p.tl, p.tb, best_bn, m_tiles, d.Npad / best_bn);
   plan->BN = best_bn;
+  plan->epi = epi_kind(d);
   plan->grid_x = m_tiles;
   plan->grid_y = d.Npad / best_bn;
   rc = make_map_2d(&plan->tmB, d.W, (int64_t)d.ntaps * d.Kc, d.Npad, (int64_t)d.ntaps * d.Kc, 64, best_bn);
@@ -1081,6 +1082,10 @@ int plan_wgrad_bf16(const b2h_wgrad_t& d, TcWgradPlan* plan) {
   // prefer more tiles over wider tiles when the grid would not fill the machine
   const int sms = sm_count();
   while (wn > 64 && (int64_t)ceil_div(d.Mpad, WG_BM) * (d.Npad / wn) * d.ntaps * std::max(1, p.total_kb / 8) < sms) wn >>= 1;
+  if (const char* e = getenv("B2H_FORCE_WN")) {   // tests: run a given tile width at any problem size
+    const int f = atoi(e);
+    if ((f == 64 || f == 128 || f == 256) && d.Npad % f == 0) wn = f;
+  }
   plan->WN = wn;
   int64_t tiles = (int64_t)ceil_div(d.Mpad, WG_BM) * (d.Npad / wn) * d.ntaps;
   // split-K target: CTAs per launch.  The weight gradients run beside the dgrad chain, so the launch does not

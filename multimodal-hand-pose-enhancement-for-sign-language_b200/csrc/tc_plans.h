@@ -25,6 +25,7 @@ struct alignas(64) TcGemmPlan {
   CUtensorMap tmZ0, tmZ1;  // fuse_bwd: the producer layer's z (all rows / even rows, odd rows), not swizzled
   TcGemmParams p;
   int BN, grid_x, grid_y;
+  int epi;         // specialised epilogue id (EPI_*)
   int fuse_stats;  // BatchNorm statistics of the output produced by the epilogue
   int fuse_bwd;    // first pass of the producer's BatchNorm backward produced by the epilogue
   const float* bs_mean;

@@ -146,6 +146,20 @@ class Program:
         rc = L.load().b2h_program_run(self._handle, first, end - first, C.c_void_p(stream))
         L.check(rc, f"b2h_program_run[{first}:{end}]")
 
+    def op_plan(self, idx: int) -> dict:
+        """Launch plan of op `idx` as the library built it (b2h_program_op_plan): tile width, split-K, fusions."""
+        if self._handle is None:
+            self.finalize()
+        st = L.OpPlan()
+        L.check(L.load().b2h_program_op_plan(self._handle, idx, C.byref(st)), f"b2h_program_op_plan[{idx}]")
+        return {"tag": self.recs[idx].tag, "kind": st.kind, "tensor_core": bool(st.tensor_core), "tile_n": st.tile_n,
+                "splits": st.splits, "merged": bool(st.merged), "fuse_stats": bool(st.fuse_stats),
+                "fuse_bwd": bool(st.fuse_bwd), "epilogue": st.epilogue, "grid": tuple(st.grid)}
+
+    def tile_report(self) -> List[dict]:
+        """op_plan() of every GEMM-class op (tap-GEMMs and weight gradients) of the program."""
+        return [self.op_plan(i) for i, r in enumerate(self.recs) if r.kind in (L.OP_GEMM, L.OP_WGRAD)]
+
     def launches(self) -> int:
         return int(L.load().b2h_program_launches(self._handle)) if self._handle else 0
 

@@ -1,7 +1,6 @@
 """The kept entry points end to end on the device: `train_gan.py` on synthetic How2Sign-shaped clips (generator epochs
 with validation + checkpoints, a discriminator epoch, resume with --use_checkpoint) and `inference.py` on its
-checkpoint.  Written when the round's GPU budget was spent: opt-in (B2H_TEST_ENTRY=1) until it has run once on
-hardware, then to be made a plain `-m gpu` test."""
+checkpoint (train_gan.py:27-121 / inference.py:24-153 of the reference, end to end)."""
 import os
 import sys
 
@@ -18,8 +17,6 @@ pytestmark = pytest.mark.gpu
 
 @pytest.mark.parametrize("precision,extra", [("bf16", []), ("fp32", ["--require_text"]), ("bf16", ["--loss", "Huber1"])])
 def test_train_then_infer(tmp_path, capsys, precision, extra):
-    if not os.environ.get("B2H_TEST_ENTRY"):
-        pytest.skip("opt-in (B2H_TEST_ENTRY=1): not yet run on hardware")
     os.environ.setdefault("WANDB_MODE", "disabled")
     import inference
     import train_gan
@@ -49,3 +46,27 @@ def test_train_then_infer(tmp_path, capsys, precision, extra):
     r6d = np.load(os.path.join(res, "t1_r6d.npy"))
     assert r6d.shape == (16, 64, 252) and np.isfinite(r6d).all()
     assert np.isfinite(np.load(os.path.join(res, "t1_xyz.npy"))).all()
+
+
+def test_inference_refuses_a_missing_checkpoint(tmp_path):
+    import inference
+    with pytest.raises(SystemExit):
+        inference.main(inference.build_parser().parse_args(
+            ["--checkpoint", str(tmp_path / "nope.pth"), "--synthetic", "8", "--frames", "64", "--results_dir",
+             str(tmp_path)]))
+
+
+def test_autograd_flow_matches_reference_step_order(tmp_path, capsys):
+    """`--autograd`: the reference's literal flow through the drop-in modules (module forward under torch.autograd,
+    torch losses, torch.optim.Adam), including the discriminator epoch with its two train-mode forwards before one
+    backward."""
+    os.environ.setdefault("WANDB_MODE", "disabled")
+    import train_gan
+    models = str(tmp_path / "models") + "/"
+    train_gan.main(train_gan.build_parser().parse_args(
+        ["--synthetic", "64", "--frames", "64", "--batch_size", "16", "--model_path", models, "--exp_name", "a1",
+         "--precision", "fp32", "--epochs_train_disc", "2", "--num_epochs", "3", "--autograd"]))
+    out = capsys.readouterr().out
+    assert "Tr. Disc. Loss" in out and out.count("Val. Loss:") == 2
+    d = float(out.split("Tr. Disc. Loss:")[1].split()[0])
+    assert np.isfinite(d)

@@ -79,13 +79,44 @@ def test_incremental_finger_pipelines_fp32(cin, cout):
     assert rel_err(tr.infer(), ref) <= FP32_TOL
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
-@pytest.mark.parametrize("variant,rf", [("v1", False), ("v1", True), ("b2h", True)])
-def test_gan_step_vs_oracle(variant, rf, precision):
-    """One generator step + one discriminator step with replayed dropout masks (BASELINE config 2 shape
-    family) against train_gan's restatement with torch.optim.Adam."""
+def fp64_twin(m):
+    """The arbiter of SURVEY.md 8c: the same oracle module in float64 (same weights, same replayed masks)."""
+    import copy
+    return copy.deepcopy(m).double()
+
+
+def call_log_hooks(model):
+    """Outputs of every LeakyReLU / ReLU of an oracle model, one entry per call (the discriminator runs twice)."""
+    acts = {}
+    for name, m in model.named_modules():
+        if isinstance(m, (torch.nn.LeakyReLU, torch.nn.ReLU)):
+            m.register_forward_hook(lambda mod, i, o, name=name: acts.setdefault(name, []).append(o.detach().clone()))
+    return acts
+
+
+def noise_bound(ref32, ref64, floor=FP32_TOL, factor=4.0):
+    """fp32-mode tolerance of one tensor: the 1e-5 bar, or -- where the REFERENCE's own fp32 arithmetic is further
+    than that from the fp64 truth (ill-conditioned tensors: the discriminator's BatchNorm layers over 1-2 positions,
+    gradients summed over 16k rows) -- `factor` times the reference's measured fp32-vs-fp64 error on this very
+    tensor.  Returns (tolerance, reference noise)."""
+    noise = rel_err(ref32, ref64)
+    return max(floor, factor * noise), noise
+
+
+def _report(name, rows):
+    import os
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open(os.path.join("gpurun_out", "parity_noise_report.txt"), "a") as fh:
+        fh.write(f"== {name}\n")
+        for r in sorted(rows, key=lambda r: -r[1])[:14]:
+            fh.write("  %-44s ours_vs_fp64=%.3e  reference_fp32_vs_fp64=%.3e  tol=%.3e\n" % r)
+
+
+def gan_step_case(variant, rf, precision, B, T, cin=36, cout=252, lr=1e-3):
+    """One generator step + one discriminator step with replayed dropout masks against train_gan's restatement with
+    torch.optim.Adam.  fp32 mode is judged against the float64 twin of the oracle: every output, loss, gradient and
+    BN buffer within max(1e-5, 4 x the reference's own fp32 error on that tensor) (noise_bound)."""
     torch.manual_seed(0)
-    B, T, cin, cout, lr = 32, 64, 36, 252, 1e-3
     G = R.build_generator(variant, cin, cout, rf)
     D = R.build_discriminator(cout)
     randomize_bn(G, 5)
@@ -99,31 +130,62 @@ def test_gan_step_vs_oracle(variant, rf, precision):
     tr.y.copy_(y)
     if f is not None:
         tr.feats.copy_(f)
-    g_opt = torch.optim.Adam(G.parameters(), lr=lr)
-    d_opt = torch.optim.Adam(D.parameters(), lr=lr)
-    g_acts, _ = activation_hooks(G)
     fp32 = precision == "fp32"
     tol = FP32_TOL if fp32 else BF16_TOL
+    G64, D64 = fp64_twin(G), fp64_twin(D)
+    d64 = lambda t: None if t is None else t.double()   # noqa: E731
+    g_opt = torch.optim.Adam(G.parameters(), lr=lr)
+    d_opt = torch.optim.Adam(D.parameters(), lr=lr)
+    g_opt64 = torch.optim.Adam(G64.parameters(), lr=lr)
+    d_opt64 = torch.optim.Adam(D64.parameters(), lr=lr)
+    g_acts, _ = activation_hooks(G)
+    g_acts64, _ = activation_hooks(G64)
+    name = f"gan-step {variant} feats={rf} {precision} B={B} T={T}"
+    rows = []
     # ---- generator step
     g_masks = R.make_masks(G, x, seed=100, feats=f)
     tr.G_train.set_masks(g_masks)
     g_loss, l1, adv, out = R.generator_step(G, D, g_opt, x, y, f, g_masks)
+    g_loss64, l164, adv64, out64 = R.generator_step(G64, D64, g_opt64, d64(x), d64(y), d64(f), g_masks)
     tr.generator_step()
     torch.cuda.synchronize()
-    assert rel_err(tr.G_train.out, out) <= tol
     losses = tr.losses.cpu()
-    assert abs(float(losses[0]) - float(l1)) <= tol * abs(float(l1))
-    assert abs(float(losses[1]) - float(adv)) <= 20 * tol * abs(float(adv)) + 1e-6
-    assert abs(float(losses[2]) - float(g_loss)) <= 20 * tol * abs(float(g_loss))
     if fp32:
-        flips = count_kink_flips(tr.G_train, g_acts)
-        flips += int((torch.sign(tr.G_train.out.cpu() - y) != torch.sign(out - y)).sum())
-        gtol = 5e-5 if flips == 0 else 0.2
-        for k, p in G.named_parameters():
-            if p.grad is not None:
-                assert grads_close(tr.g_store.g(k).cpu(), p.grad, gtol), (k, flips)
-            check_adam_params(tr.g_store.p(k).cpu(), p, lr, k, tight=flips == 0)
+        t_out, n_out = noise_bound(out, out64)
+        rows.append(("G out", rel_err(tr.G_train.out, out64), n_out, t_out))
+        assert rel_err(tr.G_train.out, out64) <= t_out
+        for nm, ours, r32, r64 in (("l1", losses[0], l1, l164), ("adv", losses[1], adv, adv64),
+                                   ("g_loss", losses[2], g_loss, g_loss64)):
+            t, n = noise_bound(r32, r64)
+            e = abs(float(ours) - float(r64)) / abs(float(r64))
+            rows.append((nm, e, n, t))
+            assert e <= t, (nm, e, t)
+        # activation kinks / sign(out - gt): a value within fp32 noise of 0 on either side of the comparison flips ONE
+        # mask element and moves single gradient entries by percents -- in the reference's fp32 run as much as in ours
+        flips = count_kink_flips(tr.G_train, g_acts64)
+        assert flips <= 16, flips   # isolated coincidences only (of ~10^7 activations at 256 x 64)
+        flips += int((torch.sign(tr.G_train.out.cpu().double() - y) != torch.sign(out64 - y)).sum())
+        ref_flips = sum(int(((g_acts[k] > 0) != (g_acts64[k] > 0)).sum()) for k in g_acts)
+        ref_flips += int((torch.sign(out.double() - y) != torch.sign(out64 - y)).sum())
+        rows.append(("(kink flips: ours, reference)", float(flips), float(ref_flips), 0.0))
+        for (k, p), (_, p64) in zip(G.named_parameters(), G64.named_parameters()):
+            if p.grad is None:
+                continue
+            t, n = noise_bound(p.grad, p64.grad)
+            e = rel_err(tr.g_store.g(k), p64.grad)
+            rows.append((f"G grad {k}", e, n, t))
+            if flips == 0 and ref_flips == 0:
+                assert e <= t, (k, e, t, n)
+            elif flips == 0:
+                assert e <= t or grads_close(tr.g_store.g(k).cpu().double(), p64.grad, 5e-5), (k, e, t, n)
+            else:
+                assert e <= max(t, 0.05), (k, e, flips)   # a flipped kink moves single gradient entries by percents
+            check_adam_params(tr.g_store.p(k).cpu(), p, lr, k, tight=flips == 0 and ref_flips == 0)
     else:
+        assert rel_err(tr.G_train.out, out) <= tol
+        assert abs(float(losses[0]) - float(l1)) <= tol * abs(float(l1))
+        assert abs(float(losses[1]) - float(adv)) <= tol * abs(float(adv)) + 1e-6
+        assert abs(float(losses[2]) - float(g_loss)) <= tol * abs(float(g_loss))
         for k, p in G.named_parameters():
             if p.grad is not None and p.grad.numel() > 1024:
                 # the L1 gradient is sign(out - gt)/N: a bf16-level output difference flips the sign of
@@ -131,12 +193,20 @@ def test_gan_step_vs_oracle(variant, rf, precision):
                 # per-kernel bf16 accuracy is pinned by test_gpu_replay, here only the direction is
                 cos = torch.nn.functional.cosine_similarity(tr.g_store.g(k).cpu().reshape(-1), p.grad.reshape(-1), dim=0)
                 assert float(cos) > 0.95, (k, float(cos))
+    live_bn = {l.bnkey for l in tr.g_spec.layers}
     for k, v in G.state_dict().items():
         if k.endswith(("running_mean", "running_var")) and k in dict(tr.g_store.buffer_shapes) and \
-                k.rsplit(".", 1)[0] in {l.bnkey for l in tr.g_spec.layers}:
-            assert rel_err(tr.g_store.b(k), v) <= 5 * tol, k
+                k.rsplit(".", 1)[0] in live_bn:
+            if fp32:
+                t, n = noise_bound(v, G64.state_dict()[k])
+                e = rel_err(tr.g_store.b(k), G64.state_dict()[k])
+                rows.append((f"G buf {k}", e, n, t))
+                assert e <= t, (k, e, t)
+            else:
+                assert rel_err(tr.g_store.b(k), v) <= tol, k
     # ---- discriminator step (restart from the oracle's exact generator state)
     tr.g_store.load_state_dict({k: v.cuda() for k, v in G.state_dict().items()})
+    G64.load_state_dict({k: v.double() if v.is_floating_point() else v for k, v in G.state_dict().items()})
     with torch.no_grad():
         G.eval()
         fake = G(x, feats_=f)
@@ -144,16 +214,69 @@ def test_gan_step_vs_oracle(variant, rf, precision):
     mr = R.make_masks(D, R.calc_motion(y), seed=300)
     tr.D_train.set_masks(mf, group=0)
     tr.D_train.set_masks(mr, group=1)
+    d_acts, d_acts64 = call_log_hooks(D), call_log_hooks(D64)
     d_loss, fs, rs = R.discriminator_step(G, D, d_opt, x, y, f, mf, mr)
+    d_loss64, fs64, rs64 = R.discriminator_step(G64, D64, d_opt64, d64(x), d64(y), d64(f), mf, mr)
     tr.discriminator_step()
     torch.cuda.synchronize()
-    assert abs(float(tr.losses[3]) - float(d_loss)) <= 50 * tol * abs(float(d_loss))
     if fp32:
-        for k, p in D.named_parameters():
-            assert grads_close(tr.d_store.g(k).cpu(), p.grad, 5e-4), k
+        t, n = noise_bound(d_loss, d_loss64)
+        e = abs(float(tr.losses[3]) - float(d_loss64)) / abs(float(d_loss64))
+        rows.append(("d_loss", e, n, t))
+        assert e <= t, (e, t)
+        # LeakyReLU kinks of the two discriminator passes (fake = group 0, real = group 1), ours and the reference's
+        flips = ref_flips = 0
+        for l in tr.D_train.spec.layers:
+            key = f"{l.seq}.{l.w_idx + 1}"
+            if key not in d_acts64 or not l.bn:
+                continue
+            z = tr.D_train.bufs[l.name].z[:, :, :l.cout].float().cpu()
+            for grp in (0, 1):
+                r64 = d_acts64[key][grp].permute(0, 2, 1)
+                flips += int(((z[grp * B:(grp + 1) * B] > 0) != (r64 > 0)).sum())
+                ref_flips += int(((d_acts[key][grp].permute(0, 2, 1) > 0) != (r64 > 0)).sum())
+        rows.append(("(D kink flips: ours, reference)", float(flips), float(ref_flips), 0.0))
+        assert flips <= 16
+        for (k, p), (_, p64) in zip(D.named_parameters(), D64.named_parameters()):
+            t, n = noise_bound(p.grad, p64.grad)
+            e = rel_err(tr.d_store.g(k), p64.grad)
+            rows.append((f"D grad {k}", e, n, t))
+            if flips == 0 and ref_flips == 0:
+                assert e <= t, (k, e, t, n)
+            else:
+                assert e <= 0.05, (k, e, flips)    # a flipped kink moves one channel's gradients by percents
         for k, v in D.state_dict().items():
             if k.endswith(("running_mean", "running_var")):
-                assert rel_err(tr.d_store.b(k), v) <= 1e-4, k
+                t, n = noise_bound(v, D64.state_dict()[k])
+                e = rel_err(tr.d_store.b(k), D64.state_dict()[k])
+                rows.append((f"D buf {k}", e, n, t))
+                assert e <= t, (k, e, t)
+        _report(name, rows)
+    else:
+        assert abs(float(tr.losses[3]) - float(d_loss)) <= tol * abs(float(d_loss)) + 1e-6
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("variant,rf", [("v1", False), ("v1", True), ("b2h", True)])
+def test_gan_step_vs_oracle(variant, rf, precision):
+    """BASELINE config 2 shape family at a small batch (32 x 64)."""
+    gan_step_case(variant, rf, precision, 32, 64)
+
+
+@pytest.mark.parametrize("variant,rf,precision", [("v1", False, "fp32"), ("v1", False, "bf16"), ("v1", True, "bf16"),
+                                                  ("b2h", True, "bf16"), ("v1", True, "fp32")])
+def test_gan_step_vs_oracle_at_the_benched_shape(variant, rf, precision):
+    """BASELINE configs 2 / 3 / 4 at the per-GPU batch bench.py times (256 clips x 64 frames): these shapes select the
+    wide tiles (BN = 256 / 128, WN = 256 / 128), split-K and the fused statistics / backward sums."""
+    gan_step_case(variant, rf, precision, 256, 64)
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", FP32_TOL), ("bf16", BF16_TOL)])
+@pytest.mark.parametrize("variant,rf,B,T", [("v1", False, 256, 64), ("v1", False, 64, 1024), ("v1", True, 256, 64),
+                                            ("v2", True, 128, 256)])
+def test_eval_forward_vs_oracle_at_benched_shapes(variant, rf, B, T, precision, tol):
+    """The inference sweep's large end (BASELINE config 5: T up to 1024) and the training batch."""
+    test_eval_forward_vs_oracle(variant, rf, B, T, precision, tol)
 
 
 def test_graph_replay_equals_eager():

@@ -143,3 +143,79 @@ def test_reg_criterion_matches_reference_losses(loss):
     our_grad, = torch.autograd.grad(ours, out)
     assert abs(float(ours) - float(ref)) <= 1e-6 * abs(float(ref))
     assert float((our_grad - ref_grad).abs().max()) <= 1e-6 * float(ref_grad.abs().max())
+
+
+@pytest.fixture(scope="module")
+def reference_train_gan():
+    """The REAL /root/reference/train_gan.py imported unmodified (runs here under WANDB_MODE=disabled)."""
+    import importlib.util
+    import os
+    import sys
+    os.environ["WANDB_MODE"] = "disabled"
+    ref = "/root/reference"
+    added = [ref, os.path.join(ref, "utils"), os.path.join(ref, "viz")]
+    saved = {k: sys.modules.pop(k) for k in ("modelZoo", "constants", "load_save_utils", "standardization_utils",
+                                              "postprocess_utils") if k in sys.modules}
+    sys.path[:0] = added
+    try:
+        spec = importlib.util.spec_from_file_location("_ref_train_gan", os.path.join(ref, "train_gan.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        import wandb
+        wandb.init(mode="disabled")
+    finally:
+        for p in added:
+            sys.path.remove(p)
+        for k in ("modelZoo", "constants", "load_save_utils", "standardization_utils", "postprocess_utils"):
+            sys.modules.pop(k, None)
+        sys.modules.update(saved)
+    mod.device = torch.device("cpu")
+    return mod
+
+
+@pytest.mark.parametrize("variant,rf,label_smooth", [("v1", False, False), ("v1", True, True), ("b2h", True, False)])
+def test_step_bodies_match_reference_train_gan(reference_train_gan, variant, rf, label_smooth):
+    """oracle.generator_step / discriminator_step against the reference's own train_generator / train_discriminator
+    (train_gan.py:215-308) over two batches each, same torch RNG stream (dropout included): bit-identical parameters,
+    Adam moments and BN buffers, and the printed average losses."""
+    import argparse
+    tg = reference_train_gan
+    mz = tg.modelZoo
+    B, T, cin, cout, lr = 4, 32, 36, 252, 1e-3
+    torch.manual_seed(23456)
+    Gr = _build_ref(mz, variant, rf, cin, cout)
+    Dr = mz.regressor_fcn_bn_discriminator()
+    Dr.build_net(cout)
+    Go, Do = R.build_generator(variant, cin, cout, rf), R.build_discriminator(cout)
+    Go.load_state_dict(Gr.state_dict())
+    Do.load_state_dict(Dr.state_dict())
+    g = torch.Generator().manual_seed(5)
+    X, Y = torch.randn(2 * B + 1, cin, T, generator=g).numpy(), torch.randn(2 * B + 1, cout, T, generator=g).numpy()
+    F = _feats(variant, rf, 2 * B + 1, T, g)
+    Fn = F.numpy() if F is not None else None
+    args = argparse.Namespace(batch_size=B, num_epochs=3, log_step=1, epoch=1, loss="L1", disc_label_smooth=label_smooth,
+                              require_text=rf and variant != "b2h", require_image=rf and variant == "b2h")
+    opt = lambda m: torch.optim.Adam(m.parameters(), lr=lr, weight_decay=0)   # noqa: E731  (train_gan.py:69,88)
+    gr_opt, dr_opt, go_opt, do_opt = opt(Gr), opt(Dr), opt(Go), opt(Do)
+    # ---- reference: one generator epoch, one discriminator epoch (2 full batches each, the 9th clip is dropped)
+    torch.manual_seed(11)
+    tg.train_generator(args, Gr, Dr, torch.nn.L1Loss(), torch.nn.MSELoss(), gr_opt, X, Y, 1, train_feats=Fn)
+    tg.train_discriminator(args, Gr, Dr, torch.nn.MSELoss(), dr_opt, X, Y, 2, train_feats=Fn)
+    # ---- oracle restatement of the same step bodies
+    torch.manual_seed(11)
+    tx, ty = torch.from_numpy(X), torch.from_numpy(Y)
+    for i in range(2):
+        sl = slice(i * B, (i + 1) * B)
+        R.generator_step(Go, Do, go_opt, tx[sl], ty[sl], F[sl] if F is not None else None)
+    for i in range(2):
+        sl = slice(i * B, (i + 1) * B)
+        R.discriminator_step(Go, Do, do_opt, tx[sl], ty[sl], F[sl] if F is not None else None,
+                             label_smooth=label_smooth)
+    for ref, ora in ((Gr, Go), (Dr, Do)):
+        for k, v in ref.state_dict().items():
+            assert torch.equal(v, ora.state_dict()[k]), k
+    for ro, oo in ((gr_opt, go_opt), (dr_opt, do_opt)):
+        rs, os_ = ro.state_dict()["state"], oo.state_dict()["state"]
+        assert rs.keys() == os_.keys()
+        for i in rs:
+            assert torch.equal(rs[i]["exp_avg"], os_[i]["exp_avg"]) and torch.equal(rs[i]["exp_avg_sq"], os_[i]["exp_avg_sq"])
