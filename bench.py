@@ -7,6 +7,10 @@
 A "step" = one generator step + one discriminator step on one synthetic How2Sign-shaped batch
 (BASELINE.json configs[1]: v1 body-only regressor + discriminator, batch 256 x 64 frames per GPU).
 metric = training frames/s = B*T*N / step time.  One JSON line on stdout (rank 0).
+
+Besides the headline workload the same line carries (key "configs") short runs of the other BASELINE configs --
+the fp32 mode of the same step, the text- and image-conditioned steps, the inference sweep points -- so one
+driver run records all of them (`--no-extra-configs` to skip).
 """
 from __future__ import annotations
 
@@ -16,6 +20,7 @@ import os
 import statistics
 import subprocess
 import sys
+import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -24,6 +29,8 @@ if ROOT not in sys.path:
 
 import numpy as np
 import torch
+
+POOL = 8   # resident input batches the timed steps rotate over (8 x 18.9 MB = 151 MB > the 126 MB L2)
 
 
 def parse():
@@ -48,6 +55,8 @@ def parse():
                          "sequential: generator_step then discriminator_step on the same batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-breakdown", action="store_true")
+    ap.add_argument("--no-extra-configs", action="store_true")
+    ap.add_argument("--extra-steps", type=int, default=20)
     return ap.parse_args()
 
 
@@ -60,9 +69,21 @@ def workload_name(a):
     return f"{a.variant}{cond} {a.pipeline} {cin}->{cout}, {what}, batch {a.batch} x {a.frames} frames per GPU"
 
 
+def config_of(a, world):
+    """The `config` object: identical in both arms (the reference arm times this arm's workload)."""
+    return {"workload": workload_name(a), "global_batch": a.batch * world, "frames": a.frames,
+            "parallelism": f"dp{world}" if world > 1 else "single",
+            "l2": f"no flush kernels in the timed interval: the steps rotate over {POOL} resident input batches "
+                  f"({POOL} x per-step inputs > the 126 MB L2), so no step finds its inputs cached"}
+
+
 def pipeline_dims(a):
     from b2h_b200.data import FEATURE_MAP
     return FEATURE_MAP[a.pipeline]
+
+
+def feats_kind_of(variant, feats):
+    return None if not feats else ("image" if variant == "b2h" else "text")
 
 
 def synth_batch(B, T, cin, cout, feats_kind, seed=23456):
@@ -94,7 +115,7 @@ def run_cpu_reference(a, steps, warmup, device="cpu", autocast=False):
     torch.set_num_threads(os.cpu_count() or 1)
     torch.manual_seed(23456)
     cin, cout = pipeline_dims(a)
-    feats_kind = None if not a.feats else ("image" if a.variant == "b2h" else "text")
+    feats_kind = feats_kind_of(a.variant, a.feats)
     G = R.build_generator(a.variant, cin, cout, a.feats).to(device)
     D = R.build_discriminator(cout).to(device)
     x, y, f = synth_batch(a.batch, a.frames, cin, cout, feats_kind)
@@ -131,15 +152,16 @@ def reference_main(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = min(a.steps, 8)
-    warmup = min(a.warmup, 2)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    steps, warmup = a.steps, a.warmup
     fps, med, cores = run_cpu_reference(a, steps, warmup)
-    sample = f"{steps} steps (+{warmup} warm-up) of the full {a.batch}x{a.frames} batch, torch CPU, {cores} threads"
+    sample = (f"{steps} steps (+{warmup} warm-up), each the full {a.batch}x{a.frames} per-GPU batch of the workload, through "
+              f"the oracle restatement of train_gan.py's step bodies on torch CPU fp32, {cores} threads")
     line = {
         "impl": "reference", "metric": "training frames/sec" if a.mode == "train" else "inference frames/sec",
         "value": fps, "unit": "frames/s", "n_gpus": a.gpus, "steps": steps, "warmup": warmup,
         "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": {"workload": workload_name(a)},
+        "dtype": "f32", "data": "synthetic", "config": config_of(a, world),
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -177,7 +199,6 @@ class ClockSampler:
     def start(self):
         # NVML in a thread of this process (4 ms period: the timed region is ~100 ms); nvidia-smi as a fallback
         try:
-            import threading
             import pynvml as nv
             nv.nvmlInit()
             # NVML indexes physical devices: map through CUDA_VISIBLE_DEVICES via the PCI bus id
@@ -242,36 +263,202 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # this repo's arm
 # ------------------------------------------------------------------------------------------------
-def kernel_breakdown(tr, flush, reps=5):
-    """CUDA-event time of every GEMM-class op of the step (L2 flushed before each launch) and its
-    algorithmic FLOP/s; returns (list, dominant entry)."""
+def _time_op(prog, idx, flush, reps=5):
+    ts = []
+    for _ in range(reps):
+        flush()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        prog.run_range(idx, idx + 1)
+        e1.record()
+        e1.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return statistics.median(ts)
+
+
+def kernel_breakdown(tr, flush):
+    """CUDA-event time of every GEMM-class op of the step, launched alone (L2 flushed before each launch), and its
+    algorithmic FLOP/s.  Returns the rows, slowest first (no op is excluded)."""
     from b2h_b200 import _lib as L
     rows = []
     plans = [("G_train", tr.G_train), ("D_eval", tr.D_eval), ("G_eval", tr.G_eval), ("D_train", tr.D_train)]
     for pname, plan in plans:
         for idx, macs in sorted(plan.op_macs.items()):
             rec = plan.prog.recs[idx]
-            seg_ok = any(s <= idx < e for n, (s, e) in plan.prog.segments.items() if n in ("fwd", "bwd"))
-            if not seg_ok:
+            if not any(s <= idx < e for n, (s, e) in plan.prog.segments.items() if n in ("fwd", "bwd")):
                 continue
-            ts = []
-            for _ in range(reps):
-                flush()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                plan.prog.run_range(idx, idx + 1)
-                e1.record()
-                e1.synchronize()
-                ts.append(e0.elapsed_time(e1))
-            ms = statistics.median(ts)
+            ms = _time_op(plan.prog, idx, flush)
             row = {"op": f"{pname}.{rec.tag}", "ms": ms, "gflop": 2 * macs / 1e9,
                    "tflops": 2 * macs / (ms * 1e-3) / 1e12 if ms > 0 else 0.0}
-            if rec.kind == L.OP_WGRAD and plan.wgrad_direct and rec.f.get("splits") == 1:
-                # split-free weight gradient: a dozen CTAs by design (it runs beside the backward chain on a side
-                # stream); its duration alone says nothing about the GPU's tensor throughput
-                row["side_stream_few_ctas"] = True
+            try:
+                pl = plan.prog.op_plan(idx)
+                row["tile_n"], row["ctas"] = pl["tile_n"], pl["grid"][0] * pl["grid"][1] * pl["grid"][2]
+                if rec.kind == L.OP_WGRAD:
+                    row["splits"] = pl["splits"]
+            except Exception:
+                pass
             rows.append(row)
+    rows.sort(key=lambda r: -r["ms"])
     return rows
+
+
+def hbm_records(tr, flush, peak_gbs):
+    """The bandwidth-bound kernels of the step launched alone (L2 flushed before): achieved GB/s of their ALGORITHMIC
+    bytes (L1 12 B/element in fp32 mode, Adam 28 B/parameter, BN-apply read z + write a + keep flags)."""
+    from b2h_b200 import _lib as L
+    esz = 2 if tr.dtype == L.BF16 else 4
+    out = []
+
+    def add(name, prog, idx, nbytes, what):
+        ms = _time_op(prog, idx, flush)
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        out.append({"kernel": name, "launch_ms": round(ms, 5), "algorithmic_bytes": int(nbytes),
+                    "achieved": round(gbs, 1), "peak": peak_gbs, "unit": "GB/s", "frac": round(gbs / peak_gbs, 4),
+                    "bytes": what})
+
+    for i, rec in enumerate(tr.g_loss_prog.recs):
+        if rec.kind == L.OP_L1:
+            n = rec.f["B"] * rec.f["C"] * rec.f["L"]
+            add("l1_kernel (" + rec.tag + ")", tr.g_loss_prog, i, n * (4 + 4 + esz),
+                f"read out fp32 + read gt fp32 + write dout {esz} B, per element")
+        if rec.kind == L.OP_ADAM and rec.f.get("phase", 0) == 0:
+            add("adam_kernel (generator, whole flat buffer)", tr.g_loss_prog, i, rec.f["n"] * 28,
+                "28 B/parameter: read p, g, m, v; write p, m, v")
+    big = None
+    for i, rec in enumerate(tr.G_train.prog.recs):
+        if rec.kind == L.OP_BN_APPLY:
+            n = rec.f["B"] * rec.f["L"] * rec.f["C"] * rec.f["nsrc"]
+            if big is None or n > big[1]:
+                big = (i, n, rec)
+    if big is not None:
+        i, _, rec = big
+        elems = rec.f["B"] * rec.f["L"] * rec.f["C"]
+        nbytes = elems * (esz * rec.f["nsrc"] + esz + (1 if rec.f["drop"].get("save") is not None else 0))
+        add(f"bn_apply_kernel ({rec.tag})", tr.G_train.prog, i, nbytes,
+            f"read {rec.f['nsrc']} x z + write a ({esz} B each) + 1 B keep flag, per element")
+    return out
+
+
+def make_pool(B, T, cin, cout, feats_kind, dev, seed):
+    xs, ys, fs = [], [], []
+    for k in range(POOL):
+        x, y, f = synth_batch(B, T, cin, cout, feats_kind, seed=seed + 1000 * k)
+        xs.append(x.to(dev))
+        ys.append(y.to(dev))
+        fs.append(f.to(dev) if f is not None else None)
+    return xs, ys, fs
+
+
+def interval_ms(fn_step, steps, world):
+    """K steps as ONE device-timed interval (CUDA events on the launch stream, barrier + synchronize on both sides)."""
+    import torch.distributed as dist
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(steps):
+        fn_step(k)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    return e0.elapsed_time(e1)
+
+
+def max_over_ranks(v, dev, world):
+    if world <= 1:
+        return float(v)
+    import torch.distributed as dist
+    t = torch.tensor([v], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t[0])
+
+
+def run_train_config(variant, feats, precision, B, T, cin, cout, dev, world, rank, pg, steps, warmup, pipelined=True,
+                     keep=False):
+    """GAN training step of one configuration: builds the trainer, warms up, times `steps` steps as one interval.
+    Returns (result dict, trainer or None)."""
+    import torch.distributed as dist
+    from b2h_b200.trainer import GanTrainer
+    kw = {}
+    if os.environ.get("B2H_BUCKETS"):
+        kw["n_buckets"] = int(os.environ["B2H_BUCKETS"])
+    tr = GanTrainer(variant, cin, cout, feats, B, T, precision=precision, device=dev, lr=1e-4, seed=23456 + rank,
+                    drop_mode="philox", world_size=world, process_group=pg, **kw)
+    if world > 1:   # identical initial weights on every rank (DDP convention)
+        for st in (tr.g_store, tr.d_store):
+            dist.broadcast(st.flat, 0)
+            dist.broadcast(st.bufs, 0)
+    fk = feats_kind_of(variant, feats)
+    xs, ys, fs = make_pool(B, T, cin, cout, fk, dev, seed=23456 + rank)
+    tr.load_batch(xs[0], ys[0], fs[0])
+
+    def step(k):
+        j = (k + 1) % POOL
+        if pipelined:
+            tr.advance_batch(xs[j], ys[j], fs[j])   # the batch G just saw goes to D, the next one to G
+            tr.gan_step(graph=True)                 # D step on the previous batch || G step on the current one
+        else:
+            tr.load_batch(xs[j], ys[j], fs[j])
+            tr.generator_step(graph=True)
+            tr.discriminator_step(graph=True)
+
+    if pipelined:                             # pipeline prologue: G0; every timed step is then [D_k || G_k+1]
+        tr.generator_step(graph=True)
+    for k in range(max(warmup, 3)):
+        step(k)
+    ms = max_over_ranks(interval_ms(step, steps, world), dev, world)
+    res = {"ms_per_step": ms / steps, "value": B * T * world * steps / (ms * 1e-3), "steps": steps,
+           "dtype": "bf16" if precision == "bf16" else "f32", "n_gpus": world}
+    if not keep:
+        tr.release_graphs()
+        tr = None
+    return res, (tr, xs, ys, fs)
+
+
+def run_infer_config(variant, feats, precision, B, T, cin, cout, dev, world, steps, warmup):
+    """Batched eval forward (inference.py:96-121): inputs resident, rotating over POOL batches."""
+    from b2h_b200 import _lib as L
+    from b2h_b200 import nets
+    spec = nets.generator_spec(variant, cin, cout, feats, train=False)
+    store = nets.ParamStore(spec, dev, seed=23456)
+    plan = nets.NetPlan(spec, store, B, T, L.BF16 if precision == "bf16" else L.F32, dev, train=False)
+    fk = feats_kind_of(variant, feats)
+    g = torch.Generator(device=dev).manual_seed(7)
+    xs = [torch.randn(B, cin, T, device=dev, generator=g) for _ in range(POOL)]
+    fs = [None] * POOL
+    if fk == "text":
+        fs = [torch.nn.functional.normalize(torch.randn(B, 512, device=dev, generator=g), dim=1) for _ in range(POOL)]
+    elif fk == "image":
+        fs = [torch.randn(B, T, 2000, device=dev, generator=g) * 2 for _ in range(POOL)]
+
+    def step(k):
+        j = k % POOL
+        plan.x.copy_(xs[j], non_blocking=True)
+        if fs[j] is not None:
+            plan.feats.copy_(fs[j], non_blocking=True)
+        plan.forward()
+
+    for k in range(max(warmup, 3)):
+        step(k)
+    ms = max_over_ranks(interval_ms(step, steps, world), dev, world)
+    launches = plan.prog.segment_launches.get("fwd", 0)
+    return {"ms_per_step": ms / steps, "value": B * T * world * steps / (ms * 1e-3), "steps": steps,
+            "dtype": "bf16" if precision == "bf16" else "f32", "n_gpus": world, "gpu_launches_per_step": launches}
+
+
+def algorithmic_gflop_per_step(tr):
+    """SURVEY 8d: generator step 3 x forward MACs minus the first layer's dgrad plus the discriminator scoring pass;
+    discriminator step = generator forward + 2 x (D forward + backward minus the first layer's dgrad)."""
+    g_fwd = sum(tr.G_train._layer_macs(l) for l in tr.G_train.spec.layers)
+    g_first = sum(tr.G_train._layer_macs(l) for l in tr.G_train.spec.layers if not tr.G_train._needs_dgrad(l))
+    d_fwd_1 = sum(tr.D_eval._layer_macs(l) for l in tr.D_eval.spec.layers)             # B clips
+    d_first_1 = sum(tr.D_eval._layer_macs(l) for l in tr.D_eval.spec.layers if not tr.D_eval._needs_dgrad(l))
+    g_step = 3 * g_fwd - g_first + d_fwd_1
+    d_step = g_fwd + 2 * d_fwd_1 + 2 * (2 * d_fwd_1 - d_first_1)
+    return 2 * (g_step + d_step) / 1e9
 
 
 def main():
@@ -280,7 +467,6 @@ def main():
         return reference_main(a)
     import torch.distributed as dist
     import b2h_b200  # noqa: F401
-    from b2h_b200.trainer import GanTrainer
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -293,116 +479,62 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
         pg = dist.group.WORLD
     cin, cout = pipeline_dims(a)
-    feats_kind = None if not a.feats else ("image" if a.variant == "b2h" else "text")
+    feats_kind = feats_kind_of(a.variant, a.feats)
+    cfg = config_of(a, world)   # (before a.batch becomes the per-GPU batch under strong scaling)
     if a.scaling == "strong":
         assert a.batch % world == 0, "--scaling strong: --batch must be divisible by the number of GPUs"
         a.batch //= world                     # from here on a.batch is the per-GPU batch
+        cfg["global_batch"] = a.batch * world
     B, T = a.batch, a.frames
-    kw = {}
-    if os.environ.get("B2H_BUCKETS"):
-        kw["n_buckets"] = int(os.environ["B2H_BUCKETS"])
-    tr = GanTrainer(a.variant, cin, cout, a.feats, B, T, precision=a.precision, device=dev, lr=1e-4, seed=23456 + rank,
-                    drop_mode="philox", world_size=world, process_group=pg, **kw)
-    if world > 1:   # identical initial weights on every rank (DDP convention)
-        for st in (tr.g_store, tr.d_store):
-            dist.broadcast(st.flat, 0)
-            dist.broadcast(st.bufs, 0)
-    x, y, f = synth_batch(B, T, cin, cout, feats_kind, seed=23456 + rank)
-    hx, hy = x.pin_memory(), y.pin_memory()
-    hf = f.pin_memory() if f is not None else None
-    tr.x.copy_(hx)
-    tr.y.copy_(hy)
-    if hf is not None:
-        tr.feats.copy_(hf)
-    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
-
-    def flush():
-        flush_buf.fill_(1)
-
-    use_graph = True
-
     pipelined = a.mode == "train" and a.schedule == "pipelined"
-
-    def step():
-        if pipelined:
-            tr.gan_step(graph=use_graph)      # D step on the previous batch || G step on the current one
-        elif a.mode == "train":
-            tr.generator_step(graph=use_graph)
-            tr.discriminator_step(graph=use_graph)
-        else:
-            tr.infer()
-
-    if pipelined:                             # pipeline prologue: G0; every timed step is then [D_k || G_k+1]
-        tr.generator_step(graph=use_graph)
-        tr._sync_d_batch()
-    for _ in range(max(a.warmup, 3)):
-        step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    torch.cuda.synchronize()
-    ev = []
     t_wall0 = time.perf_counter()
-    for _ in range(a.steps):
-        flush()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        step()
-        e1.record()
-        ev.append((e0, e1))
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
+    tr = None
+    if a.mode == "train":
+        res, (tr, xs, ys, fs) = run_train_config(a.variant, a.feats, a.precision, B, T, cin, cout, dev, world, rank, pg,
+                                                 a.steps, a.warmup, pipelined=pipelined, keep=True)
+    else:
+        res = run_infer_config(a.variant, a.feats, a.precision, B, T, cin, cout, dev, world, a.steps, a.warmup)
     t_wall = time.perf_counter() - t_wall0
-    dev_ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
     # ---- end to end: pinned host buffers -> H2D -> step -> D2H of the losses, every step
-    h_loss = torch.empty(8, dtype=torch.float32).pin_memory()
-    for _ in range(2):                     # untimed: creates the copy stream and the staging buffers
-        tr.prefetch_batch(hx, hy, hf)
-        tr.swap_batch(pipelined=pipelined)
-        step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
+    e2e_value = h2d = d2h = None
+    if a.mode == "train":
+        x, y, f = synth_batch(B, T, cin, cout, feats_kind, seed=99 + rank)
+        hx, hy = x.pin_memory(), y.pin_memory()
+        hf = f.pin_memory() if f is not None else None
+        h_loss = torch.empty(8, dtype=torch.float32).pin_memory()
+
+        def step():
+            if pipelined:
+                tr.gan_step(graph=True)
+            else:
+                tr.generator_step(graph=True)
+                tr.discriminator_step(graph=True)
+
+        for _ in range(2):                     # untimed: creates the copy stream and the staging buffers
+            tr.prefetch_batch(hx, hy, hf)
+            tr.swap_batch(pipelined=pipelined)
+            step()
         torch.cuda.synchronize()
-    if a.mode != "train":
-        # inference: every step's prediction goes back to pinned host memory; the D2H of step k runs on its own
-        # stream from a device staging copy while step k+1 computes (the timed region ends when all have landed)
-        h_out = torch.empty(tr.G_eval.out.shape, dtype=torch.float32).pin_memory()
-        stage_out = torch.empty_like(tr.G_eval.out)
-        d2h = torch.cuda.Stream(dev)
-        d2h_done = None
-        torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    tr.prefetch_batch(hx, hy, hf)          # batch 0; every later batch is copied while the previous one trains
-    for _ in range(a.steps):
-        tr.swap_batch(pipelined=pipelined)
-        tr.prefetch_batch(hx, hy, hf)      # H2D of the next step's inputs, pinned host -> staging, copy stream
-        step()
-        if a.mode == "train":
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        tr.prefetch_batch(hx, hy, hf)          # batch 0; every later batch is copied while the previous one trains
+        for _ in range(a.steps):
+            tr.swap_batch(pipelined=pipelined)
+            tr.prefetch_batch(hx, hy, hf)      # H2D of the next step's inputs, pinned host -> staging, copy stream
+            step()
             h_loss.copy_(tr.losses, non_blocking=True)
             torch.cuda.synchronize()
-        else:
-            cur = torch.cuda.current_stream(dev)
-            if d2h_done is not None:
-                cur.wait_event(d2h_done)             # the staging copy is free again
-            stage_out.copy_(tr.G_eval.out, non_blocking=True)
-            ready = torch.cuda.Event()
-            ready.record(cur)
-            d2h.wait_event(ready)
-            with torch.cuda.stream(d2h):
-                h_out.copy_(stage_out, non_blocking=True)
-            d2h_done = torch.cuda.Event()
-            d2h_done.record(d2h)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+        e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3, dev, world)
+        e2e_value = B * T * world * a.steps / (e2e_ms * 1e-3)
+        h2d = (hx.numel() * 4 + hy.numel() * 4 + (hf.numel() * 4 if hf is not None else 0)) * world
+        d2h = 32 * world
     clocks = sampler.stop()
-    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
     ranks_in_sync = None
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if world > 1 and tr is not None:
         # data-parallel sanity: identical initial weights + summed gradients -> identical weights on every rank
         chk = torch.stack([tr.g_store.flat.double().sum(), tr.g_store.flat.double().abs().sum(),
                            tr.d_store.flat.double().sum(), tr.d_store.flat.double().abs().sum()])
@@ -410,60 +542,93 @@ def main():
         dist.all_reduce(hi, op=dist.ReduceOp.MAX)
         dist.all_reduce(lo, op=dist.ReduceOp.MIN)
         ranks_in_sync = bool(((hi - lo).abs() <= 1e-9 * hi.abs()).all()) and bool(torch.isfinite(chk).all())
-    dev_ms, e2e_ms = float(t[0]), float(t[1])
-    frames = B * T * world * a.steps
-    value = frames / (dev_ms * 1e-3)
-    e2e_value = frames / (e2e_ms * 1e-3)
-    # whole-job bytes per step (every rank copies its own batch)
-    h2d = (hx.numel() * 4 + hy.numel() * 4 + (hf.numel() * 4 if hf is not None else 0)) * world
-    d2h = (32 if a.mode == "train" else tr.G_eval.out.numel() * 4) * world
-    launches = tr.launches_per_gan_step() if a.mode == "train" else tr.G_eval.prog.segment_launches.get("fwd", 0)
+    launches = tr.launches_per_gan_step() if tr is not None else res.get("gpu_launches_per_step", 0)
     line = {
         "metric": "training frames/sec" if a.mode == "train" else "inference frames/sec",
-        "value": value, "unit": "frames/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
-        "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
+        "value": res["value"], "unit": "frames/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+        "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
         "dtype": a.precision if a.precision == "bf16" else "f32", "data": "synthetic",
-        "config": {"workload": workload_name(a), "global_batch": B * world, "frames": T,
-                   "parallelism": f"dp{world}" if world > 1 else "single",
-                   **({"dp_exchange": "b2h_dp_adam: reduce-scatter + Adam + all-gather in one kernel over peer memory"
-                       if getattr(tr, "fused_dp", False) else "ncclAllReduce of the flat gradient, then b2h_adam"}
-                      if world > 1 else {}),
-                   "timing": "CUDA events per step on the launch stream, 256 MiB L2 flush before every timed step, "
-                             "CUDA-graph replay, dropout = Philox",
+        "config": cfg,
+        "method": {"timing": "the K steps are ONE interval between two CUDA events on the launch stream (barrier + "
+                             "synchronize on both sides, max over ranks); CUDA-graph replay; dropout = Philox",
                    "schedule": ("pipelined: every timed step = discriminator step k overlapped with generator step "
                                 "k+1 (independent work: same results as the alternating order)") if pipelined else
-                               "sequential: generator step then discriminator step"},
+                               "sequential: generator step then discriminator step",
+                   **({"dp_exchange": "b2h_dp_adam: reduce-scatter + Adam + all-gather in one kernel over peer memory"
+                       if getattr(tr, "fused_dp", False) else "ncclAllReduce of the flat gradient, then b2h_adam"}
+                      if world > 1 and tr is not None else {})},
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches) * a.steps,
         "ranks_in_sync": ranks_in_sync,
         "wall_s": t_wall,
     }
+    if e2e_value is not None:
+        line["e2e"] = {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
+    # ---- the other BASELINE configs, short runs, every rank takes part (data parallel where they train)
+    if not a.no_extra_configs and a.mode == "train":
+        extras = {}
+        ks, kw_ = a.extra_steps, 3
+        todo = [("config2_fp32_mode", "train", "v1", False, "fp32", 256, 64),
+                ("config3_text_bf16", "train", "v1", True, "bf16", 256, 64),
+                ("config4_image_bf16", "train", "b2h", True, "bf16", 256, 64),
+                ("config1_eval_32x64_fp32", "infer", "v1", False, "fp32", 32, 64),
+                ("config5_infer_4096x64_bf16", "infer", "v1", False, "bf16", 4096, 64),
+                ("config5_infer_64x1024_bf16", "infer", "v1", False, "bf16", 64, 1024),
+                ("config5_infer_v2text_4096x64_bf16", "infer", "v2", True, "bf16", 4096, 64),
+                ("config5_infer_4096x64_fp32", "infer", "v1", False, "fp32", 4096, 64)]
+        for name, mode, variant, feats, prec, eb, et in todo:
+            try:
+                if mode == "train":
+                    r, _ = run_train_config(variant, feats, prec, eb, et, 36, 252, dev, world, rank, pg, ks, kw_)
+                else:
+                    r = run_infer_config(variant, feats, prec, eb, et, 36, 252, dev, world, ks, kw_)
+                cond = "" if not feats else ("+image" if variant == "b2h" else "+text")
+                r["workload"] = (f"{variant}{cond} arm2wh 36->252, " + ("GAN training step" if mode == "train" else
+                                 "eval forward") + f", batch {eb} x {et} frames per GPU")
+                r["unit"] = "frames/s"
+                extras[name] = {k: (round(v, 5) if isinstance(v, float) else v) for k, v in r.items()}
+            except Exception as ex:   # an extra must never take the headline line down
+                extras[name] = {"error": str(ex)[:300]}
+            torch.cuda.empty_cache()
+        line["configs"] = extras
     if rank == 0:
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        if not a.no_kernel_breakdown and a.mode == "train":
+        flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+        def flush():
+            flush_buf.fill_(1)
+
+        if not a.no_kernel_breakdown and tr is not None:
             rows = kernel_breakdown(tr, flush)
-            rows.sort(key=lambda r: -r["ms"])
-            dom = [r for r in rows if not r.get("side_stream_few_ctas")][0]   # dominant full-grid GEMM launch
+            dom = rows[0]                                 # the time-dominant launch, whatever it is
             peak = peaks.get("bf16_tflops", 1590.0)
             which = "measured burst (MEASURED_PEAKS.json bf16_tflops)" if "bf16_tflops" in peaks else "fallback 1.59 PF"
+            if a.precision != "bf16":
+                # fp32 mode = 3 x TF32 passes on the tensor cores: the ceiling is a third of the TF32 rate (half of bf16)
+                peak, which = peak / 6.0, which + " / 6 (TF32 = half the bf16 rate, three passes per product)"
             traffic = None
             try:
                 traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(dom["op"])
             except Exception:
                 pass
+            gflop_step = algorithmic_gflop_per_step(tr)
+            step_tflops = gflop_step / res["ms_per_step"]          # GFLOP / ms = TFLOP/s
             line["roofline"] = {"bound": "tensor", "kernel": dom["op"], "achieved": dom["tflops"], "peak": peak,
                                 "unit": "TFLOP/s", "frac": dom["tflops"] / peak, "traffic": traffic,
                                 "peak_source": which, "launch_ms": dom["ms"], "algorithmic_gflop": dom["gflop"],
-                                "how": "CUDA events around the launch alone, L2 flushed before it (cold operands; in "
-                                       "the step they are L2-resident), median of 5; the split-free side-stream "
-                                       "wgrads (a dozen CTAs by design) are excluded from the choice"}
+                                "step_frac": step_tflops / peak, "step_tflops": step_tflops,
+                                "step_algorithmic_gflop": gflop_step,
+                                "how": "kernel = the slowest GEMM-class launch of the step, nothing excluded; CUDA events "
+                                       "around the launch alone, L2 flushed before it (cold operands; in the step they "
+                                       "are L2-resident), median of 5.  step_frac = algorithmic FLOP of the whole GAN "
+                                       "step / ms_per_step / peak",
+                                "hbm": hbm_records(tr, flush, peaks.get("hbm_gbs", 6549.4))}
             line["kernel_breakdown"] = [{k: (round(v, 5) if isinstance(v, float) else v) for k, v in r.items()}
-                                        for r in rows[:12]]
+                                        for r in rows[:14]]
             line["gemm_ms_sum"] = sum(r["ms"] for r in rows)
         if not a.no_cpu_baseline:
             fps, med, cores = run_cpu_reference(a, steps=5, warmup=2)
@@ -480,12 +645,18 @@ def main():
                 line["cpu_baseline"]["same_port_torch_eager_on_this_gpu"] = {"error": str(ex)[:200]}
         print(json.dumps(line), flush=True)
     if world > 1:
-        # CUDA graphs that captured NCCL kernels keep the communicator busy at interpreter teardown: leave
-        # without destroying the process group (every rank has finished its work and its output by now)
-        torch.cuda.synchronize()
+        # teardown: the captured graphs hold NCCL kernels -- drop them before the communicator goes away.  A watchdog
+        # ends the process if the teardown itself wedges (the result line is already out).
         sys.stdout.flush()
         sys.stderr.flush()
-        os._exit(0)
+        torch.cuda.synchronize()
+        dist.barrier()           # rank 0 has finished its single-rank measurements (breakdown, CPU baseline)
+        threading.Thread(target=lambda: (time.sleep(45), sys.stderr.write("bench: teardown timed out\n"), os._exit(0)),
+                         daemon=True).start()
+        if tr is not None:
+            tr.release_graphs()
+        torch.cuda.synchronize()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
