@@ -93,4 +93,31 @@ __device__ __forceinline__ void epilogue_store(const EpiParams& e, const DropCtx
   }
 }
 
+// finish 8 accumulator columns [nn, nn+8) of one output row: bias -> act -> eval-BN -> dropout keep*2
+__device__ __forceinline__ void epi_finish8(const EpiParams& e, const DropCtx& drop, uint64_t drop_row_base, int nn,
+                                            const uint32_t* acc_bits, float* v) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float x = __uint_as_float(acc_bits[j]);
+    if (e.bias) x += __ldg(e.bias + nn + j);
+    x = act_fwd(x, e.act);
+    if (e.post_scale) x = fmaf(x, __ldg(e.post_scale + nn + j), __ldg(e.post_shift + nn + j));
+    v[j] = x;
+  }
+  if (drop.mode != B2H_DROP_NONE) {
+#pragma unroll
+    for (int j = 0; j < 8; j += 4) {
+      if (nn + j + 3 < e.drop_C) {
+        float4 m = drop.scale4(drop_row_base + nn + j);
+        v[j] *= m.x, v[j + 1] *= m.y, v[j + 2] *= m.z, v[j + 3] *= m.w;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (nn + j + k < e.drop_C) v[j + k] *= drop.scale1(drop_row_base + nn + j + k);
+      }
+    }
+  }
+}
+
+
 }  // namespace b2h

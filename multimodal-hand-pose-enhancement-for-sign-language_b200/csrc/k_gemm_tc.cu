@@ -95,32 +95,6 @@ __device__ __forceinline__ void epi_fast8(const float* s_bias, const float* s_sc
   }
 }
 
-// finish 8 accumulator columns [nn, nn+8) of one output row: bias -> act -> eval-BN -> dropout keep*2
-__device__ __forceinline__ void epi_finish8(const EpiParams& e, const DropCtx& drop, uint64_t drop_row_base, int nn,
-                                            const uint32_t* acc_bits, float* v) {
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    float x = __uint_as_float(acc_bits[j]);
-    if (e.bias) x += __ldg(e.bias + nn + j);
-    x = act_fwd(x, e.act);
-    if (e.post_scale) x = fmaf(x, __ldg(e.post_scale + nn + j), __ldg(e.post_shift + nn + j));
-    v[j] = x;
-  }
-  if (drop.mode != B2H_DROP_NONE) {
-#pragma unroll
-    for (int j = 0; j < 8; j += 4) {
-      if (nn + j + 3 < e.drop_C) {
-        float4 m = drop.scale4(drop_row_base + nn + j);
-        v[j] *= m.x, v[j + 1] *= m.y, v[j + 2] *= m.z, v[j + 3] *= m.w;
-      } else {
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (nn + j + k < e.drop_C) v[j + k] *= drop.scale1(drop_row_base + nn + j + k);
-      }
-    }
-  }
-}
-
 // STATS: the epilogue also produces the train-mode BatchNorm statistics of the tile it stores (per-column
 // shifted sums of the bf16-rounded outputs -> fp64 atomics -> the last CTA finalises), see bn_finalize.cuh.
 // BWDSUM (dgrad): the store phase also accumulates the first pass of the producer layer's BatchNorm backward,
@@ -705,36 +679,38 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// bf16 tensor map over a (C, L, B) view: element (c, l, b) at base + (b*sample_pitch + l*row_pitch + c)*2 bytes
-static int make_map_3d(CUtensorMap* m, const void* base, int64_t C, int64_t L, int64_t B, int64_t row_pitch,
-                       int64_t sample_pitch, int box_c, int box_l, int box_b, bool swizzle128 = true) {
+// tensor map over a (C, L, B) view of a bf16 (esz = 2) or fp32 (esz = 4) tensor: element (c, l, b) at
+// base + (b*sample_pitch + l*row_pitch + c) * esz bytes
+int make_map_3d(CUtensorMap* m, const void* base, int64_t C, int64_t L, int64_t B, int64_t row_pitch,
+                int64_t sample_pitch, int box_c, int box_l, int box_b, bool swizzle128, int esz) {
   EncodeTiledFn fn = get_encode_fn();
   B2H_CHECK_ARG(fn != nullptr, B2H_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
   cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)L, (cuuint64_t)B};
-  cuuint64_t strides[2] = {(cuuint64_t)row_pitch * 2, (cuuint64_t)sample_pitch * 2};
+  cuuint64_t strides[2] = {(cuuint64_t)row_pitch * esz, (cuuint64_t)sample_pitch * esz};
   cuuint32_t box[3] = {(cuuint32_t)box_c, (cuuint32_t)box_l, (cuuint32_t)box_b};
   cuuint32_t estr[3] = {1, 1, 1};
   B2H_CHECK_ARG(((uintptr_t)base % 16) == 0 && strides[0] % 16 == 0 && strides[1] % 16 == 0, B2H_ERR_ALIGN,
                 "tensor map: base/strides must be 16-byte aligned");
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+  CUresult r = fn(m, esz == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+                  const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   B2H_CHECK_ARG(r == CUDA_SUCCESS, B2H_ERR_CUDA, "cuTensorMapEncodeTiled(3d) failed: %d (C=%lld L=%lld B=%lld)", (int)r,
                 (long long)C, (long long)L, (long long)B);
   return B2H_OK;
 }
 
-static int make_map_2d(CUtensorMap* m, const void* base, int64_t K, int64_t N, int64_t row_pitch, int box_k, int box_n) {
+int make_map_2d(CUtensorMap* m, const void* base, int64_t K, int64_t N, int64_t row_pitch, int box_k, int box_n, int esz) {
   EncodeTiledFn fn = get_encode_fn();
   B2H_CHECK_ARG(fn != nullptr, B2H_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
-  cuuint64_t strides[1] = {(cuuint64_t)row_pitch * 2};
+  cuuint64_t strides[1] = {(cuuint64_t)row_pitch * esz};
   cuuint32_t box[2] = {(cuuint32_t)box_k, (cuuint32_t)box_n};
   cuuint32_t estr[2] = {1, 1};
   B2H_CHECK_ARG(((uintptr_t)base % 16) == 0 && strides[0] % 16 == 0, B2H_ERR_ALIGN, "tensor map: alignment");
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = fn(m, esz == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                  const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   B2H_CHECK_ARG(r == CUDA_SUCCESS, B2H_ERR_CUDA, "cuTensorMapEncodeTiled(2d) failed: %d", (int)r);
   return B2H_OK;
 }
@@ -766,22 +742,24 @@ static void tap_view(int stride, int off, int* map, int* coord) {
 }
 
 // strided views of a [B][L][ld] tensor: view 0 = rows 0,2,4.. (or all rows if stride 1), view 1 = rows 1,3,5..
+// (boxes of 128 bytes of channels: 64 bf16 / 32 fp32)
 static int make_row_views(CUtensorMap* m0, CUtensorMap* m1, bool* has1, const void* base, int C, int L, int B, int ld,
-                          int stride, int box_l, int box_b) {
-  const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(base);
+                          int stride, int box_l, int box_b, int esz) {
+  const uint8_t* p = reinterpret_cast<const uint8_t*>(base);
+  const int box_c = 128 / esz;
   int rc;
   if (stride == 1) {
-    rc = make_map_3d(m0, p, C, L, B, ld, (int64_t)L * ld, 64, box_l, box_b);
+    rc = make_map_3d(m0, p, C, L, B, ld, (int64_t)L * ld, box_c, box_l, box_b, true, esz);
     if (rc) return rc;
     *m1 = *m0;
     *has1 = false;
     return B2H_OK;
   }
   int Le = (L + 1) / 2, Lod = L / 2;
-  rc = make_map_3d(m0, p, C, Le, B, 2 * (int64_t)ld, (int64_t)L * ld, 64, box_l, box_b);
+  rc = make_map_3d(m0, p, C, Le, B, 2 * (int64_t)ld, (int64_t)L * ld, box_c, box_l, box_b, true, esz);
   if (rc) return rc;
   if (Lod > 0) {
-    rc = make_map_3d(m1, p + ld, C, Lod, B, 2 * (int64_t)ld, (int64_t)L * ld, 64, box_l, box_b);
+    rc = make_map_3d(m1, p + (size_t)ld * esz, C, Lod, B, 2 * (int64_t)ld, (int64_t)L * ld, box_c, box_l, box_b, true, esz);
     if (rc) return rc;
     *has1 = true;
   } else {
@@ -793,14 +771,22 @@ static int make_row_views(CUtensorMap* m0, CUtensorMap* m1, bool* has1, const vo
 
 static int epi_kind(const b2h_gemm_t& d);
 
-int plan_gemm_bf16(const b2h_gemm_t& d, TcGemmPlan* plan) {
+int plan_gemm_bf16(const b2h_gemm_t& d, TcGemmPlan* plan) { return plan_gemm_tc(d, plan, 2); }
+
+// esz = 2: bf16 operands (kind::f16);  esz = 4: fp32 operands, 3xTF32 (k_gemm_tf32.cu).  A k-block is 128 bytes of
+// channels either way: 64 bf16 / 32 fp32.
+int plan_gemm_tc(const b2h_gemm_t& d, TcGemmPlan* plan, int esz) {
   TcGemmParams& p = plan->p;
+  const int bke = 128 / esz;
+  plan->esz = esz;
   p.B = d.B;
   p.Lo = d.Lo;
   p.Kc = d.Kc;
   p.stride = d.stride;
-  B2H_CHECK_ARG(d.ldo % 8 == 0 && d.out_coff % 8 == 0 && ((uintptr_t)d.out % 16) == 0, B2H_ERR_ALIGN,
-                "gemm_bf16: out/ldo/out_coff must allow 16-byte row stores (ldo=%d coff=%d)", d.ldo, d.out_coff);
+  B2H_CHECK_ARG(d.ldo % (16 / esz) == 0 && d.out_coff % (16 / esz) == 0 && ((uintptr_t)d.out % 16) == 0 &&
+                    (d.out_f32 == 0 || d.ldo % 4 == 0),
+                B2H_ERR_ALIGN, "gemm_tc: out/ldo/out_coff must allow 16-byte row stores (ldo=%d coff=%d)", d.ldo,
+                d.out_coff);
   int rc;
   // tap-merged main loop: stride 1, taps forming a run of consecutive row offsets, and a tile of tl <= 16 rows x
   // tb >= 8 samples whose A box (tl + ntaps - 1 rows) fits the A stage
@@ -829,7 +815,7 @@ int plan_gemm_bf16(const b2h_gemm_t& d, TcGemmPlan* plan) {
       p.ntaps = d.ntaps;
       for (int t = 0; t < d.ntaps; ++t) p.tap_w[t] = order[t], p.tap_map[t] = 0, p.tap_coord[t] = d.tap_off[order[t]];
       // dims (C, B, L): the box lands as [row][sample][64 channels]
-      rc = make_map_3d(&plan->tmA0, d.A, d.Kc, d.B, d.La, (int64_t)d.La * d.lda, d.lda, 64, p.tb, best + h);
+      rc = make_map_3d(&plan->tmA0, d.A, d.Kc, d.B, d.La, (int64_t)d.La * d.lda, d.lda, bke, p.tb, best + h, true, esz);
       if (rc) return rc;
       plan->tmA1 = plan->tmA0;
     }
@@ -838,7 +824,7 @@ int plan_gemm_bf16(const b2h_gemm_t& d, TcGemmPlan* plan) {
     p.tl = choose_tl(d.Lo, TC_BM);
     p.tb = TC_BM / p.tl;
     bool has1 = false;
-    rc = make_row_views(&plan->tmA0, &plan->tmA1, &has1, d.A, d.Kc, d.La, d.B, d.lda, d.stride, p.tl, p.tb);
+    rc = make_row_views(&plan->tmA0, &plan->tmA1, &has1, d.A, d.Kc, d.La, d.B, d.lda, d.stride, p.tl, p.tb, esz);
     if (rc) return rc;
     // taps that only ever read the (empty) odd view contribute nothing: drop them
     p.ntaps = 0;
@@ -863,15 +849,18 @@ int plan_gemm_bf16(const b2h_gemm_t& d, TcGemmPlan* plan) {
   const int m_tiles = ceil_div(d.B, p.tb) * p.n_lchunks;
   // tile width: the largest BN (dividing one phase) that minimises the estimated wave time
   const int half = d.Npad / d.nphase;
-  const int nkb = p.ntaps * (d.Kc / TC_BK);
+  const int nkb = p.ntaps * (d.Kc / bke);
   int best_bn = 64;
   double best_t = 1e30;
   const int sms = sm_count();
-  for (int bn = 64; bn <= 256; bn <<= 1) {
+  // (3xTF32: three MMAs of half the rate per 32-channel k-block, tiles up to 128 columns: two accumulator slots)
+  const int bn_max = esz == 4 ? 128 : 256;
+  const double kcost = esz == 4 ? 6.0 : 2.0;
+  for (int bn = 64; bn <= bn_max; bn <<= 1) {
     if (half % bn) continue;
     int64_t tiles = (int64_t)m_tiles * (d.Npad / bn);
     double waves = (double)((tiles + sms - 1) / sms);
-    double t = waves * (3000.0 + (double)nkb * 2.0 * bn + 12.0 * bn);
+    double t = waves * (3000.0 + (double)nkb * kcost * bn + 12.0 * bn);
     if (t < best_t * 0.999) {
       best_t = t;
       best_bn = bn;
@@ -879,7 +868,7 @@ int plan_gemm_bf16(const b2h_gemm_t& d, TcGemmPlan* plan) {
   }
   if (const char* f = getenv("B2H_FORCE_BN")) {  // tuning aid
     int bn = atoi(f);
-    if ((bn == 64 || bn == 128 || bn == 256) && half % bn == 0) best_bn = bn;
+    if ((bn == 64 || bn == 128 || bn == 256) && bn <= bn_max && half % bn == 0) best_bn = bn;
   }
   if (getenv("B2H_DEBUG_PLAN"))
     fprintf(stderr, "[b2h] gemm plan: B=%d Lo=%d Kc=%d Npad=%d ntaps=%d stride=%d nphase=%d -> merged=%d tl=%d tb=%d BN=%d tiles=%dx%d\n",
@@ -888,9 +877,11 @@ int plan_gemm_bf16(const b2h_gemm_t& d, TcGemmPlan* plan) {
   plan->epi = epi_kind(d);
   plan->grid_x = m_tiles;
   plan->grid_y = d.Npad / best_bn;
-  rc = make_map_2d(&plan->tmB, d.W, (int64_t)d.ntaps * d.Kc, d.Npad, (int64_t)d.ntaps * d.Kc, 64, best_bn);
+  rc = make_map_2d(&plan->tmB, d.W, (int64_t)d.ntaps * d.Kc, d.Npad, (int64_t)d.ntaps * d.Kc, bke, best_bn, esz);
   if (rc) return rc;
   plan->fuse_stats = 0;
+  plan->fuse_bwd = 0;
+  if (esz == 4) return B2H_OK;   // fp32 mode: statistics / backward sums are separate passes
   if (d.stats.z) {
     const b2h_bn_stats_t& st = d.stats;
     B2H_CHECK_ARG(st.z == d.out && d.out_coff == 0 && st.ld == d.ldo && st.C == d.Nvalid && st.groups >= 1 &&
@@ -921,25 +912,25 @@ int plan_gemm_bf16(const b2h_gemm_t& d, TcGemmPlan* plan) {
       const int box_l = up2 ? p.tl / 2 : p.tl;
       const int64_t zs_b = (int64_t)bs.Lz * bs.ld;   // sample pitch of z
       if (p.merged && d.nphase == 1) {   // (C, B, L) like the A operand of a merged plan
-        rc = make_map_3d(&plan->tmZ0, z, bs.ld, d.B, bs.Lz, zs_b, bs.ld, best_bn, p.tb, box_l, false);
+        rc = make_map_3d(&plan->tmZ0, z, bs.ld, d.B, bs.Lz, zs_b, bs.ld, best_bn, p.tb, box_l, false, 2);
         plan->tmZ1 = plan->tmZ0;
       } else if (p.merged) {
         const int Le = (bs.Lz + 1) / 2, Lod = bs.Lz / 2;
-        rc = make_map_3d(&plan->tmZ0, z, bs.ld, d.B, Le, zs_b, 2 * (int64_t)bs.ld, best_bn, p.tb, box_l, false);
+        rc = make_map_3d(&plan->tmZ0, z, bs.ld, d.B, Le, zs_b, 2 * (int64_t)bs.ld, best_bn, p.tb, box_l, false, 2);
         if (!rc && Lod > 0)
-          rc = make_map_3d(&plan->tmZ1, z + bs.ld, bs.ld, d.B, Lod, zs_b, 2 * (int64_t)bs.ld, best_bn, p.tb, box_l, false);
+          rc = make_map_3d(&plan->tmZ1, z + bs.ld, bs.ld, d.B, Lod, zs_b, 2 * (int64_t)bs.ld, best_bn, p.tb, box_l, false, 2);
         else
           plan->tmZ1 = plan->tmZ0;
       } else if (d.nphase == 1) {
-        rc = make_map_3d(&plan->tmZ0, z, bs.ld, bs.Lz, d.B, bs.ld, (int64_t)bs.Lz * bs.ld, best_bn, box_l, p.tb, false);
+        rc = make_map_3d(&plan->tmZ0, z, bs.ld, bs.Lz, d.B, bs.ld, (int64_t)bs.Lz * bs.ld, best_bn, box_l, p.tb, false, 2);
         plan->tmZ1 = plan->tmZ0;
       } else {   // output row 2*lo + ph <-> the even / odd rows of z
         const int Le = (bs.Lz + 1) / 2, Lod = bs.Lz / 2;
         rc = make_map_3d(&plan->tmZ0, z, bs.ld, Le, d.B, 2 * (int64_t)bs.ld, (int64_t)bs.Lz * bs.ld, best_bn, box_l, p.tb,
-                         false);
+                         false, 2);
         if (!rc && Lod > 0)
           rc = make_map_3d(&plan->tmZ1, z + bs.ld, bs.ld, Lod, d.B, 2 * (int64_t)bs.ld, (int64_t)bs.Lz * bs.ld, best_bn,
-                           box_l, p.tb, false);
+                           box_l, p.tb, false, 2);
         else   // no odd rows: the odd-phase tiles have no valid row and ignore what they load
           plan->tmZ1 = plan->tmZ0;
       }
@@ -1055,26 +1046,31 @@ int run_gemm_bf16(const TcGemmPlan& plan, const b2h_gemm_t& d, cudaStream_t s) {
   return rc;
 }
 
-int plan_wgrad_bf16(const b2h_wgrad_t& d, TcWgradPlan* plan) {
+int plan_wgrad_bf16(const b2h_wgrad_t& d, TcWgradPlan* plan) { return plan_wgrad_tc(d, plan, 2); }
+
+// esz = 4 (3xTF32): k-blocks of 32 rows (both operands are staged twice: as loaded and as the low-order split)
+int plan_wgrad_tc(const b2h_wgrad_t& d, TcWgradPlan* plan, int esz) {
   TcWgradParams& p = plan->p;
+  plan->esz = esz;
+  const int wk = wgrad_kblock_rows(esz);
   p.Mpad = d.Mpad;
   p.Npad = d.Npad;
   p.ntaps = d.ntaps;
-  p.tl = choose_tl(d.Lp, WG_BK);
-  p.tb = WG_BK / p.tl;
+  p.tl = choose_tl(d.Lp, wk);
+  p.tb = wk / p.tl;
   p.n_lchunks = ceil_div(d.Lp, p.tl);
   p.total_kb = ceil_div(d.B, p.tb) * p.n_lchunks;
-  int rc = make_map_3d(&plan->tmP, d.P, d.Mpad, d.Lp, d.B, d.ldp, (int64_t)d.Lp * d.ldp, 64, p.tl, p.tb);
+  int rc = make_map_3d(&plan->tmP, d.P, d.Mpad, d.Lp, d.B, d.ldp, (int64_t)d.Lp * d.ldp, 128 / esz, p.tl, p.tb, true, esz);
   if (rc) return rc;
   bool has1 = false;
-  rc = make_row_views(&plan->tmQ0, &plan->tmQ1, &has1, d.Q, d.Npad, d.Lq, d.B, d.ldq, d.stride, p.tl, p.tb);
+  rc = make_row_views(&plan->tmQ0, &plan->tmQ1, &has1, d.Q, d.Npad, d.Lq, d.B, d.ldq, d.stride, p.tl, p.tb, esz);
   if (rc) return rc;
   for (int t = 0; t < d.ntaps; ++t) {
     tap_view(d.stride, d.tap_off[t], &p.tap_map[t], &p.tap_coord[t]);
     if (p.tap_map[t] == 1 && !has1) p.tap_map[t] = -1;  // empty odd-row view: the tap's gradient is zero
   }
   int wn = 64;
-  if (d.Npad % 256 == 0)
+  if (d.Npad % 256 == 0 && esz == 2)
     wn = 256;
   else if (d.Npad % 128 == 0)
     wn = 128;
@@ -1084,7 +1080,7 @@ int plan_wgrad_bf16(const b2h_wgrad_t& d, TcWgradPlan* plan) {
   while (wn > 64 && (int64_t)ceil_div(d.Mpad, WG_BM) * (d.Npad / wn) * d.ntaps * std::max(1, p.total_kb / 8) < sms) wn >>= 1;
   if (const char* e = getenv("B2H_FORCE_WN")) {   // tests: run a given tile width at any problem size
     const int f = atoi(e);
-    if ((f == 64 || f == 128 || f == 256) && d.Npad % f == 0) wn = f;
+    if ((f == 64 || f == 128 || (f == 256 && esz == 2)) && d.Npad % f == 0) wn = f;
   }
   plan->WN = wn;
   int64_t tiles = (int64_t)ceil_div(d.Mpad, WG_BM) * (d.Npad / wn) * d.ntaps;
@@ -1095,7 +1091,7 @@ int plan_wgrad_bf16(const b2h_wgrad_t& d, TcWgradPlan* plan) {
   if (const char* e = getenv("B2H_WGRAD_CTAS")) target = std::min(sms, std::max(1, atoi(e)));
   // WN = 256 runs one CTA per SM: a grid of target+1 CTAs would take two waves, so round the split count down
   int splits = d.splits > 0 ? d.splits
-               : (int)std::max<int64_t>(1, wn == 256 ? target / tiles : (target + tiles - 1) / tiles);
+               : (int)std::max<int64_t>(1, (wn == 256 || esz == 4) ? target / tiles : (target + tiles - 1) / tiles);
   if (splits > p.total_kb) splits = p.total_kb;
   if (splits > 64) splits = 64;
   p.kb_per_split = ceil_div(p.total_kb, splits);
@@ -1139,10 +1135,13 @@ int run_wgrad_bf16(const TcWgradPlan& plan, const b2h_wgrad_t& d, cudaStream_t s
   return launch_wgrad_reduce(d, plan.splits, s);
 }
 
-int64_t wgrad_bf16_workspace_bytes(const b2h_wgrad_t& d) {
+int64_t wgrad_bf16_workspace_bytes(const b2h_wgrad_t& d) { return wgrad_tc_workspace_bytes(d, 2); }
+
+int64_t wgrad_tc_workspace_bytes(const b2h_wgrad_t& d, int esz) {
   // upper bound independent of the plan: splits <= 64 but never more than total k-blocks
-  int tl = choose_tl(d.Lp, WG_BK);
-  int total_kb = ceil_div(d.B, WG_BK / tl) * ceil_div(d.Lp, tl);
+  const int wk = wgrad_kblock_rows(esz);
+  int tl = choose_tl(d.Lp, wk);
+  int total_kb = ceil_div(d.B, wk / tl) * ceil_div(d.Lp, tl);
   int sms = sm_count();
   int64_t tiles_min = (int64_t)ceil_div(d.Mpad, WG_BM) * std::max(1, d.Npad / 256) * d.ntaps;
   int64_t splits = d.splits > 0 ? d.splits : std::max<int64_t>(1, (sms + tiles_min - 1) / tiles_min);

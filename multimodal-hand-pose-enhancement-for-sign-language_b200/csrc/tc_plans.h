@@ -26,6 +26,7 @@ struct alignas(64) TcGemmPlan {
   TcGemmParams p;
   int BN, grid_x, grid_y;
   int epi;         // specialised epilogue id (EPI_*)
+  int esz;         // operand element size: 2 = bf16 (kind::f16), 4 = fp32 (3xTF32)
   int fuse_stats;  // BatchNorm statistics of the output produced by the epilogue
   int fuse_bwd;    // first pass of the producer's BatchNorm backward produced by the epilogue
   const float* bs_mean;
@@ -47,8 +48,19 @@ struct alignas(64) TcWgradPlan {
   CUtensorMap tmP, tmQ0, tmQ1;
   TcWgradParams p;
   int WN, grid_x, splits;
+  int esz;
 };
 
+inline int wgrad_kblock_rows(int esz) { return esz == 4 ? 32 : 64; }
+int make_map_3d(CUtensorMap* m, const void* base, int64_t C, int64_t L, int64_t B, int64_t row_pitch, int64_t sample_pitch,
+                int box_c, int box_l, int box_b, bool swizzle128, int esz);
+int make_map_2d(CUtensorMap* m, const void* base, int64_t K, int64_t N, int64_t row_pitch, int box_k, int box_n, int esz);
+int plan_gemm_tc(const b2h_gemm_t& d, TcGemmPlan* plan, int esz);
+int plan_wgrad_tc(const b2h_wgrad_t& d, TcWgradPlan* plan, int esz);
+int64_t wgrad_tc_workspace_bytes(const b2h_wgrad_t& d, int esz);
+// fp32 mode on the tensor cores (3xTF32, k_gemm_tf32.cu)
+int run_gemm_tf32(const TcGemmPlan& plan, const b2h_gemm_t& d, cudaStream_t s);
+int run_wgrad_tf32(const TcWgradPlan& plan, const b2h_wgrad_t& d, cudaStream_t s);
 int plan_gemm_bf16(const b2h_gemm_t& d, TcGemmPlan* plan);
 int run_gemm_bf16(const TcGemmPlan& plan, const b2h_gemm_t& d, cudaStream_t s);
 int plan_wgrad_bf16(const b2h_wgrad_t& d, TcWgradPlan* plan);

@@ -72,6 +72,11 @@ def synthetic_r6d(n_clips: int, T: int, seed: int = 23456):
     converted to the first two columns of the rotation matrix (np_mat_to_rot6d, conversion_utils.py:26)."""
     rng = np.random.RandomState(seed)
     aa = rng.randn(n_clips, 1, 48, 3) * 0.5 + np.cumsum(rng.randn(n_clips, T, 48, 3) * 0.05, axis=1)
+    # the 42 hand bones follow the 6 arm bones through a fixed smooth map (+ 20 % of their own motion), so that
+    # arm -> hand regression has something to learn (the entry-point tests check that training makes progress)
+    mix = np.random.RandomState(4242).randn(18, 126) / np.sqrt(18.0)
+    arm = aa[:, :, :6].reshape(n_clips, T, 18)
+    aa[:, :, 6:] = 0.2 * aa[:, :, 6:] + np.tanh(arm @ mix).reshape(n_clips, T, 42, 3)
     th = np.linalg.norm(aa, axis=-1, keepdims=True) + 1e-12
     k = aa / th
     K = np.zeros(aa.shape[:-1] + (3, 3))

@@ -22,7 +22,9 @@ def test_train_then_infer(tmp_path, capsys, precision, extra):
     import train_gan
     models = str(tmp_path / "models") + "/"
     common = ["--synthetic", "256", "--frames", "64", "--batch_size", "32", "--model_path", models, "--exp_name", "t1",
-              "--precision", precision, "--epochs_train_disc", "2", "--log_step", "4"] + extra
+              "--precision", precision, "--epochs_train_disc", "2", "--log_step", "4", "--learning_rate", "1e-3"] + extra
+    # (synthetic hands follow the arms, data.synthetic_r6d; the same 3 generator epochs through the CPU oracle take the
+    # validation L1 from 5.98 to 5.13 at this learning rate)
     train_gan.main(train_gan.build_parser().parse_args(common + ["--num_epochs", "4"]))
     out = capsys.readouterr().out
     vals = [float(line.split("Val. Loss:")[1].split(",")[0]) for line in out.splitlines() if "Val. Loss:" in line]

@@ -142,7 +142,8 @@ def test_inference_entry_point_writes_r6d_rotmat_xyz(tmp_path):
     sys.path.insert(0, os.path.dirname(HERE))
     import inference
     args = inference.build_parser().parse_args(
-        ["--synthetic", "8", "--frames", "64", "--batch_size", "4", "--results_dir", str(tmp_path), "--precision", "bf16"])
+        ["--synthetic", "8", "--frames", "64", "--batch_size", "4", "--results_dir", str(tmp_path), "--precision", "bf16",
+         "--random_weights"])
     inference.main(args)
     r6d = np.load(tmp_path / "experiment_r6d.npy")
     mat = np.load(tmp_path / "experiment_rotmat.npy")

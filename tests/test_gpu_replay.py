@@ -188,8 +188,10 @@ def disc_train_replay(Bg, T, groups, dtype):
     st_c = nets.ParamStore(spec_c, "cpu", seed=0)
     st_g = nets.ParamStore(spec_g, "cuda", seed=0)
     st_c.load_state_dict(D.state_dict())
-    pc = nets.NetPlan(spec_c, st_c, Bg * groups, T, dtype, "cpu", train=True, groups=groups, drop_mode="mask")
-    pg = nets.NetPlan(spec_g, st_g, Bg * groups, T, dtype, "cuda", train=True, groups=groups, drop_mode="mask")
+    pc = nets.NetPlan(spec_c, st_c, Bg * groups, T, dtype, "cpu", train=True, groups=groups, drop_mode="mask",
+                      wgrad_direct=True)
+    pg = nets.NetPlan(spec_g, st_g, Bg * groups, T, dtype, "cuda", train=True, groups=groups, drop_mode="mask",
+                      wgrad_direct=True)   # as GanTrainer builds it
     for i in range(groups):
         pc.set_masks(masks[i], group=i)
         pc.motion_src[i].copy_(srcs[i])
