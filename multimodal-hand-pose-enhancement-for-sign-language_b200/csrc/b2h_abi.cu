@@ -4,6 +4,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <new>
 #include <vector>
 
@@ -112,9 +113,11 @@ struct alignas(64) Op {
 static int run_op(const Op& op, int dtype, cudaStream_t s) {
   switch (op.kind) {
     case B2H_OP_GEMM:
-      return dtype == B2H_BF16 ? run_gemm_bf16(op.gplan, op.d.gemm, s) : launch_gemm_f32(op.d.gemm, s);
+      if (dtype == B2H_BF16) return run_gemm_bf16(op.gplan, op.d.gemm, s);
+      return op.gplan.esz == 4 ? run_gemm_tf32(op.gplan, op.d.gemm, s) : launch_gemm_f32(op.d.gemm, s);
     case B2H_OP_WGRAD:
-      return dtype == B2H_BF16 ? run_wgrad_bf16(op.wplan, op.d.wgrad, s) : launch_wgrad_f32(op.d.wgrad, s);
+      if (dtype == B2H_BF16) return run_wgrad_bf16(op.wplan, op.d.wgrad, s);
+      return op.wplan.esz == 4 ? run_wgrad_tf32(op.wplan, op.d.wgrad, s) : launch_wgrad_f32(op.d.wgrad, s);
     case B2H_OP_BN_STATS: return launch_bn_stats(op.d.bn_stats, dtype, s);
     case B2H_OP_BN_APPLY: return launch_bn_apply(op.d.bn_apply, dtype, s);
     case B2H_OP_BN_BWD: return launch_bn_bwd(op.d.bn_bwd, dtype, s);
@@ -136,11 +139,21 @@ static int run_op(const Op& op, int dtype, cudaStream_t s) {
   }
 }
 
-// bf16 GEMM-class ops need their TMA descriptors; fp32 ones only validation at launch
+// fp32 mode runs its contractions on the tensor cores as 3xTF32 (k_gemm_tf32.cu); B2H_FP32_SIMT=1 selects the FFMA
+// kernels of k_gemm_f32.cu instead (same contracts; kept for comparison)
+static bool fp32_on_tensor_cores() {
+  static const bool on = getenv("B2H_FP32_SIMT") == nullptr;
+  return on;
+}
+
+// tensor-core GEMM-class ops need their TMA descriptors; the FFMA ones only validation at launch
 static int prepare_op(Op& op, int dtype) {
-  if (dtype != B2H_BF16) return B2H_OK;
-  if (op.kind == B2H_OP_GEMM) return plan_gemm_bf16(op.d.gemm, &op.gplan);
-  if (op.kind == B2H_OP_WGRAD) return plan_wgrad_bf16(op.d.wgrad, &op.wplan);
+  op.gplan.esz = 0;
+  op.wplan.esz = 0;
+  if (dtype != B2H_BF16 && !fp32_on_tensor_cores()) return B2H_OK;
+  const int esz = dtype == B2H_BF16 ? 2 : 4;
+  if (op.kind == B2H_OP_GEMM) return plan_gemm_tc(op.d.gemm, &op.gplan, esz);
+  if (op.kind == B2H_OP_WGRAD) return plan_wgrad_tc(op.d.wgrad, &op.wplan, esz);
   return B2H_OK;
 }
 
@@ -228,7 +241,9 @@ int b2h_fill(const b2h_fill_t* d, b2h_stream_t s) {
 
 int64_t b2h_wgrad_workspace_bytes(const b2h_wgrad_t* d, int dtype) {
   if (!d) return B2H_ERR_ARG;
-  return dtype == B2H_BF16 ? wgrad_bf16_workspace_bytes(*d) : wgrad_workspace_bytes(*d, dtype);
+  if (dtype == B2H_BF16) return wgrad_bf16_workspace_bytes(*d);
+  // fp32 mode: enough for either implementation (3xTF32 or B2H_FP32_SIMT=1)
+  return std::max(wgrad_tc_workspace_bytes(*d, 4), wgrad_workspace_bytes(*d, dtype));
 }
 int64_t b2h_bn_partial_floats(int rows, int C, int groups) { return bn_partial_floats(rows, C, groups); }
 int64_t b2h_l1_partial_floats(const b2h_l1_t* d) { return d ? l1_partial_floats(*d) : (int64_t)B2H_ERR_ARG; }
@@ -289,7 +304,7 @@ int b2h_program_op_plan(const b2h_program* p, int idx, b2h_op_plan_t* out) {
   const Op& op = p->ops[idx];
   memset(out, 0, sizeof(*out));
   out->kind = op.kind;
-  if (p->dtype == B2H_BF16 && op.kind == B2H_OP_GEMM) {
+  if (op.gplan.esz && op.kind == B2H_OP_GEMM) {
     const TcGemmPlan& g = op.gplan;
     out->tensor_core = 1;
     out->tile_n = g.BN;
@@ -298,7 +313,7 @@ int b2h_program_op_plan(const b2h_program* p, int idx, b2h_op_plan_t* out) {
     out->fuse_bwd = g.fuse_bwd;
     out->epilogue = g.epi;
     out->grid[0] = g.grid_x, out->grid[1] = g.grid_y, out->grid[2] = 1;
-  } else if (p->dtype == B2H_BF16 && op.kind == B2H_OP_WGRAD) {
+  } else if (op.wplan.esz && op.kind == B2H_OP_WGRAD) {
     const TcWgradPlan& w = op.wplan;
     out->tensor_core = 1;
     out->tile_n = w.WN;

@@ -80,6 +80,10 @@ __device__ __forceinline__ void multimem_st_f4(float* p, const float4& v) {
 
 }  // namespace
 
+// W = compile-time bound of the world size (2, 4, 8), U = elements (float4) per thread and iteration: small worlds
+// have few peer loads per element, so several elements are fetched before the first add to keep the NVLink latency
+// covered (W * U = 8 sixteen-byte loads in flight per thread in every configuration)
+template <int W, int U>
 __global__ void __launch_bounds__(512) dp_adam_kernel(b2h_dp_adam_t d) {
   pdl_sync();
   const uint64_t timeout_ns = (uint64_t)(d.timeout_ms > 0 ? d.timeout_ms : 10000) * 1000000ull;
@@ -95,43 +99,59 @@ __global__ void __launch_bounds__(512) dp_adam_kernel(b2h_dp_adam_t d) {
   const int64_t hi = lo + chunk < n4 ? lo + chunk : n4;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   float* p_own = d.p[d.rank];
-  for (int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += stride) {
-    float4 g;
+  for (int64_t i0 = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < hi; i0 += stride * U) {
+    float4 g[U];
     if (d.g_mc) {
-      g = multimem_ld_reduce_f4(d.g_mc + i * 4);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t i = i0 + u * stride;
+        if (i < hi) g[u] = multimem_ld_reduce_f4(d.g_mc + i * 4);
+      }
     } else {
-      float4 part[B2H_DP_MAX_PEERS];
+      float4 part[U][W];
 #pragma unroll
-      for (int q = 0; q < B2H_DP_MAX_PEERS; ++q)      // all loads in flight before the first add
-        if (q < d.world) part[q] = ld_sys_f4(d.g[q] + i * 4);
-      g = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int u = 0; u < U; ++u) {
+        const int64_t i = i0 + u * stride;
 #pragma unroll
-      for (int q = 0; q < B2H_DP_MAX_PEERS; ++q)      // rank order: the same sum whoever owns the slice
-        if (q < d.world) {
-          g.x += part[q].x, g.y += part[q].y, g.z += part[q].z, g.w += part[q].w;
-        }
+        for (int q = 0; q < W; ++q)      // all loads in flight before the first add
+          if (q < d.world && i < hi) part[u][q] = ld_sys_f4(d.g[q] + i * 4);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        g[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int q = 0; q < W; ++q)      // rank order: the same sum whoever owns the slice
+          if (q < d.world) {
+            g[u].x += part[u][q].x, g[u].y += part[u][q].y, g[u].z += part[u][q].z, g[u].w += part[u][q].w;
+          }
+      }
     }
-    float4 p = reinterpret_cast<const float4*>(p_own)[i];
-    float4 m = reinterpret_cast<float4*>(d.m)[i];
-    float4 v = reinterpret_cast<float4*>(d.v)[i];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {                     // the arithmetic of adam_kernel (k_misc.cu), same order
-      float gk = f4(g, k) * gs;
-      float mk = f4(m, k) + w1 * (gk - f4(m, k));
-      float vk = f4(v, k) * b2 + (w2 * gk) * gk;
-      float denom = sqrtf(vk) / bc2_sqrt + eps;
-      f4(p, k) += (neg_step * mk) / denom;
-      f4(m, k) = mk;
-      f4(v, k) = vk;
-    }
-    reinterpret_cast<float4*>(d.m)[i] = m;
-    reinterpret_cast<float4*>(d.v)[i] = v;
-    if (d.p_mc) {
-      multimem_st_f4(d.p_mc + i * 4, p);
-    } else {
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i >= hi) break;
+      float4 p = reinterpret_cast<const float4*>(p_own)[i];
+      float4 m = reinterpret_cast<float4*>(d.m)[i];
+      float4 v = reinterpret_cast<float4*>(d.v)[i];
 #pragma unroll
-      for (int q = 0; q < B2H_DP_MAX_PEERS; ++q)
-        if (q < d.world) st_sys_f4(d.p[q] + i * 4, p);
+      for (int k = 0; k < 4; ++k) {                     // the arithmetic of adam_kernel (k_misc.cu), same order
+        float gk = f4(g[u], k) * gs;
+        float mk = f4(m, k) + w1 * (gk - f4(m, k));
+        float vk = f4(v, k) * b2 + (w2 * gk) * gk;
+        float denom = sqrtf(vk) / bc2_sqrt + eps;
+        f4(p, k) += (neg_step * mk) / denom;
+        f4(m, k) = mk;
+        f4(v, k) = vk;
+      }
+      reinterpret_cast<float4*>(d.m)[i] = m;
+      reinterpret_cast<float4*>(d.v)[i] = v;
+      if (d.p_mc) {
+        multimem_st_f4(d.p_mc + i * 4, p);
+      } else {
+#pragma unroll
+        for (int q = 0; q < W; ++q)
+          if (q < d.world) st_sys_f4(d.p[q] + i * 4, p);
+      }
     }
   }
   __threadfence_system();
@@ -144,7 +164,6 @@ int dp_adam_blocks(int64_t n, int world) {
 }
 
 int launch_dp_adam(const b2h_dp_adam_t& d, cudaStream_t s) {
-  B2H_CARVE(dp_adam_kernel);
   B2H_CHECK_ARG(d.world >= 1 && d.world <= B2H_DP_MAX_PEERS && d.rank >= 0 && d.rank < d.world, B2H_ERR_ARG,
                 "dp_adam: bad rank / world");
   B2H_CHECK_ARG(d.n > 0 && d.n % 4 == 0, B2H_ERR_SHAPE, "dp_adam: n must be a positive multiple of 4");
@@ -159,7 +178,15 @@ int launch_dp_adam(const b2h_dp_adam_t& d, cudaStream_t s) {
   }
   // few CTAs by design: the kernel spins on its peers, and two of them (generator / discriminator) may be
   // resident at once — together they must never be able to fill the GPU
-  launch(dp_adam_kernel, dp_adam_blocks(d.n, d.world), 512, 0, s, d);
+  const int blocks = dp_adam_blocks(d.n, d.world);
+  if (d.world <= 2)
+    launch(dp_adam_kernel<2, 4>, blocks, 512, 0, s, d);
+  else if (d.world <= 4)
+    launch(dp_adam_kernel<4, 2>, blocks, 512, 0, s, d);
+  else if (d.world <= 8)
+    launch(dp_adam_kernel<8, 1>, blocks, 512, 0, s, d);
+  else
+    launch(dp_adam_kernel<B2H_DP_MAX_PEERS, 1>, blocks, 512, 0, s, d);
   B2H_LAUNCH_CHECK("dp_adam");
   return B2H_OK;
 }

@@ -301,6 +301,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const uint64_t drop_row_base = (uint64_t)grow * (uint64_t)e.drop_C;
       const bool row_in = (b < p.B) && (lo < p.Lo) && (lo * e.nphase + ph < e.Lo_actual);
       const uint8_t* mask_row = (KIND == EPI_MASK && row_in) ? e.drop.mask + drop_row_base : nullptr;
+      if (KIND == EPI_GENERIC && !row_in) drop.mode = B2H_DROP_NONE;   // never index the mask with a row outside the tensor
       uint8_t* my = stage + (size_t)lane * pitch;
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
@@ -682,7 +683,7 @@ static EncodeTiledFn get_encode_fn() {
 // tensor map over a (C, L, B) view of a bf16 (esz = 2) or fp32 (esz = 4) tensor: element (c, l, b) at
 // base + (b*sample_pitch + l*row_pitch + c) * esz bytes
 int make_map_3d(CUtensorMap* m, const void* base, int64_t C, int64_t L, int64_t B, int64_t row_pitch,
-                int64_t sample_pitch, int box_c, int box_l, int box_b, bool swizzle128, int esz) {
+                int64_t sample_pitch, int box_c, int box_l, int box_b, int swizzle, int esz) {
   EncodeTiledFn fn = get_encode_fn();
   B2H_CHECK_ARG(fn != nullptr, B2H_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
   cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)L, (cuuint64_t)B};
@@ -693,7 +694,8 @@ int make_map_3d(CUtensorMap* m, const void* base, int64_t C, int64_t L, int64_t 
                 "tensor map: base/strides must be 16-byte aligned");
   CUresult r = fn(m, esz == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  swizzle == 2 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                               : (swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE),
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   B2H_CHECK_ARG(r == CUDA_SUCCESS, B2H_ERR_CUDA, "cuTensorMapEncodeTiled(3d) failed: %d (C=%lld L=%lld B=%lld)", (int)r,
                 (long long)C, (long long)L, (long long)B);
@@ -744,22 +746,22 @@ static void tap_view(int stride, int off, int* map, int* coord) {
 // strided views of a [B][L][ld] tensor: view 0 = rows 0,2,4.. (or all rows if stride 1), view 1 = rows 1,3,5..
 // (boxes of 128 bytes of channels: 64 bf16 / 32 fp32)
 static int make_row_views(CUtensorMap* m0, CUtensorMap* m1, bool* has1, const void* base, int C, int L, int B, int ld,
-                          int stride, int box_l, int box_b, int esz) {
+                          int stride, int box_l, int box_b, int esz, int swz = 1) {
   const uint8_t* p = reinterpret_cast<const uint8_t*>(base);
   const int box_c = 128 / esz;
   int rc;
   if (stride == 1) {
-    rc = make_map_3d(m0, p, C, L, B, ld, (int64_t)L * ld, box_c, box_l, box_b, true, esz);
+    rc = make_map_3d(m0, p, C, L, B, ld, (int64_t)L * ld, box_c, box_l, box_b, swz, esz);
     if (rc) return rc;
     *m1 = *m0;
     *has1 = false;
     return B2H_OK;
   }
   int Le = (L + 1) / 2, Lod = L / 2;
-  rc = make_map_3d(m0, p, C, Le, B, 2 * (int64_t)ld, (int64_t)L * ld, box_c, box_l, box_b, true, esz);
+  rc = make_map_3d(m0, p, C, Le, B, 2 * (int64_t)ld, (int64_t)L * ld, box_c, box_l, box_b, swz, esz);
   if (rc) return rc;
   if (Lod > 0) {
-    rc = make_map_3d(m1, p + (size_t)ld * esz, C, Lod, B, 2 * (int64_t)ld, (int64_t)L * ld, box_c, box_l, box_b, true, esz);
+    rc = make_map_3d(m1, p + (size_t)ld * esz, C, Lod, B, 2 * (int64_t)ld, (int64_t)L * ld, box_c, box_l, box_b, swz, esz);
     if (rc) return rc;
     *has1 = true;
   } else {
@@ -1060,10 +1062,12 @@ int plan_wgrad_tc(const b2h_wgrad_t& d, TcWgradPlan* plan, int esz) {
   p.tb = wk / p.tl;
   p.n_lchunks = ceil_div(d.Lp, p.tl);
   p.total_kb = ceil_div(d.B, p.tb) * p.n_lchunks;
-  int rc = make_map_3d(&plan->tmP, d.P, d.Mpad, d.Lp, d.B, d.ldp, (int64_t)d.Lp * d.ldp, 128 / esz, p.tl, p.tb, true, esz);
+  // MN-major fp32 operands: the 128-byte swizzle over 32-byte chunks (smem_desc_sw128_base32)
+  const int swz = esz == 4 ? 2 : 1;
+  int rc = make_map_3d(&plan->tmP, d.P, d.Mpad, d.Lp, d.B, d.ldp, (int64_t)d.Lp * d.ldp, 128 / esz, p.tl, p.tb, swz, esz);
   if (rc) return rc;
   bool has1 = false;
-  rc = make_row_views(&plan->tmQ0, &plan->tmQ1, &has1, d.Q, d.Npad, d.Lq, d.B, d.ldq, d.stride, p.tl, p.tb, esz);
+  rc = make_row_views(&plan->tmQ0, &plan->tmQ1, &has1, d.Q, d.Npad, d.Lq, d.B, d.ldq, d.stride, p.tl, p.tb, esz, swz);
   if (rc) return rc;
   for (int t = 0; t < d.ntaps; ++t) {
     tap_view(d.stride, d.tap_off[t], &p.tap_map[t], &p.tap_coord[t]);
@@ -1092,6 +1096,9 @@ int plan_wgrad_tc(const b2h_wgrad_t& d, TcWgradPlan* plan, int esz) {
   // WN = 256 runs one CTA per SM: a grid of target+1 CTAs would take two waves, so round the split count down
   int splits = d.splits > 0 ? d.splits
                : (int)std::max<int64_t>(1, (wn == 256 || esz == 4) ? target / tiles : (target + tiles - 1) / tiles);
+  // 3xTF32: the tensor core adds into its fp32 accumulator with truncation, a relative loss of ~2^-24 per add that
+  // grows with the length of the k range: bound the k-blocks of one split (the partial planes are summed in fp32 RN)
+  if (esz == 4) splits = std::max(splits, ceil_div(p.total_kb, kTf32MaxKbPerSplit));
   if (splits > p.total_kb) splits = p.total_kb;
   if (splits > 64) splits = 64;
   p.kb_per_split = ceil_div(p.total_kb, splits);
@@ -1145,6 +1152,7 @@ int64_t wgrad_tc_workspace_bytes(const b2h_wgrad_t& d, int esz) {
   int sms = sm_count();
   int64_t tiles_min = (int64_t)ceil_div(d.Mpad, WG_BM) * std::max(1, d.Npad / 256) * d.ntaps;
   int64_t splits = d.splits > 0 ? d.splits : std::max<int64_t>(1, (sms + tiles_min - 1) / tiles_min);
+  if (esz == 4) splits = std::max<int64_t>(splits, ceil_div(total_kb, kTf32MaxKbPerSplit));
   splits = std::min<int64_t>(std::min<int64_t>(splits, total_kb), 64);
   return (splits + 1) * (int64_t)d.ntaps * d.Mpad * d.Npad * (int64_t)sizeof(float);
 }

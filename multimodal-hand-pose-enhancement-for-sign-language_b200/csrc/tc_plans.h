@@ -52,8 +52,9 @@ struct alignas(64) TcWgradPlan {
 };
 
 inline int wgrad_kblock_rows(int esz) { return esz == 4 ? 32 : 64; }
+constexpr int kTf32MaxKbPerSplit = 24;   // 3xTF32 wgrad: at most 24 k-blocks (768 rows) per split-K slice
 int make_map_3d(CUtensorMap* m, const void* base, int64_t C, int64_t L, int64_t B, int64_t row_pitch, int64_t sample_pitch,
-                int box_c, int box_l, int box_b, bool swizzle128, int esz);
+                int box_c, int box_l, int box_b, int swizzle /* 0 none, 1 = 128B, 2 = 128B over 32-byte chunks */, int esz);
 int make_map_2d(CUtensorMap* m, const void* base, int64_t K, int64_t N, int64_t row_pitch, int box_k, int box_n, int esz);
 int plan_gemm_tc(const b2h_gemm_t& d, TcGemmPlan* plan, int esz);
 int plan_wgrad_tc(const b2h_wgrad_t& d, TcWgradPlan* plan, int esz);
