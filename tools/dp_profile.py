@@ -30,8 +30,9 @@ def main():
         pg = dist.group.WORLD
     B, T, steps = int(os.environ.get("B", 256)), int(os.environ.get("T", 64)), int(os.environ.get("STEPS", 20))
     variant, feats = os.environ.get("VARIANT", "v1"), os.environ.get("FEATS", "0") == "1"
+    kw = {"n_buckets": int(os.environ["B2H_BUCKETS"])} if os.environ.get("B2H_BUCKETS") else {}
     tr = GanTrainer(variant, 36, 252, feats, B, T, precision=os.environ.get("PRECISION", "bf16"), device=dev, lr=1e-4,
-                    seed=23456 + rank, drop_mode="philox", world_size=world, process_group=pg)
+                    seed=23456 + rank, drop_mode="philox", world_size=world, process_group=pg, **kw)
     if world > 1:
         for st in (tr.g_store, tr.d_store):
             dist.broadcast(st.flat, 0)
@@ -70,7 +71,7 @@ def main():
             t1 = e if t1 is None else max(t1, e)
         span = (t1 - t0) / steps if t0 is not None else float("nan")
         print(f"world {world}, {variant} feats={feats} {B}x{T}, {steps} gan_steps under torch.profiler (CUPTI): "
-              f"{span:.1f} us per step wall span on rank 0; exchange = {'fused dp_adam' if tr.fused_dp else 'NCCL'}")
+              f"{span:.1f} us per step wall span on rank 0; exchange = {'fused dp_adam' if tr.fused_dp else 'NCCL'}, {tr.n_buckets} bucket(s) per network")
         print(f"{'kernel':60s} {'launches/step':>14s} {'us/step':>10s} {'us/launch':>10s}")
         for name, (n, us) in sorted(rows.items(), key=lambda kv: -kv[1][1])[:25]:
             print(f"{name[:60]:60s} {n / steps:14.1f} {us / steps:10.1f} {us / n:10.2f}")
