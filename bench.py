@@ -367,6 +367,17 @@ def interval_ms(fn_step, steps, world):
     return e0.elapsed_time(e1)
 
 
+def check_ranks_in_sync(tr, world):
+    """Data-parallel sanity: identical initial weights + summed gradients -> identical weights on every rank."""
+    import torch.distributed as dist
+    chk = torch.stack([tr.g_store.flat.double().sum(), tr.g_store.flat.double().abs().sum(),
+                       tr.d_store.flat.double().sum(), tr.d_store.flat.double().abs().sum()])
+    hi, lo = chk.clone(), chk.clone()
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    return bool(((hi - lo).abs() <= 1e-9 * hi.abs()).all()) and bool(torch.isfinite(chk).all())
+
+
 def max_over_ranks(v, dev, world):
     if world <= 1:
         return float(v)
@@ -503,7 +514,11 @@ def main():
         x, y, f = synth_batch(B, T, cin, cout, feats_kind, seed=99 + rank)
         hx, hy = x.pin_memory(), y.pin_memory()
         hf = f.pin_memory() if f is not None else None
-        h_loss = torch.empty(8, dtype=torch.float32).pin_memory()
+        # the losses of every step are read back into a ring of two pinned buffers; the host waits for the read of
+        # step k-1 while step k is already enqueued (a training loop that logs its losses never needs step k's value
+        # before it has launched step k+1), so launch latency and the copy's completion are off the device's chain
+        h_loss = [torch.empty(8, dtype=torch.float32).pin_memory() for _ in range(2)]
+        loss_read = [None, None]
 
         def step():
             if pipelined:
@@ -522,26 +537,26 @@ def main():
             torch.cuda.synchronize()
         t0 = time.perf_counter()
         tr.prefetch_batch(hx, hy, hf)          # batch 0; every later batch is copied while the previous one trains
-        for _ in range(a.steps):
+        loss_sum = 0.0
+        for k in range(a.steps):
             tr.swap_batch(pipelined=pipelined)
             tr.prefetch_batch(hx, hy, hf)      # H2D of the next step's inputs, pinned host -> staging, copy stream
             step()
-            h_loss.copy_(tr.losses, non_blocking=True)
-            torch.cuda.synchronize()
+            h_loss[k & 1].copy_(tr.losses, non_blocking=True)
+            loss_read[k & 1] = torch.cuda.Event()
+            loss_read[k & 1].record()
+            if k > 0:                          # step k-1's losses are on the host now: use them
+                loss_read[(k - 1) & 1].synchronize()
+                loss_sum += float(h_loss[(k - 1) & 1][2])
+        loss_read[(a.steps - 1) & 1].synchronize()
+        loss_sum += float(h_loss[(a.steps - 1) & 1][2])
+        torch.cuda.synchronize()
         e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3, dev, world)
         e2e_value = B * T * world * a.steps / (e2e_ms * 1e-3)
         h2d = (hx.numel() * 4 + hy.numel() * 4 + (hf.numel() * 4 if hf is not None else 0)) * world
         d2h = 32 * world
     clocks = sampler.stop()
-    ranks_in_sync = None
-    if world > 1 and tr is not None:
-        # data-parallel sanity: identical initial weights + summed gradients -> identical weights on every rank
-        chk = torch.stack([tr.g_store.flat.double().sum(), tr.g_store.flat.double().abs().sum(),
-                           tr.d_store.flat.double().sum(), tr.d_store.flat.double().abs().sum()])
-        hi, lo = chk.clone(), chk.clone()
-        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
-        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
-        ranks_in_sync = bool(((hi - lo).abs() <= 1e-9 * hi.abs()).all()) and bool(torch.isfinite(chk).all())
+    ranks_in_sync = check_ranks_in_sync(tr, world) if (world > 1 and tr is not None) else None
     launches = tr.launches_per_gan_step() if tr is not None else res.get("gpu_launches_per_step", 0)
     line = {
         "metric": "training frames/sec" if a.mode == "train" else "inference frames/sec",
@@ -563,7 +578,11 @@ def main():
         "wall_s": t_wall,
     }
     if e2e_value is not None:
-        line["e2e"] = {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
+        line["e2e"] = {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                       "how": "host wall clock over K calls of the public step API; every step: pinned-host inputs -> "
+                              "device (copy stream, under the previous step), step, losses -> pinned host; the host "
+                              "consumes the losses of step k-1 after enqueuing step k (all K read inside the interval)",
+                       "mean_g_loss_read_on_host": loss_sum / a.steps}
     # ---- the other BASELINE configs, short runs, every rank takes part (data parallel where they train)
     if not a.no_extra_configs and a.mode == "train":
         extras = {}

@@ -240,3 +240,20 @@ def test_forced_tile_widths_replay(monkeypatch, bn, wn):
     assert {f"gemm:BN{bn}", f"gemm:BN{bn}:stats", f"gemm:BN{bn}:bwdsum", f"wgrad:WN{wn}"} <= g | t, sorted(g | t)
     assert f"wgrad:WN{wn}:direct" in g and f"wgrad:WN{wn}:splitk" in g, sorted(g)
     assert d
+
+
+def test_fp32_mode_contractions_run_on_the_tensor_cores():
+    """fp32 mode = 3xTF32 on tcgen05 (k_gemm_tf32.cu): every GEMM / weight-gradient op of the benchmarked step carries a
+    tensor-core plan (B2H_FP32_SIMT=1 selects the FFMA kernels instead), weight gradients are split-K slices of at most
+    24 k-blocks (the bound that keeps the accumulator's truncation below the 1e-5 bar)."""
+    from b2h_b200.trainer import GanTrainer
+    tr = GanTrainer("v1", 36, 252, False, 256, 64, precision="fp32", device="cuda", drop_mode="mask")
+    n = 0
+    for plan in (tr.G_train, tr.G_eval, tr.D_train, tr.D_eval):
+        for r in plan.prog.tile_report():
+            if r["kind"] in (L.OP_GEMM, L.OP_WGRAD):
+                assert r["tensor_core"] and r["tile_n"] in (64, 128), r
+                n += 1
+                if r["kind"] == L.OP_WGRAD:
+                    assert r["splits"] >= 1
+    assert n > 60

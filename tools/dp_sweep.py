@@ -44,8 +44,7 @@ def main():
                 continue
             for k in ("B2H_FUSED_DP", "B2H_DP_NO_MULTICAST", "B2H_BUCKETS"):
                 os.environ.pop(k, None)
-            if exch.startswith("fused"):
-                os.environ["B2H_FUSED_DP"] = "1"
+            os.environ["B2H_FUSED_DP"] = "1" if exch.startswith("fused") else "0"
             if exch == "fused-p2p":
                 os.environ["B2H_DP_NO_MULTICAST"] = "1"
             if world > 1 or nb != "1":
@@ -54,7 +53,7 @@ def main():
             try:
                 res, (tr, *_rest) = bench.run_train_config(variant, feats, "bf16", 256, 64, 36, 252, dev, world, rank, pg,
                                                            steps, 5, pipelined=True, keep=True)
-                sync = bench.ranks_in_sync(tr, dev, world) if hasattr(bench, "ranks_in_sync") else None
+                sync = bench.check_ranks_in_sync(tr, world) if world > 1 else None
                 tr.release_graphs()
                 del tr, _rest
                 row = {"case": case, "exchange": exch, "buckets": int(nb), "n_gpus": world,

@@ -32,7 +32,7 @@ def main():
         if m:
             cur = per.setdefault(m.group(1), collections.Counter())
             continue
-        m = re.match(r"\s*/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_]*)((?:\.[A-Z0-9_]+)*)", line)
+        m = re.match(r"\s*/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_]*)((?:\.[A-Z0-9_]+)*)", line)
         if m and cur is not None:
             op, mods = m.group(1), m.group(2)
             cur[op] += 1
