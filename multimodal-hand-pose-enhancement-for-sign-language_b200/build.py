@@ -20,7 +20,7 @@ ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libb2h.so")
 OBJ_DIR = os.path.join(HERE, "build")
 
-SOURCES = ["b2h_abi.cu", "k_norm.cu", "k_misc.cu", "k_dp.cu", "k_gemm_f32.cu", "k_gemm_tf32.cu", "k_gemm_tc.cu"]
+SOURCES = ["b2h_abi.cu", "k_norm.cu", "k_misc.cu", "k_dp.cu", "k_gemm_f32.cu", "k_gemm_tf32.cu", "k_gemm_persist.cu", "k_gemm_tc.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",

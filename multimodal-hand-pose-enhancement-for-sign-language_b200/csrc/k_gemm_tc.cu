@@ -16,6 +16,7 @@
 #include "ptx_sm100.cuh"
 #include "bn_finalize.cuh"
 #include "tc_plans.h"
+#include "gemm_tc_shared.cuh"
 
 namespace b2h {
 
@@ -24,77 +25,6 @@ using namespace ptx;
 // ---------------------------------------------------------------------------------------------
 // device: fprop-like kernel
 // ---------------------------------------------------------------------------------------------
-constexpr int TC_BM = 128;
-constexpr int TC_BK = 64;                       // bf16 elements = 128 bytes = one swizzle row
-constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;   // 16 KB
-
-// BN = 256: one CTA per SM, 4 stages.  BN <= 128: two co-resident CTAs per SM (<= 113 KB each) so that one
-// CTA's epilogue overlaps the other's MMA main loop on the shared tensor core.
-template <int BN>
-struct FpropCfg {
-  static constexpr int B_BYTES = BN * TC_BK * 2;
-  static constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
-  static constexpr int OCC = (BN == 256) ? 1 : 2;
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 3 : 4);
-  // epilogue staging (reuses the pipeline buffers): 128 rows x (BN * 4 bytes + 16)
-  static constexpr int EPI_PITCH_MAX = BN * 4 + 16;
-  static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
-  static constexpr int EPI_BYTES = 128 * EPI_PITCH_MAX;
-  static constexpr int MAIN_BYTES = PIPE_BYTES > EPI_BYTES ? PIPE_BYTES : EPI_BYTES;
-  static constexpr int SMEM_BYTES = MAIN_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 3 * BN * 4 /*bias, pivot | scale, shift*/;
-  // tap-merged main loop: the A ring holds (tl + ntaps - 1) x tb rows of 64 channels once per channel chunk (all
-  // taps read it through shifted descriptors), the B ring one (BN x 64) weight tile per (chunk, tap)
-  static constexpr int SA = 2;
-  static constexpr int A_STAGE = 24 * 1024;
-  static constexpr int SB = (BN == 256) ? 4 : (BN == 128 ? 3 : 4);
-  static_assert(SA * A_STAGE + SB * B_BYTES <= MAIN_BYTES, "merged rings must fit the pipeline buffers");
-};
-
-constexpr int TC_THREADS = 64 + 256;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (2 per TMEM sub-partition)
-
-// specialised epilogues (everything else falls back to EPI_GENERIC)
-enum {
-  EPI_GENERIC = 0, EPI_BIAS_LEAKY = 1, EPI_BIAS_RELU = 2, EPI_BIAS_F32 = 3, EPI_MASK = 4, EPI_PLAIN = 5,
-  EPI_BIAS_LEAKY_BN = 6, EPI_BIAS_RELU_BN = 7   // + eval-mode BatchNorm folded to a per-channel affine
-};
-constexpr bool epi_has_bias(int k) {
-  return k == EPI_BIAS_LEAKY || k == EPI_BIAS_RELU || k == EPI_BIAS_F32 || k == EPI_BIAS_LEAKY_BN || k == EPI_BIAS_RELU_BN;
-}
-constexpr bool epi_has_bn(int k) { return k == EPI_BIAS_LEAKY_BN || k == EPI_BIAS_RELU_BN; }
-
-template <int KIND>
-__device__ __forceinline__ void epi_fast8(const float* s_bias, const float* s_scale, const float* s_shift,
-                                          const uint8_t* mask_row, int col, int nn, const uint32_t* acc_bits, float* v) {
-  float4 b0 = make_float4(0, 0, 0, 0), b1 = b0;
-  if (epi_has_bias(KIND)) {
-    b0 = *reinterpret_cast<const float4*>(s_bias + col);
-    b1 = *reinterpret_cast<const float4*>(s_bias + col + 4);
-  }
-  const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-  float sc[8], sh[8];
-  if (epi_has_bn(KIND)) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) sc[j] = s_scale[col + j], sh[j] = s_shift[col + j];
-  }
-  uint32_t m0 = 0x01010101u, m1 = 0x01010101u;
-  if (KIND == EPI_MASK) {
-    m0 = *reinterpret_cast<const uint32_t*>(mask_row + nn);
-    m1 = *reinterpret_cast<const uint32_t*>(mask_row + nn + 4);
-  }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    float x = __uint_as_float(acc_bits[j]) + bb[j];
-    if (KIND == EPI_BIAS_LEAKY || KIND == EPI_BIAS_LEAKY_BN) x = x > 0.f ? x : x * kLeakySlope;
-    if (KIND == EPI_BIAS_RELU || KIND == EPI_BIAS_RELU_BN) x = x > 0.f ? x : 0.f;
-    if (epi_has_bn(KIND)) x = fmaf(x, sc[j], sh[j]);
-    if (KIND == EPI_MASK) {
-      uint32_t byte = ((j < 4 ? m0 : m1) >> (8 * (j & 3))) & 0xFFu;
-      x = byte ? 2.f * x : 0.f;
-    }
-    v[j] = x;
-  }
-}
-
 // STATS: the epilogue also produces the train-mode BatchNorm statistics of the tile it stores (per-column
 // shifted sums of the bf16-rounded outputs -> fp64 atomics -> the last CTA finalises), see bn_finalize.cuh.
 // BWDSUM (dgrad): the store phase also accumulates the first pass of the producer layer's BatchNorm backward,
@@ -115,7 +45,12 @@ struct BwdSumsDev {
 // tb >= 8 samples, so the A box — tl + ntaps - 1 rows of tb samples, loaded ONCE per 64-channel chunk — serves
 // every tap through a descriptor shifted by tap * tb rows (a multiple of the 8-row swizzle atom): A traffic and
 // TMA issue drop by the tap count.
-template <int BN, int KIND, int MODE, bool MERGED>
+// PAIR (BN = 256 only, opt-in B2H_PAIR=1): CTA pairs (thread-block clusters of two neighbouring M tiles on one TPC) run
+// ONE tcgen05.mma.cta_group::2 of M = 256: each CTA stages its own 128 rows of A and HALF of the B tile (128 of the
+// 256 weight rows), the leader (cluster rank 0) issues the MMAs for both, each CTA's TMEM receives its own 128 x 256
+// accumulator.  The TMA loads of both CTAs count their bytes on the leader's `full` barrier; the leader's
+// tcgen05.commit multicasts to the `empty` / `tmem_full` barriers of both.  See gemm_tc_shared.cuh for what it measured.
+template <int BN, int KIND, int MODE, bool MERGED, bool PAIR = false>
 __global__ void __launch_bounds__(TC_THREADS, FpropCfg<BN>::OCC)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmZ0,
@@ -124,12 +59,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   constexpr bool STATS = MODE == MODE_STATS;
   constexpr bool BWDSUM = MODE == MODE_BWDSUM;
   using Cfg = FpropCfg<BN>;
-  constexpr int STAGES = Cfg::STAGES;
+  // joint (A + B) ring of the plain loop / B ring of the tap-merged loop: depth and strides
+  constexpr int STAGES = PAIR ? Cfg::PAIR_STAGES : Cfg::STAGES;
+  constexpr int STAGE_BYTES = PAIR ? Cfg::PAIR_STAGE_BYTES : Cfg::STAGE_BYTES;
+  constexpr int SB = PAIR ? Cfg::PAIR_SB : Cfg::SB;
+  constexpr int B_STRIDE = PAIR ? Cfg::PAIR_B_BYTES : Cfg::B_BYTES;
+  constexpr int NBAR = STAGES > SB ? STAGES : SB;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::MAIN_BYTES);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint64_t* empty_bar = full_bar + NBAR;
+  uint64_t* tmem_full_bar = empty_bar + NBAR;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
   float* s_bias = reinterpret_cast<float*>(smem + Cfg::MAIN_BYTES + 256);
   float* s_piv = s_bias + BN;     // STATS / BWDSUM: pivot / mean;  *_BN kinds: folded BN scale
@@ -139,6 +79,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   uint64_t* a_full = z_bar + 1;            // MERGED: the A ring (full_bar / empty_bar are the B ring)
   uint64_t* a_empty = a_full + Cfg::SA;
 
+  static_assert(!PAIR || BN == 256, "CTA pairs run the 256-column tile");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mt = blockIdx.x, nt = blockIdx.y;
   const int bt = mt / p.n_lchunks, lc = mt - bt * p.n_lchunks;
@@ -146,12 +87,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const int n0 = nt * BN;
   const int kpt = p.Kc / TC_BK;
   const int nkb = p.ntaps * kpt;
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0u;
+  constexpr int B_LOAD_BYTES = PAIR ? Cfg::B_BYTES / 2 : Cfg::B_BYTES;   // what THIS CTA loads of the B tile
+  const int nB = n0 + (PAIR ? (int)cta_rank * (BN / 2) : 0);
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA0);
     prefetch_tmap(&tmA1);
     prefetch_tmap(&tmB);
-    for (int i = 0; i < STAGES; ++i) {
+    for (int i = 0; i < NBAR; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
@@ -170,11 +115,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_ptr, BN);
-    tmem_relinquish();
+    if (PAIR) {
+      tmem_alloc2(tmem_ptr, BN);
+      tmem_relinquish2();
+    } else {
+      tmem_alloc(tmem_ptr, BN);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR)
+    cluster_sync_all();   // the peer's TMA / commits must find this CTA's barriers initialised
+  else
+    __syncthreads();
   tc_fence_after();
   pdl_sync();  // barriers, TMEM and descriptor prefetch above overlap the previous kernel's tail
   const uint32_t tmem_base = *tmem_ptr;
@@ -186,20 +139,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       for (int kc = 0; kc < kpt; ++kc) {
         const int sa = kc % Cfg::SA;
         mbar_wait(&a_empty[sa], ((kc / Cfg::SA) & 1) ^ 1);
-        mbar_arrive_expect_tx(&a_full[sa], (uint32_t)p.a_box_bytes);
         // tensor map dims (C, B, L): rows land as [row-in-sample][sample], zero outside [0, La)
-        tma_load_3d(smem + sa * Cfg::A_STAGE, &tmA0, &a_full[sa], kc * TC_BK, b0, l0 + p.tap_lo);
+        if (PAIR) {
+          if (leader) mbar_arrive_expect_tx(&a_full[sa], 2u * (uint32_t)p.a_box_bytes);
+          tma_load_3d_pair(smem + sa * Cfg::A_STAGE, &tmA0, &a_full[sa], kc * TC_BK, b0, l0 + p.tap_lo);
+        } else {
+          mbar_arrive_expect_tx(&a_full[sa], (uint32_t)p.a_box_bytes);
+          tma_load_3d(smem + sa * Cfg::A_STAGE, &tmA0, &a_full[sa], kc * TC_BK, b0, l0 + p.tap_lo);
+        }
         for (int t = 0; t < p.ntaps; ++t, ++ib) {
-          const int sb = ib % Cfg::SB;
-          mbar_wait(&empty_bar[sb], ((ib / Cfg::SB) & 1) ^ 1);
-          mbar_arrive_expect_tx(&full_bar[sb], Cfg::B_BYTES);
-          tma_load_2d(ringB + sb * Cfg::B_BYTES, &tmB, &full_bar[sb], p.tap_w[t] * p.Kc + kc * TC_BK, n0);
+          const int sb = ib % SB;
+          mbar_wait(&empty_bar[sb], ((ib / SB) & 1) ^ 1);
+          if (PAIR) {
+            if (leader) mbar_arrive_expect_tx(&full_bar[sb], Cfg::B_BYTES);   // both halves
+            tma_load_2d_pair(ringB + sb * B_STRIDE, &tmB, &full_bar[sb], p.tap_w[t] * p.Kc + kc * TC_BK, nB);
+          } else {
+            mbar_arrive_expect_tx(&full_bar[sb], Cfg::B_BYTES);
+            tma_load_2d(ringB + sb * B_STRIDE, &tmB, &full_bar[sb], p.tap_w[t] * p.Kc + kc * TC_BK, n0);
+          }
         }
       }
     }
   } else if (MERGED && warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = idesc_bf16(TC_BM, BN, 0, 0);
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = idesc_bf16(PAIR ? 2 * TC_BM : TC_BM, BN, 0, 0);
       const uint32_t ringB = smem_u32(smem + Cfg::SA * Cfg::A_STAGE);
       int ib = 0;
       for (int kc = 0; kc < kpt; ++kc) {
@@ -208,20 +171,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         tc_fence_after();
         const uint32_t sA = smem_u32(smem + sa * Cfg::A_STAGE);
         for (int t = 0; t < p.ntaps; ++t, ++ib) {
-          const int sb = ib % Cfg::SB;
-          mbar_wait(&full_bar[sb], (ib / Cfg::SB) & 1);
+          const int sb = ib % SB;
+          mbar_wait(&full_bar[sb], (ib / SB) & 1);
           tc_fence_after();
           // tap t reads the rows [t*tb, t*tb + 128) of the A box: t*tb rows = a whole number of 8-row atoms
           const uint64_t adesc = smem_desc_sw128(sA + (uint32_t)(t * p.tb) * 128u, 16, 1024);
-          const uint64_t bdesc = smem_desc_sw128(ringB + sb * Cfg::B_BYTES, 16, 1024);
+          const uint64_t bdesc = smem_desc_sw128(ringB + sb * B_STRIDE, 16, 1024);
 #pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k)
-            umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kc | t | k) != 0);
-          umma_commit(&empty_bar[sb]);
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            if (PAIR)
+              umma_bf16_pair(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kc | t | k) != 0);
+            else
+              umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kc | t | k) != 0);
+          }
+          if (PAIR) umma_commit_pair(&empty_bar[sb]); else umma_commit(&empty_bar[sb]);
         }
-        umma_commit(&a_empty[sa]);
+        if (PAIR) umma_commit_pair(&a_empty[sa]); else umma_commit(&a_empty[sa]);
       }
-      umma_commit(tmem_full_bar);
+      if (PAIR) umma_commit_pair(tmem_full_bar); else umma_commit(tmem_full_bar);
     }
   } else if (warp == 0) {
     if (lane == 0) {
@@ -229,34 +196,43 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int stage = kb % STAGES;
         const uint32_t phase = (kb / STAGES) & 1;
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
         const int t = kb / kpt, kc = kb - t * kpt;
-        uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
+        uint8_t* sA = smem + stage * STAGE_BYTES;
         uint8_t* sB = sA + TC_A_BYTES;
-        tma_load_3d(sA, p.tap_map[t] ? &tmA1 : &tmA0, &full_bar[stage], kc * TC_BK, l0 + p.tap_coord[t], b0);
-        tma_load_2d(sB, &tmB, &full_bar[stage], p.tap_w[t] * p.Kc + kc * TC_BK, n0);
+        if (PAIR) {
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * TC_A_BYTES + Cfg::B_BYTES);   // A of both, B halves
+          tma_load_3d_pair(sA, p.tap_map[t] ? &tmA1 : &tmA0, &full_bar[stage], kc * TC_BK, l0 + p.tap_coord[t], b0);
+          tma_load_2d_pair(sB, &tmB, &full_bar[stage], p.tap_w[t] * p.Kc + kc * TC_BK, nB);
+        } else {
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          tma_load_3d(sA, p.tap_map[t] ? &tmA1 : &tmA0, &full_bar[stage], kc * TC_BK, l0 + p.tap_coord[t], b0);
+          tma_load_2d(sB, &tmB, &full_bar[stage], p.tap_w[t] * p.Kc + kc * TC_BK, n0);
+        }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = idesc_bf16(TC_BM, BN, 0, 0);
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = idesc_bf16(PAIR ? 2 * TC_BM : TC_BM, BN, 0, 0);
       for (int kb = 0; kb < nkb; ++kb) {
         const int stage = kb % STAGES;
         const uint32_t phase = (kb / STAGES) & 1;
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t sA = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+        const uint32_t sA = smem_u32(smem + stage * STAGE_BYTES);
         const uint32_t sB = sA + TC_A_BYTES;
         const uint64_t adesc = smem_desc_sw128(sA, 16, 1024);
         const uint64_t bdesc = smem_desc_sw128(sB, 16, 1024);
 #pragma unroll
         for (int k = 0; k < TC_BK / 16; ++k) {
           // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in the >>4 address field
-          umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          if (PAIR)
+            umma_bf16_pair(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          else
+            umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
         }
-        umma_commit(&empty_bar[stage]);
+        if (PAIR) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
       }
-      umma_commit(tmem_full_bar);
+      if (PAIR) umma_commit_pair(tmem_full_bar); else umma_commit(tmem_full_bar);
     }
   } else {
     // epilogue warps 2..9: TMEM sub-partition = warp % 4 (hardware rule), two warps per sub-partition split
@@ -280,7 +256,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
     }
-    const int grp = (STATS || BWDSUM) ? b0 / (p.B / (STATS ? st.groups : bs.groups)) : 0;
+    // (a pair's padding CTA past the last M tile has no valid row: its sums are zeros, its group index is clamped)
+    const int grp = (STATS || BWDSUM) ? min(b0 / (p.B / (STATS ? st.groups : bs.groups)), (STATS ? st.groups : bs.groups) - 1) : 0;
     if (BWDSUM) {
       for (int i = et; i < BN; i += 256) {
         const bool in = nn0 + i < bs.C;
@@ -481,10 +458,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR)
+    cluster_sync_all();   // the leader's MMAs read the peer's shared memory; both TMEM halves are released together
+  else
+    __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, BN);
+    if (PAIR) tmem_dealloc2(tmem_base, BN); else tmem_dealloc(tmem_base, BN);
   }
 }
 
@@ -773,6 +753,15 @@ static int make_row_views(CUtensorMap* m0, CUtensorMap* m1, bool* has1, const vo
 
 static int epi_kind(const b2h_gemm_t& d);
 
+// B2H_PAIR=0 runs every tile as a single CTA (cta_group::1)
+static bool pair_mode_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("B2H_PAIR");
+    return e ? atoi(e) != 0 : B2H_PAIR_DEFAULT != 0;
+  }();
+  return on;
+}
+
 int plan_gemm_bf16(const b2h_gemm_t& d, TcGemmPlan* plan) { return plan_gemm_tc(d, plan, 2); }
 
 // esz = 2: bf16 operands (kind::f16);  esz = 4: fp32 operands, 3xTF32 (k_gemm_tf32.cu).  A k-block is 128 bytes of
@@ -877,9 +866,18 @@ int plan_gemm_tc(const b2h_gemm_t& d, TcGemmPlan* plan, int esz) {
             d.B, d.Lo, d.Kc, d.Npad, d.ntaps, d.stride, d.nphase, p.merged, p.tl, p.tb, best_bn, m_tiles, d.Npad / best_bn);
   plan->BN = best_bn;
   plan->epi = epi_kind(d);
-  plan->grid_x = m_tiles;
+  // CTA pairs (cta_group::2) for the 256-column bf16 tile: two neighbouring M tiles share one MMA of M = 256, each
+  // CTA stages half of the B tile.  An odd tile count is padded with a CTA whose rows are all outside the tensor.
+  plan->pair = (esz == 2 && best_bn == 256 && m_tiles >= 2 && pair_mode_enabled()) ? 1 : 0;
+  plan->grid_x = plan->pair ? (m_tiles + 1) / 2 * 2 : m_tiles;
   plan->grid_y = d.Npad / best_bn;
-  rc = make_map_2d(&plan->tmB, d.W, (int64_t)d.ntaps * d.Kc, d.Npad, (int64_t)d.ntaps * d.Kc, bke, best_bn, esz);
+  // launches of more than one wave of 256-column tiles with a plain epilogue (batched inference): persistent CTAs
+  // with a double-buffered accumulator, so launch / pipeline fill / epilogue of a tile overlap the next tile's MMAs
+  plan->persist = (esz == 2 && best_bn == 256 && !plan->pair && !d.stats.z && !d.bwd_sums.z &&
+                   (int64_t)plan->grid_x * plan->grid_y > sms && persist_supports_epilogue(plan->epi) &&
+                   !getenv("B2H_NO_PERSIST")) ? 1 : 0;
+  rc = make_map_2d(&plan->tmB, d.W, (int64_t)d.ntaps * d.Kc, d.Npad, (int64_t)d.ntaps * d.Kc, bke,
+                   plan->pair ? best_bn / 2 : best_bn, esz);
   if (rc) return rc;
   plan->fuse_stats = 0;
   plan->fuse_bwd = 0;
@@ -987,6 +985,12 @@ static int launch_fprop_m(const TcGemmPlan& plan, const EpiParams& e, cudaStream
     cudaError_t er = cudaFuncSetAttribute(gemm_tc_kernel<BN, KIND, MODE, MERGED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           Cfg::SMEM_BYTES);
     if (er != cudaSuccess) return cuda_fail(er, "gemm_tc smem attribute");
+    if (BN == 256) {
+      B2H_CARVE(gemm_tc_kernel<256, KIND, MODE, MERGED, true>);
+      er = cudaFuncSetAttribute(gemm_tc_kernel<256, KIND, MODE, MERGED, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                FpropCfg<256>::SMEM_BYTES);
+      if (er != cudaSuccess) return cuda_fail(er, "gemm_tc (pair) smem attribute");
+    }
     attr_set = true;
   }
   dim3 grid(plan.grid_x, plan.grid_y);
@@ -1003,8 +1007,12 @@ static int launch_fprop_m(const TcGemmPlan& plan, const EpiParams& e, cudaStream
     bs.zbytes = plan.bs_zbytes;
   }
   const bool z = MODE == MODE_BWDSUM;
-  launch(gemm_tc_kernel<BN, KIND, MODE, MERGED>, grid, TC_THREADS, Cfg::SMEM_BYTES, s, plan.tmA0, plan.tmA1, plan.tmB,
-         z ? plan.tmZ0 : plan.tmA0, z ? plan.tmZ1 : plan.tmA0, plan.p, e, st, bs);
+  if (BN == 256 && plan.pair)
+    launch_cluster(gemm_tc_kernel<256, KIND, MODE, MERGED, true>, grid, TC_THREADS, FpropCfg<256>::SMEM_BYTES, s, 2u,
+                   plan.tmA0, plan.tmA1, plan.tmB, z ? plan.tmZ0 : plan.tmA0, z ? plan.tmZ1 : plan.tmA0, plan.p, e, st, bs);
+  else
+    launch(gemm_tc_kernel<BN, KIND, MODE, MERGED>, grid, TC_THREADS, Cfg::SMEM_BYTES, s, plan.tmA0, plan.tmA1, plan.tmB,
+           z ? plan.tmZ0 : plan.tmA0, z ? plan.tmZ1 : plan.tmA0, plan.p, e, st, bs);
   B2H_LAUNCH_CHECK("gemm_tc");
   return B2H_OK;
 }
@@ -1035,6 +1043,7 @@ static int launch_fprop_kind(const TcGemmPlan& plan, const EpiParams& e, int kin
 int run_gemm_bf16(const TcGemmPlan& plan, const b2h_gemm_t& d, cudaStream_t s) {
   EpiParams e = make_epi(d);
   const int kind = epi_kind(d);
+  if (plan.persist && persist_supports_epilogue(kind)) return run_gemm_persist(plan, d, kind, s);
   int rc;
   switch (plan.BN) {
     case 256: rc = launch_fprop_kind<256>(plan, e, kind, s, d.stats); break;

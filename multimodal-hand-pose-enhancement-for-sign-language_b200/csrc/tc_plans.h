@@ -27,6 +27,8 @@ struct alignas(64) TcGemmPlan {
   int BN, grid_x, grid_y;
   int epi;         // specialised epilogue id (EPI_*)
   int esz;         // operand element size: 2 = bf16 (kind::f16), 4 = fp32 (3xTF32)
+  int pair;        // BN = 256 tiles run as CTA pairs (cta_group::2): tmB boxes are half tiles, grid_x is even
+  int persist;     // several waves of BN = 256 tiles with a plain epilogue: the persistent kernel (k_gemm_persist.cu)
   int fuse_stats;  // BatchNorm statistics of the output produced by the epilogue
   int fuse_bwd;    // first pass of the producer's BatchNorm backward produced by the epilogue
   const float* bs_mean;
@@ -62,6 +64,9 @@ int64_t wgrad_tc_workspace_bytes(const b2h_wgrad_t& d, int esz);
 // fp32 mode on the tensor cores (3xTF32, k_gemm_tf32.cu)
 int run_gemm_tf32(const TcGemmPlan& plan, const b2h_gemm_t& d, cudaStream_t s);
 int run_wgrad_tf32(const TcWgradPlan& plan, const b2h_wgrad_t& d, cudaStream_t s);
+// persistent multi-tile form of the bf16 tap-GEMM (k_gemm_persist.cu)
+bool persist_supports_epilogue(int kind);
+int run_gemm_persist(const TcGemmPlan& plan, const b2h_gemm_t& d, int kind, cudaStream_t s);
 int plan_gemm_bf16(const b2h_gemm_t& d, TcGemmPlan* plan);
 int run_gemm_bf16(const TcGemmPlan& plan, const b2h_gemm_t& d, cudaStream_t s);
 int plan_wgrad_bf16(const b2h_wgrad_t& d, TcWgradPlan* plan);
