@@ -2,6 +2,8 @@
 //   v = acc + bias -> activation -> (eval BN scale/shift) -> (dropout keep*2 of the dgrad site)
 // and the sub-pixel (2-phase) output addressing used by ConvTranspose1d forward / strided dgrad.
 #pragma once
+#include <stdlib.h>
+
 #include "b2h_common.cuh"
 
 namespace b2h {

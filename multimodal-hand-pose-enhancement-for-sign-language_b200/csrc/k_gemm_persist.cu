@@ -9,8 +9,13 @@
 //   * the TMA producer warp runs ahead across tile boundaries (the operand rings never drain),
 //   * the accumulator is double-buffered in TMEM (2 x 256 columns): the MMA warp starts tile i+1 while the eight
 //     epilogue warps drain tile i, handing slots back through tmem_empty barriers,
-//   * the epilogue stores straight from registers (each thread owns one output row: 64 contiguous bytes per 32-column
-//     chunk = two full sectors), so no shared-memory staging competes with the rings.
+//   * the epilogue never waits for global memory: with per-thread st.global the store phase alone took 60 % of such a
+//     launch (skipping the stores: 100.6 -> 39.4 us for the first layer at 4096 x 64, profiles/persist_r02.md) -- the
+//     LSU's store queue back-pressures the epilogue warps, which hold the TMEM slot the MMA warp is waiting for.  The
+//     bf16 tile is written to a 128B-swizzled staging buffer (4 boxes of 128 rows x 64 channels), the TMEM slot is
+//     released at once, and ONE thread issues 4 TMA stores (cp.async.bulk.tensor, UTMASTG) that drain in the
+//     background; rows / channels outside the tensor are clipped by the tensor map.  (fp32 outputs -- the last layer
+//     -- are twice the staging size and keep per-thread stores.)
 // Same tile decomposition, operands, descriptors and epilogue arithmetic as gemm_tc_kernel<256, KIND, MODE_PLAIN, MERGED>:
 // results are bit-identical (tests/test_gpu_replay.py compares both against the restatement).
 #include <stdio.h>
@@ -25,6 +30,20 @@ namespace b2h {
 using namespace ptx;
 
 constexpr int PBN = 256;
+
+// shared memory of the persistent kernel: operand rings (3 joint stages of 48 KB, or the tap-merged A ring 2 x 24 KB +
+// B ring 3 x 32 KB = 144 KB) + the output staging buffer (4 swizzled boxes of 128 rows x 128 bytes = 64 KB)
+struct PersistCfg {
+  static constexpr int STAGES = 3;
+  static constexpr int SB = 3;
+  static constexpr int RING_BYTES = STAGES * FpropCfg<PBN>::STAGE_BYTES;
+  static_assert(FpropCfg<PBN>::SA * FpropCfg<PBN>::A_STAGE + SB * FpropCfg<PBN>::B_BYTES <= RING_BYTES, "merged rings");
+  static constexpr int BOX_BYTES = 128 * 128;
+  static constexpr int STAGING_BYTES = 4 * BOX_BYTES;
+  static constexpr int MAIN_BYTES = RING_BYTES + STAGING_BYTES;
+  static constexpr int SMEM_BYTES = MAIN_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static_assert(RING_BYTES % 1024 == 0 && SMEM_BYTES <= 232448, "shared memory budget");
+};
 
 // epi_fast8 with the bias / folded-BN vectors read straight from global memory (warp-uniform addresses, L1-resident
 // after the first tile): the tiles of a persistent CTA have different column offsets and its warps are not in step
@@ -44,12 +63,17 @@ __device__ __forceinline__ void epi_global8(const EpiParams& e, int nn, const ui
 template <int KIND, bool MERGED>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-                       const __grid_constant__ CUtensorMap tmB, TcGemmParams p, EpiParams e, int m_tiles, int n_tiles) {
+                       const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO0,
+                       const __grid_constant__ CUtensorMap tmO1, TcGemmParams p, EpiParams e, int m_tiles, int n_tiles,
+                       int dbg /* timing experiments only: 1 = no global stores, 2 = no TMEM loads either */) {
   using Cfg = FpropCfg<PBN>;
-  constexpr int STAGES = Cfg::STAGES;
+  using PC = PersistCfg;
+  constexpr int STAGES = PC::STAGES;
+  constexpr bool TMA_OUT = KIND != EPI_BIAS_F32;   // bf16 tiles leave through the staging buffer + TMA stores
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::MAIN_BYTES);
+  uint8_t* staging = smem + PC::RING_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + PC::MAIN_BYTES);
   uint64_t* empty_bar = full_bar + 4;
   uint64_t* a_full = empty_bar + 4;        // MERGED: the A ring (full_bar / empty_bar are the B ring)
   uint64_t* a_empty = a_full + 2;
@@ -66,6 +90,10 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
     prefetch_tmap(&tmA0);
     prefetch_tmap(&tmA1);
     prefetch_tmap(&tmB);
+    if (TMA_OUT) {
+      prefetch_tmap(&tmO0);
+      prefetch_tmap(&tmO1);
+    }
     for (int i = 0; i < 4; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -103,8 +131,8 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
             mbar_arrive_expect_tx(&a_full[sa], (uint32_t)p.a_box_bytes);
             tma_load_3d(smem + sa * Cfg::A_STAGE, &tmA0, &a_full[sa], kc * TC_BK, b0, l0 + p.tap_lo);
             for (int t = 0; t < p.ntaps; ++t, ++ib) {
-              const int sb = ib % Cfg::SB;
-              mbar_wait(&empty_bar[sb], ((ib / Cfg::SB) & 1) ^ 1);
+              const int sb = ib % PC::SB;
+              mbar_wait(&empty_bar[sb], ((ib / PC::SB) & 1) ^ 1);
               mbar_arrive_expect_tx(&full_bar[sb], Cfg::B_BYTES);
               tma_load_2d(ringB + sb * Cfg::B_BYTES, &tmB, &full_bar[sb], p.tap_w[t] * p.Kc + kc * TC_BK, n0);
             }
@@ -139,8 +167,8 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
             tc_fence_after();
             const uint32_t sA = smem_u32(smem + sa * Cfg::A_STAGE);
             for (int t = 0; t < p.ntaps; ++t, ++ib) {
-              const int sb = ib % Cfg::SB;
-              mbar_wait(&full_bar[sb], (ib / Cfg::SB) & 1);
+              const int sb = ib % PC::SB;
+              mbar_wait(&full_bar[sb], (ib / PC::SB) & 1);
               tc_fence_after();
               const uint64_t adesc = smem_desc_sw128(sA + (uint32_t)(t * p.tb) * 128u, 16, 1024);
               const uint64_t bdesc = smem_desc_sw128(ringB + sb * Cfg::B_BYTES, 16, 1024);
@@ -172,8 +200,8 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
     // epilogue warps 2..9: TMEM sub-partition = warp % 4, two warps per sub-partition split the tile columns
     const int sub = warp & 3;
     const int chalf = (warp - 2) >> 2;
-    const int esz = e.out_f32 ? 4 : 2;
-    const int r = sub * 32 + lane;   // tile row == TMEM lane
+    const int et = threadIdx.x - 64;   // 0..255
+    const int r = sub * 32 + lane;     // tile row == TMEM lane
     int it = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
       const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
@@ -187,25 +215,44 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
       const int ris = lo * e.nphase + ph;
       const bool row_in = (b < p.B) && (lo < p.Lo) && (ris < e.Lo_actual);
       const int64_t grow = (int64_t)b * e.Lo_actual + ris;
-      uint8_t* grow_ptr = reinterpret_cast<uint8_t*>(e.out) + ((size_t)grow * e.ldo + e.out_coff + nn0) * esz;
+      float* grow_f32 = reinterpret_cast<float*>(e.out) + (size_t)grow * e.ldo + e.out_coff + nn0;
       const int slot = it & 1;
+      if (TMA_OUT) {
+        // the staging buffer is free once the previous tile's TMA stores have read it
+        if (et == 0) tma_store_wait_read();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
       mbar_wait(&tmem_full[slot], (it >> 1) & 1);
       tc_fence_after();
       constexpr int CH = PBN / 2;  // columns per epilogue warp
 #pragma unroll 1
       for (int c = chalf * CH; c < (chalf + 1) * CH; c += 32) {
         uint32_t acc[32];
+        if (dbg & 2) continue;
         tmem_ld_32x32(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(slot * PBN + c), acc);
         tmem_ld_wait();
-        if (!row_in) continue;
+        if (!TMA_OUT && !row_in) continue;
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
           if (c + j >= valid_cols) break;
           float v[8];
           epi_global8<KIND>(e, nn0 + c + j, acc + j, v);
-          const int nv = min(8, valid_cols - (c + j));
-          if (KIND == EPI_BIAS_F32) {
-            float* dst = reinterpret_cast<float*>(grow_ptr) + c + j;
+          if (TMA_OUT) {
+            // box = 64 channels; 16-byte chunk g of row r sits at chunk g ^ (r & 7) of its 128-byte line (128B swizzle)
+            const int col = c + j;
+            __nv_bfloat162 q0 = __floats2bfloat162_rn(v[0], v[1]), q1 = __floats2bfloat162_rn(v[2], v[3]);
+            __nv_bfloat162 q2 = __floats2bfloat162_rn(v[4], v[5]), q3 = __floats2bfloat162_rn(v[6], v[7]);
+            uint4 u;
+            u.x = *reinterpret_cast<uint32_t*>(&q0);
+            u.y = *reinterpret_cast<uint32_t*>(&q1);
+            u.z = *reinterpret_cast<uint32_t*>(&q2);
+            u.w = *reinterpret_cast<uint32_t*>(&q3);
+            uint8_t* dst = staging + (col >> 6) * PC::BOX_BYTES + r * 128 + ((((col & 63) >> 3) ^ (r & 7)) << 4);
+            *reinterpret_cast<uint4*>(dst) = u;
+          } else {
+            const int nv = min(8, valid_cols - (c + j));
+            if ((dbg & 1) && v[0] != 123456.f) continue;   // (keeps the arithmetic alive)
+            float* dst = grow_f32 + c + j;
             if (nv == 8) {
               reinterpret_cast<float4*>(dst)[0] = make_float4(v[0], v[1], v[2], v[3]);
               reinterpret_cast<float4*>(dst)[1] = make_float4(v[4], v[5], v[6], v[7]);
@@ -214,22 +261,6 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
               for (int k = 0; k < 8; ++k)
                 if (k < nv) dst[k] = v[k];
             }
-          } else {
-            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(grow_ptr) + c + j;
-            if (nv == 8) {
-              __nv_bfloat162 q0 = __floats2bfloat162_rn(v[0], v[1]), q1 = __floats2bfloat162_rn(v[2], v[3]);
-              __nv_bfloat162 q2 = __floats2bfloat162_rn(v[4], v[5]), q3 = __floats2bfloat162_rn(v[6], v[7]);
-              uint4 u;
-              u.x = *reinterpret_cast<uint32_t*>(&q0);
-              u.y = *reinterpret_cast<uint32_t*>(&q1);
-              u.z = *reinterpret_cast<uint32_t*>(&q2);
-              u.w = *reinterpret_cast<uint32_t*>(&q3);
-              *reinterpret_cast<uint4*>(dst) = u;
-            } else {
-#pragma unroll
-              for (int k = 0; k < 8; ++k)
-                if (k < nv) dst[k] = __float2bfloat16_rn(v[k]);
-            }
           }
         }
       }
@@ -237,7 +268,25 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[slot]);
+      if (TMA_OUT) {
+        fence_proxy_async_smem();   // the staged tile: generic-proxy writes -> async-proxy (TMA) reads
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (et == 0 && !(dbg & 1)) {
+          const CUtensorMap* mo = ph ? &tmO1 : &tmO0;
+#pragma unroll
+          for (int bx = 0; bx < 4; ++bx) {
+            if (bx * 64 < valid_cols) {
+              if (MERGED)   // output maps of a merged plan are (C, B, L) like its A operand
+                tma_store_3d(mo, staging + bx * PC::BOX_BYTES, nn0 + bx * 64, b0, l0);
+              else
+                tma_store_3d(mo, staging + bx * PC::BOX_BYTES, nn0 + bx * 64, l0, b0);
+            }
+          }
+          tma_store_commit();
+        }
+      }
     }
+    if (TMA_OUT && et == 0) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -252,8 +301,7 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
 // ---------------------------------------------------------------------------------------------
 template <int KIND, bool MERGED>
 static int launch_persist(const TcGemmPlan& plan, const EpiParams& e, cudaStream_t s) {
-  using Cfg = FpropCfg<PBN>;
-  constexpr int SMEM = Cfg::MAIN_BYTES + 1024 + 256;
+  constexpr int SMEM = PersistCfg::SMEM_BYTES;
   B2H_CARVE(gemm_tc_persist_kernel<KIND, MERGED>);
   static bool attr_set = false;
   if (!attr_set) {
@@ -263,8 +311,9 @@ static int launch_persist(const TcGemmPlan& plan, const EpiParams& e, cudaStream
   }
   const int total = plan.grid_x * plan.grid_y;
   const int ctas = std::min(total, sm_count());
-  launch(gemm_tc_persist_kernel<KIND, MERGED>, dim3(ctas), TC_THREADS, SMEM, s, plan.tmA0, plan.tmA1, plan.tmB, plan.p, e,
-         plan.grid_x, plan.grid_y);
+  static const int dbg = getenv("B2H_PERSIST_DBG") ? atoi(getenv("B2H_PERSIST_DBG")) : 0;
+  launch(gemm_tc_persist_kernel<KIND, MERGED>, dim3(ctas), TC_THREADS, SMEM, s, plan.tmA0, plan.tmA1, plan.tmB, plan.tmO0,
+         plan.tmO1, plan.p, e, plan.grid_x, plan.grid_y, dbg);
   B2H_LAUNCH_CHECK("gemm_tc_persist");
   return B2H_OK;
 }

@@ -876,6 +876,26 @@ int plan_gemm_tc(const b2h_gemm_t& d, TcGemmPlan* plan, int esz) {
   plan->persist = (esz == 2 && best_bn == 256 && !plan->pair && !d.stats.z && !d.bwd_sums.z &&
                    (int64_t)plan->grid_x * plan->grid_y > sms && persist_supports_epilogue(plan->epi) &&
                    !getenv("B2H_NO_PERSIST")) ? 1 : 0;
+  if (plan->persist && !d.out_f32) {
+    // output tensor maps of the TMA-store epilogue: one per sub-pixel phase (rows ph, ph + nphase, ...), boxes of 64
+    // channels x the M tile in the tile's own row order; channels >= Nvalid and rows outside the tensor are clipped
+    const __nv_bfloat16* o = reinterpret_cast<const __nv_bfloat16*>(d.out) + d.out_coff;
+    for (int ph = 0; ph < d.nphase && !rc; ++ph) {
+      CUtensorMap* mo = ph ? &plan->tmO1 : &plan->tmO0;
+      const int rows = std::min(d.Lo, (d.Lo_actual - ph + d.nphase - 1) / d.nphase);
+      if (rows <= 0) {   // a phase without rows (one-row outputs): not a multi-wave shape anyway
+        plan->persist = 0;
+        break;
+      }
+      const int64_t row_pitch = (int64_t)d.nphase * d.ldo, sample_pitch = (int64_t)d.Lo_actual * d.ldo;
+      if (p.merged)
+        rc = make_map_3d(mo, o + (int64_t)ph * d.ldo, d.Nvalid, d.B, rows, sample_pitch, row_pitch, 64, p.tb, p.tl, 1, 2);
+      else
+        rc = make_map_3d(mo, o + (int64_t)ph * d.ldo, d.Nvalid, rows, d.B, row_pitch, sample_pitch, 64, p.tl, p.tb, 1, 2);
+    }
+    if (d.nphase == 1) plan->tmO1 = plan->tmO0;
+    if (rc) return rc;
+  }
   rc = make_map_2d(&plan->tmB, d.W, (int64_t)d.ntaps * d.Kc, d.Npad, (int64_t)d.ntaps * d.Kc, bke,
                    plan->pair ? best_bn / 2 : best_bn, esz);
   if (rc) return rc;

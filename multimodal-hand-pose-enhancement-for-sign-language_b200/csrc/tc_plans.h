@@ -23,6 +23,7 @@ struct TcGemmParams {
 struct alignas(64) TcGemmPlan {
   CUtensorMap tmA0, tmA1, tmB;
   CUtensorMap tmZ0, tmZ1;  // fuse_bwd: the producer layer's z (all rows / even rows, odd rows), not swizzled
+  CUtensorMap tmO0, tmO1;  // persist: the output tensor (phase 0 / phase 1 rows) for the TMA stores of the epilogue
   TcGemmParams p;
   int BN, grid_x, grid_y;
   int epi;         // specialised epilogue id (EPI_*)
