@@ -135,7 +135,10 @@ typedef struct {
   int32_t act;       /* b2h_act, applied after bias                                            */
   const float* post_scale; /* eval-mode BatchNorm folded to y = v*scale + shift after act, or NULL */
   const float* post_shift;
-  int32_t out_f32;
+  int32_t out_f32;   /* 0: `out` is BLC in the activation dtype; 1: BLC fp32; 2 (bf16 mode, output layer of a batched
+                        inference): `out` is the reference's own (B, Nvalid, Lo_actual) fp32 NCL tensor and the op
+                        writes it itself -- needs nphase = 1, stride = 1, bias only (no activation / BN / dropout /
+                        statistics), Npad % 256 == 0, Lo_actual == Lo, Lo % 4 == 0; ldo / out_coff are ignored */
   b2h_dropout_t drop; /* dgrad: multiply by keep*2 of the dropout site that produced A_prev    */
   int32_t drop_C;     /* valid channel count of that site (mask row length)                    */
   b2h_bn_stats_t stats; /* optional (stats.z != NULL, must equal `out`): also compute the train-mode BatchNorm

@@ -111,6 +111,7 @@ static int check_gemm(const b2h_gemm_t& d) {
                 "gemm: lda=%d ldo=%d coff=%d alignment", d.lda, d.ldo, d.out_coff);
   B2H_CHECK_ARG(d.Nvalid > 0 && d.Nvalid <= d.Npad / d.nphase && d.Lo_actual > 0, B2H_ERR_SHAPE, "gemm: Nvalid/Lo_actual");
   B2H_CHECK_ARG(d.stride == 1 || d.stride == 2, B2H_ERR_SHAPE, "gemm: stride must be 1 or 2");
+  B2H_CHECK_ARG(d.out_f32 == 0 || d.out_f32 == 1, B2H_ERR_ARG, "gemm: NCL output (out_f32 = 2) is a bf16-mode feature");
   B2H_CHECK_ARG((d.post_scale == nullptr) == (d.post_shift == nullptr), B2H_ERR_ARG, "gemm: post scale/shift");
   return B2H_OK;
 }

@@ -14,8 +14,13 @@
 //     LSU's store queue back-pressures the epilogue warps, which hold the TMEM slot the MMA warp is waiting for.  The
 //     bf16 tile is written to a 128B-swizzled staging buffer (4 boxes of 128 rows x 64 channels), the TMEM slot is
 //     released at once, and ONE thread issues 4 TMA stores (cp.async.bulk.tensor, UTMASTG) that drain in the
-//     background; rows / channels outside the tensor are clipped by the tensor map.  (fp32 outputs -- the last layer
-//     -- are twice the staging size and keep per-thread stores.)
+//     background; rows / channels outside the tensor are clipped by the tensor map.  (fp32 BLC outputs are twice the
+//     staging size and keep per-thread stores.)
+//   * NCL: the output layer of a batched inference writes the (B, C, T) fp32 result of the network itself
+//     (b2h_gemm_t.out_f32 = 2): a thread owns one frame of one clip, so it writes its 32 channels of a chunk as column
+//     [clip][channel][frame] of the staging buffer (lanes = consecutive frames: conflict-free) and TMA stores of
+//     (tl frames x 32 channels x tb clips) boxes produce the transposed layout, two rounds of 128 channels per tile --
+//     instead of fp32 BLC to HBM, a to_ncl pass reading it back and writing NCL (264 MB each way at 4096 x 64).
 // Same tile decomposition, operands, descriptors and epilogue arithmetic as gemm_tc_kernel<256, KIND, MODE_PLAIN, MERGED>:
 // results are bit-identical (tests/test_gpu_replay.py compares both against the restatement).
 #include <stdio.h>
@@ -60,7 +65,7 @@ __device__ __forceinline__ void epi_global8(const EpiParams& e, int nn, const ui
   }
 }
 
-template <int KIND, bool MERGED>
+template <int KIND, bool MERGED, bool NCL = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                        const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO0,
@@ -70,6 +75,7 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
   using PC = PersistCfg;
   constexpr int STAGES = PC::STAGES;
   constexpr bool TMA_OUT = KIND != EPI_BIAS_F32;   // bf16 tiles leave through the staging buffer + TMA stores
+  static_assert(!NCL || (KIND == EPI_BIAS_F32 && !MERGED), "NCL output: fp32, rows of a warp = consecutive frames");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* staging = smem + PC::RING_BYTES;
@@ -90,7 +96,7 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
     prefetch_tmap(&tmA0);
     prefetch_tmap(&tmA1);
     prefetch_tmap(&tmB);
-    if (TMA_OUT) {
+    if (TMA_OUT || NCL) {
       prefetch_tmap(&tmO0);
       prefetch_tmap(&tmO1);
     }
@@ -217,6 +223,48 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
       const int64_t grow = (int64_t)b * e.Lo_actual + ris;
       float* grow_f32 = reinterpret_cast<float*>(e.out) + (size_t)grow * e.ldo + e.out_coff + nn0;
       const int slot = it & 1;
+      if (NCL) {
+        // two rounds of 128 channels: warp (sub, chalf) drains channels round*128 + chalf*64 + [0, 64) of its 32 rows
+        const int tl = p.tl;
+#pragma unroll 1
+        for (int round = 0; round < 2; ++round) {
+          if (et == 0) tma_store_wait_read();          // the previous round's boxes have left the staging buffer
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (round == 0) {
+            mbar_wait(&tmem_full[slot], (it >> 1) & 1);
+            tc_fence_after();
+          }
+#pragma unroll 1
+          for (int cc = 0; cc < 2; ++cc) {
+            const int box = chalf * 2 + cc;            // 32-channel box of this round
+            const int c = round * 128 + box * 32;
+            uint32_t acc[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(slot * PBN + c), acc);
+            tmem_ld_wait();
+            if (c >= valid_cols) continue;
+            float* col0 = reinterpret_cast<float*>(staging + box * PC::BOX_BYTES) + (size_t)(bi * 32) * tl + li;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)   // [clip][channel][frame]: the lanes of a warp are consecutive frames
+              col0[(size_t)j * tl] = __uint_as_float(acc[j]) + __ldg(e.bias + nn0 + c + j);
+          }
+          if (round == 1) {   // every TMEM read of this tile is done: hand the slot back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[slot]);
+          }
+          fence_proxy_async_smem();
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (et == 0) {
+#pragma unroll
+            for (int bx = 0; bx < 4; ++bx) {
+              const int c = round * 128 + bx * 32;
+              if (c < valid_cols) tma_store_3d(&tmO0, staging + bx * PC::BOX_BYTES, l0, nn0 + c, b0);
+            }
+            tma_store_commit();
+          }
+        }
+        continue;
+      }
       if (TMA_OUT) {
         // the staging buffer is free once the previous tile's TMA stores have read it
         if (et == 0) tma_store_wait_read();
@@ -286,7 +334,7 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
         }
       }
     }
-    if (TMA_OUT && et == 0) tma_store_wait_all();
+    if ((TMA_OUT || NCL) && et == 0) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -299,20 +347,20 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
 // ---------------------------------------------------------------------------------------------
 // host
 // ---------------------------------------------------------------------------------------------
-template <int KIND, bool MERGED>
+template <int KIND, bool MERGED, bool NCL = false>
 static int launch_persist(const TcGemmPlan& plan, const EpiParams& e, cudaStream_t s) {
   constexpr int SMEM = PersistCfg::SMEM_BYTES;
-  B2H_CARVE(gemm_tc_persist_kernel<KIND, MERGED>);
+  B2H_CARVE(gemm_tc_persist_kernel<KIND, MERGED, NCL>);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t er = cudaFuncSetAttribute(gemm_tc_persist_kernel<KIND, MERGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    cudaError_t er = cudaFuncSetAttribute(gemm_tc_persist_kernel<KIND, MERGED, NCL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (er != cudaSuccess) return cuda_fail(er, "gemm_tc_persist smem attribute");
     attr_set = true;
   }
   const int total = plan.grid_x * plan.grid_y;
   const int ctas = std::min(total, sm_count());
   static const int dbg = getenv("B2H_PERSIST_DBG") ? atoi(getenv("B2H_PERSIST_DBG")) : 0;
-  launch(gemm_tc_persist_kernel<KIND, MERGED>, dim3(ctas), TC_THREADS, SMEM, s, plan.tmA0, plan.tmA1, plan.tmB, plan.tmO0,
+  launch(gemm_tc_persist_kernel<KIND, MERGED, NCL>, dim3(ctas), TC_THREADS, SMEM, s, plan.tmA0, plan.tmA1, plan.tmB, plan.tmO0,
          plan.tmO1, plan.p, e, plan.grid_x, plan.grid_y, dbg);
   B2H_LAUNCH_CHECK("gemm_tc_persist");
   return B2H_OK;
@@ -334,7 +382,12 @@ int run_gemm_persist(const TcGemmPlan& plan, const b2h_gemm_t& d, int kind, cuda
   switch (kind) {
     case EPI_BIAS_LEAKY: return launch_persist_m<EPI_BIAS_LEAKY>(plan, e, s);
     case EPI_BIAS_RELU: return launch_persist_m<EPI_BIAS_RELU>(plan, e, s);
-    case EPI_BIAS_F32: return launch_persist_m<EPI_BIAS_F32>(plan, e, s);
+    case EPI_BIAS_F32:
+      if (d.out_f32 == 2) {
+        B2H_CHECK_ARG(!plan.p.merged, B2H_ERR_ARG, "gemm_tc_persist: NCL output needs the plain (unmerged) tile order");
+        return launch_persist<EPI_BIAS_F32, false, true>(plan, e, s);
+      }
+      return launch_persist_m<EPI_BIAS_F32>(plan, e, s);
     case EPI_BIAS_LEAKY_BN: return launch_persist_m<EPI_BIAS_LEAKY_BN>(plan, e, s);
     case EPI_BIAS_RELU_BN: return launch_persist_m<EPI_BIAS_RELU_BN>(plan, e, s);
     case EPI_PLAIN: return launch_persist_m<EPI_PLAIN>(plan, e, s);

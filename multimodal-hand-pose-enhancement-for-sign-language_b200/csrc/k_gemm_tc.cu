@@ -774,10 +774,17 @@ int plan_gemm_tc(const b2h_gemm_t& d, TcGemmPlan* plan, int esz) {
   p.Lo = d.Lo;
   p.Kc = d.Kc;
   p.stride = d.stride;
-  B2H_CHECK_ARG(d.ldo % (16 / esz) == 0 && d.out_coff % (16 / esz) == 0 && ((uintptr_t)d.out % 16) == 0 &&
-                    (d.out_f32 == 0 || d.ldo % 4 == 0),
+  const bool ncl = d.out_f32 == 2;   // the op writes the (B, Nvalid, Lo_actual) fp32 NCL tensor itself
+  B2H_CHECK_ARG(ncl || (d.ldo % (16 / esz) == 0 && d.out_coff % (16 / esz) == 0 && ((uintptr_t)d.out % 16) == 0 &&
+                        (d.out_f32 == 0 || d.ldo % 4 == 0)),
                 B2H_ERR_ALIGN, "gemm_tc: out/ldo/out_coff must allow 16-byte row stores (ldo=%d coff=%d)", d.ldo,
                 d.out_coff);
+  B2H_CHECK_ARG(!ncl || (esz == 2 && d.nphase == 1 && d.stride == 1 && d.out_coff == 0 && d.Npad % 256 == 0 &&
+                         d.Lo_actual % 4 == 0 && d.Lo_actual == d.Lo && ((uintptr_t)d.out % 16) == 0 && d.bias &&
+                         d.act == B2H_ACT_NONE && !d.post_scale && d.drop.mode == B2H_DROP_NONE && !d.stats.z &&
+                         !d.bwd_sums.z),
+                B2H_ERR_ARG, "gemm: NCL output (out_f32 = 2) needs bf16 operands, a stride-1 single-phase op with bias "
+                "only, Npad %% 256 == 0 and Lo %% 4 == 0");
   int rc;
   // tap-merged main loop: stride 1, taps forming a run of consecutive row offsets, and a tile of tl <= 16 rows x
   // tb >= 8 samples whose A box (tl + ntaps - 1 rows) fits the A stage
@@ -785,7 +792,7 @@ int plan_gemm_tc(const b2h_gemm_t& d, TcGemmPlan* plan, int esz) {
   int order[B2H_MAX_TAPS];
   for (int t = 0; t < d.ntaps; ++t) order[t] = t;
   std::sort(order, order + d.ntaps, [&](int a, int b) { return d.tap_off[a] < d.tap_off[b]; });
-  bool run = d.stride == 1 && d.ntaps >= 2 && !getenv("B2H_NO_TAP_MERGE");
+  bool run = d.stride == 1 && d.ntaps >= 2 && !ncl && !getenv("B2H_NO_TAP_MERGE");
   for (int t = 1; t < d.ntaps && run; ++t) run = d.tap_off[order[t]] == d.tap_off[order[t - 1]] + 1;
   if (run) {
     const int h = d.ntaps - 1;
@@ -857,7 +864,8 @@ int plan_gemm_tc(const b2h_gemm_t& d, TcGemmPlan* plan, int esz) {
       best_bn = bn;
     }
   }
-  if (const char* f = getenv("B2H_FORCE_BN")) {  // tuning aid
+  if (ncl) best_bn = 256;
+  if (const char* f = getenv("B2H_FORCE_BN"); f && !ncl) {  // tuning aid
     int bn = atoi(f);
     if ((bn == 64 || bn == 128 || bn == 256) && bn <= bn_max && half % bn == 0) best_bn = bn;
   }
@@ -868,7 +876,7 @@ int plan_gemm_tc(const b2h_gemm_t& d, TcGemmPlan* plan, int esz) {
   plan->epi = epi_kind(d);
   // CTA pairs (cta_group::2) for the 256-column bf16 tile: two neighbouring M tiles share one MMA of M = 256, each
   // CTA stages half of the B tile.  An odd tile count is padded with a CTA whose rows are all outside the tensor.
-  plan->pair = (esz == 2 && best_bn == 256 && m_tiles >= 2 && pair_mode_enabled()) ? 1 : 0;
+  plan->pair = (esz == 2 && best_bn == 256 && m_tiles >= 2 && !ncl && pair_mode_enabled()) ? 1 : 0;
   plan->grid_x = plan->pair ? (m_tiles + 1) / 2 * 2 : m_tiles;
   plan->grid_y = d.Npad / best_bn;
   // launches of more than one wave of 256-column tiles with a plain epilogue (batched inference): persistent CTAs
@@ -876,6 +884,14 @@ int plan_gemm_tc(const b2h_gemm_t& d, TcGemmPlan* plan, int esz) {
   plan->persist = (esz == 2 && best_bn == 256 && !plan->pair && !d.stats.z && !d.bwd_sums.z &&
                    (int64_t)plan->grid_x * plan->grid_y > sms && persist_supports_epilogue(plan->epi) &&
                    !getenv("B2H_NO_PERSIST")) ? 1 : 0;
+  if (ncl) {
+    // NCL output exists only in the persistent kernel: (T, C, B) fp32 map, boxes of tl frames x 32 channels x tb clips
+    plan->persist = 1;
+    rc = make_map_3d(&plan->tmO0, d.out, d.Lo_actual, d.Nvalid, d.B, d.Lo_actual, (int64_t)d.Nvalid * d.Lo_actual, p.tl, 32,
+                     p.tb, 0, 4);
+    if (rc) return rc;
+    plan->tmO1 = plan->tmO0;
+  }
   if (plan->persist && !d.out_f32) {
     // output tensor maps of the TMA-store epilogue: one per sub-pixel phase (rows ph, ph + nphase, ...), boxes of 64
     // channels x the M tile in the tile's own row order; channels >= Nvalid and rows outside the tensor are clipped

@@ -338,6 +338,9 @@ class LayerBufs:
     ain_C: int = 0                # valid channels of `a`
 
 
+NCL_DIRECT_MIN_ROWS = 32768   # frames per eval forward from which the output layer writes NCL itself (see NetPlan)
+
+
 class NetPlan:
     """One network at a fixed batch / length / precision / mode, lowered to a recorded program."""
 
@@ -500,6 +503,13 @@ class NetPlan:
         olb = self.bufs[ol.name]
         self.out_blc = self._zeros(B, olb.Lz, max(olb.Cp, 4), dtype=torch.float32)
         self.out = self._zeros(B, ol.cout, olb.Lz, dtype=torch.float32)   # (B, C_out, T) NCL
+        # batched inference (bf16, >= NCL_DIRECT_MIN_ROWS frames per forward): the output layer's GEMM writes the NCL
+        # fp32 result itself (b2h_gemm_t.out_f32 = 2: persistent kernel, transposing staging buffer, TMA stores) -- no
+        # fp32 BLC round trip through HBM and no to_ncl pass (at 4096 x 64: 264 MB written + read + written again)
+        import os as _os0
+        self.ncl_direct = (not self.train and self.dtype == L.BF16 and spec.input_kind == "x" and ol.kind != "convT" and
+                           ol.stride == 1 and olb.Cp % 256 == 0 and olb.Lz % 4 == 0 and
+                           B * olb.Lz >= NCL_DIRECT_MIN_ROWS and not _os0.environ.get("B2H_NO_NCL_DIRECT"))
 
         with P.segment("pack"):
             self._pack_items: List[dict] = []
@@ -525,7 +535,7 @@ class NetPlan:
             for l in spec.layers:
                 self._emit_input(l)
                 self._emit_fwd_gemm(l)
-            if spec.input_kind == "x":
+            if spec.input_kind == "x" and not self.ncl_direct:
                 P.add(L.OP_TO_NCL, "out", src=self.out_blc, dst=self.out, B=B, L=olb.Lz, C=ol.cout,
                       ld=self.out_blc.shape[-1], src_f32=1)
         if self.train:
@@ -724,10 +734,13 @@ class NetPlan:
         is_out = l is self.out_layer
         out = self.out_blc if is_out else lb.z
         ldo = out.shape[-1]
+        out_f32 = 1 if is_out else 0
+        if is_out and self.ncl_direct:
+            out, out_f32 = self.out, 2     # (B, C_out, T) fp32, written by the GEMM itself
         taps = lb.fwd_taps
         common = dict(A=lb.a, W=lb.wf, bias=lb.bias, out=out, B=B, La=l.La, lda=lb.Kc, ldo=ldo, out_coff=0, Kc=lb.Kc,
                       Nvalid=l.cout, ntaps=len(taps), tap_off=taps + [0] * (L.MAX_TAPS - len(taps)), act=l.act,
-                      post_scale=None, post_shift=None, out_f32=1 if is_out else 0, drop=no_drop(), drop_C=0)
+                      post_scale=None, post_shift=None, out_f32=out_f32, drop=no_drop(), drop_C=0)
         if l.bn and self.train:
             # the GEMM also produces the batch statistics of its output (tensor-core path: in the epilogue)
             common["stats"] = self._bn_stats_desc(l)

@@ -76,9 +76,14 @@ def gemm(f: Dict):
     half = f["Npad"] // nph
     Nv, Lact = f["Nvalid"], f["Lo_actual"]
     out = f["out"]
-    ldo = out.shape[-1]
-    out2 = out.reshape(B, Lact, ldo)
-    assert ldo == f["ldo"]
+    ncl = f["out_f32"] == 2     # the op writes the (B, Nvalid, Lo_actual) fp32 NCL tensor itself (b2h_abi.h)
+    if ncl:
+        assert nph == 1 and f["out_coff"] == 0 and tuple(out.shape) == (B, Nv, Lact)
+        out2 = torch.zeros(B, Lact, Nv)
+    else:
+        ldo = out.shape[-1]
+        out2 = out.reshape(B, Lact, ldo)
+        assert ldo == f["ldo"]
     for ph in range(nph):
         v = acc[:, :, ph * half: ph * half + Nv]
         if f.get("bias") is not None:
@@ -98,6 +103,8 @@ def gemm(f: Dict):
             v = v.clone()
             v[:, :, :nn] = v[:, :, :nn] * m[:, :, :nn]
         out2[:, ra, f["out_coff"]: f["out_coff"] + Nv] = v.to(out.dtype)
+    if ncl:
+        out.copy_(out2.permute(0, 2, 1))
     st = f.get("stats")
     if st and st.get("z") is not None:   # the op also produces the batch statistics of its output
         bn_stats(st)

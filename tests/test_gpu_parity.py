@@ -37,9 +37,12 @@ def make_trainer(variant, rf, B, T, precision, G, D, lr=1e-3, drop_mode="mask", 
 @pytest.mark.parametrize("precision,tol", [("fp32", FP32_TOL), ("bf16", BF16_TOL)])
 @pytest.mark.parametrize("variant,rf,B,T", [("v1", False, 32, 64), ("v1", True, 8, 64), ("b2h", True, 4, 32),
                                             ("v2", True, 4, 64), ("v4", True, 4, 64), ("v4_deeper", True, 4, 64),
-                                            ("v1", False, 3, 192), ("v1", False, 5, 62), ("v1", False, 2, 1024)])
+                                            ("v1", False, 3, 192), ("v1", False, 5, 62), ("v1", False, 2, 1024),
+                                            ("v1", False, 520, 64), ("v2", True, 35, 1000)])
 def test_eval_forward_vs_oracle(variant, rf, B, T, precision, tol):
-    """BASELINE config 1 (B=32, T=64 eval forward) and the inference.py sweep shapes."""
+    """BASELINE config 1 (B=32, T=64 eval forward) and the inference.py sweep shapes.  The last two (>= 32768 frames
+    per forward) run the multi-wave launches of batched inference: in bf16 mode the persistent tap-GEMM with TMA-store
+    epilogues, and the output layer writing the NCL result itself (ragged: 520 = 4 x 128 + 8 clips, T = 1000)."""
     torch.manual_seed(0)
     G = R.build_generator(variant, 36, 252, rf)
     D = R.build_discriminator(252)
