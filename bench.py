@@ -659,7 +659,7 @@ def main():
             line["kernel_breakdown"] = [{k: (round(v, 5) if isinstance(v, float) else v) for k, v in r.items()}
                                         for r in rows[:14]]
             line["gemm_ms_sum"] = sum(r["ms"] for r in rows)
-        if not a.no_cpu_baseline:
+        if not a.no_cpu_baseline and world == 1:   # (N > 1: the other ranks' host threads would share the cores)
             fps, med, cores = run_cpu_reference(a, steps=5, warmup=2)
             line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                                     "sample": f"5 steps (+2 warm-up) of the full {B}x{T} batch through the oracle "
