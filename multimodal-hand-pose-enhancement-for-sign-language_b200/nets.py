@@ -431,9 +431,20 @@ class NetPlan:
 
     def _bn_src(self, l: Layer, rowmap=L.ROW_IDENT, coff=0):
         lb = self.bufs[l.name]
+        scale, shift = lb.scale, lb.shift
+        if l.name in getattr(self, "eval_y", {}):   # lb.z already holds BN(z): the consumers apply the identity
+            scale, shift = self._ident_affine(lb.Cp)
         return {"z": lb.z, "ld": lb.Cp, "coff": coff, "rowmap": rowmap, "L_src": lb.Lz if rowmap != L.ROW_BCAST else 1,
-                "Cs": lb.Cp, "scale": lb.scale, "shift": lb.shift,
+                "Cs": lb.Cp, "scale": scale, "shift": shift,
                 "mean": lb.mean if self.train else None, "invstd": lb.invstd if self.train else None}
+
+    def _ident_affine(self, C: int):
+        """(ones, zeros) per-channel arrays [1][C] for sources that are stored normalised (eval plans, eval_y)."""
+        if getattr(self, "_ident", None) is None or self._ident[0].shape[-1] < C:
+            n = max(C, 1024)
+            self._ident = (torch.ones(1, n, dtype=torch.float32, device=self.device),
+                           torch.zeros(1, n, dtype=torch.float32, device=self.device))
+        return self._ident
 
     # ---- build -------------------------------------------------------------------------------
     def _build(self):
@@ -531,6 +542,22 @@ class NetPlan:
                     if (len(c.feeds) == 1 and f.rowmap == L.ROW_IDENT and f.dst_coff == 0 and pl.cout == c.cin and
                             c.La == self.bufs[pl.name].Lz and self.groups == 1):
                         self.eval_fused[pl.name] = c
+        # eval mode, BN layers with SEVERAL consumers (skip connections): the GEMM epilogue stores BN(z) in the layer's
+        # own buffer (eval_y) -- every consumer then reads it with the identity affine, and a consumer fed by this
+        # layer alone (identity rows, all columns) takes the buffer as its GEMM operand without a bn_apply pass
+        # (eval_alias).  Only additions / up-sampling / pooling of normalised tensors keep their pass.
+        self.eval_y: Dict[str, bool] = {}
+        self.eval_alias: Dict[str, Layer] = {}
+        if not self.train and self.groups == 1 and not _os.environ.get("B2H_NO_EVAL_FUSE"):
+            for pl in spec.layers:
+                cons = self.consumers[pl.name]
+                if pl.bn and len(cons) >= 2 and pl.name not in self.eval_fused:
+                    self.eval_y[pl.name] = True
+                    pb = self.bufs[pl.name]
+                    for c, f in cons:
+                        if (len(c.feeds) == 1 and f.rowmap == L.ROW_IDENT and f.dst_coff == 0 and pl.cout == c.cin and
+                                c.La == pb.Lz and self.bufs[c.name].Kc == pb.Cp):
+                            self.eval_alias[c.name] = pl
         with P.segment("fwd"):
             for l in spec.layers:
                 self._emit_input(l)
@@ -713,6 +740,8 @@ class NetPlan:
             return
         if isinstance(f0.src, Layer) and self.eval_fused.get(f0.src.name) is l:
             return   # the producer's GEMM epilogue wrote BN(z) into lb.a
+        if l.name in self.eval_alias:
+            return   # the producer's buffer holds BN(z) and IS this layer's GEMM operand
         # BN outputs of producer layers (+ residual / up-sampling / pooling), then this block's dropout
         cuts = sorted({f.dst_coff for f in l.feeds} | {f.dst_coff + f.src.cout for f in l.feeds})
         assert cuts[0] == 0 and cuts[-1] == l.cin, (l.name, cuts, l.cin)
@@ -738,7 +767,8 @@ class NetPlan:
         if is_out and self.ncl_direct:
             out, out_f32 = self.out, 2     # (B, C_out, T) fp32, written by the GEMM itself
         taps = lb.fwd_taps
-        common = dict(A=lb.a, W=lb.wf, bias=lb.bias, out=out, B=B, La=l.La, lda=lb.Kc, ldo=ldo, out_coff=0, Kc=lb.Kc,
+        a_in = self.bufs[self.eval_alias[l.name].name].z if l.name in self.eval_alias else lb.a
+        common = dict(A=a_in, W=lb.wf, bias=lb.bias, out=out, B=B, La=l.La, lda=lb.Kc, ldo=ldo, out_coff=0, Kc=lb.Kc,
                       Nvalid=l.cout, ntaps=len(taps), tap_off=taps + [0] * (L.MAX_TAPS - len(taps)), act=l.act,
                       post_scale=None, post_shift=None, out_f32=out_f32, drop=no_drop(), drop_C=0)
         if l.bn and self.train:
@@ -747,6 +777,8 @@ class NetPlan:
         if l.name in self.eval_fused:
             cb = self.bufs[self.eval_fused[l.name].name]
             common.update(out=cb.a, ldo=cb.Kc, post_scale=lb.scale, post_shift=lb.shift)
+        elif l.name in self.eval_y:
+            common.update(post_scale=lb.scale, post_shift=lb.shift)   # lb.z holds BN(z) from here on
         if l.kind == "convT":
             i = P.add(L.OP_GEMM, f"gemm.{l.name}", Lo=l.La, Npad=2 * lb.Cp, stride=1, nphase=2, Lo_actual=2 * l.La,
                       **common)

@@ -203,3 +203,42 @@ def test_wgrad_workspace_covers_the_library_bound(B, T):
                 desc = _fill_struct(L.Wgrad(), {k: v for k, v in rec.f.items()
                                                 if not k.startswith("_") and k not in ("P", "Q", "dW", "partial")})
                 assert lib.b2h_wgrad_workspace_bytes(C.byref(desc), dtype) <= have, rec.tag
+
+
+def test_batched_inference_plan_writes_ncl_from_the_output_layer(monkeypatch):
+    """From NCL_DIRECT_MIN_ROWS frames per forward on, a bf16 eval plan has no to_ncl pass: the output layer's GEMM record
+    carries out_f32 = 2 and the (B, C, T) fp32 tensor itself (include/b2h_abi.h).  The threshold is lowered so the
+    interpreted plan stays small; v2's 48-channel output (Npad = 64) must keep the BLC + to_ncl form."""
+    monkeypatch.setattr(nets, "NCL_DIRECT_MIN_ROWS", 32)
+    for variant, rf, cout, direct in (("v1", False, 252, True), ("v2", True, 48, False)):
+        torch.manual_seed(0)
+        G = R.build_generator(variant, 36, cout, rf)
+        randomize_bn(G)
+        G.eval()
+        g = torch.Generator().manual_seed(1)
+        B, T = 3, 16
+        x = torch.randn(B, 36, T, generator=g)
+        f = feats_for(variant, rf, B, T, g)
+        with torch.no_grad():
+            ref = G(x, feats_=f)
+        spec = nets.generator_spec(variant, 36, cout, rf, train=False)
+        store = nets.ParamStore(spec, "cpu", seed=0)
+        store.load_state_dict(G.state_dict())
+        plan = nets.NetPlan(spec, store, B, T, L.BF16, "cpu", train=False)
+        assert plan.ncl_direct is direct
+        kinds = [r.kind for r in plan.prog.recs]
+        assert (L.OP_TO_NCL in kinds) is (not direct)
+        out_rec = [r for r in plan.prog.recs if r.kind == L.OP_GEMM and r.f["out_f32"]][-1]
+        assert out_rec.f["out_f32"] == (2 if direct else 1)
+        if direct:
+            assert out_rec.f["out"] is plan.out and tuple(plan.out.shape) == (B, cout, T)
+        plan.x.copy_(x)
+        if f is not None:
+            plan.feats.copy_(f)
+        E.run_records(plan.prog.recs, *plan.prog.segments["pack"])
+        E.run_records(plan.prog.recs, *plan.prog.segments["fwd"])
+        assert rel_err(plan.out, ref) < 2e-2      # bf16 mode bar
+    # train plans and fp32 plans never use it
+    spec = nets.generator_spec("v1", 36, 252, False, train=False)
+    store = nets.ParamStore(spec, "cpu", seed=0)
+    assert not nets.NetPlan(spec, store, 3, 16, L.F32, "cpu", train=False).ncl_direct
