@@ -429,6 +429,13 @@ def run_train_config(variant, feats, precision, B, T, cin, cout, dev, world, ran
     return res, (tr, xs, ys, fs)
 
 
+def load_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
 def run_infer_config(variant, feats, precision, B, T, cin, cout, dev, world, steps, warmup):
     """Batched eval forward (inference.py:96-121): inputs resident, rotating over POOL batches."""
     from b2h_b200 import _lib as L
@@ -456,8 +463,13 @@ def run_infer_config(variant, feats, precision, B, T, cin, cout, dev, world, ste
         step(k)
     ms = max_over_ranks(interval_ms(step, steps, world), dev, world)
     launches = plan.prog.segment_launches.get("fwd", 0)
+    gflop = 2 * sum(plan.op_macs.values()) / 1e9          # algorithmic FLOP of one forward (no padding)
+    tflops = gflop / (ms / steps)                          # per GPU
+    peak = load_peaks().get("bf16_tflops", 1590.0) / (1.0 if precision == "bf16" else 6.0)   # fp32 mode: 3 x TF32
     return {"ms_per_step": ms / steps, "value": B * T * world * steps / (ms * 1e-3), "steps": steps,
-            "dtype": "bf16" if precision == "bf16" else "f32", "n_gpus": world, "gpu_launches_per_step": launches}
+            "dtype": "bf16" if precision == "bf16" else "f32", "n_gpus": world, "gpu_launches_per_step": launches,
+            "algorithmic_gflop": round(gflop, 3), "tflops_per_gpu": round(tflops, 1),
+            "frac_of_tensor_peak": round(tflops / peak, 4)}
 
 
 def algorithmic_gflop_per_step(tr):
@@ -621,11 +633,7 @@ def main():
             torch.cuda.empty_cache()
         line["configs"] = extras
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
+        peaks = load_peaks()
         flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
         def flush():

@@ -93,4 +93,16 @@ __device__ __forceinline__ void epi_fast8(const float* s_bias, const float* s_sc
   }
 }
 
+// epilogue modes of the tap-GEMM kernels (k_gemm_tc.cu, k_gemm_tf32.cu): see gemm_tc_kernel
+enum { MODE_PLAIN = 0, MODE_STATS = 1, MODE_BWDSUM = 2 };
+
+struct BwdSumsDev {
+  const float* mean;
+  const float* invstd;
+  double* accum;
+  int C, Cs, groups;
+  int up2;      // z row = tile row / 2 (x2 nearest up-sampling between the producer and this GEMM's rows)
+  int zbytes;   // bytes of the z box
+};
+
 }  // namespace b2h

@@ -30,17 +30,6 @@ using namespace ptx;
 // BWDSUM (dgrad): the store phase also accumulates the first pass of the producer layer's BatchNorm backward,
 // sum(g) and sum(g * zhat) per column, against a tile of the producer's z that one TMA brings into the idle
 // pipeline buffers while the accumulator is being staged (b2h_bwd_sums_t).
-enum { MODE_PLAIN = 0, MODE_STATS = 1, MODE_BWDSUM = 2 };
-
-struct BwdSumsDev {
-  const float* mean;
-  const float* invstd;
-  double* accum;
-  int C, Cs, groups;
-  int up2;      // z row = tile row / 2 (x2 nearest up-sampling between the producer and this GEMM's rows)
-  int zbytes;   // bytes of the z box
-};
-
 // MERGED (stride-1 convolutions with consecutive taps): the M tile is ordered (row-in-sample, sample) with
 // tb >= 8 samples, so the A box — tl + ntaps - 1 rows of tb samples, loaded ONCE per 64-channel chunk — serves
 // every tap through a descriptor shifted by tap * tb rows (a multiple of the 8-row swizzle atom): A traffic and
@@ -917,7 +906,7 @@ int plan_gemm_tc(const b2h_gemm_t& d, TcGemmPlan* plan, int esz) {
   if (rc) return rc;
   plan->fuse_stats = 0;
   plan->fuse_bwd = 0;
-  if (esz == 4) return B2H_OK;   // fp32 mode: statistics / backward sums are separate passes
+  if (esz == 4 && getenv("B2H_TF32_NO_FUSE")) return B2H_OK;   // (statistics / backward sums as separate passes)
   if (d.stats.z) {
     const b2h_bn_stats_t& st = d.stats;
     B2H_CHECK_ARG(st.z == d.out && d.out_coff == 0 && st.ld == d.ldo && st.C == d.Nvalid && st.groups >= 1 &&
@@ -944,29 +933,30 @@ int plan_gemm_tc(const b2h_gemm_t& d, TcGemmPlan* plan, int esz) {
     else
       ok = ok && bs.rowmap == B2H_ROW_IDENT && d.Lo_actual == bs.Lz;
     if (ok) {
-      const __nv_bfloat16* z = reinterpret_cast<const __nv_bfloat16*>(bs.z);
+      const uint8_t* z = reinterpret_cast<const uint8_t*>(bs.z);   // (act dtype: esz bytes per element)
+      const size_t zrow = (size_t)bs.ld * esz;
       const int box_l = up2 ? p.tl / 2 : p.tl;
       const int64_t zs_b = (int64_t)bs.Lz * bs.ld;   // sample pitch of z
       if (p.merged && d.nphase == 1) {   // (C, B, L) like the A operand of a merged plan
-        rc = make_map_3d(&plan->tmZ0, z, bs.ld, d.B, bs.Lz, zs_b, bs.ld, best_bn, p.tb, box_l, false, 2);
+        rc = make_map_3d(&plan->tmZ0, z, bs.ld, d.B, bs.Lz, zs_b, bs.ld, best_bn, p.tb, box_l, false, esz);
         plan->tmZ1 = plan->tmZ0;
       } else if (p.merged) {
         const int Le = (bs.Lz + 1) / 2, Lod = bs.Lz / 2;
-        rc = make_map_3d(&plan->tmZ0, z, bs.ld, d.B, Le, zs_b, 2 * (int64_t)bs.ld, best_bn, p.tb, box_l, false, 2);
+        rc = make_map_3d(&plan->tmZ0, z, bs.ld, d.B, Le, zs_b, 2 * (int64_t)bs.ld, best_bn, p.tb, box_l, false, esz);
         if (!rc && Lod > 0)
-          rc = make_map_3d(&plan->tmZ1, z + bs.ld, bs.ld, d.B, Lod, zs_b, 2 * (int64_t)bs.ld, best_bn, p.tb, box_l, false, 2);
+          rc = make_map_3d(&plan->tmZ1, z + zrow, bs.ld, d.B, Lod, zs_b, 2 * (int64_t)bs.ld, best_bn, p.tb, box_l, false, esz);
         else
           plan->tmZ1 = plan->tmZ0;
       } else if (d.nphase == 1) {
-        rc = make_map_3d(&plan->tmZ0, z, bs.ld, bs.Lz, d.B, bs.ld, (int64_t)bs.Lz * bs.ld, best_bn, box_l, p.tb, false, 2);
+        rc = make_map_3d(&plan->tmZ0, z, bs.ld, bs.Lz, d.B, bs.ld, (int64_t)bs.Lz * bs.ld, best_bn, box_l, p.tb, false, esz);
         plan->tmZ1 = plan->tmZ0;
       } else {   // output row 2*lo + ph <-> the even / odd rows of z
         const int Le = (bs.Lz + 1) / 2, Lod = bs.Lz / 2;
         rc = make_map_3d(&plan->tmZ0, z, bs.ld, Le, d.B, 2 * (int64_t)bs.ld, (int64_t)bs.Lz * bs.ld, best_bn, box_l, p.tb,
-                         false, 2);
+                         false, esz);
         if (!rc && Lod > 0)
-          rc = make_map_3d(&plan->tmZ1, z + bs.ld, bs.ld, Lod, d.B, 2 * (int64_t)bs.ld, (int64_t)bs.Lz * bs.ld, best_bn,
-                           box_l, p.tb, false, 2);
+          rc = make_map_3d(&plan->tmZ1, z + zrow, bs.ld, Lod, d.B, 2 * (int64_t)bs.ld, (int64_t)bs.Lz * bs.ld, best_bn,
+                           box_l, p.tb, false, esz);
         else   // no odd rows: the odd-phase tiles have no valid row and ignore what they load
           plan->tmZ1 = plan->tmZ0;
       }
@@ -979,7 +969,7 @@ int plan_gemm_tc(const b2h_gemm_t& d, TcGemmPlan* plan, int esz) {
       plan->bs_Cs = bs.Cs;
       plan->bs_groups = bs.groups;
       plan->bs_up2 = up2 ? 1 : 0;
-      plan->bs_zbytes = best_bn * 2 * box_l * p.tb;
+      plan->bs_zbytes = best_bn * esz * box_l * p.tb;
     }
   }
   return B2H_OK;

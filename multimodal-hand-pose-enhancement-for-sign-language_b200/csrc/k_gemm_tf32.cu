@@ -29,7 +29,9 @@
 
 #include "gemm_epilogue.cuh"
 #include "ptx_sm100.cuh"
+#include "bn_finalize.cuh"
 #include "tc_plans.h"
+#include "gemm_tc_shared.cuh"
 
 namespace b2h {
 
@@ -82,7 +84,9 @@ struct Tf32Cfg {
   static constexpr int EPI_BYTES = 128 * EPI_PITCH;
   static constexpr int MAIN_BYTES = PIPE_BYTES > MERGED_BYTES ? PIPE_BYTES : MERGED_BYTES;
   static_assert(EPI_BYTES <= MAIN_BYTES, "the epilogue tile reuses the pipeline buffers");
-  static constexpr int SMEM_BYTES = MAIN_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = MAIN_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 2 * BN * 4 /*pivot | invstd*/;
+  // STATS / BWDSUM: per-warp partial sums and the z tile live behind the epilogue tile in the (idle) pipeline buffers
+  static_assert(((EPI_BYTES + 8 * BN * 8 + 127) & ~127) + 128 * BN * 4 <= MAIN_BYTES, "z tile placement");
   static constexpr int NACC = 512 / BN - 1;        // accumulators of the a_hi*b_hi products; + 1 for the corrections
   static constexpr int SMALL_COL = NACC * BN;
 };
@@ -110,10 +114,16 @@ __device__ __forceinline__ void tmem_sum_accumulators(uint32_t lane_base, int c,
   }
 }
 
-template <int BN, bool MERGED>
+// MODE (as in gemm_tc_kernel): STATS = the store phase also accumulates the train-mode BatchNorm statistics of the
+// tile (shifted sums of the fp32 values as stored -> fp64 atomics -> the last CTA finalises); BWDSUM (dgrad) = it
+// accumulates the first pass of the producer layer's BatchNorm backward against a TMA-staged fp32 tile of z.
+template <int BN, bool MERGED, int MODE = MODE_PLAIN>
 __global__ void __launch_bounds__(T32_THREADS, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-                 const __grid_constant__ CUtensorMap tmB, TcGemmParams p, EpiParams e) {
+                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmZ0,
+                 const __grid_constant__ CUtensorMap tmZ1, TcGemmParams p, EpiParams e, b2h_bn_stats_t st, BwdSumsDev bs) {
+  constexpr bool STATS = MODE == MODE_STATS;
+  constexpr bool BWDSUM = MODE == MODE_BWDSUM;
   using Cfg = Tf32Cfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -126,7 +136,11 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
   uint64_t* a_ready = a_full + 2;
   uint64_t* a_empty = a_ready + 2;
   uint64_t* tmem_full_bar = a_empty + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* z_bar = tmem_full_bar + 1;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(z_bar + 1);
+  int* s_flag = reinterpret_cast<int*>(tmem_ptr + 1);
+  float* s_piv = reinterpret_cast<float*>(smem + Cfg::MAIN_BYTES + 256);   // STATS: pivot;  BWDSUM: mean
+  float* s_isd = s_piv + BN;                                               // BWDSUM: invstd
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mt = blockIdx.x, nt = blockIdx.y;
@@ -151,6 +165,11 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       mbar_init(&a_empty[i], 1);
     }
     mbar_init(tmem_full_bar, 1);
+    if (BWDSUM) {
+      prefetch_tmap(&tmZ0);
+      prefetch_tmap(&tmZ1);
+      mbar_init(z_bar, 1);
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -285,6 +304,22 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const int valid_cols = min(BN, e.Nvalid - nn0);
     constexpr int pitch = Cfg::EPI_PITCH;
     uint8_t* stage = smem + (size_t)sub * 32 * pitch;
+    // a CTA past the last group's clips (ragged tiles) has no valid row: clamp its group index
+    const int grp = (STATS || BWDSUM) ? min(b0 / (p.B / (STATS ? st.groups : bs.groups)), (STATS ? st.groups : bs.groups) - 1) : 0;
+    if (STATS || BWDSUM) {
+      for (int i = et; i < BN; i += 256) {
+        if (STATS) {
+          s_piv[i] = (st.running_mean && nn0 + i < st.C) ? st.running_mean[nn0 + i] : 0.f;
+        } else {
+          const bool in = nn0 + i < bs.C;
+          s_piv[i] = in ? bs.mean[grp * bs.Cs + nn0 + i] : 0.f;
+          s_isd[i] = in ? bs.invstd[grp * bs.Cs + nn0 + i] : 0.f;
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
+    // z tile (BWDSUM): behind the staging tile and the per-warp partials; the pipeline buffers are idle by then
+    uint8_t* zs = smem + (((size_t)Cfg::EPI_BYTES + (size_t)8 * BN * 8 + 127) & ~(size_t)127);
     DropCtx drop;
     drop.init(e.drop, e.drop_C);
     {
@@ -298,6 +333,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       uint8_t* my = stage + (size_t)lane * pitch;
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
+      if (BWDSUM && et == 0) {   // every MMA has retired: the stage buffers are free
+        mbar_arrive_expect_tx(z_bar, (uint32_t)bs.zbytes);
+        if (MERGED)   // z maps of a merged plan are (C, B, L) too
+          tma_load_3d(zs, ph ? &tmZ1 : &tmZ0, z_bar, nn0, b0, bs.up2 ? (l0 >> 1) : l0);
+        else
+          tma_load_3d(zs, ph ? &tmZ1 : &tmZ0, z_bar, nn0, bs.up2 ? (l0 >> 1) : l0, b0);
+      }
       constexpr int CH = BN / 2;  // columns per epilogue warp
       const int n_main = min(NACC, nkb);
 #pragma unroll 1
@@ -315,6 +357,100 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
       }
     }
     asm volatile("bar.sync %0, 64;" ::"r"(2 + sub) : "memory");   // both warps of this sub-partition are done
+    if (STATS || BWDSUM) {
+      // lane <-> fixed 16-byte column chunk (4 channels); the lanes left over take further rows of the same iteration
+      constexpr int CHUNKS = BN / 4;
+      constexpr int LPR = CHUNKS < 32 ? CHUNKS : 32;
+      constexpr int RPI = 32 / LPR;
+      const int ch = lane % LPR, rsub = lane / LPR;
+      const bool ch_ok = ch * 4 < valid_cols;   // a ragged last chunk is stored whole (zeros in the padding)
+      float piv[4], sc[4], a1[4], a2[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        piv[i] = s_piv[ch * 4 + i], a1[i] = 0.f, a2[i] = 0.f;
+        sc[i] = BWDSUM ? s_isd[ch * 4 + i] : 1.f;
+      }
+      if (BWDSUM) mbar_wait(z_bar, 0);
+      if (ch_ok) {
+#pragma unroll 1
+        for (int rr = chalf * 16 + rsub; rr < chalf * 16 + 16; rr += RPI) {
+          const int r = sub * 32 + rr;
+          const int bi = MERGED ? (r & (p.tb - 1)) : (r >> p.tl_log2), li = MERGED ? (r >> p.tb_log2) : (r & (p.tl - 1));
+          const int b = b0 + bi, lo = l0 + li;
+          const int ris = lo * e.nphase + ph;
+          if (b >= p.B || lo >= p.Lo || ris >= e.Lo_actual) continue;
+          const int64_t grow = (int64_t)b * e.Lo_actual + ris;
+          float* gdst = reinterpret_cast<float*>(e.out) + (size_t)grow * e.ldo + e.out_coff + nn0;
+          const float4 u = *reinterpret_cast<const float4*>(stage + (size_t)rr * pitch + ch * 16);
+          *reinterpret_cast<float4*>(gdst + ch * 4) = u;
+          const float w[4] = {u.x, u.y, u.z, u.w};
+          if (STATS) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float d0 = w[i] - piv[i];
+              a1[i] += d0;
+              a2[i] = fmaf(d0, d0, a2[i]);
+            }
+          } else {
+            const int zr = !bs.up2 ? r : (MERGED ? (li >> 1) * p.tb + bi : bi * (p.tl >> 1) + (li >> 1));
+            const float4 zq = *reinterpret_cast<const float4*>(zs + ((size_t)zr * BN + ch * 4) * 4);
+            const float zw[4] = {zq.x, zq.y, zq.z, zq.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float h = (zw[i] - piv[i]) * sc[i];
+              a1[i] += w[i];
+              a2[i] = fmaf(w[i], h, a2[i]);
+            }
+          }
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int off = LPR; off < 32; off <<= 1) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          a1[i] += __shfl_xor_sync(0xffffffffu, a1[i], off);
+          a2[i] += __shfl_xor_sync(0xffffffffu, a2[i], off);
+        }
+      }
+      // per-warp partials -> fixed-order sum over the 8 epilogue warps -> fp64 atomics
+      float2* s_part = reinterpret_cast<float2*>(smem + (size_t)Cfg::EPI_BYTES);   // [8][BN]
+      if (rsub == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s_part[(warp - 2) * BN + ch * 4 + i] = make_float2(a1[i], a2[i]);
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int c = et; c < valid_cols; c += 256) {
+        float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+        for (int w8 = 0; w8 < 8; ++w8) {
+          const float2 v = s_part[w8 * BN + c];
+          t1 += v.x, t2 += v.y;
+        }
+        if (STATS) {
+          bn_stats_accumulate(st, blockIdx.x % kCopies, grp, nn0 + c, t1, t2);
+        } else {
+          double* a = bs.accum + (((int64_t)(blockIdx.x % B2H_BWD_COPIES) * bs.groups + grp) * bs.C + nn0 + c) * 2;
+          atomicAdd(a + 0, (double)t1);
+          atomicAdd(a + 1, (double)t2);
+        }
+      }
+      if (STATS) {
+        __threadfence();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (et == 0) {
+          const uint32_t t = atomicAdd(st.ticket, 1u);
+          const int last = (t == gridDim.x * gridDim.y - 1u);
+          if (last) *st.ticket = 0u;
+          *s_flag = last;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (*s_flag) {
+          __threadfence();
+          bn_stats_finalize(st, et, 256);
+        }
+      }
+    } else
     if (valid_cols > 0) {
       const int row_bytes = valid_cols * 4;
       const int full16 = row_bytes >> 4;
@@ -534,38 +670,60 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant
 // ---------------------------------------------------------------------------------------------
 // host
 // ---------------------------------------------------------------------------------------------
-template <int BN, bool MERGED>
-static int launch_tf32(const TcGemmPlan& plan, const EpiParams& e, cudaStream_t s) {
+template <int BN, bool MERGED, int MODE>
+static int launch_tf32(const TcGemmPlan& plan, const EpiParams& e, cudaStream_t s, const b2h_bn_stats_t& st) {
   using Cfg = Tf32Cfg<BN>;
-  B2H_CARVE(gemm_tf32_kernel<BN, MERGED>);
+  B2H_CARVE(gemm_tf32_kernel<BN, MERGED, MODE>);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t er = cudaFuncSetAttribute(gemm_tf32_kernel<BN, MERGED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t er = cudaFuncSetAttribute(gemm_tf32_kernel<BN, MERGED, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           Cfg::SMEM_BYTES);
     if (er != cudaSuccess) return cuda_fail(er, "gemm_tf32 smem attribute");
     attr_set = true;
   }
+  BwdSumsDev bs;
+  memset(&bs, 0, sizeof(bs));
+  if (MODE == MODE_BWDSUM) {
+    bs.mean = plan.bs_mean;
+    bs.invstd = plan.bs_invstd;
+    bs.accum = plan.bs_accum;
+    bs.C = plan.bs_C;
+    bs.Cs = plan.bs_Cs;
+    bs.groups = plan.bs_groups;
+    bs.up2 = plan.bs_up2;
+    bs.zbytes = plan.bs_zbytes;
+  }
+  const bool z = MODE == MODE_BWDSUM;
   dim3 grid(plan.grid_x, plan.grid_y);
-  launch(gemm_tf32_kernel<BN, MERGED>, grid, T32_THREADS, Cfg::SMEM_BYTES, s, plan.tmA0, plan.tmA1, plan.tmB, plan.p, e);
+  launch(gemm_tf32_kernel<BN, MERGED, MODE>, grid, T32_THREADS, Cfg::SMEM_BYTES, s, plan.tmA0, plan.tmA1, plan.tmB,
+         z ? plan.tmZ0 : plan.tmA0, z ? plan.tmZ1 : plan.tmA0, plan.p, e, st, bs);
   B2H_LAUNCH_CHECK("gemm_tf32");
   return B2H_OK;
 }
 
+template <int BN, int MODE>
+static int launch_tf32_m(const TcGemmPlan& plan, const EpiParams& e, cudaStream_t s, const b2h_bn_stats_t& st) {
+  return plan.p.merged ? launch_tf32<BN, true, MODE>(plan, e, s, st) : launch_tf32<BN, false, MODE>(plan, e, s, st);
+}
+
+template <int BN>
+static int launch_tf32_mode(const TcGemmPlan& plan, const EpiParams& e, cudaStream_t s, const b2h_bn_stats_t& st) {
+  if (plan.fuse_stats) return launch_tf32_m<BN, MODE_STATS>(plan, e, s, st);
+  if (plan.fuse_bwd) return launch_tf32_m<BN, MODE_BWDSUM>(plan, e, s, st);
+  return launch_tf32_m<BN, MODE_PLAIN>(plan, e, s, st);
+}
+
 int run_gemm_tf32(const TcGemmPlan& plan, const b2h_gemm_t& d, cudaStream_t s) {
   EpiParams e = make_epi(d);
-  int rc;
-  if (plan.BN == 128)
-    rc = plan.p.merged ? launch_tf32<128, true>(plan, e, s) : launch_tf32<128, false>(plan, e, s);
-  else
-    rc = plan.p.merged ? launch_tf32<64, true>(plan, e, s) : launch_tf32<64, false>(plan, e, s);
+  int rc = plan.BN == 128 ? launch_tf32_mode<128>(plan, e, s, d.stats) : launch_tf32_mode<64>(plan, e, s, d.stats);
   if (rc) return rc;
-  // fp32 mode: the statistics of the output and the backward sums are separate passes (as on the FFMA path)
-  if (d.stats.z) {
+  // shapes the epilogue cannot cover: separate passes with the same results
+  if (d.stats.z && !plan.fuse_stats) {
     B2H_CHECK_ARG(d.stats.z == d.out && d.out_coff == 0, B2H_ERR_ARG, "gemm: stats must describe the output tensor");
     rc = launch_bn_stats(d.stats, B2H_F32, s);
     if (rc) return rc;
   }
-  if (d.bwd_sums.z) return launch_bwd_sums_separate(d, B2H_F32, s);
+  if (d.bwd_sums.z && !plan.fuse_bwd) return launch_bwd_sums_separate(d, B2H_F32, s);
   return B2H_OK;
 }
 

@@ -248,12 +248,16 @@ def test_fp32_mode_contractions_run_on_the_tensor_cores():
     24 k-blocks (the bound that keeps the accumulator's truncation below the 1e-5 bar)."""
     from b2h_b200.trainer import GanTrainer
     tr = GanTrainer("v1", 36, 252, False, 256, 64, precision="fp32", device="cuda", drop_mode="mask")
-    n = 0
+    n = fused_stats = fused_bwd = 0
     for plan in (tr.G_train, tr.G_eval, tr.D_train, tr.D_eval):
         for r in plan.prog.tile_report():
             if r["kind"] in (L.OP_GEMM, L.OP_WGRAD):
                 assert r["tensor_core"] and r["tile_n"] in (64, 128), r
                 n += 1
+                fused_stats += int(r["fuse_stats"])
+                fused_bwd += int(r["fuse_bwd"])
                 if r["kind"] == L.OP_WGRAD:
                     assert r["splits"] >= 1
     assert n > 60
+    # BatchNorm statistics / first backward pass ride in the 3xTF32 epilogues as they do in the bf16 ones
+    assert fused_stats >= 14 and fused_bwd >= 10, (fused_stats, fused_bwd)
