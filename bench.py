@@ -319,8 +319,12 @@ def hbm_records(tr, flush, peak_gbs):
     for i, rec in enumerate(tr.g_loss_prog.recs):
         if rec.kind == L.OP_L1:
             n = rec.f["B"] * rec.f["C"] * rec.f["L"]
-            add("l1_kernel (" + rec.tag + ")", tr.g_loss_prog, i, n * (4 + 4 + esz),
-                f"read out fp32 + read gt fp32 + write dout {esz} B, per element")
+            if rec.f.get("out_blc") is not None:
+                add("l1_kernel (" + rec.tag + ", reads the output layer's BLC tile, writes NCL out)", tr.g_loss_prog, i,
+                    n * (4 + 4 + 4 + esz), f"read out_blc fp32 + read gt fp32 + write out fp32 + write dout {esz} B, per element")
+            else:
+                add("l1_kernel (" + rec.tag + ")", tr.g_loss_prog, i, n * (4 + 4 + esz),
+                    f"read out fp32 + read gt fp32 + write dout {esz} B, per element")
         if rec.kind == L.OP_ADAM and rec.f.get("phase", 0) == 0:
             add("adam_kernel (generator, whole flat buffer)", tr.g_loss_prog, i, rec.f["n"] * 28,
                 "28 B/parameter: read p, g, m, v; write p, m, v")

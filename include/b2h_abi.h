@@ -257,6 +257,11 @@ typedef struct {
   int32_t kind;        /* B2H_LOSS_* (0 = L1) */
   float* dbias;        /* optional: column sums of dout as stored = bias gradient of the output layer [C] */
   double* dbias_accum; /* workspace for dbias: [16][C] doubles, zero-initialised, self-resetting */
+  const float* out_blc; /* optional: the prediction as the output layer's GEMM left it, fp32 [B][L][out_blc_ld].  When
+                           given, the op reads it from there and WRITES `out` (the NCL fp32 tensor the reference returns)
+                           in the same pass -- it replaces b2h_to_ncl + the re-read of its result */
+  int32_t out_blc_ld;
+  int32_t reserved0;
 } b2h_l1_t;
 
 /* nn.MSELoss(score, target) (train_gan.py:93,247,292) on (groups, n) scores, one target per group;

@@ -92,7 +92,7 @@ class ToNcl(C.Structure):
 class L1(C.Structure):
     _fields_ = [("out", vp), ("gt", vp), ("dout", vp), ("loss", vp), ("partial", vp), ("ticket", vp),
                 ("B", i32), ("C", i32), ("L", i32), ("ld", i32), ("Cfill", i32), ("gscale", f32), ("kind", i32),
-                ("dbias", vp), ("dbias_accum", vp)]
+                ("dbias", vp), ("dbias_accum", vp), ("out_blc", vp), ("out_blc_ld", i32), ("reserved0", i32)]
 
 
 class Mse(C.Structure):

@@ -187,6 +187,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) l1_kernel(b2h_l1_t d, int cext, int spc) {
   pdl_sync();
   __shared__ float tile[32][33];
+  __shared__ float tile_o[32][33];   // out_blc: the prediction tile, [frame][channel]
   __shared__ double s_part[256];
   __shared__ float s_col[1024];
   const int l0 = blockIdx.x * 32;
@@ -204,12 +205,28 @@ __global__ void __launch_bounds__(256) l1_kernel(b2h_l1_t d, int cext, int spc) 
   for (int si = 0; si < spc; ++si) {
   const int b = blockIdx.y * spc + si;
   for (int c0 = 0; c0 < cext; c0 += 32) {
+    if (d.out_blc) {
+      // the prediction comes as BLC rows (channels contiguous): coalesced 128-byte row reads, transposed through
+      // shared memory; the NCL copy the reference returns is written below, in the same pass
+      for (int j = ty; j < 32; j += 8) {
+        const int l = l0 + j, c = c0 + tx;
+        tile_o[j][tx] = (l < d.L && c < d.C) ? d.out_blc[((int64_t)b * d.L + l) * d.out_blc_ld + c] : 0.f;
+      }
+      __syncthreads();
+    }
     for (int j = ty; j < 32; j += 8) {
       int c = c0 + j, l = l0 + tx;
       float sg = 0.f;
       if (c < d.C && l < d.L) {
         int64_t i = ((int64_t)b * d.C + c) * d.L + l;
-        float diff = d.out[i] - d.gt[i];
+        float o;
+        if (d.out_blc) {
+          o = tile_o[tx][j];
+          const_cast<float*>(d.out)[i] = o;
+        } else {
+          o = d.out[i];
+        }
+        float diff = o - d.gt[i];
         if (d.kind == B2H_LOSS_L1) {
           acc += fabsf(diff);
           sg = diff > 0.f ? gval : (diff < 0.f ? -gval : 0.f);  // sign(diff)/numel, sign(0) = 0

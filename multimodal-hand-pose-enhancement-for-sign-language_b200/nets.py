@@ -349,7 +349,7 @@ class NetPlan:
                  drop_state: Optional[torch.Tensor] = None, site_base: int = 0,
                  motion_src: Optional[Sequence[torch.Tensor]] = None,
                  weights_from: Optional["NetPlan"] = None, out_dbias_external: bool = False,
-                 wgrad_direct: bool = False):
+                 wgrad_direct: bool = False, out_by_loss: bool = False):
         """`weights_from`: another plan of the SAME store and dtype whose packed forward weights / biases this
         plan reads instead of packing its own (the eval twin of a train plan: one repack per optimizer step
         serves both)."""
@@ -363,6 +363,9 @@ class NetPlan:
         # slack behind it, i.e. all but the first two layers of the network (the last two of the backward); meant
         # for callers that run the wgrads on several side streams (GanTrainer)
         self.wgrad_direct = wgrad_direct and dtype == L.BF16
+        # train plans of a GanTrainer: the forward stops at the output layer's fp32 BLC tile; the loss kernel reads it
+        # and writes the NCL `out` itself (b2h_l1_t.out_blc) -- no to_ncl launch, no re-read of its result
+        self.out_by_loss = bool(out_by_loss) and train
         self.spec, self.store, self.B, self.T, self.dtype = spec, store, B, T, dtype
         self.device = torch.device(device)
         self.train, self.groups = train, groups
@@ -562,7 +565,7 @@ class NetPlan:
             for l in spec.layers:
                 self._emit_input(l)
                 self._emit_fwd_gemm(l)
-            if spec.input_kind == "x" and not self.ncl_direct:
+            if spec.input_kind == "x" and not self.ncl_direct and not self.out_by_loss:
                 P.add(L.OP_TO_NCL, "out", src=self.out_blc, dst=self.out, B=B, L=olb.Lz, C=ol.cout,
                       ld=self.out_blc.shape[-1], src_f32=1)
         if self.train:

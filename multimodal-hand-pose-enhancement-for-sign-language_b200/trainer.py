@@ -306,8 +306,10 @@ class GanTrainer:
         kw_d = dict(drop_mode=drop_mode, drop_state=self.drop_state_d)
         # generator: train plan (G step) and eval plan (D step / inference)
         direct = os.environ.get("B2H_NO_WGRAD_DIRECT") is None
+        # (the regression loss reads the output layer's BLC tile and writes the NCL `out` itself: no to_ncl pass)
+        self.l1_reads_blc = os.environ.get("B2H_NO_L1_FUSE") is None
         self.G_train = nets.NetPlan(self.g_spec, self.g_store, B, T, self.dtype, dev, train=True, site_base=0,
-                                    wgrad_direct=direct, **kw)
+                                    wgrad_direct=direct, out_by_loss=self.l1_reads_blc, **kw)
         self.G_eval = nets.NetPlan(self.g_spec_eval, self.g_store, B, T, self.dtype, dev, train=False,
                                    weights_from=self.G_train)
         self.y = torch.zeros(B, out_dim, T, dtype=torch.float32, device=dev)
@@ -433,7 +435,9 @@ class GanTrainer:
         with P.segment("loss"):
             P.add(L.OP_L1, "l1", out=Gt.out, gt=self.y, dout=olb.dpre, loss=self.losses[0:1], partial=self.l1_partial,
                   ticket=self.ticket[0:1], B=B, C=out_dim, L=T, ld=olb.Cp, Cfill=olb.Cp, gscale=1.0,
-                  kind=L.LOSS_KINDS[self.loss], dbias=None, dbias_accum=None)
+                  kind=L.LOSS_KINDS[self.loss], dbias=None, dbias_accum=None,
+                  out_blc=Gt.out_blc if self.l1_reads_blc else None,
+                  out_blc_ld=Gt.out_blc.shape[-1] if self.l1_reads_blc else 0)
             # (l1 can also emit the bias gradient of the output layer, but the in-kernel column sums cost more than
             # the separate 8 us colsum launch: 29.9 vs 13.4 + 7.7 us)
             P.add(L.OP_MSE, "adv", score=De.out_blc, dscore=None, loss=self.losses[1:2], add=self.losses[0:1],
@@ -709,8 +713,10 @@ class GanTrainer:
             assert pack_after is None and adv_after is None and deferred_adv is None
             self.D_eval.prog.run("pack")      # fold D's running statistics
             self.G_train.prog.run("fwd")
+            ls, le = self.g_loss_prog.segments["loss"]             # [l1, adv]
+            self.g_loss_prog.run_range(ls, ls + 1)                 # (writes G_train.out when it reads the BLC tile)
             self.D_eval.prog.run("fwd")
-            self.g_loss_prog.run("loss")
+            self.g_loss_prog.run_range(ls + 1, le)
             self._bwd_update("g")             # backward, Adam, repack of the updated generator weights
             return
         # The adversarial term of the generator loss carries no gradient (train_gan.py:285-287 detaches the
@@ -721,10 +727,14 @@ class GanTrainer:
         if deferred_adv is not None:
             prep_done, adv_done = deferred_adv
             fs, fe = self.G_train.prog.segments["fwd"]
-            assert self.G_train.prog.recs[fe - 1].kind == L.OP_TO_NCL
-            self.G_train.prog.run_range(fs, fe - 1, cur.cuda_stream)
-            cur.wait_event(prep_done)
-            self.G_train.prog.run_range(fe - 1, fe, cur.cuda_stream)   # writes G_train.out
+            if self.l1_reads_blc:        # the loss kernel writes G_train.out and losses[0]
+                self.G_train.prog.run_range(fs, fe, cur.cuda_stream)
+                cur.wait_event(prep_done)
+            else:
+                assert self.G_train.prog.recs[fe - 1].kind == L.OP_TO_NCL
+                self.G_train.prog.run_range(fs, fe - 1, cur.cuda_stream)
+                cur.wait_event(prep_done)
+                self.G_train.prog.run_range(fe - 1, fe, cur.cuda_stream)   # writes G_train.out
             cur.wait_event(adv_done)
             self.g_loss_prog.run_range(ls, ls + 1, cur.cuda_stream)
             self._bwd_update("g", pack_after=pack_after, joint=joint)
@@ -738,14 +748,22 @@ class GanTrainer:
             adv.wait_event(adv_after)
         self.D_eval.prog.run("pack", adv.cuda_stream)        # fold D's running statistics
         self.G_train.prog.run("fwd")
-        fwd_done = torch.cuda.Event()
-        fwd_done.record(cur)
-        adv.wait_event(fwd_done)
-        self.D_eval.prog.run("fwd", adv.cuda_stream)
-        self.g_loss_prog.run_range(ls, ls + 1, cur.cuda_stream)
-        l1_done = torch.cuda.Event()
-        l1_done.record(cur)
-        adv.wait_event(l1_done)                              # total = l1 + adv
+        if self.l1_reads_blc:
+            # G_train.out (what the scoring branch reads) is written by the loss kernel
+            self.g_loss_prog.run_range(ls, ls + 1, cur.cuda_stream)
+            l1_done = torch.cuda.Event()
+            l1_done.record(cur)
+            adv.wait_event(l1_done)
+            self.D_eval.prog.run("fwd", adv.cuda_stream)
+        else:
+            fwd_done = torch.cuda.Event()
+            fwd_done.record(cur)
+            adv.wait_event(fwd_done)
+            self.D_eval.prog.run("fwd", adv.cuda_stream)
+            self.g_loss_prog.run_range(ls, ls + 1, cur.cuda_stream)
+            l1_done = torch.cuda.Event()
+            l1_done.record(cur)
+            adv.wait_event(l1_done)                          # total = l1 + adv
         self.g_loss_prog.run_range(ls + 1, le, adv.cuda_stream)
         self._bwd_update("g", pack_after=pack_after)   # backward, Adam, repack of the updated weights
         join = torch.cuda.Event()

@@ -305,6 +305,8 @@ def to_ncl(f: Dict):
 
 def l1(f: Dict):
     B, C, L = f["B"], f["C"], f["L"]
+    if f.get("out_blc") is not None:   # the prediction arrives BLC fp32; the op also writes the NCL tensor (b2h_abi.h)
+        f["out"].reshape(B, C, L).copy_(f["out_blc"].reshape(B, L, -1)[:, :, :C].permute(0, 2, 1))
     o, g = f["out"].reshape(B, C, L), f["gt"].reshape(B, C, L)
     d = o - g
     kind = f.get("kind", 0)   # B2H_LOSS_* of include/b2h_abi.h: 0 L1, 1 L2, 2 Huber(delta 1), 3 frozen adaptive loss

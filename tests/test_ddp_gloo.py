@@ -55,7 +55,8 @@ def _worker(rank, port, ret):
     run = lambda prog, seg: E.run_records(prog.recs, *prog.segments[seg])  # noqa: E731
     for prog, seg in ((tr.G_train.prog, "pack"), (tr.D_train.prog, "pack"), (tr.D_eval.prog, "pack"),
                       (tr.G_train.prog, "fwd"),
-                      (tr.D_eval.prog, "fwd"), (tr.g_loss_prog, "loss")):
+                      (tr.g_loss_prog, "loss"),       # (l1 writes G_train.out; the adversarial VALUE is not checked here)
+                      (tr.D_eval.prog, "fwd")):
         run(prog, seg)
     buckets = tr.bucket_plan(tr.G_train)
     # the buckets tile the flat gradient exactly once, from the end of the buffer towards its start

@@ -64,8 +64,8 @@ def test_two_rank_fused_generator_step_equals_averaged_replicas(n_buckets):
         assert tr.g_store.flat.data_ptr() == tr._peer["g"].p_ptrs[r] and tr.g_store.grad.data_ptr() == tr._peer["g"].g_ptrs[r]
     for tr in trs:
         for prog, seg in ((tr.G_train.prog, "pack"), (tr.D_train.prog, "pack"), (tr.D_eval.prog, "pack"),
-                          (tr.G_train.prog, "fwd"), (tr.D_eval.prog, "fwd"), (tr.g_loss_prog, "loss")):
-            run(prog, seg)
+                          (tr.G_train.prog, "fwd"), (tr.g_loss_prog, "loss"), (tr.D_eval.prog, "fwd")):
+            run(prog, seg)     # (l1 writes G_train.out; the adversarial VALUE is not checked here)
     # backward bucket by bucket; the optimizer program of a bucket is the fused op (no all-reduce anywhere)
     bp = trs[0]._buckets["g"][0]
     assert len(bp) == n_buckets

@@ -104,6 +104,10 @@ def accesses(rec):
                         w = False
                     if rec.kind == L.OP_ADAM and rec.f.get("phase", 0) == 1 and k in ("p", "m", "v", "g"):
                         continue                       # phase 1 only advances the step
+                    if rec.kind == L.OP_L1 and k == "out" and rec.f.get("out_blc") is not None:
+                        w = True                       # the loss reads the BLC tile and writes the NCL `out` itself
+                    if rec.kind == L.OP_GEMM and k == "out" and rec.f.get("out_f32") == 2:
+                        w = True
                     if rec.kind == L.OP_WGRAD and k == "partial" and rec.f.get("splits") == 1:
                         continue                       # split-free form (bf16 plans only): no workspace traffic
                     out.append((v.data_ptr(), v.data_ptr() + v.numel() * v.element_size(), w, path))

@@ -63,11 +63,21 @@ def emul(prog, seg):
     E.run_records(prog.recs, *prog.segments[seg])
 
 
-def emul_g_step(tr):
+def emul_g_forward_and_losses(tr):
+    """Generator forward, regression loss (it writes G_train.out from the output layer's BLC tile), scoring pass of
+    the discriminator on that output, adversarial term -- the order of GanTrainer._g_ops."""
     # (the eval plans read the packed weights of their train twins: pack those first)
-    for p, s in ((tr.G_train.prog, "pack"), (tr.D_train.prog, "pack"), (tr.D_eval.prog, "pack"),
-                 (tr.G_train.prog, "fwd"), (tr.D_eval.prog, "fwd"),
-                 (tr.g_loss_prog, "loss"), (tr.G_train.prog, "bwd"), (tr.g_loss_prog, "opt")):
+    for p, s in ((tr.G_train.prog, "pack"), (tr.D_train.prog, "pack"), (tr.D_eval.prog, "pack"), (tr.G_train.prog, "fwd")):
+        emul(p, s)
+    ls, le = tr.g_loss_prog.segments["loss"]      # [l1, adv]
+    E.run_records(tr.g_loss_prog.recs, ls, ls + 1)
+    emul(tr.D_eval.prog, "fwd")
+    E.run_records(tr.g_loss_prog.recs, ls + 1, le)
+
+
+def emul_g_step(tr):
+    emul_g_forward_and_losses(tr)
+    for p, s in ((tr.G_train.prog, "bwd"), (tr.g_loss_prog, "opt")):
         emul(p, s)
 
 
@@ -294,9 +304,7 @@ def test_bucket_by_bucket_update_order_matches_the_oracle(variant, rf, precision
     assert len(all_updated) == len(set(all_updated)) == len({l.name for l in st.spec.all_layers()})
     for steps in range(2):
         R.generator_step(G, D, g_opt, x, y, f, masks)
-        for p_, s_ in ((tr.G_train.prog, "pack"), (tr.D_train.prog, "pack"), (tr.D_eval.prog, "pack"),
-                       (tr.G_train.prog, "fwd"), (tr.D_eval.prog, "fwd"), (tr.g_loss_prog, "loss")):
-            emul(p_, s_)
+        emul_g_forward_and_losses(tr)
         st.grad.fill_(float("nan"))                  # a gradient consumed before it is produced poisons the update
         live = {n for n, _ in tr.G_train.bwd_marks}
         for l in st.spec.all_layers():               # (dead branches never write theirs: they stay zero, as on the device)
