@@ -181,8 +181,9 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// grid (L/32, B/spc): a CTA walks `spc` clips so that its per-channel partial sums of the bias gradient (kept in
-// shared memory; channel c is owned by one warp) cost one fp64 atomic per channel per CTA
+// grid (L/32, B/spc, channel tiles): one 32 x 32 (frames x channels) tile per CTA and clip -- the kernel is bound by the
+// latency of a CTA's dependent phases (load, transpose, store), not by bytes, so the tiles of a clip run side by side
+// instead of one after the other (8 tiles per CTA: 25.6 us; one: see profiles/)
 template <typename T>
 __global__ void __launch_bounds__(256) l1_kernel(b2h_l1_t d, int cext, int spc) {
   pdl_sync();
@@ -199,12 +200,12 @@ __global__ void __launch_bounds__(256) l1_kernel(b2h_l1_t d, int cext, int spc) 
   }
   const int64_t numel = (int64_t)d.B * d.C * d.L;
   const float gval = d.gscale / (float)numel;
-  const uint32_t nblocks = gridDim.x * gridDim.y;
-  const uint32_t bid = blockIdx.y * gridDim.x + blockIdx.x;
+  const uint32_t nblocks = gridDim.x * gridDim.y * gridDim.z;
+  const uint32_t bid = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
   float acc = 0.f;
   for (int si = 0; si < spc; ++si) {
   const int b = blockIdx.y * spc + si;
-  for (int c0 = 0; c0 < cext; c0 += 32) {
+  for (int c0 = blockIdx.z * 32; c0 < min(cext, (int)blockIdx.z * 32 + 32); c0 += 32) {
     if (d.out_blc) {
       // the prediction comes as BLC rows (channels contiguous): coalesced 128-byte row reads, transposed through
       // shared memory; the NCL copy the reference returns is written below, in the same pass
@@ -260,7 +261,8 @@ __global__ void __launch_bounds__(256) l1_kernel(b2h_l1_t d, int cext, int spc) 
   }
   }
   if (d.dbias) {
-    for (int c = tid; c < d.C; c += 256) atomicAdd(d.dbias_accum + (int64_t)(bid % 16) * d.C + c, (double)s_col[c]);
+    for (int c = blockIdx.z * 32 + tid; c < min(d.C, (int)blockIdx.z * 32 + 32); c += 256)   // this CTA's channels
+      atomicAdd(d.dbias_accum + (int64_t)(bid % 16) * d.C + c, (double)s_col[c]);
   }
   s_part[tid] = (double)acc;
   __syncthreads();
@@ -306,7 +308,7 @@ int launch_l1(const b2h_l1_t& d, int dtype, cudaStream_t s) {
   B2H_CHECK_ARG(!d.dbias || d.C <= 1024, B2H_ERR_SHAPE, "l1: dbias supports up to 1024 channels");
   int cext = d.dout ? d.Cfill : d.C;
   const int spc = 1;   // clips per CTA (more than one was measured slower: the kernel is latency-bound per CTA)
-  dim3 grid(ceil_div(d.L, 32), d.B / spc), block(32, 8);
+  dim3 grid(ceil_div(d.L, 32), d.B / spc, ceil_div(cext, 32)), block(32, 8);
   if (dtype == B2H_BF16)
     launch(l1_kernel<__nv_bfloat16>, grid, block, 0, s, d, cext, spc);
   else
@@ -314,7 +316,9 @@ int launch_l1(const b2h_l1_t& d, int dtype, cudaStream_t s) {
   B2H_LAUNCH_CHECK("l1");
   return B2H_OK;
 }
-int64_t l1_partial_floats(const b2h_l1_t& d) { return (int64_t)ceil_div(d.L, 32) * d.B; }
+int64_t l1_partial_floats(const b2h_l1_t& d) {
+  return (int64_t)ceil_div(d.L, 32) * d.B * ceil_div(d.dout ? d.Cfill : d.C, 32);
+}
 
 // ---------------------------------------------------------------------------------------------
 // MSE on discriminator scores (nn.MSELoss, train_gan.py:93): tiny, one CTA

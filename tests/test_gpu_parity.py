@@ -529,3 +529,31 @@ def test_generator_step_other_regression_losses(loss, precision):
             if p.grad is not None:
                 assert grads_close(tr.g_store.g(k).cpu(), p.grad, gtol), (k, flips)
             check_adam_params(tr.g_store.p(k).cpu(), p, lr, k, tight=flips == 0)
+
+
+def test_persistent_inference_kernels_match_the_one_tile_kernels(monkeypatch):
+    """Batched inference (>= 32768 frames; ragged batch: 520 = 4 x 128 + 8 clips) on the same weights and inputs:
+    (a) persistent tap-GEMM + TMA-store epilogues + the output layer writing NCL itself, (b) the same with the classic
+    output layer (fp32 BLC + to_ncl), (c) the one-tile-per-CTA kernels.  (b) and (c) run the same tiles, descriptors and
+    epilogue arithmetic: every bit agrees.  (a) contracts the output layer tap by tap instead of chunk by chunk (its
+    tiles are not tap-merged), so it agrees to fp32 summation order."""
+    from b2h_b200 import _lib as L
+    from b2h_b200 import nets
+    torch.manual_seed(0)
+    B, T = 520, 64
+    spec = nets.generator_spec("v1", 36, 252, False, train=False)
+    store = nets.ParamStore(spec, "cuda", seed=3)
+    x = torch.randn(B, 36, T, device="cuda")
+    outs = []
+    for env in ({}, {"B2H_NO_NCL_DIRECT": "1"}, {"B2H_NO_NCL_DIRECT": "1", "B2H_NO_PERSIST": "1"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        plan = nets.NetPlan(spec, store, B, T, L.BF16, "cuda", train=False)
+        assert plan.ncl_direct is (not env)
+        plan.x.copy_(x)
+        plan.forward()
+        torch.cuda.synchronize()
+        outs.append(plan.out.clone())
+    assert torch.isfinite(outs[0]).all() and float(outs[0].abs().max()) > 0
+    assert torch.equal(outs[1], outs[2])
+    assert rel_err(outs[0], outs[2]) <= 2e-6
