@@ -46,7 +46,7 @@ struct PersistCfg {
   static constexpr int BOX_BYTES = 128 * 128;
   static constexpr int STAGING_BYTES = 4 * BOX_BYTES;
   static constexpr int MAIN_BYTES = RING_BYTES + STAGING_BYTES;
-  static constexpr int SMEM_BYTES = MAIN_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = MAIN_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 3 * PBN * 4 /*bias | scale | shift*/;
   static_assert(RING_BYTES % 1024 == 0 && SMEM_BYTES <= 232448, "shared memory budget");
 };
 
@@ -86,6 +86,10 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
   uint64_t* tmem_full = a_empty + 2;       // [2] accumulator slot written
   uint64_t* tmem_empty = tmem_full + 2;    // [2] accumulator slot drained (one arrival per epilogue warp)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  // bias / folded-BN scale / shift of the tile's 256 columns (bf16 tiles: reloaded when the column offset changes)
+  float* s_bias = reinterpret_cast<float*>(smem + PC::MAIN_BYTES + 256);
+  float* s_scale = s_bias + PBN;
+  float* s_shift = s_scale + PBN;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kpt = p.Kc / TC_BK;
@@ -208,7 +212,7 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
     const int chalf = (warp - 2) >> 2;
     const int et = threadIdx.x - 64;   // 0..255
     const int r = sub * 32 + lane;     // tile row == TMEM lane
-    int it = 0;
+    int it = 0, s_nn0 = -1;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
       const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
       const int bt = mt / p.n_lchunks, lc = mt - bt * p.n_lchunks;
@@ -228,6 +232,10 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
         const int tl = p.tl;
 #pragma unroll 1
         for (int round = 0; round < 2; ++round) {
+          if (round == 0 && nn0 != s_nn0) {            // (all warps are past the previous tile's arithmetic)
+            s_bias[et] = e.bias[nn0 + et];
+            s_nn0 = nn0;
+          }
           if (et == 0) tma_store_wait_read();          // the previous round's boxes have left the staging buffer
           asm volatile("bar.sync 1, 256;" ::: "memory");
           if (round == 0) {
@@ -245,7 +253,7 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
             float* col0 = reinterpret_cast<float*>(staging + box * PC::BOX_BYTES) + (size_t)(bi * 32) * tl + li;
 #pragma unroll
             for (int j = 0; j < 32; ++j)   // [clip][channel][frame]: the lanes of a warp are consecutive frames
-              col0[(size_t)j * tl] = __uint_as_float(acc[j]) + __ldg(e.bias + nn0 + c + j);
+              col0[(size_t)j * tl] = __uint_as_float(acc[j]) + s_bias[c + j];
           }
           if (round == 1) {   // every TMEM read of this tile is done: hand the slot back to the MMA warp
             tc_fence_before();
@@ -266,6 +274,12 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
         continue;
       }
       if (TMA_OUT) {
+        // (every epilogue warp is past the previous tile's arithmetic here: its bar.sync before the TMA issue)
+        if (nn0 != s_nn0) {
+          if (epi_has_bias(KIND)) s_bias[et] = e.bias[nn0 + et];
+          if (epi_has_bn(KIND)) s_scale[et] = e.post_scale[nn0 + et], s_shift[et] = e.post_shift[nn0 + et];
+          s_nn0 = nn0;
+        }
         // the staging buffer is free once the previous tile's TMA stores have read it
         if (et == 0) tma_store_wait_read();
         asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -284,7 +298,10 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
         for (int j = 0; j < 32; j += 8) {
           if (c + j >= valid_cols) break;
           float v[8];
-          epi_global8<KIND>(e, nn0 + c + j, acc + j, v);
+          if (TMA_OUT)
+            epi_fast8<KIND>(s_bias, s_scale, s_shift, nullptr, c + j, nn0 + c + j, acc + j, v);
+          else
+            epi_global8<KIND>(e, nn0 + c + j, acc + j, v);
           if (TMA_OUT) {
             // box = 64 channels; 16-byte chunk g of row r sits at chunk g ^ (r & 7) of its 128-byte line (128B swizzle)
             const int col = c + j;
