@@ -145,6 +145,14 @@ typedef struct {
                            statistics of the output, exactly as b2h_bn_stats(&stats) right after this op would
                            (on the tensor-core path inside the GEMM epilogue, without re-reading `out`) */
   b2h_bwd_sums_t bwd_sums; /* optional (bwd_sums.z != NULL), dgrad ops: see b2h_bwd_sums_t */
+  /* Residual add in the epilogue (bf16 mode, eval plans of a batched inference; runs the persistent 256-column kernel:
+   * nphase = 1, Npad % 256 == 0, no statistics): out[row] = epi(...)[row] + resid[row], both [B][Lo_actual][ld] in the
+   * activation dtype.  resid_up2 = 1: this layer's result is up-sampled x2 (nearest) on the way -- GEMM row l produces
+   * the output rows 2l and 2l+1, out[2l+k] = epi(...)[l] + resid[2l+k]; out and resid have 2*Lo_actual rows per sample.
+   * (modelZoo.py:262-270: the skip connections of the decoder) */
+  const void* resid;
+  int32_t ld_resid;
+  int32_t resid_up2;
 } b2h_gemm_t;
 
 /* wgrad: dW[m][n][t] = sum_{b,r} P[b, r, m] * Q[b, r*stride + tap_off[t], n]   (PyTorch weight layout)

@@ -17,6 +17,8 @@ struct EpiParams {
   int act, out_f32;
   int drop_C;
   b2h_dropout_t drop;
+  const void* resid;   // residual add (persistent kernel only, see b2h_gemm_t)
+  int ld_resid, resid_up2;
 };
 
 inline EpiParams make_epi(const b2h_gemm_t& d) {
@@ -36,6 +38,9 @@ inline EpiParams make_epi(const b2h_gemm_t& d) {
   e.out_f32 = d.out_f32;
   e.drop_C = d.drop_C;
   e.drop = d.drop;
+  e.resid = d.resid;
+  e.ld_resid = d.ld_resid;
+  e.resid_up2 = d.resid_up2;
   return e;
 }
 

@@ -273,6 +273,9 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
         }
         continue;
       }
+      const int n_rounds = (TMA_OUT && e.resid && e.resid_up2) ? 2 : 1;   // up2: output rows 2l (round 0) and 2l+1 (round 1)
+#pragma unroll 1
+      for (int rnd = 0; rnd < n_rounds; ++rnd) {
       if (TMA_OUT) {
         // (every epilogue warp is past the previous tile's arithmetic here: its bar.sync before the TMA issue)
         if (nn0 != s_nn0) {
@@ -284,8 +287,15 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
         if (et == 0) tma_store_wait_read();
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
-      mbar_wait(&tmem_full[slot], (it >> 1) & 1);
-      tc_fence_after();
+      if (rnd == 0) {
+        mbar_wait(&tmem_full[slot], (it >> 1) & 1);
+        tc_fence_after();
+      }
+      // residual row of this thread's output row (this round's, when up-sampling)
+      const __nv_bfloat16* rrow = nullptr;
+      if (TMA_OUT && e.resid && row_in)
+        rrow = reinterpret_cast<const __nv_bfloat16*>(e.resid) +
+               (e.resid_up2 ? ((int64_t)b * 2 * e.Lo_actual + 2 * lo + rnd) : grow) * e.ld_resid + nn0;
       constexpr int CH = PBN / 2;  // columns per epilogue warp
 #pragma unroll 1
       for (int c = chalf * CH; c < (chalf + 1) * CH; c += 32) {
@@ -305,6 +315,15 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
           if (TMA_OUT) {
             // box = 64 channels; 16-byte chunk g of row r sits at chunk g ^ (r & 7) of its 128-byte line (128B swizzle)
             const int col = c + j;
+            if (rrow) {
+              const uint4 rq = *reinterpret_cast<const uint4*>(rrow + col);
+              const uint32_t rw[4] = {rq.x, rq.y, rq.z, rq.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float2 rf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rw[k]));
+                v[2 * k] += rf.x, v[2 * k + 1] += rf.y;
+              }
+            }
             __nv_bfloat162 q0 = __floats2bfloat162_rn(v[0], v[1]), q1 = __floats2bfloat162_rn(v[2], v[3]);
             __nv_bfloat162 q2 = __floats2bfloat162_rn(v[4], v[5]), q3 = __floats2bfloat162_rn(v[6], v[7]);
             uint4 u;
@@ -329,15 +348,16 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
           }
         }
       }
-      // this warp has read its part of the slot: hand it back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[slot]);
+      if (rnd == n_rounds - 1) {   // this warp has read its part of the slot: hand it back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[slot]);
+      }
       if (TMA_OUT) {
         fence_proxy_async_smem();   // the staged tile: generic-proxy writes -> async-proxy (TMA) reads
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (et == 0 && !(dbg & 1)) {
-          const CUtensorMap* mo = ph ? &tmO1 : &tmO0;
+          const CUtensorMap* mo = (n_rounds == 2 ? rnd : ph) ? &tmO1 : &tmO0;
 #pragma unroll
           for (int bx = 0; bx < 4; ++bx) {
             if (bx * 64 < valid_cols) {
@@ -350,6 +370,7 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
           tma_store_commit();
         }
       }
+      }   // rounds
     }
     if ((TMA_OUT || NCL) && et == 0) tma_store_wait_all();
   }

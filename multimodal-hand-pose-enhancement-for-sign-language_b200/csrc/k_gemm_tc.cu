@@ -781,6 +781,11 @@ int plan_gemm_tc(const b2h_gemm_t& d, TcGemmPlan* plan, int esz) {
   int order[B2H_MAX_TAPS];
   for (int t = 0; t < d.ntaps; ++t) order[t] = t;
   std::sort(order, order + d.ntaps, [&](int a, int b) { return d.tap_off[a] < d.tap_off[b]; });
+  const bool resid = d.resid != nullptr;   // residual add in the epilogue: the persistent 256-column kernel only
+  B2H_CHECK_ARG(!resid || (esz == 2 && d.nphase == 1 && d.out_coff == 0 && d.Npad % 256 == 0 && !d.out_f32 &&
+                           d.Lo_actual == d.Lo && d.ld_resid % 8 == 0 && ((uintptr_t)d.resid % 16) == 0 &&
+                           d.drop.mode == B2H_DROP_NONE && !d.stats.z && !d.bwd_sums.z),
+                B2H_ERR_ARG, "gemm: a residual needs bf16 operands, one phase, Npad %% 256 == 0, no statistics / dropout");
   bool run = d.stride == 1 && d.ntaps >= 2 && !ncl && !getenv("B2H_NO_TAP_MERGE");
   for (int t = 1; t < d.ntaps && run; ++t) run = d.tap_off[order[t]] == d.tap_off[order[t - 1]] + 1;
   if (run) {
@@ -853,8 +858,8 @@ int plan_gemm_tc(const b2h_gemm_t& d, TcGemmPlan* plan, int esz) {
       best_bn = bn;
     }
   }
-  if (ncl) best_bn = 256;
-  if (const char* f = getenv("B2H_FORCE_BN"); f && !ncl) {  // tuning aid
+  if (ncl || resid) best_bn = 256;
+  if (const char* f = getenv("B2H_FORCE_BN"); f && !ncl && !resid) {  // tuning aid
     int bn = atoi(f);
     if ((bn == 64 || bn == 128 || bn == 256) && bn <= bn_max && half % bn == 0) best_bn = bn;
   }
@@ -865,7 +870,7 @@ int plan_gemm_tc(const b2h_gemm_t& d, TcGemmPlan* plan, int esz) {
   plan->epi = epi_kind(d);
   // CTA pairs (cta_group::2) for the 256-column bf16 tile: two neighbouring M tiles share one MMA of M = 256, each
   // CTA stages half of the B tile.  An odd tile count is padded with a CTA whose rows are all outside the tensor.
-  plan->pair = (esz == 2 && best_bn == 256 && m_tiles >= 2 && !ncl && pair_mode_enabled()) ? 1 : 0;
+  plan->pair = (esz == 2 && best_bn == 256 && m_tiles >= 2 && !ncl && !resid && pair_mode_enabled()) ? 1 : 0;
   plan->grid_x = plan->pair ? (m_tiles + 1) / 2 * 2 : m_tiles;
   plan->grid_y = d.Npad / best_bn;
   // launches of more than one wave of 256-column tiles with a plain epilogue (batched inference): persistent CTAs
@@ -881,24 +886,32 @@ int plan_gemm_tc(const b2h_gemm_t& d, TcGemmPlan* plan, int esz) {
     if (rc) return rc;
     plan->tmO1 = plan->tmO0;
   }
+  if (resid) {
+    B2H_CHECK_ARG(persist_supports_epilogue(plan->epi) && plan->epi != EPI_BIAS_F32, B2H_ERR_ARG,
+                  "gemm: a residual needs one of the specialised bf16 epilogues (bias + activation [+ folded BN])");
+    plan->persist = 1;
+  }
   if (plan->persist && !d.out_f32) {
     // output tensor maps of the TMA-store epilogue: one per sub-pixel phase (rows ph, ph + nphase, ...), boxes of 64
-    // channels x the M tile in the tile's own row order; channels >= Nvalid and rows outside the tensor are clipped
+    // channels x the M tile in the tile's own row order; channels >= Nvalid and rows outside the tensor are clipped.
+    // (resid_up2: the two "phases" are the even / odd output rows that GEMM row l is written to)
+    const int ophases = (resid && d.resid_up2) ? 2 : d.nphase;
+    const int orows = (resid && d.resid_up2) ? 2 * d.Lo_actual : d.Lo_actual;
     const __nv_bfloat16* o = reinterpret_cast<const __nv_bfloat16*>(d.out) + d.out_coff;
-    for (int ph = 0; ph < d.nphase && !rc; ++ph) {
+    for (int ph = 0; ph < ophases && !rc; ++ph) {
       CUtensorMap* mo = ph ? &plan->tmO1 : &plan->tmO0;
-      const int rows = std::min(d.Lo, (d.Lo_actual - ph + d.nphase - 1) / d.nphase);
+      const int rows = std::min(d.Lo, (orows - ph + ophases - 1) / ophases);
       if (rows <= 0) {   // a phase without rows (one-row outputs): not a multi-wave shape anyway
         plan->persist = 0;
         break;
       }
-      const int64_t row_pitch = (int64_t)d.nphase * d.ldo, sample_pitch = (int64_t)d.Lo_actual * d.ldo;
+      const int64_t row_pitch = (int64_t)ophases * d.ldo, sample_pitch = (int64_t)orows * d.ldo;
       if (p.merged)
         rc = make_map_3d(mo, o + (int64_t)ph * d.ldo, d.Nvalid, d.B, rows, sample_pitch, row_pitch, 64, p.tb, p.tl, 1, 2);
       else
         rc = make_map_3d(mo, o + (int64_t)ph * d.ldo, d.Nvalid, rows, d.B, row_pitch, sample_pitch, 64, p.tl, p.tb, 1, 2);
     }
-    if (d.nphase == 1) plan->tmO1 = plan->tmO0;
+    if (ophases == 1) plan->tmO1 = plan->tmO0;
     if (rc) return rc;
   }
   rc = make_map_2d(&plan->tmB, d.W, (int64_t)d.ntaps * d.Kc, d.Npad, (int64_t)d.ntaps * d.Kc, bke,

@@ -561,6 +561,35 @@ class NetPlan:
                         if (len(c.feeds) == 1 and f.rowmap == L.ROW_IDENT and f.dst_coff == 0 and pl.cout == c.cin and
                                 c.La == pb.Lz and self.bufs[c.name].Kc == pb.Cp):
                             self.eval_alias[c.name] = pl
+        # batched inference (bf16, >= NCL_DIRECT_MIN_ROWS frames): the additions of the skip connections move into the
+        # epilogue of the LATER producer (b2h_gemm_t.resid): a consumer fed by two BN layers over all its columns --
+        # the later one (its only consumer; identity rows or x2 up-sampling) and an earlier one (identity rows, stored
+        # normalised: eval_y) -- gets its input written by the later producer's GEMM: BN(z_later) [up-sampled] + y_earlier.
+        self.eval_resid: Dict[str, tuple] = {}      # later producer name -> (consumer, earlier producer, up2)
+        self.eval_resid_consumers = set()
+        big = (not self.train and self.groups == 1 and self.dtype == L.BF16 and spec.input_kind == "x" and
+               B * self.bufs[ol.name].Lz >= NCL_DIRECT_MIN_ROWS and not _os.environ.get("B2H_NO_EVAL_RESID") and
+               not _os.environ.get("B2H_NO_EVAL_FUSE"))
+        if big:
+            order = {l.name: i for i, l in enumerate(spec.layers)}
+            for c in spec.layers:
+                if len(c.feeds) != 2 or not all(isinstance(f.src, Layer) and f.src.bn and f.dst_coff == 0 and
+                                                f.src.cout == c.cin for f in c.feeds):
+                    continue
+                fl, fe = sorted(c.feeds, key=lambda f: -order[f.src.name])      # later, earlier producer
+                pl, pe = fl.src, fe.src
+                pb, eb, cb = self.bufs[pl.name], self.bufs[pe.name], self.bufs[c.name]
+                up2 = fl.rowmap == L.ROW_UP2
+                ok = (pl is not pe and len(self.consumers[pl.name]) == 1 and pl.kind != "convT" and
+                      pl.name not in self.eval_fused and pl.name not in self.eval_y and
+                      (fl.rowmap == L.ROW_IDENT or up2) and fe.rowmap == L.ROW_IDENT and
+                      pb.Lz * (2 if up2 else 1) == c.La and eb.Lz == c.La and
+                      pb.Cp == eb.Cp == cb.Kc and pb.Cp % 256 == 0 and pe.name not in self.eval_fused)
+                if not ok:
+                    continue
+                self.eval_resid[pl.name] = (c, pe, up2)
+                self.eval_resid_consumers.add(c.name)
+                self.eval_y[pe.name] = True      # (a single-consumer earlier producer stores BN(z) as well)
         with P.segment("fwd"):
             for l in spec.layers:
                 self._emit_input(l)
@@ -745,6 +774,8 @@ class NetPlan:
             return   # the producer's GEMM epilogue wrote BN(z) into lb.a
         if l.name in self.eval_alias:
             return   # the producer's buffer holds BN(z) and IS this layer's GEMM operand
+        if l.name in self.eval_resid_consumers:
+            return   # the later producer's GEMM epilogue wrote BN(z_later) + y_earlier into lb.a
         # BN outputs of producer layers (+ residual / up-sampling / pooling), then this block's dropout
         cuts = sorted({f.dst_coff for f in l.feeds} | {f.dst_coff + f.src.cout for f in l.feeds})
         assert cuts[0] == 0 and cuts[-1] == l.cin, (l.name, cuts, l.cin)
@@ -780,6 +811,11 @@ class NetPlan:
         if l.name in self.eval_fused:
             cb = self.bufs[self.eval_fused[l.name].name]
             common.update(out=cb.a, ldo=cb.Kc, post_scale=lb.scale, post_shift=lb.shift)
+        elif l.name in self.eval_resid:
+            c, pe, up2 = self.eval_resid[l.name]
+            cb, eb = self.bufs[c.name], self.bufs[pe.name]
+            common.update(out=cb.a, ldo=cb.Kc, post_scale=lb.scale, post_shift=lb.shift, resid=eb.z, ld_resid=eb.Cp,
+                          resid_up2=1 if up2 else 0)
         elif l.name in self.eval_y:
             common.update(post_scale=lb.scale, post_shift=lb.shift)   # lb.z holds BN(z) from here on
         if l.kind == "convT":

@@ -82,7 +82,8 @@ def gemm(f: Dict):
         out2 = torch.zeros(B, Lact, Nv)
     else:
         ldo = out.shape[-1]
-        out2 = out.reshape(B, Lact, ldo)
+        up2 = bool(f.get("resid_up2")) and f.get("resid") is not None
+        out2 = out.reshape(B, Lact * (2 if up2 else 1), ldo)
         assert ldo == f["ldo"]
     for ph in range(nph):
         v = acc[:, :, ph * half: ph * half + Nv]
@@ -102,6 +103,15 @@ def gemm(f: Dict):
             nn = min(Nv, C)
             v = v.clone()
             v[:, :, :nn] = v[:, :, :nn] * m[:, :, :nn]
+        if f.get("resid") is not None:   # residual add in the epilogue (b2h_gemm_t.resid), optionally after x2 up-sampling
+            assert nph == 1 and f["out_coff"] == 0 and not ncl
+            rs = f["resid"].to(torch.float32).reshape(B, -1, f["ld_resid"])[:, :, :Nv]
+            if f.get("resid_up2"):
+                for k in range(2):
+                    out2[:, 2 * ra + k, :Nv] = (v + rs[:, 2 * ra + k]).to(out.dtype)
+            else:
+                out2[:, ra, :Nv] = (v + rs[:, ra]).to(out.dtype)
+            continue
         out2[:, ra, f["out_coff"]: f["out_coff"] + Nv] = v.to(out.dtype)
     if ncl:
         out.copy_(out2.permute(0, 2, 1))

@@ -226,6 +226,11 @@ def test_batched_inference_plan_writes_ncl_from_the_output_layer(monkeypatch):
         store.load_state_dict(G.state_dict())
         plan = nets.NetPlan(spec, store, B, T, L.BF16, "cpu", train=False)
         assert plan.ncl_direct is direct
+        # the additions of the skip connections ride in the later producer's epilogue (b2h_gemm_t.resid), once with the
+        # x2 up-sampling of that producer's rows: only the pooled input of conv5 keeps its bn_apply pass
+        assert sorted(u for _, _, u in plan.eval_resid.values()) == [False, True]
+        s0, e0 = plan.prog.segments["fwd"]
+        assert [r.tag for r in plan.prog.recs[s0:e0] if r.kind == L.OP_BN_APPLY] == [f"apply.conv5[0:{plan.bufs['conv5'].Kc}]"]
         kinds = [r.kind for r in plan.prog.recs]
         assert (L.OP_TO_NCL in kinds) is (not direct)
         out_rec = [r for r in plan.prog.recs if r.kind == L.OP_GEMM and r.f["out_f32"]][-1]
