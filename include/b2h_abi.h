@@ -153,6 +153,10 @@ typedef struct {
   const void* resid;
   int32_t ld_resid;
   int32_t resid_up2;
+  /* MaxPool1d(2) in the epilogue (same kernel, same restrictions; modelZoo.py:197 between the encoder and conv5):
+   * out[l'] = max(epi(...)[2l'], epi(...)[2l'+1]) for l' < Lo_actual / 2 -- `out` has Lo_actual / 2 rows per sample. */
+  int32_t out_pool2;
+  int32_t reserved1;
 } b2h_gemm_t;
 
 /* wgrad: dW[m][n][t] = sum_{b,r} P[b, r, m] * Q[b, r*stride + tap_off[t], n]   (PyTorch weight layout)

@@ -48,7 +48,8 @@ class Gemm(C.Structure):
                 ("Kc", i32), ("Npad", i32), ("Nvalid", i32), ("ntaps", i32), ("stride", i32),
                 ("tap_off", i32 * MAX_TAPS), ("nphase", i32), ("Lo_actual", i32), ("act", i32),
                 ("post_scale", vp), ("post_shift", vp), ("out_f32", i32), ("drop", Dropout), ("drop_C", i32),
-                ("stats", BnStats), ("bwd_sums", BwdSums), ("resid", vp), ("ld_resid", i32), ("resid_up2", i32)]
+                ("stats", BnStats), ("bwd_sums", BwdSums), ("resid", vp), ("ld_resid", i32), ("resid_up2", i32),
+                ("out_pool2", i32), ("reserved1", i32)]
 
 
 class Wgrad(C.Structure):

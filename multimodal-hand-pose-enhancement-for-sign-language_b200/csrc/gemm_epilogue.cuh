@@ -18,7 +18,7 @@ struct EpiParams {
   int drop_C;
   b2h_dropout_t drop;
   const void* resid;   // residual add (persistent kernel only, see b2h_gemm_t)
-  int ld_resid, resid_up2;
+  int ld_resid, resid_up2, out_pool2;
 };
 
 inline EpiParams make_epi(const b2h_gemm_t& d) {
@@ -41,6 +41,7 @@ inline EpiParams make_epi(const b2h_gemm_t& d) {
   e.resid = d.resid;
   e.ld_resid = d.ld_resid;
   e.resid_up2 = d.resid_up2;
+  e.out_pool2 = d.out_pool2;
   return e;
 }
 

@@ -315,6 +315,13 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
           if (TMA_OUT) {
             // box = 64 channels; 16-byte chunk g of row r sits at chunk g ^ (r & 7) of its 128-byte line (128B swizzle)
             const int col = c + j;
+            if (e.out_pool2) {
+              // MaxPool1d(2): the partner frame of this thread's row sits in the same warp (lane ^ 1 in clip-major
+              // tiles, lane ^ tb in the tap-merged (frame, clip) order with tb <= 16)
+              const int pm = MERGED ? p.tb : 1;
+#pragma unroll
+              for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], __shfl_xor_sync(0xffffffffu, v[k], pm));
+            }
             if (rrow) {
               const uint4 rq = *reinterpret_cast<const uint4*>(rrow + col);
               const uint32_t rw[4] = {rq.x, rq.y, rq.z, rq.w};
@@ -331,8 +338,16 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
             u.y = *reinterpret_cast<uint32_t*>(&q1);
             u.z = *reinterpret_cast<uint32_t*>(&q2);
             u.w = *reinterpret_cast<uint32_t*>(&q3);
-            uint8_t* dst = staging + (col >> 6) * PC::BOX_BYTES + r * 128 + ((((col & 63) >> 3) ^ (r & 7)) << 4);
-            *reinterpret_cast<uint4*>(dst) = u;
+            if (e.out_pool2) {
+              if ((li & 1) == 0) {   // even frames carry the pair's maximum to row (frame / 2) of the half-height box
+                const int rp = MERGED ? ((li >> 1) * p.tb + bi) : (bi * (p.tl >> 1) + (li >> 1));
+                uint8_t* dst = staging + (col >> 6) * PC::BOX_BYTES + rp * 128 + ((((col & 63) >> 3) ^ (rp & 7)) << 4);
+                *reinterpret_cast<uint4*>(dst) = u;
+              }
+            } else {
+              uint8_t* dst = staging + (col >> 6) * PC::BOX_BYTES + r * 128 + ((((col & 63) >> 3) ^ (r & 7)) << 4);
+              *reinterpret_cast<uint4*>(dst) = u;
+            }
           } else {
             const int nv = min(8, valid_cols - (c + j));
             if ((dbg & 1) && v[0] != 123456.f) continue;   // (keeps the arithmetic alive)
@@ -361,10 +376,11 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
 #pragma unroll
           for (int bx = 0; bx < 4; ++bx) {
             if (bx * 64 < valid_cols) {
+              const int lrow = e.out_pool2 ? (l0 >> 1) : l0;   // (pooled output: half the rows)
               if (MERGED)   // output maps of a merged plan are (C, B, L) like its A operand
-                tma_store_3d(mo, staging + bx * PC::BOX_BYTES, nn0 + bx * 64, b0, l0);
+                tma_store_3d(mo, staging + bx * PC::BOX_BYTES, nn0 + bx * 64, b0, lrow);
               else
-                tma_store_3d(mo, staging + bx * PC::BOX_BYTES, nn0 + bx * 64, l0, b0);
+                tma_store_3d(mo, staging + bx * PC::BOX_BYTES, nn0 + bx * 64, lrow, b0);
             }
           }
           tma_store_commit();

@@ -781,9 +781,11 @@ int plan_gemm_tc(const b2h_gemm_t& d, TcGemmPlan* plan, int esz) {
   int order[B2H_MAX_TAPS];
   for (int t = 0; t < d.ntaps; ++t) order[t] = t;
   std::sort(order, order + d.ntaps, [&](int a, int b) { return d.tap_off[a] < d.tap_off[b]; });
-  const bool resid = d.resid != nullptr;   // residual add in the epilogue: the persistent 256-column kernel only
+  const bool pool2 = d.out_pool2 != 0;     // MaxPool1d(2) in the epilogue: the persistent 256-column kernel only
+  const bool resid = d.resid != nullptr || pool2;   // residual add in the epilogue: likewise
+  B2H_CHECK_ARG(!(pool2 && d.resid), B2H_ERR_ARG, "gemm: out_pool2 and resid exclude each other");
   B2H_CHECK_ARG(!resid || (esz == 2 && d.nphase == 1 && d.out_coff == 0 && d.Npad % 256 == 0 && !d.out_f32 &&
-                           d.Lo_actual == d.Lo && d.ld_resid % 8 == 0 && ((uintptr_t)d.resid % 16) == 0 &&
+                           d.Lo_actual == d.Lo && (pool2 || (d.ld_resid % 8 == 0 && ((uintptr_t)d.resid % 16) == 0)) &&
                            d.drop.mode == B2H_DROP_NONE && !d.stats.z && !d.bwd_sums.z),
                 B2H_ERR_ARG, "gemm: a residual needs bf16 operands, one phase, Npad %% 256 == 0, no statistics / dropout");
   bool run = d.stride == 1 && d.ntaps >= 2 && !ncl && !getenv("B2H_NO_TAP_MERGE");
@@ -886,6 +888,9 @@ int plan_gemm_tc(const b2h_gemm_t& d, TcGemmPlan* plan, int esz) {
     if (rc) return rc;
     plan->tmO1 = plan->tmO0;
   }
+  if (pool2)   // pairs of rows of one clip must sit in one warp: tile rows (frame, clip) with <= 16 clips, or clip-major
+    B2H_CHECK_ARG(p.tl >= 2 && (!p.merged || p.tb <= 16) && d.Lo_actual >= 2, B2H_ERR_SHAPE,
+                  "gemm: out_pool2 needs >= 2 frames per tile and clip (tl=%d tb=%d merged=%d)", p.tl, p.tb, p.merged);
   if (resid) {
     B2H_CHECK_ARG(persist_supports_epilogue(plan->epi) && plan->epi != EPI_BIAS_F32, B2H_ERR_ARG,
                   "gemm: a residual needs one of the specialised bf16 epilogues (bias + activation [+ folded BN])");
@@ -895,21 +900,23 @@ int plan_gemm_tc(const b2h_gemm_t& d, TcGemmPlan* plan, int esz) {
     // output tensor maps of the TMA-store epilogue: one per sub-pixel phase (rows ph, ph + nphase, ...), boxes of 64
     // channels x the M tile in the tile's own row order; channels >= Nvalid and rows outside the tensor are clipped.
     // (resid_up2: the two "phases" are the even / odd output rows that GEMM row l is written to)
-    const int ophases = (resid && d.resid_up2) ? 2 : d.nphase;
-    const int orows = (resid && d.resid_up2) ? 2 * d.Lo_actual : d.Lo_actual;
+    const int ophases = (d.resid && d.resid_up2) ? 2 : d.nphase;
+    const int orows = (d.resid && d.resid_up2) ? 2 * d.Lo_actual : (pool2 ? d.Lo_actual / 2 : d.Lo_actual);
     const __nv_bfloat16* o = reinterpret_cast<const __nv_bfloat16*>(d.out) + d.out_coff;
     for (int ph = 0; ph < ophases && !rc; ++ph) {
       CUtensorMap* mo = ph ? &plan->tmO1 : &plan->tmO0;
       const int rows = std::min(d.Lo, (orows - ph + ophases - 1) / ophases);
+      // (pooled output: the box holds half the tile's rows, pairs of one clip merged)
+      const int obox_l = pool2 ? p.tl / 2 : p.tl;
       if (rows <= 0) {   // a phase without rows (one-row outputs): not a multi-wave shape anyway
         plan->persist = 0;
         break;
       }
       const int64_t row_pitch = (int64_t)ophases * d.ldo, sample_pitch = (int64_t)orows * d.ldo;
       if (p.merged)
-        rc = make_map_3d(mo, o + (int64_t)ph * d.ldo, d.Nvalid, d.B, rows, sample_pitch, row_pitch, 64, p.tb, p.tl, 1, 2);
+        rc = make_map_3d(mo, o + (int64_t)ph * d.ldo, d.Nvalid, d.B, rows, sample_pitch, row_pitch, 64, p.tb, obox_l, 1, 2);
       else
-        rc = make_map_3d(mo, o + (int64_t)ph * d.ldo, d.Nvalid, rows, d.B, row_pitch, sample_pitch, 64, p.tl, p.tb, 1, 2);
+        rc = make_map_3d(mo, o + (int64_t)ph * d.ldo, d.Nvalid, rows, d.B, row_pitch, sample_pitch, 64, obox_l, p.tb, 1, 2);
     }
     if (ophases == 1) plan->tmO1 = plan->tmO0;
     if (rc) return rc;

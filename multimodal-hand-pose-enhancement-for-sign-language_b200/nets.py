@@ -565,6 +565,7 @@ class NetPlan:
         # epilogue of the LATER producer (b2h_gemm_t.resid): a consumer fed by two BN layers over all its columns --
         # the later one (its only consumer; identity rows or x2 up-sampling) and an earlier one (identity rows, stored
         # normalised: eval_y) -- gets its input written by the later producer's GEMM: BN(z_later) [up-sampled] + y_earlier.
+        self.eval_pool: Dict[str, Layer] = {}       # producer name -> its only consumer, fed through MaxPool1d(2)
         self.eval_resid: Dict[str, tuple] = {}      # later producer name -> (consumer, earlier producer, up2)
         self.eval_resid_consumers = set()
         big = (not self.train and self.groups == 1 and self.dtype == L.BF16 and spec.input_kind == "x" and
@@ -590,6 +591,19 @@ class NetPlan:
                 self.eval_resid[pl.name] = (c, pe, up2)
                 self.eval_resid_consumers.add(c.name)
                 self.eval_y[pe.name] = True      # (a single-consumer earlier producer stores BN(z) as well)
+            # MaxPool1d(2) between a BN layer and its only consumer (encoder -> conv5): pooled in the producer's epilogue
+            # (b2h_gemm_t.out_pool2), which writes the consumer's half-length input directly
+            for pl in spec.layers:
+                cons = self.consumers[pl.name]
+                if not (pl.bn and len(cons) == 1 and pl.kind != "convT" and pl.name not in self.eval_fused and
+                        pl.name not in self.eval_y and pl.name not in self.eval_resid):
+                    continue
+                c, f = cons[0]
+                pb, cb = self.bufs[pl.name], self.bufs[c.name]
+                if (len(c.feeds) == 1 and f.rowmap == L.ROW_POOL2 and f.dst_coff == 0 and pl.cout == c.cin and
+                        pb.Lz % 2 == 0 and pb.Lz // 2 == c.La and pb.Cp == cb.Kc and pb.Cp % 256 == 0 and pb.Lz >= 16):
+                    self.eval_pool[pl.name] = c
+                    self.eval_resid_consumers.add(c.name)
         with P.segment("fwd"):
             for l in spec.layers:
                 self._emit_input(l)
@@ -816,6 +830,9 @@ class NetPlan:
             cb, eb = self.bufs[c.name], self.bufs[pe.name]
             common.update(out=cb.a, ldo=cb.Kc, post_scale=lb.scale, post_shift=lb.shift, resid=eb.z, ld_resid=eb.Cp,
                           resid_up2=1 if up2 else 0)
+        elif l.name in self.eval_pool:
+            cb = self.bufs[self.eval_pool[l.name].name]
+            common.update(out=cb.a, ldo=cb.Kc, post_scale=lb.scale, post_shift=lb.shift, out_pool2=1)
         elif l.name in self.eval_y:
             common.update(post_scale=lb.scale, post_shift=lb.shift)   # lb.z holds BN(z) from here on
         if l.kind == "convT":

@@ -83,7 +83,7 @@ def gemm(f: Dict):
     else:
         ldo = out.shape[-1]
         up2 = bool(f.get("resid_up2")) and f.get("resid") is not None
-        out2 = out.reshape(B, Lact * (2 if up2 else 1), ldo)
+        out2 = None if f.get("out_pool2") else out.reshape(B, Lact * (2 if up2 else 1), ldo)
         assert ldo == f["ldo"]
     for ph in range(nph):
         v = acc[:, :, ph * half: ph * half + Nv]
@@ -103,6 +103,14 @@ def gemm(f: Dict):
             nn = min(Nv, C)
             v = v.clone()
             v[:, :, :nn] = v[:, :, :nn] * m[:, :, :nn]
+        if f.get("out_pool2"):           # MaxPool1d(2) in the epilogue: out has Lo_actual // 2 rows per sample
+            assert nph == 1 and f["out_coff"] == 0 and not ncl and f.get("resid") is None
+            Lh = Lact // 2
+            full = torch.zeros(B, Lact, Nv)
+            full[:, ra] = v
+            pooled = torch.maximum(full[:, 0:2 * Lh:2], full[:, 1:2 * Lh:2])
+            out.reshape(B, Lh, ldo)[:, :, :Nv] = pooled.to(out.dtype)
+            continue
         if f.get("resid") is not None:   # residual add in the epilogue (b2h_gemm_t.resid), optionally after x2 up-sampling
             assert nph == 1 and f["out_coff"] == 0 and not ncl
             rs = f["resid"].to(torch.float32).reshape(B, -1, f["ld_resid"])[:, :, :Nv]
