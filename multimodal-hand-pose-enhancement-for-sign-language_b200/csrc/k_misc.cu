@@ -64,6 +64,64 @@ __global__ void __launch_bounds__(256) prep_ncl_kernel(b2h_prep_t d) {
   }
 }
 
+// The same op for sources whose rows are 16-byte aligned (source length % 4 == 0; Cfill, ld % 8 == 0): one CTA = 64
+// source frames x 32 channels of one clip; every thread requests its two float4 of the source (channel t/8, 4
+// consecutive frames, + 32 frames) before anything else, the tile is transposed through shared memory (pitch 33:
+// conflict-free both ways), and a thread writes 8 channels of one frame (16 B in bf16) with ONE Philox call for its
+// 8 keep flags (the scalar kernel spends one call per 4).  Same values, same flags.
+template <typename T>
+__global__ void __launch_bounds__(256) prep_ncl_vec_kernel(b2h_prep_t d) {
+  pdl_sync();
+  __shared__ float tile[64][33];
+  const int t = threadIdx.x;
+  const int b = blockIdx.z, l0 = blockIdx.x * 64, c0 = blockIdx.y * 32;
+  const bool motion = d.kind == B2H_SRC_MOTION;
+  const int Ls = motion ? d.L + 1 : d.L;
+  const int ch = c0 + (t >> 3), f4 = (t & 7) * 4;
+  const float* src = d.src + ((int64_t)b * d.C + ch) * Ls;
+  float4 x[2];
+  float first = 0.f;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int l = l0 + f4 + 32 * h;
+    x[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ch < d.C && l < Ls) x[h] = *reinterpret_cast<const float4*>(src + l);
+  }
+  if (motion && ch < d.C) first = src[0];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int f = f4 + 32 * h;
+    // x[:, :, :1] - x[:, :, :-1]  (train_gan.py:210); frames past the end hold zeros and are never written out
+    tile[f + 0][t >> 3] = motion ? first - x[h].x : x[h].x;
+    tile[f + 1][t >> 3] = motion ? first - x[h].y : x[h].y;
+    tile[f + 2][t >> 3] = motion ? first - x[h].z : x[h].z;
+    tile[f + 3][t >> 3] = motion ? first - x[h].w : x[h].w;
+  }
+  __syncthreads();
+  const int r = t >> 2, c8 = (t & 3) * 8;
+  const int l = l0 + r, c = c0 + c8;
+  if (l >= d.L || c >= d.Cfill) return;
+  const int64_t row = (int64_t)b * d.L + l;
+  F8 v;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) v.v[k] = (c + k < d.C) ? tile[r][c8 + k] : 0.f;
+  if (c < d.C) {
+    DropCtx drop;
+    drop.init(d.drop, d.C);
+    if (drop.mode != B2H_DROP_NONE) {
+      const uint32_t bits = drop.keep8_rc((uint32_t)row, (uint32_t)c);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v.v[k] *= ((bits >> k) & 1u) ? 2.f : 0.f;
+      drop.save8((uint64_t)row * d.C + c, bits, min(8, d.C - c));
+    }
+  }
+  const int64_t o = row * d.ld + c;
+  if (d.out_f32)
+    store8<float>(reinterpret_cast<float*>(d.out) + o, v);
+  else
+    store8<T>(reinterpret_cast<T*>(d.out) + o, v);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) prep_rows_kernel(b2h_prep_t d) {
   pdl_sync();
@@ -119,6 +177,21 @@ int launch_prep(const b2h_prep_t& d, int dtype, cudaStream_t s) {
   if (d.kind == B2H_SRC_NCL || d.kind == B2H_SRC_MOTION) {
     B2H_CHECK_ARG(d.B <= 65535, B2H_ERR_SHAPE, "prep: B too large for grid.z");
     B2H_CHECK_ARG(d.Cfill % 4 == 0 && d.ld % 4 == 0, B2H_ERR_ALIGN, "prep: Cfill/ld must be multiples of 4");
+    static const bool no_vec = getenv("B2H_NO_PREP_VEC") != nullptr;
+    const int Ls = d.kind == B2H_SRC_MOTION ? d.L + 1 : d.L;
+    const int esz_out = (d.out_f32 || dtype != B2H_BF16) ? 4 : 2;
+    if (!no_vec && Ls % 4 == 0 && d.Cfill % 8 == 0 && d.ld % 8 == 0 && (uintptr_t)d.src % 16 == 0 &&
+        (uintptr_t)d.out % 16 == 0 && esz_out * d.ld % 16 == 0) {
+      B2H_CARVE(prep_ncl_vec_kernel<__nv_bfloat16>);
+      B2H_CARVE(prep_ncl_vec_kernel<float>);
+      dim3 vgrid(ceil_div(d.L, 64), ceil_div(d.Cfill, 32), d.B);
+      if (dtype == B2H_BF16)
+        launch(prep_ncl_vec_kernel<__nv_bfloat16>, vgrid, 256, 0, s, d);
+      else
+        launch(prep_ncl_vec_kernel<float>, vgrid, 256, 0, s, d);
+      B2H_LAUNCH_CHECK("prep");
+      return B2H_OK;
+    }
     dim3 grid(ceil_div(d.L, 32), ceil_div(d.Cfill, 32), d.B), block(32, 8);
     if (dtype == B2H_BF16)
       launch(prep_ncl_kernel<__nv_bfloat16>, grid, block, 0, s, d);
@@ -297,6 +370,146 @@ __global__ void __launch_bounds__(256) l1_kernel(b2h_l1_t d, int cext, int spc) 
   if (tid == 0) d.loss[0] = (float)(s_part[0] / (double)numel + (d.kind == B2H_LOSS_ROBUST ? 0.22579135264472743 : 0.0));
 }
 
+// one element of the criterion: adds its loss term to acc, returns d loss / d out (see b2h_l1_t)
+__device__ __forceinline__ float loss_elem(int kind, float diff, float gval, float& acc) {
+  if (kind == B2H_LOSS_L1) {
+    acc += fabsf(diff);
+    return diff > 0.f ? gval : (diff < 0.f ? -gval : 0.f);  // sign(diff)/numel, sign(0) = 0
+  }
+  if (kind == B2H_LOSS_HUBER1) {                            // nn.HuberLoss(delta = 1)
+    const float a = fabsf(diff);
+    acc += a < 1.f ? 0.5f * diff * diff : a - 0.5f;
+    return fminf(fmaxf(diff, -1.f), 1.f) * gval;
+  }
+  const float w = kind == B2H_LOSS_ROBUST ? 2.f : 1.f;      // L2: d^2 ; ROBUST (alpha 2, scale 1/2): 2 d^2
+  acc += w * diff * diff;
+  return 2.f * w * diff * gval;
+}
+
+// The generator step's form of the criterion (prediction given as the output layer's fp32 BLC rows, L % 4 == 0):
+// one CTA = 64 frames x 32 channels of one clip, every global access 16 bytes wide and all four loads of a thread
+// (2 x prediction rows, 2 x target rows = 64 B) issued before the first use.
+//   load   thread (row = t/8 [+32], 4 channels)  : out_blc rows, 128 B per row and warp quarter
+//          thread (channel = t/8, 4 frames [+32]): gt (NCL), 128 B per channel and warp quarter
+//   pass 1 prediction tile -> shared [frame][channel] (pitch 33: conflict-free both ways)
+//   pass 2 in NCL orientation: out (NCL, the tensor the reference returns) written as float4, loss terms, gradient
+//          -> shared [frame][channel]; column sums of the gradient as stored (bias gradient of the output layer):
+//          8 lanes share a channel -> shuffle -> one fp64 atomic per channel and CTA
+//   pass 3 gradient rows out: thread = 8 channels of one frame (16 B in bf16)
+template <typename T>
+__global__ void __launch_bounds__(256) l1_vec_kernel(b2h_l1_t d, int cext) {
+  pdl_sync();
+  __shared__ float tile_o[64][33];
+  __shared__ float tile_g[64][33];
+  __shared__ double s_part[256];
+  const int t = threadIdx.x;
+  const int l0 = blockIdx.x * 64, b = blockIdx.y, c0 = blockIdx.z * 32;
+  const int64_t numel = (int64_t)d.B * d.C * d.L;
+  const float gval = d.gscale / (float)numel;
+  const uint32_t nblocks = gridDim.x * gridDim.y * gridDim.z;
+  const uint32_t bid = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  // ---- loads
+  const int orow = t >> 3, oc = c0 + (t & 7) * 4;          // prediction: rows orow, orow + 32; channels oc..oc+3
+  const int gch = c0 + (t >> 3), gf = (t & 7) * 4;          // target: channel gch; frames l0 + gf + 32 h
+  float4 o4[2], g4[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int l = l0 + orow + 32 * h;
+    o4[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (l < d.L && oc < d.out_blc_ld)
+      o4[h] = *reinterpret_cast<const float4*>(d.out_blc + ((int64_t)b * d.L + l) * d.out_blc_ld + oc);
+  }
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int l = l0 + gf + 32 * h;
+    g4[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gch < d.C && l < d.L) g4[h] = *reinterpret_cast<const float4*>(d.gt + ((int64_t)b * d.C + gch) * d.L + l);
+  }
+  // ---- pass 1
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    float* row = tile_o[orow + 32 * h] + (t & 7) * 4;
+    row[0] = o4[h].x, row[1] = o4[h].y, row[2] = o4[h].z, row[3] = o4[h].w;
+  }
+  __syncthreads();
+  // ---- pass 2
+  float acc = 0.f, csum = 0.f;
+  const int cl = t >> 3;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int f = gf + 32 * h, l = l0 + f;
+    const bool in = gch < d.C && l < d.L;
+    const float o[4] = {tile_o[f][cl], tile_o[f + 1][cl], tile_o[f + 2][cl], tile_o[f + 3][cl]};
+    const float g[4] = {g4[h].x, g4[h].y, g4[h].z, g4[h].w};
+    float sg[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      sg[k] = in ? loss_elem(d.kind, o[k] - g[k], gval, acc) : 0.f;
+      csum += to_f<T>(from_f<T>(sg[k]));
+      tile_g[f + k][cl] = sg[k];
+    }
+    if (in)
+      *reinterpret_cast<float4*>(const_cast<float*>(d.out) + ((int64_t)b * d.C + gch) * d.L + l) =
+          make_float4(o[0], o[1], o[2], o[3]);
+  }
+  if (d.dbias) {
+    csum += __shfl_xor_sync(0xffffffffu, csum, 1);
+    csum += __shfl_xor_sync(0xffffffffu, csum, 2);
+    csum += __shfl_xor_sync(0xffffffffu, csum, 4);
+    if ((t & 7) == 0 && gch < d.C) atomicAdd(d.dbias_accum + (int64_t)(bid % 16) * d.C + gch, (double)csum);
+  }
+  __syncthreads();
+  // ---- pass 3
+  if (d.dout) {
+    const int r = t >> 2, c8 = (t & 3) * 8, l = l0 + r;
+    if (l < d.L && c0 + c8 < cext) {
+      F8 v;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v.v[k] = tile_g[r][c8 + k];
+      store8<T>(reinterpret_cast<T*>(d.dout) + ((int64_t)b * d.L + l) * d.ld + c0 + c8, v);
+    }
+  }
+  // ---- loss: CTA sum -> partial -> the last CTA sums the partials in fixed order (and finishes the bias gradient)
+  s_part[t] = (double)acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (t < o) s_part[t] += s_part[t + o];
+    __syncthreads();
+  }
+  if (t == 0) d.partial[bid] = (float)s_part[0];
+  if (!last_block_done(d.ticket, nblocks)) return;
+  if (d.dbias) {
+    for (int c = t; c < d.C; c += 256) {
+      double tt = 0.0;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        double* a = d.dbias_accum + (int64_t)k * d.C + c;
+        tt += __ldcg(a);
+        *a = 0.0;
+      }
+      d.dbias[c] = (float)tt;
+    }
+  }
+  double tt = 0.0;
+  for (uint32_t k = t; k < nblocks; k += 256) tt += (double)__ldcg(d.partial + k);
+  __syncthreads();
+  s_part[t] = tt;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (t < o) s_part[t] += s_part[t + o];
+    __syncthreads();
+  }
+  if (t == 0) d.loss[0] = (float)(s_part[0] / (double)numel + (d.kind == B2H_LOSS_ROBUST ? 0.22579135264472743 : 0.0));
+}
+
+// the vectorised form needs: the prediction as BLC rows, 16-byte aligned rows on both sides, a gradient to write
+static bool l1_vec_ok(const b2h_l1_t& d, int cext) {
+  static const bool off = getenv("B2H_NO_L1_VEC") != nullptr;
+  return !off && d.out_blc && d.dout && d.L % 4 == 0 && d.out_blc_ld % 4 == 0 && cext % 8 == 0 && d.ld % 8 == 0 &&
+         ((uintptr_t)d.out_blc % 16 == 0) && ((uintptr_t)d.gt % 16 == 0) && ((uintptr_t)d.out % 16 == 0) &&
+         ((uintptr_t)d.dout % 16 == 0);
+}
+
 int launch_l1(const b2h_l1_t& d, int dtype, cudaStream_t s) {
   B2H_CARVE(l1_kernel<__nv_bfloat16>);
   B2H_CARVE(l1_kernel<float>);
@@ -307,6 +520,17 @@ int launch_l1(const b2h_l1_t& d, int dtype, cudaStream_t s) {
   B2H_CHECK_ARG(!d.dbias || (d.dout && d.dbias_accum), B2H_ERR_ARG, "l1: dbias needs dout and its workspace");
   B2H_CHECK_ARG(!d.dbias || d.C <= 1024, B2H_ERR_SHAPE, "l1: dbias supports up to 1024 channels");
   int cext = d.dout ? d.Cfill : d.C;
+  if (l1_vec_ok(d, cext)) {
+    B2H_CARVE(l1_vec_kernel<__nv_bfloat16>);
+    B2H_CARVE(l1_vec_kernel<float>);
+    dim3 grid(ceil_div(d.L, 64), d.B, ceil_div(cext, 32));
+    if (dtype == B2H_BF16)
+      launch(l1_vec_kernel<__nv_bfloat16>, grid, 256, 0, s, d, cext);
+    else
+      launch(l1_vec_kernel<float>, grid, 256, 0, s, d, cext);
+    B2H_LAUNCH_CHECK("l1");
+    return B2H_OK;
+  }
   const int spc = 1;   // clips per CTA (more than one was measured slower: the kernel is latency-bound per CTA)
   dim3 grid(ceil_div(d.L, 32), d.B / spc, ceil_div(cext, 32)), block(32, 8);
   if (dtype == B2H_BF16)
@@ -398,7 +622,22 @@ __global__ void adam_step_kernel(b2h_adam_t d) {
   d.scalars[1] = (float)sqrt(bc2);         // bias_correction2_sqrt
 }
 
-__global__ void __launch_bounds__(256) adam_kernel(b2h_adam_t d) {
+// one element of torch's _single_tensor_adam, in its operation order
+__device__ __forceinline__ void adam_elem(float& p, float g, float& m, float& v, float gs, float w1, float w2, float b2,
+                                          float bc2_sqrt, float eps, float neg_step) {
+  const float gk = g * gs;
+  const float mk = m + w1 * (gk - m);                  // exp_avg.lerp_(grad, 1 - beta1)
+  const float vk = v * b2 + (w2 * gk) * gk;            // mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+  const float denom = sqrtf(vk) / bc2_sqrt + eps;      // (sqrt(v) / sqrt(bc2)).add_(eps)
+  p += (neg_step * mk) / denom;                        // addcdiv_(exp_avg, denom, value=-step_size)
+  m = mk;
+  v = vk;
+}
+
+// Thread = two float4 of each array per trip (the second one half a grid away), all eight loads issued before the
+// first use; the components are named, not indexed (an indexed float4 lives in local memory: the round-1 kernel had a
+// 64-byte stack frame and a store / reload per array on its dependency chain).
+__global__ void __launch_bounds__(256, 4) adam_kernel(b2h_adam_t d) {
   pdl_sync();
   const float neg_step = d.scalars[0];
   const float bc2_sqrt = d.scalars[1];
@@ -406,33 +645,33 @@ __global__ void __launch_bounds__(256) adam_kernel(b2h_adam_t d) {
   const float b2 = (float)d.beta2, eps = (float)d.eps, gs = d.gscale;
   const int64_t n4 = d.n / 4;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-    float4 p = reinterpret_cast<float4*>(d.p)[i];
-    float4 g = reinterpret_cast<const float4*>(d.g)[i];
-    float4 m = reinterpret_cast<float4*>(d.m)[i];
-    float4 v = reinterpret_cast<float4*>(d.v)[i];
-#pragma unroll 2
-    for (int k = 0; k < 4; ++k) {
-      float gk = f4(g, k) * gs;
-      float mk = f4(m, k) + w1 * (gk - f4(m, k));         // exp_avg.lerp_(grad, 1 - beta1)
-      float vk = f4(v, k) * b2 + (w2 * gk) * gk;          // mul_(beta2).addcmul_(grad, grad, 1 - beta2)
-      float denom = sqrtf(vk) / bc2_sqrt + eps;           // (sqrt(v) / sqrt(bc2)).add_(eps)
-      f4(p, k) += (neg_step * mk) / denom;                // addcdiv_(exp_avg, denom, value=-step_size)
-      f4(m, k) = mk;
-      f4(v, k) = vk;
+  float4* P4 = reinterpret_cast<float4*>(d.p);
+  float4* M4 = reinterpret_cast<float4*>(d.m);
+  float4* V4 = reinterpret_cast<float4*>(d.v);
+  const float4* G4 = reinterpret_cast<const float4*>(d.g);
+#define B2H_ADAM4(P, G, M, V)                                                  \
+  adam_elem(P.x, G.x, M.x, V.x, gs, w1, w2, b2, bc2_sqrt, eps, neg_step);      \
+  adam_elem(P.y, G.y, M.y, V.y, gs, w1, w2, b2, bc2_sqrt, eps, neg_step);      \
+  adam_elem(P.z, G.z, M.z, V.z, gs, w1, w2, b2, bc2_sqrt, eps, neg_step);      \
+  adam_elem(P.w, G.w, M.w, V.w, gs, w1, w2, b2, bc2_sqrt, eps, neg_step);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += 2 * stride) {
+    const int64_t j = i + stride;
+    const bool two = j < n4;
+    float4 p0 = P4[i], g0 = G4[i], m0 = M4[i], v0 = V4[i];
+    float4 p1 = p0, g1 = g0, m1 = m0, v1 = v0;
+    if (two) p1 = P4[j], g1 = G4[j], m1 = M4[j], v1 = V4[j];
+    B2H_ADAM4(p0, g0, m0, v0)
+    P4[i] = p0, M4[i] = m0, V4[i] = v0;
+    if (two) {
+      B2H_ADAM4(p1, g1, m1, v1)
+      P4[j] = p1, M4[j] = m1, V4[j] = v1;
     }
-    reinterpret_cast<float4*>(d.p)[i] = p;
-    reinterpret_cast<float4*>(d.m)[i] = m;
-    reinterpret_cast<float4*>(d.v)[i] = v;
   }
+#undef B2H_ADAM4
   for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < d.n; i += stride) {
-    float gk = d.g[i] * gs;
-    float mk = d.m[i] + w1 * (gk - d.m[i]);
-    float vk = d.v[i] * b2 + (w2 * gk) * gk;
-    float denom = sqrtf(vk) / bc2_sqrt + eps;
-    d.p[i] += (neg_step * mk) / denom;
-    d.m[i] = mk;
-    d.v[i] = vk;
+    float p = d.p[i], m = d.m[i], v = d.v[i];
+    adam_elem(p, d.g[i], m, v, gs, w1, w2, b2, bc2_sqrt, eps, neg_step);
+    d.p[i] = p, d.m[i] = m, d.v[i] = v;
   }
 }
 
@@ -449,7 +688,8 @@ int launch_adam(const b2h_adam_t& d, cudaStream_t s) {
   B2H_CHECK_ARG(((uintptr_t)d.p % 16 == 0) && ((uintptr_t)d.g % 16 == 0) && ((uintptr_t)d.m % 16 == 0) &&
                     ((uintptr_t)d.v % 16 == 0),
                 B2H_ERR_ALIGN, "adam: buffers must be 16-byte aligned");
-  int blocks = (int)std::min<int64_t>(ceil_div64(d.n / 4 + 1, 256), (int64_t)sm_count() * 8);
+  // 4 resident CTAs per SM (64 registers), two float4 of each array per thread and trip: 128 KB in flight per SM
+  int blocks = (int)std::min<int64_t>(ceil_div64(d.n / 8 + 1, 256), (int64_t)sm_count() * 4);
   launch(adam_kernel, blocks, 256, 0, s, d);
   B2H_LAUNCH_CHECK("adam");
   return B2H_OK;

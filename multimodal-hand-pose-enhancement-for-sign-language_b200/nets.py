@@ -11,6 +11,7 @@ Reference citations: modelZoo.py:6-166 (b2h), :169-328 (v1), :331-440 (v2), :443
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple, Union
 
@@ -338,7 +339,9 @@ class LayerBufs:
     ain_C: int = 0                # valid channels of `a`
 
 
-NCL_DIRECT_MIN_ROWS = 32768   # frames per eval forward from which the output layer writes NCL itself (see NetPlan)
+# frames per eval forward from which the output layer writes NCL itself and the skip additions / the pooling ride in
+# the GEMM epilogues (see NetPlan); B2H_NCL_DIRECT_MIN_ROWS overrides it (tuning aid)
+NCL_DIRECT_MIN_ROWS = int(os.environ.get("B2H_NCL_DIRECT_MIN_ROWS", "16384"))
 
 
 class NetPlan:
