@@ -226,6 +226,14 @@ typedef struct {
   uint32_t* ticket;
   double* accum;  /* optional: the first-pass sums were already accumulated here by the GEMMs that produced the
                      gradient sources (b2h_gemm_t.bwd_sums); the op then runs its second pass only and re-zeroes it */
+  int32_t defer;  /* 1 (needs `accum` and `dpre`): the op only writes dpre -- no reduction, no ticket, no serial tail on
+                     the dependency chain of the backward pass.  dgamma / dbeta / dbias and the re-zeroing of `accum`
+                     are left to a b2h_colsum over dpre with `bn_accum` = this accum, which only feeds the optimizer
+                     and can run beside the chain.  dgamma / dbeta / dbias / sums / partial / ticket are ignored */
+  int32_t first_pass_only; /* 1 (needs `accum`, dpre == NULL): accumulate sum(dy), sum(dy*zhat) of the given gradient
+                     sources into `accum` and stop -- the contribution of a consumer whose dgrad GEMM cannot carry
+                     b2h_gemm_t.bwd_sums for this layer (it serves another producer), run beside the chain as soon as
+                     that gradient exists */
 } b2h_bn_bwd_t;
 
 /* ------------------------------------------------------------------------------------------- */
@@ -301,6 +309,13 @@ typedef struct {
   float* partial;
   uint32_t* ticket;
   int32_t rows, ld, C, f32;
+  /* optional: finish a deferred BatchNorm backward (b2h_bn_bwd_t.defer) -- src = its dpre, out = the bias gradient;
+   * the last CTA also sums the first-pass accumulators [B2H_BWD_COPIES][bn_groups][C][2] in fixed order,
+   * writes dbeta[c] = sum dy, dgamma[c] = sum dy*zhat (over the groups) and re-zeroes them */
+  double* bn_accum;
+  float* dgamma;
+  float* dbeta;
+  int32_t bn_groups, reserved0;
 } b2h_colsum_t;
 
 /* torch.optim.Adam(lr, betas=(0.9,0.999), eps=1e-8, weight_decay=0) (train_gan.py:69,88) over a

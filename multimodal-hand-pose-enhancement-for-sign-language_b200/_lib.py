@@ -78,7 +78,7 @@ class BnBwd(C.Structure):
     _fields_ = [("gsrc", GradSrc * 2), ("ngsrc", i32), ("bn", BnSrc), ("dpre", vp),
                 ("ld_dpre", i32), ("Cfill", i32), ("B", i32), ("L", i32), ("C", i32), ("groups", i32),
                 ("act", i32), ("dgamma", vp), ("dbeta", vp), ("dbias", vp), ("sums", vp), ("partial", vp),
-                ("ticket", vp), ("accum", vp)]
+                ("ticket", vp), ("accum", vp), ("defer", i32), ("first_pass_only", i32)]
 
 
 class Prep(C.Structure):
@@ -104,7 +104,8 @@ class Mse(C.Structure):
 
 class Colsum(C.Structure):
     _fields_ = [("src", vp), ("out", vp), ("partial", vp), ("ticket", vp),
-                ("rows", i32), ("ld", i32), ("C", i32), ("f32", i32)]
+                ("rows", i32), ("ld", i32), ("C", i32), ("f32", i32),
+                ("bn_accum", vp), ("dgamma", vp), ("dbeta", vp), ("bn_groups", i32), ("reserved0", i32)]
 
 
 class Adam(C.Structure):

@@ -504,6 +504,7 @@ __global__ void __launch_bounds__(kRowThreads, 2) bn_bwd_kernel(b2h_bn_bwd_t d) 
       }
     }
   }
+  if (PASS == 2 && d.defer) return;   // dpre is all this launch owes the chain; b2h_colsum(bn_accum) finishes the rest
   block_sum8(s_red, acc_a, tx, ty, TXp, TY);
   if (PASS == 1) block_sum8(s_red, acc_b, tx, ty, TXp, TY);
   if (ty == 0 && c0 < d.C) {
@@ -607,6 +608,16 @@ static int launch_bn_bwd_passes(const b2h_bn_bwd_t& d, int dtype, int first_pass
 }
 
 int launch_bn_bwd(const b2h_bn_bwd_t& d, int dtype, cudaStream_t s) {
+  B2H_CHECK_ARG(!d.defer || (d.accum && d.dpre && !d.first_pass_only), B2H_ERR_ARG,
+                "bn_bwd: defer needs the first-pass accumulators and dpre");
+  B2H_CHECK_ARG(!d.first_pass_only || (d.accum && !d.dpre), B2H_ERR_ARG,
+                "bn_bwd: first_pass_only accumulates into `accum` and writes no dpre");
+  if (d.first_pass_only) {
+    b2h_bn_bwd_t f = d;
+    f.partial = reinterpret_cast<float*>(d.accum);   // (unused by the first pass when accum is given)
+    f.ld_dpre = 8;
+    return launch_bn_bwd_passes(f, dtype, 1, 1, s);
+  }
   // with `accum` the first pass was produced by the GEMMs that wrote the gradient sources
   return launch_bn_bwd_passes(d, dtype, d.accum ? 2 : 1, 2, s);
 }
@@ -684,6 +695,23 @@ __global__ void __launch_bounds__(kRowThreads) colsum_kernel(b2h_colsum_t d) {
       accum[(int64_t)k * d.C + c] = 0.0;
     }
     d.out[c] = (float)t;
+    if (d.bn_accum) {   // deferred BatchNorm backward: dbeta / dgamma from the first-pass sums, accumulators re-zeroed
+      double tot_a = 0.0, tot_b = 0.0;
+#pragma unroll 1
+      for (int gg = 0; gg < d.bn_groups; ++gg) {
+        double ta = 0.0, tb = 0.0;
+#pragma unroll
+        for (int k = 0; k < B2H_BWD_COPIES; ++k) {   // fixed order over the copies, as bn_bwd's own tail
+          double2* acc = reinterpret_cast<double2*>(d.bn_accum + (((int64_t)k * d.bn_groups + gg) * d.C + c) * 2);
+          const double2 v = __ldcg(acc);
+          *acc = make_double2(0.0, 0.0);
+          ta += v.x, tb += v.y;
+        }
+        tot_a += ta, tot_b += tb;
+      }
+      if (d.dbeta) d.dbeta[c] = (float)tot_a;
+      if (d.dgamma) d.dgamma[c] = (float)tot_b;
+    }
   }
 }
 
@@ -693,6 +721,8 @@ int launch_colsum(const b2h_colsum_t& d, int dtype, cudaStream_t s) {
   B2H_CHECK_ARG(d.C > 0 && d.C <= 512 && d.rows > 0 && d.ld % 8 == 0 && d.ld >= ((d.C + 7) & ~7), B2H_ERR_SHAPE,
                 "colsum: bad shape");
   B2H_CHECK_ARG(((uintptr_t)d.partial % 8) == 0, B2H_ERR_ALIGN, "colsum: workspace must be 8-byte aligned");
+  B2H_CHECK_ARG(!d.bn_accum || (d.bn_groups >= 1 && ((uintptr_t)d.bn_accum % 16) == 0), B2H_ERR_ARG,
+                "colsum: bn_accum needs bn_groups >= 1 and a 16-byte aligned accumulator");
   RowGrid rg = row_grid(d.C, d.rows);
   dim3 grid(rg.ctas), block(rg.txp, rg.ty);
   if (dtype == B2H_BF16 && !d.f32)

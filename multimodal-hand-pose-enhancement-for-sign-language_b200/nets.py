@@ -869,9 +869,9 @@ class NetPlan:
         """Layers whose BN-backward first pass (sum dy, sum dy*zhat) is produced by the dgrad GEMMs of their
         consumers (b2h_gemm_t.bwd_sums).  A dgrad GEMM can serve one producer: its output must be exactly the
         gradient of that producer's BN output (one feed over all columns, IDENT or regular x2 up-sampling)."""
-        import os
         self.dgrad_target: Dict[str, Tuple[Layer, Feed]] = {}
         self.bwd_fused = set()
+        self.bwd_helpers = {}
         if os.environ.get("B2H_NO_FUSED_BWD"):
             return
         cands = [p for p in self.spec.layers if p.bn and p is not self.out_layer and self.consumers[p.name]]
@@ -886,6 +886,34 @@ class NetPlan:
                 continue
             for (c, f) in self.consumers[p.name]:
                 self.dgrad_target[c.name] = (p, f)
+            self.bwd_fused.add(p.name)
+            pb.bwd_accum = torch.zeros(L.BWD_COPIES, self.groups, p.cout, 2, dtype=torch.float64, device=self.device)
+        # Skip connections: a layer with several consumers, some of whose dgrad GEMMs already serve another producer
+        # (skip5's input is skip4 + conv5: its dgrad carries the sums of skip4).  The consumer that comes LAST in the
+        # backward pass carries the sums in its dgrad; every other consumer's share is one first-pass launch over that
+        # consumer's gradient alone (b2h_bn_bwd_t.first_pass_only), emitted right behind its dgrad and run beside the
+        # chain (trainer: side stream) -- long before this layer's own bn_bwd is due, which then runs one pass only.
+        # Opt-in (B2H_BWD_HELPERS=1): measured on the B200 it shortens the chain but not the step -- the step is bound
+        # by the total work of its ~120 small launches, and a helper adds one (0.674 -> 0.690 ms, profiles/ab_r02_bn.log).
+        self.bwd_helpers: Dict[str, List[Tuple[Layer, Feed]]] = {}     # consumer name -> [(producer, feed)]
+        if not os.environ.get("B2H_BWD_HELPERS"):
+            return
+        order = {l.name: i for i, l in enumerate(self.spec.layers)}
+        for p in cands:
+            cons = self.consumers[p.name]
+            if p.name in self.bwd_fused or len(cons) < 2:
+                continue
+            pb = self.bufs[p.name]
+            ok = all(f.dst_coff == 0 and p.cout == c.cin and self.bufs[c.name].Kc == pb.Cp and self._needs_dgrad(c) and
+                     ((f.rowmap == L.ROW_IDENT and c.La == pb.Lz) or (f.rowmap == L.ROW_UP2 and c.La == 2 * pb.Lz))
+                     for (c, f) in cons)
+            last_c, last_f = min(cons, key=lambda cf: order[cf[0].name])   # first in the forward = last in the backward
+            if not ok or last_c.name in self.dgrad_target:
+                continue
+            self.dgrad_target[last_c.name] = (p, last_f)
+            for (c, f) in cons:
+                if c is not last_c:
+                    self.bwd_helpers.setdefault(c.name, []).append((p, f))
             self.bwd_fused.add(p.name)
             pb.bwd_accum = torch.zeros(L.BWD_COPIES, self.groups, p.cout, 2, dtype=torch.float64, device=self.device)
 
@@ -911,12 +939,28 @@ class NetPlan:
             while len(gs) < 2:
                 gs.append({})
             lb.sums = self._zeros(self.groups, l.cout, 2, dtype=torch.float32)
+            fused = l.name in self.bwd_fused
+            # first-pass sums complete in their own accumulator: the chain only needs dpre from this op (defer); the
+            # parameter gradients (dgamma, dbeta, dbias) and the re-zeroing of the accumulator ride with the weight
+            # gradient beside the chain: one b2h_colsum over dpre (bn_accum)
+            # (opt-in, B2H_DEFER_BN=1: bn_bwd drops from 12.5 to 6.5 us per launch, but the extra column-sum launches
+            # cost the step as much as they save -- 0.674 -> 0.679 ms, profiles/ab_r02_bn.log)
+            defer = fused and bool(os.environ.get("B2H_DEFER_BN"))
+            waits = [f"bwd_sums1.{l.name}.{c.name}" for (c, _) in self.consumers[l.name]
+                     if any(p is l for (p, _) in self.bwd_helpers.get(c.name, []))]
             i = P.add(L.OP_BN_BWD, f"bn_bwd.{l.name}", gsrc=gs, ngsrc=len(self.consumers[l.name]),
                       bn=self._bn_src(l), dpre=lb.dpre, ld_dpre=lb.Cp, Cfill=lb.Cp, B=B, L=lb.Lz, C=l.cout,
-                      groups=self.groups, act=l.act, dgamma=st.g(l.bnkey + ".weight"), dbeta=st.g(l.bnkey + ".bias"),
-                      dbias=st.g(l.wkey + ".bias"), sums=lb.sums, partial=None, ticket=self._ticket(),
-                      accum=lb.bwd_accum if l.name in self.bwd_fused else None)
+                      groups=self.groups, act=l.act, dgamma=None if defer else st.g(l.bnkey + ".weight"),
+                      dbeta=None if defer else st.g(l.bnkey + ".bias"),
+                      dbias=None if defer else st.g(l.wkey + ".bias"), sums=None if defer else lb.sums, partial=None,
+                      ticket=self._ticket(), accum=lb.bwd_accum if fused else None, defer=1 if defer else 0,
+                      _wait_tags=waits)
             self._need_partial(i, _bn_partial_floats(rows, l.cout, self.groups))
+            if defer:
+                lb.fin_partial = self._zeros(128 * l.cout * 2, dtype=torch.float32)
+                P.add(L.OP_COLSUM, f"bn_fin.{l.name}", src=lb.dpre, out=st.g(l.wkey + ".bias"), partial=lb.fin_partial,
+                      ticket=self._ticket(), rows=rows, ld=lb.Cp, C=l.cout, f32=0, bn_accum=lb.bwd_accum,
+                      dgamma=st.g(l.bnkey + ".weight"), dbeta=st.g(l.bnkey + ".bias"), bn_groups=self.groups)
         # weight gradient
         k = l.k
         if l.kind == "convT":
@@ -954,6 +998,15 @@ class NetPlan:
             i = P.add(L.OP_GEMM, f"dgrad.{l.name}", Lo=l.La, Npad=lb.Kc, stride=lb.bwd_stride, nphase=1,
                       Lo_actual=l.La, **common)
         self.op_macs[i] = self._layer_macs(l)
+        # this consumer's share of the first-pass sums of producers whose sums another dgrad carries (see
+        # _plan_bwd_fusion): over lb.g alone, into the producer's accumulator
+        for (p, f) in self.bwd_helpers.get(l.name, []):
+            pb = self.bufs[p.name]
+            gs = [{"g": lb.g, "ld": lb.Kc, "coff": f.dst_coff, "rowmap": f.rowmap, "L_src": l.La, "f32": 0}, {}]
+            P.add(L.OP_BN_BWD, f"bwd_sums1.{p.name}.{l.name}", gsrc=gs, ngsrc=1, bn=self._bn_src(p), dpre=None,
+                  ld_dpre=pb.Cp, Cfill=pb.Cp, B=B, L=pb.Lz, C=p.cout, groups=self.groups, act=p.act, dgamma=None,
+                  dbeta=None, dbias=None, sums=None, partial=None, ticket=None, accum=pb.bwd_accum, defer=0,
+                  first_pass_only=1)
 
     # ---- execution ---------------------------------------------------------------------------
     def pack(self):

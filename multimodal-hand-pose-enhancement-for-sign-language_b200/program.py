@@ -19,6 +19,10 @@ import torch
 
 from . import _lib as L
 
+import os as _os
+import re as _re
+_SKIP_RE = _re.compile(_os.environ["B2H_DBG_SKIP_OPS"]) if _os.environ.get("B2H_DBG_SKIP_OPS") else None
+
 
 class OpRec:
     __slots__ = ("kind", "f", "tag")
@@ -134,6 +138,8 @@ class Program:
             return
         if stream is None:
             stream = torch.cuda.current_stream(self.device).cuda_stream
+        if _SKIP_RE is not None:
+            return self._run_skipping(first, end, stream)
         rc = L.load().b2h_program_run(self._handle, first, end - first, C.c_void_p(stream))
         L.check(rc, f"b2h_program_run[{segment}]")
         self.segment_launches[segment or "*"] = self.launches()
@@ -143,8 +149,24 @@ class Program:
             self.finalize()
         if stream is None:
             stream = torch.cuda.current_stream(self.device).cuda_stream
+        if _SKIP_RE is not None:     # timing experiment (B2H_DBG_SKIP_OPS=regex): results are invalid by construction
+            return self._run_skipping(first, end, stream)
         rc = L.load().b2h_program_run(self._handle, first, end - first, C.c_void_p(stream))
         L.check(rc, f"b2h_program_run[{first}:{end}]")
+
+    def _run_skipping(self, first: int, end: int, stream: int):
+        """B2H_DBG_SKIP_OPS: replay [first, end) without the ops whose tag matches -- what would the step cost if those
+        launches were gone?  (tools/skip_exp.sh; never set in a run whose results are used)"""
+        i = first
+        while i < end:
+            if _SKIP_RE.search(self.recs[i].tag):
+                i += 1
+                continue
+            j = i
+            while j < end and not _SKIP_RE.search(self.recs[j].tag):
+                j += 1
+            L.check(L.load().b2h_program_run(self._handle, i, j - i, C.c_void_p(stream)), f"b2h_program_run[{i}:{j}]")
+            i = j
 
     def op_plan(self, idx: int) -> dict:
         """Launch plan of op `idx` as the library built it (b2h_program_op_plan): tile width, split-K, fusions."""

@@ -334,6 +334,7 @@ class GanTrainer:
         self._copy_stream = None
         self._wgrad_streams = {}
         self._wgrad_rr = {}
+        self._helper_events = {}       # first-pass helper launches of the running backward: tag -> event
         self._adv_stream = None
         self._d_stream = None
         self._g_stream = None
@@ -627,18 +628,26 @@ class GanTrainer:
             return []
         key = "d" if plan is self.D_train else "g"
         sides, recs, used, i = self._side_streams_for(plan), plan.prog.recs, [], s
+        helper_ev = self._helper_events.setdefault(key, {})
+
+        def off_chain(rec):
+            # weight gradients, bias-gradient column sums (also the finishing op of a deferred BatchNorm backward) and
+            # the first-pass shares of skip-connection consumers (b2h_bn_bwd_t.first_pass_only): nothing on the
+            # bn_bwd -> dgrad chain reads them before the optimizer / the producer's own bn_bwd
+            return rec.kind in (L.OP_WGRAD, L.OP_COLSUM) or (rec.kind == L.OP_BN_BWD and rec.f.get("first_pass_only"))
+
         while i < e:
-            # weight gradients and the bias gradient of the output layer: off the chain
-            is_w = recs[i].kind in (L.OP_WGRAD, L.OP_COLSUM)
+            is_w = off_chain(recs[i])
             j = i
-            while j < e and (recs[j].kind in (L.OP_WGRAD, L.OP_COLSUM)) == is_w:
+            while j < e and off_chain(recs[j]) == is_w:
                 j += 1
             if is_w:
                 ev = torch.cuda.Event()
-                ev.record(cur)             # dpre of this layer is complete
+                ev.record(cur)             # dpre / the input gradient of this layer is complete
                 for k in range(i, j):
                     # split-K wgrads share the plan's partial-plane workspace: they all go to stream 0, in order;
-                    # the split-free ones (and the bias column sum) own their outputs and rotate over the rest
+                    # the split-free ones (and the column sums / first-pass shares) own their outputs and rotate over
+                    # the rest
                     shared_ws = recs[k].kind == L.OP_WGRAD and not (plan.wgrad_direct and recs[k].f["splits"] == 1)
                     if shared_ws or len(sides) == 1:
                         side = sides[0]
@@ -647,12 +656,25 @@ class GanTrainer:
                         self._wgrad_rr[key] += 1
                     side.wait_event(ev)
                     plan.prog.run_range(k, k + 1, side.cuda_stream)
-                    if side_ops is not None:
+                    if recs[k].kind == L.OP_BN_BWD:     # a later bn_bwd on the chain needs these sums
+                        hev = torch.cuda.Event()
+                        hev.record(side)
+                        helper_ev[recs[k].tag] = hev
+                    elif side_ops is not None:
                         side_ops.append((side, recs[k]))
                     if side not in used:
                         used.append(side)
             else:
-                plan.prog.run_range(i, j, cur.cuda_stream)
+                k0 = i
+                for k in range(i, j):
+                    tags = recs[k].f.get("_wait_tags")
+                    if tags:                # bn_bwd of a skip-connection producer: its helpers' sums must be in
+                        if k > k0:
+                            plan.prog.run_range(k0, k, cur.cuda_stream)
+                        for t in tags:
+                            cur.wait_event(helper_ev.pop(t))
+                        k0 = k
+                plan.prog.run_range(k0, j, cur.cuda_stream)
             i = j
         return used
 

@@ -257,7 +257,7 @@ def bn_bwd(f: Dict):
     bn = f["bn"]
     z = bn["z"].to(torch.float32).reshape(B, L, -1)[:, :, bn["coff"]: bn["coff"] + C]
     Bg = B // G
-    dpre = f["dpre"].reshape(B, L, -1)
+    dpre = f["dpre"].reshape(B, L, -1) if f.get("dpre") is not None else None
     dgamma, dbeta, dbias = torch.zeros(C), torch.zeros(C), torch.zeros(C)
     for g in range(G):
         sl = slice(g * Bg, (g + 1) * Bg)
@@ -274,6 +274,11 @@ def bn_bwd(f: Dict):
         n = Bg * L
         sdy = dy.sum((0, 1))
         sdyz = (dy * zh).sum((0, 1))
+        if f.get("first_pass_only"):     # b2h_bn_bwd_t.first_pass_only: this source's share of the sums, nothing else
+            acc = f["accum"].reshape(-1, G, C, 2)
+            acc[0, g, :, 0] += sdy.double()
+            acc[0, g, :, 1] += sdyz.double()
+            continue
         if f.get("accum") is not None:   # the first-pass sums come from the GEMMs that wrote the sources
             acc = f["accum"].reshape(-1, G, C, 2)
             sdy, sdyz = acc[:, g, :, 0].sum(0).float(), acc[:, g, :, 1].sum(0).float()
@@ -284,6 +289,8 @@ def bn_bwd(f: Dict):
         dgamma += sdyz
         dbeta += sdy
         dbias += dp.sum((0, 1))
+    if f.get("first_pass_only") or f.get("defer"):   # defer: dpre only; b2h_colsum(bn_accum) finishes the op
+        return
     if f.get("accum") is not None:
         f["accum"].zero_()
     if f.get("dgamma") is not None:
@@ -369,6 +376,15 @@ def mse(f: Dict):
 def colsum(f: Dict):
     src = _rows2d(f["src"]).to(torch.float32)[: f["rows"], : f["C"]]
     f["out"].copy_(src.double().sum(0).float())
+    if f.get("bn_accum") is not None:   # finishes a deferred BatchNorm backward (b2h_colsum_t.bn_accum)
+        C = f["C"]
+        acc = f["bn_accum"].reshape(-1, f["bn_groups"], C, 2)
+        tot = acc.sum(0).sum(0)         # copies, then groups
+        if f.get("dbeta") is not None:
+            f["dbeta"].copy_(tot[:, 0].float())
+        if f.get("dgamma") is not None:
+            f["dgamma"].copy_(tot[:, 1].float())
+        f["bn_accum"].zero_()
 
 
 def adam(f: Dict):

@@ -64,6 +64,10 @@ def replay_pair(prog_gpu, prog_cpu, segments, teacher_force=True):
                 fields += [("stats." + fld, rc.f["stats"], rg.f["stats"]) for fld in OUT_FIELDS[L.OP_BN_STATS]]
             if rc.kind == L.OP_GEMM and (rc.f.get("bwd_sums") or {}).get("z") is not None:
                 fields += [("bwd_sums.accum", rc.f["bwd_sums"], rg.f["bwd_sums"])]
+            if rc.kind == L.OP_BN_BWD and rc.f.get("first_pass_only"):
+                fields += [("accum", rc.f, rg.f)]   # one consumer's share of the first-pass sums
+            if rc.kind == L.OP_COLSUM and rc.f.get("bn_accum") is not None:
+                fields += [("dgamma", rc.f, rg.f), ("dbeta", rc.f, rg.f)]   # finishes a deferred BatchNorm backward
             if rc.kind == L.OP_L1 and rc.f.get("out_blc") is not None:
                 fields += [("out", rc.f, rg.f)]     # the loss also writes the NCL prediction (b2h_l1_t.out_blc)
             for fld, fc, fg in fields:

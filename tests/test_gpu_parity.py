@@ -278,6 +278,15 @@ def test_gan_step_vs_oracle_at_the_benched_shape(variant, rf, precision):
     gan_step_case(variant, rf, precision, 256, 64)
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_gan_step_vs_oracle_with_the_opt_in_backward_variants(monkeypatch, precision):
+    """B2H_DEFER_BN / B2H_BWD_HELPERS (b2h_bn_bwd_t.defer + b2h_colsum_t.bn_accum, b2h_bn_bwd_t.first_pass_only): the
+    kernels behind the switches stay under test although the default schedule does not use them."""
+    monkeypatch.setenv("B2H_DEFER_BN", "1")
+    monkeypatch.setenv("B2H_BWD_HELPERS", "1")
+    gan_step_case("v1", False, precision, 32, 64)
+
+
 @pytest.mark.parametrize("precision,tol", [("fp32", FP32_TOL), ("bf16", BF16_TOL)])
 @pytest.mark.parametrize("variant,rf,B,T", [("v1", False, 256, 64), ("v1", False, 64, 1024), ("v1", True, 256, 64),
                                             ("v2", True, 128, 256)])

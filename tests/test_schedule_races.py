@@ -32,7 +32,7 @@ WRITES = {
     L.OP_TO_NCL: {"dst"},
     L.OP_L1: {"loss", "dout", "dbias", "partial", "ticket", "dbias_accum"},
     L.OP_MSE: {"loss", "total", "dscore", "dpre", "dbias"},
-    L.OP_COLSUM: {"out", "partial", "ticket"},
+    L.OP_COLSUM: {"out", "partial", "ticket", "bn_accum", "dgamma", "dbeta"},
     L.OP_ADAM: {"p", "m", "v", "step", "scalars"},
     L.OP_PACK: {"out", "out_bias"},
     L.OP_PACK_MULTI: {"_items[].out", "_items[].out_bias"},
@@ -110,6 +110,13 @@ def accesses(rec):
                         w = True
                     if rec.kind == L.OP_WGRAD and k == "partial" and rec.f.get("splits") == 1:
                         continue                       # split-free form (bf16 plans only): no workspace traffic
+                    if rec.kind == L.OP_BN_BWD and k == "accum" and rec.f.get("defer"):
+                        w = False                      # deferred: reads the sums; b2h_colsum(bn_accum) re-zeroes them
+                    if rec.kind == L.OP_BN_BWD and rec.f.get("first_pass_only") and k in ("partial", "ticket", "sums"):
+                        continue
+                    if ((rec.kind == L.OP_BN_BWD and k == "accum" and rec.f.get("first_pass_only")) or
+                            path == "bwd_sums.accum"):
+                        w = 2                          # fp64 atomic adds: commute with each other, conflict with the rest
                     out.append((v.data_ptr(), v.data_ptr() + v.numel() * v.element_size(), w, path))
             elif isinstance(v, dict):
                 walk(v, path + ".")
@@ -135,7 +142,7 @@ def find_races(log):
     for a, b, w, path, i in items:
         active = [t for t in active if t[1] > a]
         for (a2, b2, w2, path2, j) in active:
-            if i == j or not (w or w2):
+            if i == j or not (w or w2) or (w == 2 and w2 == 2):
                 continue
             first, second = (j, i) if j < i else (i, j)
             s1, c1 = log[first][1], log[first][2]
@@ -230,6 +237,25 @@ def test_sequential_steps_have_no_unordered_conflicts(schedule_log, variant, rf,
         tr._d_step_body()
     assert len(schedule_log) > 200
     assert len({e[1] for e in schedule_log}) >= 4               # dependency chain + wgrad / scoring / optimizer streams
+    races = find_races(schedule_log)
+    assert races == [], "\n".join(map(str, races[:20]))
+
+
+@pytest.mark.parametrize("variant,rf", [("v1", False), ("v4", True)])
+def test_deferred_bn_backward_and_first_pass_helpers_have_no_unordered_conflicts(schedule_log, monkeypatch, variant, rf):
+    """Opt-in backward variants: the finishing column sums and the first-pass shares of the skip connections run on the
+    weight-gradient streams; the producer's bn_bwd waits for its helpers' events."""
+    monkeypatch.setenv("B2H_DEFER_BN", "1")
+    monkeypatch.setenv("B2H_BWD_HELPERS", "1")
+    tr = _trainer(variant, rf)
+    assert any(r.f.get("first_pass_only") for r in tr.G_train.prog.recs if r.kind == L.OP_BN_BWD)
+    assert any(r.f.get("bn_accum") is not None for r in tr.G_train.prog.recs if r.kind == L.OP_COLSUM)
+    tr.G_train.pack()
+    tr.D_train.pack()
+    tr._g_step_body()
+    for _ in range(2):
+        tr._gan_ops(True)
+    tr.flush_adv()
     races = find_races(schedule_log)
     assert races == [], "\n".join(map(str, races[:20]))
 
