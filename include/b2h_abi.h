@@ -157,6 +157,14 @@ typedef struct {
    * out[l'] = max(epi(...)[2l'], epi(...)[2l'+1]) for l' < Lo_actual / 2 -- `out` has Lo_actual / 2 rows per sample. */
   int32_t out_pool2;
   int32_t reserved1;
+  /* dgrad ops of the bf16 tap-GEMM (one tile per CTA): out[row] = epi(...)[row] + grad_add[row] -- the gradient that
+   * ANOTHER consumer of the same tensor has already written (a skip connection: conv5's output feeds conv6 and, added
+   * to skip4's, skip5: modelZoo.py:262-270), [B][Lo_actual][ld_grad_add] in the activation dtype, added in fp32 before
+   * the one rounding of the stored value.  The producer's BatchNorm backward then reads ONE gradient source, and the
+   * sums of b2h_bwd_sums_t (taken from the stored values) cover both consumers. */
+  const void* grad_add;
+  int32_t ld_grad_add;
+  int32_t reserved2;
 } b2h_gemm_t;
 
 /* wgrad: dW[m][n][t] = sum_{b,r} P[b, r, m] * Q[b, r*stride + tap_off[t], n]   (PyTorch weight layout)

@@ -49,7 +49,7 @@ class Gemm(C.Structure):
                 ("tap_off", i32 * MAX_TAPS), ("nphase", i32), ("Lo_actual", i32), ("act", i32),
                 ("post_scale", vp), ("post_shift", vp), ("out_f32", i32), ("drop", Dropout), ("drop_C", i32),
                 ("stats", BnStats), ("bwd_sums", BwdSums), ("resid", vp), ("ld_resid", i32), ("resid_up2", i32),
-                ("out_pool2", i32), ("reserved1", i32)]
+                ("out_pool2", i32), ("reserved1", i32), ("grad_add", vp), ("ld_grad_add", i32), ("reserved2", i32)]
 
 
 class Wgrad(C.Structure):

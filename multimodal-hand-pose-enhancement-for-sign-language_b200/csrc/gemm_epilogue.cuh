@@ -19,6 +19,8 @@ struct EpiParams {
   b2h_dropout_t drop;
   const void* resid;   // residual add (persistent kernel only, see b2h_gemm_t)
   int ld_resid, resid_up2, out_pool2;
+  const void* grad_add;   // dgrad: the gradient another consumer of the same tensor wrote (bf16 one-tile kernel only)
+  int ld_grad_add;
 };
 
 inline EpiParams make_epi(const b2h_gemm_t& d) {
@@ -42,6 +44,8 @@ inline EpiParams make_epi(const b2h_gemm_t& d) {
   e.ld_resid = d.ld_resid;
   e.resid_up2 = d.resid_up2;
   e.out_pool2 = d.out_pool2;
+  e.grad_add = d.grad_add;
+  e.ld_grad_add = d.ld_grad_add;
   return e;
 }
 

@@ -113,6 +113,7 @@ static int check_gemm(const b2h_gemm_t& d) {
   B2H_CHECK_ARG(d.stride == 1 || d.stride == 2, B2H_ERR_SHAPE, "gemm: stride must be 1 or 2");
   B2H_CHECK_ARG(d.out_f32 == 0 || d.out_f32 == 1, B2H_ERR_ARG, "gemm: NCL output (out_f32 = 2) is a bf16-mode feature");
   B2H_CHECK_ARG((d.post_scale == nullptr) == (d.post_shift == nullptr), B2H_ERR_ARG, "gemm: post scale/shift");
+  B2H_CHECK_ARG(!d.grad_add, B2H_ERR_ARG, "gemm: grad_add is a bf16-mode feature");
   return B2H_OK;
 }
 

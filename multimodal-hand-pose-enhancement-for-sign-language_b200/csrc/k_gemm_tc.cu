@@ -39,7 +39,11 @@ using namespace ptx;
 // 256 weight rows), the leader (cluster rank 0) issues the MMAs for both, each CTA's TMEM receives its own 128 x 256
 // accumulator.  The TMA loads of both CTAs count their bytes on the leader's `full` barrier; the leader's
 // tcgen05.commit multicasts to the `empty` / `tmem_full` barriers of both.  See gemm_tc_shared.cuh for what it measured.
-template <int BN, int KIND, int MODE, bool MERGED, bool PAIR = false>
+// GADD (dgrad of a skip connection, b2h_gemm_t.grad_add, KIND = EPI_MASK): every epilogue thread requests its row of the
+// other consumer's gradient BEFORE it waits for the accumulator -- the loads complete under the main loop, the column
+// loop (unrolled: the prefetched chunks are named registers) adds them.  Without it (other kinds) the loads sit inside
+// the column loop, one L2 round trip per 8 columns: measured +8 us per launch.
+template <int BN, int KIND, int MODE, bool MERGED, bool PAIR = false, bool GADD = false>
 __global__ void __launch_bounds__(TC_THREADS, FpropCfg<BN>::OCC)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmZ0,
@@ -269,6 +273,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const uint8_t* mask_row = (KIND == EPI_MASK && row_in) ? e.drop.mask + drop_row_base : nullptr;
       if (KIND == EPI_GENERIC && !row_in) drop.mode = B2H_DROP_NONE;   // never index the mask with a row outside the tensor
       uint8_t* my = stage + (size_t)lane * pitch;
+      constexpr int CH = BN / 2;  // columns per epilogue warp
+      uint4 ga[GADD ? CH / 8 : 1];
+      if (GADD) {
+        const __nv_bfloat16* gp = reinterpret_cast<const __nv_bfloat16*>(e.grad_add) + grow * e.ld_grad_add + nn0 + chalf * CH;
+#pragma unroll
+        for (int q = 0; q < CH / 8; ++q)
+          ga[q] = row_in ? *reinterpret_cast<const uint4*>(gp + q * 8) : make_uint4(0u, 0u, 0u, 0u);
+      }
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
       if (BWDSUM && et == 0) {   // every MMA has retired: the stage buffers are free
@@ -278,9 +290,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         else
           tma_load_3d(zs, ph ? &tmZ1 : &tmZ0, z_bar, nn0, bs.up2 ? (l0 >> 1) : l0, b0);
       }
-      constexpr int CH = BN / 2;  // columns per epilogue warp
-#pragma unroll 1
-      for (int c = chalf * CH; c < (chalf + 1) * CH; c += 32) {
+#pragma unroll(GADD ? CH / 32 : 1)
+      for (int ci = 0; ci < CH / 32; ++ci) {
+        const int c = chalf * CH + ci * 32;
         uint32_t acc[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)c, acc);
         tmem_ld_wait();
@@ -302,6 +314,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             }
           } else {
             epi_fast8<KIND>(s_bias, s_piv, s_shift, nullptr, c + j, nn0 + c + j, acc + j, v);
+          }
+          if (GADD) {
+            // skip connection: the other consumer's gradient of the same tensor (bf16 rows, zero in the channel padding)
+            const uint4 q = ga[ci * 4 + j / 8];
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              v[2 * k] += __uint_as_float(w[k] << 16);
+              v[2 * k + 1] += __uint_as_float(w[k] & 0xFFFF0000u);
+            }
+          } else if ((KIND == EPI_MASK || KIND == EPI_PLAIN || KIND == EPI_GENERIC) && e.grad_add && row_in) {
+            const F8 o = load8<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(e.grad_add) +
+                                              grow * e.ld_grad_add + nn0 + c + j);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] += o.v[k];
           }
           if (KIND == EPI_BIAS_F32 || (KIND == EPI_GENERIC && e.out_f32)) {
             float4* dst = reinterpret_cast<float4*>(my + (size_t)(c + j) * 4);
@@ -788,6 +815,11 @@ int plan_gemm_tc(const b2h_gemm_t& d, TcGemmPlan* plan, int esz) {
                            d.Lo_actual == d.Lo && (pool2 || (d.ld_resid % 8 == 0 && ((uintptr_t)d.resid % 16) == 0)) &&
                            d.drop.mode == B2H_DROP_NONE && !d.stats.z && !d.bwd_sums.z),
                 B2H_ERR_ARG, "gemm: a residual needs bf16 operands, one phase, Npad %% 256 == 0, no statistics / dropout");
+  B2H_CHECK_ARG(!d.grad_add || (esz == 2 && !d.out_f32 && !resid && !ncl && d.out_coff == 0 && !d.bias && !d.post_scale &&
+                                d.act == B2H_ACT_NONE && !d.stats.z && d.ld_grad_add % 8 == 0 &&
+                                d.ld_grad_add >= d.Npad / d.nphase && ((uintptr_t)d.grad_add % 16) == 0),
+                B2H_ERR_ARG, "gemm: grad_add is for bf16 dgrad ops (no bias / activation / statistics, out_coff = 0, "
+                "16-byte aligned rows of at least Npad / nphase channels)");
   bool run = d.stride == 1 && d.ntaps >= 2 && !ncl && !getenv("B2H_NO_TAP_MERGE");
   for (int t = 1; t < d.ntaps && run; ++t) run = d.tap_off[order[t]] == d.tap_off[order[t - 1]] + 1;
   if (run) {
@@ -880,6 +912,7 @@ int plan_gemm_tc(const b2h_gemm_t& d, TcGemmPlan* plan, int esz) {
   plan->persist = (esz == 2 && best_bn == 256 && !plan->pair && !d.stats.z && !d.bwd_sums.z &&
                    (int64_t)plan->grid_x * plan->grid_y > sms && persist_supports_epilogue(plan->epi) &&
                    !getenv("B2H_NO_PERSIST")) ? 1 : 0;
+  if (d.grad_add) plan->persist = 0;   // (the added gradient is read by the one-tile kernel's epilogue)
   if (ncl) {
     // NCL output exists only in the persistent kernel: (T, C, B) fp32 map, boxes of tl frames x 32 channels x tb clips
     plan->persist = 1;
@@ -1053,6 +1086,22 @@ static int launch_fprop_m(const TcGemmPlan& plan, const EpiParams& e, cudaStream
     bs.zbytes = plan.bs_zbytes;
   }
   const bool z = MODE == MODE_BWDSUM;
+  if constexpr (KIND == EPI_MASK && (MODE == MODE_BWDSUM || MODE == MODE_PLAIN)) {
+    if (e.grad_add && !(BN == 256 && plan.pair) && !getenv("B2H_NO_GADD_PREFETCH")) {
+      static bool gattr = false;
+      if (!gattr) {
+        B2H_CARVE(gemm_tc_kernel<BN, KIND, MODE, MERGED, false, true>);
+        cudaError_t er = cudaFuncSetAttribute(gemm_tc_kernel<BN, KIND, MODE, MERGED, false, true>,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        if (er != cudaSuccess) return cuda_fail(er, "gemm_tc (grad_add) smem attribute");
+        gattr = true;
+      }
+      launch(gemm_tc_kernel<BN, KIND, MODE, MERGED, false, true>, grid, TC_THREADS, Cfg::SMEM_BYTES, s, plan.tmA0, plan.tmA1,
+             plan.tmB, z ? plan.tmZ0 : plan.tmA0, z ? plan.tmZ1 : plan.tmA0, plan.p, e, st, bs);
+      B2H_LAUNCH_CHECK("gemm_tc");
+      return B2H_OK;
+    }
+  }
   if (BN == 256 && plan.pair)
     launch_cluster(gemm_tc_kernel<256, KIND, MODE, MERGED, true>, grid, TC_THREADS, FpropCfg<256>::SMEM_BYTES, s, 2u,
                    plan.tmA0, plan.tmA1, plan.tmB, z ? plan.tmZ0 : plan.tmA0, z ? plan.tmZ1 : plan.tmA0, plan.p, e, st, bs);

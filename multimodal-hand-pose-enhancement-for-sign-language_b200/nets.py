@@ -872,19 +872,41 @@ class NetPlan:
         self.dgrad_target: Dict[str, Tuple[Layer, Feed]] = {}
         self.bwd_fused = set()
         self.bwd_helpers = {}
+        self.grad_add: Dict[str, Layer] = {}      # consumer (last in the backward) -> the other consumer of the tensor
+        self.grad_summed: Dict[str, Layer] = {}   # producer -> the consumer whose input gradient holds the whole sum
         if os.environ.get("B2H_NO_FUSED_BWD"):
             return
         cands = [p for p in self.spec.layers if p.bn and p is not self.out_layer and self.consumers[p.name]]
-        for p in sorted(cands, key=lambda q: len(self.consumers[q.name])):   # single-consumer layers first
+        # Skip connections (bf16 plans): a BN layer whose output feeds two consumers row by row (conv5 -> conv6 and,
+        # added to skip4's, -> skip5) receives the sum of two input gradients.  The consumer that comes last in the
+        # backward pass adds the other one's gradient in its dgrad epilogue (b2h_gemm_t.grad_add): the producer's
+        # bn_bwd then reads ONE source, and -- that dgrad being free to carry the sums -- runs one pass instead of two
+        # over two sources (bn_bwd.conv5 / conv6: 18.4 -> 9.8 us each at 256 x 64).
+        if self.dtype == L.BF16 and not os.environ.get("B2H_NO_GRAD_ADD"):
+            order = {l.name: i for i, l in enumerate(self.spec.layers)}
+            for p in cands:
+                cons = self.consumers[p.name]
+                pb = self.bufs[p.name]
+                if len(cons) != 2 or cons[0][0] is cons[1][0]:
+                    continue
+                if not all(f.dst_coff == 0 and f.rowmap == L.ROW_IDENT and p.cout == c.cin and c.La == pb.Lz and
+                           self.bufs[c.name].Kc == pb.Cp and self._needs_dgrad(c) for (c, f) in cons):
+                    continue
+                (c_last, _), (c_first, _) = sorted(cons, key=lambda cf: order[cf[0].name])
+                if c_last.name in self.grad_add:
+                    continue
+                self.grad_add[c_last.name] = c_first
+                self.grad_summed[p.name] = c_last
+        for p in sorted(cands, key=lambda q: len(self._grad_sources(q))):   # single-source layers first
             pb = self.bufs[p.name]
             ok = True
-            for (c, f) in self.consumers[p.name]:
+            for (c, f) in self._grad_sources(p):
                 covers = f.dst_coff == 0 and p.cout == c.cin and self.bufs[c.name].Kc == pb.Cp
                 simple = (f.rowmap == L.ROW_IDENT and c.La == pb.Lz) or (f.rowmap == L.ROW_UP2 and c.La == 2 * pb.Lz)
                 ok = ok and covers and simple and c.name not in self.dgrad_target and self._needs_dgrad(c)
             if not ok:
                 continue
-            for (c, f) in self.consumers[p.name]:
+            for (c, f) in self._grad_sources(p):
                 self.dgrad_target[c.name] = (p, f)
             self.bwd_fused.add(p.name)
             pb.bwd_accum = torch.zeros(L.BWD_COPIES, self.groups, p.cout, 2, dtype=torch.float64, device=self.device)
@@ -901,7 +923,7 @@ class NetPlan:
         order = {l.name: i for i, l in enumerate(self.spec.layers)}
         for p in cands:
             cons = self.consumers[p.name]
-            if p.name in self.bwd_fused or len(cons) < 2:
+            if p.name in self.bwd_fused or len(cons) < 2 or p.name in self.grad_summed:
                 continue
             pb = self.bufs[p.name]
             ok = all(f.dst_coff == 0 and p.cout == c.cin and self.bufs[c.name].Kc == pb.Cp and self._needs_dgrad(c) and
@@ -916,6 +938,13 @@ class NetPlan:
                     self.bwd_helpers.setdefault(c.name, []).append((p, f))
             self.bwd_fused.add(p.name)
             pb.bwd_accum = torch.zeros(L.BWD_COPIES, self.groups, p.cout, 2, dtype=torch.float64, device=self.device)
+
+    def _grad_sources(self, p: Layer):
+        """(consumer, feed) pairs whose input gradients the BN backward of `p` sums: all its consumers -- or, where one
+        consumer's dgrad has added the other's gradient to its own (grad_add), that consumer alone."""
+        cons = self.consumers[p.name]
+        c_sum = getattr(self, "grad_summed", {}).get(p.name)
+        return [(c, f) for (c, f) in cons if c is c_sum] if c_sum is not None else cons
 
     def _emit_bwd(self, l: Layer):
         P, st, B, lb = self.prog, self.store, self.B, self.bufs[l.name]
@@ -932,10 +961,11 @@ class NetPlan:
         else:
             lb.dpre = self._zeros(B, lb.Lz, lb.Cp)
             gs = []
-            for (c, f) in self.consumers[l.name]:
+            for (c, f) in self._grad_sources(l):
                 cb = self.bufs[c.name]
                 gs.append({"g": cb.g, "ld": cb.Kc, "coff": f.dst_coff, "rowmap": f.rowmap, "L_src": c.La, "f32": 0})
             assert 1 <= len(gs) <= 2, (l.name, len(gs))
+            ngs = len(gs)
             while len(gs) < 2:
                 gs.append({})
             lb.sums = self._zeros(self.groups, l.cout, 2, dtype=torch.float32)
@@ -948,7 +978,7 @@ class NetPlan:
             defer = fused and bool(os.environ.get("B2H_DEFER_BN"))
             waits = [f"bwd_sums1.{l.name}.{c.name}" for (c, _) in self.consumers[l.name]
                      if any(p is l for (p, _) in self.bwd_helpers.get(c.name, []))]
-            i = P.add(L.OP_BN_BWD, f"bn_bwd.{l.name}", gsrc=gs, ngsrc=len(self.consumers[l.name]),
+            i = P.add(L.OP_BN_BWD, f"bn_bwd.{l.name}", gsrc=gs, ngsrc=ngs,
                       bn=self._bn_src(l), dpre=lb.dpre, ld_dpre=lb.Cp, Cfill=lb.Cp, B=B, L=lb.Lz, C=l.cout,
                       groups=self.groups, act=l.act, dgamma=None if defer else st.g(l.bnkey + ".weight"),
                       dbeta=None if defer else st.g(l.bnkey + ".bias"),
@@ -986,6 +1016,11 @@ class NetPlan:
         common = dict(A=lb.dpre, W=lb.wb, bias=None, out=lb.g, B=B, La=lb.Lz, lda=lb.Cp, ldo=lb.Kc, out_coff=0,
                       Kc=lb.Cp, Nvalid=l.cin, ntaps=len(taps), tap_off=taps + [0] * (L.MAX_TAPS - len(taps)),
                       act=L.ACT_NONE, post_scale=None, post_shift=None, out_f32=0, drop=drop, drop_C=l.cin)
+        if l.name in self.grad_add:        # skip connection: + the gradient the other consumer of the tensor wrote
+            ob = self.bufs[self.grad_add[l.name].name]
+            assert ob.g is not None and ob.g.shape == lb.g.shape, (l.name, self.grad_add[l.name].name)
+            common["grad_add"] = ob.g
+            common["ld_grad_add"] = ob.Kc
         if l.name in self.dgrad_target:
             p, f = self.dgrad_target[l.name]
             pb = self.bufs[p.name]

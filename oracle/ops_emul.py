@@ -103,6 +103,10 @@ def gemm(f: Dict):
             nn = min(Nv, C)
             v = v.clone()
             v[:, :, :nn] = v[:, :, :nn] * m[:, :, :nn]
+        if f.get("grad_add") is not None:   # dgrad of a skip connection: + the other consumer's gradient (b2h_gemm_t.grad_add)
+            assert f["out_coff"] == 0 and not ncl and f.get("resid") is None and not f.get("out_pool2")
+            ga = f["grad_add"].to(torch.float32).reshape(B, Lact, f["ld_grad_add"])[:, :, :Nv]
+            v = v + ga[:, ra]
         if f.get("out_pool2"):           # MaxPool1d(2) in the epilogue: out has Lo_actual // 2 rows per sample
             assert nph == 1 and f["out_coff"] == 0 and not ncl and f.get("resid") is None
             Lh = Lact // 2

@@ -119,6 +119,58 @@ def test_generator_train_forward_backward(variant, rf, cin, cout, T):
         assert rel_err(store.g(k), p.grad) < 5e-5, k
 
 
+@pytest.mark.parametrize("variant,rf", [("v1", False), ("v4", True), ("v2", True)])
+def test_skip_connection_gradients_summed_in_the_dgrad_epilogue(monkeypatch, variant, rf):
+    """bf16 train plans: the consumer of a skip connection that comes last in the backward pass adds the other
+    consumer's input gradient in its dgrad epilogue (b2h_gemm_t.grad_add), the producer's bn_bwd reads one source and
+    takes its first-pass sums from that dgrad.  Same gradients as the two-source plan up to one bf16 rounding of the
+    summed gradient."""
+    B, T, cin, cout = 4, 16, 36, 252
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(B, cin, T, generator=g)
+    y = torch.randn(B, cout, T, generator=g)
+    f = feats_for(variant, rf, B, T, g)
+    G = R.build_generator(variant, cin, cout, rf)
+    randomize_bn(G)
+    masks = R.make_masks(G, x, seed=3, feats=f)
+    grads = []
+    for off in (False, True):
+        if off:
+            monkeypatch.setenv("B2H_NO_GRAD_ADD", "1")
+        spec = nets.generator_spec(variant, cin, cout, rf, train=True)
+        store = nets.ParamStore(spec, "cpu", seed=0)
+        store.load_state_dict(G.state_dict())
+        plan = nets.NetPlan(spec, store, B, T, L.BF16, "cpu", train=True, drop_mode="mask")
+        bwd = plan.prog.recs[slice(*plan.prog.segments["bwd"])]
+        n_add = sum(1 for r in bwd if r.kind == L.OP_GEMM and r.f.get("grad_add") is not None)
+        two_src = [r.tag for r in bwd if r.kind == L.OP_BN_BWD and r.f["ngsrc"] == 2]
+        if off:
+            assert n_add == 0 and two_src
+        else:
+            assert n_add >= 1 and n_add == len(plan.grad_summed)
+            for pname, c_last in plan.grad_summed.items():
+                rec = next(r for r in bwd if r.tag == f"bn_bwd.{pname}")
+                assert rec.f["ngsrc"] == 1 and rec.f["gsrc"][0]["g"] is plan.bufs[c_last.name].g
+                if variant == "v1":     # conv5 / conv6: the last consumer's dgrad also carries the first-pass sums
+                    assert rec.f["accum"] is not None
+                    dg = next(r for r in bwd if r.tag == f"dgrad.{c_last.name}")
+                    assert dg.f["bwd_sums"]["accum"] is rec.f["accum"]
+        plan.set_masks(masks)
+        plan.x.copy_(x)
+        if f is not None:
+            plan.feats.copy_(f)
+        recs = plan.prog.recs
+        E.run_records(recs, *plan.prog.segments["pack"])
+        E.run_records(recs, *plan.prog.segments["fwd"])
+        olb = plan.bufs[plan.out_layer.name]
+        E.l1(dict(out=plan.out, gt=y, dout=olb.dpre, loss=torch.zeros(1), B=B, C=cout, L=T, ld=olb.Cp, Cfill=olb.Cp,
+                  gscale=1.0))
+        E.run_records(recs, *plan.prog.segments["bwd"])
+        grads.append(store.grad.clone())
+    assert rel_err(grads[0], grads[1]) < 2e-2
+    assert float((grads[0] - grads[1]).abs().max()) > 0.0     # (the plans really differ: one more rounding)
+
+
 @pytest.mark.parametrize("T,groups", [(16, 1), (16, 2), (64, 2), (192, 2), (21, 2)])
 def test_discriminator(T, groups):
     torch.manual_seed(0)
