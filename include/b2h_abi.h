@@ -104,11 +104,16 @@ typedef struct {
 typedef struct {
   const void* z;      /* producer's post-activation tensor [B][Lz][ld], act dtype; NULL = disabled */
   int32_t ld, Lz;     /* row pitch / rows per sample of z */
-  int32_t rowmap;     /* B2H_ROW_IDENT: z row (b, l) (Lz == Lo_actual);  B2H_ROW_UP2: z row (b, l/2) (Lo_actual == 2*Lz) */
+  int32_t rowmap;     /* B2H_ROW_IDENT: z row (b, l) (Lz == Lo_actual);  B2H_ROW_UP2: z row (b, l/2) (Lo_actual == 2*Lz);
+                         B2H_ROW_POOL2 (Lz == 2*Lo_actual): the GEMM differentiates MaxPool1d(2) of the producer's BN
+                         output -- gradient row (b, l) belongs to z row (b, 2l) or (b, 2l+1), whichever has the larger
+                         z*scale + shift (the first on ties, as nn.MaxPool1d), and to no other row */
   int32_t C, Cs, groups;
   const float* mean;   /* [groups][Cs] batch statistics of the producer's forward */
   const float* invstd;
   double* accum;      /* [B2H_BWD_COPIES][groups][C][2], zero before the first contribution */
+  const float* scale; /* [groups][Cs] forward affine of the producer (B2H_ROW_POOL2 only) */
+  const float* shift;
 } b2h_bwd_sums_t;
 
 /* ------------------------------------------------------------------------------------------- */

@@ -39,7 +39,7 @@ BWD_COPIES = 8
 
 class BwdSums(C.Structure):
     _fields_ = [("z", vp), ("ld", i32), ("Lz", i32), ("rowmap", i32), ("C", i32), ("Cs", i32), ("groups", i32),
-                ("mean", vp), ("invstd", vp), ("accum", vp)]
+                ("mean", vp), ("invstd", vp), ("accum", vp), ("scale", vp), ("shift", vp)]
 
 
 class Gemm(C.Structure):

@@ -24,7 +24,7 @@ struct FpropCfg {
   static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
   static constexpr int EPI_BYTES = 128 * EPI_PITCH_MAX;
   static constexpr int MAIN_BYTES = PIPE_BYTES > EPI_BYTES ? PIPE_BYTES : EPI_BYTES;
-  static constexpr int SMEM_BYTES = MAIN_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 3 * BN * 4 /*bias, pivot | scale, shift*/;
+  static constexpr int SMEM_BYTES = MAIN_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 4 * BN * 4 /*bias, pivot | scale, shift, pooled-BWDSUM scale*/;
   // tap-merged main loop: the A ring holds (tl + ntaps - 1) x tb rows of 64 channels once per channel chunk (all
   // taps read it through shifted descriptors), the B ring one (BN x 64) weight tile per (chunk, tap)
   static constexpr int SA = 2;
@@ -103,6 +103,9 @@ struct BwdSumsDev {
   int C, Cs, groups;
   int up2;      // z row = tile row / 2 (x2 nearest up-sampling between the producer and this GEMM's rows)
   int zbytes;   // bytes of the z box
+  int pool2;    // MaxPool1d(2) between the producer and this GEMM's rows: z rows 2l, 2l+1; the larger z*scale+shift counts
+  const float* scale;
+  const float* shift;
 };
 
 }  // namespace b2h

@@ -66,7 +66,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
   float* s_bias = reinterpret_cast<float*>(smem + Cfg::MAIN_BYTES + 256);
   float* s_piv = s_bias + BN;     // STATS / BWDSUM: pivot / mean;  *_BN kinds: folded BN scale
-  float* s_shift = s_piv + BN;    // *_BN kinds: folded BN shift
+  float* s_shift = s_piv + BN;    // *_BN kinds: folded BN shift;  pooled BWDSUM: the producer's shift
+  float* s_pscale = s_shift + BN; // pooled BWDSUM: the producer's scale
   int* s_flag = reinterpret_cast<int*>(tmem_ptr + 1);
   uint64_t* z_bar = reinterpret_cast<uint64_t*>(tmem_ptr + 2);
   uint64_t* a_full = z_bar + 1;            // MERGED: the A ring (full_bar / empty_bar are the B ring)
@@ -256,6 +257,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const bool in = nn0 + i < bs.C;
         s_piv[i] = in ? bs.mean[grp * bs.Cs + nn0 + i] : 0.f;
         s_bias[i] = in ? bs.invstd[grp * bs.Cs + nn0 + i] : 0.f;
+        if (BN == 64 && bs.pool2) {
+          s_pscale[i] = in ? bs.scale[grp * bs.Cs + nn0 + i] : 0.f;
+          s_shift[i] = in ? bs.shift[grp * bs.Cs + nn0 + i] : 0.f;
+        }
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
     }
@@ -285,10 +290,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       tc_fence_after();
       if (BWDSUM && et == 0) {   // every MMA has retired: the stage buffers are free
         mbar_arrive_expect_tx(z_bar, (uint32_t)bs.zbytes);
+        const int zl0 = bs.up2 ? (l0 >> 1) : ((BN == 64 && bs.pool2) ? 2 * l0 : l0);   // first z frame of the box
         if (MERGED)   // z maps of a merged plan are (C, B, L) too
-          tma_load_3d(zs, ph ? &tmZ1 : &tmZ0, z_bar, nn0, b0, bs.up2 ? (l0 >> 1) : l0);
+          tma_load_3d(zs, ph ? &tmZ1 : &tmZ0, z_bar, nn0, b0, zl0);
         else
-          tma_load_3d(zs, ph ? &tmZ1 : &tmZ0, z_bar, nn0, bs.up2 ? (l0 >> 1) : l0, b0);
+          tma_load_3d(zs, ph ? &tmZ1 : &tmZ0, z_bar, nn0, zl0, b0);
       }
 #pragma unroll(GADD ? CH / 32 : 1)
       for (int ci = 0; ci < CH / 32; ++ci) {
@@ -384,6 +390,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               const float d0 = f.x - piv[2 * i], d1 = f.y - piv[2 * i + 1];
               a1[2 * i] += d0, a1[2 * i + 1] += d1;
               a2[2 * i] = fmaf(d0, d0, a2[2 * i]), a2[2 * i + 1] = fmaf(d1, d1, a2[2 * i + 1]);
+            }
+          } else if (BN == 64 && bs.pool2) {   // (64-column tiles only: plan_gemm_tc)
+            // MaxPool1d(2) between the producer and this GEMM: the gradient row belongs to the z row of the pair
+            // (frames 2 li, 2 li + 1 of the box) with the larger z*scale + shift, the first one on ties -- the same
+            // fmaf and comparison as bn_apply / bn_bwd
+            const int zr0 = MERGED ? (2 * li) * p.tb + bi : bi * (2 * p.tl) + 2 * li;
+            const int zr1 = MERGED ? zr0 + p.tb : zr0 + 1;
+            const uint4 zq0 = *reinterpret_cast<const uint4*>(zs + ((size_t)zr0 * BN + ch * 8) * 2);
+            const uint4 zq1 = *reinterpret_cast<const uint4*>(zs + ((size_t)zr1 * BN + ch * 8) * 2);
+            const uint32_t zw0[4] = {zq0.x, zq0.y, zq0.z, zq0.w}, zw1[4] = {zq1.x, zq1.y, zq1.z, zq1.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+              const float2 za = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&zw0[i]));
+              const float2 zb = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&zw1[i]));
+              const float s0 = s_pscale[ch * 8 + 2 * i], s1 = s_pscale[ch * 8 + 2 * i + 1];
+              const float t0 = s_shift[ch * 8 + 2 * i], t1 = s_shift[ch * 8 + 2 * i + 1];
+              const float zx = fmaf(zb.x, s0, t0) > fmaf(za.x, s0, t0) ? zb.x : za.x;
+              const float zy = fmaf(zb.y, s1, t1) > fmaf(za.y, s1, t1) ? zb.y : za.y;
+              const float h0 = (zx - piv[2 * i]) * sc[2 * i], h1 = (zy - piv[2 * i + 1]) * sc[2 * i + 1];
+              a1[2 * i] += f.x, a1[2 * i + 1] += f.y;
+              a2[2 * i] = fmaf(f.x, h0, a2[2 * i]), a2[2 * i + 1] = fmaf(f.y, h1, a2[2 * i + 1]);
             }
           } else {
             const int zr = !bs.up2 ? r : (MERGED ? (li >> 1) * p.tb + bi : bi * (p.tl >> 1) + (li >> 1));
@@ -893,7 +921,12 @@ int plan_gemm_tc(const b2h_gemm_t& d, TcGemmPlan* plan, int esz) {
     }
   }
   if (ncl || resid) best_bn = 256;
-  if (const char* f = getenv("B2H_FORCE_BN"); f && !ncl && !resid) {  // tuning aid
+  // pooled backward sums (b2h_bwd_sums_t.rowmap = POOL2): the z box is twice the tile's height -- with 64-column tiles
+  // it fits the idle pipeline buffers behind the staging tile (32 KB)
+  const bool pool_bwd = esz == 2 && d.bwd_sums.z && d.bwd_sums.rowmap == B2H_ROW_POOL2 && !getenv("B2H_NO_FUSED_BWD") &&
+                        !getenv("B2H_NO_POOL_BWDSUM");
+  if (pool_bwd) best_bn = 64;
+  if (const char* f = getenv("B2H_FORCE_BN"); f && !ncl && !resid && !pool_bwd) {  // tuning aid
     int bn = atoi(f);
     if ((bn == 64 || bn == 128 || bn == 256) && bn <= bn_max && half % bn == 0) best_bn = bn;
   }
@@ -977,18 +1010,22 @@ int plan_gemm_tc(const b2h_gemm_t& d, TcGemmPlan* plan, int esz) {
     const b2h_bwd_sums_t& bs = d.bwd_sums;
     const int kind = epi_kind(d);
     const bool up2 = bs.rowmap == B2H_ROW_UP2;
+    const bool pool2z = bs.rowmap == B2H_ROW_POOL2;
     bool ok = (kind == EPI_MASK || kind == EPI_PLAIN) && !plan->fuse_stats && bs.C == d.Nvalid && d.out_coff == 0 &&
               d.ldo >= ((d.Nvalid + 7) & ~7) && bs.groups >= 1 && d.B % bs.groups == 0 &&
               (d.B / bs.groups) % p.tb == 0 && bs.accum && ((uintptr_t)bs.accum % 16) == 0 && bs.mean && bs.invstd &&
               bs.ld % 8 == 0 && bs.ld >= d.Npad / d.nphase && !getenv("B2H_NO_FUSED_BWD");
     if (up2)
       ok = ok && d.nphase == 1 && p.tl >= 2 && d.Lo_actual == 2 * bs.Lz;
+    else if (pool2z)
+      ok = ok && pool_bwd && best_bn == 64 && d.nphase == 1 && bs.Lz == 2 * d.Lo_actual && bs.scale && bs.shift &&
+           ((128 * (64 * 2 + 16) + 64 * 64 + 127) & ~127) + 2 * 128 * 64 * 2 <= FpropCfg<64>::MAIN_BYTES;
     else
       ok = ok && bs.rowmap == B2H_ROW_IDENT && d.Lo_actual == bs.Lz;
     if (ok) {
       const uint8_t* z = reinterpret_cast<const uint8_t*>(bs.z);   // (act dtype: esz bytes per element)
       const size_t zrow = (size_t)bs.ld * esz;
-      const int box_l = up2 ? p.tl / 2 : p.tl;
+      const int box_l = up2 ? p.tl / 2 : (pool2z ? 2 * p.tl : p.tl);
       const int64_t zs_b = (int64_t)bs.Lz * bs.ld;   // sample pitch of z
       if (p.merged && d.nphase == 1) {   // (C, B, L) like the A operand of a merged plan
         rc = make_map_3d(&plan->tmZ0, z, bs.ld, d.B, bs.Lz, zs_b, bs.ld, best_bn, p.tb, box_l, false, esz);
@@ -1022,6 +1059,9 @@ int plan_gemm_tc(const b2h_gemm_t& d, TcGemmPlan* plan, int esz) {
       plan->bs_Cs = bs.Cs;
       plan->bs_groups = bs.groups;
       plan->bs_up2 = up2 ? 1 : 0;
+      plan->bs_pool2 = pool2z ? 1 : 0;
+      plan->bs_scale = bs.scale;
+      plan->bs_shift = bs.shift;
       plan->bs_zbytes = best_bn * esz * box_l * p.tb;
     }
   }
@@ -1084,6 +1124,9 @@ static int launch_fprop_m(const TcGemmPlan& plan, const EpiParams& e, cudaStream
     bs.groups = plan.bs_groups;
     bs.up2 = plan.bs_up2;
     bs.zbytes = plan.bs_zbytes;
+    bs.pool2 = plan.bs_pool2;
+    bs.scale = plan.bs_scale;
+    bs.shift = plan.bs_shift;
   }
   const bool z = MODE == MODE_BWDSUM;
   if constexpr (KIND == EPI_MASK && (MODE == MODE_BWDSUM || MODE == MODE_PLAIN)) {

@@ -626,7 +626,9 @@ int launch_bn_bwd(const b2h_bn_bwd_t& d, int dtype, cudaStream_t s) {
 // pass of bn_bwd restricted to this GEMM's output as the only gradient source.
 int launch_bwd_sums_separate(const b2h_gemm_t& g, int dtype, cudaStream_t s) {
   const b2h_bwd_sums_t& bs = g.bwd_sums;
-  B2H_CHECK_ARG(bs.rowmap == B2H_ROW_IDENT || bs.rowmap == B2H_ROW_UP2, B2H_ERR_ARG, "bwd_sums: rowmap");
+  const bool pooled = bs.rowmap == B2H_ROW_POOL2;
+  B2H_CHECK_ARG(bs.rowmap == B2H_ROW_IDENT || bs.rowmap == B2H_ROW_UP2 || (pooled && bs.scale && bs.shift), B2H_ERR_ARG,
+                "bwd_sums: rowmap (POOL2 needs the producer's scale / shift)");
   B2H_CHECK_ARG(bs.accum && bs.mean && bs.invstd && bs.C == g.Nvalid && !g.out_f32, B2H_ERR_ARG,
                 "bwd_sums: must describe the layer that produced the rows this GEMM differentiates");
   b2h_bn_bwd_t d;
@@ -642,8 +644,8 @@ int launch_bwd_sums_separate(const b2h_gemm_t& g, int dtype, cudaStream_t s) {
   d.bn.Cs = bs.Cs;
   d.bn.mean = bs.mean;
   d.bn.invstd = bs.invstd;
-  d.bn.scale = bs.mean;   // only read by the pooling path, which a bwd_sums source never takes
-  d.bn.shift = bs.mean;
+  d.bn.scale = pooled ? bs.scale : bs.mean;   // (only read by the pooling path)
+  d.bn.shift = pooled ? bs.shift : bs.mean;
   d.ld_dpre = 8;
   d.Cfill = (bs.C + 7) & ~7;
   d.B = g.B;
@@ -652,8 +654,8 @@ int launch_bwd_sums_separate(const b2h_gemm_t& g, int dtype, cudaStream_t s) {
   d.groups = bs.groups;
   d.accum = bs.accum;
   d.partial = reinterpret_cast<float*>(bs.accum);
-  B2H_CHECK_ARG(grad_src_simple(d.gsrc[0], d.L), B2H_ERR_SHAPE, "bwd_sums: Lo_actual=%d does not match Lz=%d",
-                g.Lo_actual, bs.Lz);
+  B2H_CHECK_ARG(grad_src_simple(d.gsrc[0], d.L) || (pooled && (d.L & 1) == 0 && 2 * g.Lo_actual == d.L), B2H_ERR_SHAPE,
+                "bwd_sums: Lo_actual=%d does not match Lz=%d", g.Lo_actual, bs.Lz);
   return launch_bn_bwd_passes(d, dtype, 1, 1, s);
 }
 

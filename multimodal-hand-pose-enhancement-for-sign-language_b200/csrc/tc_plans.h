@@ -35,7 +35,9 @@ struct alignas(64) TcGemmPlan {
   const float* bs_mean;
   const float* bs_invstd;
   double* bs_accum;
-  int bs_C, bs_Cs, bs_groups, bs_up2, bs_zbytes;
+  int bs_C, bs_Cs, bs_groups, bs_up2, bs_zbytes, bs_pool2;
+  const float* bs_scale;
+  const float* bs_shift;
 };
 
 struct TcWgradParams {

@@ -903,7 +903,11 @@ class NetPlan:
             for (c, f) in self._grad_sources(p):
                 covers = f.dst_coff == 0 and p.cout == c.cin and self.bufs[c.name].Kc == pb.Cp
                 simple = (f.rowmap == L.ROW_IDENT and c.La == pb.Lz) or (f.rowmap == L.ROW_UP2 and c.La == 2 * pb.Lz)
-                ok = ok and covers and simple and c.name not in self.dgrad_target and self._needs_dgrad(c)
+                # MaxPool1d(2) in between (encoder -> conv5): the dgrad's epilogue picks the pooled row of z itself
+                # (b2h_bwd_sums_t.rowmap = POOL2; the only consumer, even length)
+                pooled = (f.rowmap == L.ROW_POOL2 and pb.Lz == 2 * c.La and len(self._grad_sources(p)) == 1 and
+                          not os.environ.get("B2H_NO_POOL_BWDSUM"))
+                ok = ok and covers and (simple or pooled) and c.name not in self.dgrad_target and self._needs_dgrad(c)
             if not ok:
                 continue
             for (c, f) in self._grad_sources(p):
@@ -1025,7 +1029,9 @@ class NetPlan:
             p, f = self.dgrad_target[l.name]
             pb = self.bufs[p.name]
             common["bwd_sums"] = dict(z=pb.z, ld=pb.Cp, Lz=pb.Lz, rowmap=f.rowmap, C=p.cout, Cs=pb.Cp,
-                                      groups=self.groups, mean=pb.mean, invstd=pb.invstd, accum=pb.bwd_accum)
+                                      groups=self.groups, mean=pb.mean, invstd=pb.invstd, accum=pb.bwd_accum,
+                                      scale=pb.scale if f.rowmap == L.ROW_POOL2 else None,
+                                      shift=pb.shift if f.rowmap == L.ROW_POOL2 else None)
         if lb.bwd_nphase == 2:
             i = P.add(L.OP_GEMM, f"dgrad.{l.name}", Lo=_ceil_div(l.La, 2), Npad=2 * lb.Kc, stride=1, nphase=2,
                       Lo_actual=l.La, **common)

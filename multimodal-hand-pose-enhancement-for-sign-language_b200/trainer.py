@@ -308,8 +308,13 @@ class GanTrainer:
         direct = os.environ.get("B2H_NO_WGRAD_DIRECT") is None
         # (the regression loss reads the output layer's BLC tile and writes the NCL `out` itself: no to_ncl pass)
         self.l1_reads_blc = os.environ.get("B2H_NO_L1_FUSE") is None
+        # (opt-in, B2H_L1_DBIAS=1: its 16-byte form can also emit the bias gradient of the output layer -- column sums
+        # by warp shuffle + one fp64 atomic per channel and CTA; measured: the loss kernel, which is on the chain,
+        # grows from 12.0 to 14.9 us while the column-sum launch it replaces runs beside the chain: 0.656 vs 0.660 ms)
+        self.l1_dbias = self.l1_reads_blc and T % 4 == 0 and bool(os.environ.get("B2H_L1_DBIAS"))
         self.G_train = nets.NetPlan(self.g_spec, self.g_store, B, T, self.dtype, dev, train=True, site_base=0,
-                                    wgrad_direct=direct, out_by_loss=self.l1_reads_blc, **kw)
+                                    wgrad_direct=direct, out_by_loss=self.l1_reads_blc,
+                                    out_dbias_external=self.l1_dbias, **kw)
         self.G_eval = nets.NetPlan(self.g_spec_eval, self.g_store, B, T, self.dtype, dev, train=False,
                                    weights_from=self.G_train)
         self.y = torch.zeros(B, out_dim, T, dtype=torch.float32, device=dev)
@@ -432,15 +437,18 @@ class GanTrainer:
         P = self.g_loss_prog = Program(self.dtype, dev)
         nblk = ((T + 31) // 32) * ((olb.Cp + 31) // 32) * B
         self.l1_partial = torch.zeros(nblk, dtype=torch.float32, device=dev)
+        self.l1_dbias_accum = torch.zeros(16, out_dim, dtype=torch.float64, device=dev)
         Ld = De.bufs[De.out_layer.name].Lz
         with P.segment("loss"):
             P.add(L.OP_L1, "l1", out=Gt.out, gt=self.y, dout=olb.dpre, loss=self.losses[0:1], partial=self.l1_partial,
                   ticket=self.ticket[0:1], B=B, C=out_dim, L=T, ld=olb.Cp, Cfill=olb.Cp, gscale=1.0,
-                  kind=L.LOSS_KINDS[self.loss], dbias=None, dbias_accum=None,
+                  kind=L.LOSS_KINDS[self.loss],
+                  dbias=self.g_store.g(Gt.out_layer.wkey + ".bias") if self.l1_dbias else None,
+                  dbias_accum=self.l1_dbias_accum if self.l1_dbias else None,
                   out_blc=Gt.out_blc if self.l1_reads_blc else None,
                   out_blc_ld=Gt.out_blc.shape[-1] if self.l1_reads_blc else 0)
-            # (l1 can also emit the bias gradient of the output layer, but the in-kernel column sums cost more than
-            # the separate 8 us colsum launch: 29.9 vs 13.4 + 7.7 us)
+            # (the scalar form of the kernel -- T % 4 != 0 -- pays far more for its in-kernel column sums than the
+            # separate 8 us colsum launch costs: 29.9 vs 13.4 + 7.7 us)
             P.add(L.OP_MSE, "adv", score=De.out_blc, dscore=None, loss=self.losses[1:2], add=self.losses[0:1],
                   total=self.losses[2:3], groups=1, n=B * Ld, ld=De.out_blc.shape[-1], target=[1.0, 0.0])
         with P.segment("opt"):

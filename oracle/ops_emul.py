@@ -136,16 +136,23 @@ def gemm(f: Dict):
         assert f["out_coff"] == 0 and not f["out_f32"] and nph * 0 == 0
         g = out2[:, :, :C].to(torch.float32)                           # (B, Lo_actual, C) as stored
         z = bs["z"].to(torch.float32).reshape(B, Lz, -1)[:, :, :C]
+        pooled = bs["rowmap"] == ROW_POOL2
         if bs["rowmap"] == ROW_UP2:
             assert Lact == 2 * Lz
             z = z.repeat_interleave(2, dim=1)
+        elif pooled:
+            assert Lz == 2 * Lact     # the row of each pair with the larger z*scale + shift (the first on ties)
         else:
             assert bs["rowmap"] == ROW_IDENT and Lact == Lz
         Bg = B // G
         acc = bs["accum"].reshape(-1, G, C, 2)
         for gi in range(G):
             sl = slice(gi * Bg, (gi + 1) * Bg)
-            zh = (z[sl] - bs["mean"][gi, :C]) * bs["invstd"][gi, :C]
+            zg = z[sl]
+            if pooled:
+                y = zg * bs["scale"][gi, :C] + bs["shift"][gi, :C]
+                zg = torch.where(y[:, 1::2] > y[:, 0::2], zg[:, 1::2], zg[:, 0::2])
+            zh = (zg - bs["mean"][gi, :C]) * bs["invstd"][gi, :C]
             acc[0, gi, :, 0] += g[sl].sum((0, 1)).double()
             acc[0, gi, :, 1] += (g[sl] * zh).sum((0, 1)).double()
 

@@ -4,6 +4,7 @@ import pytest
 import torch
 
 import b2h_b200  # noqa: F401
+from b2h_b200 import _lib as L
 from b2h_b200.trainer import GanTrainer
 from oracle import ops_emul as E
 from oracle import ref_models as R
@@ -182,7 +183,8 @@ def test_gan_steps_match_oracle_with_deferred_bn_backward(monkeypatch):
     assert "bwd_sums1.conv5.skip5" in tags and "bwd_sums1.conv6.skip4" in tags and "bn_fin.conv5" in tags
     rec = {r.tag: r for r in tr.G_train.prog.recs}
     assert rec["bn_bwd.conv5"].f["defer"] == 1 and rec["bn_bwd.conv5"].f["_wait_tags"] == ["bwd_sums1.conv5.skip5"]
-    assert rec["bn_bwd.encoder"].f["defer"] == 0          # pooled gradient source: two passes, own tail
+    assert rec["bn_bwd.encoder"].f["defer"] == 1          # (pooled gradient source: sums from conv5's dgrad epilogue)
+    assert rec["dgrad.conv5"].f["bwd_sums"]["rowmap"] == L.ROW_POOL2
     test_gan_steps_match_oracle("v1", False, False)
 
 
@@ -318,13 +320,13 @@ def test_bucket_by_bucket_update_order_matches_the_oracle(variant, rf, precision
     assert len(all_updated) == len(set(all_updated)) == len({l.name for l in st.spec.all_layers()})
     for steps in range(2):
         R.generator_step(G, D, g_opt, x, y, f, masks)
-        emul_g_forward_and_losses(tr)
         st.grad.fill_(float("nan"))                  # a gradient consumed before it is produced poisons the update
         live = {n for n, _ in tr.G_train.bwd_marks}
         for l in st.spec.all_layers():               # (dead branches never write theirs: they stay zero, as on the device)
             if l.name not in live:
                 for key in [l.wkey + ".weight", l.wkey + ".bias"] + ([l.bnkey + ".weight", l.bnkey + ".bias"] if l.bn else []):
                     st.g(key).zero_()
+        emul_g_forward_and_losses(tr)                # (the loss op produces the output layer's bias gradient)
         E.run_records(P.recs, *P.segments["step"])
         for i, (s, e, lo, hi, _) in enumerate(bp):
             E.run_records(tr.G_train.prog.recs, s, e)
