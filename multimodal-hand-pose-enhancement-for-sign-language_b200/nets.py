@@ -893,7 +893,9 @@ class NetPlan:
                            self.bufs[c.name].Kc == pb.Cp and self._needs_dgrad(c) for (c, f) in cons):
                     continue
                 (c_last, _), (c_first, _) = sorted(cons, key=lambda cf: order[cf[0].name])
-                if c_last.name in self.grad_add:
+                # c_last's input gradient must belong to p alone: with a second feed (an addition in front of c_last)
+                # it is also the gradient of that other tensor, which the added term would corrupt
+                if c_last.name in self.grad_add or len(c_last.feeds) != 1:
                     continue
                 self.grad_add[c_last.name] = c_first
                 self.grad_summed[p.name] = c_last
