@@ -242,7 +242,11 @@ typedef struct {
   int32_t defer;  /* 1 (needs `accum` and `dpre`): the op only writes dpre -- no reduction, no ticket, no serial tail on
                      the dependency chain of the backward pass.  dgamma / dbeta / dbias and the re-zeroing of `accum`
                      are left to a b2h_colsum over dpre with `bn_accum` = this accum, which only feeds the optimizer
-                     and can run beside the chain.  dgamma / dbeta / dbias / sums / partial / ticket are ignored */
+                     and can run beside the chain.  dgamma / dbeta / dbias / sums / partial / ticket are ignored.
+                     2: as 1, but the op still accumulates the sums of dpre (the bias gradient) in ITS OWN `partial`
+                     (b2h_bn_partial_floats, not shared with another op in flight, zero before) and only skips the
+                     ticket and the last-CTA pass; the finishing b2h_colsum then has src = NULL (nothing to re-read)
+                     and the same `partial` */
   int32_t first_pass_only; /* 1 (needs `accum`, dpre == NULL): accumulate sum(dy), sum(dy*zhat) of the given gradient
                      sources into `accum` and stop -- the contribution of a consumer whose dgrad GEMM cannot carry
                      b2h_gemm_t.bwd_sums for this layer (it serves another producer), run beside the chain as soon as
@@ -324,7 +328,8 @@ typedef struct {
   int32_t rows, ld, C, f32;
   /* optional: finish a deferred BatchNorm backward (b2h_bn_bwd_t.defer) -- src = its dpre, out = the bias gradient;
    * the last CTA also sums the first-pass accumulators [B2H_BWD_COPIES][bn_groups][C][2] in fixed order,
-   * writes dbeta[c] = sum dy, dgamma[c] = sum dy*zhat (over the groups) and re-zeroes them */
+   * writes dbeta[c] = sum dy, dgamma[c] = sum dy*zhat (over the groups) and re-zeroes them.
+   * src = NULL (defer = 2): one CTA; the sums of dpre are taken from the bn_bwd's own `partial` (same pointer here) */
   double* bn_accum;
   float* dgamma;
   float* dbeta;

@@ -504,7 +504,7 @@ __global__ void __launch_bounds__(kRowThreads, 2) bn_bwd_kernel(b2h_bn_bwd_t d) 
       }
     }
   }
-  if (PASS == 2 && d.defer) return;   // dpre is all this launch owes the chain; b2h_colsum(bn_accum) finishes the rest
+  if (PASS == 2 && d.defer == 1) return;   // dpre is all this launch owes the chain; b2h_colsum(bn_accum) finishes the rest
   block_sum8(s_red, acc_a, tx, ty, TXp, TY);
   if (PASS == 1) block_sum8(s_red, acc_b, tx, ty, TXp, TY);
   if (ty == 0 && c0 < d.C) {
@@ -522,6 +522,7 @@ __global__ void __launch_bounds__(kRowThreads, 2) bn_bwd_kernel(b2h_bn_bwd_t d) 
     }
   }
   if (PASS == 1) return;
+  if (d.defer == 2) return;   // sums of dpre accumulated; no ticket, no serial tail: b2h_colsum(src = NULL) finishes
   if (!last_block_done(d.ticket, gridDim.x * gridDim.y)) return;
 #pragma unroll 1
   for (int c = tid; c < d.C; c += kRowThreads) {
@@ -608,8 +609,9 @@ static int launch_bn_bwd_passes(const b2h_bn_bwd_t& d, int dtype, int first_pass
 }
 
 int launch_bn_bwd(const b2h_bn_bwd_t& d, int dtype, cudaStream_t s) {
-  B2H_CHECK_ARG(!d.defer || (d.accum && d.dpre && !d.first_pass_only), B2H_ERR_ARG,
-                "bn_bwd: defer needs the first-pass accumulators and dpre");
+  B2H_CHECK_ARG(d.defer >= 0 && d.defer <= 2 && (!d.defer || (d.accum && d.dpre && !d.first_pass_only)), B2H_ERR_ARG,
+                "bn_bwd: defer (0, 1, 2) needs the first-pass accumulators and dpre");
+  B2H_CHECK_ARG(d.defer != 2 || d.partial, B2H_ERR_ARG, "bn_bwd: defer = 2 accumulates the sums of dpre in `partial`");
   B2H_CHECK_ARG(!d.first_pass_only || (d.accum && !d.dpre), B2H_ERR_ARG,
                 "bn_bwd: first_pass_only accumulates into `accum` and writes no dpre");
   if (d.first_pass_only) {
@@ -717,7 +719,50 @@ __global__ void __launch_bounds__(kRowThreads) colsum_kernel(b2h_colsum_t d) {
   }
 }
 
+// Tail of a BatchNorm backward whose bn_bwd launch ran with defer = 2 (it accumulated the sums of dpre in its own
+// `partial` and skipped the ticket / last-CTA pass): one CTA sums the accumulator copies in the same fixed order as
+// bn_bwd's own tail, writes dbeta / dgamma / dbias and re-zeroes both regions.  Runs beside the backward chain.
+__global__ void __launch_bounds__(256) bn_bwd_finish_kernel(b2h_colsum_t d) {
+  pdl_sync();
+  double* accum1 = d.bn_accum;
+  double* accum2 = reinterpret_cast<double*>(d.partial) + (int64_t)B2H_BWD_COPIES * d.bn_groups * d.C * 2;
+#pragma unroll 1
+  for (int c = threadIdx.x; c < d.C; c += 256) {
+    double tot_a = 0.0, tot_b = 0.0, tot_c = 0.0;
+#pragma unroll 1
+    for (int gg = 0; gg < d.bn_groups; ++gg) {
+      double ta = 0.0, tb = 0.0;
+#pragma unroll
+      for (int k = 0; k < B2H_BWD_COPIES; ++k) {
+        double2* acc = reinterpret_cast<double2*>(accum1 + (((int64_t)k * d.bn_groups + gg) * d.C + c) * 2);
+        const double2 v = __ldcg(acc);
+        *acc = make_double2(0.0, 0.0);
+        ta += v.x, tb += v.y;
+      }
+#pragma unroll
+      for (int k = 0; k < kCopies; ++k) {
+        double* acc = accum2 + ((int64_t)k * d.bn_groups + gg) * d.C + c;
+        tot_c += __ldcg(acc);
+        *acc = 0.0;
+      }
+      tot_a += ta, tot_b += tb;
+    }
+    if (d.dbeta) d.dbeta[c] = (float)tot_a;
+    if (d.dgamma) d.dgamma[c] = (float)tot_b;
+    if (d.out) d.out[c] = (float)tot_c;
+  }
+}
+
 int launch_colsum(const b2h_colsum_t& d, int dtype, cudaStream_t s) {
+  if (!d.src) {   // no rows to sum: the finishing launch of a bn_bwd with defer = 2
+    B2H_CARVE(bn_bwd_finish_kernel);
+    B2H_CHECK_ARG(d.bn_accum && d.partial && d.bn_groups >= 1 && d.C > 0 && d.C <= 512 &&
+                      ((uintptr_t)d.bn_accum % 16) == 0 && ((uintptr_t)d.partial % 8) == 0,
+                  B2H_ERR_ARG, "colsum: src = NULL finishes a deferred bn_bwd and needs bn_accum, partial, bn_groups");
+    launch(bn_bwd_finish_kernel, 1, 256, 0, s, d);
+    B2H_LAUNCH_CHECK("bn_bwd_finish");
+    return B2H_OK;
+  }
   B2H_CARVE(colsum_kernel<__nv_bfloat16>);
   B2H_CARVE(colsum_kernel<float>);
   B2H_CHECK_ARG(d.C > 0 && d.C <= 512 && d.rows > 0 && d.ld % 8 == 0 && d.ld >= ((d.C + 7) & ~7), B2H_ERR_SHAPE,

@@ -976,12 +976,18 @@ class NetPlan:
                 gs.append({})
             lb.sums = self._zeros(self.groups, l.cout, 2, dtype=torch.float32)
             fused = l.name in self.bwd_fused
-            # first-pass sums complete in their own accumulator: the chain only needs dpre from this op (defer); the
-            # parameter gradients (dgamma, dbeta, dbias) and the re-zeroing of the accumulator ride with the weight
-            # gradient beside the chain: one b2h_colsum over dpre (bn_accum)
-            # (opt-in, B2H_DEFER_BN=1: bn_bwd drops from 12.5 to 6.5 us per launch, but the extra column-sum launches
-            # cost the step as much as they save -- 0.674 -> 0.679 ms, profiles/ab_r02_bn.log)
-            defer = fused and bool(os.environ.get("B2H_DEFER_BN"))
+            # First-pass sums complete in their own accumulator: the chain only needs dpre from this op, its tail
+            # (threadfence, ticket, the last CTA summing the accumulator copies into dgamma / dbeta / dbias and re-zeroing
+            # them: ~2.4 us of every launch) only feeds the optimizer.  B2H_DEFER_BN selects who runs it:
+            #   2 (default)  bn_bwd still accumulates the sums of dpre -- in its OWN workspace, the finishing launch runs
+            #                while the chain's next bn_bwd does -- and skips ticket + last-CTA pass; a one-CTA launch
+            #                beside the chain (b2h_colsum, src = NULL) finishes: 0.663 -> 0.648 ms per GAN step
+            #   1            bn_bwd writes dpre only (12.5 -> 6.5 us), a full column-sum launch over dpre finishes:
+            #                measured slower (0.674 -> 0.679 ms; the re-read costs the step more than the chain gains)
+            #   0            the op's own tail
+            # (profiles/ab_r02_bn.log, profiles/ab_r02_defer2.log)
+            defer = int(os.environ.get("B2H_DEFER_BN", "2") or 0) if fused else 0
+            assert defer in (0, 1, 2), defer
             waits = [f"bwd_sums1.{l.name}.{c.name}" for (c, _) in self.consumers[l.name]
                      if any(p is l for (p, _) in self.bwd_helpers.get(c.name, []))]
             i = P.add(L.OP_BN_BWD, f"bn_bwd.{l.name}", gsrc=gs, ngsrc=ngs,
@@ -989,10 +995,17 @@ class NetPlan:
                       groups=self.groups, act=l.act, dgamma=None if defer else st.g(l.bnkey + ".weight"),
                       dbeta=None if defer else st.g(l.bnkey + ".bias"),
                       dbias=None if defer else st.g(l.wkey + ".bias"), sums=None if defer else lb.sums, partial=None,
-                      ticket=self._ticket(), accum=lb.bwd_accum if fused else None, defer=1 if defer else 0,
+                      ticket=self._ticket(), accum=lb.bwd_accum if fused else None, defer=defer,
                       _wait_tags=waits)
-            self._need_partial(i, _bn_partial_floats(rows, l.cout, self.groups))
-            if defer:
+            if defer == 2:      # its own accumulators (the finishing launch runs while the chain's next bn_bwd does)
+                lb.fin_partial = self._zeros(_bn_partial_floats(rows, l.cout, self.groups), dtype=torch.float32)
+                P.recs[i].f["partial"] = lb.fin_partial
+                P.add(L.OP_COLSUM, f"bn_fin.{l.name}", src=None, out=st.g(l.wkey + ".bias"), partial=lb.fin_partial,
+                      ticket=None, rows=0, ld=lb.Cp, C=l.cout, f32=0, bn_accum=lb.bwd_accum,
+                      dgamma=st.g(l.bnkey + ".weight"), dbeta=st.g(l.bnkey + ".bias"), bn_groups=self.groups)
+            else:
+                self._need_partial(i, _bn_partial_floats(rows, l.cout, self.groups))
+            if defer == 1:
                 lb.fin_partial = self._zeros(128 * l.cout * 2, dtype=torch.float32)
                 P.add(L.OP_COLSUM, f"bn_fin.{l.name}", src=lb.dpre, out=st.g(l.wkey + ".bias"), partial=lb.fin_partial,
                       ticket=self._ticket(), rows=rows, ld=lb.Cp, C=l.cout, f32=0, bn_accum=lb.bwd_accum,

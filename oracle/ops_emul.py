@@ -21,6 +21,7 @@ ACT_NONE, ACT_LEAKY, ACT_RELU = 0, 1, 2
 ROW_IDENT, ROW_UP2, ROW_POOL2, ROW_BCAST = 0, 1, 2, 3
 SRC_NCL, SRC_ROWS, SRC_BCAST, SRC_MOTION = 0, 1, 2, 3
 DROP_NONE, DROP_MASK, DROP_PHILOX = 0, 1, 2
+BWD_COPIES = 8   # B2H_BWD_COPIES: copies of the first-pass accumulators (region 1 of a bn_bwd workspace)
 (OP_GEMM, OP_WGRAD, OP_BN_STATS, OP_BN_APPLY, OP_BN_BWD, OP_PREP, OP_TO_NCL, OP_L1, OP_MSE, OP_COLSUM,
  OP_ADAM, OP_PACK, OP_BN_FOLD, OP_ROT6D, OP_FILL, OP_PACK_MULTI, OP_BN_FOLD_MULTI, OP_FK, OP_DP_ADAM) = range(1, 20)
 
@@ -300,6 +301,9 @@ def bn_bwd(f: Dict):
         dgamma += sdyz
         dbeta += sdy
         dbias += dp.sum((0, 1))
+        if f.get("defer") == 2:          # the sums of dpre go to the op's own accumulators (region 2 of `partial`)
+            acc2 = f["partial"].view(torch.float64)[BWD_COPIES * G * C * 2:][: 16 * G * C].reshape(16, G, C)
+            acc2[0, g] += dp.sum((0, 1)).double()
     if f.get("first_pass_only") or f.get("defer"):   # defer: dpre only; b2h_colsum(bn_accum) finishes the op
         return
     if f.get("accum") is not None:
@@ -385,8 +389,14 @@ def mse(f: Dict):
 
 
 def colsum(f: Dict):
-    src = _rows2d(f["src"]).to(torch.float32)[: f["rows"], : f["C"]]
-    f["out"].copy_(src.double().sum(0).float())
+    if f.get("src") is None:            # b2h_colsum_t.src = NULL: the sums of dpre wait in the bn_bwd's own accumulators
+        C, G = f["C"], f["bn_groups"]
+        acc2 = f["partial"].view(torch.float64)[BWD_COPIES * G * C * 2:][: 16 * G * C].reshape(16, G, C)
+        f["out"].copy_(acc2.sum(0).sum(0).float())
+        acc2.zero_()
+    else:
+        src = _rows2d(f["src"]).to(torch.float32)[: f["rows"], : f["C"]]
+        f["out"].copy_(src.double().sum(0).float())
     if f.get("bn_accum") is not None:   # finishes a deferred BatchNorm backward (b2h_colsum_t.bn_accum)
         C = f["C"]
         acc = f["bn_accum"].reshape(-1, f["bn_groups"], C, 2)

@@ -278,11 +278,12 @@ def test_gan_step_vs_oracle_at_the_benched_shape(variant, rf, precision):
     gan_step_case(variant, rf, precision, 256, 64)
 
 
+@pytest.mark.parametrize("mode", ["0", "1", "2"])
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
-def test_gan_step_vs_oracle_with_the_opt_in_backward_variants(monkeypatch, precision):
-    """B2H_DEFER_BN / B2H_BWD_HELPERS (b2h_bn_bwd_t.defer + b2h_colsum_t.bn_accum, b2h_bn_bwd_t.first_pass_only): the
-    kernels behind the switches stay under test although the default schedule does not use them."""
-    monkeypatch.setenv("B2H_DEFER_BN", "1")
+def test_gan_step_vs_oracle_with_the_opt_in_backward_variants(monkeypatch, precision, mode):
+    """B2H_DEFER_BN = 0 / 1 / 2 (b2h_bn_bwd_t.defer + b2h_colsum_t.bn_accum; 2 is the default) with B2H_BWD_HELPERS
+    (b2h_bn_bwd_t.first_pass_only): every tail variant of the BatchNorm backward stays under test on the device."""
+    monkeypatch.setenv("B2H_DEFER_BN", mode)
     monkeypatch.setenv("B2H_BWD_HELPERS", "1")
     monkeypatch.setenv("B2H_NO_GRAD_ADD", "1")     # (bf16: otherwise the skip connections need no helper launches)
     gan_step_case("v1", False, precision, 32, 64)

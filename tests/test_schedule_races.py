@@ -241,16 +241,18 @@ def test_sequential_steps_have_no_unordered_conflicts(schedule_log, variant, rf,
     assert races == [], "\n".join(map(str, races[:20]))
 
 
+@pytest.mark.parametrize("mode", ["0", "1", "2"])
 @pytest.mark.parametrize("variant,rf", [("v1", False), ("v4", True)])
-def test_deferred_bn_backward_and_first_pass_helpers_have_no_unordered_conflicts(schedule_log, monkeypatch, variant, rf):
+def test_deferred_bn_backward_and_first_pass_helpers_have_no_unordered_conflicts(schedule_log, monkeypatch, variant, rf,
+                                                                                 mode):
     """Opt-in backward variants: the finishing column sums and the first-pass shares of the skip connections run on the
     weight-gradient streams; the producer's bn_bwd waits for its helpers' events."""
-    monkeypatch.setenv("B2H_DEFER_BN", "1")
+    monkeypatch.setenv("B2H_DEFER_BN", mode)
     monkeypatch.setenv("B2H_BWD_HELPERS", "1")
     monkeypatch.setenv("B2H_NO_GRAD_ADD", "1")     # (the default bf16 plans sum skip-connection gradients in the dgrad)
     tr = _trainer(variant, rf)
     assert any(r.f.get("first_pass_only") for r in tr.G_train.prog.recs if r.kind == L.OP_BN_BWD)
-    assert any(r.f.get("bn_accum") is not None for r in tr.G_train.prog.recs if r.kind == L.OP_COLSUM)
+    assert any(r.f.get("bn_accum") is not None for r in tr.G_train.prog.recs if r.kind == L.OP_COLSUM) == (mode != "0")
     tr.G_train.pack()
     tr.D_train.pack()
     tr._g_step_body()

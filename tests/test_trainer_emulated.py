@@ -173,17 +173,19 @@ def test_gan_steps_match_oracle(variant, rf, label_smooth):
         assert float(sd["state"][i]["step"]) == float(s["step"]) == 2.0
 
 
-def test_gan_steps_match_oracle_with_deferred_bn_backward(monkeypatch):
-    """The opt-in backward variants (b2h_bn_bwd_t.defer + b2h_colsum_t.bn_accum, b2h_bn_bwd_t.first_pass_only for the
-    skip connections) compute the same step."""
-    monkeypatch.setenv("B2H_DEFER_BN", "1")
+@pytest.mark.parametrize("mode", ["0", "1", "2"])
+def test_gan_steps_match_oracle_with_deferred_bn_backward(monkeypatch, mode):
+    """The opt-in backward variants (b2h_bn_bwd_t.defer = 1 / 2 + b2h_colsum_t.bn_accum, b2h_bn_bwd_t.first_pass_only
+    for the skip connections) compute the same step."""
+    monkeypatch.setenv("B2H_DEFER_BN", mode)
     monkeypatch.setenv("B2H_BWD_HELPERS", "1")
     tr = GanTrainer("v1", 36, 252, False, 4, 16, precision="fp32", device="cpu", drop_mode="mask")
     tags = [r.tag for r in tr.G_train.prog.recs]
-    assert "bwd_sums1.conv5.skip5" in tags and "bwd_sums1.conv6.skip4" in tags and "bn_fin.conv5" in tags
+    assert "bwd_sums1.conv5.skip5" in tags and "bwd_sums1.conv6.skip4" in tags
     rec = {r.tag: r for r in tr.G_train.prog.recs}
-    assert rec["bn_bwd.conv5"].f["defer"] == 1 and rec["bn_bwd.conv5"].f["_wait_tags"] == ["bwd_sums1.conv5.skip5"]
-    assert rec["bn_bwd.encoder"].f["defer"] == 1          # (pooled gradient source: sums from conv5's dgrad epilogue)
+    assert rec["bn_bwd.conv5"].f["defer"] == int(mode) and rec["bn_bwd.conv5"].f["_wait_tags"] == ["bwd_sums1.conv5.skip5"]
+    assert rec["bn_bwd.encoder"].f["defer"] == int(mode)  # (pooled gradient source: sums from conv5's dgrad epilogue)
+    assert ("bn_fin.conv5" in rec) == (mode != "0") and (mode == "0" or (rec["bn_fin.conv5"].f["src"] is None) == (mode == "2"))
     assert rec["dgrad.conv5"].f["bwd_sums"]["rowmap"] == L.ROW_POOL2
     test_gan_steps_match_oracle("v1", False, False)
 
