@@ -12,6 +12,8 @@ that: `run()` always goes through libb2h.so and raises if it is missing.
 from __future__ import annotations
 
 import ctypes as C
+import os
+import re
 from contextlib import contextmanager
 from typing import Dict, List, Optional, Tuple
 
@@ -19,9 +21,8 @@ import torch
 
 from . import _lib as L
 
-import os as _os
-import re as _re
-_SKIP_RE = _re.compile(_os.environ["B2H_DBG_SKIP_OPS"]) if _os.environ.get("B2H_DBG_SKIP_OPS") else None
+# timing experiment only (tools/skip_exp.sh): ops whose tag matches are left out of every replay -- results invalid
+_SKIP_RE = re.compile(os.environ["B2H_DBG_SKIP_OPS"]) if os.environ.get("B2H_DBG_SKIP_OPS") else None
 
 
 class OpRec:
